@@ -1,0 +1,92 @@
+"""ctypes binding of ``libhumanliff_b200.so`` (the C ABI declared in ``include/humanliff_b200.h``).
+
+There is no fallback: if the shared library is missing or a symbol is absent the import of the
+compute path fails loudly.  ``HL`` is the loaded library with argtypes set; ``check`` turns a
+negative status into a ``RuntimeError`` carrying ``hl_last_error()``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhumanliff_b200.so")
+
+c_int, c_i64, c_u64, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/humanliff_b200.h one to one
+SIGNATURES = {
+    "hl_version": (c_int, []),
+    "hl_last_error": (ctypes.c_char_p, []),
+    "hl_conv2d_uses_tensor_cores": (c_int, [c_int] * 9),
+    "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_nhwc_to_nchw": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
+    "hl_concat_add": (c_int, [c_p, c_int, c_int, c_p, c_int, c_p, c_int, c_int, c_p, c_int, c_i64, c_p]),
+    "hl_upsample2x": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_round_tf32": (c_int, [c_p, c_int, c_p, c_int, c_int, c_i64, c_p]),
+    "hl_timestep_embedding": (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    "hl_linear_small": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
+    "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
+    "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int,
+                            c_int, c_f, c_int, c_int, c_p]),
+    "hl_conv_cout_pad": (c_int, [c_int]),
+    "hl_conv2d": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_int, c_int, c_int, c_p]),
+    "hl_attention": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
+    "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
+    "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
+                               c_i64, c_int, c_p]),
+}
+
+# offsets of the packed renderer MLP (HL_MLP_* in the header)
+MLP_W0 = 0
+MLP_B0 = MLP_W0 + 27 * 128
+MLP_W1 = MLP_B0 + 128
+MLP_B1 = MLP_W1 + 128 * 128
+MLP_W2 = MLP_B1 + 128
+MLP_B2 = MLP_W2 + 155 * 128
+MLP_WA = MLP_B2 + 128
+MLP_BA = MLP_WA + 128
+MLP_WF = MLP_BA + 4
+MLP_BF = MLP_WF + 128 * 128
+MLP_WV = MLP_BF + 128
+MLP_BV = MLP_WV + 155 * 64
+MLP_WR = MLP_BV + 64
+MLP_BR = MLP_WR + 64 * 4
+MLP_PACK_FLOATS = MLP_BR + 4
+
+CONV_FORCE_SIMT = 1
+CONV_UPSAMPLE2X = 2
+
+_lib = None
+launch_count = 0   # number of C-ABI compute calls issued (each is >= 1 kernel launch)
+
+
+def load():
+    """Load the shared library (once) and set every prototype.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m humanliff_b200.build` "
+            "(there is no CPU / PyTorch fallback for the compute path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().hl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libhumanliff_b200 {what} failed ({status}): {msg}")
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point and raise on a non-zero status."""
+    global launch_count
+    launch_count += 1
+    check(getattr(load(), name)(*args), name)

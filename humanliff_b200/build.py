@@ -1,0 +1,78 @@
+"""Build recipe for ``libhumanliff_b200.so`` (sm_100a only, in-tree).
+
+``python -m humanliff_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without
+a GPU; the resulting ``.so`` lives next to this file so that it travels with the repo snapshot.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(HERE, "csrc", "build")
+LIB_PATH = os.path.join(HERE, "libhumanliff_b200.so")
+
+SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "render.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set $NVCC)")
+
+
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        with open(p, "rb") as f:
+            h.update(p.encode())
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "humanliff_b200.h"))
+    objs = []
+    relink = force or not os.path.exists(LIB_PATH)
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        op = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        stamp = op + ".sha"
+        dg = _digest([sp] + headers)
+        fresh = (not force and os.path.exists(op) and os.path.exists(stamp)
+                 and open(stamp).read() == dg)
+        if not fresh:
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", op]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True)
+            with open(stamp, "w") as f:
+                f.write(dg)
+            relink = True
+        objs.append(op)
+    if relink:
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,494 @@
+// Memory-bound kernels of the denoise path: layout changes, GroupNorm32 + SiLU + FiLM,
+// embeddings, DDPM posterior update.  All are HBM-bound streaming kernels: 128-bit accesses,
+// grids sized in multiples of the SM count.
+#include "common.cuh"
+
+#include <mutex>
+#include <string>
+
+// ------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void hl_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int hl_version(void) { return 100; }
+extern "C" const char *hl_last_error(void) { return g_err; }
+
+static int g_num_sms = 0;
+int hl_num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
+    int64_t g = (work_items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)hl_num_sms() * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW <-> NHWC.  One block transposes a [32 pixels x Cpad] tile through shared memory so that
+// both the NCHW side (contiguous pixels) and the NHWC side (contiguous channels) are coalesced.
+// ------------------------------------------------------------------------------------------
+__global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__restrict__ src2,
+                               float *__restrict__ dst, int C, int HW, int ld, int round_tf32,
+                               int64_t n_tiles, int tiles_per_img) {
+    __shared__ float tile[32][33];
+    for (int64_t tidx = blockIdx.x; tidx < n_tiles; tidx += gridDim.x) {
+        int b = (int)(tidx / tiles_per_img);
+        int p0 = (int)(tidx % tiles_per_img) * 32;
+        for (int c0 = 0; c0 < ld; c0 += 32) {
+            // load: threadIdx.x -> pixel, threadIdx.y -> channel
+            for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+                int c = c0 + cy, p = p0 + threadIdx.x;
+                float v = 0.f;
+                if (c < C && p < HW) {
+                    int64_t o = ((int64_t)b * C + c) * HW + p;
+                    v = src[o];
+                    if (src2) v += src2[o];
+                }
+                tile[cy][threadIdx.x] = v;
+            }
+            __syncthreads();
+            for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+                int c = c0 + threadIdx.x, p = p0 + py;
+                if (c < ld && p < HW) {
+                    float v = tile[threadIdx.x][py];
+                    dst[((int64_t)b * HW + p) * ld + c] = round_tf32 ? hl_rna_tf32(v) : v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int hl_nchw_to_nhwc(const float *src, const float *src2, float *dst, int B, int C,
+                               int HW, int ld, int round_tf32, void *stream) {
+    HL_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && ld >= C);
+    int tiles_per_img = hl_cdiv(HW, 32);
+    int64_t n_tiles = (int64_t)B * tiles_per_img;
+    dim3 blk(32, 8);
+    k_nchw_to_nhwc<<<grid_for(n_tiles, 1, 16), blk, 0, (cudaStream_t)stream>>>(
+        src, src2, dst, C, HW, ld, round_tf32, n_tiles, tiles_per_img);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+__global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, float *__restrict__ dst,
+                               int C, int HW, int64_t n_tiles, int tiles_per_img) {
+    __shared__ float tile[32][33];
+    for (int64_t tidx = blockIdx.x; tidx < n_tiles; tidx += gridDim.x) {
+        int b = (int)(tidx / tiles_per_img);
+        int p0 = (int)(tidx % tiles_per_img) * 32;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+                int c = c0 + threadIdx.x, p = p0 + py;
+                tile[py][threadIdx.x] = (c < C && p < HW) ? src[((int64_t)b * HW + p) * ld + c] : 0.f;
+            }
+            __syncthreads();
+            for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+                int c = c0 + cy, p = p0 + threadIdx.x;
+                if (c < C && p < HW) dst[((int64_t)b * C + c) * HW + p] = tile[threadIdx.x][cy];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW,
+                               void *stream) {
+    HL_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && ld >= C);
+    int tiles_per_img = hl_cdiv(HW, 32);
+    int64_t n_tiles = (int64_t)B * tiles_per_img;
+    dim3 blk(32, 8);
+    k_nhwc_to_nchw<<<grid_for(n_tiles, 1, 16), blk, 0, (cudaStream_t)stream>>>(
+        src, ld, dst, C, HW, n_tiles, tiles_per_img);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// concat (+ add), upsample, tf32 staging copy -- float4 over channels (all C are multiples of 4)
+// ------------------------------------------------------------------------------------------
+__global__ void k_concat_add(const float *__restrict__ a, int lda, int C1,
+                             const float *__restrict__ b, int ldb, const float *__restrict__ c,
+                             int ldc, int C2, float *__restrict__ dst, int ldd, int64_t npix) {
+    int q1 = C1 >> 2, q = (C1 + C2) >> 2;
+    int64_t total = npix * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / q;
+        int j = (int)(i - p * q);
+        float4 v;
+        if (j < q1) {
+            v = *reinterpret_cast<const float4 *>(a + p * lda + 4 * j);
+        } else {
+            int jj = j - q1;
+            v = *reinterpret_cast<const float4 *>(b + p * ldb + 4 * jj);
+            if (c) {
+                float4 w = *reinterpret_cast<const float4 *>(c + p * ldc + 4 * jj);
+                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+        }
+        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
+    }
+}
+
+extern "C" int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb,
+                             const float *c, int ldc, int C2, float *dst, int ldd, int64_t npix,
+                             void *stream) {
+    HL_CHECK_ARG(a && b && dst && npix > 0 && C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 &&
+                 ldb % 4 == 0 && ldd % 4 == 0 && (!c || ldc % 4 == 0) && ldd >= C1 + C2);
+    int64_t total = npix * ((C1 + C2) / 4);
+    k_concat_add<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, lda, C1, b, ldb, c,
+                                                                             ldc, C2, dst, ldd, npix);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+__global__ void k_upsample2x(const float *__restrict__ src, int lds, float *__restrict__ dst,
+                             int ldd, int H, int W, int C, int round_tf32, int64_t total) {
+    int q = C >> 2, W2 = 2 * W, H2 = 2 * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / q;
+        int j = (int)(i - p * q);
+        int ox = (int)(p % W2);
+        int64_t r = p / W2;
+        int oy = (int)(r % H2);
+        int64_t b = r / H2;
+        int64_t sp = (b * H + (oy >> 1)) * W + (ox >> 1);
+        float4 v = *reinterpret_cast<const float4 *>(src + sp * lds + 4 * j);
+        if (round_tf32) {
+            v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
+            v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
+        }
+        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
+    }
+}
+
+extern "C" int hl_upsample2x(const float *src, int lds, float *dst, int ldd, int B, int H, int W,
+                             int C, int round_tf32, void *stream) {
+    HL_CHECK_ARG(src && dst && B > 0 && H > 0 && W > 0 && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0);
+    int64_t total = (int64_t)B * 4 * H * W * (C / 4);
+    k_upsample2x<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, H, W,
+                                                                             C, round_tf32, total);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+__global__ void k_round_tf32(const float *__restrict__ src, int lds, float *__restrict__ dst,
+                             int ldd, int C, int64_t npix) {
+    int q = C >> 2;
+    int64_t total = npix * q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / q;
+        int j = (int)(i - p * q);
+        float4 v = *reinterpret_cast<const float4 *>(src + p * lds + 4 * j);
+        v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
+        v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
+        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
+    }
+}
+
+extern "C" int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int C, int64_t npix,
+                             void *stream) {
+    HL_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && npix > 0);
+    k_round_tf32<<<grid_for(npix * (C / 4), 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst,
+                                                                                      ldd, C, npix);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// embeddings
+// ------------------------------------------------------------------------------------------
+__global__ void k_timestep_embedding(const float *__restrict__ t, int B, int dim,
+                                     float *__restrict__ out) {
+    int half = dim / 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    int b = i / half, k = i % half;
+    // freqs = exp(-ln(1e4) * k / half) in fp32, exactly the reference's operation order
+    float f = expf(-9.210340371976184f * (float)k / (float)half);
+    float a = t[b] * f;
+    out[b * dim + k] = cosf(a);
+    out[b * dim + half + k] = sinf(a);
+    if ((dim & 1) && k == 0) out[b * dim + dim - 1] = 0.f;
+}
+
+extern "C" int hl_timestep_embedding(const float *t, int B, int dim, float *out, void *stream) {
+    HL_CHECK_ARG(t && out && B > 0 && dim >= 2);
+    int n = B * (dim / 2);
+    k_timestep_embedding<<<hl_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, B, dim, out);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// One warp per output feature; x (activated) is staged in shared memory in chunks of 8 rows.
+// The weight matrix is streamed exactly once per 8 batch rows (HBM-bound GEMV).
+#define LIN_ROWS 8
+__global__ void k_linear_small(const float *__restrict__ x, const float *__restrict__ W,
+                               const float *__restrict__ bias, float *__restrict__ y, int B, int in_f,
+                               int out_f, int silu_in, const float *__restrict__ add_table,
+                               const int64_t *__restrict__ add_idx) {
+    extern __shared__ float xs[];  // [LIN_ROWS][in_f]
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += LIN_ROWS) {
+        int nb = min(LIN_ROWS, B - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * in_f; i += blockDim.x) {
+            float v = x[(int64_t)b0 * in_f + i];
+            xs[i] = silu_in ? hl_silu(v) : v;
+        }
+        __syncthreads();
+        for (int o = blockIdx.x * nwarp + warp; o < out_f; o += gridDim.x * nwarp) {
+            float acc[LIN_ROWS];
+#pragma unroll
+            for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+            const float *wr = W + (int64_t)o * in_f;
+            for (int i = lane; i < in_f; i += 32) {
+                float w = wr[i];
+#pragma unroll
+                for (int r = 0; r < LIN_ROWS; ++r)
+                    if (r < nb) acc[r] = fmaf(w, xs[r * in_f + i], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < LIN_ROWS; ++r) {
+                if (r < nb) {
+                    float s = hl_warp_sum(acc[r]);
+                    if (lane == 0) {
+                        s += bias ? bias[o] : 0.f;
+                        if (add_table) s += add_table[add_idx[b0 + r] * out_f + o];
+                        y[(int64_t)(b0 + r) * out_f + o] = s;
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int hl_linear_small(const float *x, const float *W, const float *bias, float *y, int B,
+                               int in_f, int out_f, int silu_in, const float *add_table,
+                               const int64_t *add_idx, void *stream) {
+    HL_CHECK_ARG(x && W && y && B > 0 && in_f > 0 && out_f > 0);
+    HL_CHECK_ARG((add_table == nullptr) == (add_idx == nullptr));
+    size_t smem = (size_t)LIN_ROWS * in_f * sizeof(float);
+    HL_CHECK_ARG(smem <= 48 * 1024);
+    int warps = 8;
+    int grid = hl_cdiv(out_f, warps);
+    int cap = hl_num_sms() * 4;
+    if (grid > cap) grid = cap;
+    k_linear_small<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(x, W, bias, y, B, in_f, out_f,
+                                                                    silu_in, add_table, add_idx);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm32.  stats: each block owns a slab of pixels of one sample, each thread a fixed
+// channel quad (so loads are 128-bit and coalesced across the block), per-channel partials are
+// folded to groups in shared memory and added to the [B, G, 2] fp64 accumulators (fp64 atomics
+// make the result independent of arrival order to well below fp32 resolution).
+// ------------------------------------------------------------------------------------------
+#define GN_MAX_C 2048
+__global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int groups,
+                           int pix_per_block, double *__restrict__ sums) {
+    __shared__ float s_sum[GN_MAX_C];
+    __shared__ float s_sq[GN_MAX_C];
+    int b = blockIdx.y;
+    int q = C >> 2;
+    int lanes_p = blockDim.x / q;  // pixels processed concurrently (blockDim.x is a multiple of q)
+    int tq = threadIdx.x % q, tp = threadIdx.x / q;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+    __syncthreads();
+    int p0 = blockIdx.x * pix_per_block;
+    int p1 = min(HW, p0 + pix_per_block);
+    float4 s = make_float4(0, 0, 0, 0), ss = make_float4(0, 0, 0, 0);
+    if (tp < lanes_p) {
+        const float *base = x + (int64_t)b * HW * ldx + 4 * tq;
+        for (int p = p0 + tp; p < p1; p += lanes_p) {
+            float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)p * ldx);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y);
+            ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
+        }
+        atomicAdd(&s_sum[4 * tq + 0], s.x); atomicAdd(&s_sq[4 * tq + 0], ss.x);
+        atomicAdd(&s_sum[4 * tq + 1], s.y); atomicAdd(&s_sq[4 * tq + 1], ss.y);
+        atomicAdd(&s_sum[4 * tq + 2], s.z); atomicAdd(&s_sq[4 * tq + 2], ss.z);
+        atomicAdd(&s_sum[4 * tq + 3], s.w); atomicAdd(&s_sq[4 * tq + 3], ss.w);
+    }
+    __syncthreads();
+    int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double a = 0.0, a2 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)s_sum[c]; a2 += (double)s_sq[c]; }
+        atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 0], a);
+        atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 1], a2);
+    }
+}
+
+extern "C" int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, int groups, double *sums,
+                           void *stream) {
+    HL_CHECK_ARG(x && sums && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C && groups > 0);
+    HL_CHECK_ARG(C % groups == 0 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C);
+    int q = C / 4;
+    HL_CHECK_ARG(q <= 512);
+    int threads = (512 / q) * q;   // largest multiple of q not above 512
+    int lanes_p = threads / q;
+    // ~4 waves over the SMs, but at least 8 pixel rounds per block so the smem fold amortises
+    int64_t want_blocks = (int64_t)hl_num_sms() * 4 / B;
+    if (want_blocks < 1) want_blocks = 1;
+    int pix_per_block = hl_cdiv(HW, want_blocks);
+    int min_ppb = lanes_p * 8;
+    if (pix_per_block < min_ppb) pix_per_block = min_ppb;
+    dim3 grid(hl_cdiv(HW, pix_per_block), B);
+    HL_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * groups, (cudaStream_t)stream));
+    k_gn_stats<<<grid, threads, 0, (cudaStream_t)stream>>>(x, ldx, HW, C, groups, pix_per_block, sums);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// apply: y = act(x * A[b,c] + Bc[b,c]) where A, Bc fold mean/rstd/gamma/beta and the FiLM
+// scale/shift; A and Bc are built per block in shared memory from the fp64 sums.
+__global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *__restrict__ sums,
+                           const float *__restrict__ gamma, const float *__restrict__ beta,
+                           const float *__restrict__ film, int film_ld, float *__restrict__ y,
+                           int ldy, int HW, int C, int groups, float eps, int silu, int round_tf32,
+                           int pix_per_block) {
+    __shared__ float sA[GN_MAX_C];
+    __shared__ float sB[GN_MAX_C];
+    int b = blockIdx.y;
+    int cpg = C / groups;
+    double n = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        int g = c / cpg;
+        double m = sums[((int64_t)b * groups + g) * 2 + 0] / n;
+        double var = sums[((int64_t)b * groups + g) * 2 + 1] / n - m * m;
+        if (var < 0.0) var = 0.0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float mean = (float)m;
+        float ga = gamma[c] * rstd;
+        float be = beta[c] - mean * ga;
+        if (film) {
+            float sc = 1.0f + film[(int64_t)b * film_ld + c];
+            float sh = film[(int64_t)b * film_ld + C + c];
+            ga *= sc;
+            be = be * sc + sh;
+        }
+        sA[c] = ga;
+        sB[c] = be;
+    }
+    __syncthreads();
+    int q = C >> 2;
+    int p0 = blockIdx.x * pix_per_block;
+    int np = min(HW, p0 + pix_per_block) - p0;
+    int64_t total = (int64_t)np * q;
+    const float *xb = x + ((int64_t)b * HW + p0) * ldx;
+    float *yb = y + ((int64_t)b * HW + p0) * ldy;
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        int p = (int)(i / q);
+        int j = (int)(i - (int64_t)p * q);
+        float4 v = *reinterpret_cast<const float4 *>(xb + (int64_t)p * ldx + 4 * j);
+        float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
+        float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
+        v.x = fmaf(v.x, a.x, c.x); v.y = fmaf(v.y, a.y, c.y);
+        v.z = fmaf(v.z, a.z, c.z); v.w = fmaf(v.w, a.w, c.w);
+        if (silu) { v.x = hl_silu(v.x); v.y = hl_silu(v.y); v.z = hl_silu(v.z); v.w = hl_silu(v.w); }
+        if (round_tf32) {
+            v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
+            v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
+        }
+        *reinterpret_cast<float4 *>(yb + (int64_t)p * ldy + 4 * j) = v;
+    }
+}
+
+extern "C" int hl_gn_apply(const float *x, int ldx, const double *sums, const float *gamma,
+                           const float *beta, const float *film, int film_ld, float *y, int ldy,
+                           int B, int HW, int C, int groups, float eps, int silu, int round_tf32,
+                           void *stream) {
+    HL_CHECK_ARG(x && sums && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C);
+    HL_CHECK_ARG(C % groups == 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
+    int64_t want_blocks = (int64_t)hl_num_sms() * 8 / B;
+    if (want_blocks < 1) want_blocks = 1;
+    int pix_per_block = hl_cdiv(HW, want_blocks);
+    int min_ppb = hl_cdiv(256 * 4 * 4, C / 4);  // >= 4 float4 per thread
+    if (pix_per_block < min_ppb) pix_per_block = min_ppb;
+    dim3 grid(hl_cdiv(HW, pix_per_block), B);
+    k_gn_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, sums, gamma, beta, film, film_ld, y,
+                                                       ldy, HW, C, groups, eps, silu, round_tf32,
+                                                       pix_per_block);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// DDPM posterior update -- 3 streams in, 2 out, 20 B / element (gaussian_diffusion.py:293-387)
+// ------------------------------------------------------------------------------------------
+__global__ void k_ddpm_step(const float *__restrict__ x, const float *__restrict__ eps,
+                            const float *__restrict__ noise, const float *__restrict__ coef,
+                            const float *__restrict__ sigma, const int64_t *__restrict__ t,
+                            float *__restrict__ sample, float *__restrict__ x0out, int64_t n4,
+                            int clip) {
+    int b = blockIdx.y;
+    int64_t ti = t[b];
+    float c0 = coef[ti * 4 + 0], c1 = coef[ti * 4 + 1], c2 = coef[ti * 4 + 2], c3 = coef[ti * 4 + 3];
+    float sg = sigma[ti];
+    const float4 *x4 = reinterpret_cast<const float4 *>(x) + (int64_t)b * n4;
+    const float4 *e4 = reinterpret_cast<const float4 *>(eps) + (int64_t)b * n4;
+    const float4 *z4 = reinterpret_cast<const float4 *>(noise) + (int64_t)b * n4;
+    float4 *s4 = reinterpret_cast<float4 *>(sample) + (int64_t)b * n4;
+    float4 *p4 = x0out ? reinterpret_cast<float4 *>(x0out) + (int64_t)b * n4 : nullptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float4 xv = x4[i], ev = e4[i], zv = z4[i], x0, s;
+        // reference order: c0*x - c1*eps ; clamp ; c2*x0 + c3*x ; + sigma*noise (separate roundings)
+        x0.x = __fsub_rn(__fmul_rn(c0, xv.x), __fmul_rn(c1, ev.x));
+        x0.y = __fsub_rn(__fmul_rn(c0, xv.y), __fmul_rn(c1, ev.y));
+        x0.z = __fsub_rn(__fmul_rn(c0, xv.z), __fmul_rn(c1, ev.z));
+        x0.w = __fsub_rn(__fmul_rn(c0, xv.w), __fmul_rn(c1, ev.w));
+        if (clip) {
+            x0.x = fminf(fmaxf(x0.x, -1.f), 1.f); x0.y = fminf(fmaxf(x0.y, -1.f), 1.f);
+            x0.z = fminf(fmaxf(x0.z, -1.f), 1.f); x0.w = fminf(fmaxf(x0.w, -1.f), 1.f);
+        }
+        s.x = __fadd_rn(__fadd_rn(__fmul_rn(c2, x0.x), __fmul_rn(c3, xv.x)), __fmul_rn(sg, zv.x));
+        s.y = __fadd_rn(__fadd_rn(__fmul_rn(c2, x0.y), __fmul_rn(c3, xv.y)), __fmul_rn(sg, zv.y));
+        s.z = __fadd_rn(__fadd_rn(__fmul_rn(c2, x0.z), __fmul_rn(c3, xv.z)), __fmul_rn(sg, zv.z));
+        s.w = __fadd_rn(__fadd_rn(__fmul_rn(c2, x0.w), __fmul_rn(c3, xv.w)), __fmul_rn(sg, zv.w));
+        s4[i] = s;
+        if (p4) p4[i] = x0;
+    }
+}
+
+extern "C" int hl_ddpm_step(const float *x, const float *eps, const float *noise, const float *coef,
+                            const float *sigma, const int64_t *t, float *sample, float *pred_xstart,
+                            int B, int64_t n, int clip, void *stream) {
+    HL_CHECK_ARG(x && eps && noise && coef && sigma && t && sample && B > 0 && n > 0 && n % 4 == 0);
+    int64_t n4 = n / 4;
+    int gx = (int)((n4 + 255) / 256);
+    int cap = hl_num_sms() * 8 / B;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, B);
+    k_ddpm_step<<<grid, 256, 0, (cudaStream_t)stream>>>(x, eps, noise, coef, sigma, t, sample,
+                                                        pred_xstart, n4, clip);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}

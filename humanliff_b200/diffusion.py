@@ -1,0 +1,317 @@
+"""DDPM sampling driver -- drop-in for the sampling half of
+human_diffusion/improved_diffusion/gaussian_diffusion.py (:18-60 schedules, :101-169 tables,
+:232-326 p_mean_variance, :356-388 p_sample, :390-482 p_sample_loop[_progressive]) and
+respace.py (:7-60 space_timesteps, :63-122 SpacedDiffusion / _WrappedModel).
+
+Host side: float64 numpy tables exactly as the reference builds them.  Device side: the tables are
+uploaded ONCE as fp32 (the reference re-uploads a float64 table 8 times per step,
+gaussian_diffusion.py:860) and the whole posterior update
+    x0 = clip(c0 x - c1 eps);  mean = c2 x0 + c3 x;  sample = mean + [t != 0] sigma_t z
+is one fused kernel (``hl_ddpm_step``).  Training-only members (training_losses, _vb_terms_bpd,
+calc_bpd_loop) and the LEARNED / START_X / PREVIOUS_X variants are outside the hot path and raise.
+"""
+import enum
+import math
+
+import numpy as np
+import torch
+
+from ._lib import call
+
+
+class ModelMeanType(enum.Enum):
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelVarType(enum.Enum):
+    LEARNED = enum.auto()
+    FIXED_SMALL = enum.auto()
+    FIXED_LARGE = enum.auto()
+    LEARNED_RANGE = enum.auto()
+
+
+class LossType(enum.Enum):
+    MSE = enum.auto()
+    RESCALED_MSE = enum.auto()
+    KL = enum.auto()
+    RESCALED_KL = enum.auto()
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
+    betas = []
+    for i in range(num_diffusion_timesteps):
+        t1 = i / num_diffusion_timesteps
+        t2 = (i + 1) / num_diffusion_timesteps
+        betas.append(min(1 - alpha_bar(t2) / alpha_bar(t1), max_beta))
+    return np.array(betas)
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps):
+    """gaussian_diffusion.py:18-42."""
+    if schedule_name == "linear":
+        scale = 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    if schedule_name == "cosine":
+        return betas_for_alpha_bar(num_diffusion_timesteps,
+                                   lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2)
+    raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+
+def _extract_into_tensor(arr, timesteps, broadcast_shape):
+    """gaussian_diffusion.py:850-863 (kept for API parity; the fused path does not use it)."""
+    res = torch.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape)
+
+
+class GaussianDiffusion:
+    def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False):
+        self.model_mean_type = model_mean_type
+        self.model_var_type = model_var_type
+        self.loss_type = loss_type
+        self.rescale_timesteps = rescale_timesteps
+
+        betas = np.array(betas, dtype=np.float64)
+        self.betas = betas
+        assert len(betas.shape) == 1, "betas must be 1-D"
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.num_timesteps = int(betas.shape[0])
+
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(
+            np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = ((1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas)
+                                     / (1.0 - self.alphas_cumprod))
+        self._dev_tables = {}
+
+    # ------------------------------------------------------------------ tables
+    def _variance_tables(self):
+        """(variance, log_variance) float64 arrays of the configured fixed-variance type (:278-291)."""
+        if self.model_var_type == ModelVarType.FIXED_LARGE:
+            v = np.append(self.posterior_variance[1], self.betas[1:])
+            return v, np.log(v)
+        if self.model_var_type == ModelVarType.FIXED_SMALL:
+            return self.posterior_variance, self.posterior_log_variance_clipped
+        raise NotImplementedError("learned variance (learn_sigma=True) is outside the sampling hot path")
+
+    def _tables(self, device):
+        key = str(device)
+        tb = self._dev_tables.get(key)
+        if tb is None:
+            if self.model_mean_type != ModelMeanType.EPSILON:
+                raise NotImplementedError("only epsilon-prediction (predict_xstart=False) is built")
+            var, logvar = self._variance_tables()
+            # cast to fp32 AFTER the float64 table arithmetic, as `_extract_into_tensor(...).float()` does
+            coef = np.stack([self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                             self.posterior_mean_coef1, self.posterior_mean_coef2], axis=1)
+            coef_t = torch.from_numpy(coef).float().contiguous().to(device)
+            logvar_t = torch.from_numpy(logvar).float()
+            sigma = torch.exp(0.5 * logvar_t)
+            sigma[0] = 0.0          # nonzero_mask = (t != 0)
+            tb = {"coef": coef_t, "sigma": sigma.contiguous().to(device),
+                  "var": torch.from_numpy(var).float().to(device), "logvar": logvar_t.to(device)}
+            self._dev_tables[key] = tb
+        return tb
+
+    def _scale_timesteps(self, t):
+        if self.rescale_timesteps:
+            return t.float() * (1000.0 / self.num_timesteps)
+        return t
+
+    # ------------------------------------------------------------------ sampling
+    def _fused_step(self, x, eps, noise, t, clip_denoised, want_x0=True):
+        tb = self._tables(x.device)
+        B = x.shape[0]
+        n = x[0].numel()
+        x = x.contiguous()
+        eps = eps.contiguous()
+        noise = noise.contiguous()
+        sample = torch.empty_like(x)
+        x0 = torch.empty_like(x) if want_x0 else None
+        t64 = t if t.dtype == torch.int64 else t.long()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        call("hl_ddpm_step", x.data_ptr(), eps.data_ptr(), noise.data_ptr(), tb["coef"].data_ptr(),
+             tb["sigma"].data_ptr(), t64.data_ptr(), sample.data_ptr(),
+             x0.data_ptr() if x0 is not None else None, B, n, 1 if clip_denoised else 0, stream)
+        return sample, x0
+
+    def p_mean_variance(self, model, x, t, x_cond=None, clip_denoised=True, denoised_fn=None,
+                        model_kwargs=None):
+        """gaussian_diffusion.py:232-326 -- NB argument order (model, x, t, x_cond=None, ...)."""
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
+        if model_kwargs is None:
+            model_kwargs = {}
+        B = x.shape[0]
+        assert t.shape == (B,)
+        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
+        tb = self._tables(x.device)
+        zeros = torch.zeros_like(x)
+        mean, x0 = self._fused_step(x, eps, zeros, t, clip_denoised)
+        shape = [B] + [1] * (x.dim() - 1)
+        return {"mean": mean,
+                "variance": tb["var"][t].view(shape).expand(x.shape),
+                "log_variance": tb["logvar"][t].view(shape).expand(x.shape),
+                "pred_xstart": x0, "eps": eps}
+
+    def p_sample(self, model, x, x_cond, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
+                 noise=None):
+        """gaussian_diffusion.py:356-388 -- NB argument order (model, x, x_cond, t, ...).
+        ``noise`` (extension): inject the per-step Gaussian instead of drawing ``randn_like(x)``."""
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
+        if model_kwargs is None:
+            model_kwargs = {}
+        assert t.shape == (x.shape[0],)
+        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
+        if noise is None:
+            noise = torch.randn_like(x)
+        sample, x0 = self._fused_step(x, eps, noise, t, clip_denoised)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def p_sample_loop(self, model, shape, x_cond=None, noise=None, clip_denoised=True, denoised_fn=None,
+                      model_kwargs=None, device=None, progress=False, step_noise=None):
+        final = None
+        for sample in self.p_sample_loop_progressive(model, shape, x_cond=x_cond, noise=noise,
+                                                     clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                                     model_kwargs=model_kwargs, device=device,
+                                                     progress=progress, step_noise=step_noise):
+            final = sample
+        return final["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, x_cond=None, noise=None, clip_denoised=True,
+                                  denoised_fn=None, model_kwargs=None, device=None, progress=False,
+                                  step_noise=None):
+        """gaussian_diffusion.py:434-482.  ``step_noise`` (extension): callable ``i -> tensor`` that
+        supplies the Gaussian of step i (parity tests inject the oracle's noise)."""
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else torch.randn(*shape, device=device)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        t = torch.empty(shape[0], device=device, dtype=torch.int64)
+        for i in indices:
+            t.fill_(i)
+            with torch.no_grad():
+                z = step_noise(i) if step_noise is not None else None
+                out = self.p_sample(model, img, x_cond, t, clip_denoised=clip_denoised,
+                                    denoised_fn=denoised_fn, model_kwargs=model_kwargs, noise=z)
+                yield out
+                img = out["sample"]
+
+    # ------------------------------------------------------------------ outside the hot path
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("training is outside the B200 inference hot path (SURVEY.md 8)")
+
+    def ddim_sample(self, *a, **k):
+        raise NotImplementedError("DDIM sampling is a 'next' row (SURVEY.md 8(f) rank 2)")
+
+    ddim_sample_loop = ddim_sample
+
+
+def space_timesteps(num_timesteps, section_counts):
+    """Which timesteps of the base process to keep (respace.py:7-60).
+
+    ``section_counts`` is a list (or comma-separated string) of per-section step counts: the base
+    range is cut into ``len(section_counts)`` near-equal sections and section k contributes
+    ``section_counts[k]`` steps spread evenly from its first to its last index.  ``"ddimN"`` asks
+    for the integer stride that yields exactly N steps."""
+    if isinstance(section_counts, str) and section_counts.startswith("ddim"):
+        want = int(section_counts[4:])
+        for stride in range(1, num_timesteps):
+            kept = range(0, num_timesteps, stride)
+            if len(kept) == want:
+                return set(kept)
+        raise ValueError(f"cannot create exactly {num_timesteps} steps with an integer stride")
+    if isinstance(section_counts, str):
+        section_counts = [int(tok) for tok in section_counts.split(",")]
+    n_sec = len(section_counts)
+    base, rem = divmod(num_timesteps, n_sec)
+    kept, first = [], 0
+    for k, count in enumerate(section_counts):
+        length = base + (1 if k < rem else 0)
+        if length < count:
+            raise ValueError(f"cannot divide section of {length} steps into {count}")
+        stride = (length - 1) / (count - 1) if count > 1 else 1
+        pos = 0.0
+        for _ in range(count):
+            kept.append(first + round(pos))
+            pos += stride
+        first += length
+    return set(kept)
+
+
+class SpacedDiffusion(GaussianDiffusion):
+    """respace.py:63-107: keep a subset of the base process' timesteps; betas are re-derived from
+    the kept cumulative alphas and the model is called with the ORIGINAL timestep indices."""
+
+    def __init__(self, use_timesteps, **kwargs):
+        self.use_timesteps = set(use_timesteps)
+        self.timestep_map = []
+        self.original_num_steps = len(kwargs["betas"])
+        base = GaussianDiffusion(**kwargs)
+        last_alpha_cumprod = 1.0
+        new_betas = []
+        for i, alpha_cumprod in enumerate(base.alphas_cumprod):
+            if i in self.use_timesteps:
+                new_betas.append(1 - alpha_cumprod / last_alpha_cumprod)
+                last_alpha_cumprod = alpha_cumprod
+                self.timestep_map.append(i)
+        kwargs["betas"] = np.array(new_betas)
+        super().__init__(**kwargs)
+        self._map_dev = {}
+
+    def p_mean_variance(self, model, *args, **kwargs):
+        return super().p_mean_variance(self._wrap_model(model), *args, **kwargs)
+
+    def p_sample(self, model, *args, **kwargs):
+        return super().p_sample(self._wrap_model(model), *args, **kwargs)
+
+    def _wrap_model(self, model):
+        if isinstance(model, _WrappedModel):
+            return model
+        return _WrappedModel(model, self, self.rescale_timesteps, self.original_num_steps)
+
+    def _scale_timesteps(self, t):
+        return t   # done by the wrapped model (respace.py:105-107)
+
+    def _map_tensor(self, device):
+        key = str(device)
+        m = self._map_dev.get(key)
+        if m is None:
+            m = torch.tensor(self.timestep_map, device=device, dtype=torch.int64)
+            self._map_dev[key] = m
+        return m
+
+
+class _WrappedModel:
+    """respace.py:110-122, with the timestep map resident on the device."""
+
+    def __init__(self, model, diffusion, rescale_timesteps, original_num_steps):
+        self.model = model
+        self.diffusion = diffusion
+        self.timestep_map = diffusion.timestep_map
+        self.rescale_timesteps = rescale_timesteps
+        self.original_num_steps = original_num_steps
+
+    def __call__(self, x, ts, x_cond, **kwargs):
+        new_ts = self.diffusion._map_tensor(ts.device)[ts]
+        if self.rescale_timesteps:
+            new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
+        return self.model(x, new_ts, x_cond, **kwargs)

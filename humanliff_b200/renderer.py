@@ -1,0 +1,244 @@
+"""Tri-plane NeRF renderer -- drop-in for human_diffusion/NeRF/renderer.py:14-50,234-281 (``Renderer``),
+recon_NeRF/lib/renderer.py:13-48,244-295 (``ReconRenderer``: owns ``tri_planes``) and the script-level
+``render()`` helper (recon_NeRF/run_nerf_batch.py:29-67 == human_diffusion/scripts/
+triplane_sample_layered.py:250-288).
+
+State-dict keys match the reference (pts_linears.{0,1,2}, feature_linear, alpha_linear, views_linear,
+rgb_linear, view_enc._freqs/_phases [, tri_planes]); the whole coarse -> resample -> fine -> composite
+chain of one ray batch is ONE kernel launch (``hl_render_rays``), so the reference's 16-chunk loop,
+its [4.2 M x 155] temporaries and ``empty_cache()`` calls disappear.  Only the inference envelope is
+built: ``use_canonical_space=False``, ``n_samples == n_importance == 128``, ``perturb == 0``,
+``white_bkgd=False`` (the reference's white_bkgd branch is shape-broken).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call
+
+N_SAMPLES = 128
+
+
+def _linear_params(mod, name, fin, fout):
+    node = nn.Module()
+    node.weight = nn.Parameter(torch.empty(fout, fin), requires_grad=False)
+    node.bias = nn.Parameter(torch.empty(fout), requires_grad=False)
+    nn.init.kaiming_uniform_(node.weight, a=math.sqrt(5))
+    bound = 1 / math.sqrt(fin)
+    nn.init.uniform_(node.bias, -bound, bound)
+    return node
+
+
+class _ViewEnc(nn.Module):
+    """Buffers of lib/fields.py:45-67 (kept so that reference checkpoints load with strict=True)."""
+
+    def __init__(self, num_freqs=4):
+        super().__init__()
+        freqs = 2.0 ** torch.linspace(0.0, num_freqs - 1, steps=num_freqs)
+        self.register_buffer("_freqs", torch.repeat_interleave(freqs, 2).view(1, -1, 1))
+        phases = torch.zeros(2 * num_freqs)
+        phases[1::2] = math.pi * 0.5
+        self.register_buffer("_phases", phases.view(1, -1, 1))
+
+
+class Renderer(nn.Module):
+    """HD variant: ``render(tp_input, world_pts, z_vals, rays_o, rays_d, near, far, tri_planes, ...)``."""
+
+    clamp_depth = True   # human_diffusion/NeRF/renderer.py:273-274
+
+    def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18,
+                 smpl_type=None, test=False):
+        super().__init__()
+        if use_canonical_space:
+            raise NotImplementedError("use_canonical_space=True (TightCap SMPL deformation) is a 'next' row")
+        if triplane_ch != 27:
+            raise NotImplementedError("the fused kernel is built for the 27-channel nine-plane layout")
+        self.use_canonical_space = use_canonical_space
+        self.num_instances = num_instances
+        self.triplane_dim = triplane_dim
+        self.triplane_ch = triplane_ch
+        self.test = test
+        self.view_enc = _ViewEnc(4)
+        d_in, d_hidden = triplane_ch, 128
+        self.skips = [1.0]
+        self.pts_linears = nn.ModuleList([_linear_params(self, "0", d_in, d_hidden),
+                                          _linear_params(self, "1", d_hidden, d_hidden),
+                                          _linear_params(self, "2", d_hidden + d_in, d_hidden)])
+        self.feature_linear = _linear_params(self, "f", d_hidden, d_hidden)
+        self.alpha_linear = _linear_params(self, "a", d_hidden, 1)
+        self.views_linear = _linear_params(self, "v", d_hidden + 27, d_hidden // 2)
+        self.rgb_linear = _linear_params(self, "r", d_hidden // 2, 3)
+        self._pack_key = None
+        self._mlp = None
+        self._tex_cache = {}
+
+    # ------------------------------------------------------------------ packing
+    def _mlp_params(self):
+        return [self.pts_linears[0], self.pts_linears[1], self.pts_linears[2], self.alpha_linear,
+                self.feature_linear, self.views_linear, self.rgb_linear]
+
+    def _pack(self, device):
+        ps = [p for m in self._mlp_params() for p in (m.weight, m.bias)]
+        key = (str(device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        if key == self._pack_key:
+            return self._mlp
+        L = _lib
+        buf = torch.zeros(L.MLP_PACK_FLOATS, dtype=torch.float32)
+
+        def put(off, t):
+            t = t.detach().float().cpu().contiguous().view(-1)
+            buf[off:off + t.numel()] = t
+
+        put(L.MLP_W0, self.pts_linears[0].weight.t()); put(L.MLP_B0, self.pts_linears[0].bias)
+        put(L.MLP_W1, self.pts_linears[1].weight.t()); put(L.MLP_B1, self.pts_linears[1].bias)
+        put(L.MLP_W2, self.pts_linears[2].weight.t()); put(L.MLP_B2, self.pts_linears[2].bias)
+        put(L.MLP_WA, self.alpha_linear.weight); put(L.MLP_BA, self.alpha_linear.bias)
+        put(L.MLP_WF, self.feature_linear.weight.t()); put(L.MLP_BF, self.feature_linear.bias)
+        put(L.MLP_WV, self.views_linear.weight.t()); put(L.MLP_BV, self.views_linear.bias)
+        wr = torch.zeros(64, 4)
+        wr[:, :3] = self.rgb_linear.weight.detach().float().cpu().t()
+        put(L.MLP_WR, wr)
+        put(L.MLP_BR, self.rgb_linear.bias)
+        self._mlp = buf.to(device)
+        self._pack_key = key
+        return self._mlp
+
+    def _texels(self, planes):
+        """[3, 9, R, R] device tensor -> texel-major float4 array (cached per tensor version)."""
+        key = (planes.data_ptr(), planes._version, tuple(planes.shape))
+        hit = self._tex_cache.get("k")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        R = planes.shape[-1]
+        tex = torch.empty(9 * R * R * 4, device=planes.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(planes.device).cuda_stream
+        call("hl_triplane_to_texels", planes.data_ptr(), tex.data_ptr(), R, stream)
+        self._tex_cache["k"] = (key, tex)
+        return tex
+
+    # ------------------------------------------------------------------ the fused launch
+    @torch.no_grad()
+    def render_rays(self, tri_planes, bounds, rays_o, rays_d, near, far, z_coarse=None, u=None, seed=0):
+        """One tri-plane ([3, 9, R, R]), one bounds box ([2, 3]), N rays -> (rgb [N,3], acc [N], depth [N])."""
+        if not rays_o.is_cuda:
+            raise RuntimeError("humanliff_b200.Renderer runs on CUDA (sm_100a) only -- no CPU fallback")
+        dev = rays_o.device
+        with torch.cuda.device(dev):
+            mlp = self._pack(dev)
+            planes = tri_planes.detach().to(dev, torch.float32).contiguous()
+            assert planes.shape[0] == 3 and planes.shape[1] == 9 and planes.shape[2] == planes.shape[3]
+            tex = self._texels(planes)
+            n = rays_o.shape[0]
+            f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+            rays_o, rays_d, near, far = f(rays_o), f(rays_d), f(near).view(-1), f(far).view(-1)
+            assert rays_d.shape == (n, 3) and near.numel() == n and far.numel() == n
+            if z_coarse is not None:
+                z_coarse = f(z_coarse)
+                assert z_coarse.shape == (n, N_SAMPLES)
+            if u is not None:
+                u = f(u)
+                assert u.shape == (n, N_SAMPLES)
+            b = [float(v) for v in torch.as_tensor(bounds, dtype=torch.float32).reshape(-1).tolist()]
+            assert len(b) == 6
+            import ctypes
+            barr = (ctypes.c_float * 6)(*b)
+            rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+            acc = torch.empty(n, device=dev, dtype=torch.float32)
+            depth = torch.empty(n, device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), rays_o.data_ptr(),
+                 rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                 z_coarse.data_ptr() if z_coarse is not None else None,
+                 u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1),
+                 ctypes.cast(barr, ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
+                 1 if self.clamp_depth else 0, stream)
+        return rgb, acc, depth
+
+    # ------------------------------------------------------------------ reference-shaped entry point
+    def _render_batched(self, tp_input, z_vals, rays_o, rays_d, near, far, tri_planes, n_importance,
+                        white_bkgd, u=None):
+        if white_bkgd:
+            raise NotImplementedError("white_bkgd=True is shape-broken in the reference and not built")
+        bs, n_rays, n_samples = z_vals.shape
+        if n_importance != N_SAMPLES or n_samples != N_SAMPLES:
+            raise NotImplementedError("the fused kernel implements n_samples == n_importance == 128")
+        wb = tp_input["world_bounds"]
+        outs = {"rgb_map": [], "acc_map": [], "normal_map": [], "depth_map": []}
+        for b in range(bs):
+            ub = None if u is None else u[b * n_rays:(b + 1) * n_rays]
+            rgb, acc, depth = self.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b],
+                                               rays_o[b], rays_d[b], near[b].reshape(-1),
+                                               far[b].reshape(-1), z_coarse=z_vals[b], u=ub,
+                                               seed=torch.initial_seed() + b)
+            outs["rgb_map"].append(rgb)
+            outs["acc_map"].append(acc)
+            outs["normal_map"].append(rgb)     # normal_map aliases rgb_map (renderer.py:237)
+            outs["depth_map"].append(depth)
+        return {k: torch.stack(v, 0) for k, v in outs.items()}
+
+    def render(self, tp_input, world_pts, z_vals, rays_o, rays_d, near, far, tri_planes, n_importance=128,
+               white_bkgd=False, u=None):
+        """human_diffusion/NeRF/renderer.py:234-281.  ``world_pts`` is accepted for signature parity and
+        ignored (the kernel recomputes o + d*z).  ``u`` (extension): the [bs*n_rays, 128] uniforms of
+        ``sample_pdf``; None -> in-kernel counter-based generator."""
+        return self._render_batched(tp_input, z_vals, rays_o, rays_d, near, far, tri_planes, n_importance,
+                                    white_bkgd, u)
+
+
+class ReconRenderer(Renderer):
+    """recon_NeRF variant: owns ``tri_planes [num_instances, 4, 3, ch/3, dim, dim]`` and selects
+    ``tri_planes[instance_idx, cloth_layer_index]`` (recon_NeRF/lib/renderer.py:26-27,247-251); no depth clamp."""
+
+    clamp_depth = False
+
+    def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18, test=False):
+        super().__init__(use_canonical_space, num_instances, triplane_dim, triplane_ch, None, test)
+        self.tri_planes = nn.Parameter(torch.empty(num_instances, 4, 3, triplane_ch // 3, triplane_dim,
+                                                   triplane_dim).normal_(0, 0.1), requires_grad=False)
+
+    @property
+    def module(self):
+        return self   # scripts call renderer.module.render (DDP wrapper in the reference)
+
+    def render(self, tp_input, world_pts, z_vals, rays_o, rays_d, near, far, n_importance=128,
+               white_bkgd=False, u=None):
+        tri = self.tri_planes[tp_input["instance_idx"], tp_input["cloth_layer_index"]]
+        return self._render_batched(tp_input, z_vals, rays_o, rays_d, near, far, tri, n_importance,
+                                    white_bkgd, u)
+
+
+@torch.no_grad()
+def render(chunk=1024 * 32, rays_o=None, rays_d=None, near=0., far=1., tri_planes=None, tp_input=None,
+           renderer=None, n_samples=128, perturb=0., n_importance=0, white_bkgd=False, u=None):
+    """Script-level helper (triplane_sample_layered.py:250-288 / run_nerf_batch.py:29-67).
+
+    Returns ``[rgb, acc, normal, depth]`` like the reference.  ``chunk`` is accepted and ignored: the
+    fused kernel keeps every per-point intermediate on chip, so the whole image is one launch.  The
+    coarse depths ``near*(1-t) + far*t`` are generated inside the kernel."""
+    if perturb > 0.:
+        raise NotImplementedError("perturb > 0 (training-time stratified jitter) is outside the inference path")
+    if white_bkgd:
+        raise NotImplementedError("white_bkgd=True is shape-broken in the reference and not built")
+    if n_importance != N_SAMPLES or n_samples != N_SAMPLES:
+        raise NotImplementedError("the fused kernel implements n_samples == n_importance == 128")
+    r = renderer.module if hasattr(renderer, "module") and not isinstance(renderer, Renderer) else renderer
+    bs = rays_d.shape[0]
+    rays_o = rays_o.reshape(bs, -1, 3)
+    rays_d = rays_d.reshape(bs, -1, 3)
+    n = rays_o.shape[1]
+    near = near.reshape(bs, -1)
+    far = far.reshape(bs, -1)
+    if tri_planes is None:
+        tri_planes = r.tri_planes[tp_input["instance_idx"], tp_input["cloth_layer_index"]]
+    wb = tp_input["world_bounds"]
+    rgbs, accs, deps = [], [], []
+    for b in range(bs):
+        ub = None if u is None else u[b * n:(b + 1) * n]
+        rgb, acc, dep = r.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b], rays_o[b],
+                                      rays_d[b], near[b], far[b], z_coarse=None, u=ub,
+                                      seed=torch.initial_seed() + b)
+        rgbs.append(rgb); accs.append(acc); deps.append(dep)
+    rgb = torch.stack(rgbs, 0)
+    return [rgb, torch.stack(accs, 0), rgb, torch.stack(deps, 0)]

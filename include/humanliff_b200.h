@@ -1,0 +1,157 @@
+/*
+ * humanliff_b200.h -- C ABI of libhumanliff_b200.so (sm_100a only).
+ *
+ * The reference (skhu101/HumanLiff) has no FFI / operator layer: every FLOP of
+ * its two hot paths is a PyTorch ATen call.  Each entry point below names the
+ * reference call site(s) (file:line under /root/reference) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless it
+ *     is documented as host memory; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it,
+ *     nothing synchronises, nothing allocates (safe under CUDA-graph capture);
+ *   - return value 0 = ok, negative = HL_E_*; hl_last_error() gives the text;
+ *   - activations are NHWC fp32 ("pixel-major"): element (b, y, x, c) lives at
+ *     ptr[((b*H + y)*W + x)*ld + c], `ld` (floats) >= C is the pixel pitch so a
+ *     tensor may be a channel slice of a wider (concat) buffer.
+ */
+#ifndef HUMANLIFF_B200_H
+#define HUMANLIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HL_OK 0
+#define HL_E_INVALID (-1)   /* bad argument / unsupported shape            */
+#define HL_E_CUDA (-2)      /* a CUDA runtime / driver call failed          */
+#define HL_E_UNSUPPORTED (-3)
+
+/* hl_conv2d flags */
+#define HL_CONV_FORCE_SIMT 1   /* use the fp32 CUDA-core kernel even where the tcgen05 path applies */
+#define HL_CONV_UPSAMPLE2X 2   /* input is read through a nearest x2 upsample (unet.py:77)          */
+
+int hl_version(void);
+const char *hl_last_error(void);
+/* 1 if the tcgen05 (tensor-core) kernel would be used for this conv shape. */
+int hl_conv2d_uses_tensor_cores(int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                int ldx, int flags);
+
+/* ---- layout / elementwise ------------------------------------------------------------------ */
+
+/* NCHW -> NHWC with zero channel padding up to ld; optional second addend (h_cond = x + x_cond,
+ * unet.py:596); optional TF32 round-to-nearest of the result (operand of the stem conv).        */
+int hl_nchw_to_nhwc(const float *src, const float *src2 /*nullable*/, float *dst, int B, int C,
+                    int HW, int ld, int round_tf32, void *stream);
+/* NHWC (pitch ld) -> NCHW.                                                                      */
+int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW, void *stream);
+/* dst[:, 0:C1] = a ; dst[:, C1:C1+C2] = b (+ c)   -- th.cat([h, hs.pop()+hs_cond.pop()], 1),
+ * unet.py:606.  Any of the three sources may alias a slice of another buffer via its pitch.     */
+int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb, const float *c /*nullable*/,
+                  int ldc, int C2, float *dst, int ldd, int64_t npix, void *stream);
+/* nearest x2 upsample, F.interpolate(scale_factor=2, mode="nearest"), unet.py:77               */
+int hl_upsample2x(const float *src, int lds, float *dst, int ldd, int B, int H, int W, int C,
+                  int round_tf32, void *stream);
+/* dst = rna_tf32(src) (operand staging for raw residual-stream inputs of 1x1 convs)             */
+int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int C, int64_t npix, void *stream);
+
+/* ---- embeddings (nn.py:103-121, unet.py:366-373,564,584-586,151-157,200) --------------------- */
+
+/* out[b, 0:half] = cos(t_b f_k), out[b, half:] = sin(t_b f_k), f_k = exp(-ln(1e4) k / half)     */
+int hl_timestep_embedding(const float *t, int B, int dim, float *out, void *stream);
+/* y[b, o] = bias[o] + sum_i W[o, i] * act(x[b, i]) (+ add[idx[b], o]);  act = SiLU if silu_in.
+ * W is row-major [out, in] exactly as nn.Linear stores it.  Used for time_embed, and once per
+ * step for ALL ResBlock emb_layers stacked into one [sum 2Cout, 768] matrix.                    */
+int hl_linear_small(const float *x, const float *W, const float *bias, float *y, int B, int in_f,
+                    int out_f, int silu_in, const float *add_table /*nullable*/,
+                    const int64_t *add_idx /*nullable*/, void *stream);
+
+/* ---- GroupNorm32 + SiLU + FiLM (nn.py:12-19,93-100; unet.py:204-206) ------------------------- */
+
+/* sums[b, g, {0,1}] (double) = sum / sum of squares over group g of sample b.  Zeroes `sums`.   */
+int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, int groups, double *sums,
+                void *stream);
+/* y = act( GN(x; gamma, beta, eps) * (1 + scale_b) + shift_b ), scale/shift optional
+ * (film + b*film_ld points at [scale(C) | shift(C)] of sample b); act = SiLU if silu;
+ * result optionally rounded to TF32 (it is the next conv's A operand).                          */
+int hl_gn_apply(const float *x, int ldx, const double *sums, const float *gamma, const float *beta,
+                const float *film /*nullable*/, int film_ld, float *y, int ldy, int B, int HW, int C,
+                int groups, float eps, int silu, int round_tf32, void *stream);
+
+/* ---- convolution / GEMM (unet.py:68,100,149,164-184,237-239,378,474,481-518) ------------------ */
+
+/* y[b,oy,ox,co] = bias[co] + sum_{ky,kx,ci} x[b, oy*stride+ky-pad, ox*stride+kx-pad, ci] *
+ *                 w[co,ci,ky,kx]  (+ residual[b,oy,ox,co]),   zero padding pad = ksize/2.
+ * wpk is the packed weight: [ksize*ksize][Cout_pad][Cin_pad] fp32, Cin_pad = Cin (the caller pads
+ * the activation buffer's channel count to a multiple of 32 for the tensor-core path),
+ * Cout_pad = hl_conv_cout_pad(Cout).  ksize in {1,3}; stride in {1,2}.  A 1x1 conv over
+ * [B*T, C] rows is the Conv1d / GEMM of the attention block.                                    */
+int hl_conv_cout_pad(int Cout);
+int hl_conv2d(const float *x, int ldx, const float *wpk, const float *bias,
+              const float *residual /*nullable*/, int ldr, float *y, int ldy, int B, int H, int W,
+              int Cin, int Cout, int ksize, int stride, int flags, void *stream);
+
+/* ---- attention (unet.py:255-274) ------------------------------------------------------------ */
+
+/* qkv: [B, T, 3C] rows (pitch ldq) with channel order [head][q(ch) k(ch) v(ch)];
+ * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c]                          */
+int hl_attention(const float *qkv, int ldq, float *out, int ldo, int B, int T, int C, int heads,
+                 int round_tf32, void *stream);
+
+/* ---- DDPM posterior step (gaussian_diffusion.py:293-314,328-333,383-387) ---------------------- */
+
+/* coef: device [T, 4] fp32 = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+ * posterior_mean_coef1, posterior_mean_coef2}; sigma: device [T] fp32 = exp(0.5*log_var) with the
+ * t == 0 entry already zeroed (nonzero_mask).  t: device int64 [B].  n = C*H*W per sample.
+ * x0 = clip(c0 x - c1 eps);  mean = c2 x0 + c3 x;  sample = mean + sigma_t * noise               */
+int hl_ddpm_step(const float *x, const float *eps, const float *noise, const float *coef,
+                 const float *sigma, const int64_t *t, float *sample, float *pred_xstart, int B,
+                 int64_t n, int clip, void *stream);
+
+/* ---- tri-plane volume renderer (recon_NeRF/lib/renderer.py:142-295,504-581;
+ *      recon_NeRF/run_nerf_batch.py:29-67; human_diffusion/NeRF/renderer.py:234-281) ----------- */
+
+/* Packed decoder MLP (one device buffer of HL_MLP_PACK_FLOATS floats).  Every matrix is stored
+ * TRANSPOSED w.r.t. nn.Linear ([in][out], "k-major") so a thread's 8 output weights are contiguous. */
+#define HL_MLP_W0 0                         /* pts_linears.0.weight^T  [27][128]                    */
+#define HL_MLP_B0 (HL_MLP_W0 + 27 * 128)    /* pts_linears.0.bias      [128]                        */
+#define HL_MLP_W1 (HL_MLP_B0 + 128)         /* pts_linears.1.weight^T  [128][128]                   */
+#define HL_MLP_B1 (HL_MLP_W1 + 128 * 128)
+#define HL_MLP_W2 (HL_MLP_B1 + 128)         /* pts_linears.2.weight^T  [155][128], in = [x | h1]    */
+#define HL_MLP_B2 (HL_MLP_W2 + 155 * 128)
+#define HL_MLP_WA (HL_MLP_B2 + 128)         /* alpha_linear.weight     [128]                        */
+#define HL_MLP_BA (HL_MLP_WA + 128)         /* alpha_linear.bias       [1] (+3 pad)                 */
+#define HL_MLP_WF (HL_MLP_BA + 4)           /* feature_linear.weight^T [128][128]                   */
+#define HL_MLP_BF (HL_MLP_WF + 128 * 128)
+#define HL_MLP_WV (HL_MLP_BF + 128)         /* views_linear.weight^T   [155][64], in = [feat | pe]  */
+#define HL_MLP_BV (HL_MLP_WV + 155 * 64)
+#define HL_MLP_WR (HL_MLP_BV + 64)          /* rgb_linear.weight^T     [64][4] (3 used)             */
+#define HL_MLP_BR (HL_MLP_WR + 64 * 4)      /* rgb_linear.bias         [4] (3 used)                 */
+#define HL_MLP_PACK_FLOATS (HL_MLP_BR + 4)
+
+/* Reference tri-plane [3 planes, 9 channels, R, R] (channel = sub*3 + c) -> texel-major
+ * [3 planes][3 sub-planes][R][R][4] (3 channels + 1 zero pad): one bilinear tap = one 16-byte load. */
+int hl_triplane_to_texels(const float *planes, float *texels, int R, void *stream);
+
+/* One call renders n_rays rays of one tri-plane: 128 coarse samples -> importance resampling with
+ * the caller's uniforms u [n_rays, 128] (the reference draws them with torch.rand on the CPU,
+ * renderer.py:563; u == NULL selects an in-kernel counter-based generator keyed by `seed`)
+ * -> sort -> 256-sample fine pass -> composite.
+ * rays_o / rays_d: [n_rays, 3]; near / far: [n_rays]; bounds: HOST float[6] = min xyz, max xyz.
+ * z_coarse: the caller's coarse depths (Renderer.render receives them from render(),
+ * run_nerf_batch.py:46-47); NULL = near*(1-t) + far*t with t = linspace(0,1,128) computed in-kernel.
+ * Outputs: rgb [n_rays,3], acc [n_rays], depth [n_rays] (normal_map aliases rgb, renderer.py:237).
+ * clamp_depth: 1 = human_diffusion/NeRF/renderer.py:273-274 variant, 0 = recon_NeRF variant.    */
+int hl_render_rays(const float *texels, int R, const float *mlp_packed, const float *rays_o,
+                   const float *rays_d, const float *near, const float *far,
+                   const float *z_coarse /*nullable [n_rays,128]*/, const float *u /*nullable*/,
+                   uint64_t seed, const float *bounds /*host*/, float *rgb, float *acc, float *depth,
+                   int64_t n_rays, int clamp_depth, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUMANLIFF_B200_H */

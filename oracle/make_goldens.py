@@ -1,0 +1,135 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
+on this container's CPU with seeded synthetic weights / inputs.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.make_goldens            # writes tests/golden/
+
+Weights are never stored: ``humanliff_b200.synth.synth_state_dict`` regenerates them bit-identically
+from (seed, tensor name) and they are loaded into the reference with ``strict=True`` -- which also
+proves the product's state-dict key set / shapes equal the reference's."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from humanliff_b200 import synth                      # noqa: E402
+from oracle import ref_shims                          # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+PROD = dict(image_size=256, in_channels=27, num_channels=192, out_channels=27, num_res_blocks=3,
+            num_heads=4, num_heads_upsample=-1, attention_resolutions="32,16,8", dropout=0.0,
+            learn_sigma=False, sigma_small=False, class_cond=True, diffusion_steps=1000,
+            noise_schedule="linear", timestep_respacing="250", use_kl=False, predict_xstart=False,
+            rescale_timesteps=False, rescale_learned_sigmas=False, use_checkpoint=False,
+            use_scale_shift_norm=True, cond_type="controlnet", use_3d_aware=False)
+TINY = dict(PROD, image_size=32, num_channels=64, num_res_blocks=1, num_heads=2,
+            attention_resolutions="16,8")
+
+
+def build_ref(flags, seed):
+    su = ref_shims.import_diffusion()
+    model, diffusion = su.create_model_and_diffusion(**flags)
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, diffusion
+
+
+def inject_noise(noises):
+    """Patch torch.randn_like so the reference's p_sample consumes our pre-drawn noise."""
+    it = iter(noises)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: next(it).to(x)
+    return orig
+
+
+def unet_case(name, flags, B, HW, ts, seed_w, loop_steps):
+    t0 = time.time()
+    model, diffusion = build_ref(flags, seed_w)
+    x, x_cond, g = synth.synth_denoise_inputs(B, 27, HW, HW, seed=1234)
+    y = torch.arange(B) % 4
+    out = {"x": x.numpy(), "x_cond": x_cond.numpy(), "y": y.numpy(), "ts": np.array(ts)}
+    with torch.no_grad():
+        for t in ts:
+            tt = torch.full((B,), t, dtype=torch.int64)
+            noise = torch.randn(B, 27, HW, HW, generator=g)
+            orig = inject_noise([noise])
+            try:
+                r = diffusion.p_sample(model, x, x_cond, tt, clip_denoised=True, model_kwargs={"y": y})
+            finally:
+                torch.randn_like = orig
+            # epsilon itself (model called with the ORIGINAL timestep index, respace.py:117-122)
+            eps = model(x, torch.tensor(diffusion.timestep_map)[tt], x_cond, y=y)
+            out[f"noise_{t}"] = noise.numpy()
+            out[f"eps_{t}"] = eps.numpy()
+            out[f"sample_{t}"] = r["sample"].numpy()
+            out[f"x0_{t}"] = r["pred_xstart"].numpy()
+        # short free-running loop: last `loop_steps` of the chain starting from x as x_T
+        T = diffusion.num_timesteps
+        noises = [torch.randn(B, 27, HW, HW, generator=g) for _ in range(loop_steps)]
+        img = x
+        orig = inject_noise(noises)
+        try:
+            for k, i in enumerate(range(T - 1, T - 1 - loop_steps, -1)):
+                tt = torch.full((B,), i, dtype=torch.int64)
+                img = diffusion.p_sample(model, img, x_cond, tt, clip_denoised=True,
+                                         model_kwargs={"y": y})["sample"]
+        finally:
+            torch.randn_like = orig
+        out["loop_steps"] = np.array(loop_steps)
+        out["loop_noise"] = torch.stack(noises).numpy()
+        out["loop_final"] = img.numpy()
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
+def render_case(name, n_rays=1024, seed_w=3):
+    t0 = time.time()
+    hd = ref_shims.import_hd_renderer()
+    torch.manual_seed(0)
+    r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    sd = synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5)
+    r.load_state_dict(sd, strict=False)
+    planes = synth.synth_triplane(256, seed=7)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, azimuth_deg=30.0)
+    g = torch.Generator(); g.manual_seed(99)
+    # half hitting rays, a quarter random, plus image-border (miss) rays
+    hit_idx = torch.nonzero(hit)[:, 0]
+    sel = torch.cat([hit_idx[torch.randperm(hit_idx.numel(), generator=g)[:n_rays // 2]],
+                     torch.randint(0, ro.shape[0], (n_rays // 2,), generator=g)])
+    ro, rd, near, far = ro[sel], rd[sel], near[sel], far[sel]
+    u = torch.rand(n_rays, 128, generator=g)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        t = torch.linspace(0., 1., steps=128)
+        z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+        pts = ro[None, :, None, :] + rd[None, :, None, :] * z[..., :, None]
+        tp = {"world_bounds": bounds[None]}
+        with torch.no_grad():
+            ret = r.render(tp, pts.reshape(1, -1, 3), z, ro[None], rd[None], near[None, :, None],
+                           far[None, :, None], planes, 128, False)
+    finally:
+        torch.rand = orig
+    np.savez(os.path.join(OUT, name), rays_o=ro.numpy(), rays_d=rd.numpy(), near=near.numpy(),
+             far=far.numpy(), u=u.numpy(), rgb=ret["rgb_map"][0].numpy(), acc=ret["acc_map"][0].numpy(),
+             depth=ret["depth_map"][0].numpy(), seed_w=np.array(seed_w))
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    assert ref_shims.available(), "reference tree not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ["tiny", "render", "prod64"]
+    if "tiny" in which:
+        unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
+    if "render" in which:
+        render_case("render_1024.npz")
+    if "prod64" in which:
+        unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)

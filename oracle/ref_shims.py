@@ -1,0 +1,39 @@
+"""Import the UNMODIFIED reference from /root/reference on this container's CPU.
+TEST INFRASTRUCTURE ONLY; used by make_goldens.py and the (optional) reference-vs-oracle tests.
+Nothing here runs on the GPU box -- /root/reference does not exist there."""
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("HUMANLIFF_REF", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "human_diffusion", "improved_diffusion"))
+
+
+def import_diffusion():
+    """-> (script_util module) of the reference's improved_diffusion package."""
+    p = os.path.join(REF_ROOT, "human_diffusion")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    from improved_diffusion import script_util   # noqa
+    return script_util
+
+
+def import_hd_renderer():
+    """-> the reference's human_diffusion/NeRF/renderer.py module, with stub modules for the absent
+    mcubes / pytorch3d (never touched when use_canonical_space=False) and anomaly mode switched back off."""
+    import torch
+    for name in ("mcubes", "pytorch3d", "pytorch3d.ops", "pytorch3d.ops.knn"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            if name.endswith("knn"):
+                m.knn_points = None
+            sys.modules[name] = m
+    p = os.path.join(REF_ROOT, "human_diffusion")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    from NeRF import renderer as hd_renderer    # noqa
+    torch.autograd.set_detect_anomaly(False)      # fields.py:2 turns it on at import
+    return hd_renderer

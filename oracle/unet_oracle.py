@@ -1,0 +1,167 @@
+"""Functional CPU restatement of ``UNetModel.forward`` (TEST INFRASTRUCTURE ONLY).
+
+Follows human_diffusion/improved_diffusion/unet.py:550-615 with
+``cond_type in {"controlnet", ""}``, ``use_scale_shift_norm=True``,
+``use_3d_aware=False``.  The block structure is re-derived from the state-dict
+keys (no architecture table shared with the product):
+
+* ``<blk>.0.in_layers.2.weight``  -> ResBlock            (unet.py:198-219)
+* ``<blk>.N.qkv.weight``          -> AttentionBlock      (unet.py:244-274)
+* ``<blk>.0.op.weight``           -> Downsample conv s2  (unet.py:104-106)
+* ``<blk>.N.conv.weight``         -> Upsample + conv     (unet.py:70-80)
+
+``operand_round`` optionally emulates the product's numerics: conv / conv1d
+operands rounded to TF32 (10-bit mantissa, round-to-nearest, ties away) with
+fp32 accumulation.  It exists only to predict the parity margin in tests.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32: round-to-nearest (ties away from zero) to 10 mantissa bits."""
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
+    i = x.contiguous().view(torch.int32)
+    return (i & ~0x1FFF).view(torch.float32)
+
+
+class _Numerics:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def op(self, x, raw=False):
+        if self.mode is None:
+            return x
+        if self.mode == "tf32":
+            return round_tf32(x)
+        if self.mode == "tf32_trunc_raw":
+            return trunc_tf32(x) if raw else round_tf32(x)
+        raise ValueError(self.mode)
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    """nn.py:103-121 -- [cos | sin] blocks, fp32."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def _gn(x, sd, prefix):
+    return F.group_norm(x.float(), 32, sd[prefix + ".weight"], sd[prefix + ".bias"], eps=1e-5)
+
+
+def _silu(x):
+    return x * torch.sigmoid(x)
+
+
+def _conv(x, sd, prefix, nm, stride=1, raw=False):
+    w = sd[prefix + ".weight"]
+    pad = w.shape[-1] // 2
+    return F.conv2d(nm.op(x, raw), nm.op(w), sd[prefix + ".bias"], stride=stride, padding=pad)
+
+
+def _resblock(x, emb, sd, p, nm):
+    """unet.py:198-219 (scale-shift norm)."""
+    h = _conv(_silu(_gn(x, sd, p + ".in_layers.0")), sd, p + ".in_layers.2", nm)
+    e = F.linear(_silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
+    cout = h.shape[1]
+    scale, shift = e[:, :cout, None, None], e[:, cout:, None, None]
+    h = _gn(h, sd, p + ".out_layers.0") * (1 + scale) + shift
+    h = _conv(_silu(h), sd, p + ".out_layers.3", nm)
+    if (p + ".skip_connection.weight") in sd:
+        x = _conv(x, sd, p + ".skip_connection", nm, raw=True)
+    return x + h
+
+
+def _attention(x, sd, p, heads, nm):
+    """unet.py:244-274 -- head-major qkv channel order."""
+    b, c, hh, ww = x.shape
+    xf = x.reshape(b, c, -1)
+    n = F.group_norm(xf.float(), 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
+    qkv = F.conv1d(nm.op(n), nm.op(sd[p + ".qkv.weight"]), sd[p + ".qkv.bias"])
+    qkv = qkv.reshape(b * heads, -1, qkv.shape[2])
+    ch = qkv.shape[1] // 3
+    q, k, v = torch.split(qkv, ch, dim=1)
+    s = 1.0 / math.sqrt(math.sqrt(ch))
+    w = torch.einsum("bct,bcs->bts", nm.op(q * s), nm.op(k * s))
+    w = torch.softmax(w.float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", nm.op(w), nm.op(v)).reshape(b, -1, xf.shape[-1])
+    a = F.conv1d(nm.op(a), nm.op(sd[p + ".proj_out.weight"]), sd[p + ".proj_out.bias"])
+    return (xf + a).reshape(b, c, hh, ww)
+
+
+def _run_block(h, emb, sd, p, heads, nm):
+    """One TimestepEmbedSequential (unet.py:41-49): walk sub-indices 0,1,2."""
+    j = 0
+    while True:
+        q = f"{p}.{j}"
+        if (q + ".in_layers.2.weight") in sd:
+            h = _resblock(h, emb, sd, q, nm)
+        elif (q + ".qkv.weight") in sd:
+            h = _attention(h, sd, q, heads, nm)
+        elif (q + ".op.weight") in sd:
+            h = _conv(h, sd, q + ".op", nm, stride=2, raw=True)
+        elif (q + ".conv.weight") in sd:
+            h = F.interpolate(h, scale_factor=2, mode="nearest")
+            h = _conv(h, sd, q + ".conv", nm, raw=True)
+        elif (q + ".weight") in sd and sd[q + ".weight"].dim() == 4:
+            h = _conv(h, sd, q, nm, raw=True)  # stem conv
+        else:
+            break
+        j += 1
+    assert j > 0, p
+    return h
+
+
+def _count(sd, prefix):
+    idx = set()
+    for k in sd:
+        if k.startswith(prefix + "."):
+            idx.add(int(k[len(prefix) + 1:].split(".")[0]))
+    return (max(idx) + 1) if idx else 0
+
+
+@torch.no_grad()
+def unet_forward(sd, x, timesteps, x_cond=None, y=None, num_heads=4, operand_round=None):
+    """ε = UNetModel.forward(x, timesteps, x_cond, y)   (unet.py:550-615)."""
+    nm = _Numerics(operand_round)
+    model_ch = sd["time_embed.0.weight"].shape[1]
+    emb = timestep_embedding(timesteps, model_ch)
+    emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    emb = F.linear(_silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    if "label_emb.weight" in sd:
+        assert y is not None and y.shape == (x.shape[0],)
+        emb = emb + sd["label_emb.weight"][y]
+
+    n_in = _count(sd, "input_blocks")
+    hs = []
+    h = x.float()
+    for i in range(n_in):
+        h = _run_block(h, emb, sd, f"input_blocks.{i}", num_heads, nm)
+        hs.append(h)
+    h = _run_block(h, emb, sd, "middle_block", num_heads, nm)  # Res, Attn, Res (unet.py:416-438)
+
+    controlnet = "input_blocks_cond.0.0.weight" in sd
+    hs_cond = []
+    if controlnet:
+        hc = x.float() + x_cond.float()
+        for i in range(n_in):
+            hc = _run_block(hc, emb, sd, f"input_blocks_cond.{i}", num_heads, nm)
+            # NB unet.py:599-601 -- the projection REPLACES h_cond and feeds the next block
+            hc = _conv(hc, sd, f"input_blocks_proj_cond.{i}", nm, raw=True)
+            hs_cond.append(hc)
+
+    for i in range(_count(sd, "output_blocks")):
+        skip = hs.pop() + hs_cond.pop() if controlnet else hs.pop()
+        h = _run_block(torch.cat([h, skip], dim=1), emb, sd, f"output_blocks.{i}", num_heads, nm)
+    h = _silu(_gn(h, sd, "out.0"))
+    return _conv(h, sd, "out.2", nm)
+

@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: tri-plane denoise sample-steps/s (27x256x256), BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one DDPM ``p_sample`` (production UNet forward + fused posterior update) over one batch
+of B = 4 samples per GPU (weak scaling: per-GPU work is fixed as N grows; samples are independent so
+there is no data-path collective inside the loop -- the single all-gather of finished samples,
+triplane_sample_layered.py:211-219, is issued once after the K timed steps, inside the timed region).
+
+Prints ONE JSON line (rank 0).  ``value`` = device-resident inputs; ``e2e`` = the public API
+(``SpacedDiffusion.p_sample``) fed from pinned HOST buffers with H2D/D2H inside the timed region.
+``--impl reference`` times the reference algorithm's CPU path (the oracle port; /root/reference does
+not exist on the GPU box) on the host cores.  The oracle is used here ONLY as that CPU baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "tri-plane denoise sample-steps/sec (27x256x256)"
+UNIT = "sample-steps/s"
+GFLOP_PER_SAMPLE_STEP = 2015.4          # BASELINE.md section 2 (forward hooks on the reference UNet)
+C, HW = 27, 256
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # median over the samples taken under load (upper half of the clock distribution excluded idle)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device, precision="tf32"):
+    from humanliff_b200 import factory, synth
+    model, diffusion = factory.create_model_and_diffusion(**dict(factory.production_flags(""), precision=precision))
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval(), diffusion, sd
+
+
+def dominant_kernel_roofline(device, B, peaks, reps=20):
+    """conv3x3 192->192 @ 256x256 (36.7 % of the step's FLOPs, 17 launches/step): CUDA events around
+    `reps` back-to-back launches on the launching stream; L2 is flushed between launches by cycling
+    through input/output buffers whose union exceeds the 126 MB L2."""
+    from humanliff_b200._lib import call
+    from humanliff_b200.unet import pack_conv
+    g = torch.Generator().manual_seed(0)
+    Cin = Cout = 192
+    nbuf = 3
+    xs = [torch.randn(B, HW, HW, Cin, device=device) for _ in range(nbuf)]
+    ys = [torch.empty(B, HW, HW, Cout, device=device) for _ in range(nbuf)]
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / 41.6
+    wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, True, device)
+    st = torch.cuda.current_stream(device)
+
+    def launch(i):
+        call("hl_conv2d", xs[i % nbuf].data_ptr(), Cin, wpk.data_ptr(), bpk.data_ptr(), None, 0,
+             ys[i % nbuf].data_ptr(), Cout, B, HW, HW, Cin, Cout, 3, 1, 0, st.cuda_stream)
+
+    for i in range(3):
+        launch(i)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(reps):
+        launch(i)
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * HW * HW * Cout * Cin * 9
+    ach = flops / (ms * 1e-3) / 1e12
+    bytes_alg = 4.0 * (B * HW * HW * (Cin + Cout) + 9 * Cin * Cout)
+    return {"kernel": "k_conv_tc (tcgen05 kind::tf32 implicit-GEMM conv3x3 192->192 @256^2, B=%d)" % B,
+            "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+            "frac": round(ach / peaks["bf16_burst"], 4), "traffic": None,
+            "peak_source": peaks["source"] + "; bf16 burst figure -- the kernel computes in TF32 whose dense peak is "
+                                             "half of bf16, so frac 0.5 is the TF32 speed of light",
+            "frac_of_tf32_peak": round(ach / (peaks["bf16_burst"] / 2), 4),
+            "ms_per_launch": round(ms, 4), "algorithmic_gflop_per_launch": round(flops / 1e9, 2),
+            "algorithmic_hbm_mb_per_launch": round(bytes_alg / 1e6, 1)}
+
+
+def cpu_baseline(sd, threads, steps=2):
+    """Oracle port of the reference's p_sample on the host cores: B=1, 27x256x256, `steps` timed steps
+    after one warm-up (a bounded sample of the B=4 workload; sample-steps/s is batch-size invariant on
+    the CPU path)."""
+    from oracle.diffusion_oracle import DiffusionOracle
+    torch.set_num_threads(threads)
+    orc = DiffusionOracle(1000, "")
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, C, HW, HW, generator=g)
+    xc = torch.zeros(1, C, HW, HW)
+    y = torch.tensor([0])
+    t = torch.tensor([500])
+    z = torch.randn(1, C, HW, HW, generator=g)
+    orc.p_sample(sd, x, xc, t, y, z)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.p_sample(sd, x, xc, t, y, z)
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from humanliff_b200 import factory, synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model, _ = factory.create_model_and_diffusion(**factory.production_flags(""))
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
+    del model
+    from oracle.diffusion_oracle import DiffusionOracle
+    orc = DiffusionOracle(1000, "")
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, C, HW, HW, generator=g)
+    xc, y, z = torch.zeros(1, C, HW, HW), torch.tensor([0]), torch.randn(1, C, HW, HW, generator=g)
+    for _ in range(min(args.warmup, 1)):
+        orc.p_sample(sd, x, xc, torch.tensor([999]), y, z)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        x = orc.p_sample(sd, x, xc, torch.tensor([999 - k]), y, z)["sample"]
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = "oracle port of p_sample, B=1 x 27x256x256 per step (1/4 of the B=4 workload), %d threads" % threads
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT,
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+                      "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "1000-step DDPM p_sample_loop, 27x256x256 tri-plane (configs[1]); one step = one p_sample",
+                                 "batch_per_step": 1},
+                      "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from humanliff_b200 import _lib
+    from humanliff_b200.dist import all_gather_samples
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    peaks = measured_peaks()
+    model, diffusion, sd = build_model(device, args.precision)
+    g = torch.Generator().manual_seed(1234 + rank)
+    shape = (B, C, HW, HW)
+    # inputs: a few rotating noise buffers (resident in HBM for `value`, pinned on the host for `e2e`)
+    h_x = torch.randn(shape, generator=g).pin_memory()
+    h_xc = torch.zeros(shape).pin_memory()
+    h_z = [torch.randn(shape, generator=g).pin_memory() for _ in range(2)]
+    y = (torch.arange(B) % 4).to(device)
+    x, xc = h_x.to(device), h_xc.to(device)
+    zs = [z.to(device) for z in h_z]
+    T = diffusion.num_timesteps
+    t_dev = torch.empty(B, dtype=torch.int64, device=device)
+    st = torch.cuda.current_stream(device)
+
+    def step_resident(img, i):
+        t_dev.fill_(T - 1 - (i % T))
+        return diffusion.p_sample(model, img, xc, t_dev, clip_denoised=True, model_kwargs={"y": y}, noise=zs[i % 2])["sample"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------- device-resident timing (`value`) ----------------
+    img = x
+    for i in range(W):
+        img = step_resident(img, i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(K):
+        img = step_resident(img, W + i)
+    gathered, _ = all_gather_samples(img, y)
+    e1.record(st)
+    barrier()
+    launches = _lib.launch_count - calls0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---------------- end-to-end through the public API with HOST buffers (`e2e`) ----------------
+    h_out = torch.empty(shape).pin_memory()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(st)
+    for i in range(K):
+        xi = h_x.to(device, non_blocking=True)
+        xci = h_xc.to(device, non_blocking=True)
+        zi = h_z[i % 2].to(device, non_blocking=True)
+        t_dev.fill_(T - 1 - (i % T))
+        out = diffusion.p_sample(model, xi, xci, t_dev, clip_denoised=True, model_kwargs={"y": y}, noise=zi)["sample"]
+        h_out.copy_(out, non_blocking=True)
+    e3.record(st)
+    barrier()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(ms2.item()) * 1e-3)
+    nbytes = B * C * HW * HW * 4
+
+    if rank == 0:
+        roof = dominant_kernel_roofline(device, B, peaks)
+        step_tflops = GFLOP_PER_SAMPLE_STEP * B / (ms_total / K)          # GFLOP / ms = TFLOP/s
+        roof["whole_step_tflops"] = round(step_tflops, 2)
+        roof["whole_step_frac_of_bf16_sustained"] = round(step_tflops / peaks["bf16_sustained"], 4)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_baseline(sd, threads)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "oracle port of the reference p_sample (torch CPU fp32), B=1 x 27x256x256, 2 timed "
+                             "steps after 1 warm-up (%.1f s/step)" % dt}
+        line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": "1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); "
+                                       "one step = one p_sample (UNet 497M params + posterior update)",
+                           "batch_per_gpu": B, "global_batch": B * world, "resolution": "27x256x256",
+                           "parallelism": "dp%d (batch sharded, no data-path collective; one all-gather of finished samples)" % world,
+                           "l2_policy": "per-step working set (>= 6 GB of activations + 2 GB of weights) exceeds the 126 MB L2",
+                           "precision": args.precision},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes,
+                        "d2h_bytes_per_step": nbytes, "ms_per_step": round(float(ms2.item()) / K, 3)},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,7 @@ SIGNATURES = {
     "hl_concat_add": (c_int, [c_p, c_int, c_int, c_p, c_int, c_p, c_int, c_int, c_p, c_int, c_i64, c_p]),
     "hl_upsample2x": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_round_tf32": (c_int, [c_p, c_int, c_p, c_int, c_int, c_i64, c_p]),
-    "hl_timestep_embedding": (c_int, [c_p, c_int, c_int, c_p, c_p]),
+    "hl_timestep_embedding": (c_int, [c_p, c_p, c_int, c_int, c_p, c_p]),
     "hl_linear_small": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int,

@@ -364,7 +364,7 @@ int hl_conv2d_tc(const float *x, int ldx, const float *wpk, const float *bias, c
     p.kchunks_per_tap = Cin / BLOCK_K;
     p.n_tile = pick_n_tile(cout_pad);
     const int b_stage = p.n_tile * BLOCK_K * 4;
-    int stages = (227 * 1024 - 2048) / (A_STAGE_BYTES + b_stage);
+    int stages = (227 * 1024 - 1024 - 1024) / (A_STAGE_BYTES + b_stage);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     const int total_chunks = p.taps * p.kchunks_per_tap;
     if (stages > total_chunks) stages = total_chunks;
@@ -412,11 +412,12 @@ int hl_conv2d_tc(const float *x, int ldx, const float *wpk, const float *bias, c
         }
     }
     const size_t smem = (size_t)p.stages * (A_STAGE_BYTES + b_stage) + 1024;
-    static size_t smem_configured = 0;
-    if (smem > smem_configured) {
+    static bool smem_configured = false;
+    if (!smem_configured) {
+        // 227 KB per CTA minus the kernel's static shared memory (barriers + TMEM slot)
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024));
-        smem_configured = 227 * 1024;
+                                           227 * 1024 - 1024));
+        smem_configured = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, cout_pad / p.n_tile);
     k_conv_tc<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);

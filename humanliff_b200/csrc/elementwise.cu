@@ -220,24 +220,23 @@ extern "C" int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int
 // ------------------------------------------------------------------------------------------
 // embeddings
 // ------------------------------------------------------------------------------------------
-__global__ void k_timestep_embedding(const float *__restrict__ t, int B, int dim,
-                                     float *__restrict__ out) {
+__global__ void k_timestep_embedding(const float *__restrict__ t, const float *__restrict__ freqs, int B,
+                                     int dim, float *__restrict__ out) {
     int half = dim / 2;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     int b = i / half, k = i % half;
-    // freqs = exp(-ln(1e4) * k / half) in fp32, exactly the reference's operation order
-    float f = expf(-9.210340371976184f * (float)k / (float)half);
-    float a = t[b] * f;
+    float a = __fmul_rn(t[b], freqs[k]);
     out[b * dim + k] = cosf(a);
     out[b * dim + half + k] = sinf(a);
     if ((dim & 1) && k == 0) out[b * dim + dim - 1] = 0.f;
 }
 
-extern "C" int hl_timestep_embedding(const float *t, int B, int dim, float *out, void *stream) {
-    HL_CHECK_ARG(t && out && B > 0 && dim >= 2);
+extern "C" int hl_timestep_embedding(const float *t, const float *freqs, int B, int dim, float *out,
+                                     void *stream) {
+    HL_CHECK_ARG(t && freqs && out && B > 0 && dim >= 2);
     int n = B * (dim / 2);
-    k_timestep_embedding<<<hl_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, B, dim, out);
+    k_timestep_embedding<<<hl_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, freqs, B, dim, out);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -42,6 +42,30 @@ def _set_param(root, dotted, shape):
     node.register_parameter(parts[-1], nn.Parameter(torch.zeros(*shape), requires_grad=False))
 
 
+def pack_conv(weight, bias, cin_pad=None, round_tf32=True, device=None, stream=None):
+    """OIHW (or Conv1d [O, I, 1]) weight -> packed ``[kh*kw][Cout_pad][Cin_pad]`` fp32 + padded bias.
+    ``round_tf32`` applies cvt.rna.tf32 on the device (B operand of tcgen05 kind::tf32)."""
+    lib = _lib.load()
+    device = device if device is not None else weight.device
+    w = weight.detach().to(device=device, dtype=torch.float32)
+    if w.dim() == 3:
+        w = w[..., None]
+    cout, cin, kh, kw = w.shape
+    cin_pad = cin_pad or cin
+    cout_pad = lib.hl_conv_cout_pad(cout)
+    pk = torch.zeros(kh * kw, cout_pad, cin_pad, device=device, dtype=torch.float32)
+    pk[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    if round_tf32:
+        if stream is None:
+            stream = torch.cuda.current_stream(device).cuda_stream
+        flat = pk.view(-1, 4)
+        call("hl_round_tf32", _ptr(flat), 4, _ptr(flat), 4, 4, flat.shape[0], stream)
+    b = torch.zeros(cout_pad, device=device, dtype=torch.float32)
+    if bias is not None:
+        b[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+    return pk, b
+
+
 class _Conv:
     """One packed convolution / conv1d / linear-over-pixels."""
 
@@ -221,20 +245,8 @@ class UNetModel(nn.Module):
         lib = _lib.load()
         stream = torch.cuda.current_stream(device).cuda_stream
         for c in self._convs.values():
-            w = self._p(c.name + ".weight").detach().to(device=device, dtype=torch.float32)
-            if w.dim() == 3:
-                w = w[..., None]
-            cout_pad = lib.hl_conv_cout_pad(c.cout)
-            taps = c.ksize * c.ksize
-            pk = torch.zeros(taps, cout_pad, c.cin_pad, device=device, dtype=torch.float32)
-            pk[:, :c.cout, :c.cin] = w.permute(2, 3, 0, 1).reshape(taps, c.cout, c.cin)
-            if rnd:
-                flat = pk.view(-1, 4)
-                call("hl_round_tf32", _ptr(flat), 4, _ptr(flat), 4, 4, flat.shape[0], stream)
-            c.w = pk
-            bias = torch.zeros(cout_pad, device=device, dtype=torch.float32)
-            bias[:c.cout] = self._p(c.name + ".bias").detach().to(device=device, dtype=torch.float32)
-            c.b = bias
+            c.w, c.b = pack_conv(self._p(c.name + ".weight"), self._p(c.name + ".bias"), c.cin_pad, rnd,
+                                 device, stream)
         ws, bs = [], []
         for prefix, cout, off in self._film:
             ws.append(self._p(prefix + ".emb_layers.1.weight").detach().to(device, torch.float32))
@@ -247,6 +259,9 @@ class UNetModel(nn.Module):
         if self.num_classes is not None:
             self._small["label_emb.weight"] = self._p("label_emb.weight").detach().to(
                 device, torch.float32).contiguous()
+        half = self.model_channels // 2
+        self._freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32)
+                                / half).to(device)     # host fp32, as nn.py:114-116
         self._norm_p = {}
         for name, p in self.named_parameters():
             if p.dim() == 1 and (name.endswith("in_layers.0.weight") or name.endswith("in_layers.0.bias")
@@ -448,7 +463,7 @@ class UNetModel(nn.Module):
             e1 = ws.get("e1", B * ed)
             emb = ws.get("emb", B * ed)
             film = ws.get("film", B * self._film_rows)
-            call("hl_timestep_embedding", _ptr(tf), B, mc, _ptr(temb), self._stream)
+            call("hl_timestep_embedding", _ptr(tf), _ptr(self._freqs), B, mc, _ptr(temb), self._stream)
             call("hl_linear_small", _ptr(temb), _ptr(self._small["time_embed.0.weight"]),
                  _ptr(self._small["time_embed.0.bias"]), _ptr(e1), B, mc, ed, 0, None, None, self._stream)
             if self.num_classes is not None:

@@ -60,8 +60,9 @@ int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int C, int64_t
 
 /* ---- embeddings (nn.py:103-121, unet.py:366-373,564,584-586,151-157,200) --------------------- */
 
-/* out[b, 0:half] = cos(t_b f_k), out[b, half:] = sin(t_b f_k), f_k = exp(-ln(1e4) k / half)     */
-int hl_timestep_embedding(const float *t, int B, int dim, float *out, void *stream);
+/* out[b, 0:half] = cos(t_b f_k), out[b, half:] = sin(t_b f_k); freqs [dim/2] is the device copy of
+ * f_k = exp(-ln(1e4) k / half), which the reference evaluates on the HOST in fp32 (nn.py:114-116).      */
+int hl_timestep_embedding(const float *t, const float *freqs, int B, int dim, float *out, void *stream);
 /* y[b, o] = bias[o] + sum_i W[o, i] * act(x[b, i]) (+ add[idx[b], o]);  act = SiLU if silu_in.
  * W is row-major [out, in] exactly as nn.Linear stores it.  Used for time_embed, and once per
  * step for ALL ResBlock emb_layers stacked into one [sum 2Cout, 768] matrix.                    */

@@ -35,7 +35,8 @@ def kept_timesteps(T, respacing):
 
 
 class DiffusionOracle:
-    def __init__(self, T=1000, respacing="", sigma_small=False):
+    def __init__(self, T=1000, respacing="", sigma_small=False, num_heads=4):
+        self.num_heads = num_heads
         abar_full = np.cumprod(1.0 - linear_betas(T))
         self.timestep_map = kept_timesteps(T, respacing)
         kept = abar_full[self.timestep_map]
@@ -71,7 +72,7 @@ class DiffusionOracle:
     @torch.no_grad()
     def p_sample(self, sd, x, x_cond, t, y, noise, clip=True, operand_round=None):
         ts = torch.tensor(self.timestep_map, dtype=torch.int64)[t]
-        eps = unet_forward(sd, x, ts, x_cond, y, operand_round=operand_round)
+        eps = unet_forward(sd, x, ts, x_cond, y, num_heads=self.num_heads, operand_round=operand_round)
         sample, x0 = self.posterior(x, eps, t, noise, clip)
         return {"sample": sample, "pred_xstart": x0, "eps": eps}
 

@@ -1,0 +1,99 @@
+"""GPU parity of the denoise path against the golden vectors frozen from the unmodified reference
+(tests/golden, made by oracle/make_goldens.py) and against the oracle on fresh seeded inputs.
+
+Tolerances (north_star: 1e-3 relative fp32): ``precision="fp32"`` (CUDA-core kernels, same arithmetic
+as the reference up to summation order) 5e-5; ``precision="tf32"`` (tcgen05, TF32 operands) 1e-3 on
+rel-L2 and max-norm-relative (SURVEY.md 8(d) parity metric)."""
+import pytest
+import torch
+
+from common import CASES, load_golden, model_state_dict, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 5e-5, "tf32": 1e-3}
+
+
+def _model(case, precision):
+    fname, flags, seed, heads = CASES[case]
+    model, diffusion, sd = model_state_dict(dict(flags, precision=precision), seed)
+    model.load_state_dict(sd, strict=True)
+    return model.to("cuda:0").eval(), diffusion, load_golden(fname), sd, heads
+
+
+@pytest.mark.parametrize("case,precision", [("tiny", "fp32"), ("tiny", "tf32"), ("prod64", "fp32"), ("prod64", "tf32")])
+def test_unet_forward_and_p_sample_vs_reference_golden(case, precision):
+    model, diffusion, g, _, _ = _model(case, precision)
+    dev = torch.device("cuda:0")
+    x, xc, y = g["x"].to(dev), g["x_cond"].to(dev), g["y"].to(dev)
+    tol = TOL[precision]
+    if precision == "tf32":
+        from humanliff_b200 import _lib
+        assert any(model._uses_tc(n, x.shape[0], x.shape[2], x.shape[3], c.cin_pad) for n, c in model._convs.items()
+                   if c.ksize == 3 and c.stride == 1), "tf32 mode must route convs through the tcgen05 kernel"
+    for t in g["ts"].tolist():
+        tt = torch.full((x.shape[0],), t, dtype=torch.int64, device=dev)
+        ts = torch.tensor(diffusion.timestep_map, device=dev)[tt]
+        eps = model(x, ts, xc, y=y)
+        e2, em = rel_l2(eps, g[f"eps_{t}"]), rel_max(eps, g[f"eps_{t}"])
+        assert e2 < tol and em < tol, f"{case}/{precision} t={t}: eps rel-L2 {e2:.3e} max {em:.3e}"
+        out = diffusion.p_sample(model, x, xc, tt, clip_denoised=True, model_kwargs={"y": y},
+                                 noise=g[f"noise_{t}"].to(dev))
+        assert rel_l2(out["sample"], g[f"sample_{t}"]) < tol, (case, precision, t)
+        assert rel_l2(out["pred_xstart"], g[f"x0_{t}"]) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_free_running_loop_vs_reference_golden(precision):
+    model, diffusion, g, _, _ = _model("tiny", precision)
+    dev = torch.device("cuda:0")
+    n, T = int(g["loop_steps"]), diffusion.num_timesteps
+    img, xc, y = g["x"].to(dev), g["x_cond"].to(dev), g["y"].to(dev)
+    for k, i in enumerate(range(T - 1, T - 1 - n, -1)):
+        tt = torch.full((img.shape[0],), i, dtype=torch.int64, device=dev)
+        img = diffusion.p_sample(model, img, xc, tt, model_kwargs={"y": y}, noise=g["loop_noise"][k].to(dev))["sample"]
+    err = rel_l2(img, g["loop_final"])
+    assert err < (1e-4 if precision == "fp32" else 2e-3), err
+
+
+def test_p_sample_loop_api_with_injected_noise():
+    """p_sample_loop (the call triplane_sample_layered.py:145-151 makes) over a 6-step respacing vs the oracle."""
+    from humanliff_b200 import factory, synth
+    from oracle.diffusion_oracle import DiffusionOracle
+    fname, flags, seed, heads = CASES["tiny"]
+    flags = dict(flags, timestep_respacing="6", precision="fp32")
+    model, diffusion = factory.create_model_and_diffusion(**flags)
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=seed)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    B = 2
+    xT = torch.randn(B, 27, 32, 32, generator=g)
+    xc = torch.zeros(B, 27, 32, 32)
+    y = torch.tensor([1, 3])
+    noises = {i: torch.randn(B, 27, 32, 32, generator=g) for i in range(6)}
+    out = diffusion.p_sample_loop(model, (B, 27, 32, 32), x_cond=xc.cuda(), noise=xT.cuda(), clip_denoised=True,
+                                  model_kwargs={"y": y.cuda()}, step_noise=lambda i: noises[i].cuda())
+    orc = DiffusionOracle(1000, "6", num_heads=heads)
+    assert orc.timestep_map == diffusion.timestep_map
+    ref = orc.p_sample_loop(sd, xT, xc, y, lambda i: noises[i])
+    assert rel_l2(out, ref) < 1e-4
+
+
+def test_unconditional_variant_and_errors():
+    from humanliff_b200 import factory, synth
+    from oracle import unet_oracle
+    fname, flags, seed, heads = CASES["tiny"]
+    flags = dict(flags, cond_type="", class_cond=False, precision="fp32")
+    model, _ = factory.create_model_and_diffusion(**flags)
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=3)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0")
+    x = torch.randn(1, 27, 32, 32, generator=torch.Generator().manual_seed(1))
+    t = torch.tensor([17])
+    eps = model(x.cuda(), t.cuda())
+    ref = unet_oracle.unet_forward(sd, x, t, None, None, num_heads=heads)
+    assert rel_l2(eps, ref) < 2e-5
+    with pytest.raises(RuntimeError):
+        model(x, t)                       # CPU tensors: there is no CPU fallback
+    with pytest.raises(NotImplementedError):
+        factory.create_model_and_diffusion(**dict(flags, cond_type="AdaGN"))

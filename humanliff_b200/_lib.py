@@ -16,26 +16,30 @@ c_int, c_i64, c_u64, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, c
 SIGNATURES = {
     "hl_version": (c_int, []),
     "hl_last_error": (ctypes.c_char_p, []),
-    "hl_conv2d_uses_tensor_cores": (c_int, [c_int] * 9),
-    "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_conv2d_uses_tensor_cores": (c_int, [c_int] * 11),
+    "hl_conv_set_tuning": (c_int, [c_int] * 5),
+    "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_nhwc_to_nchw": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
     "hl_concat_add": (c_int, [c_p, c_int, c_int, c_p, c_int, c_p, c_int, c_int, c_p, c_int, c_i64, c_p]),
-    "hl_upsample2x": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
-    "hl_round_tf32": (c_int, [c_p, c_int, c_p, c_int, c_int, c_i64, c_p]),
+    "hl_upsample2x": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_cast_operand": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_i64, c_int, c_p]),
+    "hl_zero": (c_int, [c_p, c_i64, c_p]),
     "hl_timestep_embedding": (c_int, [c_p, c_p, c_int, c_int, c_p, c_p]),
     "hl_linear_small": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
-    "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
-    "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int,
-                            c_int, c_f, c_int, c_int, c_p]),
+    "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_int, c_p]),
+    "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_p, c_int,
+                            c_int, c_int, c_int, c_int, c_f, c_int, c_int, c_p]),
     "hl_conv_cout_pad": (c_int, [c_int]),
-    "hl_conv2d": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int,
-                          c_int, c_int, c_int, c_int, c_p]),
-    "hl_attention": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_conv2d": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int,
+                          c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_attention": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                c_i64, c_int, c_p]),
 }
+
+DT_F32, DT_F16 = 0, 1
 
 # offsets of the packed renderer MLP (HL_MLP_* in the header)
 MLP_W0 = 0
@@ -56,6 +60,7 @@ MLP_PACK_FLOATS = MLP_BR + 4
 
 CONV_FORCE_SIMT = 1
 CONV_UPSAMPLE2X = 2
+CONV_TF32 = 4
 
 _lib = None
 launch_count = 0   # number of C-ABI compute calls issued (each is >= 1 kernel launch)

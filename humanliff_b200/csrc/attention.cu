@@ -6,14 +6,16 @@
 // [head][q(ch) | k(ch) | v(ch)]  (qkv.reshape(b*heads, 3*ch, T), unet.py:248,267-268).
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace {
 
 constexpr int TQ = 64, TK = 64;
 
 template <int CH>
 __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv, int ldq,
-                                                   float *__restrict__ out, int ldo, int T, int heads,
-                                                   float scale, int round_tf32) {
+                                                   void *__restrict__ out, int out_dtype, int ldo, int T,
+                                                   int heads, float scale, int round_tf32) {
     constexpr int LD = CH + 4;           // padded row pitch (floats): conflict-free float4 rows
     constexpr int NJ = CH / 16;          // output columns per thread
     extern __shared__ float sm[];
@@ -142,18 +144,19 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
         int r = ty + 16 * i;
         if (q0 + r >= T) continue;
         float inv = 1.0f / row_l[r];
-        float *orow = out + ((int64_t)b * T + q0 + r) * ldo + h * CH;
+        const int64_t obase = ((int64_t)b * T + q0 + r) * ldo + h * CH;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             float v = o[i][j] * inv;
-            orow[tx + 16 * j] = round_tf32 ? hl_rna_tf32(v) : v;
+            if (out_dtype == HL_DT_F16) reinterpret_cast<__half *>(out)[obase + tx + 16 * j] = __float2half_rn(v);
+            else reinterpret_cast<float *>(out)[obase + tx + 16 * j] = round_tf32 ? hl_rna_tf32(v) : v;
         }
     }
 }
 
 template <int CH>
-int launch(const float *qkv, int ldq, float *out, int ldo, int B, int T, int heads, int round_tf32,
-           cudaStream_t stream) {
+int launch(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int heads,
+           int round_tf32, cudaStream_t stream) {
     constexpr int LD = CH + 4;
     size_t smem = sizeof(float) * (size_t)(3 * 64 * LD + 64 * 65 + 3 * 64);
     static bool configured = false;
@@ -164,25 +167,25 @@ int launch(const float *qkv, int ldq, float *out, int ldo, int B, int T, int hea
     }
     dim3 grid(hl_cdiv(T, TQ), heads, B);
     float scale = 1.0f / sqrtf((float)CH);
-    k_attention<CH><<<grid, 256, smem, stream>>>(qkv, ldq, out, ldo, T, heads, scale, round_tf32);
+    k_attention<CH><<<grid, 256, smem, stream>>>(qkv, ldq, out, out_dtype, ldo, T, heads, scale, round_tf32);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 }  // namespace
 
-extern "C" int hl_attention(const float *qkv, int ldq, float *out, int ldo, int B, int T, int C,
+extern "C" int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
                             int heads, int round_tf32, void *stream) {
     HL_CHECK_ARG(qkv && out && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0);
     HL_CHECK_ARG(ldq >= 3 * C && ldo >= C && ldq % 4 == 0);
     int ch = C / heads;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ch) {
-        case 32: return launch<32>(qkv, ldq, out, ldo, B, T, heads, round_tf32, st);
-        case 64: return launch<64>(qkv, ldq, out, ldo, B, T, heads, round_tf32, st);
-        case 96: return launch<96>(qkv, ldq, out, ldo, B, T, heads, round_tf32, st);
-        case 128: return launch<128>(qkv, ldq, out, ldo, B, T, heads, round_tf32, st);
-        case 192: return launch<192>(qkv, ldq, out, ldo, B, T, heads, round_tf32, st);
+        case 32: return launch<32>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
+        case 64: return launch<64>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
+        case 96: return launch<96>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
+        case 128: return launch<128>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
+        case 192: return launch<192>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
         default:
             hl_set_error("hl_attention: unsupported head width %d (supported: 32,64,96,128,192)", ch);
             return HL_E_UNSUPPORTED;

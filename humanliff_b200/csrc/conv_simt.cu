@@ -1,4 +1,4 @@
-// fp32 CUDA-core implicit-GEMM convolution (NHWC).  General shapes: ksize 1/3, stride 1/2, any
+// CUDA-core implicit-GEMM convolution (NHWC), fp32 accumulate; operands fp32 or fp16.  General shapes: ksize 1/3, stride 1/2, any
 // Cin/Cout, optional nearest-x2 upsampled input, bias + residual epilogue.  This is the exact-fp32
 // companion of the tcgen05 kernel in conv_tc.cu: it serves the shapes the tensor-core path does
 // not tile (stride 2, tiny feature maps, W not a power of two) and the `precision="fp32"` mode.
@@ -8,13 +8,19 @@
 // the previous chunk is multiplied out of shared memory.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
+__device__ __forceinline__ float ldf(const float *p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ldf(const __half *p, int64_t i) { return __half2float(p[i]); }
+
+template <typename T>
 struct ConvArgs {
-    const float *x; int ldx;
-    const float *w; const float *bias;
+    const T *x; int ldx;
+    const T *w; const float *bias;
     const float *res; int ldr;
     float *y; int ldy;
     int B, H, W, Cin, Cout, Cout_pad, ksize, stride, ups;
@@ -24,7 +30,8 @@ struct ConvArgs {
     int K;
 };
 
-__global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -71,10 +78,10 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a) {
                     int ix = ox * a.stride + kx - pad;
                     if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
                         if (a.ups) { iy >>= 1; ix >>= 1; }
-                        va = a.x[(((int64_t)ob * a.H + iy) * a.W + ix) * a.ldx + ci];
+                        va = ldf(a.x, (((int64_t)ob * a.H + iy) * a.W + ix) * a.ldx + ci);
                     }
                 }
-                if (nvalid) vb = a.w[((int64_t)tap * a.Cout_pad + nrow) * a.Cin + ci];
+                if (nvalid) vb = ldf(a.w, ((int64_t)tap * a.Cout_pad + nrow) * a.Cin + ci);
             }
             ra[j] = va;
             rb[j] = vb;
@@ -119,12 +126,11 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a) {
     }
 }
 
-}  // namespace
-
-int hl_conv2d_simt(const float *x, int ldx, const float *wpk, const float *bias,
-                   const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin,
-                   int Cout, int ksize, int stride, int flags, cudaStream_t stream) {
-    ConvArgs a;
+template <typename T>
+static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, const float *residual, int ldr,
+                       float *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                       int flags, cudaStream_t stream) {
+    ConvArgs<T> a;
     a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = hl_conv_cout_pad(Cout);
     a.ksize = ksize; a.stride = stride; a.ups = (flags & HL_CONV_UPSAMPLE2X) ? 1 : 0;
@@ -136,7 +142,19 @@ int hl_conv2d_simt(const float *x, int ldx, const float *wpk, const float *bias,
     a.M = (int64_t)B * a.Ho * a.Wo;
     a.K = ksize * ksize * Cin;
     dim3 grid(hl_cdiv(a.M, BM), hl_cdiv(Cout, BN));
-    k_conv_simt<<<grid, 256, 0, stream>>>(a);
+    k_conv_simt<T><<<grid, 256, 0, stream>>>(a);
     HL_CHECK_LAUNCH();
     return HL_OK;
+}
+
+}  // namespace
+
+int hl_conv2d_simt(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+                   const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout,
+                   int ksize, int stride, int flags, cudaStream_t stream) {
+    if (x_dtype == HL_DT_F16)
+        return launch_simt<__half>((const __half *)x, ldx, (const __half *)wpk, bias, residual, ldr, y, ldy, B, H,
+                                   W, Cin, Cout, ksize, stride, flags, stream);
+    return launch_simt<float>((const float *)x, ldx, (const float *)wpk, bias, residual, ldr, y, ldy, B, H, W,
+                              Cin, Cout, ksize, stride, flags, stream);
 }

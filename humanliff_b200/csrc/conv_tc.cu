@@ -1,54 +1,82 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a, NHWC fp32 in / fp32 out,
-// TF32 operands with fp32 accumulation in TMEM.
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+// NHWC activations (fp16, or fp32 read as TF32), fp32 accumulation in TMEM, fp32 NHWC output.
 //
-//   GEMM view   M = B*H*W output pixels (tile: 128 pixels = a [bn x bh x bw] box of the image)
-//               N = Cout               (tile: UMMA_N = 32..256 output channels)
-//               K = taps * Cin         (chunk: 32 channels of one filter tap = one 128-byte row)
+//   GEMM view   M = B*H*W output pixels   tile: mh x 128 pixels (mh = 1 or 2 "halves", one TMEM
+//                                         accumulator of 128 lanes x n_tile columns per half)
+//               N = Cout                  tile: n_tile = 32..256 output channels
+//               K = taps * Cin            chunk: 128 bytes of channels (64 fp16 / 32 tf32) of one tap
 //
-//   A operand   the activation tensor itself, fetched by TMA as a 4-D box {32ch, bw, bh, bn} whose
-//               (x, y) origin is shifted by the filter tap; out-of-bounds pixels are zero-filled by
+//   A operand   the activation tensor itself, fetched by TMA; out-of-bounds pixels are zero-filled by
 //               the TMA unit, which IS the conv's zero padding -- no im2col buffer ever exists.
-//   B operand   packed weights [tap][Cout_pad][Cin], 3-D TMA box {32ch, UMMA_N, 1}.
+//       TAP  mode: one 4-D box {chunk, bw, bh, bn} per (tap, chunk, half), origin shifted by the tap
+//                  (stride-2 convs use the tensor map's element strides).
+//       HALO mode (3x3, stride 1, W % 128 == 0): a half is one image row segment of 128 pixels; the
+//                  mh+2 halo rows {chunk, 130 px} are loaded ONCE per channel chunk into a ring of
+//                  row slots and all 9 taps read them through shifted shared-memory descriptors
+//                  (start = slot + (dx+1)*128 B, descriptor base_offset = (start >> 7) & 7):
+//                  2.9x (mh=1) .. 4.3x (mh=2) fewer A bytes from L2 than per-tap boxes.
+//   B operand   packed weights [tap][Cout_pad][Cin], 3-D TMA box {chunk, n_tile, 1}; with mh = 2 one
+//               weight tile feeds both halves (halves the weight traffic per flop).
 //   both land in shared memory in the SWIZZLE_128B K-major layout tcgen05.mma consumes directly.
 //
-//   warp roles  warp 0: TMA producer (one lane)      warp 1: TMEM alloc + MMA issue (one lane)
-//               warps 2-5: epilogue (tcgen05.ld -> +bias (+residual) -> global)
-//   pipeline    `stages`-deep full/empty mbarrier ring between TMA and MMA; tcgen05.commit releases
-//               a stage when the MMAs that read it retire; a final commit hands TMEM to the epilogue.
+//   persistent  grid = min(tiles, SMs); each CTA walks tiles t = blockIdx.x + i*gridDim.x (n-tile
+//               fastest so concurrently running CTAs share activations in L2).
+//   warp roles  warp 0: A producer (TMA)   warp 1: B producer (TMA)   warp 2: TMEM alloc + MMA issue
+//               warps 3-6: epilogue.  Two independent smem rings (A, B) with full/empty mbarriers;
+//               tcgen05.commit releases slots; TMEM accumulators are double-buffered when they fit
+//               (acc_stages = 2) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   epilogue    tcgen05.ld (32 columns) -> + bias (+ residual, TMA-prefetched into the staging
+//               buffer, added in place) -> swizzled smem staging -> TMA store (coalesced, clipped
+//               at the tensor edge); optional per-channel sum / sum-of-squares of the OUTPUT
+//               (the following GroupNorm's statistics), accumulated per CTA in shared memory and
+//               flushed with fp64 atomics once per sample.
 //
-// Algorithmic work per launch: 2*M*N*K flop; compulsory HBM bytes: 4*(M*Cin + taps*Cout*Cin + M*Cout
-// (+ M*Cout residual)).
+// Algorithmic work per launch: 2*M*N*K flop; compulsory HBM bytes: e*(M*Cin + taps*Cout*Cin) +
+// 4*M*Cout (+ 4*M*Cout residual), e = operand bytes per element.
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 int hl_num_sms();
 
 namespace {
 
+constexpr int ROW_BYTES = 128;                   // one K chunk of one pixel / one weight row
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;   // fp32/tf32 elements per K chunk (128 bytes)
-constexpr int UMMA_K = 8;     // tf32: 32 bytes per MMA K step
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;
-constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
+constexpr int A_BOX_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
+constexpr int HALO_PIX = BLOCK_M + 2;
+constexpr int HALO_ROW_BYTES = HALO_PIX * ROW_BYTES;   // 16640
+constexpr int HALO_SLOT_BYTES = 17 * 1024;            // rounded up to the 1024 B swizzle period
+constexpr int STAGE_BUF_BYTES = BLOCK_M * 128;        // epilogue staging: 128 rows x 32 fp32
+constexpr int MAX_SLOTS = 8;
+constexpr int MAX_NBUF = 4;
+constexpr int NUM_THREADS = 7 * 32;
+constexpr int EPI_THREADS = 128;
+constexpr int STATS_MAX_C = 768;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 8 * 1024;   // static smem: barriers + statistics accumulators
 
 struct TcParams {
-    int taps, ksize, kchunks_per_tap, n_tile, stages, tmem_cols;
+    int B, H, W;             // OUTPUT spatial size
+    int Cout, stride, ksize, taps, kchunks, kind;   // kind: 0 = tf32, 1 = f16
     int bw, bh, bn, tiles_w, tiles_h;
-    int B, H, W, Cout;
+    int mh, n_tile, n_tiles, nchunks;
+    int total_tiles;
+    int halo, hp;            // hp = H / mh (halo mode)
+    int base_off;            // halo descriptors carry base_offset = (addr >> 7) & 7
+    int acc_stages, acc_stride, tmem_cols;
+    int a_slots, a_slot_bytes, b_slots, b_slot_bytes, nbuf;
     const float *bias;
-    const float *res;
-    int ldr;
-    float *y;
-    int ldy;
-    int vec_ok;   // 1: 16-byte epilogue accesses are legal
+    int has_res;
+    double *stats;
+    int stats_ld;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -56,10 +84,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // Bounded spin: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -88,27 +119,53 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
-// rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart (SBO), LBO unused for swizzled K-major.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1): rows of 128
+// bytes, 8-row swizzle atoms 1024 bytes apart (SBO); LBO unused for swizzled K-major.  base_offset
+// = (addr >> 7) & 7 lets the start address sit on any 128 B row of the swizzle pattern (halo taps).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t use_base_offset = 1u) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(use_base_offset ? ((saddr >> 7) & 7u) : 0u) << 49;
     d |= (uint64_t)2 << 61;
     return d;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+__device__ __forceinline__ void umma(int kind, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+    if (kind) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -132,42 +189,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// origin (output pixel coordinates) of half `half` of m-tile `mt`
+__device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, int &w0, int &h0, int &n0) {
+    if (p.halo) {
+        const int tw = mt % p.tiles_w;
+        const int r = mt / p.tiles_w;
+        w0 = tw * BLOCK_M;
+        h0 = (r % p.hp) * p.mh + half;
+        n0 = r / p.hp;
+    } else {
+        const int bi = mt * p.mh + half;
+        const int tw = bi % p.tiles_w;
+        const int r = bi / p.tiles_w;
+        w0 = tw * p.bw;
+        h0 = (r % p.tiles_h) * p.bh;
+        n0 = (r / p.tiles_h) * p.bn;
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
           const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + MAX_NBUF];
     __shared__ uint32_t tmem_slot;
+    __shared__ float sacc[2][STATS_MAX_C];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int b_stage_bytes = p.n_tile * BLOCK_K * 4;
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_base + (uint32_t)p.stages * A_STAGE_BYTES;
-    const uint32_t bar_full = smem_u32(&bars[0]);
-    const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
-    const uint32_t bar_tmem = smem_u32(&bars[2 * MAX_STAGES]);
-
-    // tile coordinates
-    const int mt = blockIdx.x;
-    const int tw = mt % p.tiles_w;
-    const int th = (mt / p.tiles_w) % p.tiles_h;
-    const int tn = mt / (p.tiles_w * p.tiles_h);
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-    const int nt0 = blockIdx.y * p.n_tile;
-    const int total_chunks = p.taps * p.kchunks_per_tap;
+    const uint32_t smem_b = smem_a + (uint32_t)(p.a_slots * p.a_slot_bytes);
+    const uint32_t smem_e = smem_b + (uint32_t)(p.b_slots * p.b_slot_bytes);
+    const uint32_t bar_a_full = smem_u32(&bars[0]);
+    const uint32_t bar_a_empty = smem_u32(&bars[MAX_SLOTS]);
+    const uint32_t bar_b_full = smem_u32(&bars[2 * MAX_SLOTS]);
+    const uint32_t bar_b_empty = smem_u32(&bars[3 * MAX_SLOTS]);
+    const uint32_t bar_t_full = smem_u32(&bars[4 * MAX_SLOTS]);
+    const uint32_t bar_t_empty = smem_u32(&bars[4 * MAX_SLOTS + 2]);
+    const uint32_t bar_r_full = smem_u32(&bars[4 * MAX_SLOTS + 4]);
+    const int chunk_elems = p.kind ? 64 : 32;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     }
-    if (warp == 1) {
+    if (warp == 2) {
         if (lane == 0) {
-            for (int s = 0; s < p.stages; ++s) {
-                mbar_init(bar_full + 8 * s, 1);
-                mbar_init(bar_empty + 8 * s, 1);
+            for (int s = 0; s < MAX_SLOTS; ++s) {
+                mbar_init(bar_a_full + 8 * s, 1);
+                mbar_init(bar_a_empty + 8 * s, 1);
+                mbar_init(bar_b_full + 8 * s, 1);
+                mbar_init(bar_b_empty + 8 * s, 1);
             }
-            mbar_init(bar_tmem, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(bar_t_full + 8 * s, 1);
+                mbar_init(bar_t_empty + 8 * s, EPI_THREADS);
+            }
+            for (int s = 0; s < MAX_NBUF; ++s) mbar_init(bar_r_full + 8 * s, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -177,96 +258,270 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp >= 3 && p.stats) {
+        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_THREADS) (&sacc[0][0])[i] = 0.f;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_slot;
+    const int pad = p.ksize / 2;
 
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------ TMA producer ------------------------------
-            const int pad = p.ksize / 2;
-            const uint32_t tx_bytes = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int kc = 0; kc < total_chunks; ++kc) {
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                mbar_expect_tx(bar_full + 8 * s, tx_bytes);
-                const int tap = kc / p.kchunks_per_tap;
-                const int c0 = (kc - tap * p.kchunks_per_tap) * BLOCK_K;
-                const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
-                tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmA, bar_full + 8 * s, c0, w0 + dx, h0 + dy, n0);
-                tma_load_3d(smem_b + s * b_stage_bytes, &tmB, bar_full + 8 * s, c0, nt0, tap);
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            // ------------------------------ A producer ------------------------------
+            uint32_t ai = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    const int c0 = kc * chunk_elems;
+                    if (p.halo) {
+                        int w0, h0, n0;
+                        box_origin(p, mt, 0, w0, h0, n0);
+                        for (int r = 0; r < p.mh + 2; ++r, ++ai) {
+                            const uint32_t s = ai % (uint32_t)p.a_slots, ph = (ai / (uint32_t)p.a_slots) & 1u;
+                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+                            mbar_expect_tx(bar_a_full + 8 * s, HALO_ROW_BYTES);
+                            tma_load_4d(smem_a + s * p.a_slot_bytes, &tmA, bar_a_full + 8 * s, c0, w0 - 1,
+                                        h0 - 1 + r, n0);
+                        }
+                    } else {
+                        for (int tap = 0; tap < p.taps; ++tap, ++ai) {
+                            const uint32_t s = ai % (uint32_t)p.a_slots, ph = (ai / (uint32_t)p.a_slots) & 1u;
+                            const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+                            mbar_expect_tx(bar_a_full + 8 * s, (uint32_t)(p.mh * A_BOX_BYTES));
+                            for (int half = 0; half < p.mh; ++half) {
+                                int w0, h0, n0;
+                                box_origin(p, mt, half, w0, h0, n0);
+                                tma_load_4d(smem_a + s * p.a_slot_bytes + half * A_BOX_BYTES, &tmA,
+                                            bar_a_full + 8 * s, c0, w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                            }
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ------------------------------ MMA issuer --------------------------------
-            // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
-                                   ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int kc = 0; kc < total_chunks; ++kc) {
-                mbar_wait(bar_full + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_a + s * A_STAGE_BYTES;
-                const uint32_t b0 = smem_b + s * b_stage_bytes;
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    umma_tf32(tmem_base, umma_desc_sw128(a0 + k * UMMA_K * 4),
-                              umma_desc_sw128(b0 + k * UMMA_K * 4), idesc, (kc | k) != 0);
+            // ------------------------------ B producer ------------------------------
+            uint32_t bi = 0;
+            const uint32_t bytes = (uint32_t)(p.n_tile * ROW_BYTES);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt0 = (tile % p.n_tiles) * p.n_tile;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int tap = 0; tap < p.taps; ++tap, ++bi) {
+                        const uint32_t s = bi % (uint32_t)p.b_slots, ph = (bi / (uint32_t)p.b_slots) & 1u;
+                        mbar_wait(bar_b_empty + 8 * s, ph ^ 1u);
+                        mbar_expect_tx(bar_b_full + 8 * s, bytes);
+                        tma_load_3d(smem_b + s * p.b_slot_bytes, &tmB, bar_b_full + 8 * s, kc * chunk_elems, nt0,
+                                    tap);
+                    }
                 }
-                umma_commit(bar_empty + 8 * s);   // stage reusable once these MMAs retire
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            umma_commit(bar_tmem);                // accumulator complete -> epilogue
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ------------------------------ MMA issuer --------------------------------
+            // instruction descriptor: D=f32, A/B format (0 = f16, 2 = tf32), both K-major, N>>3 @17, M>>4 @24
+            const uint32_t fmt = p.kind ? 0u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) |
+                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+            uint32_t ai = 0, bi = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int as = it % p.acc_stages;
+                const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
+                mbar_wait(bar_t_empty + 8 * as, aph ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc0 = tmem_base + (uint32_t)(as * p.mh * p.acc_stride);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    if (p.halo) {
+                        const uint32_t a_base = ai;
+                        ai += (uint32_t)(p.mh + 2);
+                        int rows_waited = 0;
+                        for (int ty = 0; ty < 3; ++ty) {
+                            while (rows_waited < ty + p.mh) {
+                                const uint32_t c = a_base + rows_waited;
+                                mbar_wait(bar_a_full + 8 * (c % (uint32_t)p.a_slots), (c / (uint32_t)p.a_slots) & 1u);
+                                ++rows_waited;
+                            }
+                            for (int tx = 0; tx < 3; ++tx, ++bi) {
+                                const uint32_t sb = bi % (uint32_t)p.b_slots;
+                                mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                const uint32_t b0 = smem_b + sb * p.b_slot_bytes;
+                                for (int half = 0; half < p.mh; ++half) {
+                                    const uint32_t sa = (a_base + ty + half) % (uint32_t)p.a_slots;
+                                    const uint32_t a0 = smem_a + sa * p.a_slot_bytes + tx * ROW_BYTES;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma(p.kind, acc0 + half * p.acc_stride,
+                                             umma_desc_sw128(a0 + k * 32, (uint32_t)p.base_off),
+                                             umma_desc_sw128(b0 + k * 32), idesc, (kc | ty | tx | k) != 0);
+                                }
+                                umma_commit(bar_b_empty + 8 * sb);
+                            }
+                            // halo row `ty` is not needed by later taps; the last tap row frees the rest
+                            umma_commit(bar_a_empty + 8 * ((a_base + ty) % (uint32_t)p.a_slots));
+                            if (ty == 2)
+                                for (int r = 3; r < p.mh + 2; ++r)
+                                    umma_commit(bar_a_empty + 8 * ((a_base + r) % (uint32_t)p.a_slots));
+                        }
+                    } else {
+                        for (int tap = 0; tap < p.taps; ++tap, ++ai, ++bi) {
+                            const uint32_t sa = ai % (uint32_t)p.a_slots, sb = bi % (uint32_t)p.b_slots;
+                            mbar_wait(bar_a_full + 8 * sa, (ai / (uint32_t)p.a_slots) & 1u);
+                            mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t b0 = smem_b + sb * p.b_slot_bytes;
+                            for (int half = 0; half < p.mh; ++half) {
+                                const uint32_t a0 = smem_a + sa * p.a_slot_bytes + half * A_BOX_BYTES;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma(p.kind, acc0 + half * p.acc_stride, umma_desc_sw128(a0 + k * 32),
+                                         umma_desc_sw128(b0 + k * 32), idesc, (kc | tap | k) != 0);
+                            }
+                            umma_commit(bar_a_empty + 8 * sa);
+                            umma_commit(bar_b_empty + 8 * sb);
+                        }
+                    }
+                }
+                umma_commit(bar_t_full + 8 * as);   // accumulators complete -> epilogue
+            }
         }
     } else {
         // ---------------------------------- epilogue ----------------------------------
-        mbar_wait(bar_tmem, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int et = threadIdx.x - 96;          // 0..127
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;            // GEMM row = pixel index inside the box
-        const int pw = row % p.bw;
-        const int phh = (row / p.bw) % p.bh;
-        const int pn = row / (p.bw * p.bh);
-        const bool valid = (n0 + pn) < p.B && (h0 + phh) < p.H && (w0 + pw) < p.W;
-        const int64_t pix = ((int64_t)(n0 + pn) * p.H + (h0 + phh)) * p.W + (w0 + pw);
-        float *yrow = p.y + pix * p.ldy;
-        const float *rrow = p.res ? p.res + pix * p.ldr : nullptr;
-        for (int c = 0; c < p.n_tile; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            const int nbase = nt0 + c;
-            if (!valid || nbase >= p.Cout) {
-                // nothing to store for this lane (padding row / padded channels)
-            } else if (p.vec_ok && nbase + 32 <= p.Cout) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 bz = *reinterpret_cast<const float4 *>(p.bias + nbase + j);
-                    float4 o = make_float4(v[j] + bz.x, v[j + 1] + bz.y, v[j + 2] + bz.z, v[j + 3] + bz.w);
-                    if (rrow) {
-                        float4 r = *reinterpret_cast<const float4 *>(rrow + nbase + j);
-                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                    }
-                    *reinterpret_cast<float4 *>(yrow + nbase + j) = o;
+        const bool e0 = et == 0;
+        const uint32_t sw = (uint32_t)(row & 7);
+        uint32_t qn = 0;                          // chunk counter (staging ring position)
+        int cur_n = -1;                           // sample whose statistics sit in sacc
+
+        // residual prefetch cursor (thread e0 only): walks the same (tile, half, chunk) sequence
+        int l_tile = blockIdx.x, l_half = 0, l_cc = 0;
+        uint32_t l_q = 0;
+        auto issue_res_load = [&]() {
+            if (l_tile >= p.total_tiles) return;
+            const int nt0 = (l_tile % p.n_tiles) * p.n_tile;
+            int w0, h0, n0;
+            box_origin(p, l_tile / p.n_tiles, l_half, w0, h0, n0);
+            const uint32_t b = l_q % (uint32_t)p.nbuf;
+            mbar_expect_tx(bar_r_full + 8 * b, STAGE_BUF_BYTES);
+            tma_load_4d(smem_e + b * STAGE_BUF_BYTES, &tmR, bar_r_full + 8 * b, nt0 + l_cc * 32, w0, h0, n0);
+            ++l_q;
+            ++l_cc;
+            if (l_cc == p.nchunks || nt0 + l_cc * 32 >= p.Cout) {
+                l_cc = 0;
+                if (++l_half == p.mh) { l_half = 0; l_tile += gridDim.x; }
+            }
+        };
+        if (p.has_res && e0)
+            for (int i = 0; i < p.nbuf - 1; ++i) issue_res_load();
+
+        auto flush_stats = [&]() {
+            named_bar(2, EPI_THREADS);
+            for (int c = et; c < p.Cout; c += EPI_THREADS) {
+                double *dst = p.stats + ((size_t)cur_n * p.stats_ld + c) * 2;
+                atomicAdd(dst, (double)sacc[0][c]);
+                atomicAdd(dst + 1, (double)sacc[1][c]);
+                sacc[0][c] = 0.f;
+                sacc[1][c] = 0.f;
+            }
+            named_bar(2, EPI_THREADS);
+        };
+
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int as = it % p.acc_stages;
+            const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
+            const int nt0 = (tile % p.n_tiles) * p.n_tile;
+            const int mt = tile / p.n_tiles;
+            mbar_wait(bar_t_full + 8 * as, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int half = 0; half < p.mh; ++half) {
+                int w0, h0, n0;
+                box_origin(p, mt, half, w0, h0, n0);
+                if (p.stats && n0 != cur_n) {
+                    if (cur_n >= 0) flush_stats();
+                    cur_n = n0;
                 }
-            } else {
-                for (int j = 0; j < 32 && nbase + j < p.Cout; ++j) {
-                    float o = v[j] + p.bias[nbase + j];
-                    if (rrow) o += rrow[nbase + j];
-                    yrow[nbase + j] = o;
+                const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                     (uint32_t)((as * p.mh + half) * p.acc_stride);
+                for (int cc = 0; cc < p.nchunks; ++cc, ++qn) {
+                    const int nbase = nt0 + cc * 32;
+                    if (nbase >= p.Cout) break;
+                    const uint32_t b = qn % (uint32_t)p.nbuf;
+                    const uint32_t sbuf = smem_e + b * STAGE_BUF_BYTES;
+                    const uint32_t srow = sbuf + (uint32_t)row * 128u;
+                    float v[32];
+                    tmem_ld32(acc + (uint32_t)(cc * 32), v);
+                    if (p.has_res) mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bz = __ldg(reinterpret_cast<const float4 *>(p.bias + nbase) + j);
+                        float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
+                                               v[4 * j + 3] + bz.w);
+                        const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
+                        if (p.has_res) {
+                            float4 r;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                         : "r"(addr));
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y),
+                                     "f"(o.z), "f"(o.w)
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (!p.has_res && e0) {
+                        // the buffer the NEXT chunk writes must have been read out by its old store
+                        if (p.nbuf == 2) bulk_wait_read<0>(); else bulk_wait_read<2>();
+                    }
+                    named_bar(1, EPI_THREADS);
+                    if (e0) {
+                        tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0);
+                        bulk_commit();
+                        if (p.has_res) {
+                            bulk_wait_read<1>();      // store(qn-1) has drained its buffer -> refill it
+                            issue_res_load();
+                        }
+                    }
+                    if (p.stats) {
+                        const int col = et & 31, rq = et >> 5;
+                        if (nbase + col < p.Cout) {
+                            float s = 0.f, ss = 0.f;
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                const int rr = rq * 32 + r;
+                                const uint32_t addr = sbuf + (uint32_t)rr * 128u +
+                                                      ((((uint32_t)col >> 2) ^ (uint32_t)(rr & 7)) << 4) +
+                                                      (((uint32_t)col & 3u) << 2);
+                                float x;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+                                s += x;
+                                ss = fmaf(x, x, ss);
+                            }
+                            atomicAdd(&sacc[0][nbase + col], s);
+                            atomicAdd(&sacc[1][nbase + col], ss);
+                        }
+                    }
                 }
             }
-            __syncwarp();   // tcgen05.ld is warp-collective: reconverge before the next one
+            // all tcgen05.ld of this tile have completed (wait::ld) -> hand the accumulators back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_t_empty + 8 * as);
         }
+        if (p.stats && cur_n >= 0) flush_stats();
+        if (e0) bulk_wait_read<0>();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)p.tmem_cols)
@@ -299,19 +554,12 @@ PFN_encodeTiled get_encode() {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-int pick_n_tile(int cout_pad) {
-    if (cout_pad % 256 == 0) return 256;
-    if (cout_pad % 192 == 0) return 192;
-    if (cout_pad % 128 == 0) return 128;
-    if (cout_pad % 64 == 0) return 64;
-    return 32;
-}
-
 struct Tiling {
     int bw, bh, bn;
 };
 
-bool pick_tiling(int B, int H, int W, Tiling *t) {
+// 128-pixel boxes {bw, bh, bn}: whole rows first, then rows, then samples.  Power-of-two maps only.
+bool pick_tiling(int H, int W, Tiling *t) {
     int bw;
     if (W >= 128) {
         if (W % 128) return false;
@@ -326,128 +574,290 @@ bool pick_tiling(int B, int H, int W, Tiling *t) {
     t->bw = bw;
     t->bh = bh;
     t->bn = 128 / (bw * bh);
-    (void)B;
     return true;
+}
+
+// tuning overrides (-1 = automatic); set through hl_conv_set_tuning (tests / experiments)
+int g_tune_mh = -1, g_tune_ntile = -1, g_tune_halo = -1, g_tune_epi_stats = -1, g_tune_base_off = -1;
+
+struct Plan {
+    TcParams p;
+    Tiling t;
+    int cout_pad;
+    size_t smem;
+    int grid;
+};
+
+int acc_stride_for(int n_tile) {
+    int s = 32;
+    while (s < n_tile) s <<= 1;
+    return s;
+}
+
+bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, bool has_res,
+               bool want_stats, Plan *pl) {
+    // H, W are OUTPUT dims here
+    Tiling t;
+    if (!pick_tiling(H, W, &t)) return false;
+    const int chunk = kind ? 64 : 32;
+    if (Cin % chunk) return false;
+    TcParams &p = pl->p;
+    p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.stride = stride; p.ksize = ksize;
+    p.taps = ksize * ksize;
+    p.kchunks = Cin / chunk;
+    p.kind = kind;
+    p.bw = t.bw; p.bh = t.bh; p.bn = t.bn;
+    p.tiles_w = W / t.bw;
+    p.tiles_h = H / t.bh;
+    const int tiles_n = (B + t.bn - 1) / t.bn;
+    const int boxes = p.tiles_w * p.tiles_h * tiles_n;
+    const int cout_pad = hl_conv_cout_pad(Cout);
+    pl->cout_pad = cout_pad;
+    pl->t = t;
+    const int sms = hl_num_sms();
+
+    bool halo_ok = ksize == 3 && stride == 1 && W % 128 == 0;
+    int halo = halo_ok ? 1 : 0;
+    if (g_tune_halo >= 0) halo = halo_ok && g_tune_halo;
+
+    // halves per CTA tile: 2 shares each weight tile between two 128-pixel boxes
+    int mh = 1;
+    if (halo ? (H % 2 == 0) : (boxes % 2 == 0)) mh = 2;
+    if (g_tune_mh == 1) mh = 1;
+    if (g_tune_mh == 2 && !(halo ? (H % 2 == 0) : (boxes % 2 == 0))) mh = 1;
+
+    // (mh, n_tile): the largest legal UMMA N dividing cout_pad that still yields at least one CTA tile
+    // per SM, preferring two halves per CTA; problems too small to fill the machine take mh = 1 and
+    // a narrow tile (more CTAs = more TMA streams for their long, weight-bound K loops)
+    static const int cand[] = {256, 192, 128, 96, 64, 32};
+    int n_tile = 0;
+    const int mh_max = mh;
+    for (int m = mh_max; m >= 1 && n_tile == 0; --m) {
+        if (g_tune_mh == 2 && m != mh_max) break;
+        for (int c : cand) {
+            if (cout_pad % c || m * acc_stride_for(c) > 512) continue;
+            if ((boxes / m) * (cout_pad / c) >= sms) { n_tile = c; mh = m; break; }
+        }
+    }
+    if (n_tile == 0) {
+        mh = (g_tune_mh == 2) ? mh_max : 1;
+        n_tile = cout_pad % 64 == 0 ? 64 : 32;
+    }
+    if (g_tune_ntile > 0 && cout_pad % g_tune_ntile == 0 && g_tune_ntile % 32 == 0 && g_tune_ntile <= 256 &&
+        mh * acc_stride_for(g_tune_ntile) <= 512)
+        n_tile = g_tune_ntile;
+
+    p.halo = halo;
+    p.base_off = g_tune_base_off == 0 ? 0 : 1;
+    p.mh = mh;
+    p.hp = halo ? H / mh : 1;
+    p.n_tile = n_tile;
+    p.n_tiles = cout_pad / n_tile;
+    p.nchunks = n_tile / 32;
+    p.total_tiles = (boxes / mh) * p.n_tiles;
+    p.acc_stride = acc_stride_for(n_tile);
+    p.acc_stages = 512 / (mh * p.acc_stride) >= 2 ? 2 : 1;
+    int cols = 32;
+    while (cols < p.acc_stages * mh * p.acc_stride) cols <<= 1;
+    p.tmem_cols = cols;
+
+    // shared-memory budget: staging ring, then A slots, the rest to B slots
+    const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/;
+    p.b_slot_bytes = n_tile * ROW_BYTES;
+    p.has_res = has_res ? 1 : 0;
+    int nbuf = has_res ? 4 : 2;
+    for (;;) {
+        int rest = budget - nbuf * STAGE_BUF_BYTES;
+        if (halo) {
+            p.a_slot_bytes = HALO_SLOT_BYTES;
+            p.a_slots = mh + 3;
+            int b_slots = (rest - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+            if (b_slots < 3 && p.a_slots > mh + 2) {
+                p.a_slots = mh + 2;
+                b_slots = (rest - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+            }
+            p.b_slots = b_slots > MAX_SLOTS ? MAX_SLOTS : b_slots;
+        } else {
+            p.a_slot_bytes = mh * A_BOX_BYTES;
+            int stages = rest / (p.a_slot_bytes + p.b_slot_bytes);
+            if (stages > MAX_SLOTS) stages = MAX_SLOTS;
+            p.a_slots = p.b_slots = stages;
+        }
+        if (p.b_slots >= 3 || nbuf == 2) break;
+        nbuf = 2;                      // trade residual prefetch depth for pipeline depth
+    }
+    if (p.b_slots < 2 || p.a_slots < (halo ? mh + 2 : 2)) return false;
+    p.nbuf = nbuf;
+    pl->smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes +
+               (size_t)nbuf * STAGE_BUF_BYTES + 1024;
+
+    p.stats = nullptr;     // filled by the caller when the epilogue computes the statistics
+    p.stats_ld = 0;
+    pl->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    (void)want_stats;
+    return true;
+}
+
+// in-epilogue GroupNorm statistics need one sample per 128-pixel box (every box row valid)
+bool plan_epi_stats(const Plan &pl, bool want_stats) {
+    if (!want_stats || g_tune_epi_stats == 0) return false;
+    return pl.t.bn == 1 && pl.cout_pad <= STATS_MAX_C;
 }
 
 }  // namespace
 
 extern "C" int hl_conv_cout_pad(int Cout) { return (Cout + 31) / 32 * 32; }
 
-bool hl_conv_tc_applicable(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int ldx,
-                           int flags) {
+extern "C" int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, int base_off) {
+    g_tune_base_off = base_off;
+    g_tune_mh = mh;
+    g_tune_ntile = n_tile;
+    g_tune_halo = halo;
+    g_tune_epi_stats = epi_stats;
+    return HL_OK;
+}
+
+bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                           int ldx, int ldy, int flags) {
     if (flags & (HL_CONV_FORCE_SIMT | HL_CONV_UPSAMPLE2X)) return false;
-    if (stride != 1 || (ksize != 1 && ksize != 3)) return false;
-    if (Cin % 32 || ldx % 4 || Cin > ldx) return false;
-    if ((int64_t)B * H * W < 128) return false;     // tiny maps: the fp32 kernel is as fast
-    Tiling t;
-    if (!pick_tiling(B, H, W, &t)) return false;
-    (void)Cout;
+    if ((stride != 1 && stride != 2) || (ksize != 1 && ksize != 3)) return false;
+    if (stride == 2 && (ksize != 3 || (H % 2) || (W % 2))) return false;
+    if (x_dtype == HL_DT_F32 && !(flags & HL_CONV_TF32)) return false;
+    const int esz = x_dtype == HL_DT_F16 ? 2 : 4;
+    if ((ldx * esz) % 16 || Cin > ldx || ldy % 4) return false;
+    Plan pl;
+    if (!make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, false, false,
+                   &pl))
+        return false;
     return get_encode() != nullptr;
 }
 
-int hl_conv2d_tc(const float *x, int ldx, const float *wpk, const float *bias, const float *residual,
-                 int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
-                 cudaStream_t stream) {
+int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
+                       cudaStream_t stream);
+
+int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+                 const float *residual, int ldr, float *y, int ldy, double *stats, int stats_ld, int B,
+                 int Hin, int Win, int Cin, int Cout, int ksize, int stride, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) {
         hl_set_error("cuTensorMapEncodeTiled unavailable");
         return HL_E_CUDA;
     }
-    Tiling t;
-    HL_CHECK_ARG(pick_tiling(B, H, W, &t));
-    HL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && bias != nullptr);
-    const int cout_pad = hl_conv_cout_pad(Cout);
-    TcParams p;
-    p.taps = ksize * ksize;
-    p.ksize = ksize;
-    p.kchunks_per_tap = Cin / BLOCK_K;
-    p.n_tile = pick_n_tile(cout_pad);
-    const int b_stage = p.n_tile * BLOCK_K * 4;
-    int stages = (227 * 1024 - 1024 - 1024) / (A_STAGE_BYTES + b_stage);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    const int total_chunks = p.taps * p.kchunks_per_tap;
-    if (stages > total_chunks) stages = total_chunks;
-    if (stages < 1) stages = 1;
-    p.stages = stages;
-    int cols = 32;
-    while (cols < p.n_tile) cols <<= 1;
-    p.tmem_cols = cols;
-    p.bw = t.bw; p.bh = t.bh; p.bn = t.bn;
-    p.tiles_w = W / t.bw;
-    p.tiles_h = H / t.bh;
-    const int tiles_n = (B + t.bn - 1) / t.bn;
-    p.B = B; p.H = H; p.W = W; p.Cout = Cout;
-    p.bias = bias; p.res = residual; p.ldr = ldr; p.y = y; p.ldy = ldy;
-    p.vec_ok = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (((uintptr_t)bias & 15) == 0) &&
-               (!residual || (ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0));
+    const int kind = x_dtype == HL_DT_F16 ? 1 : 0;
+    const int esz = kind ? 2 : 4;
+    const int chunk = kind ? 64 : 32;
+    const int H = Hin / stride, W = Win / stride;
+    Plan pl;
+    HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl));
+    HL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+                 bias != nullptr && ((uintptr_t)bias & 15) == 0);
+    HL_CHECK_ARG(!residual || (((uintptr_t)residual & 15) == 0 && ldr % 4 == 0));
+    TcParams &p = pl.p;
+    p.bias = bias;
+    const bool epi_stats = plan_epi_stats(pl, stats != nullptr);
+    if (epi_stats) {
+        p.stats = stats;
+        p.stats_ld = stats_ld;
+    }
+    const CUtensorMapDataType dt = kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmY, tmR;
     {
-        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-        cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)t.bw, (cuuint32_t)t.bh, (cuuint32_t)t.bn};
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)Win * ldx * esz,
+                              (cuuint64_t)Hin * Win * ldx * esz};
+        cuuint32_t box[4], estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        if (p.halo) {
+            box[0] = chunk; box[1] = HALO_PIX; box[2] = 1; box[3] = 1;
+        } else {
+            box[0] = chunk; box[1] = pl.t.bw * stride; box[2] = pl.t.bh * stride; box[3] = pl.t.bn;
+        }
+        CUresult r = encode(&tmA, dt, 4, (void *)x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            hl_set_error("cuTensorMapEncodeTiled(A) failed: %d (B=%d H=%d W=%d Cin=%d ldx=%d stride=%d halo=%d)",
+                         (int)r, B, Hin, Win, Cin, ldx, stride, p.halo);
+            return HL_E_CUDA;
+        }
+    }
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)pl.cout_pad, (cuuint64_t)p.taps};
+        cuuint64_t gstr[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)pl.cout_pad * Cin * esz};
+        cuuint32_t box[3] = {(cuuint32_t)chunk, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, dt, 3, (void *)wpk, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            hl_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cin=%d Cout_pad=%d taps=%d)", (int)r, Cin,
+                         pl.cout_pad, p.taps);
+            return HL_E_CUDA;
+        }
+    }
+    for (int which = 0; which < 2; ++which) {
+        const float *ptr = which ? residual : y;
+        const int ld = which ? ldr : ldy;
+        CUtensorMap *tm = which ? &tmR : &tmY;
+        if (!ptr) { *tm = tmY; continue; }
+        cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
+        if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)x, gdim, gstr, box, estr,
+        CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr, gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
-            hl_set_error("cuTensorMapEncodeTiled(A) failed: %d (B=%d H=%d W=%d Cin=%d ldx=%d)", (int)r, B,
-                         H, W, Cin, ldx);
+            hl_set_error("cuTensorMapEncodeTiled(%s) failed: %d (B=%d H=%d W=%d Cout=%d ld=%d)",
+                         which ? "residual" : "output", (int)r, B, H, W, Cout, ld);
             return HL_E_CUDA;
         }
     }
-    {
-        cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)cout_pad, (cuuint64_t)p.taps};
-        cuuint64_t gstr[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)cout_pad * Cin * 4};
-        cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.n_tile, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)wpk, gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            hl_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cin=%d Cout_pad=%d taps=%d)", (int)r, Cin,
-                         cout_pad, p.taps);
-            return HL_E_CUDA;
-        }
-    }
-    const size_t smem = (size_t)p.stages * (A_STAGE_BYTES + b_stage) + 1024;
     static bool smem_configured = false;
     if (!smem_configured) {
-        // 227 KB per CTA minus the kernel's static shared memory (barriers + TMEM slot)
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024 - 1024));
+                                           DYN_SMEM_MAX));
         smem_configured = true;
     }
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, cout_pad / p.n_tile);
-    k_conv_tc<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+    HL_CHECK_ARG(pl.smem <= (size_t)DYN_SMEM_MAX);
+    k_conv_tc<<<pl.grid, NUM_THREADS, pl.smem, stream>>>(tmA, tmB, tmY, tmR, p);
     HL_CHECK_LAUNCH();
+    if (stats && !epi_stats) return hl_gn_stats_launch(y, ldy, B, H * W, Cout, stats, stats_ld, stream);
     return HL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // public entry: dispatch
 // ---------------------------------------------------------------------------------------------
-int hl_conv2d_simt(const float *x, int ldx, const float *wpk, const float *bias, const float *residual,
-                   int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize,
-                   int stride, int flags, cudaStream_t stream);
+int hl_conv2d_simt(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+                   const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout,
+                   int ksize, int stride, int flags, cudaStream_t stream);
 
-extern "C" int hl_conv2d_uses_tensor_cores(int B, int H, int W, int Cin, int Cout, int ksize,
-                                           int stride, int ldx, int flags) {
-    return hl_conv_tc_applicable(B, H, W, Cin, Cout, ksize, stride, ldx, flags) ? 1 : 0;
+extern "C" int hl_conv2d_uses_tensor_cores(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize,
+                                           int stride, int ldx, int ldy, int flags) {
+    return hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags) ? 1 : 0;
 }
 
-extern "C" int hl_conv2d(const float *x, int ldx, const float *wpk, const float *bias,
-                         const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin,
-                         int Cout, int ksize, int stride, int flags, void *stream) {
+extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+                         const float *residual, int ldr, float *y, int ldy, double *stats, int stats_ld,
+                         int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
+                         void *stream) {
     HL_CHECK_ARG(x && wpk && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+    HL_CHECK_ARG(x_dtype == HL_DT_F32 || x_dtype == HL_DT_F16);
     HL_CHECK_ARG(ksize == 1 || ksize == 3);
     HL_CHECK_ARG(stride == 1 || stride == 2);
     HL_CHECK_ARG(ldx >= Cin && ldy >= Cout && (!residual || ldr >= Cout));
     HL_CHECK_ARG(!((flags & HL_CONV_UPSAMPLE2X) && stride != 1));
-    if (hl_conv_tc_applicable(B, H, W, Cin, Cout, ksize, stride, ldx, flags))
-        return hl_conv2d_tc(x, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize,
-                            (cudaStream_t)stream);
-    return hl_conv2d_simt(x, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize, stride,
-                          flags, (cudaStream_t)stream);
+    HL_CHECK_ARG(!stats || stats_ld >= Cout);
+    if (hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags))
+        return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin,
+                            Cout, ksize, stride, (cudaStream_t)stream);
+    int rc = hl_conv2d_simt(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize, stride,
+                            flags, (cudaStream_t)stream);
+    if (rc != HL_OK || !stats) return rc;
+    const int ups = (flags & HL_CONV_UPSAMPLE2X) ? 2 : 1;
+    const int pad = ksize / 2;
+    const int Ho = (H * ups + 2 * pad - ksize) / stride + 1, Wo = (W * ups + 2 * pad - ksize) / stride + 1;
+    return hl_gn_stats_launch(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
 }

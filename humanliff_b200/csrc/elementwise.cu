@@ -3,8 +3,7 @@
 // grids sized in multiples of the SM count.
 #include "common.cuh"
 
-#include <mutex>
-#include <string>
+#include <cuda_fp16.h>
 
 // ------------------------------------------------------------------------------------------
 // diagnostics
@@ -34,6 +33,23 @@ int hl_num_sms() {
     return g_num_sms;
 }
 
+// store 4 consecutive channels of an operand buffer: fp32 (optionally TF32-rounded) or fp16
+__device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, float4 v, int round_tf32) {
+    if (dtype == HL_DT_F16) {
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t *>(&lo);
+        u.y = *reinterpret_cast<uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + idx) = u;
+    } else {
+        if (round_tf32) {
+            v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
+            v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
+        }
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dst) + idx) = v;
+    }
+}
+
 static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
     int64_t g = (work_items + per_block - 1) / per_block;
     int64_t cap = (int64_t)hl_num_sms() * max_waves;
@@ -47,7 +63,7 @@ static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8)
 // both the NCHW side (contiguous pixels) and the NHWC side (contiguous channels) are coalesced.
 // ------------------------------------------------------------------------------------------
 __global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__restrict__ src2,
-                               float *__restrict__ dst, int C, int HW, int ld, int round_tf32,
+                               void *__restrict__ dst, int dst_dtype, int C, int HW, int ld, int round_tf32,
                                int64_t n_tiles, int tiles_per_img) {
     __shared__ float tile[32][33];
     for (int64_t tidx = blockIdx.x; tidx < n_tiles; tidx += gridDim.x) {
@@ -70,7 +86,9 @@ __global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__res
                 int c = c0 + threadIdx.x, p = p0 + py;
                 if (c < ld && p < HW) {
                     float v = tile[threadIdx.x][py];
-                    dst[((int64_t)b * HW + p) * ld + c] = round_tf32 ? hl_rna_tf32(v) : v;
+                    const int64_t o = ((int64_t)b * HW + p) * ld + c;
+                    if (dst_dtype == HL_DT_F16) reinterpret_cast<__half *>(dst)[o] = __float2half_rn(v);
+                    else reinterpret_cast<float *>(dst)[o] = round_tf32 ? hl_rna_tf32(v) : v;
                 }
             }
             __syncthreads();
@@ -78,14 +96,14 @@ __global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__res
     }
 }
 
-extern "C" int hl_nchw_to_nhwc(const float *src, const float *src2, float *dst, int B, int C,
+extern "C" int hl_nchw_to_nhwc(const float *src, const float *src2, void *dst, int dst_dtype, int B, int C,
                                int HW, int ld, int round_tf32, void *stream) {
     HL_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && ld >= C);
     int tiles_per_img = hl_cdiv(HW, 32);
     int64_t n_tiles = (int64_t)B * tiles_per_img;
     dim3 blk(32, 8);
     k_nchw_to_nhwc<<<grid_for(n_tiles, 1, 16), blk, 0, (cudaStream_t)stream>>>(
-        src, src2, dst, C, HW, ld, round_tf32, n_tiles, tiles_per_img);
+        src, src2, dst, dst_dtype, C, HW, ld, round_tf32, n_tiles, tiles_per_img);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -162,7 +180,7 @@ extern "C" int hl_concat_add(const float *a, int lda, int C1, const float *b, in
     return HL_OK;
 }
 
-__global__ void k_upsample2x(const float *__restrict__ src, int lds, float *__restrict__ dst,
+__global__ void k_upsample2x(const float *__restrict__ src, int lds, void *__restrict__ dst, int dst_dtype,
                              int ldd, int H, int W, int C, int round_tf32, int64_t total) {
     int q = C >> 2, W2 = 2 * W, H2 = 2 * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -175,26 +193,22 @@ __global__ void k_upsample2x(const float *__restrict__ src, int lds, float *__re
         int64_t b = r / H2;
         int64_t sp = (b * H + (oy >> 1)) * W + (ox >> 1);
         float4 v = *reinterpret_cast<const float4 *>(src + sp * lds + 4 * j);
-        if (round_tf32) {
-            v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
-            v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
-        }
-        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
+        store_quad(dst, dst_dtype, p * ldd + 4 * j, v, round_tf32);
     }
 }
 
-extern "C" int hl_upsample2x(const float *src, int lds, float *dst, int ldd, int B, int H, int W,
+extern "C" int hl_upsample2x(const float *src, int lds, void *dst, int dst_dtype, int ldd, int B, int H, int W,
                              int C, int round_tf32, void *stream) {
     HL_CHECK_ARG(src && dst && B > 0 && H > 0 && W > 0 && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0);
     int64_t total = (int64_t)B * 4 * H * W * (C / 4);
-    k_upsample2x<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, H, W,
-                                                                             C, round_tf32, total);
+    k_upsample2x<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, dst_dtype, ldd, H,
+                                                                             W, C, round_tf32, total);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
-__global__ void k_round_tf32(const float *__restrict__ src, int lds, float *__restrict__ dst,
-                             int ldd, int C, int64_t npix) {
+__global__ void k_cast_operand(const float *__restrict__ src, int lds, void *__restrict__ dst, int dst_dtype,
+                               int ldd, int C, int64_t npix, int round_tf32) {
     int q = C >> 2;
     int64_t total = npix * q;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -202,18 +216,23 @@ __global__ void k_round_tf32(const float *__restrict__ src, int lds, float *__re
         int64_t p = i / q;
         int j = (int)(i - p * q);
         float4 v = *reinterpret_cast<const float4 *>(src + p * lds + 4 * j);
-        v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
-        v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
-        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
+        store_quad(dst, dst_dtype, p * ldd + 4 * j, v, round_tf32);
     }
 }
 
-extern "C" int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int C, int64_t npix,
-                             void *stream) {
+extern "C" int hl_cast_operand(const float *src, int lds, void *dst, int dst_dtype, int ldd, int C,
+                               int64_t npix, int round_tf32, void *stream) {
     HL_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && npix > 0);
-    k_round_tf32<<<grid_for(npix * (C / 4), 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst,
-                                                                                      ldd, C, npix);
+    HL_CHECK_ARG(dst_dtype == HL_DT_F32 || dst_dtype == HL_DT_F16);
+    k_cast_operand<<<grid_for(npix * (C / 4), 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, dst_dtype,
+                                                                                        ldd, C, npix, round_tf32);
     HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+extern "C" int hl_zero(void *ptr, int64_t bytes, void *stream) {
+    HL_CHECK_ARG(ptr && bytes >= 0);
+    HL_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
     return HL_OK;
 }
 
@@ -302,14 +321,17 @@ extern "C" int hl_linear_small(const float *x, const float *W, const float *bias
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm32.  stats: each block owns a slab of pixels of one sample, each thread a fixed
-// channel quad (so loads are 128-bit and coalesced across the block), per-channel partials are
-// folded to groups in shared memory and added to the [B, G, 2] fp64 accumulators (fp64 atomics
-// make the result independent of arrival order to well below fp32 resolution).
+// GroupNorm32.  Statistics are kept PER CHANNEL (sum, sum of squares, fp64) so that they can be
+// produced by whoever writes the tensor (the tcgen05 conv epilogue, or k_gn_stats below) and folded
+// into any group layout by the consumer -- including groups straddling the two halves of the
+// decoder's never-materialised concat.
+// stats kernel: each block owns a slab of pixels of one sample, each thread a fixed channel quad
+// (128-bit coalesced loads); per-channel partials are combined in shared memory and added to the
+// fp64 accumulators (fp64 atomics: arrival order changes the result far below fp32 resolution).
 // ------------------------------------------------------------------------------------------
 #define GN_MAX_C 2048
-__global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int groups,
-                           int pix_per_block, double *__restrict__ sums) {
+__global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int pix_per_block,
+                           double *__restrict__ stats, int stats_ld) {
     __shared__ float s_sum[GN_MAX_C];
     __shared__ float s_sq[GN_MAX_C];
     int b = blockIdx.y;
@@ -335,19 +357,17 @@ __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, 
         atomicAdd(&s_sum[4 * tq + 3], s.w); atomicAdd(&s_sq[4 * tq + 3], ss.w);
     }
     __syncthreads();
-    int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double a = 0.0, a2 = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)s_sum[c]; a2 += (double)s_sq[c]; }
-        atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 0], a);
-        atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 1], a2);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double *dst = stats + ((int64_t)b * stats_ld + c) * 2;
+        atomicAdd(dst, (double)s_sum[c]);
+        atomicAdd(dst + 1, (double)s_sq[c]);
     }
 }
 
-extern "C" int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, int groups, double *sums,
-                           void *stream) {
-    HL_CHECK_ARG(x && sums && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C && groups > 0);
-    HL_CHECK_ARG(C % groups == 0 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C);
+int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
+                       cudaStream_t stream) {
+    HL_CHECK_ARG(x && stats && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C);
+    HL_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && ldx >= C && stats_ld >= C);
     int q = C / 4;
     HL_CHECK_ARG(q <= 512);
     int threads = (512 / q) * q;   // largest multiple of q not above 512
@@ -359,33 +379,46 @@ extern "C" int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, int gr
     int min_ppb = lanes_p * 8;
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    HL_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * groups, (cudaStream_t)stream));
-    k_gn_stats<<<grid, threads, 0, (cudaStream_t)stream>>>(x, ldx, HW, C, groups, pix_per_block, sums);
+    k_gn_stats<<<grid, threads, 0, stream>>>(x, ldx, HW, C, pix_per_block, stats, stats_ld);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
+extern "C" int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
+                           void *stream) {
+    return hl_gn_stats_launch(x, ldx, B, HW, C, stats, stats_ld, (cudaStream_t)stream);
+}
+
 // apply: y = act(x * A[b,c] + Bc[b,c]) where A, Bc fold mean/rstd/gamma/beta and the FiLM
-// scale/shift; A and Bc are built per block in shared memory from the fp64 sums.
-__global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *__restrict__ sums,
-                           const float *__restrict__ gamma, const float *__restrict__ beta,
-                           const float *__restrict__ film, int film_ld, float *__restrict__ y,
-                           int ldy, int HW, int C, int groups, float eps, int silu, int round_tf32,
-                           int pix_per_block) {
+// scale/shift; A and Bc are built per block in shared memory from the per-channel fp64 sums.
+// Each thread walks (pixel, channel-quad) pairs with an incrementally updated index (no divisions
+// in the loop); loads are 128-bit, stores 64-bit (fp16 operand) or 128-bit (fp32 operand).
+__global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *__restrict__ stats,
+                           int stats_ld, const float *__restrict__ gamma, const float *__restrict__ beta,
+                           const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
+                           int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
+                           int silu, int round_tf32, int pix_per_block) {
     __shared__ float sA[GN_MAX_C];
     __shared__ float sB[GN_MAX_C];
+    __shared__ float gmean[64], grstd[64];
     int b = blockIdx.y;
     int cpg = C / groups;
     double n = (double)HW * cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double a = 0.0, a2 = 0.0;
+        const double *st = stats + ((int64_t)b * stats_ld + g * cpg) * 2;
+        for (int c = 0; c < cpg; ++c) { a += st[2 * c]; a2 += st[2 * c + 1]; }
+        double m = a / n;
+        double var = a2 / n - m * m;
+        if (var < 0.0) var = 0.0;
+        gmean[g] = (float)m;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         int g = c / cpg;
-        double m = sums[((int64_t)b * groups + g) * 2 + 0] / n;
-        double var = sums[((int64_t)b * groups + g) * 2 + 1] / n - m * m;
-        if (var < 0.0) var = 0.0;
-        float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        float mean = (float)m;
-        float ga = gamma[c] * rstd;
-        float be = beta[c] - mean * ga;
+        float ga = gamma[c] * grstd[g];
+        float be = beta[c] - gmean[g] * ga;
         if (film) {
             float sc = 1.0f + film[(int64_t)b * film_ld + c];
             float sh = film[(int64_t)b * film_ld + C + c];
@@ -396,44 +429,47 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
         sB[c] = be;
     }
     __syncthreads();
-    int q = C >> 2;
-    int p0 = blockIdx.x * pix_per_block;
-    int np = min(HW, p0 + pix_per_block) - p0;
-    int64_t total = (int64_t)np * q;
-    const float *xb = x + ((int64_t)b * HW + p0) * ldx;
-    float *yb = y + ((int64_t)b * HW + p0) * ldy;
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-        int p = (int)(i / q);
-        int j = (int)(i - (int64_t)p * q);
-        float4 v = *reinterpret_cast<const float4 *>(xb + (int64_t)p * ldx + 4 * j);
-        float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
-        float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
-        v.x = fmaf(v.x, a.x, c.x); v.y = fmaf(v.y, a.y, c.y);
-        v.z = fmaf(v.z, a.z, c.z); v.w = fmaf(v.w, a.w, c.w);
-        if (silu) { v.x = hl_silu(v.x); v.y = hl_silu(v.y); v.z = hl_silu(v.z); v.w = hl_silu(v.w); }
-        if (round_tf32) {
-            v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
-            v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
-        }
-        *reinterpret_cast<float4 *>(yb + (int64_t)p * ldy + 4 * j) = v;
+    const int q = C >> 2;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int np = min(HW, p0 + pix_per_block) - p0;
+    const int64_t pix0 = (int64_t)b * HW + p0;
+    const int dp = blockDim.x / q, dj = blockDim.x % q;
+    int p = threadIdx.x / q, j = threadIdx.x % q;
+    while (p < np) {
+        const int64_t pix = pix0 + p;
+        const float4 v = *reinterpret_cast<const float4 *>(x + pix * ldx + 4 * j);
+        const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
+        const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
+        float4 o;
+        o.x = fmaf(v.x, a.x, c.x); o.y = fmaf(v.y, a.y, c.y);
+        o.z = fmaf(v.z, a.z, c.z); o.w = fmaf(v.w, a.w, c.w);
+        if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
+        store_quad(y, y_dtype, pix * ldy + 4 * j, o, round_tf32);
+        if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, round_tf32);
+        p += dp;
+        j += dj;
+        if (j >= q) { j -= q; ++p; }
     }
 }
 
-extern "C" int hl_gn_apply(const float *x, int ldx, const double *sums, const float *gamma,
-                           const float *beta, const float *film, int film_ld, float *y, int ldy,
-                           int B, int HW, int C, int groups, float eps, int silu, int round_tf32,
-                           void *stream) {
-    HL_CHECK_ARG(x && sums && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C);
-    HL_CHECK_ARG(C % groups == 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
+extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma,
+                           const float *beta, const float *film, int film_ld, void *y, int y_dtype, int ldy,
+                           void *raw, int ldraw, int B, int HW, int C, int groups, float eps, int silu,
+                           int round_tf32, void *stream) {
+    HL_CHECK_ARG(x && stats && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C);
+    HL_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 &&
+                 ldx >= C && ldy >= C && stats_ld >= C);
+    HL_CHECK_ARG(y_dtype == HL_DT_F32 || y_dtype == HL_DT_F16);
+    HL_CHECK_ARG(!raw || (ldraw % 4 == 0 && ldraw >= C));
     int64_t want_blocks = (int64_t)hl_num_sms() * 8 / B;
     if (want_blocks < 1) want_blocks = 1;
     int pix_per_block = hl_cdiv(HW, want_blocks);
     int min_ppb = hl_cdiv(256 * 4 * 4, C / 4);  // >= 4 float4 per thread
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    k_gn_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, sums, gamma, beta, film, film_ld, y,
-                                                       ldy, HW, C, groups, eps, silu, round_tf32,
-                                                       pix_per_block);
+    k_gn_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
+                                                       y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu,
+                                                       round_tf32, pix_per_block);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

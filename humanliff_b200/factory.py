@@ -22,7 +22,7 @@ def model_and_diffusion_defaults():
 
 def create_model(image_size, in_channels, num_channels, out_channels, num_res_blocks, learn_sigma,
                  class_cond, use_checkpoint, attention_resolutions, num_heads, num_heads_upsample,
-                 use_scale_shift_norm, cond_type, use_3d_aware, dropout, precision="tf32"):
+                 use_scale_shift_norm, cond_type, use_3d_aware, dropout, precision="fp16"):
     if image_size not in _CHANNEL_MULT:
         raise ValueError(f"unsupported image size: {image_size}")
     attention_ds = tuple(image_size // int(res) for res in attention_resolutions.split(","))
@@ -61,7 +61,7 @@ def create_model_and_diffusion(image_size, class_cond, learn_sigma, sigma_small,
                                attention_resolutions, dropout, diffusion_steps, noise_schedule,
                                timestep_respacing, use_kl, predict_xstart, rescale_timesteps,
                                rescale_learned_sigmas, use_checkpoint, use_scale_shift_norm, cond_type,
-                               use_3d_aware, precision="tf32"):
+                               use_3d_aware, precision="fp16"):
     """The 23 keyword flags of script_util.py:42-66 (+ ``precision``); returns (model, diffusion)."""
     model = create_model(image_size, in_channels, num_channels, out_channels, num_res_blocks,
                          learn_sigma=learn_sigma, class_cond=class_cond, use_checkpoint=use_checkpoint,

@@ -12,9 +12,13 @@
  *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it,
  *     nothing synchronises, nothing allocates (safe under CUDA-graph capture);
  *   - return value 0 = ok, negative = HL_E_*; hl_last_error() gives the text;
- *   - activations are NHWC fp32 ("pixel-major"): element (b, y, x, c) lives at
- *     ptr[((b*H + y)*W + x)*ld + c], `ld` (floats) >= C is the pixel pitch so a
- *     tensor may be a channel slice of a wider (concat) buffer.
+ *   - activations are NHWC ("pixel-major"): element (b, y, x, c) lives at
+ *     ptr[((b*H + y)*W + x)*ld + c], `ld` (elements) >= C is the pixel pitch so a
+ *     tensor may be a channel slice of a wider (concat) buffer.  The residual
+ *     stream and every conv result are fp32; conv OPERANDS (the activated /
+ *     normalised tensors a conv reads, and the packed weights) are HL_DT_F16 or
+ *     HL_DT_F32 buffers -- the rounding to the operand type is the only place
+ *     precision is given up (fp32 accumulation everywhere).
  */
 #ifndef HUMANLIFF_B200_H
 #define HUMANLIFF_B200_H
@@ -30,33 +34,48 @@ extern "C" {
 #define HL_E_CUDA (-2)      /* a CUDA runtime / driver call failed          */
 #define HL_E_UNSUPPORTED (-3)
 
+/* element types of activation / weight OPERAND buffers (results and the residual stream are fp32) */
+#define HL_DT_F32 0   /* fp32; the tensor-core path reads it as TF32 (caller rounds with cvt.rna)   */
+#define HL_DT_F16 1   /* IEEE fp16: 11-bit significand like TF32, half the bytes, 2x the MMA rate   */
+
 /* hl_conv2d flags */
 #define HL_CONV_FORCE_SIMT 1   /* use the fp32 CUDA-core kernel even where the tcgen05 path applies */
 #define HL_CONV_UPSAMPLE2X 2   /* input is read through a nearest x2 upsample (unet.py:77)          */
+#define HL_CONV_TF32 4         /* fp32 operands may go through tcgen05 kind::tf32                   */
 
 int hl_version(void);
 const char *hl_last_error(void);
 /* 1 if the tcgen05 (tensor-core) kernel would be used for this conv shape. */
-int hl_conv2d_uses_tensor_cores(int B, int H, int W, int Cin, int Cout, int ksize, int stride,
-                                int ldx, int flags);
+int hl_conv2d_uses_tensor_cores(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                int ldx, int ldy, int flags);
+/* Experiment / test hook for the tcgen05 conv: force halves per CTA (mh 1|2), the N tile, HALO
+ * operand reuse (0|1), in-epilogue GroupNorm statistics (0|1), descriptor base_offset (0|1);
+ * -1 = automatic.  Process-wide; not part of the reference-facing surface.                      */
+int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, int base_off);
 
 /* ---- layout / elementwise ------------------------------------------------------------------ */
 
-/* NCHW -> NHWC with zero channel padding up to ld; optional second addend (h_cond = x + x_cond,
- * unet.py:596); optional TF32 round-to-nearest of the result (operand of the stem conv).        */
-int hl_nchw_to_nhwc(const float *src, const float *src2 /*nullable*/, float *dst, int B, int C,
-                    int HW, int ld, int round_tf32, void *stream);
-/* NHWC (pitch ld) -> NCHW.                                                                      */
+/* NCHW fp32 -> NHWC (dst_dtype) with zero channel padding up to ld; optional second addend
+ * (h_cond = x + x_cond, unet.py:596); for HL_DT_F32 optional TF32 round-to-nearest.              */
+int hl_nchw_to_nhwc(const float *src, const float *src2 /*nullable*/, void *dst, int dst_dtype, int B,
+                    int C, int HW, int ld, int round_tf32, void *stream);
+/* NHWC fp32 (pitch ld) -> NCHW fp32.                                                             */
 int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW, void *stream);
 /* dst[:, 0:C1] = a ; dst[:, C1:C1+C2] = b (+ c)   -- th.cat([h, hs.pop()+hs_cond.pop()], 1),
  * unet.py:606.  Any of the three sources may alias a slice of another buffer via its pitch.     */
 int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb, const float *c /*nullable*/,
                   int ldc, int C2, float *dst, int ldd, int64_t npix, void *stream);
-/* nearest x2 upsample, F.interpolate(scale_factor=2, mode="nearest"), unet.py:77               */
-int hl_upsample2x(const float *src, int lds, float *dst, int ldd, int B, int H, int W, int C,
-                  int round_tf32, void *stream);
-/* dst = rna_tf32(src) (operand staging for raw residual-stream inputs of 1x1 convs)             */
-int hl_round_tf32(const float *src, int lds, float *dst, int ldd, int C, int64_t npix, void *stream);
+/* nearest x2 upsample of the fp32 residual stream into an operand buffer,
+ * F.interpolate(scale_factor=2, mode="nearest"), unet.py:77                                     */
+int hl_upsample2x(const float *src, int lds, void *dst, int dst_dtype, int ldd, int B, int H, int W,
+                  int C, int round_tf32, void *stream);
+/* dst = operand copy of the fp32 tensor src: fp16 (round-to-nearest-even) or TF32-rounded fp32 --
+ * staging for convs that read the raw residual stream (1x1 skips, projections, down-sampling)   */
+int hl_cast_operand(const float *src, int lds, void *dst, int dst_dtype, int ldd, int C, int64_t npix,
+                    int round_tf32, void *stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes): one call per step zeroes every GroupNorm statistics buffer.     */
+int hl_zero(void *ptr, int64_t bytes, void *stream);
 
 /* ---- embeddings (nn.py:103-121, unet.py:366-373,564,584-586,151-157,200) --------------------- */
 
@@ -72,35 +91,46 @@ int hl_linear_small(const float *x, const float *W, const float *bias, float *y,
 
 /* ---- GroupNorm32 + SiLU + FiLM (nn.py:12-19,93-100; unet.py:204-206) ------------------------- */
 
-/* sums[b, g, {0,1}] (double) = sum / sum of squares over group g of sample b.  Zeroes `sums`.   */
-int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, int groups, double *sums,
-                void *stream);
-/* y = act( GN(x; gamma, beta, eps) * (1 + scale_b) + shift_b ), scale/shift optional
- * (film + b*film_ld points at [scale(C) | shift(C)] of sample b); act = SiLU if silu;
- * result optionally rounded to TF32 (it is the next conv's A operand).                          */
-int hl_gn_apply(const float *x, int ldx, const double *sums, const float *gamma, const float *beta,
-                const float *film /*nullable*/, int film_ld, float *y, int ldy, int B, int HW, int C,
-                int groups, float eps, int silu, int round_tf32, void *stream);
+/* Per-channel statistics: stats[(b*stats_ld + c)*2 + {0,1}] (double) += sum / sum of squares of
+ * channel c of sample b over the HW pixels.  ACCUMULATES: the caller zeroes `stats` (one memset per
+ * step covers every tensor).  Channel sums fold into any group layout, including groups that
+ * straddle the two sources of a concatenation (unet.py:606).  hl_conv2d can produce the same
+ * numbers from its epilogue.                                                                     */
+int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld, void *stream);
+/* y = act( GN(x; gamma, beta, eps) * (1 + scale_b) + shift_b ) written as an OPERAND (y_dtype),
+ * scale/shift optional (film + b*film_ld points at [scale(C) | shift(C)] of sample b); act = SiLU if
+ * silu; `raw` (nullable) additionally receives the plain operand copy of x (same dtype, pitch ldraw)
+ * for the ResBlock's 1x1 skip convolution, saving a second pass over x.                          */
+int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma,
+                const float *beta, const float *film /*nullable*/, int film_ld, void *y, int y_dtype,
+                int ldy, void *raw /*nullable*/, int ldraw, int B, int HW, int C, int groups, float eps,
+                int silu, int round_tf32, void *stream);
 
 /* ---- convolution / GEMM (unet.py:68,100,149,164-184,237-239,378,474,481-518) ------------------ */
 
 /* y[b,oy,ox,co] = bias[co] + sum_{ky,kx,ci} x[b, oy*stride+ky-pad, ox*stride+kx-pad, ci] *
  *                 w[co,ci,ky,kx]  (+ residual[b,oy,ox,co]),   zero padding pad = ksize/2.
- * wpk is the packed weight: [ksize*ksize][Cout_pad][Cin_pad] fp32, Cin_pad = Cin (the caller pads
- * the activation buffer's channel count to a multiple of 32 for the tensor-core path),
- * Cout_pad = hl_conv_cout_pad(Cout).  ksize in {1,3}; stride in {1,2}.  A 1x1 conv over
- * [B*T, C] rows is the Conv1d / GEMM of the attention block.                                    */
+ * x: NHWC operand buffer of x_dtype, B x H x W x Cin with pixel pitch ldx (elements); H, W are the
+ * INPUT size.  wpk is the packed weight in the SAME dtype: [ksize*ksize][Cout_pad][Cin], Cin = the
+ * (padded) channel count of x -- a multiple of 64 (fp16) / 32 (tf32) for the tensor-core path --
+ * Cout_pad = hl_conv_cout_pad(Cout); bias fp32 [Cout_pad].  ksize in {1,3}; stride in {1,2}.
+ * y / residual: fp32 NHWC with pitches ldy / ldr (channel slices of wider buffers are fine: the
+ * decoder's concat is never materialised).  stats (nullable): per-channel sum / sum-of-squares of
+ * y, layout as hl_gn_stats, ACCUMULATED into the caller-zeroed buffer.
+ * A 1x1 conv over [B*T, C] rows is the Conv1d / GEMM of the attention block.                    */
 int hl_conv_cout_pad(int Cout);
-int hl_conv2d(const float *x, int ldx, const float *wpk, const float *bias,
-              const float *residual /*nullable*/, int ldr, float *y, int ldy, int B, int H, int W,
-              int Cin, int Cout, int ksize, int stride, int flags, void *stream);
+int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+              const float *residual /*nullable*/, int ldr, float *y, int ldy, double *stats /*nullable*/,
+              int stats_ld, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
+              void *stream);
 
 /* ---- attention (unet.py:255-274) ------------------------------------------------------------ */
 
-/* qkv: [B, T, 3C] rows (pitch ldq) with channel order [head][q(ch) k(ch) v(ch)];
- * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c]                          */
-int hl_attention(const float *qkv, int ldq, float *out, int ldo, int B, int T, int C, int heads,
-                 int round_tf32, void *stream);
+/* qkv: fp32 [B, T, 3C] rows (pitch ldq) with channel order [head][q(ch) k(ch) v(ch)];
+ * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c], written as an operand
+ * (out_dtype) for the proj_out GEMM.                                                             */
+int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
+                 int heads, int round_tf32, void *stream);
 
 /* ---- DDPM posterior step (gaussian_diffusion.py:293-314,328-333,383-387) ---------------------- */
 

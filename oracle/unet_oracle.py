@@ -43,6 +43,17 @@ class _Numerics:
             return round_tf32(x)
         if self.mode == "tf32_trunc_raw":
             return trunc_tf32(x) if raw else round_tf32(x)
+        if self.mode == "fp16":
+            # cvt.rn.f16.f32 operands (11-bit significand like TF32, 5-bit exponent), fp32 accumulate
+            return x.to(torch.float16).to(torch.float32)
+        if self.mode == "fp16_rawsplit":
+            # raw residual-stream operands carried as an fp16 hi + lo pair (two MMA passes): ~22 bits
+            if raw:
+                hi = x.to(torch.float16).to(torch.float32)
+                return hi + (x - hi).to(torch.float16).to(torch.float32)
+            return x.to(torch.float16).to(torch.float32)
+        if self.mode == "bf16":
+            return x.to(torch.bfloat16).to(torch.float32)
         raise ValueError(self.mode)
 
 

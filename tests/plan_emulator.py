@@ -1,0 +1,170 @@
+"""CPU interpreter of a ``_StepPlan`` launch list (TEST INFRASTRUCTURE).
+
+``humanliff_b200.unet._StepPlan`` compiles one UNet forward into a flat list of C-ABI calls over a
+fixed workspace.  Built on the CPU device, the very same list can be *interpreted* here with
+numpy/torch restatements of each entry point's documented semantics (include/humanliff_b200.h), which
+checks the whole host-side dataflow -- pointers, pitches, concat slices, statistics rows, FiLM offsets --
+against the oracle without a GPU.  The kernels themselves are checked on the GPU (tests/*_gpu.py)."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_CT = {np.float32: ctypes.c_float, np.float16: ctypes.c_uint16, np.float64: ctypes.c_double, np.int64: ctypes.c_int64}
+
+
+def view(ptr, n, dtype=np.float32):
+    """numpy view of n elements of `dtype` at raw address `ptr`."""
+    ct = _CT[dtype]
+    arr = np.ctypeslib.as_array((ct * int(n)).from_address(int(ptr)))
+    return arr.view(dtype) if dtype == np.float16 else arr
+
+
+def pitched(ptr, rows, cols, ld, dtype=np.float32):
+    """[rows, cols] view with row pitch ld (elements)."""
+    flat = view(ptr, (rows - 1) * ld + cols, dtype)
+    return np.lib.stride_tricks.as_strided(flat, shape=(rows, cols), strides=(ld * flat.itemsize, flat.itemsize))
+
+
+def _dt(code):
+    return np.float16 if code == 1 else np.float32
+
+
+def _round_tf32(a):
+    i = a.astype(np.float32).view(np.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(np.float32)
+
+
+def _store_operand(dst_ptr, dtype_code, rows, cols, ld, values, round_tf32):
+    out = pitched(dst_ptr, rows, cols, ld, _dt(dtype_code))
+    if dtype_code == 1:
+        out[...] = values.astype(np.float16)
+    else:
+        out[...] = _round_tf32(values) if round_tf32 else values
+
+
+def hl_zero(ptr, nbytes, stream):
+    view(ptr, nbytes // 8, np.float64)[...] = 0
+
+
+def hl_timestep_embedding(t, freqs, B, dim, out, stream):
+    half = dim // 2
+    tt, ff = view(t, B), view(freqs, half)
+    a = (tt[:, None] * ff[None]).astype(np.float32)
+    o = view(out, B * dim).reshape(B, dim)
+    o[:, :half] = np.cos(a)
+    o[:, half:2 * half] = np.sin(a)
+
+
+def hl_linear_small(x, W, bias, y, B, in_f, out_f, silu_in, add_table, add_idx, stream):
+    xv = torch.from_numpy(view(x, B * in_f).reshape(B, in_f).copy())
+    if silu_in:
+        xv = xv * torch.sigmoid(xv)
+    Wv = torch.from_numpy(view(W, out_f * in_f).reshape(out_f, in_f))
+    r = xv @ Wv.T
+    if bias:
+        r = r + torch.from_numpy(view(bias, out_f))
+    if add_table:
+        idx = view(add_idx, B, np.int64)
+        r = r + torch.from_numpy(view(add_table, (int(idx.max()) + 1) * out_f).reshape(-1, out_f))[idx]
+    view(y, B * out_f).reshape(B, out_f)[...] = r.numpy()
+
+
+def hl_nchw_to_nhwc(src, src2, dst, dst_dtype, B, C, HW, ld, round_tf32, stream):
+    v = view(src, B * C * HW).reshape(B, C, HW).copy()
+    if src2:
+        v = v + view(src2, B * C * HW).reshape(B, C, HW)
+    full = np.zeros((B * HW, ld), np.float32)
+    full[:, :C] = v.transpose(0, 2, 1).reshape(B * HW, C)
+    _store_operand(dst, dst_dtype, B * HW, ld, ld, full, round_tf32)
+
+
+def hl_nhwc_to_nchw(src, ld, dst, B, C, HW, stream):
+    v = pitched(src, B * HW, C, ld)
+    view(dst, B * C * HW).reshape(B, C, HW)[...] = v.reshape(B, HW, C).transpose(0, 2, 1)
+
+
+def hl_cast_operand(src, lds, dst, dst_dtype, ldd, C, npix, round_tf32, stream):
+    _store_operand(dst, dst_dtype, npix, C, ldd, pitched(src, npix, C, lds).copy(), round_tf32)
+
+
+def hl_upsample2x(src, lds, dst, dst_dtype, ldd, B, H, W, C, round_tf32, stream):
+    v = pitched(src, B * H * W, C, lds).reshape(B, H, W, C)
+    up = v.repeat(2, axis=1).repeat(2, axis=2).reshape(B * 4 * H * W, C)
+    _store_operand(dst, dst_dtype, B * 4 * H * W, C, ldd, up, round_tf32)
+
+
+def hl_gn_stats(x, ldx, B, HW, C, stats, stats_ld, stream):
+    v = pitched(x, B * HW, C, ldx).reshape(B, HW, C).astype(np.float64)
+    st = pitched(stats, B, 2 * C, 2 * stats_ld, np.float64).reshape(B, C, 2)
+    st[:, :, 0] += v.sum(1)
+    st[:, :, 1] += (v * v).sum(1)
+
+
+def hl_gn_apply(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y, y_dtype, ldy, raw, ldraw, B, HW, C, groups,
+                eps, silu, round_tf32, stream):
+    v = pitched(x, B * HW, C, ldx).reshape(B, HW, C)
+    st = pitched(stats, B, 2 * C, 2 * stats_ld, np.float64).reshape(B, groups, C // groups, 2).sum(2)
+    n = HW * (C // groups)
+    mean = st[..., 0] / n
+    var = np.maximum(st[..., 1] / n - mean * mean, 0.0)
+    rstd = (1.0 / np.sqrt(var + eps)).astype(np.float32)
+    mean = mean.astype(np.float32)
+    cpg = C // groups
+    ga = view(gamma, C)[None] * np.repeat(rstd, cpg, axis=1)
+    be = view(beta, C)[None] - np.repeat(mean, cpg, axis=1) * ga
+    if film:
+        f = pitched(film, B, 2 * C, film_ld)
+        sc, sh = 1.0 + f[:, :C], f[:, C:]
+        ga, be = ga * sc, be * sc + sh
+    o = v * ga[:, None, :] + be[:, None, :]
+    if silu:
+        t = torch.from_numpy(o)
+        o = (t * torch.sigmoid(t)).numpy()
+    _store_operand(y, y_dtype, B * HW, C, ldy, o.reshape(B * HW, C).astype(np.float32), round_tf32)
+    if raw:
+        _store_operand(raw, y_dtype, B * HW, C, ldraw, v.reshape(B * HW, C).copy(), round_tf32)
+
+
+def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin, Cout, ksize, stride,
+              flags, stream):
+    assert not (flags & 2), "the plan upsamples explicitly"
+    cout_pad = (Cout + 31) // 32 * 32
+    xv = torch.from_numpy(pitched(x, B * H * W, Cin, ldx, _dt(x_dtype)).astype(np.float32)).reshape(B, H, W, Cin)
+    wv = torch.from_numpy(view(wpk, ksize * ksize * cout_pad * Cin, _dt(x_dtype)).astype(np.float32))
+    wv = wv.reshape(ksize, ksize, cout_pad, Cin)[:, :, :Cout].permute(2, 3, 0, 1).contiguous()
+    bv = torch.from_numpy(view(bias, Cout).copy())
+    out = F.conv2d(xv.permute(0, 3, 1, 2), wv, bv, stride=stride, padding=ksize // 2).permute(0, 2, 3, 1)
+    Ho, Wo = out.shape[1], out.shape[2]
+    out = out.reshape(B * Ho * Wo, Cout).numpy()
+    if residual:
+        out = out + pitched(residual, B * Ho * Wo, Cout, ldr)
+    pitched(y, B * Ho * Wo, Cout, ldy)[...] = out
+    if stats:
+        hl_gn_stats(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, stream)
+
+
+def hl_attention(qkv, ldq, out, out_dtype, ldo, B, T, C, heads, round_tf32, stream):
+    v = torch.from_numpy(pitched(qkv, B * T, 3 * C, ldq).copy()).reshape(B, T, heads, 3, C // heads)
+    q, k, vv = v[:, :, :, 0], v[:, :, :, 1], v[:, :, :, 2]            # [B, T, heads, ch]
+    w = torch.einsum("bthc,bshc->bhts", q, k) / (C // heads) ** 0.5
+    w = torch.softmax(w, dim=-1)
+    a = torch.einsum("bhts,bshc->bthc", w, vv).reshape(B * T, C).numpy()
+    _store_operand(out, out_dtype, B * T, C, ldo, a, round_tf32)
+
+
+_OPS = {k: v for k, v in globals().items() if k.startswith("hl_")}
+
+
+def run_plan(plan, x, timesteps, x_cond, y):
+    """Interpret the plan's launch list on the CPU; returns eps [B, C, H, W]."""
+    plan.x_in.copy_(x)
+    plan.t_in.copy_(timesteps)
+    if plan.xc_in is not None:
+        plan.xc_in.copy_(x_cond)
+    if y is not None:
+        plan.y_in.copy_(y)
+    for name, args in plan.calls:
+        _OPS[name](*args, None)
+    return plan.out.clone()

@@ -87,7 +87,7 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(device, precision="tf32"):
+def build_model(device, precision="fp16"):
     from humanliff_b200 import factory, synth
     model, diffusion = factory.create_model_and_diffusion(**dict(factory.production_flags(""), precision=precision))
     sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
@@ -95,24 +95,32 @@ def build_model(device, precision="tf32"):
     return model.to(device).eval(), diffusion, sd
 
 
-def dominant_kernel_roofline(device, B, peaks, reps=20):
-    """conv3x3 192->192 @ 256x256 (36.7 % of the step's FLOPs, 17 launches/step): CUDA events around
-    `reps` back-to-back launches on the launching stream; L2 is flushed between launches by cycling
-    through input/output buffers whose union exceeds the 126 MB L2."""
+def dominant_kernel_roofline(device, B, peaks, precision, reps=20):
+    """conv3x3 192->192 @ 256x256 with residual add and GroupNorm statistics in the epilogue (the second
+    conv of a 256^2 ResBlock; this shape is 36.7 % of the step's FLOPs, 17 launches/step): CUDA events
+    around `reps` back-to-back launches on the launching stream; L2 is defeated between launches by cycling
+    through input/residual/output buffers whose union (3 x 0.5 GB) exceeds the 126 MB L2."""
+    from humanliff_b200 import _lib
     from humanliff_b200._lib import call
-    from humanliff_b200.unet import pack_conv
+    from humanliff_b200.unet import pack_conv, _DT
     g = torch.Generator().manual_seed(0)
     Cin = Cout = 192
     nbuf = 3
-    xs = [torch.randn(B, HW, HW, Cin, device=device) for _ in range(nbuf)]
+    code, tdt, _ = _DT[precision]
+    esz = 2 if precision == "fp16" else 4
+    xs = [torch.randn(B, HW, HW, Cin, device=device).to(tdt) for _ in range(nbuf)]
+    rs = [torch.randn(B, HW, HW, Cout, device=device) for _ in range(nbuf)]
     ys = [torch.empty(B, HW, HW, Cout, device=device) for _ in range(nbuf)]
+    stats = torch.zeros(B * Cout * 2, device=device, dtype=torch.float64)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / 41.6
-    wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, True, device)
+    wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, precision, device)
     st = torch.cuda.current_stream(device)
+    flags = {"fp16": 0, "tf32": _lib.CONV_TF32, "fp32": _lib.CONV_FORCE_SIMT}[precision]
 
     def launch(i):
-        call("hl_conv2d", xs[i % nbuf].data_ptr(), Cin, wpk.data_ptr(), bpk.data_ptr(), None, 0,
-             ys[i % nbuf].data_ptr(), Cout, B, HW, HW, Cin, Cout, 3, 1, 0, st.cuda_stream)
+        call("hl_conv2d", xs[i % nbuf].data_ptr(), code, Cin, wpk.data_ptr(), bpk.data_ptr(), rs[i % nbuf].data_ptr(),
+             Cout, ys[i % nbuf].data_ptr(), Cout, stats.data_ptr(), Cout, B, HW, HW, Cin, Cout, 3, 1, flags,
+             st.cuda_stream)
 
     for i in range(3):
         launch(i)
@@ -126,15 +134,47 @@ def dominant_kernel_roofline(device, B, peaks, reps=20):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * HW * HW * Cout * Cin * 9
     ach = flops / (ms * 1e-3) / 1e12
-    bytes_alg = 4.0 * (B * HW * HW * (Cin + Cout) + 9 * Cin * Cout)
-    return {"kernel": "k_conv_tc (tcgen05 kind::tf32 implicit-GEMM conv3x3 192->192 @256^2, B=%d)" % B,
+    bytes_alg = B * HW * HW * (esz * Cin + 4 * Cout + 4 * Cout) + esz * 9 * Cin * Cout
+    kind = {"fp16": "kind::f16 (fp16 operands, fp32 accumulate)", "tf32": "kind::tf32", "fp32": "CUDA-core fp32"}[precision]
+    note = ("bf16/fp16 burst figure; the kernel's operand type runs at that peak" if precision == "fp16" else
+            "bf16 burst figure -- TF32's dense peak is half of it")
+    return {"kernel": "k_conv_tc (tcgen05 %s implicit-GEMM conv3x3 192->192 @256^2 + residual + GN statistics, B=%d)" % (kind, B),
             "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_burst"], 4), "traffic": None,
-            "peak_source": peaks["source"] + "; bf16 burst figure -- the kernel computes in TF32 whose dense peak is "
-                                             "half of bf16, so frac 0.5 is the TF32 speed of light",
-            "frac_of_tf32_peak": round(ach / (peaks["bf16_burst"] / 2), 4),
+            "peak_source": peaks["source"] + "; " + note,
             "ms_per_launch": round(ms, 4), "algorithmic_gflop_per_launch": round(flops / 1e9, 2),
-            "algorithmic_hbm_mb_per_launch": round(bytes_alg / 1e6, 1)}
+            "algorithmic_hbm_mb_per_launch": round(bytes_alg / 1e6, 1),
+            "hbm_floor_ms": round(bytes_alg / (peaks["hbm_gbs"] * 1e9) * 1e3, 4)}
+
+
+def render_throughput(device, n_rays=65536, reps=3):
+    """Secondary metric of BASELINE.json (rendered rays/s, 128+128 samples): the fused render kernel on the
+    512x512 synthetic camera of SURVEY.md 8(d) config 3 (a quarter image per launch), CUDA events."""
+    from humanliff_b200 import synth
+    from humanliff_b200.renderer import Renderer
+    r = Renderer(triplane_ch=27, test=True)
+    synth.randomize_(r, seed=3, weight_gain=1.5)
+    r = r.to(device)
+    planes = synth.synth_triplane(256, seed=7)[0].to(device)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    ro, rd, near, far, _ = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=30.0)
+    sel = slice(512 * 192, 512 * 192 + n_rays)               # rows through the middle of the body box
+    ro, rd, near, far = (t[sel].contiguous().to(device) for t in (ro, rd, near, far))
+    st = torch.cuda.current_stream(device)
+    r.render_rays(planes, bounds, ro, rd, near, far, u=None, seed=1)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(reps):
+        r.render_rays(planes, bounds, ro, rd, near, far, u=None, seed=2 + i)
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    rays_s = n_rays / (ms * 1e-3)
+    return {"metric": "rendered rays/sec (128+128 samples/ray, 27x256x256 tri-plane)", "value": round(rays_s, 1),
+            "unit": "rays/s", "rays_per_launch": n_rays, "ms_per_launch": round(ms, 3),
+            "mlp_tflops": round(rays_s * 44.14e6 / 1e12, 2),
+            "note": "44.14 MFLOP/ray (BASELINE.md section 2); in-kernel counter-based uniforms (throughput mode)"}
 
 
 def cpu_baseline(sd, threads, steps=2):
@@ -272,7 +312,7 @@ def run_ours(args):
     nbytes = B * C * HW * HW * 4
 
     if rank == 0:
-        roof = dominant_kernel_roofline(device, B, peaks)
+        roof = dominant_kernel_roofline(device, B, peaks, args.precision)
         step_tflops = GFLOP_PER_SAMPLE_STEP * B / (ms_total / K)          # GFLOP / ms = TFLOP/s
         roof["whole_step_tflops"] = round(step_tflops, 2)
         roof["whole_step_frac_of_bf16_sustained"] = round(step_tflops / peaks["bf16_sustained"], 4)
@@ -285,17 +325,27 @@ def run_ours(args):
                              "steps after 1 warm-up (%.1f s/step)" % dt}
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "vs_baseline": None,
+                "dtype": {"fp16": "fp16 operands (11-bit significand, = TF32) x fp32 accumulate, fp32 residual stream / "
+                                  "GroupNorm / softmax / posterior", "tf32": "tf32", "fp32": "f32"}[args.precision],
+                "data": "synthetic",
                 "config": {"workload": "1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); "
                                        "one step = one p_sample (UNet 497M params + posterior update)",
                            "batch_per_gpu": B, "global_batch": B * world, "resolution": "27x256x256",
                            "parallelism": "dp%d (batch sharded, no data-path collective; one all-gather of finished samples)" % world,
-                           "l2_policy": "per-step working set (>= 6 GB of activations + 2 GB of weights) exceeds the 126 MB L2",
+                           "l2_policy": "per-step working set (>= 6 GB of activations + 1 GB of fp16 weights) exceeds the 126 MB L2",
+                           "execution": "one CUDA graph replay per UNet forward (%d C-ABI launches) + 1 posterior kernel" % (
+                               launches // K - 1),
                            "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes,
                         "d2h_bytes_per_step": nbytes, "ms_per_step": round(float(ms2.item()) / K, 3)},
                 "roofline": roof, "cpu_baseline": cpu}
+        if world == 1 and not args.no_render:
+            try:
+                line["render"] = render_throughput(device)
+            except Exception as e:                      # the secondary metric must not take the headline down
+                line["render"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -308,8 +358,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

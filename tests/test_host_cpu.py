@@ -92,3 +92,27 @@ def test_all_gather_world_size_2_gloo(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 1.5e-3)])
+def test_step_plan_dataflow_by_cpu_interpretation(precision, tol):
+    """The launch list `_StepPlan` compiles (pointers, pitches, concat slices, statistics rows, FiLM offsets,
+    ControlNet projection wiring) interpreted on the CPU must reproduce the reference golden."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import plan_emulator
+    from common import CASES, load_golden, model_state_dict, rel_l2
+    from humanliff_b200.unet import _StepPlan
+    fname, flags, seed, heads = CASES["tiny"]
+    model, diffusion, sd = model_state_dict(dict(flags, precision=precision), seed)
+    model.load_state_dict(sd)
+    g = load_golden(fname)
+    B, _, H, W = g["x"].shape
+    cpu = torch.device("cpu")
+    model._pack(cpu)
+    plan = _StepPlan(model, cpu, B, H, W)
+    names = [n for n, _ in plan.calls]
+    assert names.count("hl_zero") == 1 and "hl_concat_add" not in names and "hl_gn_stats" not in names
+    ts = torch.tensor(diffusion.timestep_map)[torch.full((B,), 100)]
+    for rep in range(2):            # twice: the statistics arena must be re-zeroed by the plan itself
+        eps = plan_emulator.run_plan(plan, g["x"], ts, g["x_cond"], g["y"])
+        assert rel_l2(eps, g["eps_100"]) < tol

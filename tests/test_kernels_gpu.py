@@ -1,6 +1,7 @@
 """GPU: every C-ABI kernel against a plain torch-CPU statement of the same op (the oracle's arithmetic
-library) on seeded inputs.  Tolerances: 1e-5 (fp32 kernels, accumulation-order differences only),
-1e-3 rel-L2 for the TF32 tensor-core convolution (north_star bar), bit-exact for the DDPM update."""
+library) on seeded inputs.  Tolerances: 1e-5 (fp32-accumulate kernels on identical operands: accumulation-
+order differences only), 1e-3 rel-L2 for the reduced-precision-operand tensor-core convolution against the
+exact fp32 conv (north_star bar), bit-exact for layout / cast / DDPM update."""
 import math
 
 import pytest
@@ -34,7 +35,7 @@ def test_layout_roundtrip(dev):
         x2 = torch.randn(B, C, H, W, generator=g)
         xd, x2d = x.to(dev), x2.to(dev)
         nhwc = torch.full((B, H * W, ld), 7.0, device=dev)
-        _call("hl_nchw_to_nhwc", xd.data_ptr(), x2d.data_ptr(), nhwc.data_ptr(), B, C, H * W, ld, 0, _stream())
+        _call("hl_nchw_to_nhwc", xd.data_ptr(), x2d.data_ptr(), nhwc.data_ptr(), 0, B, C, H * W, ld, 0, _stream())
         ref = (x + x2).permute(0, 2, 3, 1).reshape(B, H * W, C)
         assert torch.equal(nhwc[:, :, :C].cpu(), ref)
         assert float(nhwc[:, :, C:].abs().max() if ld > C else 0) == 0.0, "channel padding must be zero"
@@ -43,13 +44,28 @@ def test_layout_roundtrip(dev):
         assert torch.equal(back.cpu(), x + x2)
 
 
-def test_round_tf32_matches_emulation(dev):
+def test_layout_fp16_operand(dev):
+    g = torch.Generator().manual_seed(0)
+    B, C, H, W, ld = 2, 27, 8, 8, 64
+    x = torch.randn(B, C, H, W, generator=g)
+    nhwc = torch.full((B, H * W, ld), 7.0, device=dev, dtype=torch.float16)
+    _call("hl_nchw_to_nhwc", x.to(dev).data_ptr(), None, nhwc.data_ptr(), 1, B, C, H * W, ld, 0, _stream())
+    ref = x.permute(0, 2, 3, 1).reshape(B, H * W, C).half()
+    assert torch.equal(nhwc[:, :, :C].cpu(), ref) and float(nhwc[:, :, C:].abs().max()) == 0.0
+
+
+def test_cast_operand_matches_emulation(dev):
     from oracle.unet_oracle import round_tf32
-    x = torch.randn(1000, 8) * torch.logspace(-6, 6, 1000)[:, None]
+    x = torch.randn(1000, 8) * torch.logspace(-6, 4, 1000)[:, None]
     xd = x.to(dev)
     out = torch.empty_like(xd)
-    _call("hl_round_tf32", xd.data_ptr(), 8, out.data_ptr(), 8, 8, 1000, _stream())
+    _call("hl_cast_operand", xd.data_ptr(), 8, out.data_ptr(), 0, 8, 8, 1000, 1, _stream())
     assert torch.equal(out.cpu(), round_tf32(x))
+    _call("hl_cast_operand", xd.data_ptr(), 8, out.data_ptr(), 0, 8, 8, 1000, 0, _stream())
+    assert torch.equal(out.cpu(), x)
+    outh = torch.empty(1000, 8, device=dev, dtype=torch.float16)
+    _call("hl_cast_operand", xd.data_ptr(), 8, outh.data_ptr(), 1, 8, 8, 1000, 0, _stream())
+    assert torch.equal(outh.cpu(), x.half())          # round-to-nearest-even, like torch
 
 
 def test_concat_add_and_upsample(dev):
@@ -65,11 +81,12 @@ def test_concat_add_and_upsample(dev):
           C1 + C2, npix, _stream())
     assert torch.equal(out.cpu(), torch.cat([a, b], 1))
     x = torch.randn(2, 3, 5, 8, generator=g)                       # NHWC [B,H,W,C]
-    up = torch.empty(2, 6, 10, 8, device=dev)
-    xd = x.to(dev)
-    _call("hl_upsample2x", xd.data_ptr(), 8, up.data_ptr(), 8, 2, 3, 5, 8, 0, _stream())
     ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
-    assert torch.equal(up.cpu(), ref)
+    xd = x.to(dev)
+    for code, tdt in ((0, torch.float32), (1, torch.float16)):
+        up = torch.empty(2, 6, 10, 8, device=dev, dtype=tdt)
+        _call("hl_upsample2x", xd.data_ptr(), 8, up.data_ptr(), code, 8, 2, 3, 5, 8, 0, _stream())
+        assert torch.equal(up.cpu(), ref.to(tdt))
 
 
 def test_embeddings(dev):
@@ -99,24 +116,51 @@ def test_groupnorm_silu_film(dev, C, HW, B):
     gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
     film = 0.3 * torch.randn(B, 2 * C + 10, generator=g)
     xd, gd, bd, fd = x.to(dev), gamma.to(dev), beta.to(dev), film.to(dev)
-    sums = torch.empty(B * 32 * 2, device=dev, dtype=torch.float64)
-    y = torch.empty_like(xd)
-    _call("hl_gn_stats", xd.data_ptr(), C, B, HW, C, 32, sums.data_ptr(), _stream())
+    ld_st = C + 8                                                   # statistics row wider than the tensor
+    stats = torch.zeros(B * ld_st * 2, device=dev, dtype=torch.float64)
+    _call("hl_gn_stats", xd.data_ptr(), C, B, HW, C, stats.data_ptr(), ld_st, _stream())
+    st = stats.cpu().reshape(B, ld_st, 2)
+    assert rel_l2(st[:, :C, 0], x.double().sum(1)) < 1e-6 and rel_l2(st[:, :C, 1], (x.double() ** 2).sum(1)) < 1e-6
+    assert float(st[:, C:].abs().max()) == 0.0
     xn = F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, eps=1e-5)          # [B, C, HW]
     for use_film, silu in [(False, True), (True, True), (False, False)]:
-        _call("hl_gn_apply", xd.data_ptr(), C, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(),
-              fd.data_ptr() if use_film else None, 2 * C + 10, y.data_ptr(), C, B, HW, C, 32, 1e-5,
-              1 if silu else 0, 0, _stream())
         r = xn
         if use_film:
             r = r * (1 + film[:, :C, None]) + film[:, C:2 * C, None]
         if silu:
             r = r * torch.sigmoid(r)
-        assert rel_l2(y.permute(0, 2, 1), r) < 2e-6, (use_film, silu)
-        assert rel_max(y.permute(0, 2, 1), r) < 2e-5
+        for code, tdt, tol in ((0, torch.float32, 2e-6), (1, torch.float16, 6e-4)):
+            y = torch.empty(B, HW, C, device=dev, dtype=tdt)
+            raw = torch.empty(B, HW, C, device=dev, dtype=tdt)
+            _call("hl_gn_apply", xd.data_ptr(), C, stats.data_ptr(), ld_st, gd.data_ptr(), bd.data_ptr(),
+                  fd.data_ptr() if use_film else None, 2 * C + 10, y.data_ptr(), code, C, raw.data_ptr(), C, B, HW,
+                  C, 32, 1e-5, 1 if silu else 0, 0, _stream())
+            assert rel_l2(y.float().permute(0, 2, 1), r) < tol, (use_film, silu, code)
+            assert torch.equal(raw.cpu(), x.to(tdt)), "raw operand copy of the input"
+            if code == 1:   # the fp16 operand is the correctly rounded fp32 result (up to 1 ulp of the fp32 value)
+                y32 = torch.empty(B, HW, C, device=dev)
+                _call("hl_gn_apply", xd.data_ptr(), C, stats.data_ptr(), ld_st, gd.data_ptr(), bd.data_ptr(),
+                      fd.data_ptr() if use_film else None, 2 * C + 10, y32.data_ptr(), 0, C, None, 0, B, HW, C, 32,
+                      1e-5, 1 if silu else 0, 0, _stream())
+                assert torch.equal(y.cpu(), y32.cpu().half())
 
 
-def _conv_case(dev, B, H, W, Cin, Cout, k, stride, flags=0, residual=True, tf32=False, cin_pad=None, seed=0):
+def _operand(t, mode):
+    """fp32 tensor -> (device-ready operand tensor, dtype code, fp32 view of the rounded values)."""
+    from oracle.unet_oracle import round_tf32
+    if mode == "fp16":
+        h = t.half()
+        return h, 1, h.float()
+    if mode == "tf32":
+        r = round_tf32(t)
+        return r, 0, r
+    return t, 0, t
+
+
+def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residual=True, stats=False, cin_pad=None,
+               seed=0, ldy=None, tuning=None):
+    """Runs hl_conv2d on seeded inputs; returns (y NCHW cpu, fp32 reference, reference on the ROUNDED operands,
+    stats cpu or None)."""
     from humanliff_b200.unet import pack_conv
     from humanliff_b200 import _lib
     g = torch.Generator().manual_seed(seed)
@@ -129,87 +173,130 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, flags=0, residual=True, tf32=
     ref = F.conv2d(xr, w, b, stride=stride, padding=k // 2)
     Ho, Wo = ref.shape[2:]
     res = torch.randn(B, Cout, Ho, Wo, generator=g) if residual else None
-    if residual:
-        ref = ref + res
     xn = torch.zeros(B, H, W, cin_pad)
     xn[..., :Cin] = x.permute(0, 2, 3, 1)
-    xd = xn.to(dev)
-    if tf32:
-        _call("hl_round_tf32", xd.data_ptr(), cin_pad, xd.data_ptr(), cin_pad, cin_pad, B * H * W, _stream())
-    wpk, bpk = pack_conv(w, b, cin_pad, tf32, dev)
-    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev)
+    xop, code, xround = _operand(xn, mode)
+    wr = _operand(w, mode)[2]
+    ref_r = F.conv2d(F.interpolate(xround[..., :Cin].permute(0, 3, 1, 2), scale_factor=2, mode="nearest") if ups
+                     else xround[..., :Cin].permute(0, 3, 1, 2), wr, b, stride=stride, padding=k // 2)
+    if residual:
+        ref, ref_r = ref + res, ref_r + res
+    if mode == "tf32":
+        flags |= _lib.CONV_TF32
+    xd = xop.to(dev)
+    wpk, bpk = pack_conv(w, b, cin_pad, mode, dev)
+    ldy = ldy or Cout
+    y = torch.full((B, Ho, Wo, ldy), float("nan"), device=dev)
     rd = res.permute(0, 2, 3, 1).contiguous().to(dev) if residual else None
-    _call("hl_conv2d", xd.data_ptr(), cin_pad, wpk.data_ptr(), bpk.data_ptr(), rd.data_ptr() if residual else None,
-          Cout, y.data_ptr(), Cout, B, H, W, cin_pad, Cout, k, stride, flags, _stream())
-    torch.cuda.synchronize()
-    return y.permute(0, 3, 1, 2).cpu(), ref, (xd, wpk, bpk, rd, (Ho, Wo))
+    st = torch.zeros(B * ldy * 2, device=dev, dtype=torch.float64) if stats else None
+    lib = _lib.load()
+    if tuning is not None:
+        lib.hl_conv_set_tuning(*tuning)
+    try:
+        _call("hl_conv2d", xd.data_ptr(), code, cin_pad, wpk.data_ptr(), bpk.data_ptr(),
+              rd.data_ptr() if residual else None, Cout, y.data_ptr(), ldy, st.data_ptr() if stats else None, ldy,
+              B, H, W, cin_pad, Cout, k, stride, flags, _stream())
+        torch.cuda.synchronize()
+    finally:
+        lib.hl_conv_set_tuning(-1, -1, -1, -1, -1)
+    return y[..., :Cout].permute(0, 3, 1, 2).cpu(), ref, ref_r, (st.cpu().reshape(B, ldy, 2) if stats else None)
+
+
+def _check_stats(st, y, Cout):
+    yy = y.double()                                                    # [B, C, H, W]
+    assert rel_l2(st[:, :Cout, 0], yy.sum((2, 3))) < 1e-5, "channel sums from the conv epilogue"
+    assert rel_l2(st[:, :Cout, 1], (yy * yy).sum((2, 3))) < 1e-5, "channel sums of squares from the conv epilogue"
 
 
 @pytest.mark.parametrize("shape", [
     (2, 16, 16, 32, 48, 3, 1), (1, 9, 7, 27, 20, 3, 1), (2, 16, 16, 64, 64, 3, 2), (1, 8, 8, 96, 40, 1, 1),
     (2, 5, 5, 33, 7, 3, 2), (1, 4, 4, 768, 768, 3, 1)])
-def test_conv_simt_exact(dev, shape):
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_conv_simt_exact(dev, shape, mode):
     from humanliff_b200 import _lib
     B, H, W, Cin, Cout, k, s = shape
-    y, ref, _ = _conv_case(dev, B, H, W, Cin, Cout, k, s, flags=_lib.CONV_FORCE_SIMT)
-    assert rel_l2(y, ref) < 2e-6 and rel_max(y, ref) < 2e-5
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, flags=_lib.CONV_FORCE_SIMT, stats=True)
+    assert rel_l2(y, ref_r) < 2e-6 and rel_max(y, ref_r) < 2e-5
+    _check_stats(st, y, Cout)
 
 
 def test_conv_simt_upsample_folded(dev):
     from humanliff_b200 import _lib
-    y, ref, _ = _conv_case(dev, 2, 8, 8, 32, 32, 3, 1, flags=_lib.CONV_FORCE_SIMT | _lib.CONV_UPSAMPLE2X)
+    y, ref, _, _ = _conv_case(dev, 2, 8, 8, 32, 32, 3, 1, flags=_lib.CONV_FORCE_SIMT | _lib.CONV_UPSAMPLE2X)
     assert rel_l2(y, ref) < 2e-6
 
 
 TC_SHAPES = [
-    # B, H, W, Cin, Cout, k   -- tile shapes: (bw,bh,bn)
-    (1, 64, 64, 192, 192, 3),     # (64,2,1)  N=192
-    (2, 32, 32, 384, 384, 3),     # (32,4,1)  N=192 x2
-    (4, 8, 8, 768, 768, 3),       # (8,8,2)   N=256 x3
-    (1, 128, 128, 32, 192, 3),    # (128,1,1) stem: Cin padded 27->32
-    (1, 256, 256, 64, 64, 3),     # W > 128 : 2 tiles per row
-    (2, 16, 16, 384, 192, 1),     # 1x1 skip conv
-    (1, 16, 16, 384, 1152, 1),    # qkv GEMM
-    (1, 64, 64, 192, 27, 3),      # out conv: Cout 27 (padded N tile, scalar epilogue)
-    (3, 8, 8, 64, 32, 3),         # bn=2 with B=3: out-of-range batch rows are zero-filled + masked
-    (1, 16, 8, 96, 64, 3),        # non-square
+    # B, H, W, Cin, Cout, k, stride
+    (1, 64, 64, 192, 192, 3, 1),     # box (64,2,1)
+    (2, 32, 32, 384, 384, 3, 1),     # box (32,4,1), 2+ n-tiles
+    (4, 8, 8, 768, 768, 3, 1),       # box (8,8,2): two samples per box
+    (1, 128, 128, 64, 192, 3, 1),    # stem-like (Cin padded to one chunk); HALO eligible
+    (1, 256, 256, 64, 64, 3, 1),     # W > 128 : 2 boxes per row; HALO eligible
+    (2, 128, 128, 192, 192, 3, 1),   # HALO, mh = 2, several tiles per CTA
+    (2, 16, 16, 384, 192, 1, 1),     # 1x1 skip conv
+    (1, 16, 16, 384, 1152, 1, 1),    # qkv GEMM
+    (1, 64, 64, 192, 27, 3, 1),      # out conv: Cout 27 (TMA store clipped at the channel edge)
+    (3, 8, 8, 64, 32, 3, 1),         # bn = 2 with B = 3: out-of-range batch rows zero-filled / clipped
+    (1, 16, 8, 128, 64, 3, 1),       # non-square
+    (2, 64, 64, 192, 192, 3, 2),     # Downsample conv: stride 2 through TMA element strides
+    (1, 256, 256, 64, 128, 3, 2),    # stride 2, 256-wide traversal box
 ]
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_conv_tensor_core_vs_simt_and_fp32(dev, shape):
-    """tcgen05 kernel vs (a) the fp32 CUDA-core kernel on the SAME TF32-rounded operands (only the
-    accumulation order differs -> 5e-5) and (b) the fp32 reference conv (TF32 operand error -> 1e-3)."""
+@pytest.mark.parametrize("mode", ["fp16", "tf32"])
+def test_conv_tensor_core(dev, shape, mode):
+    """tcgen05 kernel (automatic tiling) vs the fp32 reference conv evaluated on the SAME rounded
+    operands (only the accumulation order differs -> 2e-5) and vs the exact fp32 conv (operand rounding
+    -> 1e-3, the north_star bar); residual add and in-epilogue GroupNorm statistics included."""
     from humanliff_b200 import _lib
-    B, H, W, Cin, Cout, k = shape
+    B, H, W, Cin, Cout, k, s = shape
     lib = _lib.load()
-    assert lib.hl_conv2d_uses_tensor_cores(B, H, W, Cin, Cout, k, 1, Cin, 0) == 1, "shape must take the tcgen05 path"
-    y, ref, (xd, wpk, bpk, rd, (Ho, Wo)) = _conv_case(dev, B, H, W, Cin, Cout, k, 1, tf32=True, seed=7)
-    y2 = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev)
-    _call("hl_conv2d", xd.data_ptr(), Cin, wpk.data_ptr(), bpk.data_ptr(), rd.data_ptr(), Cout, y2.data_ptr(),
-          Cout, B, H, W, Cin, Cout, k, 1, _lib.CONV_FORCE_SIMT, _stream())
-    y2 = y2.permute(0, 3, 1, 2).cpu()
+    code = 1 if mode == "fp16" else 0
+    fl = _lib.CONV_TF32 if mode == "tf32" else 0
+    assert lib.hl_conv2d_uses_tensor_cores(code, B, H, W, Cin, Cout, k, s, Cin, Cout, fl) == 1, "must take the tcgen05 path"
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, stats=True, seed=7)
     assert not torch.isnan(y).any()
-    assert rel_l2(y, y2) < 5e-5, f"tcgen05 vs fp32-core on identical operands: {rel_l2(y, y2)}"
+    assert rel_l2(y, ref_r) < 2e-5, f"vs fp32 conv on identical (rounded) operands: {rel_l2(y, ref_r)}"
     assert rel_l2(y, ref) < 1e-3, f"vs fp32 reference: {rel_l2(y, ref)}"
+    _check_stats(st, y, Cout)
+
+
+@pytest.mark.parametrize("tuning", [(1, -1, 0, -1, -1), (2, -1, 0, -1, -1), (1, -1, 1, -1, -1), (2, 192, 1, -1, -1),
+                                    (2, 96, 1, -1, -1), (2, 64, 1, 0, -1), (1, 32, 0, -1, -1)])
+@pytest.mark.parametrize("residual", [False, True])
+def test_conv_tensor_core_tilings(dev, tuning, residual):
+    """Every tiling variant of the kernel (halves per CTA, N tile, TAP vs HALO operand path, statistics in
+    the epilogue or by the separate kernel) must give the same numbers."""
+    B, H, W, Cin, Cout = 2, 128, 128, 192, 192
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, 3, 1, mode="fp16", stats=True, residual=residual, seed=3,
+                                   tuning=tuning)
+    assert not torch.isnan(y).any()
+    assert rel_l2(y, ref_r) < 2e-5, (tuning, rel_l2(y, ref_r))
+    _check_stats(st, y, Cout)
 
 
 def test_conv_tc_strided_output_and_input(dev):
-    """Operands living inside wider (concat) buffers: ldx > Cin, ldy > Cout."""
+    """Operands living inside wider (concat) buffers: ldx > Cin, ldy > Cout, statistics row at an offset."""
     from humanliff_b200.unet import pack_conv
     g = torch.Generator().manual_seed(5)
     B, H, W, Cin, Cout = 1, 32, 32, 64, 64
-    big = torch.randn(B, H, W, 160, generator=g).to(dev)
+    big = torch.randn(B, H, W, 192, generator=g).half().to(dev)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / 24
     b = torch.zeros(Cout)
-    wpk, bpk = pack_conv(w, b, Cin, False, dev)
+    wpk, bpk = pack_conv(w, b, Cin, "fp16", dev)
     out = torch.zeros(B, H, W, 96, device=dev)
-    x_off, y_off = 32, 16
-    _call("hl_conv2d", big.data_ptr() + 4 * x_off, 160, wpk.data_ptr(), bpk.data_ptr(), None, 0,
-          out.data_ptr() + 4 * y_off, 96, B, H, W, Cin, Cout, 3, 1, 0, _stream())
-    ref = F.conv2d(big[..., x_off:x_off + Cin].permute(0, 3, 1, 2).cpu(), w, b, padding=1)
-    assert rel_l2(out[..., y_off:y_off + Cout].permute(0, 3, 1, 2), ref) < 1e-3
+    st = torch.zeros(B, 96, 2, device=dev, dtype=torch.float64)
+    x_off, y_off = 64, 16
+    _call("hl_conv2d", big.data_ptr() + 2 * x_off, 1, 192, wpk.data_ptr(), bpk.data_ptr(), None, 0,
+          out.data_ptr() + 4 * y_off, 96, st.data_ptr() + 16 * y_off, 96, B, H, W, Cin, Cout, 3, 1, 0, _stream())
+    ref = F.conv2d(big[..., x_off:x_off + Cin].float().permute(0, 3, 1, 2).cpu(), w.half().float(), b, padding=1)
+    got = out[..., y_off:y_off + Cout].permute(0, 3, 1, 2).cpu()
+    assert rel_l2(got, ref) < 2e-5
     assert float(out[..., :y_off].abs().max()) == 0 and float(out[..., y_off + Cout:].abs().max()) == 0
+    assert rel_l2(st[:, y_off:y_off + Cout, 0].cpu(), got.double().sum((2, 3))) < 1e-5
+    assert float(st[:, :y_off].abs().max()) == 0 and float(st[:, y_off + Cout:].abs().max()) == 0
 
 
 @pytest.mark.parametrize("B,T,C,heads", [(2, 64, 384, 4), (1, 1024, 384, 4), (2, 256, 768, 4), (1, 16, 128, 2), (3, 4, 64, 2), (1, 100, 256, 4)])
@@ -224,9 +311,12 @@ def test_attention(dev, B, T, C, heads):
     ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
     qd = qkv.permute(0, 2, 1).contiguous().to(dev)             # [B, T, 3C]
     out = torch.empty(B, T, C, device=dev)
-    _call("hl_attention", qd.data_ptr(), 3 * C, out.data_ptr(), C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", qd.data_ptr(), 3 * C, out.data_ptr(), 0, C, B, T, C, heads, 0, _stream())
     assert rel_l2(out.permute(0, 2, 1), ref) < 5e-6
     assert rel_max(out.permute(0, 2, 1), ref) < 5e-5
+    outh = torch.empty(B, T, C, device=dev, dtype=torch.float16)
+    _call("hl_attention", qd.data_ptr(), 3 * C, outh.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    assert torch.equal(outh.cpu(), out.cpu().half())
 
 
 def test_ddpm_step_bit_exact(dev):

@@ -1,0 +1,150 @@
+"""First-contact probe of the tcgen05 conv on a real B200: every tiling variant in its own subprocess
+(a trap or hang in one variant must not poison the rest), parity vs torch on the rounded operands, then
+CUDA-event timing of the dominant shape per variant.  Usage: python tools/tc_probe.py [--time]"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = [
+    # name, (B,H,W,Cin,Cout,k,stride), mode, residual, stats, tuning(mh,n_tile,halo,epi_stats,base_off)
+    ("tap1_f16", (1, 64, 64, 192, 192, 3, 1), "fp16", False, False, (1, -1, 0, -1, -1)),
+    ("tap1_tf32", (1, 64, 64, 192, 192, 3, 1), "tf32", False, False, (1, -1, 0, -1, -1)),
+    ("tap1_res", (1, 64, 64, 192, 192, 3, 1), "fp16", True, False, (1, -1, 0, -1, -1)),
+    ("tap1_stats", (1, 64, 64, 192, 192, 3, 1), "fp16", True, True, (1, -1, 0, -1, -1)),
+    ("tap2", (2, 64, 64, 192, 192, 3, 1), "fp16", True, True, (2, -1, 0, -1, -1)),
+    ("tap_persist", (4, 128, 128, 192, 192, 3, 1), "fp16", True, True, (1, -1, 0, -1, -1)),
+    ("stride2", (2, 64, 64, 192, 192, 3, 2), "fp16", False, True, (-1, -1, -1, -1, -1)),
+    ("one_by_one", (2, 32, 32, 384, 192, 1, 1), "fp16", True, True, (-1, -1, -1, -1, -1)),
+    ("cout27", (1, 64, 64, 192, 27, 3, 1), "fp16", False, False, (-1, -1, -1, -1, -1)),
+    ("halo1_bo1", (1, 128, 128, 64, 64, 3, 1), "fp16", False, False, (1, -1, 1, -1, 1)),
+    ("halo1_bo0", (1, 128, 128, 64, 64, 3, 1), "fp16", False, False, (1, -1, 1, -1, 0)),
+    ("halo2_bo1", (2, 128, 128, 192, 192, 3, 1), "fp16", True, True, (2, 192, 1, -1, 1)),
+    ("halo2_bo0", (2, 128, 128, 192, 192, 3, 1), "fp16", True, True, (2, 192, 1, -1, 0)),
+    ("halo2_n96", (2, 128, 128, 192, 192, 3, 1), "fp16", True, True, (2, 96, 1, -1, -1)),
+    ("halo_tf32", (1, 256, 256, 64, 64, 3, 1), "tf32", True, True, (2, -1, 1, -1, -1)),
+    ("auto_256", (1, 256, 256, 192, 192, 3, 1), "fp16", True, True, (-1, -1, -1, -1, -1)),
+    ("small8", (4, 8, 8, 768, 768, 3, 1), "fp16", True, True, (-1, -1, -1, -1, -1)),
+]
+
+TIMING = [
+    # name, tuning  -- conv3x3 192->192 @ 256x256, B=4, residual + stats (the dominant launch)
+    ("tap mh1 n192", (1, 192, 0, -1, -1)),
+    ("tap mh2 n192", (2, 192, 0, -1, -1)),
+    ("tap mh2 n96", (2, 96, 0, -1, -1)),
+    ("halo mh1 n192", (1, 192, 1, -1, -1)),
+    ("halo mh2 n192", (2, 192, 1, -1, -1)),
+    ("halo mh2 n96", (2, 96, 1, -1, -1)),
+    ("halo mh2 n192 nostats", (2, 192, 1, 0, -1)),
+]
+
+
+def run_case(idx):
+    import torch
+    from test_kernels_gpu import _conv_case, _check_stats
+    from common import rel_l2
+    name, shape, mode, residual, stats, tuning = CASES[idx]
+    dev = torch.device("cuda:0")
+    B, H, W, Cin, Cout, k, s = shape
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, residual=residual, stats=stats, seed=7,
+                                   tuning=tuning)
+    out = {"name": name, "nan": bool(torch.isnan(y).any()), "err_rounded": rel_l2(y, ref_r), "err_fp32": rel_l2(y, ref)}
+    if stats:
+        try:
+            _check_stats(st, y, Cout)
+            out["stats"] = "ok"
+        except AssertionError as e:
+            out["stats"] = "BAD " + str(e)[:60]
+    print("RESULT " + json.dumps(out))
+
+
+def run_timing(idx):
+    import torch
+    from humanliff_b200 import _lib
+    from humanliff_b200._lib import call
+    from humanliff_b200.unet import pack_conv
+    name, tuning = TIMING[idx]
+    dev = torch.device("cuda:0")
+    B, HW, Cin, Cout = 4, 256, 192, 192
+    g = torch.Generator().manual_seed(0)
+    nbuf = 3
+    xs = [torch.randn(B, HW, HW, Cin, device=dev).half() for _ in range(nbuf)]
+    rs = [torch.randn(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
+    ys = [torch.empty(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
+    st = torch.zeros(B * Cout * 2, device=dev, dtype=torch.float64)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / 41.6
+    wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, "fp16", dev)
+    lib = _lib.load()
+    lib.hl_conv_set_tuning(*tuning)
+    stream = torch.cuda.current_stream(dev)
+
+    def launch(i):
+        call("hl_conv2d", xs[i % nbuf].data_ptr(), 1, Cin, wpk.data_ptr(), bpk.data_ptr(), rs[i % nbuf].data_ptr(), Cout,
+             ys[i % nbuf].data_ptr(), Cout, st.data_ptr(), Cout, B, HW, HW, Cin, Cout, 3, 1, 0, stream.cuda_stream)
+    for i in range(3):
+        launch(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record(stream)
+    for i in range(reps):
+        launch(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 2.0 * B * HW * HW * Cout * Cin * 9 / (ms * 1e-3) / 1e12
+    print("RESULT " + json.dumps({"name": name, "ms": round(ms, 4), "tflops": round(tf, 1)}))
+
+
+def worker(kind, start):
+    n = len(CASES) if kind == "case" else len(TIMING)
+    for i in range(start, n):
+        print("BEGIN %d" % i, flush=True)
+        (run_case if kind == "case" else run_timing)(i)
+        sys.stdout.flush()
+
+
+def drive(kind):
+    """Run all jobs of `kind` in as few worker processes as possible: a worker that traps / hangs is replaced
+    and the sweep continues after the job that killed it."""
+    n = len(CASES) if kind == "case" else len(TIMING)
+    names = [c[0] for c in (CASES if kind == "case" else TIMING)]
+    start = 0
+    while start < n:
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", kind, str(start)],
+                               capture_output=True, text=True, timeout=600)
+            out, rc = p.stdout, p.returncode
+            err = p.stderr
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            err, rc = "timeout", "timeout"
+        last_begin = start - 1
+        for line in out.splitlines():
+            if line.startswith("RESULT "):
+                print(line[7:], flush=True)
+            elif line.startswith("BEGIN "):
+                last_begin = int(line[6:])
+        done = sum(1 for l in out.splitlines() if l.startswith("RESULT "))
+        if start + done >= n:
+            break
+        failed = start + done
+        tail = [l for l in (err or "").strip().splitlines() if l.strip()][-2:]
+        print(json.dumps({"name": names[failed], "FAILED": rc, "tail": tail}), flush=True)
+        start = failed + 1
+
+
+def main():
+    if len(sys.argv) >= 4 and sys.argv[1] == "--worker":
+        return worker(sys.argv[2], int(sys.argv[3]))
+    drive("case")
+    if "--time" in sys.argv:
+        drive("timing")
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,8 @@
 //       HALO mode (3x3, stride 1, W % 128 == 0): a half is one image row segment of 128 pixels; the
 //                  mh+2 halo rows {chunk, 130 px} are loaded ONCE per channel chunk into a ring of
 //                  row slots and all 9 taps read them through shifted shared-memory descriptors
-//                  (start = slot + (dx+1)*128 B, descriptor base_offset = (start >> 7) & 7):
+//                  (start = slot + (dx+1)*128 B; the hardware derives the swizzle phase from the absolute
+//                  shared-memory address, so the descriptor's base_offset field stays 0 -- measured):
 //                  2.9x (mh=1) .. 4.3x (mh=2) fewer A bytes from L2 than per-tap boxes.
 //   B operand   packed weights [tap][Cout_pad][Cin], 3-D TMA box {chunk, n_tile, 1}; with mh = 2 one
 //               weight tile feeds both halves (halves the weight traffic per flop).
@@ -65,7 +66,8 @@ struct TcParams {
     int mh, n_tile, n_tiles, nchunks;
     int total_tiles;
     int halo, hp;            // hp = H / mh (halo mode)
-    int base_off;            // halo descriptors carry base_offset = (addr >> 7) & 7
+    int base_off;            // experiment: halo descriptors carry base_offset = (addr >> 7) & 7
+    unsigned long long *prof;   // optional cycle counters of CTA 0 (hl_conv_set_profile)
     int acc_stages, acc_stride, tmem_cols;
     int a_slots, a_slot_bytes, b_slots, b_slot_bytes, nbuf;
     const float *bias;
@@ -136,8 +138,10 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1): rows of 128
-// bytes, 8-row swizzle atoms 1024 bytes apart (SBO); LBO unused for swizzled K-major.  base_offset
-// = (addr >> 7) & 7 lets the start address sit on any 128 B row of the swizzle pattern (halo taps).
+// bytes, 8-row swizzle atoms 1024 bytes apart (SBO); LBO unused for swizzled K-major.  The start
+// address may sit on any 128 B row of a TMA-written tile (halo taps): the swizzle XOR is taken from
+// the absolute address bits [7,10), so base_offset stays 0 (setting it to (addr >> 7) & 7 was
+// measured to be WRONG on B200; kept switchable for the record).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t use_base_offset = 1u) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -188,6 +192,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// profiling: cycles CTA 0 spends blocked in each wait, accumulated into p.prof[slot]
+struct ProfTimer {
+    unsigned long long *dst;
+    long long t0;
+    __device__ __forceinline__ ProfTimer(unsigned long long *prof, int slot)
+        : dst(prof && blockIdx.x == 0 ? prof + slot : nullptr), t0(0) {
+        if (dst) t0 = clock64();
+    }
+    __device__ __forceinline__ ~ProfTimer() {
+        if (dst) atomicAdd(dst, (unsigned long long)(clock64() - t0));
+    }
+};
+#define PROF(slot) ProfTimer prof_timer_##slot(p.prof, slot)
 
 // origin (output pixel coordinates) of half `half` of m-tile `mt`
 __device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, int &w0, int &h0, int &n0) {
@@ -280,7 +298,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         box_origin(p, mt, 0, w0, h0, n0);
                         for (int r = 0; r < p.mh + 2; ++r, ++ai) {
                             const uint32_t s = ai % (uint32_t)p.a_slots, ph = (ai / (uint32_t)p.a_slots) & 1u;
-                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+                            { PROF(7); mbar_wait(bar_a_empty + 8 * s, ph ^ 1u); }
                             mbar_expect_tx(bar_a_full + 8 * s, HALO_ROW_BYTES);
                             tma_load_4d(smem_a + s * p.a_slot_bytes, &tmA, bar_a_full + 8 * s, c0, w0 - 1,
                                         h0 - 1 + r, n0);
@@ -289,7 +307,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int tap = 0; tap < p.taps; ++tap, ++ai) {
                             const uint32_t s = ai % (uint32_t)p.a_slots, ph = (ai / (uint32_t)p.a_slots) & 1u;
                             const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
-                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+                            { PROF(7); mbar_wait(bar_a_empty + 8 * s, ph ^ 1u); }
                             mbar_expect_tx(bar_a_full + 8 * s, (uint32_t)(p.mh * A_BOX_BYTES));
                             for (int half = 0; half < p.mh; ++half) {
                                 int w0, h0, n0;
@@ -312,7 +330,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int tap = 0; tap < p.taps; ++tap, ++bi) {
                         const uint32_t s = bi % (uint32_t)p.b_slots, ph = (bi / (uint32_t)p.b_slots) & 1u;
-                        mbar_wait(bar_b_empty + 8 * s, ph ^ 1u);
+                        { PROF(8); mbar_wait(bar_b_empty + 8 * s, ph ^ 1u); }
                         mbar_expect_tx(bar_b_full + 8 * s, bytes);
                         tma_load_3d(smem_b + s * p.b_slot_bytes, &tmB, bar_b_full + 8 * s, kc * chunk_elems, nt0,
                                     tap);
@@ -329,10 +347,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                    ((uint32_t)(BLOCK_M >> 4) << 24);
             uint32_t ai = 0, bi = 0;
             int it = 0;
+            PROF(0);
+            if (p.prof && blockIdx.x == 0) p.prof[10] = (unsigned long long)((p.total_tiles + gridDim.x - 1) / gridDim.x);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int as = it % p.acc_stages;
                 const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
-                mbar_wait(bar_t_empty + 8 * as, aph ^ 1u);
+                { PROF(2); mbar_wait(bar_t_empty + 8 * as, aph ^ 1u); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc0 = tmem_base + (uint32_t)(as * p.mh * p.acc_stride);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -343,12 +363,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int ty = 0; ty < 3; ++ty) {
                             while (rows_waited < ty + p.mh) {
                                 const uint32_t c = a_base + rows_waited;
-                                mbar_wait(bar_a_full + 8 * (c % (uint32_t)p.a_slots), (c / (uint32_t)p.a_slots) & 1u);
+                                { PROF(1); mbar_wait(bar_a_full + 8 * (c % (uint32_t)p.a_slots), (c / (uint32_t)p.a_slots) & 1u); }
                                 ++rows_waited;
                             }
                             for (int tx = 0; tx < 3; ++tx, ++bi) {
                                 const uint32_t sb = bi % (uint32_t)p.b_slots;
-                                mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u);
+                                { PROF(3); mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u); }
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                                 const uint32_t b0 = smem_b + sb * p.b_slot_bytes;
                                 for (int half = 0; half < p.mh; ++half) {
@@ -371,8 +391,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     } else {
                         for (int tap = 0; tap < p.taps; ++tap, ++ai, ++bi) {
                             const uint32_t sa = ai % (uint32_t)p.a_slots, sb = bi % (uint32_t)p.b_slots;
-                            mbar_wait(bar_a_full + 8 * sa, (ai / (uint32_t)p.a_slots) & 1u);
-                            mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u);
+                            { PROF(1); mbar_wait(bar_a_full + 8 * sa, (ai / (uint32_t)p.a_slots) & 1u); }
+                            { PROF(3); mbar_wait(bar_b_full + 8 * sb, (bi / (uint32_t)p.b_slots) & 1u); }
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint32_t b0 = smem_b + sb * p.b_slot_bytes;
                             for (int half = 0; half < p.mh; ++half) {
@@ -439,7 +459,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
             const int nt0 = (tile % p.n_tiles) * p.n_tile;
             const int mt = tile / p.n_tiles;
-            mbar_wait(bar_t_full + 8 * as, aph);
+            if (et == 1) { PROF(4); mbar_wait(bar_t_full + 8 * as, aph); } else mbar_wait(bar_t_full + 8 * as, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
@@ -458,7 +478,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t srow = sbuf + (uint32_t)row * 128u;
                     float v[32];
                     tmem_ld32(acc + (uint32_t)(cc * 32), v);
-                    if (p.has_res) mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
+                    if (p.has_res) {
+                        if (et == 1) { PROF(5); mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u); }
+                        else mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 bz = __ldg(reinterpret_cast<const float4 *>(p.bias + nbase) + j);
@@ -479,14 +502,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (!p.has_res && e0) {
                         // the buffer the NEXT chunk writes must have been read out by its old store
+                        PROF(9);
                         if (p.nbuf == 2) bulk_wait_read<0>(); else bulk_wait_read<2>();
                     }
-                    named_bar(1, EPI_THREADS);
+                    if (et == 1) { PROF(6); named_bar(1, EPI_THREADS); } else named_bar(1, EPI_THREADS);
                     if (e0) {
                         tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0);
                         bulk_commit();
                         if (p.has_res) {
-                            bulk_wait_read<1>();      // store(qn-1) has drained its buffer -> refill it
+                            { PROF(9); bulk_wait_read<1>(); }     // store(qn-1) has drained its buffer -> refill it
                             issue_res_load();
                         }
                     }
@@ -579,6 +603,7 @@ bool pick_tiling(int H, int W, Tiling *t) {
 
 // tuning overrides (-1 = automatic); set through hl_conv_set_tuning (tests / experiments)
 int g_tune_mh = -1, g_tune_ntile = -1, g_tune_halo = -1, g_tune_epi_stats = -1, g_tune_base_off = -1;
+unsigned long long *g_prof = nullptr;
 
 struct Plan {
     TcParams p;
@@ -648,7 +673,8 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
         n_tile = g_tune_ntile;
 
     p.halo = halo;
-    p.base_off = g_tune_base_off == 0 ? 0 : 1;
+    p.prof = g_prof;
+    p.base_off = g_tune_base_off == 1 ? 1 : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits
     p.mh = mh;
     p.hp = halo ? H / mh : 1;
     p.n_tile = n_tile;
@@ -714,6 +740,11 @@ extern "C" int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, i
     g_tune_ntile = n_tile;
     g_tune_halo = halo;
     g_tune_epi_stats = epi_stats;
+    return HL_OK;
+}
+
+extern "C" int hl_conv_set_profile(void *dev_counters) {
+    g_prof = (unsigned long long *)dev_counters;
     return HL_OK;
 }
 

@@ -215,9 +215,12 @@ def _check_stats(st, y, Cout):
 def test_conv_simt_exact(dev, shape, mode):
     from humanliff_b200 import _lib
     B, H, W, Cin, Cout, k, s = shape
-    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, flags=_lib.CONV_FORCE_SIMT, stats=True)
+    want_stats = Cout % 4 == 0                     # the statistics kernel works on channel quads
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, flags=_lib.CONV_FORCE_SIMT,
+                                   stats=want_stats)
     assert rel_l2(y, ref_r) < 2e-6 and rel_max(y, ref_r) < 2e-5
-    _check_stats(st, y, Cout)
+    if want_stats:
+        _check_stats(st, y, Cout)
 
 
 def test_conv_simt_upsample_folded(dev):

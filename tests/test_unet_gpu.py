@@ -65,8 +65,9 @@ def test_free_running_loop_vs_reference_golden(precision):
 
 
 def test_cuda_graph_replay_equals_eager():
-    """The step plan replayed as a CUDA graph must reproduce the eager launch list bit for bit, call after call
-    (statistics buffers are re-zeroed inside the graph), and pick up new inputs."""
+    """The step plan replayed as a CUDA graph must reproduce the eager launch list call after call (statistics
+    buffers are re-zeroed inside the graph) and pick up new inputs.  Not bit-for-bit: the fp64 atomics of the
+    GroupNorm statistics commute only up to ~1e-16, which occasionally flips the last fp32 bit downstream."""
     model, diffusion, g, _, _ = _model("tiny", "fp16")
     dev = torch.device("cuda:0")
     x, xc, y = g["x"].to(dev), g["x_cond"].to(dev), g["y"].to(dev)
@@ -76,8 +77,8 @@ def test_cuda_graph_replay_equals_eager():
     e2 = model(0.5 * x, ts + 7, xc, y=y)
     model.use_cuda_graph = True
     outs = [model(x, ts, xc, y=y) for _ in range(3)]          # eager, capture + replay, replay
-    assert all(torch.equal(o, e1) for o in outs)
-    assert torch.equal(model(0.5 * x, ts + 7, xc, y=y), e2)
+    assert all(rel_l2(o, e1) < 1e-6 for o in outs), [rel_l2(o, e1) for o in outs]
+    assert rel_l2(model(0.5 * x, ts + 7, xc, y=y), e2) < 1e-6
     plan = next(iter(model._plans.values()))
     assert plan.graph is not None
 

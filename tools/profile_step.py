@@ -1,17 +1,17 @@
-"""One production p_sample step (B=4, 27x256x256) bracketed by cudaProfilerStart/Stop, for
-    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv ...
-Never a bench number: ncu serialises launches and runs them cold-cache."""
+"""One production p_sample step (B=4, 27x256x256) between cudaProfilerStart/Stop, for
+`ncu --profile-from-start off`.  The step is launched EAGERLY (no CUDA graph) so every kernel is visible."""
 import os
 import sys
 
-import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from bench import build_model  # noqa: E402
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-
-B = int(os.environ.get("HL_PROFILE_BATCH", "4"))
 dev = torch.device("cuda:0")
-model, diffusion, _ = bench.build_model(dev)
+B = int(os.environ.get("HL_BATCH", "4"))
+model, diffusion, _ = build_model(dev, os.environ.get("HL_PRECISION", "fp16"))
+model.use_cuda_graph = False
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, 27, 256, 256, generator=g).to(dev)
 xc = torch.zeros_like(x)
@@ -21,7 +21,7 @@ t = torch.full((B,), 500, dtype=torch.int64, device=dev)
 for _ in range(2):
     diffusion.p_sample(model, x, xc, t, model_kwargs={"y": y}, noise=z)
 torch.cuda.synchronize()
-torch.cuda.profiler.start()
+torch.cuda.cudart().cudaProfilerStart()
 diffusion.p_sample(model, x, xc, t, model_kwargs={"y": y}, noise=z)
 torch.cuda.synchronize()
-torch.cuda.profiler.stop()
+torch.cuda.cudart().cudaProfilerStop()

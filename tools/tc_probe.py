@@ -32,16 +32,18 @@ CASES = [
 ]
 
 TIMING = [
-    # name, tuning  -- conv3x3 192->192 @ 256x256, B=4, residual + stats (the dominant launch)
-    ("tap mh1 n192", (1, 192, 0, -1, -1)),
-    ("tap mh2 n192", (2, 192, 0, -1, -1)),
-    ("tap mh2 n96", (2, 96, 0, -1, -1)),
-    ("halo mh1 n192", (1, 192, 1, -1, -1)),
-    ("halo mh2 n192", (2, 192, 1, -1, -1)),
-    ("halo mh2 n96", (2, 96, 1, -1, -1)),
-    ("halo mh2 n192 nostats", (2, 192, 1, 0, -1)),
+    # name, tuning, residual, stats  -- conv3x3 192->192 @ 256x256, B=4 (the dominant launch)
+    ("tap mh1 n192 res+stats", (1, 192, 0, -1, -1), True, True),
+    ("tap mh1 n192 plain", (1, 192, 0, -1, -1), False, False),
+    ("tap mh1 n192 stats", (1, 192, 0, -1, -1), False, True),
+    ("tap mh1 n192 res", (1, 192, 0, -1, -1), True, False),
+    ("halo mh1 n192 res+stats", (1, 192, 1, -1, -1), True, True),
+    ("halo mh1 n192 plain", (1, 192, 1, -1, -1), False, False),
+    ("halo mh2 n192 res+stats", (2, 192, 1, -1, -1), True, True),
+    ("halo mh2 n192 plain", (2, 192, 1, -1, -1), False, False),
+    ("halo mh2 n96 plain", (2, 96, 1, -1, -1), False, False),
+    ("tap mh2 n192 plain", (2, 192, 0, -1, -1), False, False),
 ]
-
 
 def run_case(idx):
     import torch
@@ -67,7 +69,7 @@ def run_timing(idx):
     from humanliff_b200 import _lib
     from humanliff_b200._lib import call
     from humanliff_b200.unet import pack_conv
-    name, tuning = TIMING[idx]
+    name, tuning, residual, stats = TIMING[idx]
     dev = torch.device("cuda:0")
     B, HW, Cin, Cout = 4, 256, 192, 192
     g = torch.Generator().manual_seed(0)
@@ -76,6 +78,7 @@ def run_timing(idx):
     rs = [torch.randn(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
     ys = [torch.empty(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
     st = torch.zeros(B * Cout * 2, device=dev, dtype=torch.float64)
+    prof = torch.zeros(16, device=dev, dtype=torch.int64)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / 41.6
     wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, "fp16", dev)
     lib = _lib.load()
@@ -83,8 +86,9 @@ def run_timing(idx):
     stream = torch.cuda.current_stream(dev)
 
     def launch(i):
-        call("hl_conv2d", xs[i % nbuf].data_ptr(), 1, Cin, wpk.data_ptr(), bpk.data_ptr(), rs[i % nbuf].data_ptr(), Cout,
-             ys[i % nbuf].data_ptr(), Cout, st.data_ptr(), Cout, B, HW, HW, Cin, Cout, 3, 1, 0, stream.cuda_stream)
+        call("hl_conv2d", xs[i % nbuf].data_ptr(), 1, Cin, wpk.data_ptr(), bpk.data_ptr(),
+             rs[i % nbuf].data_ptr() if residual else None, Cout, ys[i % nbuf].data_ptr(), Cout,
+             st.data_ptr() if stats else None, Cout, B, HW, HW, Cin, Cout, 3, 1, 0, stream.cuda_stream)
     for i in range(3):
         launch(i)
     torch.cuda.synchronize()
@@ -97,7 +101,16 @@ def run_timing(idx):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * B * HW * HW * Cout * Cin * 9 / (ms * 1e-3) / 1e12
-    print("RESULT " + json.dumps({"name": name, "ms": round(ms, 4), "tflops": round(tf, 1)}))
+    # one more launch with the in-kernel wait counters of CTA 0 switched on
+    lib.hl_conv_set_profile(prof.data_ptr())
+    launch(0)
+    torch.cuda.synchronize()
+    lib.hl_conv_set_profile(None)
+    pr = prof.cpu().tolist()
+    keys = ["total", "mma_wait_A", "mma_wait_tmem_empty", "mma_wait_B", "epi_wait_tmem_full", "epi_wait_res",
+            "epi_barrier", "prodA_wait_empty", "prodB_wait_empty", "e0_store_drain", "tiles"]
+    print("RESULT " + json.dumps({"name": name, "ms": round(ms, 4), "tflops": round(tf, 1),
+                                  "prof_kcycles": {k: (round(v / 1e3, 1) if k != "tiles" else v) for k, v in zip(keys, pr)}}))
 
 
 def worker(kind, start):

@@ -89,10 +89,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded spin: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
+// Bounded wait (~2 s of SM clock): a protocol bug becomes a trap (an error the host sees) instead of a
+// hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    const long long t_start = clock64();
+    for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -101,6 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+        if ((it & 1023u) == 1023u && clock64() - t_start > 4000000000ll) break;
     }
     __trap();
 }
@@ -197,8 +200,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 struct ProfTimer {
     unsigned long long *dst;
     long long t0;
-    __device__ __forceinline__ ProfTimer(unsigned long long *prof, int slot)
-        : dst(prof && blockIdx.x == 0 ? prof + slot : nullptr), t0(0) {
+    __device__ __forceinline__ ProfTimer(unsigned long long *prof, int slot, bool on = true)
+        : dst(prof && on && blockIdx.x == 0 ? prof + slot : nullptr), t0(0) {
         if (dst) t0 = clock64();
     }
     __device__ __forceinline__ ~ProfTimer() {
@@ -206,6 +209,7 @@ struct ProfTimer {
     }
 };
 #define PROF(slot) ProfTimer prof_timer_##slot(p.prof, slot)
+#define PROF_IF(slot, cond) ProfTimer prof_timer_##slot(p.prof, slot, cond)   // warp-convergent: all threads time
 
 // origin (output pixel coordinates) of half `half` of m-tile `mt`
 __device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, int &w0, int &h0, int &n0) {
@@ -459,7 +463,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
             const int nt0 = (tile % p.n_tiles) * p.n_tile;
             const int mt = tile / p.n_tiles;
-            if (et == 1) { PROF(4); mbar_wait(bar_t_full + 8 * as, aph); } else mbar_wait(bar_t_full + 8 * as, aph);
+            { PROF_IF(4, et == 1); mbar_wait(bar_t_full + 8 * as, aph); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
@@ -479,8 +483,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float v[32];
                     tmem_ld32(acc + (uint32_t)(cc * 32), v);
                     if (p.has_res) {
-                        if (et == 1) { PROF(5); mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u); }
-                        else mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
+                        PROF_IF(5, et == 1);
+                        mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -505,7 +509,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         PROF(9);
                         if (p.nbuf == 2) bulk_wait_read<0>(); else bulk_wait_read<2>();
                     }
-                    if (et == 1) { PROF(6); named_bar(1, EPI_THREADS); } else named_bar(1, EPI_THREADS);
+                    { PROF_IF(6, et == 1); named_bar(1, EPI_THREADS); }
                     if (e0) {
                         tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0);
                         bulk_commit();

@@ -130,7 +130,7 @@ def drive(kind):
     while start < n:
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", kind, str(start)],
-                               capture_output=True, text=True, timeout=600)
+                               capture_output=True, text=True, timeout=150)
             out, rc = p.stdout, p.returncode
             err = p.stderr
         except subprocess.TimeoutExpired as e:

@@ -136,6 +136,18 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// exactly one lane of a fully converged warp gets 1 (the same lane every time): the issuing thread
+// of TMA / tcgen05 instructions.  Unlike `if (lane == 0)`, ptxas knows the guarded code runs on one
+// thread and keeps descriptors / barrier addresses in uniform registers without a waterfall loop.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -295,7 +307,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // Measured on B200: ~1000 cycles of scalar overhead per stage (runtime div/mod) capped the first
     // version of this kernel at 27 % of the tensor peak regardless of tile shape.
     if (warp == 0) {
-        if (lane == 0) {
+        {
             // ------------------------------ A producer ------------------------------
             // TAP mode shares the stage ring (and its barriers) with the B producer; HALO mode owns
             // the row ring.
@@ -311,10 +323,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int rows = p.mh + 2;
                     for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
                         for (int r = 0; r < rows; ++r) {
-                            { PROF(7); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
-                            mbar_expect_tx(full0 + 8 * slot, HALO_ROW_BYTES);
-                            tma_load_4d(smem_a + slot * slot_bytes, &tmA, full0 + 8 * slot, c0, w0[0] - 1,
-                                        h0[0] - 1 + r, n0[0]);
+                            { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
+                            if (elect_one_sync()) {
+                                mbar_expect_tx(full0 + 8 * slot, HALO_ROW_BYTES);
+                                tma_load_4d(smem_a + slot * slot_bytes, &tmA, full0 + 8 * slot, c0, w0[0] - 1,
+                                            h0[0] - 1 + r, n0[0]);
+                            }
+                            __syncwarp();
                             if (++slot == nslots) { slot = 0; phase ^= 1u; }
                         }
                     }
@@ -325,12 +340,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
                         for (int ty = 0; ty < p.ksize; ++ty) {
                             for (int tx = 0; tx < p.ksize; ++tx) {
-                                { PROF(7); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
-                                mbar_expect_tx(full0 + 8 * slot, bytes);
-                                const uint32_t dst = smem_a + slot * slot_bytes;
-                                tma_load_4d(dst, &tmA, full0 + 8 * slot, c0, xs0 + tx, ys0 + ty, n0[0]);
-                                if (p.mh == 2)
-                                    tma_load_4d(dst + A_BOX_BYTES, &tmA, full0 + 8 * slot, c0, xs1 + tx, ys1 + ty, n0[1]);
+                                { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
+                                if (elect_one_sync()) {
+                                    mbar_expect_tx(full0 + 8 * slot, bytes);
+                                    const uint32_t dst = smem_a + slot * slot_bytes;
+                                    tma_load_4d(dst, &tmA, full0 + 8 * slot, c0, xs0 + tx, ys0 + ty, n0[0]);
+                                    if (p.mh == 2)
+                                        tma_load_4d(dst + A_BOX_BYTES, &tmA, full0 + 8 * slot, c0, xs1 + tx, ys1 + ty,
+                                                    n0[1]);
+                                }
+                                __syncwarp();
                                 if (++slot == nslots) { slot = 0; phase ^= 1u; }
                             }
                         }
@@ -339,7 +358,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // ------------------------------ B producer ------------------------------
             const uint32_t bytes = (uint32_t)(p.n_tile * ROW_BYTES);
             const uint32_t nslots = (uint32_t)p.b_slots, slot_bytes = (uint32_t)p.b_slot_bytes;
@@ -348,16 +367,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int nt0 = (tile % p.n_tiles) * p.n_tile;
                 for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
                     for (int tap = 0; tap < p.taps; ++tap) {
-                        { PROF(8); mbar_wait(bar_b_empty + 8 * slot, phase ^ 1u); }
-                        mbar_expect_tx(bar_b_full + 8 * slot, bytes);
-                        tma_load_3d(smem_b + slot * slot_bytes, &tmB, bar_b_full + 8 * slot, c0, nt0, tap);
+                        { PROF_IF(8, lane == 0); mbar_wait(bar_b_empty + 8 * slot, phase ^ 1u); }
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(bar_b_full + 8 * slot, bytes);
+                            tma_load_3d(smem_b + slot * slot_bytes, &tmB, bar_b_full + 8 * slot, c0, nt0, tap);
+                        }
+                        __syncwarp();
                         if (++slot == nslots) { slot = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
+        {
             // ------------------------------ MMA issuer --------------------------------
             // instruction descriptor: D=f32, A/B format (0 = f16, 2 = tf32), both K-major, N>>3 @17, M>>4 @24
             const uint32_t fmt = p.kind ? 0u : 2u;
@@ -376,13 +398,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t sb = 0, phb = 0;      // B ring (= the stage ring in TAP mode)
             uint32_t sa = 0, pha = 0;      // A row ring (HALO mode)
             int it = 0;
-            PROF(0);
-            if (p.prof && blockIdx.x == 0) p.prof[10] = (unsigned long long)((p.total_tiles + gridDim.x - 1) / gridDim.x);
+            PROF_IF(0, lane == 0);
+            if (p.prof && blockIdx.x == 0 && lane == 0) p.prof[10] = (unsigned long long)((p.total_tiles + gridDim.x - 1) / gridDim.x);
             const int steps = p.kchunks * p.taps;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int as = p.acc_stages == 2 ? (it & 1) : 0;
                 const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
-                { PROF(2); mbar_wait(bar_t_empty + 8 * as, aph ^ 1u); }
+                { PROF_IF(2, lane == 0); mbar_wait(bar_t_empty + 8 * as, aph ^ 1u); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc0 = tmem_base + (uint32_t)(as * p.mh * p.acc_stride);
                 const uint32_t acc1 = acc0 + (uint32_t)p.acc_stride;
@@ -403,58 +425,67 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int ty = 0; ty < 3; ++ty) {
                             // tap row ty reads halo rows ty (half 0) and ty+1 (half 1)
                             if (ty == 0) {
-                                { PROF(1); mbar_wait(bar_a_full + 8 * row_bar[0], row_par[0]); }
-                                if (p.mh == 2) { PROF(1); mbar_wait(bar_a_full + 8 * row_bar[1], row_par[1]); }
+                                { PROF_IF(1, lane == 0); mbar_wait(bar_a_full + 8 * row_bar[0], row_par[0]); }
+                                if (p.mh == 2) { PROF_IF(1, lane == 0); mbar_wait(bar_a_full + 8 * row_bar[1], row_par[1]); }
                             } else {
-                                PROF(1);
+                                PROF_IF(1, lane == 0);
                                 const uint32_t rb = p.mh == 2 ? row_bar[ty + 1] : row_bar[ty];
                                 const uint32_t rp = p.mh == 2 ? row_par[ty + 1] : row_par[ty];
                                 mbar_wait(bar_a_full + 8 * rb, rp);
                             }
 #pragma unroll
                             for (int tx = 0; tx < 3; ++tx) {
-                                { PROF(3); mbar_wait(bar_b_full + 8 * sb, phb); }
+                                { PROF_IF(3, lane == 0); mbar_wait(bar_b_full + 8 * sb, phb); }
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                const uint64_t bd = desc(smem_b + sb * b_bytes);
-                                const uint64_t ad0 = desc(row_addr[ty] + tx * ROW_BYTES);
-                                const uint32_t accf = (kc | ty | tx) != 0;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
-                                if (p.mh == 2) {
-                                    const uint64_t ad1 = desc(row_addr[ty + 1] + tx * ROW_BYTES);
+                                if (elect_one_sync()) {
+                                    const uint64_t bd = desc(smem_b + sb * b_bytes);
+                                    const uint64_t ad0 = desc(row_addr[ty] + tx * ROW_BYTES);
+                                    const uint32_t accf = (kc | ty | tx) != 0;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                        umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                    if (p.mh == 2) {
+                                        const uint64_t ad1 = desc(row_addr[ty + 1] + tx * ROW_BYTES);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                    }
+                                    umma_commit(bar_b_empty + 8 * sb);
+                                    // halo row `ty` is not needed by later taps; the last tap row frees the rest
+                                    if (tx == 2) {
+                                        umma_commit(bar_a_empty + 8 * row_bar[ty]);
+                                        if (ty == 2 && p.mh == 2) umma_commit(bar_a_empty + 8 * row_bar[3]);
+                                    }
                                 }
-                                umma_commit(bar_b_empty + 8 * sb);
+                                __syncwarp();
                                 if (++sb == nb) { sb = 0; phb ^= 1u; }
-                            }
-                            // halo row `ty` is not needed by later taps; the last tap row frees the rest
-                            umma_commit(bar_a_empty + 8 * row_bar[ty]);
-                            if (ty == 2) {
-                                if (p.mh == 2) umma_commit(bar_a_empty + 8 * row_bar[3]);
                             }
                         }
                     }
                 } else {
                     for (int st = 0; st < steps; ++st) {
-                        { PROF(3); mbar_wait(bar_b_full + 8 * sb, phb); }
+                        { PROF_IF(3, lane == 0); mbar_wait(bar_b_full + 8 * sb, phb); }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t bd = desc(smem_b + sb * b_bytes);
-                        const uint64_t ad0 = desc(smem_a + sb * a_bytes);
-                        const uint32_t accf = st != 0;
+                        if (elect_one_sync()) {
+                            const uint64_t bd = desc(smem_b + sb * b_bytes);
+                            const uint64_t ad0 = desc(smem_a + sb * a_bytes);
+                            const uint32_t accf = st != 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
-                        if (p.mh == 2) {
-                            const uint64_t ad1 = ad0 + (A_BOX_BYTES >> 4);
+                            for (int k = 0; k < 4; ++k) umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                            if (p.mh == 2) {
+                                const uint64_t ad1 = ad0 + (A_BOX_BYTES >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                for (int k = 0; k < 4; ++k)
+                                    umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                            }
+                            umma_commit(bar_b_empty + 8 * sb);
                         }
-                        umma_commit(bar_b_empty + 8 * sb);
+                        __syncwarp();
                         if (++sb == nb) { sb = 0; phb ^= 1u; }
                     }
                 }
-                umma_commit(bar_t_full + 8 * as);   // accumulators complete -> epilogue
+                if (elect_one_sync()) umma_commit(bar_t_full + 8 * as);   // accumulators complete -> epilogue
+                __syncwarp();
             }
         }
     } else {

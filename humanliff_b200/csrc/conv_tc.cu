@@ -57,7 +57,7 @@ constexpr int NUM_THREADS = 7 * 32;
 constexpr int EPI_THREADS = 128;
 constexpr int STATS_MAX_C = 768;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 8 * 1024;   // static smem: barriers + statistics accumulators
+constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 14 * 1024;  // static smem: barriers + fp64 statistics accumulators (12 KB)
 
 struct TcParams {
     int B, H, W;             // OUTPUT spatial size
@@ -248,7 +248,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + MAX_NBUF];
     __shared__ uint32_t tmem_slot;
-    __shared__ float sacc[2][STATS_MAX_C];
+    // per-CTA channel sums in fp64: floating-point atomics commute only up to rounding, and fp64 rounding
+    // (1e-16) is far below the fp32 resolution of everything downstream -> results are reproducible run to run
+    __shared__ double sacc[2][STATS_MAX_C];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -293,7 +295,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 3 && p.stats) {
-        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_THREADS) (&sacc[0][0])[i] = 0.f;
+        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_THREADS) (&sacc[0][0])[i] = 0.0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -523,10 +525,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             named_bar(2, EPI_THREADS);
             for (int c = et; c < p.Cout; c += EPI_THREADS) {
                 double *dst = p.stats + ((size_t)cur_n * p.stats_ld + c) * 2;
-                atomicAdd(dst, (double)sacc[0][c]);
-                atomicAdd(dst + 1, (double)sacc[1][c]);
-                sacc[0][c] = 0.f;
-                sacc[1][c] = 0.f;
+                atomicAdd(dst, sacc[0][c]);
+                atomicAdd(dst + 1, sacc[1][c]);
+                sacc[0][c] = 0.0;
+                sacc[1][c] = 0.0;
             }
             named_bar(2, EPI_THREADS);
         };
@@ -607,8 +609,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 s += x;
                                 ss = fmaf(x, x, ss);
                             }
-                            atomicAdd(&sacc[0][nbase + col], s);
-                            atomicAdd(&sacc[1][nbase + col], ss);
+                            atomicAdd(&sacc[0][nbase + col], (double)s);
+                            atomicAdd(&sacc[1][nbase + col], (double)ss);
                         }
                     }
                 }

@@ -332,13 +332,13 @@ extern "C" int hl_linear_small(const float *x, const float *W, const float *bias
 #define GN_MAX_C 2048
 __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int pix_per_block,
                            double *__restrict__ stats, int stats_ld) {
-    __shared__ float s_sum[GN_MAX_C];
-    __shared__ float s_sq[GN_MAX_C];
+    __shared__ double s_sum[GN_MAX_C];   // fp64: atomics then commute to ~1e-16 -> reproducible statistics
+    __shared__ double s_sq[GN_MAX_C];
     int b = blockIdx.y;
     int q = C >> 2;
     int lanes_p = blockDim.x / q;  // pixels processed concurrently (blockDim.x is a multiple of q)
     int tq = threadIdx.x % q, tp = threadIdx.x / q;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.0; s_sq[i] = 0.0; }
     __syncthreads();
     int p0 = blockIdx.x * pix_per_block;
     int p1 = min(HW, p0 + pix_per_block);
@@ -351,16 +351,16 @@ __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, 
             ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y);
             ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
         }
-        atomicAdd(&s_sum[4 * tq + 0], s.x); atomicAdd(&s_sq[4 * tq + 0], ss.x);
-        atomicAdd(&s_sum[4 * tq + 1], s.y); atomicAdd(&s_sq[4 * tq + 1], ss.y);
-        atomicAdd(&s_sum[4 * tq + 2], s.z); atomicAdd(&s_sq[4 * tq + 2], ss.z);
-        atomicAdd(&s_sum[4 * tq + 3], s.w); atomicAdd(&s_sq[4 * tq + 3], ss.w);
+        atomicAdd(&s_sum[4 * tq + 0], (double)s.x); atomicAdd(&s_sq[4 * tq + 0], (double)ss.x);
+        atomicAdd(&s_sum[4 * tq + 1], (double)s.y); atomicAdd(&s_sq[4 * tq + 1], (double)ss.y);
+        atomicAdd(&s_sum[4 * tq + 2], (double)s.z); atomicAdd(&s_sq[4 * tq + 2], (double)ss.z);
+        atomicAdd(&s_sum[4 * tq + 3], (double)s.w); atomicAdd(&s_sq[4 * tq + 3], (double)ss.w);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double *dst = stats + ((int64_t)b * stats_ld + c) * 2;
-        atomicAdd(dst, (double)s_sum[c]);
-        atomicAdd(dst + 1, (double)s_sq[c]);
+        atomicAdd(dst, s_sum[c]);
+        atomicAdd(dst + 1, s_sq[c]);
     }
 }
 
@@ -435,20 +435,32 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
     const int64_t pix0 = (int64_t)b * HW + p0;
     const int dp = blockDim.x / q, dj = blockDim.x % q;
     int p = threadIdx.x / q, j = threadIdx.x % q;
+    constexpr int U = 4;                       // independent 128-bit loads in flight per thread
     while (p < np) {
-        const int64_t pix = pix0 + p;
-        const float4 v = *reinterpret_cast<const float4 *>(x + pix * ldx + 4 * j);
-        const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
-        const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
-        float4 o;
-        o.x = fmaf(v.x, a.x, c.x); o.y = fmaf(v.y, a.y, c.y);
-        o.z = fmaf(v.z, a.z, c.z); o.w = fmaf(v.w, a.w, c.w);
-        if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
-        store_quad(y, y_dtype, pix * ldy + 4 * j, o, round_tf32);
-        if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, round_tf32);
-        p += dp;
-        j += dj;
-        if (j >= q) { j -= q; ++p; }
+        int pp[U], jj[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pp[u] = p;
+            jj[u] = j;
+            if (p < np) v[u] = __ldcs(reinterpret_cast<const float4 *>(x + (pix0 + p) * ldx + 4 * j));
+            p += dp;
+            j += dj;
+            if (j >= q) { j -= q; ++p; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (pp[u] >= np) break;
+            const int64_t pix = pix0 + pp[u];
+            const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * jj[u]]);
+            const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * jj[u]]);
+            float4 o;
+            o.x = fmaf(v[u].x, a.x, c.x); o.y = fmaf(v[u].y, a.y, c.y);
+            o.z = fmaf(v[u].z, a.z, c.z); o.w = fmaf(v[u].w, a.w, c.w);
+            if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
+            store_quad(y, y_dtype, pix * ldy + 4 * jj[u], o, round_tf32);
+            if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * jj[u], v[u], round_tf32);
+        }
     }
 }
 

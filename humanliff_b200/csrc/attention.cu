@@ -172,6 +172,169 @@ int launch(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, 
     return HL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core version (operand mode fp16): the same flash-style algorithm with both contractions on
+// mma.sync m16n8k16 (fp16 operands, fp32 accumulate) -- Q, K, V and the softmax weights P are rounded
+// to fp16 exactly like every other GEMM operand of the denoise path; scores, running max / sum and the
+// output accumulator stay fp32.  One CTA = 64 query rows of one (sample, head), 4 warps x 16 rows;
+// K / V tiles of 64 keys are converted to fp16 on their way into shared memory (row pitch padded by
+// 16 B so ldmatrix is conflict-free).  T x T scores never leave registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__ qkv, int ldq,
+                                                       __half *__restrict__ out, int ldo, int T, float scale_log2e) {
+    constexpr int PITCH = CH * 2 + 16;          // bytes per smem row
+    constexpr int KS = CH / 16;                 // k steps of Q.K^T
+    constexpr int NO = CH / 8;                  // n tiles of the output
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t *Qs = smraw, *Ks = Qs + 64 * PITCH, *Vs = Ks + 64 * PITCH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+    const float *base = qkv + (int64_t)b * T * ldq + h * 3 * CH;
+
+    auto load_tile = [&](uint8_t *dst, int row0, int col0) {   // 64 rows x CH fp32 -> fp16 smem
+        for (int i = tid; i < 64 * (CH / 4); i += 128) {
+            const int r = i / (CH / 4), c4 = i % (CH / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < T) v = *reinterpret_cast<const float4 *>(base + (int64_t)(row0 + r) * ldq + col0 + 4 * c4);
+            uint2 u;
+            u.x = pack_h2(v.x, v.y);
+            u.y = pack_h2(v.z, v.w);
+            *reinterpret_cast<uint2 *>(dst + r * PITCH + c4 * 8) = u;
+        }
+    };
+    load_tile(Qs, q0, 0);
+
+    float o[NO][4];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;    // rows g and g+8 of this warp's 16
+    const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs) +
+                            (uint32_t)((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
+    const uint32_t k_addr = (uint32_t)__cvta_generic_to_shared(Ks) +
+                            (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
+    const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(Vs) +
+                            (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16);
+
+    for (int k0 = 0; k0 < T; k0 += 64) {
+        __syncthreads();                         // previous tile fully consumed (and Q visible)
+        load_tile(Ks, k0, CH);
+        load_tile(Vs, k0, 2 * CH);
+        __syncthreads();
+
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            uint32_t a[4];
+            ldsm_x4(q_addr + kk * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(k_addr + jp * 16 * PITCH + kk * 32, b0, b1, b2, b3);
+                mma16816(s[2 * jp], a, b0, b1);
+                mma16816(s[2 * jp + 1], a, b2, b3);
+            }
+        }
+        // scale (log2 domain), mask keys beyond T, online softmax
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int key = k0 + j * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool ok = key + (e & 1) < T;
+                s[j][e] = ok ? s[j][e] * scale_log2e : -INFINITY;
+            }
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile holds >= 1 valid key
+        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = exp2f(s[j][0] - mn0), p1 = exp2f(s[j][1] - mn0);
+            const float p2 = exp2f(s[j][2] - mn1), p3 = exp2f(s[j][3] - mn1);
+            sum0 += p0 + p1;
+            sum1 += p2 + p3;
+            pa[j >> 1][(j & 1) * 2 + 0] = pack_h2(p0, p1);
+            pa[j >> 1][(j & 1) * 2 + 1] = pack_h2(p2, p3);
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        l0 = l0 * al0 + sum0;
+        l1 = l1 * al1 + sum1;
+        m0 = mn0;
+        m1 = mn1;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) { o[j][0] *= al0; o[j][1] *= al0; o[j][2] *= al1; o[j][3] *= al1; }
+        // O += P . V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int np = 0; np < NO / 2; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(v_addr + kk * 16 * PITCH + np * 32, b0, b1, b2, b3);
+                mma16816(o[2 * np], pa[kk], b0, b1);
+                mma16816(o[2 * np + 1], pa[kk], b2, b3);
+            }
+        }
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        const int col = h * CH + j * 8 + 2 * t;
+        if (r0 < T) *reinterpret_cast<uint32_t *>(out + ((int64_t)b * T + r0) * ldo + col) = pack_h2(o[j][0] * inv0, o[j][1] * inv0);
+        if (r1 < T) *reinterpret_cast<uint32_t *>(out + ((int64_t)b * T + r1) * ldo + col) = pack_h2(o[j][2] * inv1, o[j][3] * inv1);
+    }
+}
+
+template <int CH>
+int launch_mma(const float *qkv, int ldq, __half *out, int ldo, int B, int T, int heads, cudaStream_t stream) {
+    constexpr int PITCH = CH * 2 + 16;
+    size_t smem = (size_t)3 * 64 * PITCH;
+    static bool configured = false;
+    if (!configured) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_attention_mma<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(hl_cdiv(T, 64), heads, B);
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)CH);
+    k_attention_mma<CH><<<grid, 128, smem, stream>>>(qkv, ldq, out, ldo, T, scale_log2e);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
 }  // namespace
 
 extern "C" int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
@@ -180,12 +343,23 @@ extern "C" int hl_attention(const float *qkv, int ldq, void *out, int out_dtype,
     HL_CHECK_ARG(ldq >= 3 * C && ldo >= C && ldq % 4 == 0);
     int ch = C / heads;
     cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == HL_DT_F16 && !(round_tf32 & 2) && ldo % 2 == 0 && ((uintptr_t)out & 3) == 0) {
+        __half *oh = (__half *)out;
+        switch (ch) {
+            case 32: return launch_mma<32>(qkv, ldq, oh, ldo, B, T, heads, st);
+            case 64: return launch_mma<64>(qkv, ldq, oh, ldo, B, T, heads, st);
+            case 96: return launch_mma<96>(qkv, ldq, oh, ldo, B, T, heads, st);
+            case 128: return launch_mma<128>(qkv, ldq, oh, ldo, B, T, heads, st);
+            case 192: return launch_mma<192>(qkv, ldq, oh, ldo, B, T, heads, st);
+            default: break;   // other head widths: CUDA-core kernel below
+        }
+    }
     switch (ch) {
-        case 32: return launch<32>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
-        case 64: return launch<64>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
-        case 96: return launch<96>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
-        case 128: return launch<128>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
-        case 192: return launch<192>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32, st);
+        case 32: return launch<32>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 64: return launch<64>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 96: return launch<96>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 128: return launch<128>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 192: return launch<192>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
         default:
             hl_set_error("hl_attention: unsupported head width %d (supported: 32,64,96,128,192)", ch);
             return HL_E_UNSUPPORTED;

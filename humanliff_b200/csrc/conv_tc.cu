@@ -731,21 +731,32 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     if (g_tune_mh == 1) mh = 1;
     if (g_tune_mh == 2 && !(halo ? (H % 2 == 0) : (boxes % 2 == 0))) mh = 1;
 
-    // (mh, n_tile): the largest legal UMMA N dividing cout_pad that still yields at least one CTA tile
-    // per SM, preferring two halves per CTA; problems too small to fill the machine take mh = 1 and
-    // a narrow tile (more CTAs = more TMA streams for their long, weight-bound K loops)
+    // (mh, n_tile).  Measured on B200 (profiles/r1_conv_tilings.md): a tcgen05.mma with M = 128 takes
+    // ~(128 + N)/2 cycles (operand fetch from shared memory), so wide N tiles win, and a double-buffered
+    // TMEM accumulator (epilogue overlapped with the next main loop) beats sharing a weight tile between
+    // two halves whenever both do not fit (mh * stride(N) * 2 <= 512 columns).  Preference order: the
+    // largest legal N that still yields one CTA tile per SM, with mh = 1 unless two halves keep the
+    // double buffer; problems too small to fill the machine take mh = 1 and a narrow tile (more CTAs =
+    // more TMA streams for their long, weight-bound K loops).
     static const int cand[] = {256, 192, 128, 96, 64, 32};
     int n_tile = 0;
     const int mh_max = mh;
-    for (int m = mh_max; m >= 1 && n_tile == 0; --m) {
-        if (g_tune_mh == 2 && m != mh_max) break;
-        for (int c : cand) {
-            if (cout_pad % c || m * acc_stride_for(c) > 512) continue;
-            if ((boxes / m) * (cout_pad / c) >= sms) { n_tile = c; mh = m; break; }
-        }
+    if (g_tune_mh != 2) mh = 1;
+    for (int c : cand) {
+        if (cout_pad % c) continue;
+        if ((boxes / mh) * (cout_pad / c) >= sms) { n_tile = c; break; }
+    }
+    if (n_tile != 0 && g_tune_mh != 1 && mh_max == 2 && 4 * acc_stride_for(n_tile) <= 512 &&
+        (boxes / 2) * (cout_pad / n_tile) >= sms)
+        mh = 2;                                   // two halves AND two accumulator stages fit
+    if (g_tune_mh == 2) {
+        mh = mh_max;
+        n_tile = 0;
+        for (int c : cand)
+            if (cout_pad % c == 0 && mh * acc_stride_for(c) <= 512) { n_tile = c; break; }
     }
     if (n_tile == 0) {
-        mh = (g_tune_mh == 2) ? mh_max : 1;
+        mh = 1;
         n_tile = cout_pad % 64 == 0 ? 64 : 32;
     }
     if (g_tune_ntile > 0 && cout_pad % g_tune_ntile == 0 && g_tune_ntile % 32 == 0 && g_tune_ntile <= 256 &&

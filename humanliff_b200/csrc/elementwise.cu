@@ -457,7 +457,13 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
             float4 o;
             o.x = fmaf(v[u].x, a.x, c.x); o.y = fmaf(v[u].y, a.y, c.y);
             o.z = fmaf(v[u].z, a.z, c.z); o.w = fmaf(v[u].w, a.w, c.w);
-            if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
+            if (silu) {
+                if (y_dtype == HL_DT_F16 || round_tf32) {
+                    o.x = hl_silu_fast(o.x); o.y = hl_silu_fast(o.y); o.z = hl_silu_fast(o.z); o.w = hl_silu_fast(o.w);
+                } else {
+                    o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w);
+                }
+            }
             store_quad(y, y_dtype, pix * ldy + 4 * jj[u], o, round_tf32);
             if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * jj[u], v[u], round_tf32);
         }

@@ -133,7 +133,10 @@ int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float 
 
 /* qkv: fp32 [B, T, 3C] rows (pitch ldq) with channel order [head][q(ch) k(ch) v(ch)];
  * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c], written as an operand
- * (out_dtype) for the proj_out GEMM.                                                             */
+ * (out_dtype) for the proj_out GEMM.  With an fp16 output both contractions run on the tensor
+ * cores (q, k, v, softmax weights rounded to fp16; scores / softmax / accumulation fp32); an fp32
+ * output selects the exact CUDA-core kernel.  round_tf32: bit 0 = TF32-round an fp32 output,
+ * bit 1 = force the CUDA-core kernel (tests).                                                     */
 int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
                  int heads, int round_tf32, void *stream);
 

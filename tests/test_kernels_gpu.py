@@ -137,12 +137,15 @@ def test_groupnorm_silu_film(dev, C, HW, B):
                   C, 32, 1e-5, 1 if silu else 0, 0, _stream())
             assert rel_l2(y.float().permute(0, 2, 1), r) < tol, (use_film, silu, code)
             assert torch.equal(raw.cpu(), x.to(tdt)), "raw operand copy of the input"
-            if code == 1:   # the fp16 operand is the correctly rounded fp32 result (up to 1 ulp of the fp32 value)
+            if code == 1:   # the fp16 operand is the rounded fp32 result; SiLU uses ex2/rcp.approx here (2e-7), so a
+                #             value sitting on an fp16 rounding boundary may land one fp16 ulp away
                 y32 = torch.empty(B, HW, C, device=dev)
                 _call("hl_gn_apply", xd.data_ptr(), C, stats.data_ptr(), ld_st, gd.data_ptr(), bd.data_ptr(),
                       fd.data_ptr() if use_film else None, 2 * C + 10, y32.data_ptr(), 0, C, None, 0, B, HW, C, 32,
                       1e-5, 1 if silu else 0, 0, _stream())
-                assert torch.equal(y.cpu(), y32.cpu().half())
+                exact = y32.cpu().half()
+                assert float((y.cpu() != exact).float().mean()) < 2e-3
+                assert rel_l2(y.float(), exact.float()) < 2e-5
 
 
 def _operand(t, mode):
@@ -260,7 +263,8 @@ def test_conv_tensor_core(dev, shape, mode):
     fl = _lib.CONV_TF32 if mode == "tf32" else 0
     ldy = (Cout + 3) // 4 * 4                      # output pitch: 16-byte rows for the TMA store
     assert lib.hl_conv2d_uses_tensor_cores(code, B, H, W, Cin, Cout, k, s, Cin, ldy, fl) == 1, "must take the tcgen05 path"
-    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, stats=Cout % 4 == 0, seed=7, ldy=ldy)
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, stats=Cout % 4 == 0, seed=7, ldy=ldy,
+                                   residual=Cout % 4 == 0)
     assert not torch.isnan(y).any()
     assert rel_l2(y, ref_r) < 2e-5, f"vs fp32 conv on identical (rounded) operands: {rel_l2(y, ref_r)}"
     assert rel_l2(y, ref) < 1e-3, f"vs fp32 reference: {rel_l2(y, ref)}"
@@ -320,8 +324,19 @@ def test_attention(dev, B, T, C, heads):
     assert rel_l2(out.permute(0, 2, 1), ref) < 5e-6
     assert rel_max(out.permute(0, 2, 1), ref) < 5e-5
     outh = torch.empty(B, T, C, device=dev, dtype=torch.float16)
-    _call("hl_attention", qd.data_ptr(), 3 * C, outh.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", qd.data_ptr(), 3 * C, outh.data_ptr(), 1, C, B, T, C, heads, 2, _stream())   # CUDA cores
     assert torch.equal(outh.cpu(), out.cpu().half())
+    # tensor-core kernel (mma.sync, fp16 operands / fp32 accumulate): vs the same attention evaluated in fp32 on
+    # the fp16-ROUNDED q, k, v (isolates the kernel from the operand rounding), and vs the exact result
+    outm = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
+    _call("hl_attention", qd.data_ptr(), 3 * C, outm.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    rh = qkv.half().float().reshape(B * heads, 3 * ch, T)
+    qh, kh, vh = torch.split(rh, ch, dim=1)
+    wh = torch.softmax(torch.einsum("bct,bcs->bts", qh, kh) / math.sqrt(ch), -1)
+    refh = torch.einsum("bts,bcs->bct", wh, vh).reshape(B, C, T)
+    assert not torch.isnan(outm.float()).any()
+    assert rel_l2(outm.float().permute(0, 2, 1), refh) < 6e-4      # P and the output rounded to fp16
+    assert rel_l2(outm.float().permute(0, 2, 1), ref) < 2e-3
 
 
 def test_ddpm_step_bit_exact(dev):

@@ -213,14 +213,27 @@ __global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__
     const float *base = qkv + (int64_t)b * T * ldq + h * 3 * CH;
 
     auto load_tile = [&](uint8_t *dst, int row0, int col0) {   // 64 rows x CH fp32 -> fp16 smem
-        for (int i = tid; i < 64 * (CH / 4); i += 128) {
-            const int r = i / (CH / 4), c4 = i % (CH / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < T) v = *reinterpret_cast<const float4 *>(base + (int64_t)(row0 + r) * ldq + col0 + 4 * c4);
-            uint2 u;
-            u.x = pack_h2(v.x, v.y);
-            u.y = pack_h2(v.z, v.w);
-            *reinterpret_cast<uint2 *>(dst + r * PITCH + c4 * 8) = u;
+        constexpr int N4 = 64 * (CH / 4), U = 8;               // U independent 128-bit loads in flight per thread
+        for (int i0 = tid; i0 < N4; i0 += 128 * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * 128;
+                const int r = i / (CH / 4), c4 = i % (CH / 4);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < N4 && row0 + r < T)
+                    v[u] = *reinterpret_cast<const float4 *>(base + (int64_t)(row0 + r) * ldq + col0 + 4 * c4);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * 128;
+                if (i >= N4) break;
+                const int r = i / (CH / 4), c4 = i % (CH / 4);
+                uint2 w;
+                w.x = pack_h2(v[u].x, v[u].y);
+                w.y = pack_h2(v[u].z, v[u].w);
+                *reinterpret_cast<uint2 *>(dst + r * PITCH + c4 * 8) = w;
+            }
         }
     };
     load_tile(Qs, q0, 0);

@@ -684,6 +684,7 @@ bool pick_tiling(int H, int W, Tiling *t) {
 // tuning overrides (-1 = automatic); set through hl_conv_set_tuning (tests / experiments)
 int g_tune_mh = -1, g_tune_ntile = -1, g_tune_halo = -1, g_tune_epi_stats = -1, g_tune_base_off = -1;
 unsigned long long *g_prof = nullptr;
+int g_tune_stages = -1, g_tune_nbuf = -1;   // experiment: cap on pipeline slots / staging buffers
 
 struct Plan {
     TcParams p;
@@ -783,6 +784,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     p.b_slot_bytes = n_tile * ROW_BYTES;
     p.has_res = has_res ? 1 : 0;
     int nbuf = has_res ? 4 : 2;
+    if (g_tune_nbuf == 2 || g_tune_nbuf == 4) nbuf = g_tune_nbuf;
     for (;;) {
         int rest = budget - nbuf * STAGE_BUF_BYTES;
         if (halo) {
@@ -794,10 +796,12 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
                 b_slots = (rest - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
             }
             p.b_slots = b_slots > MAX_SLOTS ? MAX_SLOTS : b_slots;
+            if (g_tune_stages >= 2 && p.b_slots > g_tune_stages) p.b_slots = g_tune_stages;
         } else {
             p.a_slot_bytes = mh * A_BOX_BYTES;
             int stages = rest / (p.a_slot_bytes + p.b_slot_bytes);
             if (stages > MAX_SLOTS) stages = MAX_SLOTS;
+            if (g_tune_stages >= 2 && stages > g_tune_stages) stages = g_tune_stages;
             p.a_slots = p.b_slots = stages;
         }
         if (p.b_slots >= 3 || nbuf == 2) break;
@@ -831,6 +835,12 @@ extern "C" int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, i
     g_tune_ntile = n_tile;
     g_tune_halo = halo;
     g_tune_epi_stats = epi_stats;
+    return HL_OK;
+}
+
+extern "C" int hl_conv_set_tuning2(int max_stages, int nbuf) {
+    g_tune_stages = max_stages;
+    g_tune_nbuf = nbuf;
     return HL_OK;
 }
 

@@ -32,17 +32,22 @@ CASES = [
 ]
 
 TIMING = [
-    # name, tuning, residual, stats  -- conv3x3 192->192 @ 256x256, B=4 (the dominant launch)
-    ("tap mh1 n192 res+stats", (1, 192, 0, -1, -1), True, True),
-    ("tap mh1 n192 plain", (1, 192, 0, -1, -1), False, False),
-    ("tap mh1 n192 stats", (1, 192, 0, -1, -1), False, True),
-    ("tap mh1 n192 res", (1, 192, 0, -1, -1), True, False),
-    ("halo mh1 n192 res+stats", (1, 192, 1, -1, -1), True, True),
-    ("halo mh1 n192 plain", (1, 192, 1, -1, -1), False, False),
-    ("halo mh2 n192 res+stats", (2, 192, 1, -1, -1), True, True),
-    ("halo mh2 n192 plain", (2, 192, 1, -1, -1), False, False),
-    ("halo mh2 n96 plain", (2, 96, 1, -1, -1), False, False),
-    ("tap mh2 n192 plain", (2, 192, 0, -1, -1), False, False),
+    # name, shape (B,H,W,Cin,Cout,k), tuning, tuning2 (max_stages, nbuf), residual, stats
+    ("3x3 192@256 plain auto", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1), False, False),
+    ("3x3 192@256 plain stages2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (2, -1), False, False),
+    ("3x3 192@256 plain stages3", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (3, -1), False, False),
+    ("3x3 192@256 res+stats auto", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 192@256 res+stats nbuf2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, 2), True, True),
+    ("3x3 192@256 res+stats tap", (4, 256, 256, 192, 192, 3), (1, 192, 0, -1, -1), (-1, -1), True, True),
+    ("1x1 192@256 res+stats", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1), True, True),
+    ("1x1 192@256 res+stats nbuf2", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, 2), True, True),
+    ("1x1 192@256 plain", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1), False, False),
+    ("3x3 768@16 res+stats", (4, 16, 16, 768, 768, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 768@16 res+stats n32", (4, 16, 16, 768, 768, 3), (1, 32, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 768@16 res+stats n128", (4, 16, 16, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 768@8 res+stats", (4, 8, 8, 768, 768, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 384@64 res+stats", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
+    ("3x3 384@64 res+stats mh2", (4, 64, 64, 384, 384, 3), (2, -1, -1, -1, -1), (-1, -1), True, True),
 ]
 
 def run_case(idx):
@@ -69,26 +74,28 @@ def run_timing(idx):
     from humanliff_b200 import _lib
     from humanliff_b200._lib import call
     from humanliff_b200.unet import pack_conv
-    name, tuning, residual, stats = TIMING[idx]
+    name, shape, tuning, tuning2, residual, stats = TIMING[idx]
     dev = torch.device("cuda:0")
-    B, HW, Cin, Cout = 4, 256, 192, 192
+    B, H, W, Cin, Cout, k = shape
     g = torch.Generator().manual_seed(0)
-    nbuf = 3
-    xs = [torch.randn(B, HW, HW, Cin, device=dev).half() for _ in range(nbuf)]
-    rs = [torch.randn(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
-    ys = [torch.empty(B, HW, HW, Cout, device=dev) for _ in range(nbuf)]
+    nbytes = B * H * W * (Cin * 2 + Cout * 8)
+    nbuf = max(3, min(64, int(400e6 // nbytes)))          # rotate through > 126 MB of L2
+    xs = [torch.randn(B, H, W, Cin, device=dev).half() for _ in range(nbuf)]
+    rs = [torch.randn(B, H, W, Cout, device=dev) for _ in range(nbuf)]
+    ys = [torch.empty(B, H, W, Cout, device=dev) for _ in range(nbuf)]
     st = torch.zeros(B * Cout * 2, device=dev, dtype=torch.float64)
     prof = torch.zeros(16, device=dev, dtype=torch.int64)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / 41.6
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
     wpk, bpk = pack_conv(w, torch.zeros(Cout), Cin, "fp16", dev)
     lib = _lib.load()
     lib.hl_conv_set_tuning(*tuning)
+    lib.hl_conv_set_tuning2(*tuning2)
     stream = torch.cuda.current_stream(dev)
 
     def launch(i):
         call("hl_conv2d", xs[i % nbuf].data_ptr(), 1, Cin, wpk.data_ptr(), bpk.data_ptr(),
              rs[i % nbuf].data_ptr() if residual else None, Cout, ys[i % nbuf].data_ptr(), Cout,
-             st.data_ptr() if stats else None, Cout, B, HW, HW, Cin, Cout, 3, 1, 0, stream.cuda_stream)
+             st.data_ptr() if stats else None, Cout, B, H, W, Cin, Cout, k, 1, 0, stream.cuda_stream)
     for i in range(3):
         launch(i)
     torch.cuda.synchronize()
@@ -100,7 +107,8 @@ def run_timing(idx):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    tf = 2.0 * B * HW * HW * Cout * Cin * 9 / (ms * 1e-3) / 1e12
+    tf = 2.0 * B * H * W * Cout * Cin * k * k / (ms * 1e-3) / 1e12
+    gbs = (B * H * W * (Cin * 2 + Cout * 4 * (2 if residual else 1))) / (ms * 1e-3) / 1e9
     # one more launch with the in-kernel wait counters of CTA 0 switched on
     lib.hl_conv_set_profile(prof.data_ptr())
     launch(0)
@@ -109,8 +117,8 @@ def run_timing(idx):
     pr = prof.cpu().tolist()
     keys = ["total", "mma_wait_A", "mma_wait_tmem_empty", "mma_wait_B", "epi_wait_tmem_full", "epi_wait_res",
             "epi_barrier", "prodA_wait_empty", "prodB_wait_empty", "e0_store_drain", "tiles"]
-    print("RESULT " + json.dumps({"name": name, "ms": round(ms, 4), "tflops": round(tf, 1),
-                                  "prof_kcycles": {k: (round(v / 1e3, 1) if k != "tiles" else v) for k, v in zip(keys, pr)}}))
+    print("RESULT " + json.dumps({"name": name, "ms": round(ms, 4), "tflops": round(tf, 1), "hbm_gbs": round(gbs),
+                                  "prof_kcycles": {k_: (round(v / 1e3, 1) if k_ != "tiles" else v) for k_, v in zip(keys, pr)}}))
 
 
 def worker(kind, start):

@@ -53,8 +53,9 @@ constexpr int HALO_SLOT_BYTES = 17 * 1024;            // rounded up to the 1024 
 constexpr int STAGE_BUF_BYTES = BLOCK_M * 128;        // epilogue staging: 128 rows x 32 fp32
 constexpr int MAX_SLOTS = 8;
 constexpr int MAX_NBUF = 4;
-constexpr int NUM_THREADS = 7 * 32;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_GROUPS = 2;                         // independent epilogue warpgroups (alternate chunks)
+constexpr int EPI_THREADS = 128;                      // threads per epilogue group (one per TMEM lane)
+constexpr int NUM_THREADS = (3 + 4 * EPI_GROUPS) * 32;
 constexpr int STATS_MAX_C = 768;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 14 * 1024;  // static smem: barriers + fp64 statistics accumulators (12 KB)
@@ -246,7 +247,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
           const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + MAX_NBUF];
+    __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + EPI_GROUPS * MAX_NBUF];
     __shared__ uint32_t tmem_slot;
     // per-CTA channel sums in fp64: floating-point atomics commute only up to rounding, and fp64 rounding
     // (1e-16) is far below the fp32 resolution of everything downstream -> results are reproducible run to run
@@ -282,9 +283,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(bar_t_full + 8 * s, 1);
-                mbar_init(bar_t_empty + 8 * s, EPI_THREADS);
+                mbar_init(bar_t_empty + 8 * s, EPI_GROUPS * EPI_THREADS);
             }
-            for (int s = 0; s < MAX_NBUF; ++s) mbar_init(bar_r_full + 8 * s, 1);
+            for (int s = 0; s < EPI_GROUPS * MAX_NBUF; ++s) mbar_init(bar_r_full + 8 * s, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -295,7 +296,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 3 && p.stats) {
-        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_THREADS) (&sacc[0][0])[i] = 0.0;
+        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_GROUPS * EPI_THREADS) (&sacc[0][0])[i] = 0.0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -492,54 +493,73 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else {
         // ---------------------------------- epilogue ----------------------------------
-        const int et = threadIdx.x - 96;          // 0..127
+        // Two independent warpgroups take alternate 32-column chunks (each with its own staging ring,
+        // named barrier, TMA-issuing thread and residual prefetch cursor): per chunk a thread runs a
+        // serial chain of ~200 instructions on its one accumulator row, so a single group is latency-
+        // bound (measured 1400-2900 cycles per chunk) and two groups double the drain rate.
+        const int ew = warp - 3;
+        const int eg = ew >> 2;                   // epilogue group
+        const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;            // GEMM row = pixel index inside the box
         const bool e0 = et == 0;
+        const bool pt = et == 1 && eg == 0;       // the thread whose waits are profiled
         const uint32_t sw = (uint32_t)(row & 7);
-        uint32_t qn = 0;                          // chunk counter (staging ring position)
+        const uint32_t smem_g = smem_e + (uint32_t)(eg * p.nbuf) * STAGE_BUF_BYTES;
+        const uint32_t bar_r = bar_r_full + 8u * (uint32_t)(eg * MAX_NBUF);
+        const uint32_t nbuf_mask = (uint32_t)p.nbuf - 1u, nbuf_shift = p.nbuf == 4 ? 2u : 1u;
+        uint32_t qn = 0;                          // global chunk counter of this CTA
+        uint32_t ql = 0;                          // chunks owned by this group so far (staging ring position)
         int cur_n = -1;                           // sample whose statistics sit in sacc
 
-        // residual prefetch cursor (thread e0 only): walks the same (tile, half, chunk) sequence
+        // residual prefetch cursor (thread e0 of the group): walks the same (tile, half, chunk) sequence
+        // and issues loads for the chunks this group owns
         int l_tile = blockIdx.x, l_half = 0, l_cc = 0;
-        uint32_t l_q = 0;
+        uint32_t l_qn = 0, l_ql = 0;
         auto issue_res_load = [&]() {
-            if (l_tile >= p.total_tiles) return;
-            const int nt0 = (l_tile % p.n_tiles) * p.n_tile;
-            int w0, h0, n0;
-            box_origin(p, l_tile / p.n_tiles, l_half, w0, h0, n0);
-            const uint32_t b = l_q % (uint32_t)p.nbuf;
-            mbar_expect_tx(bar_r_full + 8 * b, STAGE_BUF_BYTES);
-            tma_load_4d(smem_e + b * STAGE_BUF_BYTES, &tmR, bar_r_full + 8 * b, nt0 + l_cc * 32, w0, h0, n0);
-            ++l_q;
-            ++l_cc;
-            if (l_cc == p.nchunks || nt0 + l_cc * 32 >= p.Cout) {
-                l_cc = 0;
-                if (++l_half == p.mh) { l_half = 0; l_tile += gridDim.x; }
+            for (;;) {
+                if (l_tile >= p.total_tiles) return;
+                const int nt0 = (l_tile % p.n_tiles) * p.n_tile;
+                const bool mine = (int)(l_qn & (EPI_GROUPS - 1)) == eg;
+                if (mine) {
+                    int w0, h0, n0;
+                    box_origin(p, l_tile / p.n_tiles, l_half, w0, h0, n0);
+                    const uint32_t b = l_ql & nbuf_mask;
+                    mbar_expect_tx(bar_r + 8 * b, STAGE_BUF_BYTES);
+                    tma_load_4d(smem_g + b * STAGE_BUF_BYTES, &tmR, bar_r + 8 * b, nt0 + l_cc * 32, w0, h0, n0);
+                    ++l_ql;
+                }
+                ++l_qn;
+                ++l_cc;
+                if (l_cc == p.nchunks || nt0 + l_cc * 32 >= p.Cout) {
+                    l_cc = 0;
+                    if (++l_half == p.mh) { l_half = 0; l_tile += gridDim.x; }
+                }
+                if (mine) return;
             }
         };
         if (p.has_res && e0)
             for (int i = 0; i < p.nbuf - 1; ++i) issue_res_load();
 
         auto flush_stats = [&]() {
-            named_bar(2, EPI_THREADS);
-            for (int c = et; c < p.Cout; c += EPI_THREADS) {
+            named_bar(3, EPI_GROUPS * EPI_THREADS);
+            for (int c = eg * EPI_THREADS + et; c < p.Cout; c += EPI_GROUPS * EPI_THREADS) {
                 double *dst = p.stats + ((size_t)cur_n * p.stats_ld + c) * 2;
                 atomicAdd(dst, sacc[0][c]);
                 atomicAdd(dst + 1, sacc[1][c]);
                 sacc[0][c] = 0.0;
                 sacc[1][c] = 0.0;
             }
-            named_bar(2, EPI_THREADS);
+            named_bar(3, EPI_GROUPS * EPI_THREADS);
         };
 
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int as = it % p.acc_stages;
-            const uint32_t aph = (uint32_t)(it / p.acc_stages) & 1u;
+            const int as = p.acc_stages == 2 ? (it & 1) : 0;
+            const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
             const int nt0 = (tile % p.n_tiles) * p.n_tile;
             const int mt = tile / p.n_tiles;
-            { PROF_IF(4, et == 1); mbar_wait(bar_t_full + 8 * as, aph); }
+            { PROF_IF(4, pt); mbar_wait(bar_t_full + 8 * as, aph); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
@@ -553,18 +573,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int cc = 0; cc < p.nchunks; ++cc, ++qn) {
                     const int nbase = nt0 + cc * 32;
                     if (nbase >= p.Cout) break;
-                    const uint32_t b = qn % (uint32_t)p.nbuf;
-                    const uint32_t sbuf = smem_e + b * STAGE_BUF_BYTES;
+                    if ((int)(qn & (EPI_GROUPS - 1)) != eg) continue;       // the other group's chunk
+                    const uint32_t b = ql & nbuf_mask;
+                    const uint32_t sbuf = smem_g + b * STAGE_BUF_BYTES;
                     const uint32_t srow = sbuf + (uint32_t)row * 128u;
                     float v[32];
                     tmem_ld32(acc + (uint32_t)(cc * 32), v);
                     if (p.has_res) {
-                        PROF_IF(5, et == 1);
-                        mbar_wait(bar_r_full + 8 * b, (qn / (uint32_t)p.nbuf) & 1u);
+                        PROF_IF(5, pt);
+                        mbar_wait(bar_r + 8 * b, (ql >> nbuf_shift) & 1u);
                     }
+                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + nbase);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 bz = __ldg(reinterpret_cast<const float4 *>(p.bias + nbase) + j);
+                        const float4 bz = __ldg(bias4 + j);
                         float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
                                                v[4 * j + 3] + bz.w);
                         const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
@@ -581,16 +603,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (!p.has_res && e0) {
-                        // the buffer the NEXT chunk writes must have been read out by its old store
-                        PROF(9);
+                        // the buffer the group's NEXT chunk writes must have been read out by its old store
+                        PROF_IF(9, eg == 0);
                         if (p.nbuf == 2) bulk_wait_read<0>(); else bulk_wait_read<2>();
                     }
-                    { PROF_IF(6, et == 1); named_bar(1, EPI_THREADS); }
+                    { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
                         tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0);
                         bulk_commit();
                         if (p.has_res) {
-                            { PROF(9); bulk_wait_read<1>(); }     // store(qn-1) has drained its buffer -> refill it
+                            { PROF_IF(9, eg == 0); bulk_wait_read<1>(); }   // previous store drained -> refill its buffer
                             issue_res_load();
                         }
                     }
@@ -613,6 +635,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             atomicAdd(&sacc[1][nbase + col], (double)ss);
                         }
                     }
+                    ++ql;
                 }
             }
             // all tcgen05.ld of this tile have completed (wait::ld) -> hand the accumulators back
@@ -783,10 +806,10 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/;
     p.b_slot_bytes = n_tile * ROW_BYTES;
     p.has_res = has_res ? 1 : 0;
-    int nbuf = has_res ? 4 : 2;
+    int nbuf = 2;                                  // staging buffers PER epilogue group
     if (g_tune_nbuf == 2 || g_tune_nbuf == 4) nbuf = g_tune_nbuf;
     for (;;) {
-        int rest = budget - nbuf * STAGE_BUF_BYTES;
+        int rest = budget - EPI_GROUPS * nbuf * STAGE_BUF_BYTES;
         if (halo) {
             p.a_slot_bytes = HALO_SLOT_BYTES;
             p.a_slots = mh + 3;
@@ -810,7 +833,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     if (p.b_slots < 2 || p.a_slots < (halo ? mh + 2 : 2)) return false;
     p.nbuf = nbuf;
     pl->smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes +
-               (size_t)nbuf * STAGE_BUF_BYTES + 1024;
+               (size_t)EPI_GROUPS * nbuf * STAGE_BUF_BYTES + 1024;
 
     p.stats = nullptr;     // filled by the caller when the epilogue computes the statistics
     p.stats_ld = 0;

@@ -18,7 +18,7 @@ SIGNATURES = {
     "hl_last_error": (ctypes.c_char_p, []),
     "hl_conv2d_uses_tensor_cores": (c_int, [c_int] * 11),
     "hl_conv_set_tuning": (c_int, [c_int] * 5),
-    "hl_conv_set_tuning2": (c_int, [c_int] * 2),
+    "hl_conv_set_tuning2": (c_int, [c_int] * 3),
     "hl_conv_set_profile": (c_int, [c_p]),
     "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_nhwc_to_nchw": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p]),

@@ -65,6 +65,7 @@ struct TcParams {
     int Cout, stride, ksize, taps, kchunks, kind;   // kind: 0 = tf32, 1 = f16
     int bw, bh, bn, tiles_w, tiles_h;
     int mh, n_tile, n_tiles, nchunks;
+    int pair;                // CTAs cooperating on one MMA (cta_group): 1, or 2 = CTA pair, M = 256
     int total_tiles;
     int halo, hp;            // hp = H / mh (halo mode)
     int base_off;            // experiment: halo descriptors carry base_offset = (addr >> 7) & 7
@@ -149,6 +150,69 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
         : "=r"(pred));
     return pred;
 }
+// ---- CTA-pair (cta_group::2) variants: barriers of the LEADER CTA (cluster rank 0) are addressed through
+// mapa / shared::cluster, TMA loads signal the leader's barrier, commits are multicast to both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                                int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma2(int kind, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                      uint32_t accumulate) {
+    if (kind) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// arrive on the barrier at the same offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+}
 __device__ __forceinline__ void named_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -225,15 +289,17 @@ struct ProfTimer {
 #define PROF_IF(slot, cond) ProfTimer prof_timer_##slot(p.prof, slot, cond)   // warp-convergent: all threads time
 
 // origin (output pixel coordinates) of half `half` of m-tile `mt`
-__device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, int &w0, int &h0, int &n0) {
+// (a cluster tile holds p.pair * p.mh boxes; CTA `rank` of the pair owns boxes rank*mh .. rank*mh + mh-1)
+__device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, int rank, int &w0, int &h0, int &n0) {
+    const int per = p.mh * p.pair, sub = rank * p.mh + half;
     if (p.halo) {
         const int tw = mt % p.tiles_w;
         const int r = mt / p.tiles_w;
         w0 = tw * BLOCK_M;
-        h0 = (r % p.hp) * p.mh + half;
+        h0 = (r % p.hp) * per + sub;
         n0 = r / p.hp;
     } else {
-        const int bi = mt * p.mh + half;
+        const int bi = mt * per + sub;
         const int tw = bi % p.tiles_w;
         const int r = bi / p.tiles_w;
         w0 = tw * p.bw;
@@ -242,6 +308,7 @@ __device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, 
     }
 }
 
+template <bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
@@ -266,6 +333,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t bar_t_empty = smem_u32(&bars[4 * MAX_SLOTS + 2]);
     const uint32_t bar_r_full = smem_u32(&bars[4 * MAX_SLOTS + 4]);
     const int chunk_elems = p.kind ? 64 : 32;
+    // CTA pair: rank 0 is the leader (issues the MMAs, owns the barriers the MMA thread waits on)
+    const int rank = CTA2 ? (int)cluster_rank() : 0;
+    const int cid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // first tile of this CTA / pair
+    const int nct = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;      // tile stride
+    const int nprod = CTA2 ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -276,30 +348,38 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 2) {
         if (lane == 0) {
             for (int s = 0; s < MAX_SLOTS; ++s) {
-                mbar_init(bar_a_full + 8 * s, 1);
+                mbar_init(bar_a_full + 8 * s, nprod);
                 mbar_init(bar_a_empty + 8 * s, 1);
-                mbar_init(bar_b_full + 8 * s, p.halo ? 1 : 2);   // TAP: A and B producers fill one stage
+                mbar_init(bar_b_full + 8 * s, (p.halo ? 1 : 2) * nprod);   // TAP: A and B producers fill one stage
                 mbar_init(bar_b_empty + 8 * s, 1);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(bar_t_full + 8 * s, 1);
-                mbar_init(bar_t_empty + 8 * s, EPI_GROUPS * EPI_THREADS);
+                mbar_init(bar_t_empty + 8 * s, nprod * EPI_GROUPS * EPI_THREADS);
             }
             for (int s = 0; s < EPI_GROUPS * MAX_NBUF; ++s) mbar_init(bar_r_full + 8 * s, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_slot)),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_slot)),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp >= 3 && p.stats) {
         for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_GROUPS * EPI_THREADS) (&sacc[0][0])[i] = 0.0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();     // barriers initialised + TMEM allocated in both CTAs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_slot;
     const int pad = p.ksize / 2;
@@ -314,23 +394,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             // ------------------------------ A producer ------------------------------
             // TAP mode shares the stage ring (and its barriers) with the B producer; HALO mode owns
             // the row ring.
-            const uint32_t full0 = p.halo ? bar_a_full : bar_b_full, empty0 = p.halo ? bar_a_empty : bar_b_empty;
+            const uint32_t full_l = p.halo ? bar_a_full : bar_b_full, empty0 = p.halo ? bar_a_empty : bar_b_empty;
+            const uint32_t full0 = CTA2 ? mapa_u32(full_l, 0) : full_l;     // the leader's barrier
             const uint32_t nslots = (uint32_t)p.a_slots, slot_bytes = (uint32_t)p.a_slot_bytes;
             uint32_t slot = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = cid; tile < p.total_tiles; tile += nct) {
                 const int mt = tile / p.n_tiles;
                 int w0[2], h0[2], n0[2];
-                box_origin(p, mt, 0, w0[0], h0[0], n0[0]);
-                box_origin(p, mt, p.mh - 1, w0[1], h0[1], n0[1]);
+                box_origin(p, mt, 0, rank, w0[0], h0[0], n0[0]);
+                box_origin(p, mt, p.mh - 1, rank, w0[1], h0[1], n0[1]);
                 if (p.halo) {
                     const int rows = p.mh + 2;
                     for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
                         for (int r = 0; r < rows; ++r) {
                             { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
                             if (elect_one_sync()) {
-                                mbar_expect_tx(full0 + 8 * slot, HALO_ROW_BYTES);
-                                tma_load_4d(smem_a + slot * slot_bytes, &tmA, full0 + 8 * slot, c0, w0[0] - 1,
-                                            h0[0] - 1 + r, n0[0]);
+                                if (CTA2) {
+                                    mbar_expect_tx_cluster(full0 + 8 * slot, HALO_ROW_BYTES);
+                                    tma_load_4d_2sm(smem_a + slot * slot_bytes, &tmA, full0 + 8 * slot, c0, w0[0] - 1,
+                                                    h0[0] - 1 + r, n0[0]);
+                                } else {
+                                    mbar_expect_tx(full0 + 8 * slot, HALO_ROW_BYTES);
+                                    tma_load_4d(smem_a + slot * slot_bytes, &tmA, full0 + 8 * slot, c0, w0[0] - 1,
+                                                h0[0] - 1 + r, n0[0]);
+                                }
                             }
                             __syncwarp();
                             if (++slot == nslots) { slot = 0; phase ^= 1u; }
@@ -345,12 +432,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             for (int tx = 0; tx < p.ksize; ++tx) {
                                 { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
                                 if (elect_one_sync()) {
-                                    mbar_expect_tx(full0 + 8 * slot, bytes);
                                     const uint32_t dst = smem_a + slot * slot_bytes;
-                                    tma_load_4d(dst, &tmA, full0 + 8 * slot, c0, xs0 + tx, ys0 + ty, n0[0]);
-                                    if (p.mh == 2)
-                                        tma_load_4d(dst + A_BOX_BYTES, &tmA, full0 + 8 * slot, c0, xs1 + tx, ys1 + ty,
-                                                    n0[1]);
+                                    if (CTA2) {
+                                        mbar_expect_tx_cluster(full0 + 8 * slot, bytes);
+                                        tma_load_4d_2sm(dst, &tmA, full0 + 8 * slot, c0, xs0 + tx, ys0 + ty, n0[0]);
+                                    } else {
+                                        mbar_expect_tx(full0 + 8 * slot, bytes);
+                                        tma_load_4d(dst, &tmA, full0 + 8 * slot, c0, xs0 + tx, ys0 + ty, n0[0]);
+                                        if (p.mh == 2)
+                                            tma_load_4d(dst + A_BOX_BYTES, &tmA, full0 + 8 * slot, c0, xs1 + tx,
+                                                        ys1 + ty, n0[1]);
+                                    }
                                 }
                                 __syncwarp();
                                 if (++slot == nslots) { slot = 0; phase ^= 1u; }
@@ -363,17 +455,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else if (warp == 1) {
         {
             // ------------------------------ B producer ------------------------------
-            const uint32_t bytes = (uint32_t)(p.n_tile * ROW_BYTES);
+            // a CTA of a pair loads its half of the weight tile (rows rank*N/2 .. +N/2)
+            const int rows_b = p.n_tile / p.pair;
+            const uint32_t bytes = (uint32_t)(rows_b * ROW_BYTES);
             const uint32_t nslots = (uint32_t)p.b_slots, slot_bytes = (uint32_t)p.b_slot_bytes;
+            const uint32_t bfull = CTA2 ? mapa_u32(bar_b_full, 0) : bar_b_full;
             uint32_t slot = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt0 = (tile % p.n_tiles) * p.n_tile;
+            for (int tile = cid; tile < p.total_tiles; tile += nct) {
+                const int nt0 = (tile % p.n_tiles) * p.n_tile + rank * rows_b;
                 for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
                     for (int tap = 0; tap < p.taps; ++tap) {
                         { PROF_IF(8, lane == 0); mbar_wait(bar_b_empty + 8 * slot, phase ^ 1u); }
                         if (elect_one_sync()) {
-                            mbar_expect_tx(bar_b_full + 8 * slot, bytes);
-                            tma_load_3d(smem_b + slot * slot_bytes, &tmB, bar_b_full + 8 * slot, c0, nt0, tap);
+                            if (CTA2) {
+                                mbar_expect_tx_cluster(bfull + 8 * slot, bytes);
+                                tma_load_3d_2sm(smem_b + slot * slot_bytes, &tmB, bfull + 8 * slot, c0, nt0, tap);
+                            } else {
+                                mbar_expect_tx(bfull + 8 * slot, bytes);
+                                tma_load_3d(smem_b + slot * slot_bytes, &tmB, bfull + 8 * slot, c0, nt0, tap);
+                            }
                         }
                         __syncwarp();
                         if (++slot == nslots) { slot = 0; phase ^= 1u; }
@@ -382,12 +482,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     } else if (warp == 2) {
-        {
-            // ------------------------------ MMA issuer --------------------------------
+        if (!CTA2 || rank == 0) {
+            // ------------------------------ MMA issuer (leader CTA of a pair) ---------
             // instruction descriptor: D=f32, A/B format (0 = f16, 2 = tf32), both K-major, N>>3 @17, M>>4 @24
             const uint32_t fmt = p.kind ? 0u : 2u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)((BLOCK_M * (CTA2 ? 2 : 1)) >> 4) << 24);
+            auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+                if (CTA2) umma2(p.kind, d, ad, bd, idesc, acc); else umma(p.kind, d, ad, bd, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (CTA2) umma_commit2(bar); else umma_commit(bar);
+            };
             // shared-memory descriptor: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B), low
             // word = LBO field (unused, 1) | start address >> 4; a K step of 32 B adds 2 to the low word
             const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -404,7 +510,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             PROF_IF(0, lane == 0);
             if (p.prof && blockIdx.x == 0 && lane == 0) p.prof[10] = (unsigned long long)((p.total_tiles + gridDim.x - 1) / gridDim.x);
             const int steps = p.kchunks * p.taps;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = cid; tile < p.total_tiles; tile += nct, ++it) {
                 const int as = p.acc_stages == 2 ? (it & 1) : 0;
                 const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
                 { PROF_IF(2, lane == 0); mbar_wait(bar_t_empty + 8 * as, aph ^ 1u); }
@@ -446,18 +552,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     const uint32_t accf = (kc | ty | tx) != 0;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                        mma(acc0, ad0 + 2 * k, bd + 2 * k, accf | (k != 0));
                                     if (p.mh == 2) {
                                         const uint64_t ad1 = desc(row_addr[ty + 1] + tx * ROW_BYTES);
 #pragma unroll
                                         for (int k = 0; k < 4; ++k)
-                                            umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                            mma(acc1, ad1 + 2 * k, bd + 2 * k, accf | (k != 0));
                                     }
-                                    umma_commit(bar_b_empty + 8 * sb);
+                                    commit(bar_b_empty + 8 * sb);
                                     // halo row `ty` is not needed by later taps; the last tap row frees the rest
                                     if (tx == 2) {
-                                        umma_commit(bar_a_empty + 8 * row_bar[ty]);
-                                        if (ty == 2 && p.mh == 2) umma_commit(bar_a_empty + 8 * row_bar[3]);
+                                        commit(bar_a_empty + 8 * row_bar[ty]);
+                                        if (ty == 2 && p.mh == 2) commit(bar_a_empty + 8 * row_bar[3]);
                                     }
                                 }
                                 __syncwarp();
@@ -474,20 +580,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             const uint64_t ad0 = desc(smem_a + sb * a_bytes);
                             const uint32_t accf = st != 0;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma(p.kind, acc0, ad0 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                            for (int k = 0; k < 4; ++k) mma(acc0, ad0 + 2 * k, bd + 2 * k, accf | (k != 0));
                             if (p.mh == 2) {
                                 const uint64_t ad1 = ad0 + (A_BOX_BYTES >> 4);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma(p.kind, acc1, ad1 + 2 * k, bd + 2 * k, idesc, accf | (k != 0));
+                                    mma(acc1, ad1 + 2 * k, bd + 2 * k, accf | (k != 0));
                             }
-                            umma_commit(bar_b_empty + 8 * sb);
+                            commit(bar_b_empty + 8 * sb);
                         }
                         __syncwarp();
                         if (++sb == nb) { sb = 0; phb ^= 1u; }
                     }
                 }
-                if (elect_one_sync()) umma_commit(bar_t_full + 8 * as);   // accumulators complete -> epilogue
+                if (elect_one_sync()) commit(bar_t_full + 8 * as);   // accumulators complete -> epilogue
                 __syncwarp();
             }
         }
@@ -514,7 +620,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
         // residual prefetch cursor (thread e0 of the group): walks the same (tile, half, chunk) sequence
         // and issues loads for the chunks this group owns
-        int l_tile = blockIdx.x, l_half = 0, l_cc = 0;
+        int l_tile = cid, l_half = 0, l_cc = 0;
         uint32_t l_qn = 0, l_ql = 0;
         auto issue_res_load = [&]() {
             for (;;) {
@@ -523,7 +629,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const bool mine = (int)(l_qn & (EPI_GROUPS - 1)) == eg;
                 if (mine) {
                     int w0, h0, n0;
-                    box_origin(p, l_tile / p.n_tiles, l_half, w0, h0, n0);
+                    box_origin(p, l_tile / p.n_tiles, l_half, rank, w0, h0, n0);
                     const uint32_t b = l_ql & nbuf_mask;
                     mbar_expect_tx(bar_r + 8 * b, STAGE_BUF_BYTES);
                     tma_load_4d(smem_g + b * STAGE_BUF_BYTES, &tmR, bar_r + 8 * b, nt0 + l_cc * 32, w0, h0, n0);
@@ -533,7 +639,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 ++l_cc;
                 if (l_cc == p.nchunks || nt0 + l_cc * 32 >= p.Cout) {
                     l_cc = 0;
-                    if (++l_half == p.mh) { l_half = 0; l_tile += gridDim.x; }
+                    if (++l_half == p.mh) { l_half = 0; l_tile += nct; }
                 }
                 if (mine) return;
             }
@@ -554,7 +660,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         };
 
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = cid; tile < p.total_tiles; tile += nct, ++it) {
             const int as = p.acc_stages == 2 ? (it & 1) : 0;
             const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
             const int nt0 = (tile % p.n_tiles) * p.n_tile;
@@ -563,7 +669,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
-                box_origin(p, mt, half, w0, h0, n0);
+                box_origin(p, mt, half, rank, w0, h0, n0);
                 if (p.stats && n0 != cur_n) {
                     if (cur_n >= 0) flush_stats();
                     cur_n = n0;
@@ -640,19 +746,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             // all tcgen05.ld of this tile have completed (wait::ld) -> hand the accumulators back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar_t_empty + 8 * as);
+            if (CTA2) mbar_arrive_cluster(mapa_u32(bar_t_empty + 8 * as, 0)); else mbar_arrive(bar_t_empty + 8 * as);
         }
         if (p.stats && cur_n >= 0) flush_stats();
         if (e0) bulk_wait_read<0>();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();     // no remote arrive / MMA may still target this CTA
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
+        if (CTA2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
     }
 }
 
@@ -707,7 +818,7 @@ bool pick_tiling(int H, int W, Tiling *t) {
 // tuning overrides (-1 = automatic); set through hl_conv_set_tuning (tests / experiments)
 int g_tune_mh = -1, g_tune_ntile = -1, g_tune_halo = -1, g_tune_epi_stats = -1, g_tune_base_off = -1;
 unsigned long long *g_prof = nullptr;
-int g_tune_stages = -1, g_tune_nbuf = -1;   // experiment: cap on pipeline slots / staging buffers
+int g_tune_stages = -1, g_tune_nbuf = -1, g_tune_cta2 = -1;   // experiment: cap on pipeline slots / staging buffers
 
 struct Plan {
     TcParams p;
@@ -787,15 +898,27 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
         mh * acc_stride_for(g_tune_ntile) <= 512)
         n_tile = g_tune_ntile;
 
-    p.halo = halo;
+    // CTA pair (cta_group::2): M = 256 over two SMs, each SM supplies 128 A rows and N/2 B rows, so the
+    // per-MMA operand fetch drops from (128 + N)/2 to (128 + N/2)/2 cycles (N = 192: 160 -> 112).
+    // Needs an even number of boxes (rows, in HALO mode), enough pair tiles for all 74 SM pairs and a
+    // weight half-tile of whole 8-row swizzle atoms.
+    int pair = 1;
+    {
+        const bool even = halo ? (H % 2 == 0) : (boxes % 2 == 0);
+        const bool legal = even && mh == 1 && n_tile % 32 == 0 && (n_tile / 2) % 8 == 0 && n_tile >= 64;
+        const bool worth = n_tile >= 128 && (boxes / 2) * (cout_pad / n_tile) >= sms / 2;
+        if (legal && (g_tune_cta2 == 1 || (g_tune_cta2 != 0 && worth))) pair = 2;
+    }
+
     p.prof = g_prof;
     p.base_off = g_tune_base_off == 1 ? 1 : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits
     p.mh = mh;
-    p.hp = halo ? H / mh : 1;
+    p.pair = pair;
+    p.hp = halo ? H / (mh * pair) : 1;
     p.n_tile = n_tile;
     p.n_tiles = cout_pad / n_tile;
     p.nchunks = n_tile / 32;
-    p.total_tiles = (boxes / mh) * p.n_tiles;
+    p.total_tiles = (boxes / (mh * pair)) * p.n_tiles;
     p.acc_stride = acc_stride_for(n_tile);
     p.acc_stages = 512 / (mh * p.acc_stride) >= 2 ? 2 : 1;
     int cols = 32;
@@ -804,7 +927,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
 
     // shared-memory budget: staging ring, then A slots, the rest to B slots
     const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/;
-    p.b_slot_bytes = n_tile * ROW_BYTES;
+    p.b_slot_bytes = (n_tile / pair) * ROW_BYTES;
     p.has_res = has_res ? 1 : 0;
     int nbuf = 2;                                  // staging buffers PER epilogue group
     if (g_tune_nbuf == 2 || g_tune_nbuf == 4) nbuf = g_tune_nbuf;
@@ -837,7 +960,12 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
 
     p.stats = nullptr;     // filled by the caller when the epilogue computes the statistics
     p.stats_ld = 0;
-    pl->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (pair == 2) {
+        const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+        pl->grid = 2 * clusters;
+    } else {
+        pl->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    }
     (void)want_stats;
     return true;
 }
@@ -861,9 +989,10 @@ extern "C" int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, i
     return HL_OK;
 }
 
-extern "C" int hl_conv_set_tuning2(int max_stages, int nbuf) {
+extern "C" int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2) {
     g_tune_stages = max_stages;
     g_tune_nbuf = nbuf;
+    g_tune_cta2 = cta2;
     return HL_OK;
 }
 
@@ -939,7 +1068,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     {
         cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)pl.cout_pad, (cuuint64_t)p.taps};
         cuuint64_t gstr[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)pl.cout_pad * Cin * esz};
-        cuuint32_t box[3] = {(cuuint32_t)chunk, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t box[3] = {(cuuint32_t)chunk, (cuuint32_t)(p.n_tile / p.pair), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmB, dt, 3, (void *)wpk, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -971,12 +1100,28 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     }
     static bool smem_configured = false;
     if (!smem_configured) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
         smem_configured = true;
     }
     HL_CHECK_ARG(pl.smem <= (size_t)DYN_SMEM_MAX);
-    k_conv_tc<<<pl.grid, NUM_THREADS, pl.smem, stream>>>(tmA, tmB, tmY, tmR, p);
+    if (p.pair == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl.grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = pl.smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, tmA, tmB, tmY, tmR, p));
+    } else {
+        k_conv_tc<false><<<pl.grid, NUM_THREADS, pl.smem, stream>>>(tmA, tmB, tmY, tmR, p);
+    }
     HL_CHECK_LAUNCH();
     if (stats && !epi_stats) return hl_gn_stats_launch(y, ldy, B, H * W, Cout, stats, stats_ld, stream);
     return HL_OK;

@@ -52,8 +52,9 @@ int hl_conv2d_uses_tensor_cores(int x_dtype, int B, int H, int W, int Cin, int C
  * operand reuse (0|1), in-epilogue GroupNorm statistics (0|1), descriptor base_offset (0|1);
  * -1 = automatic.  Process-wide; not part of the reference-facing surface.                      */
 int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, int base_off);
-/* More experiment knobs: cap on the smem pipeline depth, number of epilogue staging buffers (2|4). */
-int hl_conv_set_tuning2(int max_stages, int nbuf);
+/* More experiment knobs: cap on the smem pipeline depth, epilogue staging buffers per group (2|4),
+ * CTA-pair MMA (cta_group::2: 0 off, 1 on where legal); -1 = automatic.                           */
+int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2);
 /* Experiment hook: device array of >= 16 uint64 that CTA 0 of every following tcgen05 conv adds its
  * blocked-cycle counters to (0 total, 1 A-full wait, 2 TMEM-empty wait, 3 B-full wait, 4 TMEM-full
  * wait, 5 residual wait, 6 epilogue barrier, 7 A-empty wait, 8 B-empty wait, 9 store-drain wait,

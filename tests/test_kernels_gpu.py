@@ -161,7 +161,7 @@ def _operand(t, mode):
 
 
 def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residual=True, stats=False, cin_pad=None,
-               seed=0, ldy=None, tuning=None):
+               seed=0, ldy=None, tuning=None, tuning2=None):
     """Runs hl_conv2d on seeded inputs; returns (y NCHW cpu, fp32 reference, reference on the ROUNDED operands,
     stats cpu or None)."""
     from humanliff_b200.unet import pack_conv
@@ -195,6 +195,8 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
     lib = _lib.load()
     if tuning is not None:
         lib.hl_conv_set_tuning(*tuning)
+    if tuning2 is not None:
+        lib.hl_conv_set_tuning2(*tuning2)
     try:
         _call("hl_conv2d", xd.data_ptr(), code, cin_pad, wpk.data_ptr(), bpk.data_ptr(),
               rd.data_ptr() if residual else None, Cout, y.data_ptr(), ldy, st.data_ptr() if stats else None, ldy,
@@ -202,6 +204,7 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
         torch.cuda.synchronize()
     finally:
         lib.hl_conv_set_tuning(-1, -1, -1, -1, -1)
+        lib.hl_conv_set_tuning2(-1, -1, -1)
     return y[..., :Cout].permute(0, 3, 1, 2).cpu(), ref, ref_r, (st.cpu().reshape(B, ldy, 2) if stats else None)
 
 
@@ -275,12 +278,13 @@ def test_conv_tensor_core(dev, shape, mode):
 @pytest.mark.parametrize("tuning", [(1, -1, 0, -1, -1), (2, -1, 0, -1, -1), (1, -1, 1, -1, -1), (2, 192, 1, -1, -1),
                                     (2, 96, 1, -1, -1), (2, 64, 1, 0, -1), (1, 32, 0, -1, -1)])
 @pytest.mark.parametrize("residual", [False, True])
-def test_conv_tensor_core_tilings(dev, tuning, residual):
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_conv_tensor_core_tilings(dev, tuning, residual, cta2):
     """Every tiling variant of the kernel (halves per CTA, N tile, TAP vs HALO operand path, statistics in
-    the epilogue or by the separate kernel) must give the same numbers."""
+    the epilogue or by the separate kernel, single CTA vs CTA-pair MMA) must give the same numbers."""
     B, H, W, Cin, Cout = 2, 128, 128, 192, 192
     y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, 3, 1, mode="fp16", stats=True, residual=residual, seed=3,
-                                   tuning=tuning)
+                                   tuning=tuning, tuning2=(-1, -1, cta2))
     assert not torch.isnan(y).any()
     assert rel_l2(y, ref_r) < 2e-5, (tuning, rel_l2(y, ref_r))
     _check_stats(st, y, Cout)

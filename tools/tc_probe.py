@@ -29,36 +29,46 @@ CASES = [
     ("halo_tf32", (1, 256, 256, 64, 64, 3, 1), "tf32", True, True, (2, -1, 1, -1, -1)),
     ("auto_256", (1, 256, 256, 192, 192, 3, 1), "fp16", True, True, (-1, -1, -1, -1, -1)),
     ("small8", (4, 8, 8, 768, 768, 3, 1), "fp16", True, True, (-1, -1, -1, -1, -1)),
+    # CTA-pair MMA (cta_group::2)
+    ("cta2_tap", (2, 64, 64, 192, 192, 3, 1), "fp16", False, False, (1, -1, 0, -1, -1), (-1, -1, 1)),
+    ("cta2_tap_res", (2, 64, 64, 192, 192, 3, 1), "fp16", True, True, (1, -1, 0, -1, -1), (-1, -1, 1)),
+    ("cta2_halo", (2, 128, 128, 192, 192, 3, 1), "fp16", True, True, (1, 192, 1, -1, -1), (-1, -1, 1)),
+    ("cta2_1x1", (2, 32, 32, 384, 192, 1, 1), "fp16", True, True, (1, -1, -1, -1, -1), (-1, -1, 1)),
+    ("cta2_n256", (2, 64, 64, 128, 256, 3, 1), "fp16", True, True, (1, 256, -1, -1, -1), (-1, -1, 1)),
+    ("cta2_stride2", (2, 128, 128, 192, 192, 3, 2), "fp16", False, True, (1, -1, -1, -1, -1), (-1, -1, 1)),
+    ("cta2_tf32", (2, 64, 64, 192, 192, 3, 1), "tf32", True, True, (1, -1, 0, -1, -1), (-1, -1, 1)),
+    ("cta2_persist", (4, 256, 256, 64, 192, 3, 1), "fp16", True, True, (-1, -1, -1, -1, -1), (-1, -1, 1)),
 ]
 
 TIMING = [
-    # name, shape (B,H,W,Cin,Cout,k), tuning, tuning2 (max_stages, nbuf), residual, stats
-    ("3x3 192@256 plain auto", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1), False, False),
-    ("3x3 192@256 plain stages2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (2, -1), False, False),
-    ("3x3 192@256 plain stages3", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (3, -1), False, False),
-    ("3x3 192@256 res+stats auto", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 192@256 res+stats nbuf2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, 2), True, True),
-    ("3x3 192@256 res+stats tap", (4, 256, 256, 192, 192, 3), (1, 192, 0, -1, -1), (-1, -1), True, True),
-    ("1x1 192@256 res+stats", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1), True, True),
-    ("1x1 192@256 res+stats nbuf2", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, 2), True, True),
-    ("1x1 192@256 plain", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1), False, False),
-    ("3x3 768@16 res+stats", (4, 16, 16, 768, 768, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 768@16 res+stats n32", (4, 16, 16, 768, 768, 3), (1, 32, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 768@16 res+stats n128", (4, 16, 16, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 768@8 res+stats", (4, 8, 8, 768, 768, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 384@64 res+stats", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1), True, True),
-    ("3x3 384@64 res+stats mh2", (4, 64, 64, 384, 384, 3), (2, -1, -1, -1, -1), (-1, -1), True, True),
+    # name, shape (B,H,W,Cin,Cout,k), tuning, tuning2 (max_stages, nbuf, cta2), residual, stats
+    ("3x3 192@256 plain 1cta", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 0), False, False),
+    ("3x3 192@256 plain cta2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 1), False, False),
+    ("3x3 192@256 plain cta2 tap", (4, 256, 256, 192, 192, 3), (1, -1, 0, -1, -1), (-1, -1, 1), False, False),
+    ("3x3 192@256 res+stats 1cta", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 0), True, True),
+    ("3x3 192@256 res+stats cta2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 1), True, True),
+    ("3x3 384->192@256 cta2", (4, 256, 256, 384, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 1), False, True),
+    ("3x3 384->192@256 1cta", (4, 256, 256, 384, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 0), False, True),
+    ("1x1 192@256 res+stats 1cta", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1, 0), True, True),
+    ("1x1 192@256 res+stats cta2", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1, 1), True, True),
+    ("3x3 384@64 res+stats 1cta", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1, 0), True, True),
+    ("3x3 384@64 res+stats cta2", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1, 1), True, True),
+    ("3x3 384@64 res+stats cta2 n128", (4, 64, 64, 384, 384, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
+    ("3x3 192@128 res+stats 1cta", (4, 128, 128, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 0), True, True),
+    ("3x3 192@128 res+stats cta2", (4, 128, 128, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, 1), True, True),
+    ("3x3 768@16 res+stats cta2 n128", (4, 16, 16, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
 ]
 
 def run_case(idx):
     import torch
     from test_kernels_gpu import _conv_case, _check_stats
     from common import rel_l2
-    name, shape, mode, residual, stats, tuning = CASES[idx]
+    name, shape, mode, residual, stats, tuning = CASES[idx][:6]
+    tuning2 = CASES[idx][6] if len(CASES[idx]) > 6 else (-1, -1, 0)
     dev = torch.device("cuda:0")
     B, H, W, Cin, Cout, k, s = shape
     y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, mode=mode, residual=residual, stats=stats, seed=7,
-                                   tuning=tuning)
+                                   tuning=tuning, tuning2=tuning2)
     out = {"name": name, "nan": bool(torch.isnan(y).any()), "err_rounded": rel_l2(y, ref_r), "err_fp32": rel_l2(y, ref)}
     if stats:
         try:

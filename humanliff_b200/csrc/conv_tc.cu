@@ -910,6 +910,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
         if (legal && (g_tune_cta2 == 1 || (g_tune_cta2 != 0 && worth))) pair = 2;
     }
 
+    p.halo = halo;
     p.prof = g_prof;
     p.base_off = g_tune_base_off == 1 ? 1 : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits
     p.mh = mh;
@@ -1009,7 +1010,7 @@ bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, 
     if (x_dtype == HL_DT_F32 && !(flags & HL_CONV_TF32)) return false;
     const int esz = x_dtype == HL_DT_F16 ? 2 : 4;
     if ((ldx * esz) % 16 || Cin > ldx || ldy % 4) return false;
-    Plan pl;
+    Plan pl = {};
     if (!make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, false, false,
                    &pl))
         return false;
@@ -1031,7 +1032,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     const int esz = kind ? 2 : 4;
     const int chunk = kind ? 64 : 32;
     const int H = Hin / stride, W = Win / stride;
-    Plan pl;
+    Plan pl = {};
     HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl));
     HL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                  bias != nullptr && ((uintptr_t)bias & 15) == 0);

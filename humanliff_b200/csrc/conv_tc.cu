@@ -866,49 +866,49 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     if (g_tune_mh == 1) mh = 1;
     if (g_tune_mh == 2 && !(halo ? (H % 2 == 0) : (boxes % 2 == 0))) mh = 1;
 
-    // (mh, n_tile).  Measured on B200 (profiles/r1_conv_tilings.md): a tcgen05.mma with M = 128 takes
-    // ~(128 + N)/2 cycles (operand fetch from shared memory), so wide N tiles win, and a double-buffered
-    // TMEM accumulator (epilogue overlapped with the next main loop) beats sharing a weight tile between
-    // two halves whenever both do not fit (mh * stride(N) * 2 <= 512 columns).  Preference order: the
-    // largest legal N that still yields one CTA tile per SM, with mh = 1 unless two halves keep the
-    // double buffer; problems too small to fill the machine take mh = 1 and a narrow tile (more CTAs =
-    // more TMA streams for their long, weight-bound K loops).
+    // (pair, mh, n_tile) -- measured on B200 (profiles/r1_conv_tilings.md):
+    //  * a tcgen05.mma with M = 128 per SM costs ~(128 + N_sm)/2 cycles of operand fetch from shared memory
+    //    (N_sm = B rows held by that SM), so a CTA pair (cta_group::2, M = 256, N_sm = N/2) beats a single
+    //    CTA for every 3x3 shape tried and ties on 1x1: use it whenever the boxes pair up;
+    //  * a double-buffered TMEM accumulator (epilogue overlapped with the next main loop) beats sharing a
+    //    weight tile between two halves of one CTA, so mh = 2 is only reachable through the tuning hook;
+    //  * big problems: the widest legal N with at least one tile per SM; small problems (one wave or less):
+    //    the N that yields the most CTAs without exceeding one wave (their K loops are latency-bound, more
+    //    CTAs = more TMA streams), ties to the wider tile.
     static const int cand[] = {256, 192, 128, 96, 64, 32};
-    int n_tile = 0;
+    const bool pair_ok = (halo ? (H % 2 == 0) : (boxes % 2 == 0)) && g_tune_mh != 2;
+    int pair = (pair_ok && g_tune_cta2 != 0) ? 2 : 1;
     const int mh_max = mh;
-    if (g_tune_mh != 2) mh = 1;
-    for (int c : cand) {
-        if (cout_pad % c) continue;
-        if ((boxes / mh) * (cout_pad / c) >= sms) { n_tile = c; break; }
-    }
-    if (n_tile != 0 && g_tune_mh != 1 && mh_max == 2 && 4 * acc_stride_for(n_tile) <= 512 &&
-        (boxes / 2) * (cout_pad / n_tile) >= sms)
-        mh = 2;                                   // two halves AND two accumulator stages fit
-    if (g_tune_mh == 2) {
-        mh = mh_max;
-        n_tile = 0;
-        for (int c : cand)
-            if (cout_pad % c == 0 && mh * acc_stride_for(c) <= 512) { n_tile = c; break; }
-    }
+    mh = (g_tune_mh == 2) ? mh_max : 1;
+    if (mh == 2) pair = 1;
+    auto legal = [&](int c) {
+        if (cout_pad % c || c % 32) return false;
+        if (mh * acc_stride_for(c) > 512) return false;
+        if (pair == 2 && ((c / 2) % 8 || c < 64)) return false;
+        return true;
+    };
+    auto ctas = [&](int c) { return (boxes / (mh * pair)) * (cout_pad / c) * pair; };
+    int n_tile = 0;
+    for (int c : cand)
+        if (legal(c) && ctas(c) >= sms) { n_tile = c; break; }
     if (n_tile == 0) {
-        mh = 1;
-        n_tile = cout_pad % 64 == 0 ? 64 : 32;
+        int best = -1;
+        for (int c : cand) {
+            if (!legal(c) || c < 64) continue;
+            const int n = ctas(c);
+            if (n <= sms && n > best) { best = n; n_tile = c; }
+        }
+        if (n_tile == 0)
+            for (int c : cand)
+                if (legal(c)) { n_tile = c; break; }     // everything overshoots one wave: the widest tile
     }
-    if (g_tune_ntile > 0 && cout_pad % g_tune_ntile == 0 && g_tune_ntile % 32 == 0 && g_tune_ntile <= 256 &&
-        mh * acc_stride_for(g_tune_ntile) <= 512)
-        n_tile = g_tune_ntile;
-
-    // CTA pair (cta_group::2): M = 256 over two SMs, each SM supplies 128 A rows and N/2 B rows, so the
-    // per-MMA operand fetch drops from (128 + N)/2 to (128 + N/2)/2 cycles (N = 192: 160 -> 112).
-    // Needs an even number of boxes (rows, in HALO mode), enough pair tiles for all 74 SM pairs and a
-    // weight half-tile of whole 8-row swizzle atoms.
-    int pair = 1;
-    {
-        const bool even = halo ? (H % 2 == 0) : (boxes % 2 == 0);
-        const bool legal = even && mh == 1 && n_tile % 32 == 0 && (n_tile / 2) % 8 == 0 && n_tile >= 64;
-        const bool worth = n_tile >= 128 && (boxes / 2) * (cout_pad / n_tile) >= sms / 2;
-        if (legal && (g_tune_cta2 == 1 || (g_tune_cta2 != 0 && worth))) pair = 2;
+    if (n_tile == 0 && pair == 2) {                      // e.g. Cout_pad = 32: no legal pair tile
+        pair = 1;
+        for (int c : cand)
+            if (legal(c)) { n_tile = c; break; }
     }
+    if (g_tune_ntile > 0 && legal(g_tune_ntile)) n_tile = g_tune_ntile;
+    if (n_tile == 0) return false;
 
     p.halo = halo;
     p.prof = g_prof;

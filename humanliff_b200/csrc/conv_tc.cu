@@ -894,7 +894,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     if (n_tile == 0) {
         int best = -1;
         for (int c : cand) {
-            if (!legal(c) || c < 64) continue;
+            if (!legal(c) || c < 64 || c == 96) continue;     // swept: 64 / 128 / 192 / 256
             const int n = ctas(c);
             if (n <= sms && n > best) { best = n; n_tile = c; }
         }

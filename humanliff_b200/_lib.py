@@ -39,6 +39,8 @@ SIGNATURES = {
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                c_i64, c_int, c_p]),
+    "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
+                                  c_i64, c_int, c_p]),
 }
 
 DT_F32, DT_F16 = 0, 1
@@ -59,6 +61,14 @@ MLP_BV = MLP_WV + 155 * 64
 MLP_WR = MLP_BV + 64
 MLP_BR = MLP_WR + 64 * 4
 MLP_PACK_FLOATS = MLP_BR + 4
+
+# fp16 weight image of the tensor-core renderer (HL_MLP16_* in the header): (offset, rows, pitch)
+MLP16_W0 = 0
+MLP16_W1 = MLP16_W0 + 128 * 40
+MLP16_W2 = MLP16_W1 + 128 * 136
+MLP16_WF = MLP16_W2 + 128 * 168
+MLP16_WV = MLP16_WF + 128 * 136
+MLP16_HALVES = MLP16_WV + 64 * 136
 
 CONV_FORCE_SIMT = 1
 CONV_UPSAMPLE2X = 2

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libhumanliff_b200.so")
 
-SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "render.cu"]
+SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "render.cu", "render_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

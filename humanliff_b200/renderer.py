@@ -9,6 +9,9 @@ chain of one ray batch is ONE kernel launch (``hl_render_rays``), so the referen
 its [4.2 M x 155] temporaries and ``empty_cache()`` calls disappear.  Only the inference envelope is
 built: ``use_canonical_space=False``, ``n_samples == n_importance == 128``, ``perturb == 0``,
 ``white_bkgd=False`` (the reference's white_bkgd branch is shape-broken).
+
+``precision="fp16"`` (default) runs the decoder MLP on the tensor cores (``hl_render_rays_tc``: fp16
+operands, fp32 accumulate, activations in registers); ``"fp32"`` selects the exact CUDA-core kernel.
 """
 import math
 
@@ -49,8 +52,11 @@ class Renderer(nn.Module):
     clamp_depth = True   # human_diffusion/NeRF/renderer.py:273-274
 
     def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18,
-                 smpl_type=None, test=False):
+                 smpl_type=None, test=False, precision="fp16"):
         super().__init__()
+        if precision not in ("fp16", "fp32"):
+            raise ValueError("precision must be 'fp16' (tensor-core MLP) or 'fp32' (exact CUDA-core MLP)")
+        self.precision = precision
         if use_canonical_space:
             raise NotImplementedError("use_canonical_space=True (TightCap SMPL deformation) is a 'next' row")
         if triplane_ch != 27:
@@ -102,6 +108,23 @@ class Renderer(nn.Module):
         put(L.MLP_WR, wr)
         put(L.MLP_BR, self.rgb_linear.bias)
         self._mlp = buf.to(device)
+        # fp16 weight image of the tensor-core kernel (HL_MLP16_* in the header): rows = outputs, pitch = K + 8
+        img = torch.zeros(L.MLP16_HALVES, dtype=torch.float16)
+
+        def put16(off, w, pitch, col0=0):
+            w = w.detach().float().cpu()
+            rows, cols = w.shape
+            view = img[off:off + rows * pitch].view(rows, pitch)
+            view[:, col0:col0 + cols] = w.to(torch.float16)
+
+        put16(L.MLP16_W0, self.pts_linears[0].weight, 40)
+        put16(L.MLP16_W1, self.pts_linears[1].weight, 136)
+        w2 = self.pts_linears[2].weight                       # input = cat([x(27), h1(128)])
+        put16(L.MLP16_W2, w2[:, :27], 168)
+        put16(L.MLP16_W2, w2[:, 27:], 168, col0=32)
+        put16(L.MLP16_WF, self.feature_linear.weight, 136)
+        put16(L.MLP16_WV, self.views_linear.weight[:, :128], 136)
+        self._mlp16 = img.to(device)
         self._pack_key = key
         return self._mlp
 
@@ -148,12 +171,15 @@ class Renderer(nn.Module):
             acc = torch.empty(n, device=dev, dtype=torch.float32)
             depth = torch.empty(n, device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), rays_o.data_ptr(),
-                 rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
-                 z_coarse.data_ptr() if z_coarse is not None else None,
-                 u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1),
-                 ctypes.cast(barr, ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
-                 1 if self.clamp_depth else 0, stream)
+            tail = (rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                    z_coarse.data_ptr() if z_coarse is not None else None,
+                    u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1),
+                    ctypes.cast(barr, ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
+                    1 if self.clamp_depth else 0, stream)
+            if self.precision == "fp16":
+                call("hl_render_rays_tc", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16.data_ptr(), *tail)
+            else:
+                call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), *tail)
         return rgb, acc, depth
 
     # ------------------------------------------------------------------ reference-shaped entry point
@@ -193,8 +219,9 @@ class ReconRenderer(Renderer):
 
     clamp_depth = False
 
-    def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18, test=False):
-        super().__init__(use_canonical_space, num_instances, triplane_dim, triplane_ch, None, test)
+    def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18, test=False,
+                 precision="fp16"):
+        super().__init__(use_canonical_space, num_instances, triplane_dim, triplane_ch, None, test, precision)
         self.tri_planes = nn.Parameter(torch.empty(num_instances, 4, 3, triplane_ch // 3, triplane_dim,
                                                    triplane_dim).normal_(0, 0.1), requires_grad=False)
 

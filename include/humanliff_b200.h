@@ -193,6 +193,29 @@ int hl_render_rays(const float *texels, int R, const float *mlp_packed, const fl
                    uint64_t seed, const float *bounds /*host*/, float *rgb, float *acc, float *depth,
                    int64_t n_rays, int clamp_depth, void *stream);
 
+/* Tensor-core variant of hl_render_rays: every 128-point layer of the decoder MLP runs on mma.sync
+ * (fp16 operands, fp32 accumulate; activations stay in registers between layers).  mlp_f16 is the fp16
+ * weight image below (HL_MLP16_HALVES halves; rows = output features, row pitch = K + 8 halves so that
+ * ldmatrix is bank-conflict free; unused k columns zero); mlp_packed (the fp32 pack above) still supplies
+ * biases, the alpha / rgb heads and the view-direction rows of views_linear.  Same outputs as
+ * hl_render_rays to ~1e-5 relative (operand rounding averaged over 256 samples per ray).
+ *   HL_MLP16_W0: pts_linears.0  [128][40]   k = x(27) | 0(5)
+ *   HL_MLP16_W1: pts_linears.1  [128][136]
+ *   HL_MLP16_W2: pts_linears.2  [128][168]  k = x(27) | 0(5) | h1(128)
+ *   HL_MLP16_WF: feature_linear [128][136]
+ *   HL_MLP16_WV: views_linear   [64][136]   k = feature(128); pe(d) columns are folded into a per-ray bias */
+#define HL_MLP16_W0 0
+#define HL_MLP16_W1 (HL_MLP16_W0 + 128 * 40)
+#define HL_MLP16_W2 (HL_MLP16_W1 + 128 * 136)
+#define HL_MLP16_WF (HL_MLP16_W2 + 128 * 168)
+#define HL_MLP16_WV (HL_MLP16_WF + 128 * 136)
+#define HL_MLP16_HALVES (HL_MLP16_WV + 64 * 136)
+int hl_render_rays_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
+                      const float *rays_o, const float *rays_d, const float *near, const float *far,
+                      const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
+                      const float *bounds /*host*/, float *rgb, float *acc, float *depth, int64_t n_rays,
+                      int clamp_depth, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,9 +25,9 @@ def model_state_dict(flags, seed):
     return model, diffusion, sd
 
 
-def renderer_state_dict(seed=3):
+def renderer_state_dict(seed=3, precision="fp16"):
     from humanliff_b200.renderer import Renderer
-    r = Renderer(triplane_ch=27, test=True)
+    r = Renderer(triplane_ch=27, test=True, precision=precision)
     shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
     sd = synth.synth_state_dict(shapes, seed=seed, weight_gain=1.5)
     r.load_state_dict(sd, strict=False)

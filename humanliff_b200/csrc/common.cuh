@@ -49,7 +49,7 @@ __device__ __forceinline__ float hl_rna_tf32(float x) {
 __device__ __forceinline__ float hl_silu(float x) { return x / (1.0f + expf(-x)); }
 // SiLU for values that are about to be rounded to an 11-bit significand (fp16 / TF32 operands):
 // ex2.approx + rcp.approx, relative error ~2e-7, 3x fewer instructions than the exact form
-__device__ __forceinline__ float hl_silu_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float hl_silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float hl_warp_sum(float v) {
 #pragma unroll

@@ -50,6 +50,23 @@ __device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, fl
     }
 }
 
+// 8 consecutive channels: one 128-bit store for fp16 operands, two for fp32
+__device__ __forceinline__ void store_oct(void *dst, int dtype, int64_t idx, float4 a, float4 b, int round_tf32) {
+    if (dtype == HL_DT_F16) {
+        __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t *>(&h0);
+        u.y = *reinterpret_cast<uint32_t *>(&h1);
+        u.z = *reinterpret_cast<uint32_t *>(&h2);
+        u.w = *reinterpret_cast<uint32_t *>(&h3);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(dst) + idx) = u;
+    } else {
+        store_quad(dst, dtype, idx, a, round_tf32);
+        store_quad(dst, dtype, idx + 4, b, round_tf32);
+    }
+}
+
 static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
     int64_t g = (work_items + per_block - 1) / per_block;
     int64_t cap = (int64_t)hl_num_sms() * max_waves;
@@ -397,7 +414,7 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
                            int stats_ld, const float *__restrict__ gamma, const float *__restrict__ beta,
                            const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
                            int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
-                           int silu, int round_tf32, int pix_per_block) {
+                           int silu, int round_tf32, int pix_per_block, int oct) {
     __shared__ float sA[GN_MAX_C];
     __shared__ float sB[GN_MAX_C];
     __shared__ float gmean[64], grstd[64];
@@ -445,44 +462,69 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
         sB[c] = be;
     }
     __syncthreads();
-    const int q = C >> 2;
     const int p0 = blockIdx.x * pix_per_block;
     const int np = min(HW, p0 + pix_per_block) - p0;
     const int64_t pix0 = (int64_t)b * HW + p0;
-    const int dp = blockDim.x / q, dj = blockDim.x % q;
-    int p = threadIdx.x / q, j = threadIdx.x % q;
-    constexpr int U = 4;                       // independent 128-bit loads in flight per thread
-    while (p < np) {
-        int pp[U], jj[U];
-        float4 v[U];
+    if (oct) {
+        // fast path: a thread owns 8 fixed channels (coefficients in registers) and walks pixels with U rows in
+        // flight; 2 x 128-bit loads and one 128-bit (fp16) / two 128-bit (fp32) stores per 8 elements.  The
+        // first version of this loop (per-element index arithmetic, smem coefficients, IEEE reciprocal) was
+        // issue-bound at 53 % of the HBM roofline (ncu: warps stalled "not selected").
+        const int q8 = C >> 3;
+        const int lanes_p = blockDim.x / q8;
+        const int j8 = threadIdx.x % q8, tp = threadIdx.x / q8;
+        float ca[8], cb[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            pp[u] = p;
-            jj[u] = j;
-            if (p < np) v[u] = __ldcs(reinterpret_cast<const float4 *>(x + (pix0 + p) * ldx + 4 * j));
-            p += dp;
-            j += dj;
-            if (j >= q) { j -= q; ++p; }
-        }
+        for (int e = 0; e < 8; ++e) { ca[e] = sA[8 * j8 + e]; cb[e] = sB[8 * j8 + e]; }
+        const bool fast_silu = (y_dtype == HL_DT_F16) || round_tf32;
+        constexpr int U = 4;
+        for (int pb = tp; pb < np; pb += lanes_p * U) {
+            float4 v[U][2];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (pp[u] >= np) break;
-            const int64_t pix = pix0 + pp[u];
-            const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * jj[u]]);
-            const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * jj[u]]);
-            float4 o;
-            o.x = fmaf(v[u].x, a.x, c.x); o.y = fmaf(v[u].y, a.y, c.y);
-            o.z = fmaf(v[u].z, a.z, c.z); o.w = fmaf(v[u].w, a.w, c.w);
-            if (silu) {
-                if (y_dtype == HL_DT_F16 || round_tf32) {
-                    o.x = hl_silu_fast(o.x); o.y = hl_silu_fast(o.y); o.z = hl_silu_fast(o.z); o.w = hl_silu_fast(o.w);
-                } else {
-                    o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w);
+            for (int u = 0; u < U; ++u) {
+                const int pp = pb + u * lanes_p;
+                if (pp < np) {
+                    const float4 *src = reinterpret_cast<const float4 *>(x + (pix0 + pp) * ldx + 8 * j8);
+                    v[u][0] = __ldcs(src);
+                    v[u][1] = __ldcs(src + 1);
                 }
             }
-            store_quad(y, y_dtype, pix * ldy + 4 * jj[u], o, round_tf32);
-            if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * jj[u], v[u], round_tf32);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int pp = pb + u * lanes_p;
+                if (pp >= np) break;
+                const float in[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = fmaf(in[e], ca[e], cb[e]);
+                    if (silu) o[e] = fast_silu ? hl_silu_fast(o[e]) : hl_silu(o[e]);
+                }
+                const int64_t oidx = (pix0 + pp) * ldy + 8 * j8;
+                store_oct(y, y_dtype, oidx, make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]),
+                          round_tf32);
+                if (raw) store_oct(raw, y_dtype, (pix0 + pp) * ldraw + 8 * j8, v[u][0], v[u][1], round_tf32);
+            }
         }
+        return;
+    }
+    const int q = C >> 2;
+    const int dp = blockDim.x / q, dj = blockDim.x % q;
+    int p = threadIdx.x / q, j = threadIdx.x % q;
+    while (p < np) {
+        const int64_t pix = pix0 + p;
+        const float4 v = *reinterpret_cast<const float4 *>(x + pix * ldx + 4 * j);
+        const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
+        const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
+        float4 o;
+        o.x = fmaf(v.x, a.x, c.x); o.y = fmaf(v.y, a.y, c.y);
+        o.z = fmaf(v.z, a.z, c.z); o.w = fmaf(v.w, a.w, c.w);
+        if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
+        store_quad(y, y_dtype, pix * ldy + 4 * j, o, round_tf32);
+        if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, round_tf32);
+        p += dp;
+        j += dj;
+        if (j >= q) { j -= q; ++p; }
     }
 }
 
@@ -495,15 +537,20 @@ extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int sta
                  ldx >= C && ldy >= C && stats_ld >= C);
     HL_CHECK_ARG(y_dtype == HL_DT_F32 || y_dtype == HL_DT_F16);
     HL_CHECK_ARG(!raw || (ldraw % 4 == 0 && ldraw >= C));
+    const bool oct_ok = C % 8 == 0 && C / 8 <= 256 && ldy % 8 == 0 && (!raw || ldraw % 8 == 0) &&
+                        ((uintptr_t)y & 15) == 0 && (!raw || ((uintptr_t)raw & 15) == 0);
     int64_t want_blocks = (int64_t)hl_num_sms() * 8 / B;
     if (want_blocks < 1) want_blocks = 1;
     int pix_per_block = hl_cdiv(HW, want_blocks);
     int min_ppb = hl_cdiv(256 * 4 * 4, C / 4);  // >= 4 float4 per thread
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    k_gn_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
+    int threads = 256;
+    if (oct_ok) threads = (256 / (C / 8)) * (C / 8);   // fast path: whole channel octets
+    if (threads < 64) threads = 256;
+    k_gn_apply<<<grid, threads, 0, (cudaStream_t)stream>>>(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
                                                        y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu,
-                                                       round_tf32, pix_per_block);
+                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

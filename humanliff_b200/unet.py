@@ -135,6 +135,7 @@ class UNetModel(nn.Module):
         self._packed_key = None
         self._plans = {}
         self.use_cuda_graph = True
+        self.concurrent_encoders = True     # ControlNet encoder on a side stream (see _StepPlan._build)
 
     # ------------------------------------------------------------------ architecture / parameters
     def _conv(self, name, cin, cout, k, stride=1, cin_pad=None):
@@ -339,7 +340,11 @@ class _StepPlan:
         self.rnd = 1 if model.precision == "tf32" else 0
         self.calls = []
         self.bufs = {}
+        self.branch = 0              # 0 = main stream, 1 = side stream (ControlNet encoder)
+        self.n_events = 0
         self.graph = None
+        self.side = None
+        self.events = None
         self.runs = 0
         self._stats_off = 0
         self._stats_reqs = []
@@ -357,6 +362,11 @@ class _StepPlan:
     def opbuf(self, name, numel):
         return self.buf(name, numel, self.tdt)
 
+    def scratch(self, name, numel, op=False):
+        """Scratch reused in stream order; each concurrent branch (stream) owns its own copy."""
+        full = name if self.branch == 0 else f"{name}.b{self.branch}"
+        return self.opbuf(full, numel) if op else self.buf(full, numel)
+
     def stats_row(self, C):
         """Reserve a [B, C, 2] fp64 statistics block; returns its offset in doubles (resolved to a
         pointer once the arena is allocated)."""
@@ -370,7 +380,13 @@ class _StepPlan:
         return _Ref(_ptr(t), C, C, H, W, self.stats_row(C), C)
 
     def emit(self, name, *args):
-        self.calls.append((name, args))
+        self.calls.append((name, args, self.branch))
+
+    def emit_sync(self, kind, arg=None):
+        """Stream-dependency markers interpreted by _launch_all: ("fork",) side stream starts after everything
+        issued so far on the main stream; ("join",) main waits for the side stream; ("signal", k) main records
+        event k; ("wait", k) side stream waits for event k."""
+        self.calls.append(("#" + kind, (arg,), self.branch))
 
     # ---------------------------------------------------------------- op emitters
     def conv(self, cname, x_ptr, ldx, res, dst, H, W, flags=0, want_stats=True):
@@ -401,15 +417,15 @@ class _StepPlan:
         m, B = self.m, self.B
         cin, cout, H, W = blk["cin"], blk["cout"], x.H, x.W
         assert x.C == cin and dst.C == cout
-        act = _ptr(self.opbuf("act", self.max_act))
-        h = _Ref(_ptr(self.buf("h", self.max_act)), cout, cout, H, W, self.stats_row(cout), cout)
-        raw = _ptr(self.opbuf("raw", self.max_act)) if blk["skip"] is not None else None
+        act = _ptr(self.scratch("act", self.max_act, op=True))
+        h = _Ref(_ptr(self.scratch("h", self.max_act)), cout, cout, H, W, self.stats_row(cout), cout)
+        raw = _ptr(self.scratch("raw", self.max_act, op=True)) if blk["skip"] is not None else None
         self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=cin)
         self.conv(blk["c1"], act, cin, None, h, H, W)
         film = ("film", blk["film_off"])
         self.gn(blk["n2"], h, act, cout, True, film=film)
         if blk["skip"] is not None:
-            s = _Ref(_ptr(self.buf("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
+            s = _Ref(_ptr(self.scratch("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
             self.conv(blk["skip"], raw, cin, None, s, H, W, want_stats=False)
             self.conv(blk["c2"], act, cout, s, dst, H, W)
         else:
@@ -419,9 +435,9 @@ class _StepPlan:
         """unet.py:244-274."""
         m, B = self.m, self.B
         C, H, W = blk["c"], x.H, x.W
-        act = _ptr(self.opbuf("act", self.max_act))
-        qkv = _Ref(_ptr(self.buf("qkv", self.max_qkv)), 3 * C, 3 * C, H, W, None, 0)
-        att = _ptr(self.opbuf("att", self.max_act))
+        act = _ptr(self.scratch("act", self.max_act, op=True))
+        qkv = _Ref(_ptr(self.scratch("qkv", self.max_qkv)), 3 * C, 3 * C, H, W, None, 0)
+        att = _ptr(self.scratch("att", self.max_act, op=True))
         self.gn(blk["n"], x, act, C, False)
         self.conv(blk["qkv"], act, C, None, qkv, H, W, want_stats=False)
         self.emit("hl_attention", qkv.ptr, 3 * C, att, self.dt, C, B, H * W, C, m.num_heads, self.rnd)
@@ -452,11 +468,11 @@ class _StepPlan:
             elif kind == "attn":
                 self.attn_block(blk, x, out)
             elif kind == "down":
-                op = _ptr(self.opbuf("raw", self.max_act))
+                op = _ptr(self.scratch("raw", self.max_act, op=True))
                 self.cast(x, op, x.C)
                 self.conv(blk["c"], op, x.C, None, out, x.H, x.W)
             elif kind == "up":
-                op = _ptr(self.opbuf("upbuf", self.max_act))
+                op = _ptr(self.scratch("upbuf", self.max_act, op=True))
                 self.emit("hl_upsample2x", x.ptr, x.ld, op, self.dt, x.C, self.B, x.H, x.W, x.C, self.rnd)
                 self.conv(blk["c"], op, x.C, None, out, H, W)
             else:
@@ -485,12 +501,16 @@ class _StepPlan:
                 x = self.layers(layers, x, f"{tag}{i}", dst=cats[i] if direct else None)
             if controlnet_branch:
                 cname = f"input_blocks_proj_cond.{i}"
-                op = _ptr(self.opbuf("raw", self.max_act))
+                op = _ptr(self.scratch("raw", self.max_act, op=True))
                 self.cast(x, op, x.C)
                 hc = self.new_ref(f"{tag}p{i}", x.C, x.H, x.W)
                 self.conv(cname, op, x.C, None, hc, x.H, x.W)                    # h_cond (unet.py:600)
+                if self.concurrent:
+                    self.emit_sync("wait", i)                                    # hs[i] of the main encoder
                 self.conv(cname, op, x.C, self.hs[i], cats[i], x.H, x.W)         # hs + hs_cond (unet.py:606)
                 x = hc
+            elif self.keep_hs and self.concurrent:
+                self.emit_sync("signal", i)                                      # hs[i] complete
             outs.append(x)
         return outs
 
@@ -563,20 +583,31 @@ class _StepPlan:
         self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), None, _ptr(xin), self.dt, B, m.in_channels, H * W,
                   m.cin_pad, self.rnd)
 
-        # --- encoder, middle (unet.py:589-592) ---
+        # --- encoder, middle (unet.py:589-592) and ControlNet encoder (unet.py:594-602) ---
+        # The two encoders are independent until the decoder.  With `concurrent` the ControlNet branch is
+        # issued on a side stream (own scratch buffers): wherever a kernel of one branch leaves SMs idle
+        # (the 8^2 .. 32^2 layers launch 24-96 CTAs) the other branch fills them.  The only cross
+        # dependency -- the projection that adds hs[i] -- waits on an event recorded after main block i.
         controlnet = m._enc_cond is not None
+        self.concurrent = controlnet and m.concurrent_encoders
         self.hs, self.keep_hs = None, controlnet
-        hs = self.encoder(m._enc, _ptr(xin), "hs", self.cat_skip, False)
-        if controlnet:
-            self.hs = hs
-        x = self.layers(m._mid, hs[-1], "mid", dst=self.cat_h[0])
-
-        # --- ControlNet encoder (unet.py:594-602) ---
+        self.n_events = len(m._enc) if self.concurrent else 0
         if controlnet:
             xcin = self.opbuf("xcin", B * H * W * m.cin_pad)
             self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), _ptr(self.xc_in), _ptr(xcin), self.dt, B,
                       m.in_channels, H * W, m.cin_pad, self.rnd)
+        if self.concurrent:
+            self.emit_sync("fork")
+        hs = self.encoder(m._enc, _ptr(xin), "hs", self.cat_skip, False)
+        if controlnet:
+            self.hs = hs
+        x = self.layers(m._mid, hs[-1], "mid", dst=self.cat_h[0])
+        if controlnet:
+            self.branch = 1 if self.concurrent else 0
             self.encoder(m._enc_cond, _ptr(xcin), "hc", self.cat_skip, True)
+            self.branch = 0
+        if self.concurrent:
+            self.emit_sync("join")
 
         # --- decoder (unet.py:604-609) ---
         ndec = len(m._dec)
@@ -585,7 +616,7 @@ class _StepPlan:
             x = self.layers(layers, self.cat_full[j], f"dec{j}", dst=dst)
 
         # --- out: GN -> SiLU -> conv3x3 (unet.py:471-475,612) ---
-        act = _ptr(self.opbuf("act", self.max_act))
+        act = _ptr(self.scratch("act", self.max_act, op=True))
         self.gn("out.0", x, act, x.C, True)
         co_pad = 32 * ((m.out_channels + 31) // 32)
         eps = _Ref(_ptr(self.buf("eps_nhwc", B * H * W * co_pad)), co_pad, m.out_channels, H, W, None, 0)
@@ -605,13 +636,26 @@ class _StepPlan:
                 if a[0] == "stats_bytes":
                     return 8 * self.stats.numel()
             return a
-        self.calls = [(name, tuple(fix(a) for a in args)) for name, args in self.calls]
+        self.calls = [(name, tuple(fix(a) for a in args), br) for name, args, br in self.calls]
 
     # ---------------------------------------------------------------- execution
     def _launch_all(self):
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        for name, args in self.calls:
-            call(name, *args, stream)
+        main = torch.cuda.current_stream(self.device)
+        if self.n_events and self.side is None:
+            self.side = torch.cuda.Stream(self.device)
+            self.events = [torch.cuda.Event() for _ in range(self.n_events)]
+        streams = (main.cuda_stream, self.side.cuda_stream if self.side is not None else main.cuda_stream)
+        for name, args, br in self.calls:
+            if name[0] != "#":
+                call(name, *args, streams[br])
+            elif name == "#fork":
+                self.side.wait_stream(main)
+            elif name == "#join":
+                main.wait_stream(self.side)
+            elif name == "#signal":
+                self.events[args[0]].record(main)
+            elif name == "#wait":
+                self.side.wait_event(self.events[args[0]])
 
     def run(self, x, timesteps, x_cond, y):
         m = self.m
@@ -632,6 +676,10 @@ class _StepPlan:
                 self.graph = g
                 _lib.launch_count = n0               # capture records launches, it does not run them
             self.graph.replay()
-            _lib.launch_count += len(self.calls)
+            _lib.launch_count += self.n_launches
         self.runs += 1
         return self.out.clone()
+
+    @property
+    def n_launches(self):
+        return sum(1 for name, _, _ in self.calls if name[0] != "#")

@@ -165,6 +165,7 @@ def run_plan(plan, x, timesteps, x_cond, y):
         plan.xc_in.copy_(x_cond)
     if y is not None:
         plan.y_in.copy_(y)
-    for name, args in plan.calls:
-        _OPS[name](*args, None)
+    for name, args, _branch in plan.calls:
+        if name[0] != "#":                      # stream-dependency markers carry no arithmetic
+            _OPS[name](*args, None)
     return plan.out.clone()

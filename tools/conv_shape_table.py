@@ -6,7 +6,7 @@ m,d = factory.create_model_and_diffusion(**factory.production_flags(""))
 cpu=torch.device("cpu")
 m._pack(cpu)
 plan=_StepPlan(m,cpu,4,256,256)
-convs=[a for n,a in plan.calls if n=="hl_conv2d"]
+convs=[a for n,a,_b in plan.calls if n=="hl_conv2d"]
 lines=[l for l in open(sys.argv[1]) if not l.startswith('==')]
 rows=[r for r in csv.DictReader(lines) if r.get("Metric Name")=="gpu__time_duration.sum" and "k_conv_tc" in r["Kernel Name"]]
 print(len(convs), len(rows))

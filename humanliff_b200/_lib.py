@@ -36,9 +36,11 @@ SIGNATURES = {
                           c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_attention": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
+    "hl_ddim_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                c_i64, c_int, c_p]),
+    "hl_density_grid_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
     "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                   c_i64, c_int, c_p]),
 }

@@ -930,7 +930,9 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/;
     p.b_slot_bytes = (n_tile / pair) * ROW_BYTES;
     p.has_res = has_res ? 1 : 0;
-    int nbuf = 2;                                  // staging buffers PER epilogue group
+    // staging buffers PER epilogue group: 2; the HBM-bound 1x1 convs with a residual want a deeper residual
+    // prefetch (measured 0.124 -> 0.102 ms on 192->192 @ 256^2) and have the shared memory to spare
+    int nbuf = (has_res && ksize == 1) ? 4 : 2;
     if (g_tune_nbuf == 2 || g_tune_nbuf == 4) nbuf = g_tune_nbuf;
     for (;;) {
         int rest = budget - EPI_GROUPS * nbuf * STAGE_BUF_BYTES;

@@ -608,3 +608,58 @@ extern "C" int hl_ddpm_step(const float *x, const float *eps, const float *noise
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// DDIM update (gaussian_diffusion.py:484-529): same streams as the DDPM step, epsilon re-derived from the
+// clipped x0 exactly as the reference does, every operation separately rounded in the reference's order.
+// ------------------------------------------------------------------------------------------
+__global__ void k_ddim_step(const float *__restrict__ x, const float *__restrict__ eps,
+                            const float *__restrict__ noise, const float *__restrict__ coef,
+                            const float *__restrict__ sigma, const int64_t *__restrict__ t,
+                            float *__restrict__ sample, float *__restrict__ x0out, int64_t n4, int clip) {
+    int b = blockIdx.y;
+    int64_t ti = t[b];
+    const float c0 = coef[ti * 4 + 0], c1 = coef[ti * 4 + 1], ca = coef[ti * 4 + 2], cb = coef[ti * 4 + 3];
+    const float sg = sigma[ti];
+    const float4 *x4 = reinterpret_cast<const float4 *>(x) + (int64_t)b * n4;
+    const float4 *e4 = reinterpret_cast<const float4 *>(eps) + (int64_t)b * n4;
+    const float4 *z4 = noise ? reinterpret_cast<const float4 *>(noise) + (int64_t)b * n4 : nullptr;
+    float4 *s4 = reinterpret_cast<float4 *>(sample) + (int64_t)b * n4;
+    float4 *p4 = x0out ? reinterpret_cast<float4 *>(x0out) + (int64_t)b * n4 : nullptr;
+    auto one = [&](float xv, float ev, float zv, float &x0, float &s) {
+        const float cx = __fmul_rn(c0, xv);
+        x0 = __fsub_rn(cx, __fmul_rn(c1, ev));
+        if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        const float e2 = __fdiv_rn(__fsub_rn(cx, x0), c1);            // _predict_eps_from_xstart
+        const float mean = __fadd_rn(__fmul_rn(x0, ca), __fmul_rn(cb, e2));
+        s = __fadd_rn(mean, __fmul_rn(sg, zv));
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 xv = x4[i], ev = e4[i];
+        const float4 zv = z4 ? z4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x0, s;
+        one(xv.x, ev.x, zv.x, x0.x, s.x);
+        one(xv.y, ev.y, zv.y, x0.y, s.y);
+        one(xv.z, ev.z, zv.z, x0.z, s.z);
+        one(xv.w, ev.w, zv.w, x0.w, s.w);
+        s4[i] = s;
+        if (p4) p4[i] = x0;
+    }
+}
+
+extern "C" int hl_ddim_step(const float *x, const float *eps, const float *noise, const float *coef,
+                            const float *sigma, const int64_t *t, float *sample, float *pred_xstart, int B,
+                            int64_t n, int clip, void *stream) {
+    HL_CHECK_ARG(x && eps && coef && sigma && t && sample && B > 0 && n > 0 && n % 4 == 0);
+    int64_t n4 = n / 4;
+    int gx = (int)((n4 + 255) / 256);
+    int cap = hl_num_sms() * 8 / B;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, B);
+    k_ddim_step<<<grid, 256, 0, (cudaStream_t)stream>>>(x, eps, noise, coef, sigma, t, sample, pred_xstart, n4,
+                                                        clip);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}

@@ -130,13 +130,18 @@ __device__ __forceinline__ void act_pack(float (&acc)[NT8][4], uint32_t (*a)[4])
 }
 
 // Nine-plane gather of one 128-point tile into Xs[128][XP] fp16 (renderer.py:504-549; A.5 of SURVEY)
+__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, __half *Xs);
+
 __device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_s, float ox, float oy, float oz,
                                             float dx, float dy, float dz, __half *Xs) {
+    const float z = z_s[threadIdx.x & 127];
+    // pts = o + d*z (separately rounded, as the reference's broadcasting arithmetic does)
+    gather_point(a, __fadd_rn(ox, __fmul_rn(dx, z)), __fadd_rn(oy, __fmul_rn(dy, z)), __fadd_rn(oz, __fmul_rn(dz, z)), Xs);
+}
+
+// features of one world-space point per thread pair (threads p and p+128 split the nine sub-planes)
+__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, __half *Xs) {
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const float z = z_s[p];
-    const float px = __fadd_rn(ox, __fmul_rn(dx, z));
-    const float py = __fadd_rn(oy, __fmul_rn(dy, z));
-    const float pz = __fadd_rn(oz, __fmul_rn(dz, z));
     const float cx = 2.f * (px - a.bmin[0]) / (a.bmax[0] - a.bmin[0]) - 1.f;
     const float cy = 2.f * (py - a.bmin[1]) / (a.bmax[1] - a.bmin[1]) - 1.f;
     const float cz = 2.f * (pz - a.bmin[2]) / (a.bmax[2] - a.bmin[2]) - 1.f;
@@ -467,7 +472,75 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
     }
 }
 
+// Density on a regular grid (Renderer.extract_geometry, human_diffusion/NeRF/renderer.py:290-318): the
+// coarse-pass stage of the renderer (gather + density MLP) over R^3 points x = linspace(bmin, bmax, R),
+// out[xi][yi][zi] = -sigma, 128 points per tile.
+__global__ void __launch_bounds__(NT, 1) k_density_grid_tc(const RenderArgs a, int res, float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    __half *Wsm = reinterpret_cast<__half *>(smraw);
+    float *fb = reinterpret_cast<float *>(Wsm + W_HALVES);
+    __half *Xs = reinterpret_cast<__half *>(fb + FB_FLOATS);
+    float *sig = reinterpret_cast<float *>(Xs + 128 * XP);     // [128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.w16);
+        uint4 *dst = reinterpret_cast<uint4 *>(Wsm);
+        for (int i = tid; i < W_HALVES / 8; i += NT) dst[i] = __ldg(src + i);
+        for (int i = tid; i < 128; i += NT) {
+            fb[FB_B0 + i] = __ldg(a.mlp + HL_MLP_B0 + i);
+            fb[FB_B1 + i] = __ldg(a.mlp + HL_MLP_B1 + i);
+            fb[FB_B2 + i] = __ldg(a.mlp + HL_MLP_B2 + i);
+            fb[FB_WA + i] = __ldg(a.mlp + HL_MLP_WA + i);
+        }
+        if (tid < 4) fb[FB_BA + tid] = __ldg(a.mlp + HL_MLP_BA + tid);
+    }
+    __syncthreads();
+    const uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(Wsm);
+    const long long total = (long long)res * res * res;
+    const long long tiles = (total + 127) / 128;
+    // torch.linspace(lo, hi, R): lo + i*step below the midpoint, hi - (R-1-i)*step above (ATen)
+    auto lin = [&](float lo, float hi, int i) {
+        const float step = (hi - lo) / (float)(res - 1);
+        return i < res / 2 ? __fadd_rn(lo, __fmul_rn(step, (float)i)) : __fsub_rn(hi, __fmul_rn(step, (float)(res - 1 - i)));
+    };
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        long long idx = tile * 128 + (tid & 127);
+        if (idx >= total) idx = total - 1;
+        const int zi = (int)(idx % res), yi = (int)((idx / res) % res), xi = (int)(idx / ((long long)res * res));
+        __syncthreads();     // previous tile consumed (Xs, sig)
+        gather_point(a, lin(a.bmin[0], a.bmax[0], xi), lin(a.bmin[1], a.bmax[1], yi), lin(a.bmin[2], a.bmax[2], zi), Xs);
+        __syncthreads();
+        mlp_warp<false>(w_addr, fb, nullptr, Xs, sig, nullptr, 0, warp, lane);
+        __syncthreads();
+        if (tid < 128 && tile * 128 + tid < total) out[tile * 128 + tid] = -sig[tid];
+    }
+}
+
 }  // namespace
+
+extern "C" int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
+                                  const float *bounds, int resolution, float *out, void *stream) {
+    HL_CHECK_ARG(texels && mlp_packed && mlp_f16 && bounds && out && R > 0 && resolution >= 2);
+    HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0 && ((uintptr_t)mlp_f16 & 15) == 0);
+    RenderArgs a = {};
+    a.tex = reinterpret_cast<const float4 *>(texels);
+    a.R = R;
+    a.mlp = mlp_packed;
+    a.w16 = reinterpret_cast<const __half *>(mlp_f16);
+    for (int i = 0; i < 3; ++i) { a.bmin[i] = bounds[i]; a.bmax[i] = bounds[3 + i]; }
+    const size_t smem = (size_t)W_HALVES * 2 + sizeof(float) * FB_FLOATS + (size_t)128 * XP * 2 + sizeof(float) * 128;
+    static bool configured = false;
+    if (!configured) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_density_grid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long tiles = ((long long)resolution * resolution * resolution + 127) / 128;
+    long long grid = hl_num_sms();
+    if (grid > tiles) grid = tiles;
+    k_density_grid_tc<<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a, resolution, out);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
 
 extern "C" int hl_render_rays_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
                                  const float *rays_o, const float *rays_d, const float *near, const float *far,

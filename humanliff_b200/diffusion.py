@@ -219,10 +219,83 @@ class GaussianDiffusion:
     def training_losses(self, *a, **k):
         raise NotImplementedError("training is outside the B200 inference hot path (SURVEY.md 8)")
 
-    def ddim_sample(self, *a, **k):
-        raise NotImplementedError("DDIM sampling is a 'next' row (SURVEY.md 8(f) rank 2)")
+    # ------------------------------------------------------------------ DDIM (gaussian_diffusion.py:484-529,569-651)
+    def _ddim_tables(self, device, eta):
+        key = (str(device), float(eta))
+        tb = self._dev_tables.get(("ddim",) + key)
+        if tb is None:
+            if self.model_mean_type != ModelMeanType.EPSILON:
+                raise NotImplementedError("only epsilon-prediction (predict_xstart=False) is built")
+            # fp32 tensor arithmetic in the reference's order on the fp32 casts of the float64 tables
+            # (`_extract_into_tensor(...).float()` then th.sqrt / arithmetic, :512-524)
+            ab = torch.from_numpy(self.alphas_cumprod).float()
+            abp = torch.from_numpy(self.alphas_cumprod_prev).float()
+            sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+            coef = torch.stack([torch.from_numpy(self.sqrt_recip_alphas_cumprod).float(),
+                                torch.from_numpy(self.sqrt_recipm1_alphas_cumprod).float(),
+                                torch.sqrt(abp), torch.sqrt(1 - abp - sigma ** 2)], dim=1).contiguous()
+            sigma = sigma.clone()
+            sigma[0] = 0.0                                   # nonzero_mask = (t != 0)
+            tb = {"coef": coef.to(device), "sigma": sigma.contiguous().to(device)}
+            self._dev_tables[("ddim",) + key] = tb
+        return tb
 
-    ddim_sample_loop = ddim_sample
+    def ddim_sample(self, model, x, t, x_cond=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
+                    eta=0.0, noise=None):
+        """gaussian_diffusion.py:484-529 -- NB argument order (model, x, t, x_cond=None, ...), unlike p_sample.
+        ``noise`` (extension): inject the Gaussian instead of drawing ``randn_like(x)``."""
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
+        if model_kwargs is None:
+            model_kwargs = {}
+        assert t.shape == (x.shape[0],)
+        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
+        tb = self._ddim_tables(x.device, eta)
+        if noise is None and eta != 0.0:
+            noise = torch.randn_like(x)
+        x, eps = x.contiguous(), eps.contiguous()
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        t64 = t if t.dtype == torch.int64 else t.long()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        call("hl_ddim_step", x.data_ptr(), eps.data_ptr(), noise.contiguous().data_ptr() if noise is not None else None,
+             tb["coef"].data_ptr(), tb["sigma"].data_ptr(), t64.data_ptr(), sample.data_ptr(), x0.data_ptr(),
+             x.shape[0], x[0].numel(), 1 if clip_denoised else 0, stream)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def ddim_sample_loop(self, model, shape, x_cond=None, noise=None, clip_denoised=True, denoised_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0, step_noise=None):
+        final = None
+        for sample in self.ddim_sample_loop_progressive(model, shape, x_cond=x_cond, noise=noise,
+                                                        clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                                        model_kwargs=model_kwargs, device=device, progress=progress,
+                                                        eta=eta, step_noise=step_noise):
+            final = sample
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, x_cond=None, noise=None, clip_denoised=True,
+                                     denoised_fn=None, model_kwargs=None, device=None, progress=False, eta=0.0,
+                                     step_noise=None):
+        """gaussian_diffusion.py:603-651."""
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else torch.randn(*shape, device=device)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        t = torch.empty(shape[0], device=device, dtype=torch.int64)
+        for i in indices:
+            t.fill_(i)
+            with torch.no_grad():
+                z = step_noise(i) if step_noise is not None else None
+                out = self.ddim_sample(model, img, t, x_cond=x_cond, clip_denoised=clip_denoised,
+                                       denoised_fn=denoised_fn, model_kwargs=model_kwargs, eta=eta, noise=z)
+                yield out
+                img = out["sample"]
+
+    def ddim_reverse_sample(self, *a, **k):
+        raise NotImplementedError("the DDIM reverse ODE (NLL evaluation) is outside the sampling hot path")
 
 
 def space_timesteps(num_timesteps, section_counts):
@@ -282,6 +355,9 @@ class SpacedDiffusion(GaussianDiffusion):
 
     def p_sample(self, model, *args, **kwargs):
         return super().p_sample(self._wrap_model(model), *args, **kwargs)
+
+    def ddim_sample(self, model, *args, **kwargs):
+        return super().ddim_sample(self._wrap_model(model), *args, **kwargs)
 
     def _wrap_model(self, model):
         if isinstance(model, _WrappedModel):

@@ -182,6 +182,44 @@ class Renderer(nn.Module):
                 call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), *tail)
         return rgb, acc, depth
 
+    # ------------------------------------------------------------------ extract_geometry ("next" row)
+    @torch.no_grad()
+    def density_grid(self, tp_input, tri_planes, resolution=512):
+        """The field ``u`` of ``extract_geometry`` (human_diffusion/NeRF/renderer.py:290-318): ``-sigma`` of the
+        density MLP on ``linspace(min, max, resolution)^3`` inside ``tp_input['world_bounds'][0]``, evaluated by
+        the coarse stage of the fused render kernel (one launch instead of 67 chunks of 2 M points).
+        Returns a ``[res, res, res]`` fp32 CUDA tensor indexed ``[x, y, z]``."""
+        dev = tri_planes.device
+        if dev.type != "cuda":
+            raise RuntimeError("humanliff_b200.Renderer runs on CUDA (sm_100a) only -- no CPU fallback")
+        with torch.cuda.device(dev):
+            mlp = self._pack(dev)
+            planes = tri_planes.detach().to(dev, torch.float32).reshape(3, 9, *tri_planes.shape[-2:]).contiguous()
+            tex = self._texels(planes)
+            wb = tp_input["world_bounds"]
+            b = [float(v) for v in torch.as_tensor(wb, dtype=torch.float32).reshape(-1, 6)[0].tolist()]
+            import ctypes
+            barr = (ctypes.c_float * 6)(*b)
+            out = torch.empty(resolution, resolution, resolution, device=dev, dtype=torch.float32)
+            call("hl_density_grid_tc", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16.data_ptr(),
+                 ctypes.cast(barr, ctypes.c_void_p), int(resolution), out.data_ptr(),
+                 torch.cuda.current_stream(dev).cuda_stream)
+        return out
+
+    def extract_geometry(self, tp_input, tri_planes=None, resolution=512, threshold=0.0):
+        """human_diffusion/NeRF/renderer.py:290-330: density grid on the GPU, then the reference's own host-side
+        ``mcubes.smooth`` + ``marching_cubes`` (PyMCubes, a third-party CPU library the reference imports)."""
+        u = self.density_grid(tp_input, tri_planes, resolution).cpu().numpy()
+        try:
+            import mcubes
+        except ImportError as e:      # the mesh step is the reference's CPU dependency, not part of the hot path
+            raise RuntimeError("extract_geometry needs PyMCubes for marching cubes; density_grid() returns the "
+                               "field it consumes") from e
+        vertices, triangles = mcubes.marching_cubes(mcubes.smooth(u), threshold)
+        wb = torch.as_tensor(tp_input["world_bounds"], dtype=torch.float32).reshape(-1, 2, 3)[0].cpu().numpy()
+        vertices = vertices / (resolution - 1.0) * (wb[1] - wb[0])[None, :] + wb[0][None, :]
+        return vertices, triangles
+
     # ------------------------------------------------------------------ reference-shaped entry point
     def _render_batched(self, tp_input, z_vals, rays_o, rays_d, near, far, tri_planes, n_importance,
                         white_bkgd, u=None):

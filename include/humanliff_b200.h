@@ -153,6 +153,14 @@ int hl_ddpm_step(const float *x, const float *eps, const float *noise, const flo
                  const float *sigma, const int64_t *t, float *sample, float *pred_xstart, int B,
                  int64_t n, int clip, void *stream);
 
+/* DDIM update (gaussian_diffusion.py:484-529, "next" row of SURVEY 8(f)): coef [T, 4] fp32 =
+ * {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, sqrt(alpha_bar_prev), sqrt(1 - alpha_bar_prev -
+ * sigma^2)}; sigma [T] = eta-dependent DDIM sigma with the t == 0 entry zeroed; noise may be NULL (eta = 0).
+ * x0 = clip(c0 x - c1 eps);  eps' = (c0 x - x0) / c1;  sample = x0 ca + cb eps' + sigma_t noise           */
+int hl_ddim_step(const float *x, const float *eps, const float *noise /*nullable*/, const float *coef,
+                 const float *sigma, const int64_t *t, float *sample, float *pred_xstart, int B, int64_t n,
+                 int clip, void *stream);
+
 /* ---- tri-plane volume renderer (recon_NeRF/lib/renderer.py:142-295,504-581;
  *      recon_NeRF/run_nerf_batch.py:29-67; human_diffusion/NeRF/renderer.py:234-281) ----------- */
 
@@ -215,6 +223,13 @@ int hl_render_rays_tc(const float *texels, int R, const float *mlp_packed, const
                       const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
                       const float *bounds /*host*/, float *rgb, float *acc, float *depth, int64_t n_rays,
                       int clamp_depth, void *stream);
+
+/* Density on a regular grid -- the GPU part of Renderer.extract_geometry ("next" row, SURVEY 8(f) rank 1;
+ * human_diffusion/NeRF/renderer.py:290-318): out[xi][yi][zi] = -sigma(p), p = (linspace(min_x, max_x, res)[xi],
+ * ...), the coarse stage of the renderer (nine-plane gather + density MLP on the tensor cores) over res^3
+ * points.  Marching cubes stays on the host (mcubes in the reference).                              */
+int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
+                       const float *bounds /*host*/, int resolution, float *out, void *stream);
 
 #ifdef __cplusplus
 }

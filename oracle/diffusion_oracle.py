@@ -2,7 +2,7 @@
 
 Follows human_diffusion/improved_diffusion/gaussian_diffusion.py:18-42 (beta schedule), :118-169
 (tables), :232-326 (p_mean_variance, FIXED_LARGE / FIXED_SMALL, epsilon prediction), :356-388
-(p_sample), :434-482 (loop) and respace.py:7-60,72-86,117-122 (timestep respacing).  Tables are
+(p_sample), :434-482 (loop), :484-529 (ddim_sample) and respace.py:7-60,72-86,117-122 (timestep respacing).  Tables are
 float64 numpy; per-step arithmetic is fp32 torch exactly in the reference's operation order
 (SURVEY.md Appendix A.1).  Noise is always injected by the caller."""
 import numpy as np
@@ -68,6 +68,19 @@ class DiffusionOracle:
         mask = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
         sample = mean + mask * torch.exp(0.5 * self._ex(self.logvar, t, x)) * noise
         return sample, x0
+
+    def ddim_posterior(self, x, eps, t, noise, eta=0.0, clip=True):
+        """(sample, pred_xstart) of ddim_sample given the model output -- gaussian_diffusion.py:500-529."""
+        c0, c1 = self._ex(self.sqrt_recip, t, x), self._ex(self.sqrt_recipm1, t, x)
+        x0 = c0 * x - c1 * eps
+        if clip:
+            x0 = x0.clamp(-1, 1)
+        eps2 = (c0 * x - x0) / c1                                  # _predict_eps_from_xstart (:335-339)
+        ab, abp = self._ex(self.abar, t, x), self._ex(self.abar_prev, t, x)
+        sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+        mean = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps2
+        mask = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+        return mean + mask * sigma * noise, x0
 
     @torch.no_grad()
     def p_sample(self, sd, x, x_cond, t, y, noise, clip=True, operand_round=None):

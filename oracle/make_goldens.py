@@ -86,6 +86,31 @@ def unet_case(name, flags, B, HW, ts, seed_w, loop_steps):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def ddim_case(name, flags, B, HW, ts, etas, seed_w):
+    """ddim_sample of the unmodified reference (gaussian_diffusion.py:484-529) with injected noise; inputs and
+    weights are those of the matching unet_case, so epsilon is already in that golden."""
+    t0 = time.time()
+    model, diffusion = build_ref(flags, seed_w)
+    x, x_cond, g = synth.synth_denoise_inputs(B, 27, HW, HW, seed=1234)
+    y = torch.arange(B) % 4
+    noise = torch.randn(B, 27, HW, HW, generator=torch.Generator().manual_seed(4321))
+    out = {"ts": np.array(ts), "etas": np.array(etas), "noise": noise.numpy()}
+    with torch.no_grad():
+        for t in ts:
+            tt = torch.full((B,), t, dtype=torch.int64)
+            for eta in etas:
+                orig = inject_noise([noise])
+                try:
+                    r = diffusion.ddim_sample(model, x, tt, x_cond=x_cond, clip_denoised=True,
+                                              model_kwargs={"y": y}, eta=eta)
+                finally:
+                    torch.randn_like = orig
+                out[f"sample_{t}_{eta}"] = r["sample"].numpy()
+                out[f"x0_{t}_{eta}"] = r["pred_xstart"].numpy()
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
 def render_case(name, n_rays=1024, seed_w=3):
     t0 = time.time()
     hd = ref_shims.import_hd_renderer()
@@ -126,10 +151,12 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
         render_case("render_1024.npz")
+    if "ddim" in which:
+        ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)

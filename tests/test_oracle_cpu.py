@@ -43,6 +43,19 @@ def test_oracle_loop_matches_reference_golden():
     assert rel_l2(img, g["loop_final"]) < 1e-5
 
 
+def test_ddim_oracle_matches_reference_golden():
+    """ddim_sample restatement vs the unmodified reference (gaussian_diffusion.py:484-529): bit-exact given the
+    model output (eps taken from the UNet golden of the same inputs / weights)."""
+    g, gd = load_golden("unet_tiny_32.npz"), load_golden("ddim_tiny_32.npz")
+    orc = diffusion_oracle.DiffusionOracle(1000, "250")
+    for t in gd["ts"].tolist():
+        tt = torch.full((g["x"].shape[0],), t, dtype=torch.int64)
+        for eta in gd["etas"].tolist():
+            sample, x0 = orc.ddim_posterior(g["x"], g[f"eps_{t}"], tt, gd["noise"], eta=eta)
+            assert torch.equal(x0, gd[f"x0_{t}_{eta}"]), (t, eta)
+            assert torch.equal(sample, gd[f"sample_{t}_{eta}"]), (t, eta)
+
+
 def test_schedule_tables_match_product():
     from humanliff_b200 import create_gaussian_diffusion
     for resp in ("", "250", "100"):

@@ -96,3 +96,19 @@ def test_render_recon_variant_no_depth_clamp():
     ref = render_oracle.render_rays(sd, planes[0], bounds, g["rays_o"][:n], g["rays_d"][:n], g["near"][:n],
                                     g["far"][:n], g["u"][:n], clamp_depth=False)
     assert rel_l2(out["rgb_map"][0], ref[0]) < 1e-3 and rel_l2(out["depth_map"][0], ref[2]) < 1e-3
+
+
+def test_density_grid_vs_oracle():
+    """extract_geometry's field (human_diffusion/NeRF/renderer.py:290-318): -sigma on linspace(min, max, res)^3."""
+    from oracle import render_oracle
+    r, sd, g, planes, bounds = _setup("fp16")
+    dev = torch.device("cuda:0")
+    res = 20
+    u = r.density_grid({"world_bounds": bounds[None].to(dev)}, planes.to(dev), resolution=res)
+    assert u.shape == (res, res, res)
+    xs, ys, zs = (torch.linspace(float(bounds[0, i]), float(bounds[1, i]), res) for i in range(3))
+    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
+    ref = -render_oracle.mlp(sd, render_oracle.plane_features(planes[0], pts, bounds[0], bounds[1])).reshape(res, res, res)
+    assert rel_l2(u, ref) < 1e-3, rel_l2(u, ref)
+    assert rel_max(u, ref) < 2e-3

@@ -41,88 +41,21 @@ CASES = [
 ]
 
 TIMING = [
-    ("3x3 768->768@16 n64 cta2=0", (4, 16, 16, 768, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@16 n64 cta2=1", (4, 16, 16, 768, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@16 n128 cta2=0", (4, 16, 16, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@16 n128 cta2=1", (4, 16, 16, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@16 n192 cta2=0", (4, 16, 16, 768, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@16 n192 cta2=1", (4, 16, 16, 768, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@16 n256 cta2=0", (4, 16, 16, 768, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@16 n256 cta2=1", (4, 16, 16, 768, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@8 n64 cta2=0", (4, 8, 8, 768, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@8 n64 cta2=1", (4, 8, 8, 768, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@8 n128 cta2=0", (4, 8, 8, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@8 n128 cta2=1", (4, 8, 8, 768, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@8 n192 cta2=0", (4, 8, 8, 768, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@8 n192 cta2=1", (4, 8, 8, 768, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->768@8 n256 cta2=0", (4, 8, 8, 768, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->768@8 n256 cta2=1", (4, 8, 8, 768, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@16 n64 cta2=0", (4, 16, 16, 1536, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@16 n64 cta2=1", (4, 16, 16, 1536, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@16 n128 cta2=0", (4, 16, 16, 1536, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@16 n128 cta2=1", (4, 16, 16, 1536, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@16 n192 cta2=0", (4, 16, 16, 1536, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@16 n192 cta2=1", (4, 16, 16, 1536, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@16 n256 cta2=0", (4, 16, 16, 1536, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@16 n256 cta2=1", (4, 16, 16, 1536, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@8 n64 cta2=0", (4, 8, 8, 1536, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@8 n64 cta2=1", (4, 8, 8, 1536, 768, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@8 n128 cta2=0", (4, 8, 8, 1536, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@8 n128 cta2=1", (4, 8, 8, 1536, 768, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@8 n192 cta2=0", (4, 8, 8, 1536, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@8 n192 cta2=1", (4, 8, 8, 1536, 768, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 1536->768@8 n256 cta2=0", (4, 8, 8, 1536, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 1536->768@8 n256 cta2=1", (4, 8, 8, 1536, 768, 3), (1, 256, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 384->384@32 n64 cta2=0", (4, 32, 32, 384, 384, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 384->384@32 n64 cta2=1", (4, 32, 32, 384, 384, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 384->384@32 n128 cta2=0", (4, 32, 32, 384, 384, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 384->384@32 n128 cta2=1", (4, 32, 32, 384, 384, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 384->384@32 n192 cta2=0", (4, 32, 32, 384, 384, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 384->384@32 n192 cta2=1", (4, 32, 32, 384, 384, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->384@32 n64 cta2=0", (4, 32, 32, 768, 384, 3), (1, 64, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->384@32 n64 cta2=1", (4, 32, 32, 768, 384, 3), (1, 64, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->384@32 n128 cta2=0", (4, 32, 32, 768, 384, 3), (1, 128, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->384@32 n128 cta2=1", (4, 32, 32, 768, 384, 3), (1, 128, -1, -1, -1), (-1, -1, 1), True, True),
-    ("3x3 768->384@32 n192 cta2=0", (4, 32, 32, 768, 384, 3), (1, 192, -1, -1, -1), (-1, -1, 0), True, True),
-    ("3x3 768->384@32 n192 cta2=1", (4, 32, 32, 768, 384, 3), (1, 192, -1, -1, -1), (-1, -1, 1), True, True),
-    ("1x1 384->1152@32 n64 cta2=0", (4, 32, 32, 384, 1152, 1), (1, 64, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 384->1152@32 n64 cta2=1", (4, 32, 32, 384, 1152, 1), (1, 64, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 384->1152@32 n128 cta2=0", (4, 32, 32, 384, 1152, 1), (1, 128, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 384->1152@32 n128 cta2=1", (4, 32, 32, 384, 1152, 1), (1, 128, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 384->1152@32 n192 cta2=0", (4, 32, 32, 384, 1152, 1), (1, 192, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 384->1152@32 n192 cta2=1", (4, 32, 32, 384, 1152, 1), (1, 192, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@16 n64 cta2=0", (4, 16, 16, 768, 2304, 1), (1, 64, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@16 n64 cta2=1", (4, 16, 16, 768, 2304, 1), (1, 64, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@16 n128 cta2=0", (4, 16, 16, 768, 2304, 1), (1, 128, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@16 n128 cta2=1", (4, 16, 16, 768, 2304, 1), (1, 128, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@16 n192 cta2=0", (4, 16, 16, 768, 2304, 1), (1, 192, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@16 n192 cta2=1", (4, 16, 16, 768, 2304, 1), (1, 192, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@16 n256 cta2=0", (4, 16, 16, 768, 2304, 1), (1, 256, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@16 n256 cta2=1", (4, 16, 16, 768, 2304, 1), (1, 256, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@8 n64 cta2=0", (4, 8, 8, 768, 2304, 1), (1, 64, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@8 n64 cta2=1", (4, 8, 8, 768, 2304, 1), (1, 64, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@8 n128 cta2=0", (4, 8, 8, 768, 2304, 1), (1, 128, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@8 n128 cta2=1", (4, 8, 8, 768, 2304, 1), (1, 128, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@8 n192 cta2=0", (4, 8, 8, 768, 2304, 1), (1, 192, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@8 n192 cta2=1", (4, 8, 8, 768, 2304, 1), (1, 192, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->2304@8 n256 cta2=0", (4, 8, 8, 768, 2304, 1), (1, 256, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->2304@8 n256 cta2=1", (4, 8, 8, 768, 2304, 1), (1, 256, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@16 n64 cta2=0", (4, 16, 16, 768, 768, 1), (1, 64, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@16 n64 cta2=1", (4, 16, 16, 768, 768, 1), (1, 64, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@16 n128 cta2=0", (4, 16, 16, 768, 768, 1), (1, 128, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@16 n128 cta2=1", (4, 16, 16, 768, 768, 1), (1, 128, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@16 n192 cta2=0", (4, 16, 16, 768, 768, 1), (1, 192, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@16 n192 cta2=1", (4, 16, 16, 768, 768, 1), (1, 192, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@16 n256 cta2=0", (4, 16, 16, 768, 768, 1), (1, 256, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@16 n256 cta2=1", (4, 16, 16, 768, 768, 1), (1, 256, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@8 n64 cta2=0", (4, 8, 8, 768, 768, 1), (1, 64, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@8 n64 cta2=1", (4, 8, 8, 768, 768, 1), (1, 64, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@8 n128 cta2=0", (4, 8, 8, 768, 768, 1), (1, 128, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@8 n128 cta2=1", (4, 8, 8, 768, 768, 1), (1, 128, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@8 n192 cta2=0", (4, 8, 8, 768, 768, 1), (1, 192, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@8 n192 cta2=1", (4, 8, 8, 768, 768, 1), (1, 192, -1, -1, -1), (-1, -1, 1), False, False),
-    ("1x1 768->768@8 n256 cta2=0", (4, 8, 8, 768, 768, 1), (1, 256, -1, -1, -1), (-1, -1, 0), False, False),
-    ("1x1 768->768@8 n256 cta2=1", (4, 8, 8, 768, 768, 1), (1, 256, -1, -1, -1), (-1, -1, 1), False, False),
+    # name, shape (B,H,W,Cin,Cout,k), tuning (mh,n,halo,epi_stats,base_off), tuning2 (max_stages, nbuf, cta2), residual, stats
+    ("3x3 192@256 res+stats default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
+    ("3x3 192@256 res+stats tap nbuf2", (4, 256, 256, 192, 192, 3), (-1, -1, 0, -1, -1), (-1, 2, -1), True, True),
+    ("3x3 192@256 res+stats tap nbuf4", (4, 256, 256, 192, 192, 3), (-1, -1, 0, -1, -1), (-1, 4, -1), True, True),
+    ("3x3 192@256 res+stats halo nbuf4", (4, 256, 256, 192, 192, 3), (-1, -1, 1, -1, -1), (-1, 4, -1), True, True),
+    ("3x3 192@256 res only default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, False),
+    ("3x3 192@256 stats only default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), False, True),
+    ("3x3 192@256 plain default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), False, False),
+    ("3x3 192@256 plain tap", (4, 256, 256, 192, 192, 3), (-1, -1, 0, -1, -1), (-1, -1, -1), False, False),
+    ("1x1 192@256 res+stats default", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
+    ("1x1 192@256 res+stats nbuf4", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, 4, -1), True, True),
+    ("3x3 192@128 res+stats default", (4, 128, 128, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
+    ("3x3 192@128 res+stats tap nbuf4", (4, 128, 128, 192, 192, 3), (-1, -1, 0, -1, -1), (-1, 4, -1), True, True),
+    ("3x3 384@64 res+stats default", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
+    ("3x3 384@64 res+stats nbuf4", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, 4, -1), True, True),
 ]
 
 def run_case(idx):

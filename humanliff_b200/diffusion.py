@@ -254,10 +254,11 @@ class GaussianDiffusion:
         if noise is None and eta != 0.0:
             noise = torch.randn_like(x)
         x, eps = x.contiguous(), eps.contiguous()
+        noise = noise.contiguous() if noise is not None else None
         sample, x0 = torch.empty_like(x), torch.empty_like(x)
         t64 = t if t.dtype == torch.int64 else t.long()
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        call("hl_ddim_step", x.data_ptr(), eps.data_ptr(), noise.contiguous().data_ptr() if noise is not None else None,
+        call("hl_ddim_step", x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None,
              tb["coef"].data_ptr(), tb["sigma"].data_ptr(), t64.data_ptr(), sample.data_ptr(), x0.data_ptr(),
              x.shape[0], x[0].numel(), 1 if clip_denoised else 0, stream)
         return {"sample": sample, "pred_xstart": x0}

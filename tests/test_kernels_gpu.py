@@ -367,15 +367,17 @@ def test_ddim_step_bit_exact(dev):
     g = torch.Generator().manual_seed(10)
     shape = (4, 27, 16, 16)
     x, eps, z = (torch.randn(shape, generator=g) for _ in range(3))
+    xd, ed, zd = x.to(dev), eps.to(dev), z.to(dev)             # keep the device copies alive across the call
     for resp in ("250", ""):
         d = create_gaussian_diffusion(steps=1000, timestep_respacing=resp)
         o = DiffusionOracle(1000, resp)
         t = torch.tensor([0, 1, d.num_timesteps // 2, d.num_timesteps - 1])
+        td = t.to(dev)
         for eta in (0.0, 0.5):
             tb = d._ddim_tables(dev, eta)
             sample, x0 = torch.empty(shape, device=dev), torch.empty(shape, device=dev)
-            call("hl_ddim_step", x.to(dev).data_ptr(), eps.to(dev).data_ptr(), z.to(dev).data_ptr(), tb["coef"].data_ptr(),
-                 tb["sigma"].data_ptr(), t.to(dev).data_ptr(), sample.data_ptr(), x0.data_ptr(), 4, x[0].numel(), 1,
+            call("hl_ddim_step", xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), tb["coef"].data_ptr(),
+                 tb["sigma"].data_ptr(), td.data_ptr(), sample.data_ptr(), x0.data_ptr(), 4, x[0].numel(), 1,
                  _stream())
             rs, r0 = o.ddim_posterior(x, eps, t, z, eta=eta)
             assert torch.equal(x0.cpu(), r0), (resp, eta)

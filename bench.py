@@ -204,6 +204,10 @@ def cpu_baseline(sd, threads, steps=2):
     return 1.0 / dt, dt
 
 
+WORKLOAD = ("1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); one step = one p_sample "
+            "(UNet 497M params + posterior update)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -231,8 +235,11 @@ def run_reference(args):
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
                       "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "1000-step DDPM p_sample_loop, 27x256x256 tri-plane (configs[1]); one step = one p_sample",
-                                 "batch_per_step": 1},
+                      "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                                 "resolution": "27x256x256",
+                                 "reference_sample": "each timed step = p_sample on ONE sample (1/%d of the batch): "
+                                                     "sample-steps/s is batch-size invariant on the CPU path "
+                                                     "(BASELINE.md section 3)" % args.batch},
                       "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                       "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -298,17 +305,41 @@ def run_ours(args):
     value = world * B * K / (ms_total * 1e-3)
 
     # ---------------- end-to-end through the public API with HOST buffers (`e2e`) ----------------
-    h_out = torch.empty(shape).pin_memory()
+    # Every step uploads its three inputs (x, x_cond, noise) from pinned host memory and downloads the sample.
+    # The uploads of step i+1 are issued on a copy stream while step i computes (double-buffered device
+    # staging), the download of step i overlaps step i+1 -- all inside the timed region.
+    h_out = [torch.empty(shape).pin_memory() for _ in range(2)]
+    copy_st = torch.cuda.Stream(device)
+    stage = [[torch.empty(shape, device=device) for _ in range(3)] for _ in range(2)]
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_st):
+            copy_st.wait_event(free[s])                      # the step that last read this staging slot is done
+            stage[s][0].copy_(h_x, non_blocking=True)
+            stage[s][1].copy_(h_xc, non_blocking=True)
+            stage[s][2].copy_(h_z[i % 2], non_blocking=True)
+            up_done[s].record(copy_st)
+
     barrier()
+    for s_ in range(2):
+        free[s_].record(st)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(st)
+    copy_st.wait_event(e2)                                   # no upload starts before the timed region
+    upload(0)
     for i in range(K):
-        xi = h_x.to(device, non_blocking=True)
-        xci = h_xc.to(device, non_blocking=True)
-        zi = h_z[i % 2].to(device, non_blocking=True)
+        s_ = i % 2
+        if i + 1 < K:
+            upload(i + 1)
+        st.wait_event(up_done[s_])
         t_dev.fill_(T - 1 - (i % T))
-        out = diffusion.p_sample(model, xi, xci, t_dev, clip_denoised=True, model_kwargs={"y": y}, noise=zi)["sample"]
-        h_out.copy_(out, non_blocking=True)
+        out = diffusion.p_sample(model, stage[s_][0], stage[s_][1], t_dev, clip_denoised=True, model_kwargs={"y": y},
+                                 noise=stage[s_][2])["sample"]
+        free[s_].record(st)
+        h_out[s_].copy_(out, non_blocking=True)
     e3.record(st)
     barrier()
     ms2 = torch.tensor([e2.elapsed_time(e3)], device=device)
@@ -335,8 +366,7 @@ def run_ours(args):
                 "dtype": {"fp16": "fp16 operands (11-bit significand, = TF32) x fp32 accumulate, fp32 residual stream / "
                                   "GroupNorm / softmax / posterior", "tf32": "tf32", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": "1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); "
-                                       "one step = one p_sample (UNet 497M params + posterior update)",
+                "config": {"workload": WORKLOAD,
                            "batch_per_gpu": B, "global_batch": B * world, "resolution": "27x256x256",
                            "parallelism": "dp%d (batch sharded, no data-path collective; one all-gather of finished samples)" % world,
                            "l2_policy": "per-step working set (>= 6 GB of activations + 1 GB of fp16 weights) exceeds the 126 MB L2",

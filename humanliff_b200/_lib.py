@@ -40,6 +40,7 @@ SIGNATURES = {
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                c_i64, c_int, c_p]),
+    "hl_render_set_profile": (c_int, [c_p]),
     "hl_density_grid_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
     "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                   c_i64, c_int, c_p]),

@@ -56,6 +56,7 @@ struct RenderArgs {
     float *rgb, *acc, *depth;
     long long n_rays;
     int clamp_depth;
+    unsigned long long *prof;   // optional: cycles of CTA 0 per phase (0 setup, 1 gather, 2 mlp, 3 resample+sort, 4 composite, 5 total)
 };
 
 __device__ __forceinline__ float softplus_fast(float x) {
@@ -87,68 +88,22 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// acc[j][.] += A(16 x 16*KT) . W^T for NT8 output tiles of 8; W rows = outputs, pitch PITCH halves,
-// starting at input column k_off.  a[kk] = A fragment of k-tile kk.
-template <int KT, int NT8, int PITCH>
-__device__ __forceinline__ void gemm_frag(float (&acc)[NT8][4], const uint32_t (*a)[4], uint32_t w_addr, int k_off,
-                                          int lane) {
-    // lane -> (output row within a pair of n-tiles, k half) of the ldmatrix.x4 that yields {b0,b1} of two n-tiles
-    const uint32_t lane_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 8 + k_off) * 2);
-#pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-#pragma unroll
-        for (int jp = 0; jp < NT8 / 2; ++jp) {
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(w_addr + lane_off + (uint32_t)((jp * 16 * PITCH + kk * 16) * 2), b0, b1, b2, b3);
-            mma16816(acc[2 * jp], a[kk], b0, b1);
-            mma16816(acc[2 * jp + 1], a[kk], b2, b3);
-        }
-    }
-}
-
-template <int NT8>
-__device__ __forceinline__ void init_bias(float (&acc)[NT8][4], const float *bias, int t) {
-#pragma unroll
-    for (int j = 0; j < NT8; ++j) {
-        const float b0 = bias[j * 8 + 2 * t], b1 = bias[j * 8 + 2 * t + 1];
-        acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
-    }
-}
-
-// softplus on the accumulator fragment, then pack it as the A fragments of the next layer
-template <int NT8, bool ACT>
-__device__ __forceinline__ void act_pack(float (&acc)[NT8][4], uint32_t (*a)[4]) {
-#pragma unroll
-    for (int j = 0; j < NT8; ++j) {
-        if (ACT) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = softplus_fast(acc[j][e]);
-        }
-        a[j >> 1][(j & 1) * 2 + 0] = pack_h2(acc[j][0], acc[j][1]);
-        a[j >> 1][(j & 1) * 2 + 1] = pack_h2(acc[j][2], acc[j][3]);
-    }
-}
-
-// Nine-plane gather of one 128-point tile into Xs[128][XP] fp16 (renderer.py:504-549; A.5 of SURVEY)
-__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, __half *Xs);
-
-__device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_s, float ox, float oy, float oz,
-                                            float dx, float dy, float dz, __half *Xs) {
-    const float z = z_s[threadIdx.x & 127];
-    // pts = o + d*z (separately rounded, as the reference's broadcasting arithmetic does)
-    gather_point(a, __fadd_rn(ox, __fmul_rn(dx, z)), __fadd_rn(oy, __fmul_rn(dy, z)), __fadd_rn(oz, __fmul_rn(dz, z)), Xs);
-}
-
-// features of one world-space point per thread pair (threads p and p+128 split the nine sub-planes)
-__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, __half *Xs) {
-    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+// Features of one world-space point: sub-planes c = C0, C0 + CSTEP, ... (< 9) are gathered by this thread and
+// written to xrow[c*3 .. c*3+2].  Fully unrolled so that all 4 x NC bilinear taps (16-byte L2 loads) are in
+// flight together (the rolled loop exposed one L2 round trip per sub-plane: 4 k cycles per 128-point tile).
+template <int C0, int CSTEP>
+__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, __half *xrow) {
     const float cx = 2.f * (px - a.bmin[0]) / (a.bmax[0] - a.bmin[0]) - 1.f;
     const float cy = 2.f * (py - a.bmin[1]) / (a.bmax[1] - a.bmin[1]) - 1.f;
     const float cz = 2.f * (pz - a.bmin[2]) / (a.bmax[2] - a.bmin[2]) - 1.f;
     const int R = a.R;
     const float fR = (float)R, shift = 1.0f / fR;
-    __half *xrow = Xs + p * XP;
-    for (int c = half; c < 9; c += 2) {
+    constexpr int NC = (9 - C0 + CSTEP - 1) / CSTEP;
+    float4 tap[NC][4];
+    float wgt[NC][4];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = C0 + i * CSTEP;
         const int plane = c / 3, sub = c - plane * 3;
         float u = (plane == 2) ? cz : cx;
         float v = (plane == 1) ? cz : cy;
@@ -159,106 +114,206 @@ __device__ __forceinline__ void gather_point(const RenderArgs &a, float px, floa
         const float fx0 = floorf(ix), fy0 = floorf(iy);
         const float wx1 = ix - fx0, wy1 = iy - fy0;
         const float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
+        // clamp before the int cast so far-away points (miss rays) cannot overflow
         const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)R + 1.f);
         const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)R + 1.f);
         const float4 *tp = a.tex + (size_t)c * R * R;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
         const bool xin0 = x0 >= 0 && x0 < R, xin1 = x0 + 1 >= 0 && x0 + 1 < R;
         const bool yin0 = y0 >= 0 && y0 < R, yin1 = y0 + 1 >= 0 && y0 + 1 < R;
-        if (yin0 && xin0) { float4 t = __ldg(tp + (size_t)y0 * R + x0);           float w = wx0 * wy0; r0 = fmaf(t.x, w, r0); r1 = fmaf(t.y, w, r1); r2 = fmaf(t.z, w, r2); }
-        if (yin0 && xin1) { float4 t = __ldg(tp + (size_t)y0 * R + x0 + 1);       float w = wx1 * wy0; r0 = fmaf(t.x, w, r0); r1 = fmaf(t.y, w, r1); r2 = fmaf(t.z, w, r2); }
-        if (yin1 && xin0) { float4 t = __ldg(tp + (size_t)(y0 + 1) * R + x0);     float w = wx0 * wy1; r0 = fmaf(t.x, w, r0); r1 = fmaf(t.y, w, r1); r2 = fmaf(t.z, w, r2); }
-        if (yin1 && xin1) { float4 t = __ldg(tp + (size_t)(y0 + 1) * R + x0 + 1); float w = wx1 * wy1; r0 = fmaf(t.x, w, r0); r1 = fmaf(t.y, w, r1); r2 = fmaf(t.z, w, r2); }
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        tap[i][0] = (yin0 && xin0) ? __ldg(tp + (size_t)y0 * R + x0) : zero;
+        tap[i][1] = (yin0 && xin1) ? __ldg(tp + (size_t)y0 * R + x0 + 1) : zero;
+        tap[i][2] = (yin1 && xin0) ? __ldg(tp + (size_t)(y0 + 1) * R + x0) : zero;
+        tap[i][3] = (yin1 && xin1) ? __ldg(tp + (size_t)(y0 + 1) * R + x0 + 1) : zero;
+        wgt[i][0] = wx0 * wy0; wgt[i][1] = wx1 * wy0; wgt[i][2] = wx0 * wy1; wgt[i][3] = wx1 * wy1;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = C0 + i * CSTEP;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {      // same accumulation order as render.cu (taps 00, 01, 10, 11)
+            r0 = fmaf(tap[i][k].x, wgt[i][k], r0);
+            r1 = fmaf(tap[i][k].y, wgt[i][k], r1);
+            r2 = fmaf(tap[i][k].z, wgt[i][k], r2);
+        }
         xrow[c * 3 + 0] = __float2half_rn(r0);
         xrow[c * 3 + 1] = __float2half_rn(r1);
         xrow[c * 3 + 2] = __float2half_rn(r2);
     }
-    if (half == 1) {   // zero padding of features 27..31 (k columns the padded weights multiply by 0 anyway)
+}
+
+// 128-point tile: threads p and p + 128 split the nine sub-planes of point p (even / odd)
+__device__ __forceinline__ void gather_tile128(const RenderArgs &a, float px, float py, float pz, __half *Xs) {
+    __half *xrow = Xs + (threadIdx.x & 127) * XP;
+    if (threadIdx.x < 128) {
+        gather_point<0, 2>(a, px, py, pz, xrow);
+    } else {
+        gather_point<1, 2>(a, px, py, pz, xrow);
 #pragma unroll
-        for (int k = 27; k < 32; ++k) xrow[k] = __float2half_rn(0.f);
+        for (int k = 27; k < 32; ++k) xrow[k] = __float2half_rn(0.f);   // zero padding of features 27..31
+    }
+}
+// 256-point tile: one point per thread
+__device__ __forceinline__ void gather_tile256(const RenderArgs &a, float px, float py, float pz, __half *Xs) {
+    __half *xrow = Xs + threadIdx.x * XP;
+    gather_point<0, 1>(a, px, py, pz, xrow);
+#pragma unroll
+    for (int k = 27; k < 32; ++k) xrow[k] = __float2half_rn(0.f);
+}
+
+// One dense layer for this warp's MT x 16 points, output-tile-pair outer / K inner:
+//   for each pair of 8-wide output tiles: acc = bias; acc += A . W^T over the K tiles of the X part (ax) and
+//   of the hidden part (ah); then `fin(jp, acc)` consumes the 16 x 16 fp32 block (activation + packing into the
+//   next layer's A fragment, or a head's dot product).
+// With N outer only 8 accumulator registers per m-tile are live, so a warp can own two m-tiles (each weight
+// fragment loaded by ldmatrix then feeds 4 MMAs instead of 2 -- the weight traffic from shared memory was the
+// co-limiter), and the MUFU work of pair jp overlaps the ldmatrix / MMA work of pair jp+1 inside one warp.
+template <int MT, int KT_X, int KT_H, int NPAIR, int PITCH, class Fin>
+__device__ __forceinline__ void dense_layer(const uint32_t (*ax)[2][4], const uint32_t (*ah)[8][4], uint32_t w_layer,
+                                            const float *bias, int lane, Fin fin) {
+    const int t = lane & 3;
+    const uint32_t lane_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll
+    for (int jp = 0; jp < NPAIR; ++jp) {
+        float acc[MT][2][4];
+        {
+            const float b00 = bias[jp * 16 + 2 * t], b01 = bias[jp * 16 + 2 * t + 1];
+            const float b10 = bias[jp * 16 + 8 + 2 * t], b11 = bias[jp * 16 + 8 + 2 * t + 1];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                acc[m][0][0] = b00; acc[m][0][1] = b01; acc[m][0][2] = b00; acc[m][0][3] = b01;
+                acc[m][1][0] = b10; acc[m][1][1] = b11; acc[m][1][2] = b10; acc[m][1][3] = b11;
+            }
+        }
+        const uint32_t wrow = w_layer + lane_off + (uint32_t)(jp * 16 * PITCH * 2);
+#pragma unroll
+        for (int kk = 0; kk < KT_X + KT_H; ++kk) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(wrow + (uint32_t)(kk * 32), b0, b1, b2, b3);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const uint32_t(&af)[4] = kk < KT_X ? ax[m][kk < KT_X ? kk : 0] : ah[m][kk >= KT_X ? kk - KT_X : 0];
+                mma16816(acc[m][0], af, b0, b1);
+                mma16816(acc[m][1], af, b2, b3);
+            }
+        }
+        fin(jp, acc);
     }
 }
 
-// The whole decoder MLP for this warp's 16 points.  sig_out[16] / rgb_out[3][...] receive the heads.
-template <bool FINE>
+// The whole decoder MLP for this warp's MT x 16 points (rows row0 .. row0 + 16*MT - 1 of Xs).
+template <bool FINE, int MT>
 __device__ __forceinline__ void mlp_warp(uint32_t w_addr, const float *fb, const float *peb, const __half *Xs,
-                                         float *sig_out, float *rgb_out, int rgb_pitch, int warp, int lane) {
+                                         float *sig_out, float *rgb_out, int rgb_pitch, int row0, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    // A fragments of the gathered features (2 k-tiles of 16)
-    uint32_t ax[2][4];
-    {
+    uint32_t ax[MT][2][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
         const uint32_t xaddr = (uint32_t)__cvta_generic_to_shared(Xs) +
-                               (uint32_t)(((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2);
-        ldsm_x4(xaddr, ax[0][0], ax[0][1], ax[0][2], ax[0][3]);
-        ldsm_x4(xaddr + 32, ax[1][0], ax[1][1], ax[1][2], ax[1][3]);
+                               (uint32_t)(((row0 + m * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2);
+        ldsm_x4(xaddr, ax[m][0][0], ax[m][0][1], ax[m][0][2], ax[m][0][3]);
+        ldsm_x4(xaddr + 32, ax[m][1][0], ax[m][1][1], ax[m][1][2], ax[m][1][3]);
     }
-    float acc[16][4];
-    uint32_t ah[8][4];
-    // pts_linears.0 + softplus
-    init_bias<16>(acc, fb + FB_B0, t);
-    gemm_frag<2, 16, P0>(acc, ax, w_addr + OW0 * 2, 0, lane);
-    act_pack<16, true>(acc, ah);
-    // pts_linears.1 + softplus
-    init_bias<16>(acc, fb + FB_B1, t);
-    gemm_frag<8, 16, P1>(acc, ah, w_addr + OW1 * 2, 0, lane);
-    act_pack<16, true>(acc, ah);
-    // pts_linears.2 on cat([x, h1]) + softplus
-    init_bias<16>(acc, fb + FB_B2, t);
-    gemm_frag<2, 16, P2>(acc, ax, w_addr + OW2 * 2, 0, lane);
-    gemm_frag<8, 16, P2>(acc, ah, w_addr + OW2 * 2, 32, lane);
+    uint32_t h0[MT][8][4], h1[MT][8][4];
+    // softplus + pack the 16 x 16 block as k-tile jp of the next layer's A operand
+    auto act_into = [&](uint32_t (*dst)[8][4]) {
+        return [dst](int jp, float (&acc)[MT][2][4]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
+            for (int m = 0; m < MT; ++m) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[j][e] = softplus_fast(acc[j][e]);
-    // alpha_linear from the fp32 fragment: rows g and g+8
-    {
-        float s0 = 0.f, s1 = 0.f;
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float w0 = fb[FB_WA + j * 8 + 2 * t], w1 = fb[FB_WA + j * 8 + 2 * t + 1];
-            s0 = fmaf(acc[j][0], w0, fmaf(acc[j][1], w1, s0));
-            s1 = fmaf(acc[j][2], w0, fmaf(acc[j][3], w1, s1));
+                    for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
+                dst[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
+                dst[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
+                dst[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
+                dst[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
+            }
+        };
+    };
+    // pts_linears.0, pts_linears.1
+    dense_layer<MT, 2, 0, 8, P0>(ax, h0, w_addr + OW0 * 2, fb + FB_B0, lane, act_into(h0));
+    dense_layer<MT, 0, 8, 8, P1>(ax, h0, w_addr + OW1 * 2, fb + FB_B1, lane, act_into(h1));
+    // pts_linears.2 on cat([x, h1]) + softplus; alpha head from the fp32 block; h2 packed for the fine branch
+    float s0[MT], s1[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { s0[m] = 0.f; s1[m] = 0.f; }
+    dense_layer<MT, 2, 8, 8, P2>(ax, h1, w_addr + OW2 * 2, fb + FB_B2, lane, [&](int jp, float (&acc)[MT][2][4]) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
+                const float w0 = fb[FB_WA + jp * 16 + h * 8 + 2 * t], w1 = fb[FB_WA + jp * 16 + h * 8 + 2 * t + 1];
+                s0[m] = fmaf(acc[m][h][0], w0, fmaf(acc[m][h][1], w1, s0[m]));
+                s1[m] = fmaf(acc[m][h][2], w0, fmaf(acc[m][h][3], w1, s1[m]));
+            }
+            if (FINE) {
+                h0[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
+                h0[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
+                h0[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
+                h0[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
+            }
         }
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    });
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        float a0 = s0[m], a1 = s1[m];
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
         if (t == 0) {
-            sig_out[warp * 16 + g] = s0 + fb[FB_BA];
-            sig_out[warp * 16 + g + 8] = s1 + fb[FB_BA];
+            sig_out[row0 + m * 16 + g] = a0 + fb[FB_BA];
+            sig_out[row0 + m * 16 + g + 8] = a1 + fb[FB_BA];
         }
     }
     if (FINE) {
-        act_pack<16, false>(acc, ah);                       // h2 as the next A operand
-        // feature_linear (no activation)
-        init_bias<16>(acc, fb + FB_BF, t);
-        gemm_frag<8, 16, PF>(acc, ah, w_addr + OWF * 2, 0, lane);
-        act_pack<16, false>(acc, ah);
-        // views_linear on cat([feature, pe(d)]) + softplus: the pe part is the per-ray bias `peb`
-        float av[8][4];
-        init_bias<8>(av, peb, t);
-        gemm_frag<8, 8, PV>(av, ah, w_addr + OWV * 2, 0, lane);
-        float r0[3] = {0.f, 0.f, 0.f}, r1[3] = {0.f, 0.f, 0.f};
+        // feature_linear (no activation) -> h1
+        dense_layer<MT, 0, 8, 8, PF>(ax, h0, w_addr + OWF * 2, fb + FB_BF, lane, [&](int jp, float (&acc)[MT][2][4]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+            for (int m = 0; m < MT; ++m) {
+                h1[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
+                h1[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
+                h1[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
+                h1[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
+            }
+        });
+        // views_linear on cat([feature, pe(d)]) + softplus (pe part = per-ray bias peb); rgb head on the fp32 block
+        float r0[MT][3], r1[MT][3];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) av[j][e] = softplus_fast(av[j][e]);
-            const int k0 = j * 8 + 2 * t;
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { r0[m][c] = 0.f; r1[m][c] = 0.f; }
+        dense_layer<MT, 0, 8, 4, PV>(ax, h1, w_addr + OWV * 2, peb, lane, [&](int jp, float (&acc)[MT][2][4]) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
+                    const int k0 = jp * 16 + h * 8 + 2 * t;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float w0 = fb[FB_WR + k0 * 4 + c], w1 = fb[FB_WR + (k0 + 1) * 4 + c];
+                        r0[m][c] = fmaf(acc[m][h][0], w0, fmaf(acc[m][h][1], w1, r0[m][c]));
+                        r1[m][c] = fmaf(acc[m][h][2], w0, fmaf(acc[m][h][3], w1, r1[m][c]));
+                    }
+                }
+        });
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float w0 = fb[FB_WR + k0 * 4 + c], w1 = fb[FB_WR + (k0 + 1) * 4 + c];
-                r0[c] = fmaf(av[j][0], w0, fmaf(av[j][1], w1, r0[c]));
-                r1[c] = fmaf(av[j][2], w0, fmaf(av[j][3], w1, r1[c]));
+                float v0 = r0[m][c], v1 = r1[m][c];
+                v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                if (t == 0) {
+                    const float b = fb[FB_BR + c];
+                    rgb_out[c * rgb_pitch + row0 + m * 16 + g] = 1.0f / (1.0f + expf(-(v0 + b)));
+                    rgb_out[c * rgb_pitch + row0 + m * 16 + g + 8] = 1.0f / (1.0f + expf(-(v1 + b)));
+                }
             }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            r0[c] += __shfl_xor_sync(0xffffffffu, r0[c], 1); r0[c] += __shfl_xor_sync(0xffffffffu, r0[c], 2);
-            r1[c] += __shfl_xor_sync(0xffffffffu, r1[c], 1); r1[c] += __shfl_xor_sync(0xffffffffu, r1[c], 2);
-            if (t == 0) {
-                const float b = fb[FB_BR + c];
-                rgb_out[c * rgb_pitch + warp * 16 + g] = 1.0f / (1.0f + expf(-(r0[c] + b)));
-                rgb_out[c * rgb_pitch + warp * 16 + g + 8] = 1.0f / (1.0f + expf(-(r1[c] + b)));
-            }
-        }
     }
 }
 
@@ -300,7 +355,7 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
     __half *Wsm = reinterpret_cast<__half *>(smraw);                 // fp16 weight image
     float *fb = reinterpret_cast<float *>(Wsm + W_HALVES);           // fp32 pack (biases, heads)
     __half *Xs = reinterpret_cast<__half *>(fb + FB_FLOATS);
-    float *zc = reinterpret_cast<float *>(Xs + 128 * XP);   // [128] coarse z
+    float *zc = reinterpret_cast<float *>(Xs + 256 * XP);   // [128] coarse z
     float *zn = zc + NS;                  // [128] new z
     float *zf = zn + NS;                  // [256] merged z
     float *sig = zf + 2 * NS;             // [256] raw density
@@ -336,6 +391,15 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
     }
     __syncthreads();
     const uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(Wsm);
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tp = prof ? clock64() : 0;
+    const long long tp0 = tp;
+#define RPROF(slot)                                                        \
+    if (prof) {                                                            \
+        const long long now_ = clock64();                                  \
+        atomicAdd(a.prof + (slot), (unsigned long long)(now_ - tp));       \
+        tp = now_;                                                         \
+    }
 
     for (long long ray = blockIdx.x; ray < a.n_rays; ray += gridDim.x) {
         const float ox = a.o[ray * 3 + 0], oy = a.o[ray * 3 + 1], oz = a.o[ray * 3 + 2];
@@ -372,10 +436,17 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
         }
 
         // ------------------------------- coarse pass (density only) -------------------------------
-        gather_tile(a, zc, ox, oy, oz, dx, dy, dz, Xs);
+        RPROF(0)
+        {
+            const float z = zc[tid & 127];   // pts = o + d*z (separately rounded, as the reference's broadcasting does)
+            gather_tile128(a, __fadd_rn(ox, __fmul_rn(dx, z)), __fadd_rn(oy, __fmul_rn(dy, z)),
+                           __fadd_rn(oz, __fmul_rn(dz, z)), Xs);
+        }
         __syncthreads();
-        mlp_warp<false>(w_addr, fb, peb, Xs, sig, nullptr, 0, warp, lane);
+        RPROF(1)
+        mlp_warp<false, 1>(w_addr, fb, peb, Xs, sig, nullptr, 0, warp * 16, lane);
         __syncthreads();
+        RPROF(2)
 
         // ------------------------------- up_sample + sample_pdf -----------------------------------
         float al = 0.f;
@@ -395,10 +466,18 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
             if (tid >= 1 && tid <= NS - 2) part[tid] = wv / tot;                     // pdf, 126 entries
         }
         __syncthreads();
-        if (tid == 0) {   // cdf = [0, cumsum(pdf)]: sequential like torch.cumsum (bit-compatible summation order)
-            float c = 0.f;
-            cdf[0] = 0.f;
-            for (int i = 1; i <= NS - 2; ++i) { c += part[i]; cdf[i] = c; }
+        {   // cdf = [0, cumsum(pdf)] (127 entries): warp-shuffle inclusive scan + per-warp offsets
+            float v = (tid >= 1 && tid <= NS - 2) ? part[tid] : 0.f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += up;
+            }
+            if (lane == 31) red[warp] = v;
+            __syncthreads();
+            float pre = 0.f;
+            for (int i = 0; i < warp; ++i) pre += red[i];
+            if (tid <= NS - 2) cdf[tid] = pre + v;          // cdf[0] = 0, cdf[i] = pdf[1] + ... + pdf[i]
         }
         __syncthreads();
         if (tid < NS) {
@@ -440,13 +519,18 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
         }
         __syncthreads();
 
-        // ------------------------------- fine pass: 2 tiles of 128 --------------------------------
-        for (int t = 0; t < 2; ++t) {
-            gather_tile(a, zf + t * NS, ox, oy, oz, dx, dy, dz, Xs);
-            __syncthreads();
-            mlp_warp<true>(w_addr, fb, peb, Xs, sig + t * NS, rgbs + t * NS, 2 * NS, warp, lane);
-            __syncthreads();
+        RPROF(3)
+        // ------------------------------- fine pass: all 256 sorted samples at once ----------------
+        {
+            const float z = zf[tid];
+            gather_tile256(a, __fadd_rn(ox, __fmul_rn(dx, z)), __fadd_rn(oy, __fmul_rn(dy, z)),
+                           __fadd_rn(oz, __fmul_rn(dz, z)), Xs);
         }
+        __syncthreads();
+        RPROF(1)
+        mlp_warp<true, 2>(w_addr, fb, peb, Xs, sig, rgbs, 2 * NS, warp * 32, lane);
+        __syncthreads();
+        RPROF(2)
 
         // ------------------------------- composite (renderer.py:222-239) --------------------------
         {
@@ -454,11 +538,23 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
             const float al2 = 1.0f - expf(-softplus_acc(sig[tid]) * dist);
             const float T = excl_cumprod((1.0f - al2) + 1e-7f, red, 2 * NS);
             const float w = al2 * T;
-            const float s_acc = block_sum(w, red);
-            const float s_r = block_sum(w * rgbs[0 * 2 * NS + tid], red);
-            const float s_g = block_sum(w * rgbs[1 * 2 * NS + tid], red);
-            const float s_b = block_sum(w * rgbs[2 * 2 * NS + tid], red);
-            const float s_d = block_sum(w * zf[tid], red);
+            // five sums in one pass: warp shuffles, then 8 per-warp partials per quantity in shared memory
+            float q5[5] = {w, w * rgbs[0 * 2 * NS + tid], w * rgbs[1 * 2 * NS + tid], w * rgbs[2 * 2 * NS + tid], w * zf[tid]};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) q5[k] = hl_warp_sum(q5[k]);
+            __syncthreads();                      // `part` (pdf scratch) is free; red is in use by excl_cumprod
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) part[k * 8 + warp] = q5[k];
+            }
+            __syncthreads();
+            float s_acc = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, s_d = 0.f;
+            if (tid == 0) {
+                for (int i = 0; i < 8; ++i) {
+                    s_acc += part[0 * 8 + i]; s_r += part[1 * 8 + i]; s_g += part[2 * 8 + i];
+                    s_b += part[3 * 8 + i]; s_d += part[4 * 8 + i];
+                }
+            }
             if (tid == 0) {
                 a.rgb[ray * 3 + 0] = s_r;
                 a.rgb[ray * 3 + 1] = s_g;
@@ -469,7 +565,10 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
                 a.depth[ray] = dep;
             }
         }
+        RPROF(4)
     }
+    if (prof) atomicAdd(a.prof + 5, (unsigned long long)(clock64() - tp0));
+#undef RPROF
 }
 
 // Density on a regular grid (Renderer.extract_geometry, human_diffusion/NeRF/renderer.py:290-318): the
@@ -508,9 +607,9 @@ __global__ void __launch_bounds__(NT, 1) k_density_grid_tc(const RenderArgs a, i
         if (idx >= total) idx = total - 1;
         const int zi = (int)(idx % res), yi = (int)((idx / res) % res), xi = (int)(idx / ((long long)res * res));
         __syncthreads();     // previous tile consumed (Xs, sig)
-        gather_point(a, lin(a.bmin[0], a.bmax[0], xi), lin(a.bmin[1], a.bmax[1], yi), lin(a.bmin[2], a.bmax[2], zi), Xs);
+        gather_tile128(a, lin(a.bmin[0], a.bmax[0], xi), lin(a.bmin[1], a.bmax[1], yi), lin(a.bmin[2], a.bmax[2], zi), Xs);
         __syncthreads();
-        mlp_warp<false>(w_addr, fb, nullptr, Xs, sig, nullptr, 0, warp, lane);
+        mlp_warp<false, 1>(w_addr, fb, nullptr, Xs, sig, nullptr, 0, warp * 16, lane);
         __syncthreads();
         if (tid < 128 && tile * 128 + tid < total) out[tile * 128 + tid] = -sig[tid];
     }
@@ -542,6 +641,12 @@ extern "C" int hl_density_grid_tc(const float *texels, int R, const float *mlp_p
     return HL_OK;
 }
 
+static unsigned long long *g_render_prof = nullptr;
+extern "C" int hl_render_set_profile(void *dev_counters) {
+    g_render_prof = (unsigned long long *)dev_counters;
+    return HL_OK;
+}
+
 extern "C" int hl_render_rays_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
                                  const float *rays_o, const float *rays_d, const float *near, const float *far,
                                  const float *z_coarse, const float *u, uint64_t seed, const float *bounds,
@@ -561,7 +666,8 @@ extern "C" int hl_render_rays_tc(const float *texels, int R, const float *mlp_pa
     a.rgb = rgb; a.acc = acc; a.depth = depth;
     a.n_rays = n_rays;
     a.clamp_depth = clamp_depth;
-    const size_t smem = (size_t)W_HALVES * 2 + sizeof(float) * FB_FLOATS + (size_t)128 * XP * 2 +
+    a.prof = g_render_prof;
+    const size_t smem = (size_t)W_HALVES * 2 + sizeof(float) * FB_FLOATS + (size_t)256 * XP * 2 +
                         sizeof(float) * (size_t)(NS * 2 + 2 * NS * 3 + NS * 2 + 3 * 2 * NS + 64 + NS + 8 + 28 + 4);
     static bool configured = false;
     if (!configured) {

@@ -228,6 +228,9 @@ int hl_render_rays_tc(const float *texels, int R, const float *mlp_packed, const
  * human_diffusion/NeRF/renderer.py:290-318): out[xi][yi][zi] = -sigma(p), p = (linspace(min_x, max_x, res)[xi],
  * ...), the coarse stage of the renderer (nine-plane gather + density MLP on the tensor cores) over res^3
  * points.  Marching cubes stays on the host (mcubes in the reference).                              */
+/* Experiment hook: device array of >= 8 uint64; CTA 0 of following hl_render_rays_tc launches adds the cycles it
+ * spends per phase (0 per-ray setup, 1 gather, 2 MLP, 3 resample + sort, 4 composite, 5 total); NULL = off. */
+int hl_render_set_profile(void *dev_counters);
 int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
                        const float *bounds /*host*/, int resolution, float *out, void *stream);
 

@@ -87,6 +87,14 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// F.softplus(beta=1, threshold=20) in fp32 (ex2 + lg2 on the MUFU pipe), packed to fp16 afterwards.
+// Tried and rejected (measured / emulated): a half2 Horner polynomial for log1p (4e-3 absolute error -- a
+// systematic distortion of the activation, not rounding noise) and an fp32 polynomial (one MUFU op less but
+// +8 FMA-pipe instructions per activation: the MLP is as much issue-bound as MUFU-bound, it got slower).
+__device__ __forceinline__ uint32_t softplus_h2(float a, float b) { return pack_h2(softplus_fast(a), softplus_fast(b)); }
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
 
 // Features of one world-space point: sub-planes c = C0, C0 + CSTEP, ... (< 9) are gathered by this thread and
 // written to xrow[c*3 .. c*3+2].  Fully unrolled so that all 4 x NC bilinear taps (16-byte L2 loads) are in
@@ -162,158 +170,123 @@ __device__ __forceinline__ void gather_tile256(const RenderArgs &a, float px, fl
     for (int k = 27; k < 32; ++k) xrow[k] = __float2half_rn(0.f);
 }
 
-// One dense layer for this warp's MT x 16 points, output-tile-pair outer / K inner:
-//   for each pair of 8-wide output tiles: acc = bias; acc += A . W^T over the K tiles of the X part (ax) and
-//   of the hidden part (ah); then `fin(jp, acc)` consumes the 16 x 16 fp32 block (activation + packing into the
-//   next layer's A fragment, or a head's dot product).
-// With N outer only 8 accumulator registers per m-tile are live, so a warp can own two m-tiles (each weight
-// fragment loaded by ldmatrix then feeds 4 MMAs instead of 2 -- the weight traffic from shared memory was the
-// co-limiter), and the MUFU work of pair jp overlaps the ldmatrix / MMA work of pair jp+1 inside one warp.
-template <int MT, int KT_X, int KT_H, int NPAIR, int PITCH, class Fin>
-__device__ __forceinline__ void dense_layer(const uint32_t (*ax)[2][4], const uint32_t (*ah)[8][4], uint32_t w_layer,
-                                            const float *bias, int lane, Fin fin) {
-    const int t = lane & 3;
-    const uint32_t lane_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 8) * 2);
+// acc[j][.] += A(16 x 16*KT) . W^T for NT8 output tiles of 8; W rows = outputs, pitch PITCH halves,
+// starting at input column k_off.  a[kk] = A fragment of k-tile kk.
+template <int KT, int NT8, int PITCH>
+__device__ __forceinline__ void gemm_frag(float (&acc)[NT8][4], const uint32_t (*a)[4], uint32_t w_addr, int k_off,
+                                          int lane) {
+    // lane -> (output row within a pair of n-tiles, k half) of the ldmatrix.x4 that yields {b0,b1} of two n-tiles
+    const uint32_t lane_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 8 + k_off) * 2);
 #pragma unroll
-    for (int jp = 0; jp < NPAIR; ++jp) {
-        float acc[MT][2][4];
-        {
-            const float b00 = bias[jp * 16 + 2 * t], b01 = bias[jp * 16 + 2 * t + 1];
-            const float b10 = bias[jp * 16 + 8 + 2 * t], b11 = bias[jp * 16 + 8 + 2 * t + 1];
+    for (int kk = 0; kk < KT; ++kk) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                acc[m][0][0] = b00; acc[m][0][1] = b01; acc[m][0][2] = b00; acc[m][0][3] = b01;
-                acc[m][1][0] = b10; acc[m][1][1] = b11; acc[m][1][2] = b10; acc[m][1][3] = b11;
-            }
-        }
-        const uint32_t wrow = w_layer + lane_off + (uint32_t)(jp * 16 * PITCH * 2);
-#pragma unroll
-        for (int kk = 0; kk < KT_X + KT_H; ++kk) {
+        for (int jp = 0; jp < NT8 / 2; ++jp) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4(wrow + (uint32_t)(kk * 32), b0, b1, b2, b3);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                const uint32_t(&af)[4] = kk < KT_X ? ax[m][kk < KT_X ? kk : 0] : ah[m][kk >= KT_X ? kk - KT_X : 0];
-                mma16816(acc[m][0], af, b0, b1);
-                mma16816(acc[m][1], af, b2, b3);
-            }
+            ldsm_x4(w_addr + lane_off + (uint32_t)((jp * 16 * PITCH + kk * 16) * 2), b0, b1, b2, b3);
+            mma16816(acc[2 * jp], a[kk], b0, b1);
+            mma16816(acc[2 * jp + 1], a[kk], b2, b3);
         }
-        fin(jp, acc);
     }
 }
 
-// The whole decoder MLP for this warp's MT x 16 points (rows row0 .. row0 + 16*MT - 1 of Xs).
-template <bool FINE, int MT>
-__device__ __forceinline__ void mlp_warp(uint32_t w_addr, const float *fb, const float *peb, const __half *Xs,
-                                         float *sig_out, float *rgb_out, int rgb_pitch, int row0, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    uint32_t ax[MT][2][4];
+template <int NT8>
+__device__ __forceinline__ void init_bias(float (&acc)[NT8][4], const float *bias, int t) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        const uint32_t xaddr = (uint32_t)__cvta_generic_to_shared(Xs) +
-                               (uint32_t)(((row0 + m * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2);
-        ldsm_x4(xaddr, ax[m][0][0], ax[m][0][1], ax[m][0][2], ax[m][0][3]);
-        ldsm_x4(xaddr + 32, ax[m][1][0], ax[m][1][1], ax[m][1][2], ax[m][1][3]);
+    for (int j = 0; j < NT8; ++j) {
+        const float b0 = bias[j * 8 + 2 * t], b1 = bias[j * 8 + 2 * t + 1];
+        acc[j][0] = b0; acc[j][1] = b1; acc[j][2] = b0; acc[j][3] = b1;
     }
-    uint32_t h0[MT][8][4], h1[MT][8][4];
-    // softplus + pack the 16 x 16 block as k-tile jp of the next layer's A operand
-    auto act_into = [&](uint32_t (*dst)[8][4]) {
-        return [dst](int jp, float (&acc)[MT][2][4]) {
+}
+
+// softplus on the accumulator fragment, then pack it as the A fragments of the next layer
+template <int NT8, bool ACT>
+__device__ __forceinline__ void act_pack(float (&acc)[NT8][4], uint32_t (*a)[4]) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
+    for (int j = 0; j < NT8; ++j) {
+        a[j >> 1][(j & 1) * 2 + 0] = ACT ? softplus_h2(acc[j][0], acc[j][1]) : pack_h2(acc[j][0], acc[j][1]);
+        a[j >> 1][(j & 1) * 2 + 1] = ACT ? softplus_h2(acc[j][2], acc[j][3]) : pack_h2(acc[j][2], acc[j][3]);
+    }
+}
+
+// The whole decoder MLP for this warp's 16 points.  sig_out[16] / rgb_out[3][...] receive the heads.
+// ONE out-of-line copy shared by the coarse pass, both fine tiles and the density-grid kernel: fully unrolled it
+// is ~9 k instructions, and three inlined copies thrashed the instruction cache (measured: MLP phase 50 k ->
+// 63 k cycles per ray when the fine pass inlined a second copy).
+__device__ __noinline__ void mlp_warp(const bool FINE, uint32_t w_addr, const float *fb, const float *peb,
+                                      const __half *Xs, float *sig_out, float *rgb_out, int rgb_pitch, int row0,
+                                      int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    // A fragments of the gathered features (2 k-tiles of 16)
+    uint32_t ax[2][4];
+    {
+        const uint32_t xaddr = (uint32_t)__cvta_generic_to_shared(Xs) +
+                               (uint32_t)(((row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2);
+        ldsm_x4(xaddr, ax[0][0], ax[0][1], ax[0][2], ax[0][3]);
+        ldsm_x4(xaddr + 32, ax[1][0], ax[1][1], ax[1][2], ax[1][3]);
+    }
+    float acc[16][4];
+    uint32_t ah[8][4];
+    // pts_linears.0 + softplus
+    init_bias<16>(acc, fb + FB_B0, t);
+    gemm_frag<2, 16, P0>(acc, ax, w_addr + OW0 * 2, 0, lane);
+    act_pack<16, true>(acc, ah);
+    // pts_linears.1 + softplus
+    init_bias<16>(acc, fb + FB_B1, t);
+    gemm_frag<8, 16, P1>(acc, ah, w_addr + OW1 * 2, 0, lane);
+    act_pack<16, true>(acc, ah);
+    // pts_linears.2 on cat([x, h1]) + softplus
+    init_bias<16>(acc, fb + FB_B2, t);
+    gemm_frag<2, 16, P2>(acc, ax, w_addr + OW2 * 2, 0, lane);
+    gemm_frag<8, 16, P2>(acc, ah, w_addr + OW2 * 2, 32, lane);
+    act_pack<16, true>(acc, ah);                            // h2 (fp16) = operand of feature_linear
+    // alpha_linear (fp32 dot products on the fragment): rows g and g+8
+    {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
-                dst[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
-                dst[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
-                dst[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
-                dst[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
-            }
-        };
-    };
-    // pts_linears.0, pts_linears.1
-    dense_layer<MT, 2, 0, 8, P0>(ax, h0, w_addr + OW0 * 2, fb + FB_B0, lane, act_into(h0));
-    dense_layer<MT, 0, 8, 8, P1>(ax, h0, w_addr + OW1 * 2, fb + FB_B1, lane, act_into(h1));
-    // pts_linears.2 on cat([x, h1]) + softplus; alpha head from the fp32 block; h2 packed for the fine branch
-    float s0[MT], s1[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) { s0[m] = 0.f; s1[m] = 0.f; }
-    dense_layer<MT, 2, 8, 8, P2>(ax, h1, w_addr + OW2 * 2, fb + FB_B2, lane, [&](int jp, float (&acc)[MT][2][4]) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
-                const float w0 = fb[FB_WA + jp * 16 + h * 8 + 2 * t], w1 = fb[FB_WA + jp * 16 + h * 8 + 2 * t + 1];
-                s0[m] = fmaf(acc[m][h][0], w0, fmaf(acc[m][h][1], w1, s0[m]));
-                s1[m] = fmaf(acc[m][h][2], w0, fmaf(acc[m][h][3], w1, s1[m]));
-            }
-            if (FINE) {
-                h0[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
-                h0[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
-                h0[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
-                h0[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
-            }
+        for (int j = 0; j < 16; ++j) {
+            const float w0 = fb[FB_WA + j * 8 + 2 * t], w1 = fb[FB_WA + j * 8 + 2 * t + 1];
+            const float2 v0 = unpack_h2(ah[j >> 1][(j & 1) * 2 + 0]), v1 = unpack_h2(ah[j >> 1][(j & 1) * 2 + 1]);
+            s0 = fmaf(v0.x, w0, fmaf(v0.y, w1, s0));
+            s1 = fmaf(v1.x, w0, fmaf(v1.y, w1, s1));
         }
-    });
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        float a0 = s0[m], a1 = s1[m];
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
         if (t == 0) {
-            sig_out[row0 + m * 16 + g] = a0 + fb[FB_BA];
-            sig_out[row0 + m * 16 + g + 8] = a1 + fb[FB_BA];
+            sig_out[row0 + g] = s0 + fb[FB_BA];
+            sig_out[row0 + g + 8] = s1 + fb[FB_BA];
         }
     }
     if (FINE) {
-        // feature_linear (no activation) -> h1
-        dense_layer<MT, 0, 8, 8, PF>(ax, h0, w_addr + OWF * 2, fb + FB_BF, lane, [&](int jp, float (&acc)[MT][2][4]) {
+        // feature_linear (no activation)
+        init_bias<16>(acc, fb + FB_BF, t);
+        gemm_frag<8, 16, PF>(acc, ah, w_addr + OWF * 2, 0, lane);
+        act_pack<16, false>(acc, ah);
+        // views_linear on cat([feature, pe(d)]) + softplus: the pe part is the per-ray bias `peb`
+        float av[8][4];
+        init_bias<8>(av, peb, t);
+        gemm_frag<8, 8, PV>(av, ah, w_addr + OWV * 2, 0, lane);
+        float r0[3] = {0.f, 0.f, 0.f}, r1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                h1[m][jp][0] = pack_h2(acc[m][0][0], acc[m][0][1]);
-                h1[m][jp][1] = pack_h2(acc[m][0][2], acc[m][0][3]);
-                h1[m][jp][2] = pack_h2(acc[m][1][0], acc[m][1][1]);
-                h1[m][jp][3] = pack_h2(acc[m][1][2], acc[m][1][3]);
-            }
-        });
-        // views_linear on cat([feature, pe(d)]) + softplus (pe part = per-ray bias peb); rgb head on the fp32 block
-        float r0[MT][3], r1[MT][3];
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { r0[m][c] = 0.f; r1[m][c] = 0.f; }
-        dense_layer<MT, 0, 8, 4, PV>(ax, h1, w_addr + OWV * 2, peb, lane, [&](int jp, float (&acc)[MT][2][4]) {
-#pragma unroll
-            for (int m = 0; m < MT; ++m)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[m][h][e] = softplus_fast(acc[m][h][e]);
-                    const int k0 = jp * 16 + h * 8 + 2 * t;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float w0 = fb[FB_WR + k0 * 4 + c], w1 = fb[FB_WR + (k0 + 1) * 4 + c];
-                        r0[m][c] = fmaf(acc[m][h][0], w0, fmaf(acc[m][h][1], w1, r0[m][c]));
-                        r1[m][c] = fmaf(acc[m][h][2], w0, fmaf(acc[m][h][3], w1, r1[m][c]));
-                    }
-                }
-        });
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
+        for (int j = 0; j < 8; ++j) {
+            const float2 v0 = unpack_h2(softplus_h2(av[j][0], av[j][1])), v1 = unpack_h2(softplus_h2(av[j][2], av[j][3]));
+            const int k0 = j * 8 + 2 * t;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float v0 = r0[m][c], v1 = r1[m][c];
-                v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-                if (t == 0) {
-                    const float b = fb[FB_BR + c];
-                    rgb_out[c * rgb_pitch + row0 + m * 16 + g] = 1.0f / (1.0f + expf(-(v0 + b)));
-                    rgb_out[c * rgb_pitch + row0 + m * 16 + g + 8] = 1.0f / (1.0f + expf(-(v1 + b)));
-                }
+                const float w0 = fb[FB_WR + k0 * 4 + c], w1 = fb[FB_WR + (k0 + 1) * 4 + c];
+                r0[c] = fmaf(v0.x, w0, fmaf(v0.y, w1, r0[c]));
+                r1[c] = fmaf(v1.x, w0, fmaf(v1.y, w1, r1[c]));
             }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            r0[c] += __shfl_xor_sync(0xffffffffu, r0[c], 1); r0[c] += __shfl_xor_sync(0xffffffffu, r0[c], 2);
+            r1[c] += __shfl_xor_sync(0xffffffffu, r1[c], 1); r1[c] += __shfl_xor_sync(0xffffffffu, r1[c], 2);
+            if (t == 0) {
+                const float b = fb[FB_BR + c];
+                rgb_out[c * rgb_pitch + row0 + g] = 1.0f / (1.0f + expf(-(r0[c] + b)));
+                rgb_out[c * rgb_pitch + row0 + g + 8] = 1.0f / (1.0f + expf(-(r1[c] + b)));
+            }
+        }
     }
 }
 
@@ -444,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
         }
         __syncthreads();
         RPROF(1)
-        mlp_warp<false, 1>(w_addr, fb, peb, Xs, sig, nullptr, 0, warp * 16, lane);
+        mlp_warp(false, w_addr, fb, peb, Xs, sig, nullptr, 0, warp * 16, lane);
         __syncthreads();
         RPROF(2)
 
@@ -528,7 +501,8 @@ __global__ void __launch_bounds__(NT, 1) k_render_tc(const RenderArgs a) {
         }
         __syncthreads();
         RPROF(1)
-        mlp_warp<true, 2>(w_addr, fb, peb, Xs, sig, rgbs, 2 * NS, warp * 32, lane);
+        mlp_warp(true, w_addr, fb, peb, Xs, sig, rgbs, 2 * NS, warp * 16, lane);
+        mlp_warp(true, w_addr, fb, peb, Xs, sig, rgbs, 2 * NS, NS + warp * 16, lane);
         __syncthreads();
         RPROF(2)
 
@@ -609,7 +583,7 @@ __global__ void __launch_bounds__(NT, 1) k_density_grid_tc(const RenderArgs a, i
         __syncthreads();     // previous tile consumed (Xs, sig)
         gather_tile128(a, lin(a.bmin[0], a.bmax[0], xi), lin(a.bmin[1], a.bmax[1], yi), lin(a.bmin[2], a.bmax[2], zi), Xs);
         __syncthreads();
-        mlp_warp<false, 1>(w_addr, fb, nullptr, Xs, sig, nullptr, 0, warp * 16, lane);
+        mlp_warp(false, w_addr, fb, nullptr, Xs, sig, nullptr, 0, warp * 16, lane);
         __syncthreads();
         if (tid < 128 && tile * 128 + tid < total) out[tile * 128 + tid] = -sig[tid];
     }

@@ -58,7 +58,7 @@ constexpr int EPI_THREADS = 128;                      // threads per epilogue gr
 constexpr int NUM_THREADS = (3 + 4 * EPI_GROUPS) * 32;
 constexpr int STATS_MAX_C = 768;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 14 * 1024;  // static smem: barriers + fp64 statistics accumulators (12 KB)
+constexpr int DYN_SMEM_MAX = SMEM_LIMIT - 15 * 1024;  // static smem: barriers, fp64 statistics accumulators (12 KB), partials (2 KB)
 
 struct TcParams {
     int B, H, W;             // OUTPUT spatial size
@@ -319,6 +319,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // per-CTA channel sums in fp64: floating-point atomics commute only up to rounding, and fp64 rounding
     // (1e-16) is far below the fp32 resolution of everything downstream -> results are reproducible run to run
     __shared__ double sacc[2][STATS_MAX_C];
+    __shared__ float2 spart[EPI_GROUPS][4][32];     // per chunk: (sum, sum of squares) of each 32-row quarter
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -613,7 +614,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t smem_g = smem_e + (uint32_t)(eg * p.nbuf) * STAGE_BUF_BYTES;
         const uint32_t bar_r = bar_r_full + 8u * (uint32_t)(eg * MAX_NBUF);
-        const uint32_t nbuf_mask = (uint32_t)p.nbuf - 1u, nbuf_shift = p.nbuf == 4 ? 2u : 1u;
+        const uint32_t nbuf = (uint32_t)p.nbuf;   // staging ring of this group: 2, 3 or 4 buffers
+        uint32_t rb = 0, rph = 0;                 // ring slot / phase of the chunk being processed
         uint32_t qn = 0;                          // global chunk counter of this CTA
         uint32_t ql = 0;                          // chunks owned by this group so far (staging ring position)
         int cur_n = -1;                           // sample whose statistics sit in sacc
@@ -621,7 +623,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // residual prefetch cursor (thread e0 of the group): walks the same (tile, half, chunk) sequence
         // and issues loads for the chunks this group owns
         int l_tile = cid, l_half = 0, l_cc = 0;
-        uint32_t l_qn = 0, l_ql = 0;
+        uint32_t l_qn = 0, l_b = 0;               // cursor: global chunk index, ring slot of the next load
         auto issue_res_load = [&]() {
             for (;;) {
                 if (l_tile >= p.total_tiles) return;
@@ -630,10 +632,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (mine) {
                     int w0, h0, n0;
                     box_origin(p, l_tile / p.n_tiles, l_half, rank, w0, h0, n0);
-                    const uint32_t b = l_ql & nbuf_mask;
-                    mbar_expect_tx(bar_r + 8 * b, STAGE_BUF_BYTES);
-                    tma_load_4d(smem_g + b * STAGE_BUF_BYTES, &tmR, bar_r + 8 * b, nt0 + l_cc * 32, w0, h0, n0);
-                    ++l_ql;
+                    mbar_expect_tx(bar_r + 8 * l_b, STAGE_BUF_BYTES);
+                    tma_load_4d(smem_g + l_b * STAGE_BUF_BYTES, &tmR, bar_r + 8 * l_b, nt0 + l_cc * 32, w0, h0, n0);
+                    if (++l_b == nbuf) l_b = 0;
                 }
                 ++l_qn;
                 ++l_cc;
@@ -680,14 +681,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int nbase = nt0 + cc * 32;
                     if (nbase >= p.Cout) break;
                     if ((int)(qn & (EPI_GROUPS - 1)) != eg) continue;       // the other group's chunk
-                    const uint32_t b = ql & nbuf_mask;
+                    const uint32_t b = rb;
                     const uint32_t sbuf = smem_g + b * STAGE_BUF_BYTES;
                     const uint32_t srow = sbuf + (uint32_t)row * 128u;
                     float v[32];
                     tmem_ld32(acc + (uint32_t)(cc * 32), v);
                     if (p.has_res) {
                         PROF_IF(5, pt);
-                        mbar_wait(bar_r + 8 * b, (ql >> nbuf_shift) & 1u);
+                        mbar_wait(bar_r + 8 * b, rph);
                     }
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + nbase);
 #pragma unroll
@@ -711,7 +712,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (!p.has_res && e0) {
                         // the buffer the group's NEXT chunk writes must have been read out by its old store
                         PROF_IF(9, eg == 0);
-                        if (p.nbuf == 2) bulk_wait_read<0>(); else bulk_wait_read<2>();
+                        if (nbuf == 2) bulk_wait_read<0>(); else if (nbuf == 3) bulk_wait_read<1>(); else bulk_wait_read<2>();
                     }
                     { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
@@ -723,24 +724,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     }
                     if (p.stats) {
+                        // column sums of the finished chunk: each thread sums one column over its 32-row quarter
+                        // (fixed order), the four quarters are combined in a fixed order by the first warp of the
+                        // group, and only then added (one uncontended fp64 atomic per channel) to the CTA totals
                         const int col = et & 31, rq = et >> 5;
-                        if (nbase + col < p.Cout) {
-                            float s = 0.f, ss = 0.f;
+                        float s = 0.f, ss = 0.f;
 #pragma unroll 8
-                            for (int r = 0; r < 32; ++r) {
-                                const int rr = rq * 32 + r;
-                                const uint32_t addr = sbuf + (uint32_t)rr * 128u +
-                                                      ((((uint32_t)col >> 2) ^ (uint32_t)(rr & 7)) << 4) +
-                                                      (((uint32_t)col & 3u) << 2);
-                                float x;
-                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
-                                s += x;
-                                ss = fmaf(x, x, ss);
-                            }
-                            atomicAdd(&sacc[0][nbase + col], (double)s);
-                            atomicAdd(&sacc[1][nbase + col], (double)ss);
+                        for (int r = 0; r < 32; ++r) {
+                            const int rr = rq * 32 + r;
+                            const uint32_t addr = sbuf + (uint32_t)rr * 128u +
+                                                  ((((uint32_t)col >> 2) ^ (uint32_t)(rr & 7)) << 4) +
+                                                  (((uint32_t)col & 3u) << 2);
+                            float x;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+                            s += x;
+                            ss = fmaf(x, x, ss);
+                        }
+                        spart[eg][rq][col] = make_float2(s, ss);
+                        named_bar(4 + eg, EPI_THREADS);
+                        if (rq == 0 && nbase + col < p.Cout) {
+                            const float2 p0 = spart[eg][0][col], p1 = spart[eg][1][col], p2 = spart[eg][2][col],
+                                         p3 = spart[eg][3][col];
+                            atomicAdd(&sacc[0][nbase + col], (double)((p0.x + p1.x) + (p2.x + p3.x)));
+                            atomicAdd(&sacc[1][nbase + col], (double)((p0.y + p1.y) + (p2.y + p3.y)));
                         }
                     }
+                    if (++rb == nbuf) { rb = 0; rph ^= 1u; }
                     ++ql;
                 }
             }
@@ -932,8 +941,8 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     p.has_res = has_res ? 1 : 0;
     // staging buffers PER epilogue group: 2; the HBM-bound 1x1 convs with a residual want a deeper residual
     // prefetch (measured 0.124 -> 0.102 ms on 192->192 @ 256^2) and have the shared memory to spare
-    int nbuf = (has_res && ksize == 1) ? 4 : 2;
-    if (g_tune_nbuf == 2 || g_tune_nbuf == 4) nbuf = g_tune_nbuf;
+    int nbuf = (has_res && ksize == 1) ? 4 : 2;    // 3x3: measured 2 > 3 (the pipeline slots matter more)
+    if (g_tune_nbuf >= 2 && g_tune_nbuf <= 4) nbuf = g_tune_nbuf;
     for (;;) {
         int rest = budget - EPI_GROUPS * nbuf * STAGE_BUF_BYTES;
         if (halo) {
@@ -954,7 +963,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
             p.a_slots = p.b_slots = stages;
         }
         if (p.b_slots >= 3 || nbuf == 2) break;
-        nbuf = 2;                      // trade residual prefetch depth for pipeline depth
+        --nbuf;                        // trade residual prefetch depth for pipeline depth
     }
     if (p.b_slots < 2 || p.a_slots < (halo ? mh + 2 : 2)) return false;
     p.nbuf = nbuf;

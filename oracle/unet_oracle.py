@@ -46,9 +46,11 @@ class _Numerics:
         if self.mode == "fp16":
             # cvt.rn.f16.f32 operands (11-bit significand like TF32, 5-bit exponent), fp32 accumulate
             return x.to(torch.float16).to(torch.float32)
-        if self.mode == "fp16_rawsplit":
-            # raw residual-stream operands carried as an fp16 hi + lo pair (two MMA passes): ~22 bits
-            if raw:
+        if self.mode.startswith("fp16_rawsplit"):
+            # raw residual-stream operands carried as an fp16 hi + lo pair (K doubled): ~22 bits.
+            # "fp16_rawsplit" splits every raw conv; "fp16_rawsplit:skip,proj" only the named kinds.
+            kinds = self.mode.split(":")[1].split(",") if ":" in self.mode else None
+            if raw and (kinds is None or raw in kinds):
                 hi = x.to(torch.float16).to(torch.float32)
                 return hi + (x - hi).to(torch.float16).to(torch.float32)
             return x.to(torch.float16).to(torch.float32)
@@ -88,7 +90,7 @@ def _resblock(x, emb, sd, p, nm):
     h = _gn(h, sd, p + ".out_layers.0") * (1 + scale) + shift
     h = _conv(_silu(h), sd, p + ".out_layers.3", nm)
     if (p + ".skip_connection.weight") in sd:
-        x = _conv(x, sd, p + ".skip_connection", nm, raw=True)
+        x = _conv(x, sd, p + ".skip_connection", nm, raw="skip")
     return x + h
 
 
@@ -119,12 +121,12 @@ def _run_block(h, emb, sd, p, heads, nm):
         elif (q + ".qkv.weight") in sd:
             h = _attention(h, sd, q, heads, nm)
         elif (q + ".op.weight") in sd:
-            h = _conv(h, sd, q + ".op", nm, stride=2, raw=True)
+            h = _conv(h, sd, q + ".op", nm, stride=2, raw="down")
         elif (q + ".conv.weight") in sd:
             h = F.interpolate(h, scale_factor=2, mode="nearest")
-            h = _conv(h, sd, q + ".conv", nm, raw=True)
+            h = _conv(h, sd, q + ".conv", nm, raw="up")
         elif (q + ".weight") in sd and sd[q + ".weight"].dim() == 4:
-            h = _conv(h, sd, q, nm, raw=True)  # stem conv
+            h = _conv(h, sd, q, nm, raw="stem")  # stem conv
         else:
             break
         j += 1
@@ -167,7 +169,7 @@ def unet_forward(sd, x, timesteps, x_cond=None, y=None, num_heads=4, operand_rou
         for i in range(n_in):
             hc = _run_block(hc, emb, sd, f"input_blocks_cond.{i}", num_heads, nm)
             # NB unet.py:599-601 -- the projection REPLACES h_cond and feeds the next block
-            hc = _conv(hc, sd, f"input_blocks_proj_cond.{i}", nm, raw=True)
+            hc = _conv(hc, sd, f"input_blocks_proj_cond.{i}", nm, raw="proj")
             hs_cond.append(hc)
 
     for i in range(_count(sd, "output_blocks")):

@@ -34,7 +34,7 @@ SIGNATURES = {
     "hl_conv_cout_pad": (c_int, [c_int]),
     "hl_conv2d": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
-    "hl_attention": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_attention": (c_int, [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_ddim_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
@@ -76,6 +76,7 @@ MLP16_HALVES = MLP16_WV + 64 * 136
 CONV_FORCE_SIMT = 1
 CONV_UPSAMPLE2X = 2
 CONV_TF32 = 4
+CONV_OUT_F16 = 8
 
 _lib = None
 launch_count = 0   # number of C-ABI compute calls issued (each is >= 1 kernel launch)

@@ -199,18 +199,33 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <int CH>
-__global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__ qkv, int ldq,
+// F16IN: qkv was written as fp16 by the producing conv (HL_CONV_OUT_F16); K / V tiles then stream into a
+// double-buffered ring with cp.async (16 B, zero-filled beyond T) while the previous tile is being multiplied.
+template <int CH, bool F16IN>
+__global__ void __launch_bounds__(128) k_attention_mma(const void *__restrict__ qkv_, int ldq,
                                                        __half *__restrict__ out, int ldo, int T, float scale_log2e) {
     constexpr int PITCH = CH * 2 + 16;          // bytes per smem row
     constexpr int KS = CH / 16;                 // k steps of Q.K^T
     constexpr int NO = CH / 8;                  // n tiles of the output
+    constexpr int KV_BYTES = 2 * 64 * PITCH;    // one K tile + one V tile
     extern __shared__ __align__(16) uint8_t smraw[];
     uint8_t *Qs = smraw, *Ks = Qs + 64 * PITCH, *Vs = Ks + 64 * PITCH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
-    const float *base = qkv + (int64_t)b * T * ldq + h * 3 * CH;
+    const float *base = reinterpret_cast<const float *>(qkv_) + (int64_t)b * T * ldq + h * 3 * CH;
+    const __half *base_h = reinterpret_cast<const __half *>(qkv_) + (int64_t)b * T * ldq + h * 3 * CH;
+
+    auto cp_tile = [&](uint8_t *dst, int row0, int col0) {     // 64 rows x CH fp16, asynchronous
+        constexpr int N8 = 64 * (CH / 8);
+        for (int i = tid; i < N8; i += 128) {
+            const int r = i / (CH / 8), c8 = i % (CH / 8);
+            const bool ok = row0 + r < T;
+            const __half *src = base_h + (int64_t)(ok ? row0 + r : T - 1) * ldq + col0 + 8 * c8;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * PITCH + c8 * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+    };
 
     auto load_tile = [&](uint8_t *dst, int row0, int col0) {   // 64 rows x CH fp32 -> fp16 smem
         constexpr int N4 = 64 * (CH / 4), U = 8;               // U independent 128-bit loads in flight per thread
@@ -236,7 +251,14 @@ __global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__
             }
         }
     };
-    load_tile(Qs, q0, 0);
+    if constexpr (F16IN) {
+        cp_tile(Qs, q0, 0);
+        cp_tile(Ks, 0, CH);
+        cp_tile(Vs, 0, 2 * CH);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        load_tile(Qs, q0, 0);
+    }
 
     float o[NO][4];
 #pragma unroll
@@ -244,16 +266,33 @@ __global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;    // rows g and g+8 of this warp's 16
     const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs) +
                             (uint32_t)((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
-    const uint32_t k_addr = (uint32_t)__cvta_generic_to_shared(Ks) +
-                            (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
-    const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(Vs) +
-                            (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16);
+    const uint32_t k_addr0 = (uint32_t)__cvta_generic_to_shared(Ks) +
+                             (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
+    const uint32_t v_addr0 = (uint32_t)__cvta_generic_to_shared(Vs) +
+                             (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16);
 
-    for (int k0 = 0; k0 < T; k0 += 64) {
-        __syncthreads();                         // previous tile fully consumed (and Q visible)
-        load_tile(Ks, k0, CH);
-        load_tile(Vs, k0, 2 * CH);
-        __syncthreads();
+    for (int k0 = 0, it = 0; k0 < T; k0 += 64, ++it) {
+        uint32_t k_addr = k_addr0, v_addr = v_addr0;
+        if constexpr (F16IN) {
+            __syncthreads();                     // the other buffer (tile it-1) fully consumed
+            if (k0 + 64 < T) {
+                uint8_t *nk = Ks + ((it + 1) & 1) * KV_BYTES;
+                cp_tile(nk, k0 + 64, CH);
+                cp_tile(nk + 64 * PITCH, k0 + 64, 2 * CH);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            k_addr += (it & 1) * KV_BYTES;
+            v_addr += (it & 1) * KV_BYTES;
+        } else {
+            __syncthreads();                     // previous tile fully consumed (and Q visible)
+            load_tile(Ks, k0, CH);
+            load_tile(Vs, k0, 2 * CH);
+            __syncthreads();
+        }
 
         float s[8][4];
 #pragma unroll
@@ -332,47 +371,59 @@ __global__ void __launch_bounds__(128) k_attention_mma(const float *__restrict__
     }
 }
 
-template <int CH>
-int launch_mma(const float *qkv, int ldq, __half *out, int ldo, int B, int T, int heads, cudaStream_t stream) {
+template <int CH, bool F16IN>
+int launch_mma_t(const void *qkv, int ldq, __half *out, int ldo, int B, int T, int heads, cudaStream_t stream) {
     constexpr int PITCH = CH * 2 + 16;
-    size_t smem = (size_t)3 * 64 * PITCH;
+    size_t smem = (size_t)(F16IN ? 5 : 3) * 64 * PITCH;
     static bool configured = false;
     if (!configured) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_attention_mma<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_attention_mma<CH, F16IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(hl_cdiv(T, 64), heads, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)CH);
-    k_attention_mma<CH><<<grid, 128, smem, stream>>>(qkv, ldq, out, ldo, T, scale_log2e);
+    k_attention_mma<CH, F16IN><<<grid, 128, smem, stream>>>(qkv, ldq, out, ldo, T, scale_log2e);
     HL_CHECK_LAUNCH();
     return HL_OK;
+}
+template <int CH>
+int launch_mma(const void *qkv, int qkv_f16, int ldq, __half *out, int ldo, int B, int T, int heads, cudaStream_t stream) {
+    return qkv_f16 ? launch_mma_t<CH, true>(qkv, ldq, out, ldo, B, T, heads, stream)
+                   : launch_mma_t<CH, false>(qkv, ldq, out, ldo, B, T, heads, stream);
 }
 
 }  // namespace
 
-extern "C" int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
-                            int heads, int round_tf32, void *stream) {
+extern "C" int hl_attention(const void *qkv, int qkv_dtype, int ldq, void *out, int out_dtype, int ldo, int B, int T,
+                            int C, int heads, int round_tf32, void *stream) {
     HL_CHECK_ARG(qkv && out && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0);
-    HL_CHECK_ARG(ldq >= 3 * C && ldo >= C && ldq % 4 == 0);
+    const int qf16 = qkv_dtype == HL_DT_F16;
+    HL_CHECK_ARG(ldq >= 3 * C && ldo >= C && ldq % (qf16 ? 8 : 4) == 0);
     int ch = C / heads;
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_dtype == HL_DT_F16 && !(round_tf32 & 2) && ldo % 2 == 0 && ((uintptr_t)out & 3) == 0) {
+    if (out_dtype == HL_DT_F16 && !(round_tf32 & 2) && ldo % 2 == 0 && ((uintptr_t)out & 3) == 0 &&
+        (!qf16 || ((uintptr_t)qkv & 15) == 0)) {
         __half *oh = (__half *)out;
         switch (ch) {
-            case 32: return launch_mma<32>(qkv, ldq, oh, ldo, B, T, heads, st);
-            case 64: return launch_mma<64>(qkv, ldq, oh, ldo, B, T, heads, st);
-            case 96: return launch_mma<96>(qkv, ldq, oh, ldo, B, T, heads, st);
-            case 128: return launch_mma<128>(qkv, ldq, oh, ldo, B, T, heads, st);
-            case 192: return launch_mma<192>(qkv, ldq, oh, ldo, B, T, heads, st);
+            case 32: return launch_mma<32>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
+            case 64: return launch_mma<64>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
+            case 96: return launch_mma<96>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
+            case 128: return launch_mma<128>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
+            case 192: return launch_mma<192>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
             default: break;   // other head widths: CUDA-core kernel below
         }
     }
+    if (qf16) {
+        hl_set_error("hl_attention: fp16 qkv needs the tensor-core kernel (fp16 output, head width 32/64/96/128/192; got %d)", ch);
+        return HL_E_UNSUPPORTED;
+    }
+    const float *qf = (const float *)qkv;
     switch (ch) {
-        case 32: return launch<32>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
-        case 64: return launch<64>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
-        case 96: return launch<96>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
-        case 128: return launch<128>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
-        case 192: return launch<192>(qkv, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 32: return launch<32>(qf, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 64: return launch<64>(qf, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 96: return launch<96>(qf, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 128: return launch<128>(qf, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
+        case 192: return launch<192>(qf, ldq, out, out_dtype, ldo, B, T, heads, round_tf32 & 1, st);
         default:
             hl_set_error("hl_attention: unsupported head width %d (supported: 32,64,96,128,192)", ch);
             return HL_E_UNSUPPORTED;

@@ -22,7 +22,7 @@ struct ConvArgs {
     const T *x; int ldx;
     const T *w; const float *bias;
     const float *res; int ldr;
-    float *y; int ldy;
+    void *y; int ldy; int y_f16;
     int B, H, W, Cin, Cout, Cout_pad, ksize, stride, ups;
     int Ho, Wo;      // output size
     int Hi, Wi;      // logical input size (after optional upsample)
@@ -121,17 +121,18 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
             if (n >= a.Cout) continue;
             float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
             if (a.res) v += a.res[mm * a.ldr + n];
-            a.y[mm * a.ldy + n] = v;
+            if (a.y_f16) reinterpret_cast<__half *>(a.y)[mm * a.ldy + n] = __float2half_rn(v);
+            else reinterpret_cast<float *>(a.y)[mm * a.ldy + n] = v;
         }
     }
 }
 
 template <typename T>
 static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, const float *residual, int ldr,
-                       float *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                       void *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
                        int flags, cudaStream_t stream) {
     ConvArgs<T> a;
-    a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy;
+    a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.y_f16 = (flags & HL_CONV_OUT_F16) ? 1 : 0;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = hl_conv_cout_pad(Cout);
     a.ksize = ksize; a.stride = stride; a.ups = (flags & HL_CONV_UPSAMPLE2X) ? 1 : 0;
     a.Hi = a.ups ? 2 * H : H;
@@ -150,7 +151,7 @@ static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, con
 }  // namespace
 
 int hl_conv2d_simt(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
-                   const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout,
+                   const float *residual, int ldr, void *y, int ldy, int B, int H, int W, int Cin, int Cout,
                    int ksize, int stride, int flags, cudaStream_t stream) {
     if (x_dtype == HL_DT_F16)
         return launch_simt<__half>((const __half *)x, ldx, (const __half *)wpk, bias, residual, ldr, y, ldy, B, H,

@@ -74,6 +74,7 @@ struct TcParams {
     int a_slots, a_slot_bytes, b_slots, b_slot_bytes, nbuf;
     const float *bias;
     int has_res;
+    int y_f16;               // output written as fp16 (an operand buffer) instead of fp32
     double *stats;
     int stats_ld;
 };
@@ -691,22 +692,50 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         mbar_wait(bar_r + 8 * b, rph);
                     }
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + nbase);
+                    if (!p.y_f16) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 bz = __ldg(bias4 + j);
-                        float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
-                                               v[4 * j + 3] + bz.w);
-                        const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
-                        if (p.has_res) {
-                            float4 r;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                                         : "r"(addr));
-                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bz = __ldg(bias4 + j);
+                            float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
+                                                   v[4 * j + 3] + bz.w);
+                            const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
+                            if (p.has_res) {
+                                float4 r;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                             : "r"(addr));
+                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                            }
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y),
+                                         "f"(o.z), "f"(o.w)
+                                         : "memory");
                         }
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y),
-                                     "f"(o.z), "f"(o.w)
-                                     : "memory");
+                    } else {
+                        // fp16 output (the tensor is only ever read as a conv / attention operand): same fp32
+                        // arithmetic, then one rounding; staged as [128 rows][64 B] in the SWIZZLE_64B pattern
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bz = __ldg(bias4 + j);
+                            v[4 * j] += bz.x; v[4 * j + 1] += bz.y; v[4 * j + 2] += bz.z; v[4 * j + 3] += bz.w;
+                            if (p.has_res) {
+                                float4 r;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                             : "r"(srow + (((uint32_t)j ^ sw) << 4)));
+                                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                            }
+                        }
+                        if (p.has_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
+                        const uint32_t hrow = sbuf + (uint32_t)row * 64u, hsw = ((uint32_t)row >> 1) & 3u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+                            const __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((uint32_t)j ^ hsw) << 4)),
+                                         "r"(*reinterpret_cast<const uint32_t *>(&h0)), "r"(*reinterpret_cast<const uint32_t *>(&h1)),
+                                         "r"(*reinterpret_cast<const uint32_t *>(&h2)), "r"(*reinterpret_cast<const uint32_t *>(&h3))
+                                         : "memory");
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (!p.has_res && e0) {
@@ -1020,7 +1049,7 @@ bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, 
     if (stride == 2 && (ksize != 3 || (H % 2) || (W % 2))) return false;
     if (x_dtype == HL_DT_F32 && !(flags & HL_CONV_TF32)) return false;
     const int esz = x_dtype == HL_DT_F16 ? 2 : 4;
-    if ((ldx * esz) % 16 || Cin > ldx || ldy % 4) return false;
+    if ((ldx * esz) % 16 || Cin > ldx || ldy % ((flags & HL_CONV_OUT_F16) ? 8 : 4)) return false;
     Plan pl = {};
     if (!make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, false, false,
                    &pl))
@@ -1032,7 +1061,7 @@ int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *st
                        cudaStream_t stream);
 
 int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
-                 const float *residual, int ldr, float *y, int ldy, double *stats, int stats_ld, int B,
+                 const float *residual, int ldr, void *y, int y_f16, int ldy, double *stats, int stats_ld, int B,
                  int Hin, int Win, int Cin, int Cout, int ksize, int stride, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) {
@@ -1050,6 +1079,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     HL_CHECK_ARG(!residual || (((uintptr_t)residual & 15) == 0 && ldr % 4 == 0));
     TcParams &p = pl.p;
     p.bias = bias;
+    p.y_f16 = y_f16;
+    HL_CHECK_ARG(!(y_f16 && stats));
     const bool epi_stats = plan_epi_stats(pl, stats != nullptr);
     if (epi_stats) {
         p.stats = stats;
@@ -1092,17 +1123,20 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         }
     }
     for (int which = 0; which < 2; ++which) {
-        const float *ptr = which ? residual : y;
+        const void *ptr = which ? (const void *)residual : (const void *)y;
         const int ld = which ? ldr : ldy;
+        const bool f16 = !which && y_f16;
+        const int esz_o = f16 ? 2 : 4;
         CUtensorMap *tm = which ? &tmR : &tmY;
         if (!ptr) { *tm = tmY; continue; }
         cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t gstr[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+        cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
         cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
         if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr, gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CUresult r = encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr,
+                            gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             hl_set_error("cuTensorMapEncodeTiled(%s) failed: %d (B=%d H=%d W=%d Cout=%d ld=%d)",
@@ -1135,7 +1169,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         k_conv_tc<false><<<pl.grid, NUM_THREADS, pl.smem, stream>>>(tmA, tmB, tmY, tmR, p);
     }
     HL_CHECK_LAUNCH();
-    if (stats && !epi_stats) return hl_gn_stats_launch(y, ldy, B, H * W, Cout, stats, stats_ld, stream);
+    if (stats && !epi_stats) return hl_gn_stats_launch((const float *)y, ldy, B, H * W, Cout, stats, stats_ld, stream);
     return HL_OK;
 }
 
@@ -1143,7 +1177,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
 // public entry: dispatch
 // ---------------------------------------------------------------------------------------------
 int hl_conv2d_simt(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
-                   const float *residual, int ldr, float *y, int ldy, int B, int H, int W, int Cin, int Cout,
+                   const float *residual, int ldr, void *y, int ldy, int B, int H, int W, int Cin, int Cout,
                    int ksize, int stride, int flags, cudaStream_t stream);
 
 extern "C" int hl_conv2d_uses_tensor_cores(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize,
@@ -1152,7 +1186,7 @@ extern "C" int hl_conv2d_uses_tensor_cores(int x_dtype, int B, int H, int W, int
 }
 
 extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
-                         const float *residual, int ldr, float *y, int ldy, double *stats, int stats_ld,
+                         const float *residual, int ldr, void *y, int ldy, double *stats, int stats_ld,
                          int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
                          void *stream) {
     HL_CHECK_ARG(x && wpk && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
@@ -1162,14 +1196,15 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
     HL_CHECK_ARG(ldx >= Cin && ldy >= Cout && (!residual || ldr >= Cout));
     HL_CHECK_ARG(!((flags & HL_CONV_UPSAMPLE2X) && stride != 1));
     HL_CHECK_ARG(!stats || stats_ld >= Cout);
+    HL_CHECK_ARG(!((flags & HL_CONV_OUT_F16) && stats));    // statistics are defined on fp32 results only
     if (hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags))
-        return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin,
-                            Cout, ksize, stride, (cudaStream_t)stream);
+        return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y, (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, stats,
+                            stats_ld, B, H, W, Cin, Cout, ksize, stride, (cudaStream_t)stream);
     int rc = hl_conv2d_simt(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize, stride,
                             flags, (cudaStream_t)stream);
     if (rc != HL_OK || !stats) return rc;
     const int ups = (flags & HL_CONV_UPSAMPLE2X) ? 2 : 1;
     const int pad = ksize / 2;
     const int Ho = (H * ups + 2 * pad - ksize) / stride + 1, Wo = (W * ups + 2 * pad - ksize) / stride + 1;
-    return hl_gn_stats_launch(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
+    return hl_gn_stats_launch((const float *)y, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
 }

@@ -325,10 +325,11 @@ class _Ref:
     """A residual-stream tensor inside the workspace: fp32 NHWC ``ptr`` with pixel pitch ``ld``, ``C``
     channels at H x W, and the per-channel statistics row (``st`` pointer, ``st_ld`` doubles-pairs per
     sample) its producer fills."""
-    __slots__ = ("ptr", "ld", "C", "H", "W", "st", "st_ld")
+    __slots__ = ("ptr", "ld", "C", "H", "W", "st", "st_ld", "f16")
 
-    def __init__(self, ptr, ld, C, H, W, st, st_ld):
+    def __init__(self, ptr, ld, C, H, W, st, st_ld, f16=False):
         self.ptr, self.ld, self.C, self.H, self.W, self.st, self.st_ld = ptr, ld, C, H, W, st, st_ld
+        self.f16 = f16       # an fp16 OPERAND buffer written directly by the producing conv (HL_CONV_OUT_F16)
 
 
 class _StepPlan:
@@ -398,6 +399,9 @@ class _StepPlan:
         elif m.precision == "tf32":
             flags |= _lib.CONV_TF32
         st = ("stats", dst.st) if (want_stats and dst.st is not None) else None
+        if dst.f16:
+            assert st is None
+            flags |= _lib.CONV_OUT_F16
         self.emit("hl_conv2d", x_ptr, self.dt, ldx, _ptr(c.w), _ptr(c.b), res.ptr if res else None,
                   res.ld if res else 0, dst.ptr, dst.ld, st, dst.st_ld if st else 0, self.B, H, W, c.cin_pad,
                   c.cout, c.ksize, c.stride, flags)
@@ -436,11 +440,14 @@ class _StepPlan:
         m, B = self.m, self.B
         C, H, W = blk["c"], x.H, x.W
         act = _ptr(self.scratch("act", self.max_act, op=True))
-        qkv = _Ref(_ptr(self.scratch("qkv", self.max_qkv)), 3 * C, 3 * C, H, W, None, 0)
+        # fp16 mode: qkv is only ever an attention operand -> the conv writes it as fp16
+        f16 = self.dt == _lib.DT_F16
+        qkv = _Ref(_ptr(self.scratch("qkv", self.max_qkv, op=f16)), 3 * C, 3 * C, H, W, None, 0, f16=f16)
         att = _ptr(self.scratch("att", self.max_act, op=True))
         self.gn(blk["n"], x, act, C, False)
         self.conv(blk["qkv"], act, C, None, qkv, H, W, want_stats=False)
-        self.emit("hl_attention", qkv.ptr, 3 * C, att, self.dt, C, B, H * W, C, m.num_heads, self.rnd)
+        self.emit("hl_attention", qkv.ptr, self.dt if f16 else _lib.DT_F32, 3 * C, att, self.dt, C, B, H * W, C,
+                  m.num_heads, self.rnd)
         self.conv(blk["proj"], att, C, x, dst, H, W)
 
     def layers(self, layers, x, dst_name, dst=None):
@@ -491,18 +498,28 @@ class _StepPlan:
         mc = m.model_channels
         outs = []
         x = None
+        f16 = self.dt == _lib.DT_F16
         for i, layers in enumerate(enc):
             direct = (not controlnet_branch) and not self.keep_hs     # unconditional: write into cat
+            dst = cats[i] if direct else None
+            if controlnet_branch and f16:
+                # a ControlNet block's output is consumed only by its projection conv: write the fp16
+                # operand straight from the producing conv's epilogue (no fp32 tensor, no cast pass)
+                C_, H_, W_ = self.geo[i]
+                dst = _Ref(_ptr(self.scratch("hcop", self.max_act, op=True)), C_, C_, H_, W_, None, 0, f16=True)
             if i == 0:
-                out = cats[0] if direct else self.new_ref(f"{tag}{i}", mc, H, W)
+                out = dst if dst is not None else self.new_ref(f"{tag}{i}", mc, H, W)
                 self.conv(layers[0]["c"], xin_ptr, m.cin_pad, None, out, H, W)
                 x = out
             else:
-                x = self.layers(layers, x, f"{tag}{i}", dst=cats[i] if direct else None)
+                x = self.layers(layers, x, f"{tag}{i}", dst=dst)
             if controlnet_branch:
                 cname = f"input_blocks_proj_cond.{i}"
-                op = _ptr(self.scratch("raw", self.max_act, op=True))
-                self.cast(x, op, x.C)
+                if x.f16:
+                    op = x.ptr
+                else:
+                    op = _ptr(self.scratch("raw", self.max_act, op=True))
+                    self.cast(x, op, x.C)
                 hc = self.new_ref(f"{tag}p{i}", x.C, x.H, x.W)
                 self.conv(cname, op, x.C, None, hc, x.H, x.W)                    # h_cond (unet.py:600)
                 if self.concurrent:
@@ -564,6 +581,7 @@ class _StepPlan:
             if layers[0]["kind"] == "down":
                 h_, w_ = h_ // 2, w_ // 2
             geo.append((m._enc_chans[i], h_, w_))
+        self.geo = geo
         self.cat_full, self.cat_skip = [None] * nblk, [None] * nblk
         hC = m._mid[-1]["cout"]
         self.cat_h = [None] * nblk     # indexed by decoder block j

@@ -42,6 +42,7 @@ extern "C" {
 #define HL_CONV_FORCE_SIMT 1   /* use the fp32 CUDA-core kernel even where the tcgen05 path applies */
 #define HL_CONV_UPSAMPLE2X 2   /* input is read through a nearest x2 upsample (unet.py:77)          */
 #define HL_CONV_TF32 4         /* fp32 operands may go through tcgen05 kind::tf32                   */
+#define HL_CONV_OUT_F16 8      /* y is an fp16 operand buffer (pitch ldy in halves); no statistics   */
 
 int hl_version(void);
 const char *hl_last_error(void);
@@ -124,23 +125,26 @@ int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, cons
  * Cout_pad = hl_conv_cout_pad(Cout); bias fp32 [Cout_pad].  ksize in {1,3}; stride in {1,2}.
  * y / residual: fp32 NHWC with pitches ldy / ldr (channel slices of wider buffers are fine: the
  * decoder's concat is never materialised).  stats (nullable): per-channel sum / sum-of-squares of
- * y, layout as hl_gn_stats, ACCUMULATED into the caller-zeroed buffer.
+ * y, layout as hl_gn_stats, ACCUMULATED into the caller-zeroed buffer.  With HL_CONV_OUT_F16 the result
+ * (same fp32 arithmetic, rounded once) is written as an fp16 operand buffer: used where the tensor is only
+ * ever consumed as an operand (qkv -> attention, ControlNet block output -> its projection conv).
  * A 1x1 conv over [B*T, C] rows is the Conv1d / GEMM of the attention block.                    */
 int hl_conv_cout_pad(int Cout);
 int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
-              const float *residual /*nullable*/, int ldr, float *y, int ldy, double *stats /*nullable*/,
+              const float *residual /*nullable*/, int ldr, void *y, int ldy, double *stats /*nullable*/,
               int stats_ld, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
               void *stream);
 
 /* ---- attention (unet.py:255-274) ------------------------------------------------------------ */
 
-/* qkv: fp32 [B, T, 3C] rows (pitch ldq) with channel order [head][q(ch) k(ch) v(ch)];
+/* qkv: fp32 or fp16 (qkv_dtype; fp16 = written by hl_conv2d with HL_CONV_OUT_F16, tensor-core kernel only)
+ * [B, T, 3C] rows (pitch ldq elements) with channel order [head][q(ch) k(ch) v(ch)];
  * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c], written as an operand
  * (out_dtype) for the proj_out GEMM.  With an fp16 output both contractions run on the tensor
  * cores (q, k, v, softmax weights rounded to fp16; scores / softmax / accumulation fp32); an fp32
  * output selects the exact CUDA-core kernel.  round_tf32: bit 0 = TF32-round an fp32 output,
  * bit 1 = force the CUDA-core kernel (tests).                                                     */
-int hl_attention(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
+int hl_attention(const void *qkv, int qkv_dtype, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
                  int heads, int round_tf32, void *stream);
 
 /* ---- DDPM posterior step (gaussian_diffusion.py:293-314,328-333,383-387) ---------------------- */

@@ -140,13 +140,18 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
     out = out.reshape(B * Ho * Wo, Cout).numpy()
     if residual:
         out = out + pitched(residual, B * Ho * Wo, Cout, ldr)
+    if flags & 8:                                           # HL_CONV_OUT_F16
+        assert not stats
+        pitched(y, B * Ho * Wo, Cout, ldy, np.float16)[...] = out.astype(np.float16)
+        return
     pitched(y, B * Ho * Wo, Cout, ldy)[...] = out
     if stats:
         hl_gn_stats(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, stream)
 
 
-def hl_attention(qkv, ldq, out, out_dtype, ldo, B, T, C, heads, round_tf32, stream):
-    v = torch.from_numpy(pitched(qkv, B * T, 3 * C, ldq).copy()).reshape(B, T, heads, 3, C // heads)
+def hl_attention(qkv, qkv_dtype, ldq, out, out_dtype, ldo, B, T, C, heads, round_tf32, stream):
+    v = torch.from_numpy(pitched(qkv, B * T, 3 * C, ldq, _dt(qkv_dtype)).astype(np.float32))
+    v = v.reshape(B, T, heads, 3, C // heads)
     q, k, vv = v[:, :, :, 0], v[:, :, :, 1], v[:, :, :, 2]            # [B, T, heads, ch]
     w = torch.einsum("bthc,bshc->bhts", q, k) / (C // heads) ** 0.5
     w = torch.softmax(w, dim=-1)

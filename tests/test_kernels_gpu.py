@@ -161,7 +161,7 @@ def _operand(t, mode):
 
 
 def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residual=True, stats=False, cin_pad=None,
-               seed=0, ldy=None, tuning=None, tuning2=None):
+               seed=0, ldy=None, tuning=None, tuning2=None, out_f16=False):
     """Runs hl_conv2d on seeded inputs; returns (y NCHW cpu, fp32 reference, reference on the ROUNDED operands,
     stats cpu or None)."""
     from humanliff_b200.unet import pack_conv
@@ -189,7 +189,9 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
     xd = xop.to(dev)
     wpk, bpk = pack_conv(w, b, cin_pad, mode, dev)
     ldy = ldy or Cout
-    y = torch.full((B, Ho, Wo, ldy), float("nan"), device=dev)
+    y = torch.full((B, Ho, Wo, ldy), float("nan"), device=dev, dtype=torch.float16 if out_f16 else torch.float32)
+    if out_f16:
+        flags |= _lib.CONV_OUT_F16
     rd = res.permute(0, 2, 3, 1).contiguous().to(dev) if residual else None
     st = torch.zeros(B * ldy * 2, device=dev, dtype=torch.float64) if stats else None
     lib = _lib.load()
@@ -205,7 +207,7 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
     finally:
         lib.hl_conv_set_tuning(-1, -1, -1, -1, -1)
         lib.hl_conv_set_tuning2(-1, -1, -1)
-    return y[..., :Cout].permute(0, 3, 1, 2).cpu(), ref, ref_r, (st.cpu().reshape(B, ldy, 2) if stats else None)
+    return y[..., :Cout].permute(0, 3, 1, 2).float().cpu(), ref, ref_r, (st.cpu().reshape(B, ldy, 2) if stats else None)
 
 
 def _check_stats(st, y, Cout):
@@ -290,6 +292,22 @@ def test_conv_tensor_core_tilings(dev, tuning, residual, cta2):
     _check_stats(st, y, Cout)
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 64, 192, 192, 3, 1), (2, 128, 128, 192, 192, 3, 1), (2, 16, 16, 384, 192, 1, 1),
+                                   (1, 16, 16, 384, 1152, 1, 1), (2, 64, 64, 192, 192, 3, 2), (4, 8, 8, 768, 768, 3, 1),
+                                   (1, 8, 8, 96, 40, 1, 1)])
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_conv_fp16_output(dev, shape, residual, cta2):
+    """HL_CONV_OUT_F16: the same fp32 arithmetic rounded once -> bit-identical to the fp32 output's .half()
+    (tcgen05 path with / without residual, CTA pairs, 1x1 staging ring; the last shape takes the CUDA-core path)."""
+    B, H, W, Cin, Cout, k, s = shape
+    kw = dict(mode="fp16", residual=residual, seed=11, tuning2=(-1, -1, cta2))
+    y32 = _conv_case(dev, B, H, W, Cin, Cout, k, s, **kw)[0]
+    y16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
+    assert not torch.isnan(y16).any()
+    assert torch.equal(y16, y32.half().float())
+
+
 def test_conv_tc_strided_output_and_input(dev):
     """Operands living inside wider (concat) buffers: ldx > Cin, ldy > Cout, statistics row at an offset."""
     from humanliff_b200.unet import pack_conv
@@ -324,16 +342,16 @@ def test_attention(dev, B, T, C, heads):
     ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
     qd = qkv.permute(0, 2, 1).contiguous().to(dev)             # [B, T, 3C]
     out = torch.empty(B, T, C, device=dev)
-    _call("hl_attention", qd.data_ptr(), 3 * C, out.data_ptr(), 0, C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", qd.data_ptr(), 0, 3 * C, out.data_ptr(), 0, C, B, T, C, heads, 0, _stream())
     assert rel_l2(out.permute(0, 2, 1), ref) < 5e-6
     assert rel_max(out.permute(0, 2, 1), ref) < 5e-5
     outh = torch.empty(B, T, C, device=dev, dtype=torch.float16)
-    _call("hl_attention", qd.data_ptr(), 3 * C, outh.data_ptr(), 1, C, B, T, C, heads, 2, _stream())   # CUDA cores
+    _call("hl_attention", qd.data_ptr(), 0, 3 * C, outh.data_ptr(), 1, C, B, T, C, heads, 2, _stream())   # CUDA cores
     assert torch.equal(outh.cpu(), out.cpu().half())
     # tensor-core kernel (mma.sync, fp16 operands / fp32 accumulate): vs the same attention evaluated in fp32 on
     # the fp16-ROUNDED q, k, v (isolates the kernel from the operand rounding), and vs the exact result
     outm = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
-    _call("hl_attention", qd.data_ptr(), 3 * C, outm.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", qd.data_ptr(), 0, 3 * C, outm.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
     rh = qkv.half().float().reshape(B * heads, 3 * ch, T)
     qh, kh, vh = torch.split(rh, ch, dim=1)
     wh = torch.softmax(torch.einsum("bct,bcs->bts", qh, kh) / math.sqrt(ch), -1)
@@ -341,6 +359,11 @@ def test_attention(dev, B, T, C, heads):
     assert not torch.isnan(outm.float()).any()
     assert rel_l2(outm.float().permute(0, 2, 1), refh) < 6e-4      # P and the output rounded to fp16
     assert rel_l2(outm.float().permute(0, 2, 1), ref) < 2e-3
+    # fp16 qkv (as written by a HL_CONV_OUT_F16 conv): cp.async double-buffered variant, same arithmetic
+    qh16 = qd.half()
+    outf = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
+    _call("hl_attention", qh16.data_ptr(), 1, 3 * C, outf.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    assert torch.equal(outf.cpu(), outm.cpu())
 
 
 def test_ddpm_step_bit_exact(dev):

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhumanliff_b200.so")
+LIB_PATH = os.environ.get("HL_LIB") or os.path.join(_HERE, "libhumanliff_b200.so")   # $HL_LIB: experiment builds
 
 c_int, c_i64, c_u64, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
 
@@ -19,6 +19,8 @@ SIGNATURES = {
     "hl_conv2d_uses_tensor_cores": (c_int, [c_int] * 11),
     "hl_conv_set_tuning": (c_int, [c_int] * 5),
     "hl_conv_set_tuning2": (c_int, [c_int] * 3),
+    "hl_conv_set_workspace": (c_int, [c_p, c_i64, c_p]),
+    "hl_conv_set_split": (c_int, [c_int]),
     "hl_conv_set_profile": (c_int, [c_p]),
     "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_nhwc_to_nchw": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
@@ -34,6 +36,9 @@ SIGNATURES = {
     "hl_conv_cout_pad": (c_int, [c_int]),
     "hl_conv2d": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_set_pdl": (c_int, [c_int]),
+    "hl_pdl_barrier": (None, []),
+    "hl_launch_count": (c_i64, []),
     "hl_attention": (c_int, [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_ddim_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),

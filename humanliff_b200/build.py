@@ -11,8 +11,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "csrc", "build")
-LIB_PATH = os.path.join(HERE, "libhumanliff_b200.so")
+# experiment builds: HL_BUILD_TAG=<tag> HL_NVCC_EXTRA="-DX=1" -> libhumanliff_b200_<tag>.so (select with $HL_LIB)
+_TAG = os.environ.get("HL_BUILD_TAG", "")
+OBJ_DIR = os.path.join(HERE, "csrc", "build" + ("_" + _TAG if _TAG else ""))
+LIB_PATH = os.path.join(HERE, "libhumanliff_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "render.cu", "render_tc.cu"]
 
@@ -21,7 +23,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("HL_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -16,6 +16,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv, int ldq,
                                                    void *__restrict__ out, int out_dtype, int ldo, int T,
                                                    int heads, float scale, int round_tf32) {
+    hl_pdl_enter();
     constexpr int LD = CH + 4;           // padded row pitch (floats): conflict-free float4 rows
     constexpr int NJ = CH / 16;          // output columns per thread
     extern __shared__ float sm[];
@@ -167,7 +168,7 @@ int launch(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, 
     }
     dim3 grid(hl_cdiv(T, TQ), heads, B);
     float scale = 1.0f / sqrtf((float)CH);
-    k_attention<CH><<<grid, 256, smem, stream>>>(qkv, ldq, out, out_dtype, ldo, T, heads, scale, round_tf32);
+    HL_CHECK_CUDA(hl_launch(k_attention<CH>, grid, dim3(256), smem, stream, qkv, ldq, out, out_dtype, ldo, T, heads, scale, round_tf32));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -204,6 +205,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 template <int CH, bool F16IN>
 __global__ void __launch_bounds__(128) k_attention_mma(const void *__restrict__ qkv_, int ldq,
                                                        __half *__restrict__ out, int ldo, int T, float scale_log2e) {
+    hl_pdl_enter();
     constexpr int PITCH = CH * 2 + 16;          // bytes per smem row
     constexpr int KS = CH / 16;                 // k steps of Q.K^T
     constexpr int NO = CH / 8;                  // n tiles of the output
@@ -382,7 +384,7 @@ int launch_mma_t(const void *qkv, int ldq, __half *out, int ldo, int B, int T, i
     }
     dim3 grid(hl_cdiv(T, 64), heads, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)CH);
-    k_attention_mma<CH, F16IN><<<grid, 128, smem, stream>>>(qkv, ldq, out, ldo, T, scale_log2e);
+    HL_CHECK_CUDA(hl_launch(k_attention_mma<CH, F16IN>, grid, dim3(128), smem, stream, qkv, ldq, out, ldo, T, scale_log2e));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -56,3 +56,51 @@ __device__ __forceinline__ float hl_warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A denoise step is ~540 short launches; with the attribute set
+// the next kernel's CTAs are scheduled as soon as every CTA of the previous one has started (or exited),
+// run their prologue (barrier init, TMEM alloc, descriptor prefetch) and block in griddepcontrol.wait
+// until the previous grid has completed and its memory is visible -- the launch gap and the prologue
+// disappear from the critical path.  Rule: every kernel that can be launched with the attribute calls
+// hl_pdl_wait() before its first global access to anything another kernel writes or reads (so
+// completion is transitive along the stream); both instructions are no-ops in a normal launch.
+// ---------------------------------------------------------------------------------------------
+#ifndef HL_PDL_TRIGGER
+#define HL_PDL_TRIGGER 1     // 0: never (dependents start at completion), 1: at kernel entry, 2: conv after its last MMA
+#endif
+__device__ __forceinline__ void hl_pdl_trigger() {
+    if (HL_PDL_TRIGGER != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void hl_pdl_trigger_early() { if (HL_PDL_TRIGGER == 1) hl_pdl_trigger(); }
+__device__ __forceinline__ void hl_pdl_trigger_late() { if (HL_PDL_TRIGGER == 2) hl_pdl_trigger(); }
+__device__ __forceinline__ void hl_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void hl_pdl_enter() { hl_pdl_trigger(); hl_pdl_wait(); }
+
+extern int g_hl_pdl;            // hl_set_pdl(): 1 = launch with programmatic stream serialization
+extern int g_hl_pdl_skip;       // hl_pdl_barrier(): the next launch is a normal (fully serialized) one
+extern long long g_hl_launches; // kernels launched (or captured) by this library: hl_launch_count()
+
+// fills cfg.attrs[n_attrs..] ; returns the new attribute count
+static inline unsigned hl_pdl_attr(cudaLaunchAttribute *attrs, unsigned n) {
+    ++g_hl_launches;
+    if (g_hl_pdl_skip) { g_hl_pdl_skip = 0; return n; }
+    if (!g_hl_pdl) return n;
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    return n + 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t hl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    cfg.attrs = attrs;
+    cfg.numAttrs = hl_pdl_attr(attrs, 0);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

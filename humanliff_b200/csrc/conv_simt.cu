@@ -32,6 +32,7 @@ struct ConvArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
+    hl_pdl_enter();
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -143,7 +144,7 @@ static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, con
     a.M = (int64_t)B * a.Ho * a.Wo;
     a.K = ksize * ksize * Cin;
     dim3 grid(hl_cdiv(a.M, BM), hl_cdiv(Cout, BN));
-    k_conv_simt<T><<<grid, 256, 0, stream>>>(a);
+    HL_CHECK_CUDA(hl_launch(k_conv_simt<T>, grid, dim3(256), 0, stream, a));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -75,6 +75,8 @@ struct TcParams {
     const float *bias;
     int has_res;
     int y_f16;               // output written as fp16 (an operand buffer) instead of fp32
+    int ksplit, kc_split, tiles_mn;   // split-K: tile = ks * tiles_mn + (m, n); split ks covers kc_split channel chunks
+    int split_b;             // batch-coordinate offset per split in the partial-sum workspace (= B)
     double *stats;
     int stats_ld;
 };
@@ -337,6 +339,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int chunk_elems = p.kind ? 64 : 32;
     // CTA pair: rank 0 is the leader (issues the MMAs, owns the barriers the MMA thread waits on)
     const int rank = CTA2 ? (int)cluster_rank() : 0;
+    hl_pdl_trigger_early();
     const int cid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // first tile of this CTA / pair
     const int nct = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;      // tile stride
     const int nprod = CTA2 ? 2 : 1;
@@ -382,6 +385,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CTA2) cluster_sync_all(); else __syncthreads();     // barriers initialised + TMEM allocated in both CTAs
+    hl_pdl_wait();       // everything above overlapped the previous kernel's tail; from here on its results are visible
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_slot;
     const int pad = p.ksize / 2;
@@ -401,13 +405,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t nslots = (uint32_t)p.a_slots, slot_bytes = (uint32_t)p.a_slot_bytes;
             uint32_t slot = 0, phase = 0;
             for (int tile = cid; tile < p.total_tiles; tile += nct) {
-                const int mt = tile / p.n_tiles;
+                const int ks = tile / p.tiles_mn;
+                const int mt = (tile - ks * p.tiles_mn) / p.n_tiles;
+                const int cbeg = ks * p.kc_split * chunk_elems;
                 int w0[2], h0[2], n0[2];
                 box_origin(p, mt, 0, rank, w0[0], h0[0], n0[0]);
                 box_origin(p, mt, p.mh - 1, rank, w0[1], h0[1], n0[1]);
                 if (p.halo) {
                     const int rows = p.mh + 2;
-                    for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
+                    for (int kc = 0, c0 = cbeg; kc < p.kc_split; ++kc, c0 += chunk_elems) {
                         for (int r = 0; r < rows; ++r) {
                             { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
                             if (elect_one_sync()) {
@@ -429,7 +435,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t bytes = (uint32_t)(p.mh * A_BOX_BYTES);
                     const int xs0 = w0[0] * p.stride - pad, ys0 = h0[0] * p.stride - pad;
                     const int xs1 = w0[1] * p.stride - pad, ys1 = h0[1] * p.stride - pad;
-                    for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
+                    for (int kc = 0, c0 = cbeg; kc < p.kc_split; ++kc, c0 += chunk_elems) {
                         for (int ty = 0; ty < p.ksize; ++ty) {
                             for (int tx = 0; tx < p.ksize; ++tx) {
                                 { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
@@ -464,8 +470,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t bfull = CTA2 ? mapa_u32(bar_b_full, 0) : bar_b_full;
             uint32_t slot = 0, phase = 0;
             for (int tile = cid; tile < p.total_tiles; tile += nct) {
-                const int nt0 = (tile % p.n_tiles) * p.n_tile + rank * rows_b;
-                for (int kc = 0, c0 = 0; kc < p.kchunks; ++kc, c0 += chunk_elems) {
+                const int nt0 = (tile % p.n_tiles) * p.n_tile + rank * rows_b;     // tiles_mn is a multiple of n_tiles
+                for (int kc = 0, c0 = (tile / p.tiles_mn) * p.kc_split * chunk_elems; kc < p.kc_split; ++kc, c0 += chunk_elems) {
                     for (int tap = 0; tap < p.taps; ++tap) {
                         { PROF_IF(8, lane == 0); mbar_wait(bar_b_empty + 8 * slot, phase ^ 1u); }
                         if (elect_one_sync()) {
@@ -511,7 +517,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int it = 0;
             PROF_IF(0, lane == 0);
             if (p.prof && blockIdx.x == 0 && lane == 0) p.prof[10] = (unsigned long long)((p.total_tiles + gridDim.x - 1) / gridDim.x);
-            const int steps = p.kchunks * p.taps;
+            const int steps = p.kc_split * p.taps;
             for (int tile = cid; tile < p.total_tiles; tile += nct, ++it) {
                 const int as = p.acc_stages == 2 ? (it & 1) : 0;
                 const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
@@ -520,7 +526,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint32_t acc0 = tmem_base + (uint32_t)(as * p.mh * p.acc_stride);
                 const uint32_t acc1 = acc0 + (uint32_t)p.acc_stride;
                 if (p.halo) {
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int kc = 0; kc < p.kc_split; ++kc) {
                         // claim the mh+2 row slots of this chunk (addresses + the parity to wait for)
                         uint32_t row_addr[4], row_bar[4], row_par[4];
 #pragma unroll
@@ -599,6 +605,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
             }
         }
+        hl_pdl_trigger_late();     // only the last epilogue is left: let the next kernel's CTAs move in
     } else {
         // ---------------------------------- epilogue ----------------------------------
         // Two independent warpgroups take alternate 32-column chunks (each with its own staging ring,
@@ -632,7 +639,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const bool mine = (int)(l_qn & (EPI_GROUPS - 1)) == eg;
                 if (mine) {
                     int w0, h0, n0;
-                    box_origin(p, l_tile / p.n_tiles, l_half, rank, w0, h0, n0);
+                    box_origin(p, (l_tile % p.tiles_mn) / p.n_tiles, l_half, rank, w0, h0, n0);
                     mbar_expect_tx(bar_r + 8 * l_b, STAGE_BUF_BYTES);
                     tma_load_4d(smem_g + l_b * STAGE_BUF_BYTES, &tmR, bar_r + 8 * l_b, nt0 + l_cc * 32, w0, h0, n0);
                     if (++l_b == nbuf) l_b = 0;
@@ -666,7 +673,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int as = p.acc_stages == 2 ? (it & 1) : 0;
             const uint32_t aph = (uint32_t)(p.acc_stages == 2 ? (it >> 1) : it) & 1u;
             const int nt0 = (tile % p.n_tiles) * p.n_tile;
-            const int mt = tile / p.n_tiles;
+            const int ks = tile / p.tiles_mn;
+            const int mt = (tile - ks * p.tiles_mn) / p.n_tiles;
             { PROF_IF(4, pt); mbar_wait(bar_t_full + 8 * as, aph); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int half = 0; half < p.mh; ++half) {
@@ -695,7 +703,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (!p.y_f16) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 bz = __ldg(bias4 + j);
+                            const float4 bz = p.bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
                                                    v[4 * j + 3] + bz.w);
                             const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
@@ -715,7 +723,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // arithmetic, then one rounding; staged as [128 rows][64 B] in the SWIZZLE_64B pattern
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 bz = __ldg(bias4 + j);
+                            const float4 bz = p.bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             v[4 * j] += bz.x; v[4 * j + 1] += bz.y; v[4 * j + 2] += bz.z; v[4 * j + 3] += bz.w;
                             if (p.has_res) {
                                 float4 r;
@@ -745,7 +753,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
-                        tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0);
+                        tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0 + ks * p.split_b);
                         bulk_commit();
                         if (p.has_res) {
                             { PROF_IF(9, eg == 0); bulk_wait_read<1>(); }   // previous store drained -> refill its buffer
@@ -803,6 +811,75 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                          "r"((uint32_t)p.tmem_cols)
                          : "memory");
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-K second pass.  The 8^2 / 16^2 layers have M = 256 / 1024 GEMM rows: 24-48 CTAs each streaming
+// 100+ operand stages from L2 at the per-SM rate while 100 SMs idle.  With a workspace registered
+// (hl_conv_set_workspace) the K loop is cut into S slices run by S x as many CTAs, every slice stores its
+// fp32 partial tile into ws[s][B*H*W][cout_pad], and this kernel adds the slices in a FIXED order
+// (deterministic), then bias, residual, the per-channel GroupNorm statistics and the output rounding
+// exactly as the one-pass epilogue does.  One thread = 4 channels x `pix` pixels of one sample.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_splitk_reduce(const float *__restrict__ ws, int S, int64_t slice, int ldw,
+                                                      const float *__restrict__ bias,
+                                                      const float *__restrict__ res, int ldr, void *__restrict__ y,
+                                                      int y_f16, int ldy, double *__restrict__ stats, int stats_ld,
+                                                      int HW, int Cout, int pix) {
+    hl_pdl_enter();
+    const int cq = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cq * 4 >= Cout) return;
+    const int b = blockIdx.z, p0 = blockIdx.y * pix;
+    const int p1 = min(HW, p0 + pix);
+    const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias) + cq);
+    double sm[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+    for (int pp = p0; pp < p1; ++pp) {
+        const int64_t m = (int64_t)b * HW + pp;
+        const float *src = ws + m * ldw + 4 * cq;
+        float4 a = *reinterpret_cast<const float4 *>(src);
+        for (int k = 1; k < S; ++k) {
+            const float4 t = *reinterpret_cast<const float4 *>(src + k * slice);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
+        if (res) {
+            const float4 r = *reinterpret_cast<const float4 *>(res + m * ldr + 4 * cq);
+            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        }
+        if (y_f16) {
+            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+            uint2 w;
+            w.x = *reinterpret_cast<const uint32_t *>(&h0);
+            w.y = *reinterpret_cast<const uint32_t *>(&h1);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + 4 * cq) = w;
+        } else {
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + m * ldy + 4 * cq) = a;
+        }
+        if (stats) {
+            sm[0] += a.x; sm[1] += a.y; sm[2] += a.z; sm[3] += a.w;
+            sq[0] += (double)a.x * a.x; sq[1] += (double)a.y * a.y; sq[2] += (double)a.z * a.z; sq[3] += (double)a.w * a.w;
+        }
+    }
+    if (stats) {
+        double *dst = stats + ((size_t)b * stats_ld + 4 * cq) * 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            atomicAdd(dst + 2 * c, sm[c]);
+            atomicAdd(dst + 2 * c + 1, sq[c]);
+        }
+    }
+}
+
+// partial-sum workspaces, one per stream that issues split-K convolutions (two streams run concurrently)
+struct Workspace { cudaStream_t stream; float *ptr; size_t bytes; };
+Workspace g_ws[8];
+int g_n_ws = 0;
+int g_tune_split = -1;      // -1 automatic, 0 off, > 0 forced number of K slices (when it divides the chunk count)
+
+const Workspace *find_ws(cudaStream_t st) {
+    for (int i = 0; i < g_n_ws; ++i)
+        if (g_ws[i].stream == st && g_ws[i].ptr) return &g_ws[i];
+    return nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1008,6 +1085,10 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
         pl->grid = p.total_tiles < sms ? p.total_tiles : sms;
     }
     (void)want_stats;
+    p.ksplit = 1;
+    p.kc_split = p.kchunks;
+    p.tiles_mn = p.total_tiles;
+    p.split_b = 0;
     return true;
 }
 
@@ -1034,6 +1115,34 @@ extern "C" int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2) {
     g_tune_stages = max_stages;
     g_tune_nbuf = nbuf;
     g_tune_cta2 = cta2;
+    return HL_OK;
+}
+
+extern "C" int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    HL_CHECK_ARG(((uintptr_t)ws & 15) == 0 && bytes >= 0);
+    for (int i = 0; i < g_n_ws; ++i)
+        if (g_ws[i].stream == st) {
+            g_ws[i].ptr = (float *)ws;
+            g_ws[i].bytes = ws ? (size_t)bytes : 0;
+            return HL_OK;
+        }
+    if (!ws) return HL_OK;
+    for (int i = 0; i < g_n_ws; ++i)
+        if (!g_ws[i].ptr) {                      // reuse an unregistered slot
+            g_ws[i] = {st, (float *)ws, (size_t)bytes};
+            return HL_OK;
+        }
+    if (g_n_ws == 8) {
+        hl_set_error("hl_conv_set_workspace: more than 8 streams registered");
+        return HL_E_INVALID;
+    }
+    g_ws[g_n_ws++] = {st, (float *)ws, (size_t)bytes};
+    return HL_OK;
+}
+
+extern "C" int hl_conv_set_split(int ksplit) {
+    g_tune_split = ksplit;
     return HL_OK;
 }
 
@@ -1081,7 +1190,44 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     p.bias = bias;
     p.y_f16 = y_f16;
     HL_CHECK_ARG(!(y_f16 && stats));
-    const bool epi_stats = plan_epi_stats(pl, stats != nullptr);
+    bool epi_stats = plan_epi_stats(pl, stats != nullptr);
+
+    // split-K (see k_splitk_reduce): 3x3 layers whose whole grid is under half a wave
+    int S = 1;
+    const Workspace *wsp = find_ws(stream);
+    if (wsp && g_tune_split != 0 && Cout % 4 == 0 && B % pl.t.bn == 0 && p.kchunks >= 2) {
+        const int sms = hl_num_sms();
+        const size_t slice_bytes = (size_t)B * H * W * pl.cout_pad * sizeof(float);
+        auto fits = [&](int s) { return p.kchunks % s == 0 && (size_t)s * slice_bytes <= wsp->bytes; };
+        if (g_tune_split > 1) {
+            if (fits(g_tune_split)) S = g_tune_split;
+        } else if (ksize == 3 && 2 * pl.grid <= sms) {
+            for (int s = 8; s >= 2; --s)
+                if (fits(s) && pl.grid * s <= sms && (p.kchunks / s) * p.taps >= 12) { S = s; break; }
+        }
+    }
+    const void *y_final = y;
+    const int ldy_final = ldy, yf16_final = y_f16;
+    if (S > 1) {
+        p.ksplit = S;
+        p.kc_split = p.kchunks / S;
+        p.split_b = B;
+        p.total_tiles = p.tiles_mn * S;
+        const int sms = hl_num_sms();
+        if (p.pair == 2) {
+            const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+            pl.grid = 2 * clusters;
+        } else {
+            pl.grid = p.total_tiles < sms ? p.total_tiles : sms;
+        }
+        p.bias = nullptr;          // bias, residual, statistics and rounding move to the second pass
+        p.has_res = 0;
+        p.y_f16 = 0;
+        epi_stats = false;
+        y = wsp->ptr;
+        ldy = pl.cout_pad;
+        y_f16 = 0;
+    }
     if (epi_stats) {
         p.stats = stats;
         p.stats_ld = stats_ld;
@@ -1128,8 +1274,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         const bool f16 = !which && y_f16;
         const int esz_o = f16 ? 2 : 4;
         CUtensorMap *tm = which ? &tmR : &tmY;
-        if (!ptr) { *tm = tmY; continue; }
-        cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        if (!ptr || (which && S > 1)) { *tm = tmY; continue; }
+        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : Cout), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * S};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
         cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
         if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
@@ -1157,18 +1303,28 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = pl.smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = hl_pdl_attr(attr, 1);
         HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, tmA, tmB, tmY, tmR, p));
     } else {
-        k_conv_tc<false><<<pl.grid, NUM_THREADS, pl.smem, stream>>>(tmA, tmB, tmY, tmR, p);
+        HL_CHECK_CUDA(hl_launch(k_conv_tc<false>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, p));
     }
     HL_CHECK_LAUNCH();
+    if (S > 1) {
+        const int HW = H * W;
+        int pix = HW / 8;
+        if (pix < 8) pix = 8;
+        dim3 grid(hl_cdiv(Cout / 4, 64), hl_cdiv(HW, pix), B);
+        HL_CHECK_CUDA(hl_launch(k_splitk_reduce, grid, dim3(64), 0, stream, (const float *)wsp->ptr, S,
+                                (int64_t)B * HW * pl.cout_pad, pl.cout_pad, bias, residual, ldr, (void *)y_final,
+                                yf16_final, ldy_final, stats, stats_ld, HW, Cout, pix));
+        return HL_OK;
+    }
     if (stats && !epi_stats) return hl_gn_stats_launch((const float *)y, ldy, B, H * W, Cout, stats, stats_ld, stream);
     return HL_OK;
 }

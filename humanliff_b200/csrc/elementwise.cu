@@ -82,6 +82,7 @@ static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8)
 __global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__restrict__ src2,
                                void *__restrict__ dst, int dst_dtype, int C, int HW, int ld, int round_tf32,
                                int64_t n_tiles, int tiles_per_img) {
+    hl_pdl_enter();
     __shared__ float tile[32][33];
     for (int64_t tidx = blockIdx.x; tidx < n_tiles; tidx += gridDim.x) {
         int b = (int)(tidx / tiles_per_img);
@@ -119,14 +120,15 @@ extern "C" int hl_nchw_to_nhwc(const float *src, const float *src2, void *dst, i
     int tiles_per_img = hl_cdiv(HW, 32);
     int64_t n_tiles = (int64_t)B * tiles_per_img;
     dim3 blk(32, 8);
-    k_nchw_to_nhwc<<<grid_for(n_tiles, 1, 16), blk, 0, (cudaStream_t)stream>>>(
-        src, src2, dst, dst_dtype, C, HW, ld, round_tf32, n_tiles, tiles_per_img);
+    HL_CHECK_CUDA(hl_launch(k_nchw_to_nhwc, dim3(grid_for(n_tiles, 1, 16)), dim3(blk), 0, (cudaStream_t)stream, 
+        src, src2, dst, dst_dtype, C, HW, ld, round_tf32, n_tiles, tiles_per_img));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 __global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, float *__restrict__ dst,
                                int C, int HW, int64_t n_tiles, int tiles_per_img) {
+    hl_pdl_enter();
     __shared__ float tile[32][33];
     for (int64_t tidx = blockIdx.x; tidx < n_tiles; tidx += gridDim.x) {
         int b = (int)(tidx / tiles_per_img);
@@ -152,8 +154,8 @@ extern "C" int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int 
     int tiles_per_img = hl_cdiv(HW, 32);
     int64_t n_tiles = (int64_t)B * tiles_per_img;
     dim3 blk(32, 8);
-    k_nhwc_to_nchw<<<grid_for(n_tiles, 1, 16), blk, 0, (cudaStream_t)stream>>>(
-        src, ld, dst, C, HW, n_tiles, tiles_per_img);
+    HL_CHECK_CUDA(hl_launch(k_nhwc_to_nchw, dim3(grid_for(n_tiles, 1, 16)), dim3(blk), 0, (cudaStream_t)stream, 
+        src, ld, dst, C, HW, n_tiles, tiles_per_img));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -164,6 +166,7 @@ extern "C" int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int 
 __global__ void k_concat_add(const float *__restrict__ a, int lda, int C1,
                              const float *__restrict__ b, int ldb, const float *__restrict__ c,
                              int ldc, int C2, float *__restrict__ dst, int ldd, int64_t npix) {
+    hl_pdl_enter();
     int q1 = C1 >> 2, q = (C1 + C2) >> 2;
     int64_t total = npix * q;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -191,14 +194,15 @@ extern "C" int hl_concat_add(const float *a, int lda, int C1, const float *b, in
     HL_CHECK_ARG(a && b && dst && npix > 0 && C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 &&
                  ldb % 4 == 0 && ldd % 4 == 0 && (!c || ldc % 4 == 0) && ldd >= C1 + C2);
     int64_t total = npix * ((C1 + C2) / 4);
-    k_concat_add<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a, lda, C1, b, ldb, c,
-                                                                             ldc, C2, dst, ldd, npix);
+    HL_CHECK_CUDA(hl_launch(k_concat_add, dim3(grid_for(total, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, a, lda, C1, b, ldb, c,
+                                                                             ldc, C2, dst, ldd, npix));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 __global__ void k_upsample2x(const float *__restrict__ src, int lds, void *__restrict__ dst, int dst_dtype,
                              int ldd, int H, int W, int C, int round_tf32, int64_t total) {
+    hl_pdl_enter();
     int q = C >> 2, W2 = 2 * W, H2 = 2 * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -218,14 +222,15 @@ extern "C" int hl_upsample2x(const float *src, int lds, void *dst, int dst_dtype
                              int C, int round_tf32, void *stream) {
     HL_CHECK_ARG(src && dst && B > 0 && H > 0 && W > 0 && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0);
     int64_t total = (int64_t)B * 4 * H * W * (C / 4);
-    k_upsample2x<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, dst_dtype, ldd, H,
-                                                                             W, C, round_tf32, total);
+    HL_CHECK_CUDA(hl_launch(k_upsample2x, dim3(grid_for(total, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, src, lds, dst, dst_dtype, ldd, H,
+                                                                             W, C, round_tf32, total));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 __global__ void k_cast_operand(const float *__restrict__ src, int lds, void *__restrict__ dst, int dst_dtype,
                                int ldd, int C, int64_t npix, int round_tf32) {
+    hl_pdl_enter();
     int q = C >> 2;
     int64_t total = npix * q;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -241,8 +246,8 @@ extern "C" int hl_cast_operand(const float *src, int lds, void *dst, int dst_dty
                                int64_t npix, int round_tf32, void *stream) {
     HL_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && npix > 0);
     HL_CHECK_ARG(dst_dtype == HL_DT_F32 || dst_dtype == HL_DT_F16);
-    k_cast_operand<<<grid_for(npix * (C / 4), 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, dst_dtype,
-                                                                                        ldd, C, npix, round_tf32);
+    HL_CHECK_CUDA(hl_launch(k_cast_operand, dim3(grid_for(npix * (C / 4), 256 * 4)), dim3(256), 0, (cudaStream_t)stream, src, lds, dst, dst_dtype,
+                                                                                        ldd, C, npix, round_tf32));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -250,14 +255,26 @@ extern "C" int hl_cast_operand(const float *src, int lds, void *dst, int dst_dty
 extern "C" int hl_zero(void *ptr, int64_t bytes, void *stream) {
     HL_CHECK_ARG(ptr && bytes >= 0);
     HL_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+    g_hl_pdl_skip = 1;          // a memset node is not a programmatic-launch primary
     return HL_OK;
 }
+
+int g_hl_pdl = 0, g_hl_pdl_skip = 0;
+long long g_hl_launches = 0;
+extern "C" int64_t hl_launch_count(void) { return (int64_t)g_hl_launches; }
+extern "C" int hl_set_pdl(int on) {
+    const int prev = g_hl_pdl;
+    if (on >= 0) g_hl_pdl = on ? 1 : 0;
+    return prev;
+}
+extern "C" void hl_pdl_barrier(void) { g_hl_pdl_skip = 1; }
 
 // ------------------------------------------------------------------------------------------
 // embeddings
 // ------------------------------------------------------------------------------------------
 __global__ void k_timestep_embedding(const float *__restrict__ t, const float *__restrict__ freqs, int B,
                                      int dim, float *__restrict__ out) {
+    hl_pdl_enter();
     int half = dim / 2;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -272,7 +289,7 @@ extern "C" int hl_timestep_embedding(const float *t, const float *freqs, int B, 
                                      void *stream) {
     HL_CHECK_ARG(t && freqs && out && B > 0 && dim >= 2);
     int n = B * (dim / 2);
-    k_timestep_embedding<<<hl_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(t, freqs, B, dim, out);
+    HL_CHECK_CUDA(hl_launch(k_timestep_embedding, dim3(hl_cdiv(n, 128)), dim3(128), 0, (cudaStream_t)stream, t, freqs, B, dim, out));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -284,6 +301,7 @@ __global__ void k_linear_small(const float *__restrict__ x, const float *__restr
                                const float *__restrict__ bias, float *__restrict__ y, int B, int in_f,
                                int out_f, int silu_in, const float *__restrict__ add_table,
                                const int64_t *__restrict__ add_idx) {
+    hl_pdl_enter();
     extern __shared__ float xs[];  // [LIN_ROWS][in_f]
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int b0 = 0; b0 < B; b0 += LIN_ROWS) {
@@ -331,8 +349,8 @@ extern "C" int hl_linear_small(const float *x, const float *W, const float *bias
     int grid = hl_cdiv(out_f, warps);
     int cap = hl_num_sms() * 4;
     if (grid > cap) grid = cap;
-    k_linear_small<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(x, W, bias, y, B, in_f, out_f,
-                                                                    silu_in, add_table, add_idx);
+    HL_CHECK_CUDA(hl_launch(k_linear_small, dim3(grid), dim3(warps * 32), smem, (cudaStream_t)stream, x, W, bias, y, B, in_f, out_f,
+                                                                    silu_in, add_table, add_idx));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -349,6 +367,7 @@ extern "C" int hl_linear_small(const float *x, const float *W, const float *bias
 #define GN_MAX_C 2048
 __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int pix_per_block,
                            double *__restrict__ stats, int stats_ld) {
+    hl_pdl_enter();
     __shared__ double s_sum[GN_MAX_C];   // fp64: atomics then commute to ~1e-16 -> reproducible statistics
     __shared__ double s_sq[GN_MAX_C];
     int b = blockIdx.y;
@@ -396,7 +415,7 @@ int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *st
     int min_ppb = lanes_p * 8;
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    k_gn_stats<<<grid, threads, 0, stream>>>(x, ldx, HW, C, pix_per_block, stats, stats_ld);
+    HL_CHECK_CUDA(hl_launch(k_gn_stats, dim3(grid), dim3(threads), 0, stream, x, ldx, HW, C, pix_per_block, stats, stats_ld));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -415,6 +434,7 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
                            const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
                            int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
                            int silu, int round_tf32, int pix_per_block, int oct) {
+    hl_pdl_enter();
     __shared__ float sA[GN_MAX_C];
     __shared__ float sB[GN_MAX_C];
     __shared__ float gmean[64], grstd[64];
@@ -548,9 +568,9 @@ extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int sta
     int threads = 256;
     if (oct_ok) threads = (256 / (C / 8)) * (C / 8);   // fast path: whole channel octets
     if (threads < 64) threads = 256;
-    k_gn_apply<<<grid, threads, 0, (cudaStream_t)stream>>>(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
+    HL_CHECK_CUDA(hl_launch(k_gn_apply, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
                                                        y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu,
-                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0);
+                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -563,6 +583,7 @@ __global__ void k_ddpm_step(const float *__restrict__ x, const float *__restrict
                             const float *__restrict__ sigma, const int64_t *__restrict__ t,
                             float *__restrict__ sample, float *__restrict__ x0out, int64_t n4,
                             int clip) {
+    hl_pdl_enter();
     int b = blockIdx.y;
     int64_t ti = t[b];
     float c0 = coef[ti * 4 + 0], c1 = coef[ti * 4 + 1], c2 = coef[ti * 4 + 2], c3 = coef[ti * 4 + 3];
@@ -603,8 +624,8 @@ extern "C" int hl_ddpm_step(const float *x, const float *eps, const float *noise
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
     dim3 grid(gx, B);
-    k_ddpm_step<<<grid, 256, 0, (cudaStream_t)stream>>>(x, eps, noise, coef, sigma, t, sample,
-                                                        pred_xstart, n4, clip);
+    HL_CHECK_CUDA(hl_launch(k_ddpm_step, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, eps, noise, coef, sigma, t, sample,
+                                                        pred_xstart, n4, clip));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -617,6 +638,7 @@ __global__ void k_ddim_step(const float *__restrict__ x, const float *__restrict
                             const float *__restrict__ noise, const float *__restrict__ coef,
                             const float *__restrict__ sigma, const int64_t *__restrict__ t,
                             float *__restrict__ sample, float *__restrict__ x0out, int64_t n4, int clip) {
+    hl_pdl_enter();
     int b = blockIdx.y;
     int64_t ti = t[b];
     const float c0 = coef[ti * 4 + 0], c1 = coef[ti * 4 + 1], ca = coef[ti * 4 + 2], cb = coef[ti * 4 + 3];
@@ -658,8 +680,8 @@ extern "C" int hl_ddim_step(const float *x, const float *eps, const float *noise
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
     dim3 grid(gx, B);
-    k_ddim_step<<<grid, 256, 0, (cudaStream_t)stream>>>(x, eps, noise, coef, sigma, t, sample, pred_xstart, n4,
-                                                        clip);
+    HL_CHECK_CUDA(hl_launch(k_ddim_step, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, eps, noise, coef, sigma, t, sample, pred_xstart, n4,
+                                                        clip));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

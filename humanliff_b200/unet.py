@@ -22,6 +22,7 @@ Internals
     single streaming GEMV per step (unet.py:151-157,200).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -136,6 +137,8 @@ class UNetModel(nn.Module):
         self._plans = {}
         self.use_cuda_graph = True
         self.concurrent_encoders = True     # ControlNet encoder on a side stream (see _StepPlan._build)
+        self.split_k = os.environ.get("HL_SPLITK", "1") != "0"   # split-K for the 8^2 / 16^2 3x3 layers (hl_conv_set_workspace)
+        self.programmatic_launch = os.environ.get("HL_PDL", "0") == "1"    # PDL: each kernel's prologue overlaps its predecessor's tail (hl_set_pdl)
 
     # ------------------------------------------------------------------ architecture / parameters
     def _conv(self, name, cin, cout, k, stride=1, cin_pad=None):
@@ -334,6 +337,7 @@ class _Ref:
 
 class _StepPlan:
     """One UNet forward at a fixed (B, H, W): workspace + flat launch list (+ its CUDA graph)."""
+    SPLITK_BYTES = 16 << 20      # >= S * B*H*W*Cout*4 of every layer that splits (8^2: 4.7 MB, 16^2: 9.4 MB at B = 4)
 
     def __init__(self, model, device, B, H, W):
         self.m, self.device, self.B, self.H, self.W = model, device, B, H, W
@@ -345,6 +349,9 @@ class _StepPlan:
         self.n_events = 0
         self.graph = None
         self.side = None
+        self.splitk_ws = None
+        self.kernels_per_run = 0
+        self.SPLITK_BYTES = (4 << 20) * max(4, B)
         self.events = None
         self.runs = 0
         self._stats_off = 0
@@ -663,17 +670,37 @@ class _StepPlan:
             self.side = torch.cuda.Stream(self.device)
             self.events = [torch.cuda.Event() for _ in range(self.n_events)]
         streams = (main.cuda_stream, self.side.cuda_stream if self.side is not None else main.cuda_stream)
-        for name, args, br in self.calls:
-            if name[0] != "#":
-                call(name, *args, streams[br])
-            elif name == "#fork":
-                self.side.wait_stream(main)
-            elif name == "#join":
-                main.wait_stream(self.side)
-            elif name == "#signal":
-                self.events[args[0]].record(main)
-            elif name == "#wait":
-                self.side.wait_event(self.events[args[0]])
+        lib = _lib.load()
+        prev = lib.hl_set_pdl(1 if self.m.programmatic_launch else 0)
+        serialize = [True, True]        # first launch of a stream / after a cross-stream wait: a normal launch
+        # split-K partial sums of the 8^2 / 16^2 layers: one workspace per concurrently running stream
+        if self.splitk_ws is None:
+            n = 2 if self.side is not None else 1
+            self.splitk_ws = [torch.empty(self.SPLITK_BYTES // 4, device=self.device) for _ in range(n)]
+        for ws, st in zip(self.splitk_ws if self.m.split_k else [], streams):
+            _lib.check(lib.hl_conv_set_workspace(_ptr(ws), self.SPLITK_BYTES, st), "hl_conv_set_workspace")
+        try:
+            for name, args, br in self.calls:
+                if name[0] != "#":
+                    if serialize[br]:
+                        lib.hl_pdl_barrier()
+                        serialize[br] = False
+                    call(name, *args, streams[br])
+                elif name == "#fork":
+                    self.side.wait_stream(main)
+                    serialize[1] = True
+                elif name == "#join":
+                    main.wait_stream(self.side)
+                    serialize[0] = True
+                elif name == "#signal":
+                    self.events[args[0]].record(main)
+                elif name == "#wait":
+                    self.side.wait_event(self.events[args[0]])
+                    serialize[1] = True
+        finally:
+            lib.hl_set_pdl(prev)
+            for st in set(streams):
+                lib.hl_conv_set_workspace(None, 0, st)     # the registry must not outlive this plan's memory
 
     def run(self, x, timesteps, x_cond, y):
         m = self.m
@@ -684,7 +711,11 @@ class _StepPlan:
         if m.num_classes is not None:
             self.y_in.copy_(y)
         if not m.use_cuda_graph or self.runs == 0:
+            lib, n0 = _lib.load(), _lib.launch_count
+            k0 = lib.hl_launch_count()
             self._launch_all()                       # first run is eager: function attributes, driver entry points
+            self.kernels_per_run = lib.hl_launch_count() - k0     # a split-K conv is two kernels
+            _lib.launch_count = n0 + self.kernels_per_run
         else:
             if self.graph is None:
                 n0 = _lib.launch_count
@@ -700,4 +731,6 @@ class _StepPlan:
 
     @property
     def n_launches(self):
+        if self.kernels_per_run:
+            return self.kernels_per_run
         return sum(1 for name, _, _ in self.calls if name[0] != "#")

@@ -56,6 +56,15 @@ int hl_conv_set_tuning(int mh, int n_tile, int halo, int epi_stats, int base_off
 /* More experiment knobs: cap on the smem pipeline depth, epilogue staging buffers per group (2|4),
  * CTA-pair MMA (cta_group::2: 0 off, 1 on where legal); -1 = automatic.                           */
 int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2);
+/* Split-K for the low-resolution 3x3 layers (8^2, 16^2: a grid of 24-48 CTAs streaming a 100+ stage K loop):
+ * with a partial-sum workspace registered for `stream` (caller-owned device memory, >= S * B*H*W*cout_pad*4
+ * bytes for the layers that should split; NULL unregisters) hl_conv2d cuts K into S slices over S x the CTAs
+ * and a second kernel adds the slices in a fixed order (deterministic) with bias / residual / statistics /
+ * rounding.  Streams that run concurrently need distinct workspaces.  hl_conv_set_split: -1 automatic
+ * (default), 0 off, n > 1 forces n slices wherever n divides the K chunk count (tests).                     */
+int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream);
+int hl_conv_set_split(int ksplit);
+
 /* Experiment hook: device array of >= 16 uint64 that CTA 0 of every following tcgen05 conv adds its
  * blocked-cycle counters to (0 total, 1 A-full wait, 2 TMEM-empty wait, 3 B-full wait, 4 TMEM-full
  * wait, 5 residual wait, 6 epilogue barrier, 7 A-empty wait, 8 B-empty wait, 9 store-drain wait,
@@ -134,6 +143,19 @@ int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float 
               const float *residual /*nullable*/, int ldr, void *y, int ldy, double *stats /*nullable*/,
               int stats_ld, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
               void *stream);
+
+/* ---- launch mode ------------------------------------------------------------------------------ */
+
+/* Programmatic dependent launch for every UNet-step kernel of this library (default off): with on = 1 each
+ * launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs are scheduled while
+ * the previous kernel of the stream drains and block in griddepcontrol.wait until it has completed (stream
+ * order semantics are unchanged; works eagerly and under stream capture).  on < 0 only queries.  Returns the
+ * previous mode.  hl_pdl_barrier(): the NEXT launch is issued as a normal, fully serialized one (used after
+ * cross-stream event waits).                                                                          */
+int hl_set_pdl(int on);
+void hl_pdl_barrier(void);
+/* Kernels launched (or recorded into a stream capture) by the UNet-step entry points since load.    */
+int64_t hl_launch_count(void);
 
 /* ---- attention (unet.py:255-274) ------------------------------------------------------------ */
 

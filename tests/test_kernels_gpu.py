@@ -161,7 +161,7 @@ def _operand(t, mode):
 
 
 def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residual=True, stats=False, cin_pad=None,
-               seed=0, ldy=None, tuning=None, tuning2=None, out_f16=False):
+               seed=0, ldy=None, tuning=None, tuning2=None, out_f16=False, split=None):
     """Runs hl_conv2d on seeded inputs; returns (y NCHW cpu, fp32 reference, reference on the ROUNDED operands,
     stats cpu or None)."""
     from humanliff_b200.unet import pack_conv
@@ -199,6 +199,10 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
         lib.hl_conv_set_tuning(*tuning)
     if tuning2 is not None:
         lib.hl_conv_set_tuning2(*tuning2)
+    if split is not None:                                    # split-K: partial-sum workspace on the launching stream
+        ws = torch.full((64 << 20,), float("nan"), device=dev)
+        _call("hl_conv_set_workspace", ws.data_ptr(), ws.numel() * 4, _stream())
+        lib.hl_conv_set_split(split)
     try:
         _call("hl_conv2d", xd.data_ptr(), code, cin_pad, wpk.data_ptr(), bpk.data_ptr(),
               rd.data_ptr() if residual else None, Cout, y.data_ptr(), ldy, st.data_ptr() if stats else None, ldy,
@@ -207,6 +211,9 @@ def _conv_case(dev, B, H, W, Cin, Cout, k, stride, mode="fp32", flags=0, residua
     finally:
         lib.hl_conv_set_tuning(-1, -1, -1, -1, -1)
         lib.hl_conv_set_tuning2(-1, -1, -1)
+        if split is not None:
+            lib.hl_conv_set_split(-1)
+            lib.hl_conv_set_workspace(None, 0, _stream())
     return y[..., :Cout].permute(0, 3, 1, 2).float().cpu(), ref, ref_r, (st.cpu().reshape(B, ldy, 2) if stats else None)
 
 
@@ -306,6 +313,32 @@ def test_conv_fp16_output(dev, shape, residual, cta2):
     y16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
     assert not torch.isnan(y16).any()
     assert torch.equal(y16, y32.half().float())
+
+
+@pytest.mark.parametrize("shape,split", [
+    ((4, 8, 8, 768, 768, 3, 1), -1),      # automatic: 24 CTAs -> 6 slices
+    ((4, 16, 16, 768, 768, 3, 1), -1),    # automatic: 48 CTAs -> 3 slices
+    ((4, 16, 16, 1536, 768, 3, 1), -1),
+    ((4, 32, 32, 768, 768, 3, 2), -1),    # stride-2 Downsample conv onto 16^2
+    ((2, 16, 16, 384, 192, 1, 1), 3),     # forced: 1x1
+    ((3, 8, 8, 128, 64, 3, 1), 2),        # bn = 2 with B = 3: split refused (partial batch box), one-pass result
+    ((1, 128, 128, 192, 192, 3, 1), 3),   # forced on the HALO operand path
+    ((2, 32, 32, 384, 384, 3, 1), 2)])
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_conv_split_k(dev, shape, split, residual, cta2):
+    """K cut into slices over more CTAs + fixed-order second pass: same numbers as the one-pass kernel
+    (fp32 accumulation order differs -> 2e-5), statistics and fp16 output included."""
+    B, H, W, Cin, Cout, k, s = shape
+    kw = dict(mode="fp16", residual=residual, seed=13, tuning2=(-1, -1, cta2), split=split)
+    y, ref, ref_r, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, stats=True, **kw)
+    assert not torch.isnan(y).any()
+    assert rel_l2(y, ref_r) < 2e-5, rel_l2(y, ref_r)
+    _check_stats(st, y, Cout)
+    y2 = _conv_case(dev, B, H, W, Cin, Cout, k, s, stats=True, **kw)[0]
+    assert torch.equal(y, y2), "fixed-order reduction: bit-reproducible"
+    y16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
+    assert torch.equal(y16, y.half().float())
 
 
 def test_conv_tc_strided_output_and_input(dev):

@@ -140,7 +140,10 @@ def dominant_kernel_roofline(device, B, peaks, precision, reps=20):
             "bf16 burst figure -- TF32's dense peak is half of it")
     return {"kernel": "k_conv_tc (tcgen05 %s implicit-GEMM conv3x3 192->192 @256^2 + residual + GN statistics, B=%d)" % (kind, B),
             "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-            "frac": round(ach / peaks["bf16_burst"], 4), "traffic": None,
+            "frac": round(ach / peaks["bf16_burst"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
+            # (profiles/r1_conv_full_v10.md: 302.75 + 165.85 MB; only quoted for the shape / precision it was taken on)
+            "traffic": 468.6e6 if (B == 4 and precision == "fp16") else None, "traffic_unit": "bytes/launch",
             "peak_source": peaks["source"] + "; " + note,
             "ms_per_launch": round(ms, 4), "algorithmic_gflop_per_launch": round(flops / 1e9, 2),
             "algorithmic_hbm_mb_per_launch": round(bytes_alg / 1e6, 1),
@@ -310,6 +313,7 @@ def run_ours(args):
     # staging), the download of step i overlaps step i+1 -- all inside the timed region.
     h_out = [torch.empty(shape).pin_memory() for _ in range(2)]
     copy_st = torch.cuda.Stream(device)
+    down_st = torch.cuda.Stream(device)                      # device -> host reads of finished samples
     stage = [[torch.empty(shape, device=device) for _ in range(3)] for _ in range(2)]
     up_done = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
@@ -324,8 +328,11 @@ def run_ours(args):
             up_done[s].record(copy_st)
 
     barrier()
+    d_out = [torch.empty(shape, device=device) for _ in range(2)]
+    down_done = [torch.cuda.Event() for _ in range(2)]
     for s_ in range(2):
         free[s_].record(st)
+        down_done[s_].record(st)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(st)
     copy_st.wait_event(e2)                                   # no upload starts before the timed region
@@ -338,8 +345,18 @@ def run_ours(args):
         t_dev.fill_(T - 1 - (i % T))
         out = diffusion.p_sample(model, stage[s_][0], stage[s_][1], t_dev, clip_denoised=True, model_kwargs={"y": y},
                                  noise=stage[s_][2])["sample"]
-        free[s_].record(st)
-        h_out[s_].copy_(out, non_blocking=True)
+        if args.e2e_download == "inline":
+            free[s_].record(st)
+            h_out[s_].copy_(out, non_blocking=True)
+        else:
+            st.wait_event(down_done[s_])                     # the download that last used this slot has finished
+            d_out[s_].copy_(out)                             # 28 MB device copy; frees `out` for the allocator
+            free[s_].record(st)
+            down_st.wait_event(free[s_])
+            with torch.cuda.stream(down_st):
+                h_out[s_].copy_(d_out[s_], non_blocking=True)    # overlaps step i+1
+                down_done[s_].record(down_st)
+    st.wait_stream(down_st)                                  # every download lands inside the timed region
     e3.record(st)
     barrier()
     ms2 = torch.tensor([e2.elapsed_time(e3)], device=device)
@@ -395,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32", "fp32"])
+    ap.add_argument("--e2e-download", default="overlap", choices=["overlap", "inline"],
+                    help="e2e: read each finished sample back on a copy stream (overlapping the next step) or in line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()

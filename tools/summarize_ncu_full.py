@@ -1,0 +1,31 @@
+"""Key metrics of one `ncu --set full` capture (first kernel in the report) as a markdown table.
+usage: python tools/summarize_ncu_full.py gpurun_out/conv_full_v10.ncu-rep > profiles/..."""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = [
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__time_duration.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "launch__block_size",
+    "launch__cluster_size", "launch__grid_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct",
+    "sm__cycles_elapsed.avg", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__mem_tensor_reads_op_utcmma_matrix_c.sum.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "sm__cycles_active.avg",
+    "smsp__cycles_active.avg", "gpc__cycles_elapsed.max", "sm__inst_executed.sum",
+]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+print("| metric | value | unit |\n|---|---|---|")
+name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
+for k in KEEP:
+    if k in hdr:
+        i = hdr.index(k)
+        print(f"| `{k}` | {vals[i]} | {units[i]} |")
+print(f"\nkernel: `{name}`")

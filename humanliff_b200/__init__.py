@@ -7,6 +7,7 @@ Public surface mirrors the reference:
     GaussianDiffusion, SpacedDiffusion, space_timesteps                                   (gaussian_diffusion.py, respace.py)
     Renderer, render                                                                      (renderer.py, run_nerf_batch.py)
     all_gather_samples                                                                    (triplane_sample_layered.py:211-219)
+    sample_layer, sample_all_layers                                                       (triplane_sample_layered.py:110-151,229-244)
 """
 from .diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType, SpacedDiffusion,
                         get_named_beta_schedule, space_timesteps)
@@ -15,8 +16,9 @@ from .factory import (create_gaussian_diffusion, create_model, create_model_and_
 from .unet import UNetModel
 from .renderer import Renderer, render
 from .dist import all_gather_samples, shard_batch
+from .layered import sample_all_layers, sample_layer
 
 __all__ = ["GaussianDiffusion", "SpacedDiffusion", "space_timesteps", "get_named_beta_schedule",
            "ModelMeanType", "ModelVarType", "LossType", "create_model_and_diffusion", "create_model",
            "create_gaussian_diffusion", "model_and_diffusion_defaults", "production_flags", "UNetModel",
-           "Renderer", "render", "all_gather_samples", "shard_batch"]
+           "Renderer", "render", "all_gather_samples", "shard_batch", "sample_layer", "sample_all_layers"]

@@ -85,8 +85,8 @@ def test_conv_full_size_spot_check(shape):
     # (2) checksum of checksums
     if stats:
         yy = out.double()
-        assert rel_l2(st[:, :Cout, 0], yy.sum((1, 2))) < 1e-9
-        assert rel_l2(st[:, :Cout, 1], (yy * yy).sum((1, 2))) < 1e-9
+        assert rel_l2(st[:, :Cout, 0], yy.sum((1, 2))) < 1e-5
+        assert rel_l2(st[:, :Cout, 1], (yy * yy).sum((1, 2))) < 1e-5
 
 
 @pytest.fixture(scope="module")

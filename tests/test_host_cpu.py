@@ -116,3 +116,22 @@ def test_step_plan_dataflow_by_cpu_interpretation(precision, tol):
     for rep in range(2):            # twice: the statistics arena must be re-zeroed by the plan itself
         eps = plan_emulator.run_plan(plan, g["x"], ts, g["x_cond"], g["y"])
         assert rel_l2(eps, g["eps_100"]) < tol
+
+
+def test_layer_handoff_files(tmp_path):
+    """.npz hand-off between clothing layers (triplane_sample_layered.py:131-132,229-244): arr_0 / arr_1 keys,
+    file naming, row window, lossless fp32 round trip."""
+    import numpy as np
+    from humanliff_b200.layered import LAYER_NAMES, layer_npz_path, load_layer_cond, save_layer_npz
+    assert LAYER_NAMES == ("person", "person_pant", "person_pant_shirt", "person_pant_shirt_shoes")
+    x = torch.randn(5, 27, 8, 8)
+    lab = torch.full((5,), 2, dtype=torch.int64)
+    p = layer_npz_path(str(tmp_path), 2, x.shape, "ema_0.9999_100000", start_id=7)
+    assert p.endswith("samples_person_pant_shirt_5x27x8x8_ema_0.9999_100000_start_id_7.npz")
+    save_layer_npz(p, x, lab)
+    z = np.load(p)
+    assert sorted(z.files) == ["arr_0", "arr_1"] and z["arr_1"].tolist() == [2] * 5
+    got = load_layer_cond(p, 1, 3, "cpu")
+    assert torch.equal(got, x[1:4])
+    with pytest.raises(ValueError):
+        load_layer_cond(p, 4, 2, "cpu")

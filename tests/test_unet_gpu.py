@@ -173,3 +173,47 @@ def test_ddim_loop_api():
         eps = unet_oracle.unet_forward(sd, img, ts, xc, y, num_heads=heads)
         img, _ = orc.ddim_posterior(img, eps, t, torch.zeros_like(img), eta=0.0)
     assert rel_l2(out, img) < 1e-4
+
+
+def test_layered_handoff(tmp_path):
+    """Layer-wise generation (triplane_sample_layered.py:110-151,229-244): layer k is
+    sampled with y = k and x_cond = the finished layer k-1.  (i) the in-process chain equals the oracle's chain,
+    (ii) the reference's .npz hand-off route (arr_0 / arr_1, one sample_layer call per file) is bit-identical to
+    keeping the tri-planes in HBM, (iii) file names follow the script."""
+    import numpy as np
+    from humanliff_b200 import factory, synth, sample_all_layers, sample_layer
+    from humanliff_b200.layered import layer_npz_path
+    from oracle.diffusion_oracle import DiffusionOracle
+    fname, flags, seed, heads = CASES["tiny"]
+    flags = dict(flags, timestep_respacing="3", precision="fp32")
+    model, diffusion = factory.create_model_and_diffusion(**flags)
+    sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=seed)
+    model.load_state_dict(sd)
+    model = model.to("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    B, L = 2, 3
+    xT = [torch.randn(B, 27, 32, 32, generator=g) for _ in range(L)]
+    zs = [{i: torch.randn(B, 27, 32, 32, generator=g) for i in range(3)} for _ in range(L)]
+    outs = sample_all_layers(model, diffusion, B, num_layers=L, image_size=32, noise=lambda k: xT[k].cuda(),
+                             step_noise=lambda k: (lambda i: zs[k][i].cuda()), out_dir=str(tmp_path), suffix="t")
+    orc = DiffusionOracle(1000, "3", num_heads=heads)
+    cond = torch.zeros(B, 27, 32, 32)
+    for k in range(L):
+        ref = orc.p_sample_loop(sd, xT[k], cond, torch.full((B,), k), lambda i: zs[k][i])
+        assert rel_l2(outs[k][0], ref) < 2e-4, (k, rel_l2(outs[k][0], ref))
+        assert outs[k][1].tolist() == [k] * B
+        cond = ref
+    # the reference's route: one invocation per layer, conditioned through the previous layer's file
+    prev = None
+    for k in range(L):
+        path = layer_npz_path(str(tmp_path), k, (B, 27, 32, 32), "t")
+        z = np.load(path)
+        assert z["arr_0"].dtype == np.float32 and z["arr_1"].tolist() == [k] * B
+        assert torch.equal(torch.from_numpy(z["arr_0"]), outs[k][0].cpu())
+        s, _ = sample_layer(model, diffusion, k, B, sample_npz=prev, image_size=32, noise=xT[k].cuda(),
+                            step_noise=lambda i: zs[k][i].cuda())
+        assert torch.equal(s, outs[k][0]), "disk hand-off and in-HBM hand-off must agree bit for bit"
+        prev = path
+    assert path.endswith("samples_person_pant_shirt_2x27x32x32_t_start_id_0.npz")
+    with pytest.raises(ValueError):
+        sample_layer(model, diffusion, 1, B, image_size=32)        # layers >= 1 need a condition

@@ -387,7 +387,7 @@ def run_ours(args):
                            "batch_per_gpu": B, "global_batch": B * world, "resolution": "27x256x256",
                            "parallelism": "dp%d (batch sharded, no data-path collective; one all-gather of finished samples)" % world,
                            "l2_policy": "per-step working set (>= 6 GB of activations + 1 GB of fp16 weights) exceeds the 126 MB L2",
-                           "execution": "one CUDA graph replay per UNet forward (%d C-ABI launches) + 1 posterior kernel" % (
+                           "execution": "one CUDA graph replay per UNet forward (%d kernels on two streams) + 1 posterior kernel" % (
                                launches // K - 1),
                            "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches,

@@ -329,13 +329,13 @@ __global__ void __launch_bounds__(128) k_attention_mma(const void *__restrict__ 
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile holds >= 1 valid key
-        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+        const float al0 = hl_ex2(m0 - mn0), al1 = hl_ex2(m1 - mn1);
         float sum0 = 0.f, sum1 = 0.f;
         uint32_t pa[4][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float p0 = exp2f(s[j][0] - mn0), p1 = exp2f(s[j][1] - mn0);
-            const float p2 = exp2f(s[j][2] - mn1), p3 = exp2f(s[j][3] - mn1);
+            const float p0 = hl_ex2(s[j][0] - mn0), p1 = hl_ex2(s[j][1] - mn0);
+            const float p2 = hl_ex2(s[j][2] - mn1), p3 = hl_ex2(s[j][3] - mn1);
             sum0 += p0 + p1;
             sum1 += p2 + p3;
             pa[j >> 1][(j & 1) * 2 + 0] = pack_h2(p0, p1);

@@ -46,10 +46,24 @@ __device__ __forceinline__ float hl_rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// MUFU ex2 / lg2 without the denormal-range fix-up sequence nvcc wraps around __expf / __logf / exp2f
+// (FSETP + 2 FMUL per call: measured 12 -> 6 instructions per softplus in the render MLP).  Flush-to-zero is exact
+// enough wherever the result feeds 1 + e^x or a value that is rounded to an 11-bit significand.
+__device__ __forceinline__ float hl_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float hl_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float hl_silu(float x) { return x / (1.0f + expf(-x)); }
 // SiLU for values that are about to be rounded to an 11-bit significand (fp16 / TF32 operands):
 // ex2.approx + rcp.approx, relative error ~2e-7, 3x fewer instructions than the exact form
-__device__ __forceinline__ float hl_silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float hl_silu_fast(float x) { return __fdividef(x, 1.0f + hl_ex2(-1.4426950408889634f * x)); }
 
 __device__ __forceinline__ float hl_warp_sum(float v) {
 #pragma unroll

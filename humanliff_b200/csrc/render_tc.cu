@@ -59,9 +59,11 @@ struct RenderArgs {
     unsigned long long *prof;   // optional: cycles of CTA 0 per phase (0 setup, 1 gather, 2 mlp, 3 resample+sort, 4 composite, 5 total)
 };
 
+// softplus(x) = max(x, 0) + ln(1 + e^-|x|): 6 instructions (FMUL, MUFU.EX2, FADD, MUFU.LG2, FMNMX, FFMA).  The
+// reference's threshold (x > 20 -> x) needs no select: there the log term is < 2.1e-9 and x + it rounds to x.
 __device__ __forceinline__ float softplus_fast(float x) {
-    float r = fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(x)));
-    return x > 20.f ? x : r;
+    const float l = hl_lg2(1.0f + hl_ex2(-1.4426950408889634f * fabsf(x)));
+    return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float softplus_acc(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 

@@ -137,6 +137,7 @@ class UNetModel(nn.Module):
         self._plans = {}
         self.use_cuda_graph = True
         self.concurrent_encoders = True     # ControlNet encoder on a side stream (see _StepPlan._build)
+        self.batch_split = int(os.environ.get("HL_BATCH_SPLIT", "1"))     # independent sub-batch chains in one graph (_SplitPlan)
         self.split_k = os.environ.get("HL_SPLITK", "1") != "0"   # split-K for the 8^2 / 16^2 3x3 layers (hl_conv_set_workspace)
         self.programmatic_launch = os.environ.get("HL_PDL", "0") == "1"    # PDL: each kernel's prologue overlaps its predecessor's tail (hl_set_pdl)
 
@@ -319,7 +320,11 @@ class UNetModel(nn.Module):
             key = (str(device), B, H, W)
             plan = self._plans.get(key)
             if plan is None:
-                plan = _StepPlan(self, device, B, H, W)
+                parts = self.batch_split
+                if parts > 1 and B % parts == 0 and B // parts >= 2:
+                    plan = _SplitPlan(self, device, B, H, W, parts)
+                else:
+                    plan = _StepPlan(self, device, B, H, W)
                 self._plans[key] = plan
             return plan.run(x, timesteps, x_cond, y)
 
@@ -702,14 +707,20 @@ class _StepPlan:
             for st in set(streams):
                 lib.hl_conv_set_workspace(None, 0, st)     # the registry must not outlive this plan's memory
 
-    def run(self, x, timesteps, x_cond, y):
-        m = self.m
+    def load_inputs(self, x, timesteps, x_cond, y):
         self.x_in.copy_(x)
         self.t_in.copy_(timesteps)
         if self.xc_in is not None:
             self.xc_in.copy_(x_cond)
-        if m.num_classes is not None:
+        if self.m.num_classes is not None:
             self.y_in.copy_(y)
+
+    def result(self):
+        return self.out.clone()
+
+    def run(self, x, timesteps, x_cond, y):
+        m = self.m
+        self.load_inputs(x, timesteps, x_cond, y)
         if not m.use_cuda_graph or self.runs == 0:
             lib, n0 = _lib.load(), _lib.launch_count
             k0 = lib.hl_launch_count()
@@ -727,10 +738,48 @@ class _StepPlan:
             self.graph.replay()
             _lib.launch_count += self.n_launches
         self.runs += 1
-        return self.out.clone()
+        return self.result()
 
     @property
     def n_launches(self):
         if self.kernels_per_run:
             return self.kernels_per_run
         return sum(1 for name, _, _ in self.calls if name[0] != "#")
+
+
+class _SplitPlan(_StepPlan):
+    """The batch cut into ``parts`` independent sub-batches, each with its own _StepPlan (workspace, statistics
+    arena, split-K workspaces), all launched inside ONE CUDA graph on separate streams.  Samples never interact
+    (GroupNorm is per sample), so the chains are independent for the whole forward: where one chain sits in a
+    low-resolution, latency-bound stretch (8^2 .. 32^2: a few dozen CTAs per kernel) the other chains' kernels
+    fill the idle SMs -- including the decoder, which has no ControlNet branch to overlap with."""
+
+    def __init__(self, model, device, B, H, W, parts):        # noqa: super().__init__ builds a plan; this only wraps
+        self.m, self.device, self.B, self.H, self.W = model, device, B, H, W
+        self.parts, self.b = parts, B // parts
+        self.subs = [_StepPlan(model, device, self.b, H, W) for _ in range(parts)]
+        self.streams = None
+        self.graph, self.runs, self.kernels_per_run = None, 0, 0
+        self.calls = [c for p in self.subs for c in p.calls]
+
+    def load_inputs(self, x, timesteps, x_cond, y):
+        b = self.b
+        timesteps = torch.as_tensor(timesteps, device=x.device)
+        for k, p in enumerate(self.subs):
+            sl = slice(k * b, (k + 1) * b)
+            p.load_inputs(x[sl], timesteps[sl], x_cond[sl] if x_cond is not None else None,
+                          y[sl] if y is not None else None)
+
+    def result(self):
+        return torch.cat([p.out for p in self.subs], 0)
+
+    def _launch_all(self):
+        main = torch.cuda.current_stream(self.device)
+        if self.streams is None:
+            self.streams = [torch.cuda.Stream(self.device) for _ in self.subs]
+        for p, s in zip(self.subs, self.streams):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                p._launch_all()
+        for s in self.streams:
+            main.wait_stream(s)

@@ -13,9 +13,10 @@ for l in open("gpurun_out/tc_timing.log"):
     try:
         d = json.loads(l)
         p = d.get("prof_kcycles", {})
-        print("%-40s %.4f ms %7.1f TF  hbm %5s | mma_wait_tmem %6.1f epi_wait_full %6.1f epi_wait_res %6.1f bar %5.1f / total %6.1f" % (
-            d["name"], d.get("ms", 0), d.get("tflops", 0), d.get("hbm_gbs"), p.get("mma_wait_tmem_empty", 0), p.get("epi_wait_tmem_full", 0),
-            p.get("epi_wait_res", 0), p.get("epi_barrier", 0), p.get("total", 0)))
+        print("%-34s %.4f ms %7.1f TF | mma waits A %5.1f B %5.1f tmem %5.1f | epi full %6.1f res %5.1f bar %5.1f | prod A %6.1f B %6.1f / total %6.1f" % (
+            d["name"], d.get("ms", 0), d.get("tflops", 0), p.get("mma_wait_A", 0), p.get("mma_wait_B", 0), p.get("mma_wait_tmem_empty", 0),
+            p.get("epi_wait_tmem_full", 0), p.get("epi_wait_res", 0), p.get("epi_barrier", 0), p.get("prodA_wait_empty", 0),
+            p.get("prodB_wait_empty", 0), p.get("total", 0)))
     except Exception:
         print(l.strip()[:200])
 PY

@@ -42,16 +42,13 @@ CASES = [
 
 TIMING = [
     # name, shape (B,H,W,Cin,Cout,k), tuning (mh,n,halo,epi_stats,base_off), tuning2 (max_stages, nbuf, cta2), residual, stats
-    ("3x3 192@256 res+stats default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
-    ("3x3 192@256 res+stats nbuf2", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, 2, -1), True, True),
-    ("3x3 192@256 res only default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, False),
-    ("3x3 192@256 stats only default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), False, True),
     ("3x3 192@256 plain default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), False, False),
+    ("3x3 192@256 plain stages4", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (4, -1, -1), False, False),
+    ("3x3 192@256 plain stages3", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (3, -1, -1), False, False),
+    ("3x3 192@256 plain tap", (4, 256, 256, 192, 192, 3), (-1, -1, 0, -1, -1), (-1, -1, -1), False, False),
+    ("3x3 192@256 res+stats default", (4, 256, 256, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
     ("3x3 384->192@256 stats", (4, 256, 256, 384, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), False, True),
-    ("1x1 192@256 res+stats default", (4, 256, 256, 192, 192, 1), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
     ("3x3 192@128 res+stats default", (4, 128, 128, 192, 192, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
-    ("3x3 384@64 res+stats default", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, -1, -1), True, True),
-    ("3x3 384@64 res+stats nbuf2", (4, 64, 64, 384, 384, 3), (-1, -1, -1, -1, -1), (-1, 2, -1), True, True),
 ]
 
 def run_case(idx):

@@ -217,3 +217,46 @@ def test_layered_handoff(tmp_path):
     assert path.endswith("samples_person_pant_shirt_2x27x32x32_t_start_id_0.npz")
     with pytest.raises(ValueError):
         sample_layer(model, diffusion, 1, B, image_size=32)        # layers >= 1 need a condition
+
+
+def test_optional_launch_modes_agree():
+    """Launch-mode options that are off by default (measured: no gain) must not change results:
+    programmatic dependent launch (hl_set_pdl), batch-split chains (_SplitPlan), split-K off."""
+    from humanliff_b200.unet import _SplitPlan, _StepPlan
+    dev = torch.device("cuda:0")
+    fname, flags, seed, heads = CASES["tiny"]
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(4, 27, 32, 32, generator=g).to(dev)
+    xc = (0.3 * torch.randn(4, 27, 32, 32, generator=g)).clamp(-1, 1).to(dev)
+    y = torch.tensor([0, 1, 2, 3], device=dev)
+    ts = torch.tensor([10, 400, 400, 999], device=dev)
+
+    def run(**attrs):
+        model, _, sd = model_state_dict(dict(flags, precision="fp16"), seed)
+        model.load_state_dict(sd)
+        model = model.to(dev).eval()
+        for k, v in attrs.items():
+            setattr(model, k, v)
+        outs = [model(x, ts, xc, y=y) for _ in range(3)]           # eager, capture + replay, replay
+        assert all(rel_l2(o, outs[0]) < 1e-6 for o in outs)
+        return outs[-1], next(iter(model._plans.values()))
+
+    base, plan = run()
+    assert type(plan) is _StepPlan
+    pdl, _ = run(programmatic_launch=True)
+    assert rel_l2(pdl, base) < 1e-6, "PDL changes scheduling only"
+    # a different accumulation order re-draws the fp16 rounding noise: agreement at the operand-rounding level
+    nosplit, _ = run(split_k=False)
+    assert rel_l2(nosplit, base) < 2e-3
+    halves, plan2 = run(batch_split=2)
+    assert type(plan2) is _SplitPlan and plan2.n_launches >= 2 * 100
+    assert rel_l2(halves, base) < 2e-3
+    # within the split plan a sample's result does not depend on which half it sits in
+    perm = torch.tensor([2, 3, 0, 1], device=dev)
+    model, _, sd = model_state_dict(dict(flags, precision="fp16"), seed)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    model.batch_split = 2
+    a = model(x, ts, xc, y=y)
+    b = model(x[perm], ts[perm], xc[perm], y=y[perm])
+    assert rel_l2(b, a[perm]) < 1e-6

@@ -18,7 +18,10 @@
  *     stream and every conv result are fp32; conv OPERANDS (the activated /
  *     normalised tensors a conv reads, and the packed weights) are HL_DT_F16 or
  *     HL_DT_F32 buffers -- the rounding to the operand type is the only place
- *     precision is given up (fp32 accumulation everywhere).
+ *     precision is given up (fp32 accumulation everywhere);
+ *   - process-wide settings (hl_conv_set_*, hl_set_pdl, the workspace registry, hl_launch_count) are
+ *     plain globals: one host thread per process drives the library, as in the reference's
+ *     one-process-per-GPU model.
  */
 #ifndef HUMANLIFF_B200_H
 #define HUMANLIFF_B200_H

@@ -524,6 +524,8 @@ class _StepPlan:
                 self.conv(layers[0]["c"], xin_ptr, m.cin_pad, None, out, H, W)
                 x = out
             else:
+                if i == 1 and controlnet_branch and self.concurrent:
+                    self.emit_sync("wait", self.film_event)                     # FiLM scale / shift of the ResBlocks
                 x = self.layers(layers, x, f"{tag}{i}", dst=dst)
             if controlnet_branch:
                 cname = f"input_blocks_proj_cond.{i}"
@@ -568,23 +570,6 @@ class _StepPlan:
         self.y_in = torch.zeros(B, device=dev, dtype=torch.int64)
         self.out = torch.empty(B, m.out_channels, H, W, device=dev)
 
-        # --- embeddings (unet.py:564,584-586; all ResBlock emb_layers in one GEMV) ---
-        temb, e1, emb = self.buf("temb", B * mc), self.buf("e1", B * ed), self.buf("emb", B * ed)
-        self.film = self.buf("film", B * m._film_rows)
-        self.emit("hl_zero", ("stats", 0), ("stats_bytes",))
-        self.emit("hl_timestep_embedding", _ptr(self.t_in), _ptr(m._freqs), B, mc, _ptr(temb))
-        self.emit("hl_linear_small", _ptr(temb), _ptr(m._small["time_embed.0.weight"]),
-                  _ptr(m._small["time_embed.0.bias"]), _ptr(e1), B, mc, ed, 0, None, None)
-        if m.num_classes is not None:
-            self.emit("hl_linear_small", _ptr(e1), _ptr(m._small["time_embed.2.weight"]),
-                      _ptr(m._small["time_embed.2.bias"]), _ptr(emb), B, ed, ed, 1,
-                      _ptr(m._small["label_emb.weight"]), _ptr(self.y_in))
-        else:
-            self.emit("hl_linear_small", _ptr(e1), _ptr(m._small["time_embed.2.weight"]),
-                      _ptr(m._small["time_embed.2.bias"]), _ptr(emb), B, ed, ed, 1, None, None)
-        self.emit("hl_linear_small", _ptr(emb), _ptr(m._film_w), _ptr(m._film_b), _ptr(self.film), B, ed,
-                  m._film_rows, 1, None, None)
-
         # --- concat buffers of the decoder: cat_j = [ h (hC) | skip (sC) ] at the skip's resolution ---
         nblk = len(m._enc)
         geo = []                       # per encoder block i: (C, H, W) of its output
@@ -609,6 +594,7 @@ class _StepPlan:
             self.cat_full[j] = _Ref(_ptr(t), ld, ld, sH, sW, st, ld)
             hC = layers[0]["cout"]
 
+        self.emit("hl_zero", ("stats", 0), ("stats_bytes",))
         xin = self.opbuf("xin", B * H * W * m.cin_pad)
         self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), None, _ptr(xin), self.dt, B, m.in_channels, H * W,
                   m.cin_pad, self.rnd)
@@ -621,13 +607,32 @@ class _StepPlan:
         controlnet = m._enc_cond is not None
         self.concurrent = controlnet and m.concurrent_encoders
         self.hs, self.keep_hs = None, controlnet
-        self.n_events = len(m._enc) if self.concurrent else 0
+        self.n_events = len(m._enc) + 1 if self.concurrent else 0
+        self.film_event = len(m._enc)          # recorded on the main stream once the FiLM table is complete
         if controlnet:
             xcin = self.opbuf("xcin", B * H * W * m.cin_pad)
             self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), _ptr(self.xc_in), _ptr(xcin), self.dt, B,
                       m.in_channels, H * W, m.cin_pad, self.rnd)
         if self.concurrent:
-            self.emit_sync("fork")
+            self.emit_sync("fork")             # the ControlNet stem conv needs only xcin: it overlaps the embedding GEMVs
+        # --- embeddings (unet.py:564,584-586; all ResBlock emb_layers in one GEMV) ---
+        temb, e1, emb = self.buf("temb", B * mc), self.buf("e1", B * ed), self.buf("emb", B * ed)
+        self.film = self.buf("film", B * m._film_rows)
+        self.emit("hl_timestep_embedding", _ptr(self.t_in), _ptr(m._freqs), B, mc, _ptr(temb))
+        self.emit("hl_linear_small", _ptr(temb), _ptr(m._small["time_embed.0.weight"]),
+                  _ptr(m._small["time_embed.0.bias"]), _ptr(e1), B, mc, ed, 0, None, None)
+        if m.num_classes is not None:
+            self.emit("hl_linear_small", _ptr(e1), _ptr(m._small["time_embed.2.weight"]),
+                      _ptr(m._small["time_embed.2.bias"]), _ptr(emb), B, ed, ed, 1,
+                      _ptr(m._small["label_emb.weight"]), _ptr(self.y_in))
+        else:
+            self.emit("hl_linear_small", _ptr(e1), _ptr(m._small["time_embed.2.weight"]),
+                      _ptr(m._small["time_embed.2.bias"]), _ptr(emb), B, ed, ed, 1, None, None)
+        self.emit("hl_linear_small", _ptr(emb), _ptr(m._film_w), _ptr(m._film_b), _ptr(self.film), B, ed,
+                  m._film_rows, 1, None, None)
+
+        if self.concurrent:
+            self.emit_sync("signal", self.film_event)
         hs = self.encoder(m._enc, _ptr(xin), "hs", self.cat_skip, False)
         if controlnet:
             self.hs = hs

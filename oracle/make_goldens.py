@@ -147,6 +147,21 @@ def render_case(name, n_rays=1024, seed_w=3):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def unet_full_size_case(name, flags, HW, t, seed_w, seed_in=1234):
+    """One forward of the production model at the BASELINE resolution (B = 1, 27 x HW x HW).  Only epsilon is
+    stored (7 MB at 256^2); inputs are regenerated from `seed_in` by synth.synth_denoise_inputs."""
+    t0 = time.time()
+    model, diffusion = build_ref(flags, seed_w)
+    x, x_cond, _ = synth.synth_denoise_inputs(1, 27, HW, HW, seed=seed_in)
+    y = torch.tensor([2])
+    with torch.no_grad():
+        tt = torch.full((1,), t, dtype=torch.int64)
+        eps = model(x, torch.tensor(diffusion.timestep_map)[tt], x_cond, y=y)
+    np.savez(os.path.join(OUT, name), eps=eps.numpy(), t=np.array(t), y=y.numpy(), seed_in=np.array(seed_in),
+             x_checksum=np.array(float(x.double().sum())), xc_checksum=np.array(float(x_cond.double().sum())))
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
 if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -160,3 +175,5 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "prod256" in which:        # not in the default list: ~1 min of CPU, 7 MB
+        unet_full_size_case("unet_prod_256_eps.npz", PROD, HW=256, t=100, seed_w=0)

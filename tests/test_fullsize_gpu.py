@@ -96,6 +96,34 @@ def prod_model():
     return model.to(DEV).eval(), diffusion
 
 
+def test_unet_full_resolution_vs_reference_golden(prod_model):
+    """The production UNet at the BASELINE resolution (27 x 256 x 256) against epsilon frozen from the UNMODIFIED
+    reference at that size (oracle/make_goldens.py prod256, B = 1, t = 100).  The sample is placed in every slot of
+    a B = 4 batch (the benchmarked configuration) next to different neighbours.  north_star bar: rel-L2 <= 1e-3."""
+    from common import load_golden, rel_max
+    model = prod_model[0]
+    g = load_golden("unet_prod_256_eps.npz")
+    x, xc, _ = synth.synth_denoise_inputs(1, 27, 256, 256, seed=int(g["seed_in"]))
+    assert abs(float(x.double().sum()) - float(g["x_checksum"])) < 1e-6 * 27 * 65536, "inputs regenerate bit-identically"
+    assert abs(float(xc.double().sum()) - float(g["xc_checksum"])) < 1e-6 * 27 * 65536
+    from humanliff_b200 import space_timesteps
+    tmap = sorted(space_timesteps(1000, "250"))              # the golden was drawn with the scripts' 250-step respacing
+    ts_model = tmap[int(g["t"])]
+    dev = torch.device(DEV)
+    gen = torch.Generator().manual_seed(77)
+    xb = torch.randn(4, 27, 256, 256, generator=gen)
+    xcb = (0.3 * torch.randn(4, 27, 256, 256, generator=gen)).clamp(-1, 1)
+    for slot in (0, 3):
+        xb[slot], xcb[slot] = x[0], xc[0]
+    y = torch.tensor([int(g["y"][0]), 0, 1, int(g["y"][0])])
+    t = torch.tensor([ts_model, 7, 900, ts_model])
+    eps = model(xb.to(dev), t.to(dev), xcb.to(dev), y=y.to(dev))
+    for slot in (0, 3):
+        e2, em = rel_l2(eps[slot], g["eps"][0]), rel_max(eps[slot], g["eps"][0])
+        assert e2 < 1e-3 and em < 2e-3, f"slot {slot}: eps rel-L2 {e2:.3e} max {em:.3e}"
+    print(f"full-resolution parity: rel-L2 {e2:.3e} max-rel {em:.3e}")
+
+
 def test_unet_step_full_size_batch_properties(prod_model):
     model, diffusion = prod_model
     dev = torch.device(DEV)

@@ -147,6 +147,47 @@ def render_case(name, n_rays=1024, seed_w=3):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def render_full_image_case(name, seed_w=3, azimuth=45.0, chunk=16384, seed_u=99, max_chunks=None):
+    """A whole 512 x 512 image through the reference renderer in its own chunk order
+    (run_nerf_batch.py:29-67: 16 chunks of 16,384 rays, one torch.rand([chunk, 128]) per chunk).  Only the three
+    output maps are stored (5 MB); rays and uniforms are regenerated from (azimuth, seed_u)."""
+    t0 = time.time()
+    hd = ref_shims.import_hd_renderer()
+    torch.manual_seed(0)
+    r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    sd = synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5)
+    r.load_state_dict(sd, strict=False)
+    planes = synth.synth_triplane(256, seed=7)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=azimuth)
+    n = ro.shape[0]
+    g = torch.Generator(); g.manual_seed(seed_u)
+    tp = {"world_bounds": bounds[None]}
+    t = torch.linspace(0., 1., steps=128)
+    outs = {"rgb": [], "acc": [], "depth": []}
+    orig = torch.rand
+    n_chunks = n // chunk if max_chunks is None else max_chunks
+    try:
+        for c in range(n_chunks):
+            sl = slice(c * chunk, (c + 1) * chunk)
+            u = orig(chunk, 128, generator=g)
+            torch.rand = lambda *a, **k: u.clone()
+            z = near[None, sl, None] * (1. - t) + far[None, sl, None] * t
+            pts = ro[None, sl, None, :] + rd[None, sl, None, :] * z[..., :, None]
+            with torch.no_grad():
+                ret = r.render(tp, pts.reshape(1, -1, 3), z, ro[None, sl], rd[None, sl], near[None, sl, None],
+                               far[None, sl, None], planes, 128, False)
+            outs["rgb"].append(ret["rgb_map"][0]); outs["acc"].append(ret["acc_map"][0]); outs["depth"].append(ret["depth_map"][0])
+            print("  chunk", c, "%.1fs" % (time.time() - t0), flush=True)
+    finally:
+        torch.rand = orig
+    np.savez(os.path.join(OUT, name), rgb=torch.cat(outs["rgb"]).numpy(), acc=torch.cat(outs["acc"]).numpy(),
+             depth=torch.cat(outs["depth"]).numpy(), seed_w=np.array(seed_w), seed_u=np.array(seed_u),
+             azimuth=np.array(azimuth), chunk=np.array(chunk), n_rays=np.array(n_chunks * chunk))
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
 def unet_full_size_case(name, flags, HW, t, seed_w, seed_in=1234):
     """One forward of the production model at the BASELINE resolution (B = 1, 27 x HW x HW).  Only epsilon is
     stored (7 MB at 256^2); inputs are regenerated from `seed_in` by synth.synth_denoise_inputs."""
@@ -175,5 +216,7 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "render512" in which:      # not in the default list: several minutes of CPU, 5 MB
+        render_full_image_case("render_512x512.npz")
     if "prod256" in which:        # not in the default list: ~1 min of CPU, 7 MB
         unet_full_size_case("unet_prod_256_eps.npz", PROD, HW=256, t=100, seed_w=0)

@@ -158,6 +158,29 @@ def test_unet_step_full_size_batch_properties(prod_model):
     assert rel_l2(a["sample"][2:] - b["sample"][2:], sig * (z1[2:] - z2[2:])) < 1e-4
 
 
+def test_render_full_image_vs_reference_golden():
+    """A whole 512 x 512 image (BASELINE configs[2]; 262,144 rays, 128 + 128 samples) against the three maps frozen
+    from the UNMODIFIED reference renderer run chunk by chunk on the CPU (oracle/make_goldens.py render512); rays
+    and the sample_pdf uniforms are regenerated from their seeds in the reference's chunk order."""
+    from common import load_golden, rel_max
+    g = load_golden("render_512x512.npz")
+    r, sd = renderer_state_dict(int(g["seed_w"]), "fp16")
+    r = r.to(DEV)
+    dev = torch.device(DEV)
+    planes = synth.synth_triplane(256, seed=7).to(dev)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=float(g["azimuth"]))
+    n, chunk = int(g["n_rays"]), int(g["chunk"])
+    gen = torch.Generator().manual_seed(int(g["seed_u"]))
+    u = torch.cat([torch.rand(chunk, 128, generator=gen) for _ in range(n // chunk)])
+    rgb, acc, dep = r.render_rays(planes[0], bounds, ro[:n].to(dev), rd[:n].to(dev), near[:n].to(dev), far[:n].to(dev),
+                                  u=u.to(dev))
+    for name, a, b in (("rgb", rgb, g["rgb"]), ("acc", acc, g["acc"]), ("depth", dep, g["depth"])):
+        e2, em = rel_l2(a, b), rel_max(a, b)
+        assert e2 < 1e-3, f"{name}: rel-L2 {e2:.3e} max {em:.3e}"
+        print(f"512x512 render parity {name}: rel-L2 {e2:.3e} max-rel {em:.3e}")
+
+
 def test_render_full_image_properties():
     r, sd = renderer_state_dict(3, "fp16")
     r = r.to(DEV)

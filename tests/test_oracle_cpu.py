@@ -103,3 +103,25 @@ def test_operand_rounding_margin():
         assert err["fp16"] < bar, (case, err)
         if case == "tiny":
             assert abs(err["fp16"] / err["tf32"] - 1) < 0.05 and err["bf16"] > 3e-3, err
+
+
+def test_oracle_matches_full_size_goldens():
+    """The two goldens frozen at the BASELINE sizes: the production UNet at 27 x 256 x 256 (epsilon) and the first
+    16,384-ray chunk of the 512 x 512 image.  Inputs are regenerated from their seeds, as the GPU tests do."""
+    from humanliff_b200 import space_timesteps
+    g = load_golden("unet_prod_256_eps.npz")
+    fname, flags, seed, heads = CASES["prod64"]
+    _, _, sd = model_state_dict(flags, seed)
+    x, xc, _ = synth.synth_denoise_inputs(1, 27, 256, 256, seed=int(g["seed_in"]))
+    ts = torch.tensor([sorted(space_timesteps(1000, "250"))[int(g["t"])]])
+    eps = unet_oracle.unet_forward(sd, x, ts, xc, g["y"], num_heads=heads)
+    assert rel_l2(eps, g["eps"]) < 2e-6 and rel_max(eps, g["eps"]) < 1e-5
+    gr = load_golden("render_512x512.npz")
+    _, rsd = renderer_state_dict(int(gr["seed_w"]))
+    planes = synth.synth_triplane(256, seed=7)[0]
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=float(gr["azimuth"]))
+    n = 2048                                                    # the head of chunk 0 (the uniforms are drawn per chunk)
+    u = torch.rand(int(gr["chunk"]), 128, generator=torch.Generator().manual_seed(int(gr["seed_u"])))[:n]
+    rgb, acc, depth = render_oracle.render_rays(rsd, planes, bounds, ro[:n], rd[:n], near[:n], far[:n], u, clamp_depth=True)
+    assert rel_l2(rgb, gr["rgb"][:n]) < 1e-5 and rel_l2(acc, gr["acc"][:n]) < 1e-6 and rel_l2(depth, gr["depth"][:n]) < 1e-5

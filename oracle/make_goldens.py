@@ -188,6 +188,34 @@ def render_full_image_case(name, seed_w=3, azimuth=45.0, chunk=16384, seed_u=99,
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+SCHEDULE_GRID = [(ns, ss, rs) for ns in ("linear", "cosine") for ss in (False, True)
+                 for rs in ("", "250", "ddim50", "10,15,20")]
+
+
+def schedule_case(name):
+    """The float64 tables of GaussianDiffusion / SpacedDiffusion (gaussian_diffusion.py:118-169, respace.py:7-86)
+    for the whole in-scope flag envelope, straight from the reference's objects."""
+    su = ref_shims.import_diffusion()
+    out = {}
+    for k, (ns, ss, rs) in enumerate(SCHEDULE_GRID):
+        d = su.create_gaussian_diffusion(steps=1000, learn_sigma=False, sigma_small=ss, noise_schedule=ns,
+                                         use_kl=False, predict_xstart=False, rescale_timesteps=False,
+                                         rescale_learned_sigmas=False, timestep_respacing=rs)
+        out[f"{k}_timestep_map"] = np.array(d.timestep_map)
+        for attr in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                     "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                     "posterior_mean_coef1", "posterior_mean_coef2"):
+            out[f"{k}_{attr}"] = np.asarray(getattr(d, attr), dtype=np.float64)
+        # the (variance, log-variance) pair p_mean_variance selects (gaussian_diffusion.py:278-291)
+        if ss:
+            out[f"{k}_model_var"], out[f"{k}_model_logvar"] = d.posterior_variance, d.posterior_log_variance_clipped
+        else:
+            v = np.append(d.posterior_variance[1], d.betas[1:])
+            out[f"{k}_model_var"], out[f"{k}_model_logvar"] = v, np.log(v)
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, "done", flush=True)
+
+
 def unet_full_size_case(name, flags, HW, t, seed_w, seed_in=1234):
     """One forward of the production model at the BASELINE resolution (B = 1, 27 x HW x HW).  Only epsilon is
     stored (7 MB at 256^2); inputs are regenerated from `seed_in` by synth.synth_denoise_inputs."""
@@ -207,7 +235,7 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -216,6 +244,8 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "schedules" in which:
+        schedule_case("schedules.npz")
     if "render512" in which:      # not in the default list: several minutes of CPU, 5 MB
         render_full_image_case("render_512x512.npz")
     if "prod256" in which:        # not in the default list: ~1 min of CPU, 7 MB

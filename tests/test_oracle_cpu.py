@@ -1,10 +1,12 @@
 """CPU: the oracle restatement vs the golden vectors frozen from the unmodified reference
 (oracle/make_goldens.py).  This is what pins the oracle (the reference ships no tests)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from common import CASES, load_golden, model_state_dict, renderer_state_dict, rel_l2, rel_max
+from common import CASES, GOLDEN, load_golden, model_state_dict, renderer_state_dict, rel_l2, rel_max
 from humanliff_b200 import synth
 from oracle import diffusion_oracle, render_oracle, unet_oracle
 
@@ -125,3 +127,24 @@ def test_oracle_matches_full_size_goldens():
     u = torch.rand(int(gr["chunk"]), 128, generator=torch.Generator().manual_seed(int(gr["seed_u"])))[:n]
     rgb, acc, depth = render_oracle.render_rays(rsd, planes, bounds, ro[:n], rd[:n], near[:n], far[:n], u, clamp_depth=True)
     assert rel_l2(rgb, gr["rgb"][:n]) < 1e-5 and rel_l2(acc, gr["acc"][:n]) < 1e-6 and rel_l2(depth, gr["depth"][:n]) < 1e-5
+
+
+def test_schedule_tables_vs_reference_golden():
+    """float64 tables of the product's GaussianDiffusion / SpacedDiffusion, bit for bit against the reference's own
+    objects over the in-scope flag envelope: linear / cosine x FIXED_LARGE / FIXED_SMALL x respacing
+    "", "250", "ddim50", "10,15,20" (oracle/make_goldens.py schedules)."""
+    from humanliff_b200 import create_gaussian_diffusion
+    grid = [(ns, ss, rs) for ns in ("linear", "cosine") for ss in (False, True)
+            for rs in ("", "250", "ddim50", "10,15,20")]                    # = oracle.make_goldens.SCHEDULE_GRID
+    z = np.load(os.path.join(GOLDEN, "schedules.npz"))
+    assert sum(1 for k in z.files if k.endswith("_betas")) == len(grid)
+    for k, (ns, ss, rs) in enumerate(grid):
+        d = create_gaussian_diffusion(steps=1000, sigma_small=ss, noise_schedule=ns, timestep_respacing=rs)
+        assert list(d.timestep_map) == z[f"{k}_timestep_map"].tolist(), (ns, ss, rs)
+        for attr in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                     "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                     "posterior_mean_coef1", "posterior_mean_coef2"):
+            np.testing.assert_array_equal(np.asarray(getattr(d, attr)), z[f"{k}_{attr}"], err_msg=f"{attr} {ns} {ss} {rs}")
+        v, lv = d._variance_tables()
+        np.testing.assert_array_equal(v, z[f"{k}_model_var"])
+        np.testing.assert_array_equal(lv, z[f"{k}_model_logvar"])

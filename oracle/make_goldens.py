@@ -188,6 +188,35 @@ def render_full_image_case(name, seed_w=3, azimuth=45.0, chunk=16384, seed_u=99,
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def variants_case(name):
+    """Flag-envelope variants on the tiny model (B = 1, 27 x 32 x 32), straight from the reference:
+    (a) unconditional UNet (cond_type='', class_cond=False);  (b) p_sample with rescale_timesteps=True on a 500-step
+    schedule respaced to 50 (timesteps reach the model as floats x 1000/500, respace.py:117-122) with FIXED_SMALL."""
+    out = {}
+    g = torch.Generator(); g.manual_seed(4321)
+    x = torch.randn(1, 27, 32, 32, generator=g)
+    xc = (0.3 * torch.randn(1, 27, 32, 32, generator=g)).clamp(-1, 1)
+    noise = torch.randn(1, 27, 32, 32, generator=g)
+    out.update(x=x.numpy(), x_cond=xc.numpy(), noise=noise.numpy())
+    with torch.no_grad():
+        model, _ = build_ref(dict(TINY, cond_type="", class_cond=False), 3)
+        out["a_t"] = np.array(17)
+        out["a_eps"] = model(x, torch.tensor([17])).numpy()
+        flags = dict(TINY, diffusion_steps=500, timestep_respacing="50", rescale_timesteps=True, sigma_small=True)
+        model, diffusion = build_ref(flags, 11)
+        tt = torch.tensor([20])
+        orig = inject_noise([noise])
+        try:
+            r = diffusion.p_sample(model, x, xc, tt, clip_denoised=True, model_kwargs={"y": torch.tensor([3])})
+        finally:
+            torch.randn_like = orig
+        out["b_t"] = np.array(20)
+        out["b_sample"], out["b_x0"] = r["sample"].numpy(), r["pred_xstart"].numpy()
+        out["b_timestep_map"] = np.array(diffusion.timestep_map)
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, "done", flush=True)
+
+
 SCHEDULE_GRID = [(ns, ss, rs) for ns in ("linear", "cosine") for ss in (False, True)
                  for rs in ("", "250", "ddim50", "10,15,20")]
 
@@ -235,7 +264,7 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -244,6 +273,8 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "variants" in which:
+        variants_case("unet_variants_32.npz")
     if "schedules" in which:
         schedule_case("schedules.npz")
     if "render512" in which:      # not in the default list: several minutes of CPU, 5 MB

@@ -260,3 +260,32 @@ def test_optional_launch_modes_agree():
     a = model(x, ts, xc, y=y)
     b = model(x[perm], ts[perm], xc[perm], y=y[perm])
     assert rel_l2(b, a[perm]) < 1e-6
+
+
+def test_flag_envelope_variants_vs_reference_golden():
+    """Variants inside the supported flag envelope against outputs of the unmodified reference
+    (oracle/make_goldens.py variants): the unconditional UNet, and p_sample with rescale_timesteps=True on a 500-step
+    schedule respaced to 50 with the FIXED_SMALL variance."""
+    from humanliff_b200 import factory, synth
+    g = load_golden("unet_variants_32.npz")
+    dev = torch.device("cuda:0")
+    fname, flags, seed, heads = CASES["tiny"]
+    x, xc, noise = g["x"].to(dev), g["x_cond"].to(dev), g["noise"].to(dev)
+    # (a) cond_type='' / class_cond=False
+    fa = dict(flags, cond_type="", class_cond=False, precision="fp32")
+    model, _ = factory.create_model_and_diffusion(**fa)
+    model.load_state_dict(synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=3))
+    eps = model.to(dev)(x, torch.tensor([int(g["a_t"])], device=dev))
+    assert rel_l2(eps, g["a_eps"]) < 5e-5, rel_l2(eps, g["a_eps"])
+    # (b) rescale_timesteps + FIXED_SMALL + respaced 500-step schedule
+    fb = dict(flags, diffusion_steps=500, timestep_respacing="50", rescale_timesteps=True, sigma_small=True,
+              precision="fp32")
+    model, diffusion = factory.create_model_and_diffusion(**fb)
+    model.load_state_dict(synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=11))
+    model = model.to(dev)
+    assert list(diffusion.timestep_map) == g["b_timestep_map"].tolist()
+    tt = torch.tensor([int(g["b_t"])], device=dev)
+    out = diffusion.p_sample(model, x, xc, tt, clip_denoised=True, model_kwargs={"y": torch.tensor([3], device=dev)},
+                             noise=noise)
+    assert rel_l2(out["sample"], g["b_sample"]) < 5e-5, rel_l2(out["sample"], g["b_sample"])
+    assert rel_l2(out["pred_xstart"], g["b_x0"]) < 2e-4, rel_l2(out["pred_xstart"], g["b_x0"])

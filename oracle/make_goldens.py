@@ -188,6 +188,41 @@ def render_full_image_case(name, seed_w=3, azimuth=45.0, chunk=16384, seed_u=99,
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def render_rn_case(name, n_rays=256, seed_w=3, layer=2):
+    """recon_NeRF/lib/renderer.py (the reconstruction-side Renderer that owns tri_planes [N,4,3,9,256,256] and does
+    NOT clamp depth, renderer.py:244-295) on the first rays of the render_1024 golden's ray set."""
+    t0 = time.time()
+    rn = ref_shims.import_rn_renderer()
+    torch.manual_seed(0)
+    r = rn.Renderer(use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=27, test=True)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc") and k != "tri_planes"}
+    sd = synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5)
+    r.load_state_dict(sd, strict=False)
+    planes = synth.synth_triplane(256, seed=7)
+    with torch.no_grad():
+        r.tri_planes[0, layer] = planes[0]
+    gold = np.load(os.path.join(OUT, "render_1024.npz"))
+    ro, rd = torch.from_numpy(gold["rays_o"][:n_rays]), torch.from_numpy(gold["rays_d"][:n_rays])
+    near, far = torch.from_numpy(gold["near"][:n_rays]), torch.from_numpy(gold["far"][:n_rays])
+    u = torch.from_numpy(gold["u"][:n_rays])
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        t = torch.linspace(0., 1., steps=128)
+        z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+        pts = ro[None, :, None, :] + rd[None, :, None, :] * z[..., :, None]
+        tp = {"world_bounds": bounds[None], "instance_idx": torch.tensor([0]), "cloth_layer_index": torch.tensor([layer])}
+        with torch.no_grad():
+            ret = r.render(tp, pts.reshape(1, -1, 3), z, ro[None], rd[None], near[None, :, None], far[None, :, None],
+                           128, False)
+    finally:
+        torch.rand = orig
+    np.savez(os.path.join(OUT, name), n_rays=np.array(n_rays), layer=np.array(layer), seed_w=np.array(seed_w),
+             rgb=ret["rgb_map"][0].numpy(), acc=ret["acc_map"][0].numpy(), depth=ret["depth_map"][0].numpy())
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
 def variants_case(name):
     """Flag-envelope variants on the tiny model (B = 1, 27 x 32 x 32), straight from the reference:
     (a) unconditional UNet (cond_type='', class_cond=False);  (b) p_sample with rescale_timesteps=True on a 500-step
@@ -264,7 +299,7 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -273,6 +308,8 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "render_rn" in which:
+        render_rn_case("render_rn_256.npz")
     if "variants" in which:
         variants_case("unet_variants_32.npz")
     if "schedules" in which:

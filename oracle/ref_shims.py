@@ -37,3 +37,26 @@ def import_hd_renderer():
     from NeRF import renderer as hd_renderer    # noqa
     torch.autograd.set_detect_anomaly(False)      # fields.py:2 turns it on at import
     return hd_renderer
+
+
+def import_rn_renderer():
+    """-> the reference's recon_NeRF/lib/renderer.py module.  Besides the mcubes / pytorch3d stubs it needs the
+    SMPL asset load of Renderer.__init__ (renderer.py:45-48: read_pickle + SMPL_to_tensor on
+    torch.cuda.current_device()) neutralised -- none of it is touched when use_canonical_space=False."""
+    import torch
+    for name in ("mcubes", "pytorch3d", "pytorch3d.ops", "pytorch3d.ops.knn"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            if name.endswith("knn"):
+                m.knn_points = None
+            sys.modules[name] = m
+    p = os.path.join(REF_ROOT, "recon_NeRF")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    from lib import renderer as rn_renderer     # noqa
+    torch.autograd.set_detect_anomaly(False)
+    rn_renderer.read_pickle = lambda path: {}
+    rn_renderer.SMPL_to_tensor = lambda params, device=None: {"f": None}
+    if not torch.cuda.is_available():
+        torch.cuda.current_device = lambda: 0
+    return rn_renderer

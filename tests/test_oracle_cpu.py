@@ -148,3 +148,16 @@ def test_schedule_tables_vs_reference_golden():
         v, lv = d._variance_tables()
         np.testing.assert_array_equal(v, z[f"{k}_model_var"])
         np.testing.assert_array_equal(lv, z[f"{k}_model_logvar"])
+
+
+def test_render_oracle_matches_recon_reference_golden():
+    """recon_NeRF/lib/renderer.py (no depth clamp, tri-planes owned by the module): golden render_rn_256 on the first
+    256 rays of the render_1024 ray set."""
+    g, gr = load_golden("render_1024.npz"), load_golden("render_rn_256.npz")
+    n = int(gr["n_rays"])
+    _, sd = renderer_state_dict(int(gr["seed_w"]))
+    planes = synth.synth_triplane(256, seed=7)[0]
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    rgb, acc, depth = render_oracle.render_rays(sd, planes, bounds, g["rays_o"][:n], g["rays_d"][:n], g["near"][:n],
+                                                g["far"][:n], g["u"][:n], clamp_depth=False)
+    assert rel_l2(rgb, gr["rgb"]) < 1e-5 and rel_l2(acc, gr["acc"]) < 1e-6 and rel_l2(depth, gr["depth"]) < 1e-5

@@ -96,6 +96,12 @@ def test_render_recon_variant_no_depth_clamp():
     ref = render_oracle.render_rays(sd, planes[0], bounds, g["rays_o"][:n], g["rays_d"][:n], g["near"][:n],
                                     g["far"][:n], g["u"][:n], clamp_depth=False)
     assert rel_l2(out["rgb_map"][0], ref[0]) < 1e-3 and rel_l2(out["depth_map"][0], ref[2]) < 1e-3
+    # and against the reconstruction-side reference renderer itself (recon_NeRF/lib/renderer.py, golden render_rn_256)
+    gr = load_golden("render_rn_256.npz")
+    assert int(gr["n_rays"]) == n and int(gr["layer"]) == 2
+    for name, a, b in (("rgb", out["rgb_map"][0], gr["rgb"]), ("acc", out["acc_map"][0], gr["acc"]),
+                       ("depth", out["depth_map"][0], gr["depth"])):
+        assert rel_l2(a, b) < 3e-4, (name, rel_l2(a, b))
 
 
 def test_density_grid_vs_oracle():

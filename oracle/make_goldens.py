@@ -223,6 +223,24 @@ def render_rn_case(name, n_rays=256, seed_w=3, layer=2):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def density_grid_case(name, res=24, seed_w=3):
+    """The field of Renderer.extract_geometry (human_diffusion/NeRF/renderer.py:290-318) run by the reference itself:
+    the absent `mcubes` is stubbed so that smooth() hands back the raw grid `u` (= -sigma) it was given."""
+    hd = ref_shims.import_hd_renderer()
+    grabbed = {}
+    hd.mcubes.smooth = lambda u: grabbed.setdefault("u", u.copy())
+    hd.mcubes.marching_cubes = lambda u, thr: (np.zeros((1, 3), np.float32), np.zeros((1, 3), np.int64))
+    torch.manual_seed(0)
+    r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    r.load_state_dict(synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5), strict=False)
+    planes = synth.synth_triplane(256, seed=7)
+    tp = {"world_bounds": torch.tensor(synth.WORLD_BOUNDS)[None]}
+    r.extract_geometry(tp, tri_planes=planes, resolution=res, threshold=0.0)
+    np.savez(os.path.join(OUT, name), u=grabbed["u"], res=np.array(res), seed_w=np.array(seed_w))
+    print(name, "done", flush=True)
+
+
 def variants_case(name):
     """Flag-envelope variants on the tiny model (B = 1, 27 x 32 x 32), straight from the reference:
     (a) unconditional UNet (cond_type='', class_cond=False);  (b) p_sample with rescale_timesteps=True on a 500-step
@@ -299,7 +317,7 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn", "density"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -308,6 +326,8 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "density" in which:
+        density_grid_case("density_grid_24.npz")
     if "render_rn" in which:
         render_rn_case("render_rn_256.npz")
     if "variants" in which:

@@ -161,3 +161,17 @@ def test_render_oracle_matches_recon_reference_golden():
     rgb, acc, depth = render_oracle.render_rays(sd, planes, bounds, g["rays_o"][:n], g["rays_d"][:n], g["near"][:n],
                                                 g["far"][:n], g["u"][:n], clamp_depth=False)
     assert rel_l2(rgb, gr["rgb"]) < 1e-5 and rel_l2(acc, gr["acc"]) < 1e-6 and rel_l2(depth, gr["depth"]) < 1e-5
+
+
+def test_density_field_oracle_matches_reference_golden():
+    """The -sigma field of extract_geometry (human_diffusion/NeRF/renderer.py:290-318) vs golden density_grid_24."""
+    gd = load_golden("density_grid_24.npz")
+    _, sd = renderer_state_dict(int(gd["seed_w"]))
+    planes = synth.synth_triplane(256, seed=7)[0]
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    res = int(gd["res"])
+    xs, ys, zs = (torch.linspace(float(bounds[0, i]), float(bounds[1, i]), res) for i in range(3))
+    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
+    u = -render_oracle.mlp(sd, render_oracle.plane_features(planes, pts, bounds[0], bounds[1])).reshape(res, res, res)
+    assert rel_l2(u, gd["u"]) < 1e-5, rel_l2(u, gd["u"])

@@ -118,3 +118,19 @@ def test_density_grid_vs_oracle():
     ref = -render_oracle.mlp(sd, render_oracle.plane_features(planes[0], pts, bounds[0], bounds[1])).reshape(res, res, res)
     assert rel_l2(u, ref) < 1e-3, rel_l2(u, ref)
     assert rel_max(u, ref) < 2e-3
+
+
+def test_density_grid_vs_reference_golden():
+    """Renderer.density_grid against the grid the reference's own extract_geometry evaluated (mcubes stubbed to hand
+    the raw field back): golden density_grid_24, index order [x, y, z], values -sigma (pre-softplus)."""
+    gd = load_golden("density_grid_24.npz")
+    r, sd = renderer_state_dict(int(gd["seed_w"]), "fp16")
+    r = r.to("cuda:0")
+    dev = torch.device("cuda:0")
+    planes = synth.synth_triplane(256, seed=7)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    res = int(gd["res"])
+    u = r.density_grid({"world_bounds": bounds[None].to(dev)}, planes.to(dev), resolution=res)
+    assert u.shape == (res, res, res)
+    assert rel_l2(u, gd["u"]) < 1e-3, rel_l2(u, gd["u"])
+    assert rel_max(u, gd["u"]) < 2e-3

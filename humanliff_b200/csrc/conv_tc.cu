@@ -819,53 +819,73 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // (hl_conv_set_workspace) the K loop is cut into S slices run by S x as many CTAs, every slice stores its
 // fp32 partial tile into ws[s][B*H*W][cout_pad], and this kernel adds the slices in a FIXED order
 // (deterministic), then bias, residual, the per-channel GroupNorm statistics and the output rounding
-// exactly as the one-pass epilogue does.  One thread = 4 channels x `pix` pixels of one sample.
+// exactly as the one-pass epilogue does.  One block = 32 channels of one sample (no contended atomics).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_splitk_reduce(const float *__restrict__ ws, int S, int64_t slice, int ldw,
-                                                      const float *__restrict__ bias,
-                                                      const float *__restrict__ res, int ldr, void *__restrict__ y,
-                                                      int y_f16, int ldy, double *__restrict__ stats, int stats_ld,
-                                                      int HW, int Cout, int pix) {
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__ ws, int S, int64_t slice, int ldw,
+                                                       const float *__restrict__ bias,
+                                                       const float *__restrict__ res, int ldr, void *__restrict__ y,
+                                                       int y_f16, int ldy, double *__restrict__ stats, int stats_ld,
+                                                       int HW, int Cout) {
     hl_pdl_enter();
-    const int cq = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cq * 4 >= Cout) return;
-    const int b = blockIdx.z, p0 = blockIdx.y * pix;
-    const int p1 = min(HW, p0 + pix);
-    const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias) + cq);
+    // block = (32-channel group, sample); warp w, lane = (pixel lane pl, channel quad q): a warp reads 4 pixels x 128 B
+    __shared__ double red[8][8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 7, pl = lane >> 3;
+    const int c = blockIdx.x * 32 + q * 4, b = blockIdx.y;
+    const bool live = c < Cout;
     double sm[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-    for (int pp = p0; pp < p1; ++pp) {
-        const int64_t m = (int64_t)b * HW + pp;
-        const float *src = ws + m * ldw + 4 * cq;
-        float4 a = *reinterpret_cast<const float4 *>(src);
-        for (int k = 1; k < S; ++k) {
-            const float4 t = *reinterpret_cast<const float4 *>(src + k * slice);
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
-        a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
-        if (res) {
-            const float4 r = *reinterpret_cast<const float4 *>(res + m * ldr + 4 * cq);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-        }
-        if (y_f16) {
-            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-            uint2 w;
-            w.x = *reinterpret_cast<const uint32_t *>(&h0);
-            w.y = *reinterpret_cast<const uint32_t *>(&h1);
-            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + 4 * cq) = w;
-        } else {
-            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + m * ldy + 4 * cq) = a;
-        }
-        if (stats) {
+    if (live) {
+        const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + c));
+#pragma unroll 2
+        for (int pp = warp * 4 + pl; pp < HW; pp += 32) {
+            const int64_t m = (int64_t)b * HW + pp;
+            const float *src = ws + m * ldw + c;
+            float4 a = __ldcs(reinterpret_cast<const float4 *>(src));
+#pragma unroll 4
+            for (int k = 1; k < S; ++k) {                      // fixed order: bit-reproducible
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(src + k * slice));
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
+            if (res) {
+                const float4 r = *reinterpret_cast<const float4 *>(res + m * ldr + c);
+                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            }
+            if (y_f16) {
+                const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                uint2 w;
+                w.x = *reinterpret_cast<const uint32_t *>(&h0);
+                w.y = *reinterpret_cast<const uint32_t *>(&h1);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + c) = w;
+            } else {
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + m * ldy + c) = a;
+            }
             sm[0] += a.x; sm[1] += a.y; sm[2] += a.z; sm[3] += a.w;
             sq[0] += (double)a.x * a.x; sq[1] += (double)a.y * a.y; sq[2] += (double)a.z * a.z; sq[3] += (double)a.w * a.w;
         }
     }
-    if (stats) {
-        double *dst = stats + ((size_t)b * stats_ld + 4 * cq) * 2;
+    if (!stats) return;
+    // per-channel sums over the sample's pixels: pixel lanes (shuffles), then warps (shared memory), fixed order
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            atomicAdd(dst + 2 * c, sm[c]);
-            atomicAdd(dst + 2 * c + 1, sq[c]);
+    for (int e = 0; e < 4; ++e) {
+        sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 8);
+        sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 16);
+        sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
+        sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+    }
+    if (pl == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { red[warp][q][e] = sm[e]; red[warp][q][4 + e] = sq[e]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {                       // (quad, value) pairs: 8 quads x 8 values
+        const int qq = threadIdx.x >> 3, v = threadIdx.x & 7;
+        const int cc = blockIdx.x * 32 + qq * 4 + (v & 3);
+        if (cc < Cout) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][qq][v];
+            atomicAdd(stats + ((size_t)b * stats_ld + cc) * 2 + (v >> 2), t);    // the only writer of this row
         }
     }
 }
@@ -874,7 +894,6 @@ __global__ void __launch_bounds__(64) k_splitk_reduce(const float *__restrict__ 
 struct Workspace { cudaStream_t stream; float *ptr; size_t bytes; };
 Workspace g_ws[8];
 int g_n_ws = 0;
-int g_tune_split = -1;      // -1 automatic, 0 off, > 0 forced number of K slices (when it divides the chunk count)
 
 const Workspace *find_ws(cudaStream_t st) {
     for (int i = 0; i < g_n_ws; ++i)
@@ -931,6 +950,7 @@ bool pick_tiling(int H, int W, Tiling *t) {
 }
 
 // tuning overrides (-1 = automatic); set through hl_conv_set_tuning (tests / experiments)
+int g_tune_split = -1;      // -1 automatic, 0 off, > 0 forced number of K slices (when it divides the chunk count)
 int g_tune_mh = -1, g_tune_ntile = -1, g_tune_halo = -1, g_tune_epi_stats = -1, g_tune_base_off = -1;
 unsigned long long *g_prof = nullptr;
 int g_tune_stages = -1, g_tune_nbuf = -1, g_tune_cta2 = -1;   // experiment: cap on pipeline slots / staging buffers
@@ -1092,6 +1112,56 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     return true;
 }
 
+// split-K planning: 3x3 layers whose K loop is long and whose grid is under one wave.  Every (N tile, S) with at
+// most one wave of CTAs is costed with the shared-memory model of DESIGN.md 5.1 -- stages x bytes through shared
+// memory per stage (MMA operand fetch + TMA operand writes) -- and the cheapest is taken if it at least halves the
+// K-loop cost of the one-pass plan (the second pass is not free).  May replace `pl` by a plan with a wider N tile.
+// H, W are OUTPUT dims.  Returns the number of K slices (1 = no split).
+int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, size_t ws_bytes) {
+    TcParams &p = pl.p;
+    int S = 1;
+    if (!ws_bytes || g_tune_split == 0 || Cout % 4 || B % pl.t.bn || p.kchunks < 2) return 1;
+    const int sms = hl_num_sms();
+    const size_t slice_bytes = (size_t)B * H * W * pl.cout_pad * sizeof(float);
+    auto fits = [&](const Plan &q, int s) {
+        return q.p.kchunks % s == 0 && (size_t)s * slice_bytes <= ws_bytes && q.grid * s <= sms &&
+               (q.p.kchunks / s) * q.p.taps >= 12;
+    };
+    auto cost = [&](const Plan &q, int s) {        // bytes through shared memory on one CTA's K loop
+        const double rows_b = (double)q.p.n_tile / q.p.pair;
+        const double stage = 4.0 * (128.0 * q.p.mh + rows_b) * 32.0 + rows_b * ROW_BYTES + (double)q.p.mh * A_BOX_BYTES;
+        const int units = q.p.pair == 2 ? q.grid / 2 : q.grid;
+        const double tiles = (double)((q.p.total_tiles + units - 1) / units);
+        return tiles * (q.p.kchunks / s) * q.p.taps * stage;
+    };
+    if (g_tune_split > 1) {
+        if (p.kchunks % g_tune_split == 0 && (size_t)g_tune_split * slice_bytes <= ws_bytes) S = g_tune_split;
+    } else if (ksize == 3 && !p.halo && pl.grid < sms && p.kchunks * p.taps >= 54) {
+        double best = cost(pl, 1) * 0.5;
+        Plan best_pl = pl;
+        const int keep_ntile = g_tune_ntile;
+        static const int widths[] = {0, 128, 192, 256};          // 0 = the one-pass plan's own N tile
+        for (int wdt : widths) {
+            Plan q = pl;
+            if (wdt) {
+                if (keep_ntile > 0) continue;                       // a forced tile is not second-guessed
+                q = Plan{};
+                g_tune_ntile = wdt;
+                const bool ok = make_plan(kind, B, H, W, Cin, Cout, ksize, stride, false, false, &q);
+                g_tune_ntile = keep_ntile;
+                if (!ok || q.p.n_tile != wdt || q.p.halo || B % q.t.bn) continue;
+            }
+            for (int s = 8; s >= 2; --s) {
+                if (!fits(q, s)) continue;
+                const double c = cost(q, s);
+                if (c < best) { best = c; best_pl = q; S = s; }
+            }
+        }
+        if (S > 1) pl = best_pl;
+    }
+    return S;
+}
+
 // in-epilogue GroupNorm statistics need one sample per 128-pixel box (every box row valid)
 bool plan_epi_stats(const Plan &pl, bool want_stats) {
     if (!want_stats || g_tune_epi_stats == 0) return false;
@@ -1146,6 +1216,32 @@ extern "C" int hl_conv_set_split(int ksplit) {
     return HL_OK;
 }
 
+extern "C" int hl_conv2d_plan_info(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                   int has_res, int want_stats, int64_t ws_bytes, int *out) {
+    HL_CHECK_ARG(out && B > 0 && H > 0 && W > 0 && stride > 0);
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    const int kind = x_dtype == HL_DT_F16 ? 1 : 0;
+    Plan pl = {};
+    if ((stride != 1 && stride != 2) || (ksize != 1 && ksize != 3) || (stride == 2 && (ksize != 3 || H % 2 || W % 2)) ||
+        !make_plan(kind, B, H / stride, W / stride, Cin, Cout, ksize, stride, has_res != 0, want_stats != 0, &pl))
+        return HL_OK;                                   // out[0] = 0: the CUDA-core kernel serves this shape
+    const int S = choose_split(pl, kind, B, H / stride, W / stride, Cin, Cout, ksize, stride,
+                               ws_bytes > 0 ? (size_t)ws_bytes : 0);
+    const TcParams &p = pl.p;
+    const int units = p.pair == 2 ? pl.grid / 2 : pl.grid;
+    int grid = pl.grid;
+    if (S > 1) {
+        const int total = p.total_tiles * S, sms = hl_num_sms();
+        grid = p.pair == 2 ? 2 * (total < sms / 2 ? total : sms / 2) : (total < sms ? total : sms);
+    }
+    (void)units;
+    out[0] = 1; out[1] = p.pair; out[2] = p.mh; out[3] = p.n_tile; out[4] = p.halo; out[5] = p.a_slots;
+    out[6] = p.b_slots; out[7] = p.nbuf; out[8] = p.acc_stages; out[9] = p.tmem_cols; out[10] = (int)pl.smem;
+    out[11] = grid; out[12] = p.total_tiles * S; out[13] = S; out[14] = p.kchunks / S;
+    out[15] = plan_epi_stats(pl, want_stats != 0 && S == 1) ? 1 : 0;
+    return HL_OK;
+}
+
 extern "C" int hl_conv_set_profile(void *dev_counters) {
     g_prof = (unsigned long long *)dev_counters;
     return HL_OK;
@@ -1192,20 +1288,12 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     HL_CHECK_ARG(!(y_f16 && stats));
     bool epi_stats = plan_epi_stats(pl, stats != nullptr);
 
-    // split-K (see k_splitk_reduce): 3x3 layers whose whole grid is under half a wave
-    int S = 1;
+    // split-K (see choose_split / k_splitk_reduce)
     const Workspace *wsp = find_ws(stream);
-    if (wsp && g_tune_split != 0 && Cout % 4 == 0 && B % pl.t.bn == 0 && p.kchunks >= 2) {
-        const int sms = hl_num_sms();
-        const size_t slice_bytes = (size_t)B * H * W * pl.cout_pad * sizeof(float);
-        auto fits = [&](int s) { return p.kchunks % s == 0 && (size_t)s * slice_bytes <= wsp->bytes; };
-        if (g_tune_split > 1) {
-            if (fits(g_tune_split)) S = g_tune_split;
-        } else if (ksize == 3 && 2 * pl.grid <= sms) {
-            for (int s = 8; s >= 2; --s)
-                if (fits(s) && pl.grid * s <= sms && (p.kchunks / s) * p.taps >= 12) { S = s; break; }
-        }
-    }
+    const float *keep_bias = p.bias;
+    const int S = choose_split(pl, kind, B, H, W, Cin, Cout, ksize, stride, wsp ? wsp->bytes : 0);
+    p.bias = keep_bias;
+    p.y_f16 = y_f16;
     const void *y_final = y;
     const int ldy_final = ldy, yf16_final = y_f16;
     if (S > 1) {
@@ -1317,12 +1405,10 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     HL_CHECK_LAUNCH();
     if (S > 1) {
         const int HW = H * W;
-        int pix = HW / 8;
-        if (pix < 8) pix = 8;
-        dim3 grid(hl_cdiv(Cout / 4, 64), hl_cdiv(HW, pix), B);
-        HL_CHECK_CUDA(hl_launch(k_splitk_reduce, grid, dim3(64), 0, stream, (const float *)wsp->ptr, S,
+        dim3 grid(hl_cdiv(Cout, 32), B);
+        HL_CHECK_CUDA(hl_launch(k_splitk_reduce, grid, dim3(256), 0, stream, (const float *)wsp->ptr, S,
                                 (int64_t)B * HW * pl.cout_pad, pl.cout_pad, bias, residual, ldr, (void *)y_final,
-                                yf16_final, ldy_final, stats, stats_ld, HW, Cout, pix));
+                                yf16_final, ldy_final, stats, stats_ld, HW, Cout));
         return HL_OK;
     }
     if (stats && !epi_stats) return hl_gn_stats_launch((const float *)y, ldy, B, H * W, Cout, stats, stats_ld, stream);

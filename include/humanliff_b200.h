@@ -66,6 +66,13 @@ int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2);
  * rounding.  Streams that run concurrently need distinct workspaces.  hl_conv_set_split: -1 automatic
  * (default), 0 off, n > 1 forces n slices wherever n divides the K chunk count (tests).                     */
 int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream);
+/* Host-only query of the tiling hl_conv2d would use (no device work; 148 SMs assumed without a GPU).  out[16]:
+ * 0 tensor-core path applies, 1 CTAs per MMA (1 | 2 = cta_group::2), 2 halves per CTA tile, 3 N tile,
+ * 4 HALO operand path, 5 A slots, 6 B slots, 7 staging buffers per epilogue group, 8 TMEM accumulator stages,
+ * 9 TMEM columns, 10 dynamic shared memory bytes, 11 grid, 12 tiles, 13 K slices (split-K with a workspace of
+ * ws_bytes), 14 channel chunks per slice, 15 statistics in the epilogue.                                       */
+int hl_conv2d_plan_info(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int has_res,
+                        int want_stats, int64_t ws_bytes, int *out);
 int hl_conv_set_split(int ksplit);
 
 /* Experiment hook: device array of >= 16 uint64 that CTA 0 of every following tcgen05 conv adds its

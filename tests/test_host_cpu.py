@@ -135,3 +135,41 @@ def test_layer_handoff_files(tmp_path):
     assert torch.equal(got, x[1:4])
     with pytest.raises(ValueError):
         load_layer_cond(p, 4, 2, "cpu")
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_conv_planner_on_every_production_launch(B):
+    """Host-only tiling query (hl_conv2d_plan_info) over every conv of the production step: the tcgen05 path applies
+    to all of them and each plan respects the hardware limits (227 KB shared memory minus the static part, 512 TMEM
+    columns, one wave of CTAs when K is split, workspace large enough for the partial sums)."""
+    import ctypes
+    from humanliff_b200 import _lib, factory
+    from humanliff_b200.unet import _StepPlan
+    model, _ = factory.create_model_and_diffusion(**factory.production_flags(""))
+    model._pack(torch.device("cpu"))
+    plan = _StepPlan(model, torch.device("cpu"), B, 256, 256)
+    lib = _lib.load()
+    n_conv = n_split = 0
+    for name, a, _br in plan.calls:
+        if name != "hl_conv2d":
+            continue
+        n_conv += 1
+        Bn, H, W, Cin, Cout, k, s = a[11:18]
+        out = (ctypes.c_int * 16)()
+        assert lib.hl_conv2d_plan_info(1, Bn, H, W, Cin, Cout, k, s, int(a[5] is not None), int(a[9] is not None),
+                                       plan.SPLITK_BYTES, out) == 0
+        o = list(out)
+        assert o[0] == 1, ("tensor-core path must apply", a[11:18])
+        pair, mh, n_tile, halo, a_slots, b_slots, nbuf, acc, tmem, smem, grid, tiles, S, kc = o[1:15]
+        assert pair in (1, 2) and mh in (1, 2) and n_tile % 32 == 0 and 32 <= n_tile <= 256
+        assert smem <= (227 - 15) * 1024 and tmem <= 512 and tmem >= acc * mh * n_tile
+        assert a_slots >= 2 and b_slots >= 2 and 2 <= nbuf <= 4
+        assert 1 <= grid <= 148 and tiles >= 1
+        assert kc * S == Cin // 64
+        if S > 1:
+            n_split += 1
+            Ho, Wo = H // s, W // s
+            assert k == 3 and tiles <= 148 // (pair if pair == 2 else 1) * pair   # one wave
+            assert S * Bn * Ho * Wo * _lib.load().hl_conv_cout_pad(Cout) * 4 <= plan.SPLITK_BYTES
+            assert o[15] == 0                                    # statistics move to the second pass
+    assert n_conv == 280 and n_split >= 20

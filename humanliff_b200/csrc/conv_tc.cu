@@ -1022,20 +1022,31 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
         if (pair == 2 && ((c / 2) % 8 || c < 64)) return false;
         return true;
     };
-    auto ctas = [&](int c) { return (boxes / (mh * pair)) * (cout_pad / c) * pair; };
+    // N tile: the candidate with the cheapest K loop under the shared-memory model of DESIGN.md 5.1 -- rounds of
+    // tiles per CTA (pair) x bytes through shared memory per pipeline stage (MMA operand fetch of 4 instructions
+    // + the TMA writes of the weight rows and of the activation box / halo slab); the stage count is the same for
+    // every candidate.  Large problems get the widest tile (bytes per output column fall with N), problems of one
+    // to two waves the tile that avoids a second round (32^2: N = 128 in one round beats N = 64 in two: measured
+    // 26 vs 37 us), sub-wave problems the narrowest (most CTAs; split-K then takes over).  Ties go to the wider.
+    auto tiles_of = [&](int c) { return (boxes / (mh * pair)) * (cout_pad / c); };
+    auto stage_bytes = [&](int c) {
+        const double rows_b = (double)c / pair;
+        const double a_bytes = halo ? (double)HALO_ROW_BYTES * (mh + 2) / 9.0 : (double)mh * A_BOX_BYTES;
+        return 4.0 * (128.0 * mh + rows_b) * 32.0 + rows_b * ROW_BYTES + a_bytes;
+    };
     int n_tile = 0;
-    for (int c : cand)
-        if (legal(c) && ctas(c) >= sms) { n_tile = c; break; }
-    if (n_tile == 0) {
-        int best = -1;
+    {
+        const int units = pair == 2 ? sms / 2 : sms;
+        double best = 0.0;
         for (int c : cand) {
-            if (!legal(c) || c < 64 || c == 96) continue;     // swept: 64 / 128 / 192 / 256
-            const int n = ctas(c);
-            if (n <= sms && n > best) { best = n; n_tile = c; }
+            if (!legal(c) || c < 64 || c == 96) continue;         // swept: 64 / 128 / 192 / 256
+            const int rounds = (tiles_of(c) + units - 1) / units;
+            const double cost = rounds * stage_bytes(c);
+            if (n_tile == 0 || cost < best) { best = cost; n_tile = c; }
         }
         if (n_tile == 0)
             for (int c : cand)
-                if (legal(c)) { n_tile = c; break; }     // everything overshoots one wave: the widest tile
+                if (legal(c)) { n_tile = c; break; }
     }
     if (n_tile == 0 && pair == 2) {                      // e.g. Cout_pad = 32: no legal pair tile
         pair = 1;
@@ -1137,7 +1148,10 @@ int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int
     if (g_tune_split > 1) {
         if (p.kchunks % g_tune_split == 0 && (size_t)g_tune_split * slice_bytes <= ws_bytes) S = g_tune_split;
     } else if (ksize == 3 && !p.halo && pl.grid < sms && p.kchunks * p.taps >= 54) {
-        double best = cost(pl, 1) * 0.5;
+#ifndef HL_SPLIT_GAIN
+#define HL_SPLIT_GAIN 0.5
+#endif
+        double best = cost(pl, 1) * HL_SPLIT_GAIN;
         Plan best_pl = pl;
         const int keep_ntile = g_tune_ntile;
         static const int widths[] = {0, 128, 192, 256};          // 0 = the one-pass plan's own N tile

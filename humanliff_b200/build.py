@@ -49,6 +49,13 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "humanliff_b200.h"))
+    # whole-library stamp next to the .so: a snapshot that ships the library without the object directory (the GPU
+    # box) must not recompile 6 translation units just to find out nothing changed
+    lib_stamp = LIB_PATH + ".sha"
+    lib_digest = _digest([os.path.join(CSRC, src) for src in SOURCES] + headers)
+    if (not force and os.path.exists(LIB_PATH) and os.path.exists(lib_stamp)
+            and open(lib_stamp).read() == lib_digest):
+        return LIB_PATH
     objs = []
     relink = force or not os.path.exists(LIB_PATH)
     for src in SOURCES:
@@ -73,6 +80,8 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
+    with open(lib_stamp, "w") as f:
+        f.write(lib_digest)
     return LIB_PATH
 
 

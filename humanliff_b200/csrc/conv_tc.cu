@@ -1128,12 +1128,16 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
 // memory per stage (MMA operand fetch + TMA operand writes) -- and the cheapest is taken if it at least halves the
 // K-loop cost of the one-pass plan (the second pass is not free).  May replace `pl` by a plan with a wider N tile.
 // H, W are OUTPUT dims.  Returns the number of K slices (1 = no split).
+inline int split_batch(const Plan &pl, int B) { return (B + pl.t.bn - 1) / pl.t.bn * pl.t.bn; }
+
 int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, size_t ws_bytes) {
     TcParams &p = pl.p;
     int S = 1;
-    if (!ws_bytes || g_tune_split == 0 || Cout % 4 || B % pl.t.bn || p.kchunks < 2) return 1;
+    if (!ws_bytes || g_tune_split == 0 || Cout % 4 || p.kchunks < 2) return 1;
     const int sms = hl_num_sms();
-    const size_t slice_bytes = (size_t)B * H * W * pl.cout_pad * sizeof(float);
+    // a slice holds whole batch boxes: B rounded up to the box's sample count (the padding rows receive the zero
+    // rows TMA fills in for samples beyond B and are never read back)
+    const size_t slice_bytes = (size_t)split_batch(pl, B) * H * W * pl.cout_pad * sizeof(float);
     auto fits = [&](const Plan &q, int s) {
         return q.p.kchunks % s == 0 && (size_t)s * slice_bytes <= ws_bytes && q.grid * s <= sms &&
                (q.p.kchunks / s) * q.p.taps >= 12;
@@ -1163,7 +1167,7 @@ int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int
                 g_tune_ntile = wdt;
                 const bool ok = make_plan(kind, B, H, W, Cin, Cout, ksize, stride, false, false, &q);
                 g_tune_ntile = keep_ntile;
-                if (!ok || q.p.n_tile != wdt || q.p.halo || B % q.t.bn) continue;
+                if (!ok || q.p.n_tile != wdt || q.p.halo || q.t.bn != pl.t.bn) continue;
             }
             for (int s = 8; s >= 2; --s) {
                 if (!fits(q, s)) continue;
@@ -1313,7 +1317,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     if (S > 1) {
         p.ksplit = S;
         p.kc_split = p.kchunks / S;
-        p.split_b = B;
+        p.split_b = split_batch(pl, B);
         p.total_tiles = p.tiles_mn * S;
         const int sms = hl_num_sms();
         if (p.pair == 2) {
@@ -1377,7 +1381,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         const int esz_o = f16 ? 2 : 4;
         CUtensorMap *tm = which ? &tmR : &tmY;
         if (!ptr || (which && S > 1)) { *tm = tmY; continue; }
-        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : Cout), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * S};
+        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : Cout), (cuuint64_t)W, (cuuint64_t)H,
+                              (cuuint64_t)(S > 1 ? split_batch(pl, B) * S : B)};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
         cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
         if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
@@ -1421,7 +1426,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         const int HW = H * W;
         dim3 grid(hl_cdiv(Cout, 32), B);
         HL_CHECK_CUDA(hl_launch(k_splitk_reduce, grid, dim3(256), 0, stream, (const float *)wsp->ptr, S,
-                                (int64_t)B * HW * pl.cout_pad, pl.cout_pad, bias, residual, ldr, (void *)y_final,
+                                (int64_t)split_batch(pl, B) * HW * pl.cout_pad, pl.cout_pad, bias, residual, ldr, (void *)y_final,
                                 yf16_final, ldy_final, stats, stats_ld, HW, Cout));
         return HL_OK;
     }

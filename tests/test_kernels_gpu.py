@@ -321,7 +321,8 @@ def test_conv_fp16_output(dev, shape, residual, cta2):
     ((4, 16, 16, 1536, 768, 3, 1), -1),
     ((4, 32, 32, 768, 768, 3, 2), -1),    # stride-2 Downsample conv onto 16^2
     ((2, 16, 16, 384, 192, 1, 1), 3),     # forced: 1x1
-    ((3, 8, 8, 128, 64, 3, 1), 2),        # bn = 2 with B = 3: split refused (partial batch box), one-pass result
+    ((3, 8, 8, 128, 64, 3, 1), 2),        # bn = 2 with B = 3: the last batch box is half empty (slice padded to 4 samples)
+    ((1, 8, 8, 768, 768, 3, 1), -1),      # B = 1 (layer-by-layer generation): automatic split with a padded slice
     ((1, 128, 128, 192, 192, 3, 1), 3),   # forced on the HALO operand path
     ((2, 32, 32, 384, 384, 3, 1), 2)])
 @pytest.mark.parametrize("residual", [False, True])

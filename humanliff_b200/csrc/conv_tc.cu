@@ -22,15 +22,25 @@
 //
 //   persistent  grid = min(tiles, SMs); each CTA walks tiles t = blockIdx.x + i*gridDim.x (n-tile
 //               fastest so concurrently running CTAs share activations in L2).
+//   CTA pairs   wherever the 128-pixel boxes pair up the kernel runs as 2-CTA clusters issuing
+//               tcgen05.mma.cta_group::2 (M = 256: each SM supplies its 128 A rows and half of the B rows;
+//               the leader CTA issues, barriers are reached through mapa / shared::cluster).
 //   warp roles  warp 0: A producer (TMA)   warp 1: B producer (TMA)   warp 2: TMEM alloc + MMA issue
-//               warps 3-6: epilogue.  Two independent smem rings (A, B) with full/empty mbarriers;
-//               tcgen05.commit releases slots; TMEM accumulators are double-buffered when they fit
-//               (acc_stages = 2) so the epilogue of tile i overlaps the main loop of tile i+1.
+//               warps 3-10: two epilogue warpgroups on alternate 32-column chunks.  Two independent smem
+//               rings (A, B) with full/empty mbarriers; tcgen05.commit releases slots; TMEM accumulators
+//               are double-buffered when they fit (acc_stages = 2) so the epilogue of tile i overlaps the
+//               main loop of tile i+1.
+//   split-K     sub-wave 3x3 layers: K cut into S channel-chunk slices over S x the CTAs, fp32 partial tiles
+//               into a caller-registered workspace, fixed-order second pass (k_splitk_reduce).
+//   planning    N tile and (N tile, S) are chosen by a shared-memory-bandwidth cost model (make_plan,
+//               choose_split): measured, the kernel is bound by the ~92 B/clk/SM that MMA
+//               operand fetch, TMA operand writes and the epilogue share.
 //   epilogue    tcgen05.ld (32 columns) -> + bias (+ residual, TMA-prefetched into the staging
 //               buffer, added in place) -> swizzled smem staging -> TMA store (coalesced, clipped
-//               at the tensor edge); optional per-channel sum / sum-of-squares of the OUTPUT
-//               (the following GroupNorm's statistics), accumulated per CTA in shared memory and
-//               flushed with fp64 atomics once per sample.
+//               at the tensor edge; fp32, or the fp16 operand directly with HL_CONV_OUT_F16); optional
+//               per-channel sum / sum-of-squares of the OUTPUT (the following GroupNorm's statistics),
+//               combined in a fixed order per chunk, accumulated per CTA in fp64 shared memory and flushed
+//               with fp64 atomics once per sample.
 //
 // Algorithmic work per launch: 2*M*N*K flop; compulsory HBM bytes: e*(M*Cin + taps*Cout*Cin) +
 // 4*M*Cout (+ 4*M*Cout residual), e = operand bytes per element.

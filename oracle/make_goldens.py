@@ -241,6 +241,26 @@ def density_grid_case(name, res=24, seed_w=3):
     print(name, "done", flush=True)
 
 
+def contract_case(name):
+    """state_dict key -> shape of the reference modules (the checkpoint contract of SURVEY.md 8(b)), as JSON."""
+    import json
+    su = ref_shims.import_diffusion()
+    out = {}
+    model, _ = su.create_model_and_diffusion(**PROD)
+    out["unet_production"] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    model, _ = su.create_model_and_diffusion(**dict(TINY, cond_type="", class_cond=False))
+    out["unet_tiny_unconditional"] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    hd = ref_shims.import_hd_renderer()
+    r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+    out["renderer_hd"] = [[k, list(v.shape)] for k, v in r.state_dict().items()]
+    rn = ref_shims.import_rn_renderer()
+    r = rn.Renderer(use_canonical_space=False, num_instances=2, triplane_dim=256, triplane_ch=27, test=True)
+    out["renderer_rn_2_instances"] = [[k, list(v.shape)] for k, v in r.state_dict().items()]
+    with open(os.path.join(OUT, name), "w") as f:
+        json.dump(out, f)
+    print(name, "done", {k: len(v) for k, v in out.items()}, flush=True)
+
+
 def variants_case(name):
     """Flag-envelope variants on the tiny model (B = 1, 27 x 32 x 32), straight from the reference:
     (a) unconditional UNet (cond_type='', class_cond=False);  (b) p_sample with rescale_timesteps=True on a 500-step
@@ -317,7 +337,7 @@ if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn", "density"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn", "density", "contract"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -326,6 +346,8 @@ if __name__ == "__main__":
         ddim_case("ddim_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], etas=[0.0, 0.5], seed_w=11)
     if "prod64" in which:
         unet_case("unet_prod_64.npz", PROD, B=1, HW=64, ts=[0, 100, 249], seed_w=0, loop_steps=6)
+    if "contract" in which:
+        contract_case("state_dict_contract.json")
     if "density" in which:
         density_grid_case("density_grid_24.npz")
     if "render_rn" in which:

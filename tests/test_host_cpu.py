@@ -173,3 +173,29 @@ def test_conv_planner_on_every_production_launch(B):
             assert S * Bn * Ho * Wo * _lib.load().hl_conv_cout_pad(Cout) * 4 <= plan.SPLITK_BYTES
             assert o[15] == 0                                    # statistics move to the second pass
     assert n_conv == 280 and n_split >= 20
+
+
+def test_state_dict_contract_vs_reference():
+    """Checkpoint contract: the key list (in order) and every shape of the product modules'
+    state_dict() equal what the reference modules produce (golden state_dict_contract.json, frozen from the
+    reference by oracle/make_goldens.py contract) -- reference checkpoints load with strict=True."""
+    import json
+    from common import GOLDEN, PROD, TINY
+    from humanliff_b200 import factory
+    from humanliff_b200.renderer import ReconRenderer, Renderer
+    with open(os.path.join(GOLDEN, "state_dict_contract.json")) as f:
+        ref = json.load(f)
+
+    def contract(module):
+        return [[k, list(v.shape)] for k, v in module.state_dict().items()]
+
+    model, _ = factory.create_model_and_diffusion(**PROD)
+    assert contract(model) == ref["unet_production"]
+    model, _ = factory.create_model_and_diffusion(**dict(TINY, cond_type="", class_cond=False))
+    assert contract(model) == ref["unet_tiny_unconditional"]
+    got = dict((k, s) for k, s in contract(Renderer(use_canonical_space=False, triplane_ch=27, test=True)))
+    assert got == dict((k, s) for k, s in ref["renderer_hd"]), set(got) ^ set(k for k, _ in ref["renderer_hd"])
+    got = dict((k, s) for k, s in contract(ReconRenderer(use_canonical_space=False, num_instances=2, triplane_dim=256,
+                                                          triplane_ch=27, test=True)))
+    want = dict((k, s) for k, s in ref["renderer_rn_2_instances"])
+    assert got == want, set(got) ^ set(want)

@@ -256,9 +256,11 @@ def contract_case(name):
     rn = ref_shims.import_rn_renderer()
     r = rn.Renderer(use_canonical_space=False, num_instances=2, triplane_dim=256, triplane_ch=27, test=True)
     out["renderer_rn_2_instances"] = [[k, list(v.shape)] for k, v in r.state_dict().items()]
+    out["model_and_diffusion_defaults"] = su.model_and_diffusion_defaults()          # script_util.py:11-39
+    out["NUM_CLASSES"] = su.NUM_CLASSES
     with open(os.path.join(OUT, name), "w") as f:
         json.dump(out, f)
-    print(name, "done", {k: len(v) for k, v in out.items()}, flush=True)
+    print(name, "done", {k: (len(v) if hasattr(v, "__len__") else v) for k, v in out.items()}, flush=True)
 
 
 def variants_case(name):

@@ -189,6 +189,13 @@ def test_state_dict_contract_vs_reference():
     def contract(module):
         return [[k, list(v.shape)] for k, v in module.state_dict().items()]
 
+    # the 23 flags of script_util.model_and_diffusion_defaults (plus this package's optional `precision`)
+    mine = factory.model_and_diffusion_defaults()
+    for k, v in ref["model_and_diffusion_defaults"].items():
+        assert k in mine and mine[k] == v, (k, v, mine.get(k))
+    assert set(mine) - set(ref["model_and_diffusion_defaults"]) <= {"precision"}
+    assert factory.NUM_CLASSES == ref["NUM_CLASSES"] == 4
+
     model, _ = factory.create_model_and_diffusion(**PROD)
     assert contract(model) == ref["unet_production"]
     model, _ = factory.create_model_and_diffusion(**dict(TINY, cond_type="", class_cond=False))

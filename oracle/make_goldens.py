@@ -256,6 +256,15 @@ def contract_case(name):
     rn = ref_shims.import_rn_renderer()
     r = rn.Renderer(use_canonical_space=False, num_instances=2, triplane_dim=256, triplane_ch=27, test=True)
     out["renderer_rn_2_instances"] = [[k, list(v.shape)] for k, v in r.state_dict().items()]
+    from improved_diffusion import respace
+    cases = []
+    for T, sec in [(1000, "ddim50"), (1000, "ddim333"), (1000, "ddim7"), (300, "10,10,10"), (10, "20"), (1000, "1000"),
+                   (1000, "999"), (100, "5,200"), (1000, "250"), (1000, "1"), (50, "ddim25")]:
+        try:
+            cases.append([T, sec, sorted(respace.space_timesteps(T, sec))])
+        except Exception as e:                                                       # respace.py:30,47
+            cases.append([T, sec, type(e).__name__])
+    out["space_timesteps_cases"] = cases
     out["model_and_diffusion_defaults"] = su.model_and_diffusion_defaults()          # script_util.py:11-39
     out["NUM_CLASSES"] = su.NUM_CLASSES
     with open(os.path.join(OUT, name), "w") as f:

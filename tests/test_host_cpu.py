@@ -195,6 +195,14 @@ def test_state_dict_contract_vs_reference():
         assert k in mine and mine[k] == v, (k, v, mine.get(k))
     assert set(mine) - set(ref["model_and_diffusion_defaults"]) <= {"precision"}
     assert factory.NUM_CLASSES == ref["NUM_CLASSES"] == 4
+    # space_timesteps (respace.py:7-60) incl. the ddimN form and its error cases
+    from humanliff_b200 import space_timesteps
+    for T, sec, want in ref["space_timesteps_cases"]:
+        try:
+            got = sorted(space_timesteps(T, sec))
+        except Exception as e:
+            got = type(e).__name__
+        assert got == want, (T, sec)
 
     model, _ = factory.create_model_and_diffusion(**PROD)
     assert contract(model) == ref["unet_production"]

@@ -50,7 +50,38 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
 
+    # NVML clocks-event-reason bits (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+    NVML_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+
+    def _nvml_loop(self):
+        import pynvml
+        h, rows = self._nvml_handle, self.rows
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                rows.append(["nvml", str(sm), str(mx), "", ""] +
+                            ["Active" if mask & bit else "Not Active"
+                             for bit in (0x8, 0x40, 0x20, 0x4)])       # column order of Q: hw, hw_thermal, sw_thermal, power
+            except Exception:
+                break
+            self._stop.wait(0.005)
+
     def start(self):
+        # NVML directly (a sample every ~5 ms: the timed region of a default run is only ~150 ms); nvidia-smi as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml_handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(self._nvml_handle, pynvml.NVML_CLOCK_SM)
+            self._stop = threading.Event()
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            self.proc = "nvml"
+            return
+        except Exception:
+            self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -67,11 +98,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self._stop.set()
+            self.th.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], None, set()
         for r in self.rows:
             try:
@@ -84,7 +119,8 @@ class ClockSampler:
         sm.sort()
         # median over the samples taken under load (upper half of the clock distribution excluded idle)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "sm_min_mhz": sm[0] if sm else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml" if self.proc == "nvml" else "nvidia-smi"}
 
 
 def build_model(device, precision="fp16"):

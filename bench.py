@@ -222,32 +222,156 @@ def render_throughput(device, n_rays=262144, reps=3):
                     "(throughput mode); MLP on mma.sync fp16 / fp32 accumulate"}
 
 
-def cpu_baseline(sd, threads, steps=2):
-    """Oracle port of the reference's p_sample on the host cores: B=1, 27x256x256, `steps` timed steps
-    after one warm-up (a bounded sample of the B=4 workload; sample-steps/s is batch-size invariant on
-    the CPU path)."""
-    from oracle.diffusion_oracle import DiffusionOracle
-    torch.set_num_threads(threads)
-    orc = DiffusionOracle(1000, "")
+def _reference_root():
+    """oracle/_ref (the unmodified reference staged by oracle/build_ref.py; travels to the GPU box) if present and
+    unmodified, else /root/reference when it exists (this container), else None -> the oracle port is timed."""
+    from oracle import build_ref
+    if build_ref.available() and build_ref.verify():
+        return build_ref.DEST
+    if os.path.isdir("/root/reference/human_diffusion/improved_diffusion"):
+        return "/root/reference"
+    return None
+
+
+class CpuDenoise:
+    """The reference's CPU implementation of one p_sample at 27x256x256: the UNMODIFIED reference
+    (``SpacedDiffusion.p_sample`` over ``UNetModel``, kind "reference") when a copy is available, else the oracle
+    port (kind "port").  Weights = the same synthetic state dict the GPU arm loads."""
+
+    def __init__(self, sd, threads):
+        torch.set_num_threads(threads)
+        self.sd = sd
+        root = _reference_root()
+        self.kind = "port"
+        if root is not None:
+            try:
+                from humanliff_b200 import factory
+                from oracle import ref_shims
+                ref_shims.use(root)
+                su = ref_shims.import_diffusion()
+                flags = factory.production_flags("")
+                self.model, self.diffusion = su.create_model_and_diffusion(**flags)
+                self.model.load_state_dict(sd, strict=True)
+                self.model.eval()
+                self.kind, self.root = "reference", root
+            except Exception as e:                       # noqa: BLE001 -- fall back to the port, say why
+                self.why = repr(e)[:200]
+        if self.kind == "port":
+            from oracle.diffusion_oracle import DiffusionOracle
+            self.orc = DiffusionOracle(1000, "")
+
+    @torch.no_grad()
+    def p_sample(self, x, xc, t, y, z):
+        if self.kind == "reference":
+            orig = torch.randn_like
+            torch.randn_like = lambda *a, **k: z          # the reference draws randn_like(x): inject ours
+            try:
+                return self.diffusion.p_sample(self.model, x, xc, t, clip_denoised=True, model_kwargs={"y": y})["sample"]
+            finally:
+                torch.randn_like = orig
+        return self.orc.p_sample(self.sd, x, xc, t, y, z)["sample"]
+
+    def describe(self):
+        if self.kind == "reference":
+            return "UNMODIFIED reference (improved_diffusion SpacedDiffusion.p_sample, torch CPU fp32) from %s" % (
+                "oracle/_ref" if self.root.endswith("_ref") else self.root)
+        return "oracle port of the reference p_sample (torch CPU fp32; oracle/_ref not staged)"
+
+
+def cpu_inputs(B):
     g = torch.Generator().manual_seed(1234)
-    x = torch.randn(1, C, HW, HW, generator=g)
-    xc = torch.zeros(1, C, HW, HW)
-    y = torch.tensor([0])
+    x = torch.randn(B, C, HW, HW, generator=g)
+    return x, torch.zeros(B, C, HW, HW), (torch.arange(B) % 4), torch.randn(B, C, HW, HW, generator=g)
+
+
+def cpu_baseline(sd, threads, steps=2):
+    """Bounded sample of the workload on the host cores: p_sample on ONE sample (1/4 of the batch), `steps` timed
+    steps after one warm-up (sample-steps/s is batch-size invariant on the CPU path)."""
+    arm = CpuDenoise(sd, threads)
+    x, xc, y, z = cpu_inputs(1)
     t = torch.tensor([500])
-    z = torch.randn(1, C, HW, HW, generator=g)
-    orc.p_sample(sd, x, xc, t, y, z)
+    arm.p_sample(x, xc, t, y, z)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.p_sample(sd, x, xc, t, y, z)
+        arm.p_sample(x, xc, t, y, z)
     dt = (time.perf_counter() - t0) / steps
-    return 1.0 / dt, dt
+    return 1.0 / dt, dt, arm
+
+
+class CpuRender:
+    """The reference's CPU render path on one 16,384-ray chunk of the 512x512 synthetic camera (the reference's own
+    chunk size, all_test.py:52,153): the UNMODIFIED ``human_diffusion/NeRF/renderer.py`` ``Renderer.render`` when a
+    copy is available, else the oracle port."""
+
+    def __init__(self, threads, n_rays=16384):
+        from humanliff_b200 import synth
+        torch.set_num_threads(threads)
+        self.n = n_rays
+        self.planes = synth.synth_triplane(256, seed=7)
+        self.bounds = torch.tensor(synth.WORLD_BOUNDS)
+        ro, rd, near, far, _ = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=30.0)
+        sel = slice(512 * 192, 512 * 192 + n_rays)               # rows through the middle of the body box
+        self.ro, self.rd, self.near, self.far = (t[sel].contiguous() for t in (ro, rd, near, far))
+        self.u = torch.rand(n_rays, 128, generator=torch.Generator().manual_seed(99))
+        shapes = None
+        root = _reference_root()
+        self.kind = "port"
+        if root is not None:
+            try:
+                from oracle import ref_shims
+                ref_shims.use(root)
+                hd = ref_shims.import_hd_renderer()
+                torch.manual_seed(0)
+                self.r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+                shapes = {k: v.shape for k, v in self.r.state_dict().items() if not k.startswith("view_enc")}
+                self.sd = synth.synth_state_dict(shapes, seed=3, weight_gain=1.5)
+                self.r.load_state_dict(self.sd, strict=False)
+                self.kind, self.root = "reference", root
+            except Exception as e:                       # noqa: BLE001
+                self.why = repr(e)[:200]
+        if self.kind == "port":
+            from humanliff_b200.renderer import Renderer
+            r = Renderer(triplane_ch=27, test=True)
+            shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+            self.sd = synth.synth_state_dict(shapes, seed=3, weight_gain=1.5)
+
+    @torch.no_grad()
+    def render(self):
+        ro, rd, near, far = self.ro, self.rd, self.near, self.far
+        if self.kind == "reference":
+            orig = torch.rand
+            torch.rand = lambda *a, **k: self.u.clone()          # sample_pdf draws torch.rand([rays, 128]) on the CPU
+            try:
+                t = torch.linspace(0., 1., steps=128)            # run_nerf_batch.py:46-57 (hard-codes device='cuda')
+                z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+                pts = ro[None, :, None, :] + rd[None, :, None, :] * z[..., :, None]
+                ret = self.r.render({"world_bounds": self.bounds[None]}, pts.reshape(1, -1, 3), z, ro[None], rd[None],
+                                    near[None, :, None], far[None, :, None], self.planes, 128, False)
+                return ret["rgb_map"][0]
+            finally:
+                torch.rand = orig
+        from oracle import render_oracle
+        return render_oracle.render_rays(self.sd, self.planes[0], self.bounds, ro, rd, near, far, self.u)[0]
+
+    def time(self, reps=1):
+        self.render()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            self.render()
+        dt = (time.perf_counter() - t0) / reps
+        return self.n / dt, dt
 
 
 WORKLOAD = ("1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); one step = one p_sample "
             "(UNet 497M params + posterior update)")
+RENDER_METRIC = "rendered rays/sec (128+128 samples/ray, 27x256x256 tri-plane)"
 
 
 def run_reference(args):
+    """The reference's own CPU implementation, all host threads, same config as the GPU arm: B = --batch samples
+    of 27x256x256 per p_sample step, --warmup untimed + --steps timed steps of the 1000-step chain (t = 999, 998,
+    ...).  If a B-sample step is so slow that the run would not end within ~6 minutes the per-step sample falls
+    back to ONE sample (stated in `config.reference_sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -257,30 +381,47 @@ def run_reference(args):
     model, _ = factory.create_model_and_diffusion(**factory.production_flags(""))
     sd = synth.synth_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=0)
     del model
-    from oracle.diffusion_oracle import DiffusionOracle
-    orc = DiffusionOracle(1000, "")
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(1, C, HW, HW, generator=g)
-    xc, y, z = torch.zeros(1, C, HW, HW), torch.tensor([0]), torch.randn(1, C, HW, HW, generator=g)
-    for _ in range(min(args.warmup, 1)):
-        orc.p_sample(sd, x, xc, torch.tensor([999]), y, z)
+    arm = CpuDenoise(sd, threads)
+    B = args.batch
+    x, xc, y, z = cpu_inputs(B)
+    W = max(args.warmup, 0)
+    t0 = time.perf_counter()
+    arm.p_sample(x[:1], xc[:1], torch.tensor([999]), y[:1], z[:1])          # untimed probe: cost of one sample
+    probe = time.perf_counter() - t0
+    if probe * B * (args.steps + W) > 360.0:
+        B, note = 1, ("each timed step = p_sample on ONE sample (1/%d of the batch; a full-batch run would take "
+                      "%.0f s): sample-steps/s is batch-size invariant on the CPU path" % (args.batch, probe * args.batch * (args.steps + W)))
+        x, xc, y, z = x[:1], xc[:1], y[:1], z[:1]
+    else:
+        note = "each timed step = p_sample on the full batch of %d samples (same config as the GPU arm)" % B
+    for k in range(W):
+        arm.p_sample(x, xc, torch.full((B,), 999 - k), y, z)
+    img = x
     t0 = time.perf_counter()
     for k in range(args.steps):
-        x = orc.p_sample(sd, x, xc, torch.tensor([999 - k]), y, z)["sample"]
+        img = arm.p_sample(img, xc, torch.full((B,), 999 - k), y, z)
     dt = time.perf_counter() - t0
-    v = args.steps / dt
-    sample = "oracle port of p_sample, B=1 x 27x256x256 per step (1/4 of the B=4 workload), %d threads" % threads
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT,
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-                      "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
-                                 "resolution": "27x256x256",
-                                 "reference_sample": "each timed step = p_sample on ONE sample (1/%d of the batch): "
-                                                     "sample-steps/s is batch-size invariant on the CPU path "
-                                                     "(BASELINE.md section 3)" % args.batch},
-                      "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-                      "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    v = B * args.steps / dt
+    sample = "%s, B=%d x 27x256x256 per step, %d threads" % (arm.describe(), B, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
+            "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "resolution": "27x256x256", "reference_sample": note},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": sample},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_render:
+        try:
+            cr = CpuRender(threads)
+            rv, rdt = cr.time()
+            line["render"] = {"metric": RENDER_METRIC, "value": round(rv, 1), "unit": "rays/s", "impl": "reference",
+                              "cpu_baseline": {"value": round(rv, 1), "unit": "rays/s", "cores": threads, "kind": cr.kind,
+                                               "sample": "Renderer.render on one 16,384-ray chunk of the 512x512 camera "
+                                                         "(%.1f s), injected uniforms" % rdt}}
+        except Exception as e:                      # noqa: BLE001
+            line["render"] = {"error": repr(e)[:200]}
+    print(json.dumps(line))
 
 
 def run_ours(args):
@@ -409,10 +550,11 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt = cpu_baseline(sd, threads)
-            cpu = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "oracle port of the reference p_sample (torch CPU fp32), B=1 x 27x256x256, 2 timed "
-                             "steps after 1 warm-up (%.1f s/step)" % dt}
+            v, dt, arm = cpu_baseline(sd, threads)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": arm.kind,
+                   "sample": "%s, B=1 x 27x256x256 (1/%d of the batch), 2 timed steps after 1 warm-up "
+                             "(%.1f s/step)" % (arm.describe(), B, dt)}
+            del arm
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,

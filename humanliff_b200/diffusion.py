@@ -67,6 +67,9 @@ def _extract_into_tensor(arr, timesteps, broadcast_shape):
     return res.expand(broadcast_shape)
 
 
+_RNG_STATE = {}          # device index -> [seed, draws so far] of the in-kernel Philox generator
+
+
 class GaussianDiffusion:
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False):
         self.model_mean_type = model_mean_type
@@ -132,36 +135,79 @@ class GaussianDiffusion:
         return t
 
     # ------------------------------------------------------------------ sampling
-    def _fused_step(self, x, eps, noise, t, clip_denoised, want_x0=True):
+    def _rng_draw(self, device):
+        """(seed, draw counter) of the in-kernel Philox generator: the seed follows the device's torch generator
+        (``torch.manual_seed`` restarts the sequence), every draw advances a host-side counter."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        seed = int(torch.cuda.default_generators[idx].initial_seed()) & ((1 << 64) - 1)
+        st = _RNG_STATE.setdefault(idx, [None, 0])
+        if st[0] != seed:
+            st[0], st[1] = seed, 0
+        st[1] += 1
+        return seed, st[1] - 1
+
+    def _coerce(self, ref, t, name):
+        """fp32, contiguous, on ``ref``'s device -- the kernels read raw pointers."""
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            raise TypeError(f"{name} must be a tensor")
+        if t.device != ref.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=ref.device, dtype=torch.float32).contiguous()
+        if t.shape != ref.shape:
+            raise ValueError(f"{name} shape {tuple(t.shape)} != x shape {tuple(ref.shape)}")
+        return t
+
+    def _fused_step(self, x, eps, noise, t, clip_denoised, want_x0=True, x0_given=None):
+        """One launch: x0 = clip(c0 x - c1 eps) (or ``x0_given``); sample = c2 x0 + c3 x + sigma_t z, with
+        z = ``noise`` or, if None, drawn inside the kernel (Philox)."""
+        if not x.is_cuda:
+            raise RuntimeError("humanliff_b200 sampling runs on CUDA (sm_100a) only -- no CPU fallback")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()
         tb = self._tables(x.device)
         B = x.shape[0]
         n = x[0].numel()
-        x = x.contiguous()
-        eps = eps.contiguous()
-        noise = noise.contiguous()
+        eps = self._coerce(x, eps, "eps")
+        noise = self._coerce(x, noise, "noise")
+        x0_given = self._coerce(x, x0_given, "x0")
         sample = torch.empty_like(x)
         x0 = torch.empty_like(x) if want_x0 else None
-        t64 = t if t.dtype == torch.int64 else t.long()
+        t64 = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if t64.shape != (B,):
+            raise ValueError(f"t must have shape ({B},)")
+        seed, draw = (0, 0) if noise is not None else self._rng_draw(x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        call("hl_ddpm_step", x.data_ptr(), eps.data_ptr(), noise.data_ptr(), tb["coef"].data_ptr(),
-             tb["sigma"].data_ptr(), t64.data_ptr(), sample.data_ptr(),
-             x0.data_ptr() if x0 is not None else None, B, n, 1 if clip_denoised else 0, stream)
+        call("hl_ddpm_posterior" if x0_given is not None else "hl_ddpm_step_rng", x.data_ptr(),
+             (x0_given if x0_given is not None else eps).data_ptr(), noise.data_ptr() if noise is not None else None,
+             tb["coef"].data_ptr(), tb["sigma"].data_ptr(), t64.data_ptr(), self.num_timesteps, sample.data_ptr(),
+             x0.data_ptr() if x0 is not None else None, B, n, 1 if clip_denoised else 0, None, seed, draw, stream)
         return sample, x0
+
+    def _denoise(self, model, x, t, x_cond, clip_denoised, denoised_fn, model_kwargs, noise):
+        """eps-prediction + posterior; returns (sample, pred_xstart, eps)."""
+        if model_kwargs is None:
+            model_kwargs = {}
+        if t.shape != (x.shape[0],):
+            raise ValueError(f"t must have shape ({x.shape[0]},)")
+        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
+        if denoised_fn is None:
+            sample, x0 = self._fused_step(x, eps, noise, t, clip_denoised)
+        else:
+            # gaussian_diffusion.py:293-298: x0 = denoised_fn(c0 x - c1 eps) BEFORE the clamp
+            _, x0_raw = self._fused_step(x, eps, torch.zeros_like(x), t, False)
+            sample, x0 = self._fused_step(x, None, noise, t, clip_denoised, x0_given=denoised_fn(x0_raw))
+        return sample, x0, eps
 
     def p_mean_variance(self, model, x, t, x_cond=None, clip_denoised=True, denoised_fn=None,
                         model_kwargs=None):
         """gaussian_diffusion.py:232-326 -- NB argument order (model, x, t, x_cond=None, ...)."""
-        if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
-        if model_kwargs is None:
-            model_kwargs = {}
         B = x.shape[0]
-        assert t.shape == (B,)
-        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
+        mean, x0, eps = self._denoise(model, x, t, x_cond, clip_denoised, denoised_fn, model_kwargs,
+                                      torch.zeros_like(x))
         tb = self._tables(x.device)
-        zeros = torch.zeros_like(x)
-        mean, x0 = self._fused_step(x, eps, zeros, t, clip_denoised)
         shape = [B] + [1] * (x.dim() - 1)
+        t = t.to(device=x.device, dtype=torch.int64)
         return {"mean": mean,
                 "variance": tb["var"][t].view(shape).expand(x.shape),
                 "log_variance": tb["logvar"][t].view(shape).expand(x.shape),
@@ -170,41 +216,56 @@ class GaussianDiffusion:
     def p_sample(self, model, x, x_cond, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                  noise=None):
         """gaussian_diffusion.py:356-388 -- NB argument order (model, x, x_cond, t, ...).
-        ``noise`` (extension): inject the per-step Gaussian instead of drawing ``randn_like(x)``."""
-        if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
-        if model_kwargs is None:
-            model_kwargs = {}
-        assert t.shape == (x.shape[0],)
-        eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
-        if noise is None:
-            noise = torch.randn_like(x)
-        sample, x0 = self._fused_step(x, eps, noise, t, clip_denoised)
+        ``noise`` (extension): inject the per-step Gaussian; None -> drawn inside the posterior kernel."""
+        sample, x0, _ = self._denoise(model, x, t, x_cond, clip_denoised, denoised_fn, model_kwargs, noise)
         return {"sample": sample, "pred_xstart": x0}
 
     def p_sample_loop(self, model, shape, x_cond=None, noise=None, clip_denoised=True, denoised_fn=None,
                       model_kwargs=None, device=None, progress=False, step_noise=None):
         final = None
-        for sample in self.p_sample_loop_progressive(model, shape, x_cond=x_cond, noise=noise,
-                                                     clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                                     model_kwargs=model_kwargs, device=device,
-                                                     progress=progress, step_noise=step_noise):
+        for sample in self._sample_loop(model, shape, x_cond, noise, clip_denoised, denoised_fn, model_kwargs,
+                                        device, progress, step_noise, fresh=False):
             final = sample
-        return final["sample"]
+        return final["sample"].clone()
 
     def p_sample_loop_progressive(self, model, shape, x_cond=None, noise=None, clip_denoised=True,
                                   denoised_fn=None, model_kwargs=None, device=None, progress=False,
                                   step_noise=None):
         """gaussian_diffusion.py:434-482.  ``step_noise`` (extension): callable ``i -> tensor`` that
         supplies the Gaussian of step i (parity tests inject the oracle's noise)."""
+        return self._sample_loop(model, shape, x_cond, noise, clip_denoised, denoised_fn, model_kwargs, device,
+                                 progress, step_noise, fresh=True)
+
+    def _initial_noise(self, shape, device):
+        """th.randn(*shape, device=device) (gaussian_diffusion.py:460) from the in-kernel generator."""
+        img = torch.empty(*shape, device=device, dtype=torch.float32)
+        if img.numel() % 4:
+            return torch.randn(*shape, device=device)
+        seed, draw = self._rng_draw(img.device)
+        call("hl_randn", img.data_ptr(), img.numel(), None, seed, draw, torch.cuda.current_stream(img.device).cuda_stream)
+        return img
+
+    def _sample_loop(self, model, shape, x_cond, noise, clip_denoised, denoised_fn, model_kwargs, device, progress,
+                     step_noise, fresh):
+        """``fresh``: yield freshly allocated tensors every step (the reference's generator semantics); the
+        non-progressive loop passes False and the per-step dicts alias the loop's static buffers."""
         if device is None:
             device = next(model.parameters()).device
+        device = torch.device(device)
         assert isinstance(shape, (tuple, list))
-        img = noise if noise is not None else torch.randn(*shape, device=device)
         indices = list(range(self.num_timesteps))[::-1]
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
+        img = noise if noise is not None else self._initial_noise(shape, device)
+        loop = _GraphLoop.build(self, model, img, x_cond, model_kwargs, clip_denoised, denoised_fn,
+                                step_noise is not None, want_x0=fresh)
+        if loop is not None:
+            # one CUDA-graph replay per step: UNet + posterior (+ in-kernel noise) + on-device t / RNG advance
+            loop.start(img, x_cond, model_kwargs, self.num_timesteps - 1)
+            for i in indices:
+                yield loop.step(step_noise(i) if step_noise is not None else None, fresh)
+            return
         t = torch.empty(shape[0], device=device, dtype=torch.int64)
         for i in indices:
             t.fill_(i)
@@ -245,18 +306,21 @@ class GaussianDiffusion:
         """gaussian_diffusion.py:484-529 -- NB argument order (model, x, t, x_cond=None, ...), unlike p_sample.
         ``noise`` (extension): inject the Gaussian instead of drawing ``randn_like(x)``."""
         if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is not used by any HumanLiff entry point")
+            raise NotImplementedError("denoised_fn with DDIM is not used by any HumanLiff entry point")
         if model_kwargs is None:
             model_kwargs = {}
+        if not x.is_cuda:
+            raise RuntimeError("humanliff_b200 sampling runs on CUDA (sm_100a) only -- no CPU fallback")
         assert t.shape == (x.shape[0],)
         eps = model(x, self._scale_timesteps(t), x_cond, **model_kwargs)
         tb = self._ddim_tables(x.device, eta)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()
         if noise is None and eta != 0.0:
-            noise = torch.randn_like(x)
-        x, eps = x.contiguous(), eps.contiguous()
-        noise = noise.contiguous() if noise is not None else None
+            noise = self._initial_noise(tuple(x.shape), x.device)
+        eps, noise = self._coerce(x, eps, "eps"), self._coerce(x, noise, "noise")
         sample, x0 = torch.empty_like(x), torch.empty_like(x)
-        t64 = t if t.dtype == torch.int64 else t.long()
+        t64 = t.to(device=x.device, dtype=torch.int64).contiguous()
         stream = torch.cuda.current_stream(x.device).cuda_stream
         call("hl_ddim_step", x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None,
              tb["coef"].data_ptr(), tb["sigma"].data_ptr(), t64.data_ptr(), sample.data_ptr(), x0.data_ptr(),
@@ -280,7 +344,7 @@ class GaussianDiffusion:
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
-        img = noise if noise is not None else torch.randn(*shape, device=device)
+        img = noise if noise is not None else self._initial_noise(shape, torch.device(device))
         indices = list(range(self.num_timesteps))[::-1]
         if progress:
             from tqdm.auto import tqdm
@@ -392,3 +456,109 @@ class _WrappedModel:
         if self.rescale_timesteps:
             new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
         return self.model(x, new_ts, x_cond, **kwargs)
+
+
+class _GraphLoop:
+    """The body of p_sample_loop as ONE CUDA graph per step (SURVEY.md 7.2 K11 / VERDICT r1 item 8):
+
+        UNet forward (the model's compiled launch plan, reading its static x / x_cond / t / y buffers)
+        -> hl_ddpm_step_rng: eps = plan.out, writes the next x_t straight back into the plan's x buffer
+           (noise drawn in the kernel, or read from a static buffer the caller refills when injected)
+        -> hl_loop_advance: t -= 1, model timestep = map[t] (respace.py:117-122), RNG draw counter += 1.
+
+    Nothing runs on the host between replays: no ``t.fill_``, no ``timestep_map[ts]`` index kernel, no input
+    copies (x_cond / y are uploaded once per loop), no ``randn_like``.  Only built for this package's UNetModel
+    with CUDA graphs on and no ``denoised_fn``; anything else takes the generic per-step path."""
+
+    @staticmethod
+    def build(diffusion, model, img, x_cond, model_kwargs, clip, denoised_fn, injected, want_x0):
+        from .unet import UNetModel, _StepPlan
+        inner = model.model if isinstance(model, _WrappedModel) else model
+        if (denoised_fn is not None or not isinstance(inner, UNetModel) or not inner.use_cuda_graph
+                or not img.is_cuda or img.dim() != 4):
+            return None
+        extra = set((model_kwargs or {}).keys()) - {"y"}
+        if extra:
+            return None
+        B, _, H, W = img.shape
+        with torch.cuda.device(img.device):
+            plan = inner.plan_for(img.device, B, H, W)
+        if type(plan) is not _StepPlan:
+            return None
+        key = (id(diffusion), bool(clip), bool(injected), bool(want_x0))
+        loops = plan.__dict__.setdefault("_loops", {})
+        loop = loops.get(key)
+        if loop is None:
+            loop = loops[key] = _GraphLoop(diffusion, inner, plan, clip, injected, want_x0)
+        return loop
+
+    def __init__(self, diffusion, model, plan, clip, injected, want_x0):
+        self.d, self.m, self.plan = diffusion, model, plan
+        self.clip, self.injected, self.want_x0 = clip, injected, want_x0
+        dev = plan.device
+        B = plan.B
+        self.t_idx = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.rng = torch.zeros(2, dtype=torch.int64, device=dev)          # {seed, draw} as raw 64-bit words
+        self.z_in = torch.empty_like(plan.x_in) if injected else None
+        self.x0 = torch.empty_like(plan.x_in) if want_x0 else None
+        spaced = isinstance(diffusion, SpacedDiffusion)
+        self.map = diffusion._map_tensor(dev) if spaced else None
+        if diffusion.rescale_timesteps:
+            self.scale = 1000.0 / (diffusion.original_num_steps if spaced else diffusion.num_timesteps)
+        else:
+            self.scale = 1.0
+        self.graph = None
+
+    def _body(self):
+        p, d = self.plan, self.d
+        tb = d._tables(p.device)
+        stream = torch.cuda.current_stream(p.device).cuda_stream
+        p._launch_all()
+        call("hl_ddpm_step_rng", p.x_in.data_ptr(), p.out.data_ptr(), self.z_in.data_ptr() if self.injected else None,
+             tb["coef"].data_ptr(), tb["sigma"].data_ptr(), self.t_idx.data_ptr(), d.num_timesteps, p.x_in.data_ptr(),
+             self.x0.data_ptr() if self.x0 is not None else None, p.B, p.x_in[0].numel(), 1 if self.clip else 0,
+             None if self.injected else self.rng.data_ptr(), 0, 0, stream)
+        call("hl_loop_advance", self.t_idx.data_ptr(), p.t_in.data_ptr(), self.map.data_ptr() if self.map is not None else None,
+             float(self.scale), p.B, self.rng.data_ptr(), stream)
+
+    def start(self, img, x_cond, model_kwargs, t_first):
+        from . import _lib
+        p, m = self.plan, self.m
+        y = (model_kwargs or {}).get("y")
+        if m.num_classes is not None and y is None:
+            raise ValueError("class-conditional model: model_kwargs['y'] is required")
+        if m.cond_type == "controlnet" and x_cond is None:
+            raise ValueError("cond_type='controlnet' needs x_cond")
+        with torch.cuda.device(p.device):
+            m_t = float(self.d.timestep_map[t_first] if self.map is not None else t_first) * self.scale
+            p.load_inputs(img, torch.full((p.B,), m_t), x_cond, y)
+            self.t_idx.fill_(t_first)
+            seed, draw = self.d._rng_draw(p.device)
+            to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+            self.rng.copy_(torch.tensor([to_i64(seed), to_i64(draw << 20)], dtype=torch.int64))
+            if p.runs == 0:                      # first use of this plan: one eager pass (function attributes, entry points)
+                keep = (p.x_in.clone(), self.t_idx.clone(), p.t_in.clone(), self.rng.clone())
+                n0, k0 = _lib.launch_count, _lib.load().hl_launch_count()
+                self._body()
+                p.runs += 1
+                p.kernels_per_run = _lib.load().hl_launch_count() - k0 - 2     # a split-K conv is two kernels
+                _lib.launch_count = n0
+                p.x_in.copy_(keep[0]); self.t_idx.copy_(keep[1]); p.t_in.copy_(keep[2]); self.rng.copy_(keep[3])
+            if self.graph is None:
+                n0 = _lib.launch_count
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.graph = g
+                _lib.launch_count = n0           # capture records launches, it does not run them
+
+    def step(self, z, fresh):
+        from . import _lib
+        p = self.plan
+        if self.injected:
+            self.z_in.copy_(z)
+        self.graph.replay()
+        _lib.launch_count += p.n_launches + 2
+        if fresh:
+            return {"sample": p.x_in.clone(), "pred_xstart": self.x0.clone() if self.x0 is not None else None}
+        return {"sample": p.x_in, "pred_xstart": self.x0}

@@ -2,9 +2,17 @@
 NO data-path collective during the T-step loop (samples are independent: GroupNorm is per-sample,
 there is no cross-sample op), then ONE all-gather of the finished samples (+ labels) -- exactly the
 collective the reference issues at human_diffusion/scripts/triplane_sample_layered.py:211-219.
-Backend: NCCL over NVLink 5 / NVSwitch on GPUs, gloo in the CPU tests."""
+Backend: NCCL over NVLink 5 / NVSwitch on GPUs, gloo in the CPU tests.
+
+Equal shards (the sampling scripts' case: every rank draws ``batch_size`` samples) take ONE collective: the int64
+labels are bit-cast into the tail of the fp32 sample buffer, so samples + labels travel in a single
+``all_gather_into_tensor`` into a receive buffer that is allocated once per (shape, world) and reused -- no size
+exchange, no host synchronisation.  ``warm_up()`` runs that collective once on dummy data so that communicator /
+NVLink channel set-up (tens of ms on the first NCCL call) never lands in a timed or latency-critical region."""
 import torch
 import torch.distributed as dist
+
+_RECV = {}      # (device, dtype, send numel, world) -> (send staging buffer, receive buffer)
 
 
 def shard_batch(global_batch, rank=None, world_size=None):
@@ -18,27 +26,57 @@ def shard_batch(global_batch, rank=None, world_size=None):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def all_gather_samples(sample, labels=None, group=None):
+def _buffers(device, dtype, n_send, world):
+    key = (str(device), dtype, n_send, world)
+    b = _RECV.get(key)
+    if b is None:
+        b = (torch.empty(n_send, dtype=dtype, device=device), torch.empty(world * n_send, dtype=dtype, device=device))
+        _RECV[key] = b
+    return b
+
+
+def _gather_equal(sample, labels, group, world):
+    """One all_gather_into_tensor: [sample words | labels bit-cast to the sample dtype] per rank."""
+    B = sample.shape[0]
+    flat = sample.reshape(-1)
+    n_s = flat.numel()
+    lab_words = 0
+    if labels is not None:
+        lab_raw = labels.contiguous().view(torch.uint8).view(sample.dtype)      # int64 -> 2 fp32 words each, bit-exact
+        lab_words = lab_raw.numel()
+    send, recv = _buffers(sample.device, sample.dtype, n_s + lab_words, world)
+    send[:n_s].copy_(flat)
+    if lab_words:
+        send[n_s:].copy_(lab_raw)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    per = recv.view(world, n_s + lab_words)
+    out = per[:, :n_s].reshape((world * B,) + tuple(sample.shape[1:]))       # one strided copy out of the receive buffer
+    lab = None
+    if lab_words:
+        lab = per[:, n_s:].contiguous().view(torch.uint8).view(labels.dtype).reshape(world * B)
+    return out, lab
+
+
+def all_gather_samples(sample, labels=None, group=None, equal_shards=None):
     """Gather ``sample [B_local, ...]`` (and int64 ``labels [B_local]``) from every rank, rank-major.
 
-    Equal shards use a single ``all_gather_into_tensor`` into one pre-allocated
-    ``[world * B_local, ...]`` buffer (NCCL: one ncclAllGather over NVLink; labels ride in the same
-    stream right behind it).  Ragged shards fall back to the list form the reference uses."""
+    ``equal_shards``: True -> every rank holds the same number of rows (the caller knows: ``shard_batch`` of a
+    divisible batch, or the scripts' fixed per-rank batch): no size exchange; None -> one small all-gather of the
+    row counts decides; ragged shards use the padded list form the reference uses."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return sample, labels
     world = dist.get_world_size(group)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=sample.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([sample.shape[0]], dtype=torch.int64, device=sample.device), group=group)
-    sizes = [int(s.item()) for s in sizes]
     sample = sample.contiguous()
-    if len(set(sizes)) == 1:
-        out = torch.empty((world * sizes[0],) + tuple(sample.shape[1:]), dtype=sample.dtype, device=sample.device)
-        dist.all_gather_into_tensor(out, sample, group=group)
-        lab = None
-        if labels is not None:
-            lab = torch.empty(world * sizes[0], dtype=labels.dtype, device=labels.device)
-            dist.all_gather_into_tensor(lab, labels.contiguous(), group=group)
-        return out, lab
+    if equal_shards is None:
+        mine = torch.tensor([sample.shape[0]], dtype=torch.int64, device=sample.device)
+        sizes_t = torch.empty(world, dtype=torch.int64, device=sample.device)
+        dist.all_gather_into_tensor(sizes_t, mine, group=group)
+        sizes = sizes_t.tolist()                      # one host sync for all ranks' counts
+        equal_shards = len(set(sizes)) == 1
+    else:
+        sizes = [sample.shape[0]] * world
+    if equal_shards:
+        return _gather_equal(sample, labels, group, world)
     mx = max(sizes)
     pad = torch.zeros((mx,) + tuple(sample.shape[1:]), dtype=sample.dtype, device=sample.device)
     pad[:sample.shape[0]] = sample
@@ -53,3 +91,13 @@ def all_gather_samples(sample, labels=None, group=None):
         dist.all_gather(lb, lpad, group=group)
         lab = torch.cat([b[:n] for b, n in zip(lb, sizes)], 0)
     return out, lab
+
+
+def warm_up(shape, device, dtype=torch.float32, with_labels=True, group=None):
+    """Run the equal-shard gather once on zeros of the production shape: creates the communicator's channels and
+    allocates the receive buffer the real call will reuse."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    s = torch.zeros(shape, dtype=dtype, device=device)
+    lab = torch.zeros(shape[0], dtype=torch.int64, device=device) if with_labels else None
+    all_gather_samples(s, lab, group=group, equal_shards=True)

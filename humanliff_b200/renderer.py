@@ -65,6 +65,12 @@ class Renderer(nn.Module):
         self.num_instances = num_instances
         self.triplane_dim = triplane_dim
         self.triplane_ch = triplane_ch
+        if not test:
+            # the reference adds torch.randn_like density noise in render_core when test=False (training,
+            # recon_NeRF/lib/renderer.py:221); every inference script constructs Renderer(test=True)
+            import warnings
+            warnings.warn("humanliff_b200.Renderer implements the inference path (test=True): the training-time "
+                          "density noise of render_core is not applied", stacklevel=2)
         self.test = test
         self.view_enc = _ViewEnc(4)
         d_in, d_hidden = triplane_ch, 128
@@ -78,7 +84,7 @@ class Renderer(nn.Module):
         self.rgb_linear = _linear_params(self, "r", d_hidden // 2, 3)
         self._pack_key = None
         self._mlp = None
-        self._tex_cache = {}
+        self._calls = 0          # render calls so far: decorrelates the in-kernel uniform streams of successive frames
 
     # ------------------------------------------------------------------ packing
     def _mlp_params(self):
@@ -129,17 +135,20 @@ class Renderer(nn.Module):
         return self._mlp
 
     def _texels(self, planes):
-        """[3, 9, R, R] device tensor -> texel-major float4 array (cached per tensor version)."""
-        key = (planes.data_ptr(), planes._version, tuple(planes.shape))
-        hit = self._tex_cache.get("k")
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        """[3, 9, R, R] device tensor -> texel-major float4 array.  Re-done on every call (one 7 MB pass, a few
+        microseconds): a cache keyed on the tensor's address / version would serve stale texels when the caching
+        allocator hands a new tri-plane the address of a freed one."""
         R = planes.shape[-1]
         tex = torch.empty(9 * R * R * 4, device=planes.device, dtype=torch.float32)
         stream = torch.cuda.current_stream(planes.device).cuda_stream
         call("hl_triplane_to_texels", planes.data_ptr(), tex.data_ptr(), R, stream)
-        self._tex_cache["k"] = (key, tex)
         return tex
+
+    def _next_seed(self, b=0):
+        """Seed of the in-kernel uniforms of sample_pdf for this call: follows torch's seed (torch.manual_seed
+        makes a run reproducible) and advances with every render call, as successive torch.rand draws would."""
+        self._calls += 1
+        return (torch.initial_seed() + 0x9E3779B97F4A7C15 * self._calls + b) & ((1 << 64) - 1)
 
     # ------------------------------------------------------------------ the fused launch
     @torch.no_grad()
@@ -235,7 +244,7 @@ class Renderer(nn.Module):
             rgb, acc, depth = self.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b],
                                                rays_o[b], rays_d[b], near[b].reshape(-1),
                                                far[b].reshape(-1), z_coarse=z_vals[b], u=ub,
-                                               seed=torch.initial_seed() + b)
+                                               seed=self._next_seed(b))
             outs["rgb_map"].append(rgb)
             outs["acc_map"].append(acc)
             outs["normal_map"].append(rgb)     # normal_map aliases rgb_map (renderer.py:237)
@@ -303,7 +312,7 @@ def render(chunk=1024 * 32, rays_o=None, rays_d=None, near=0., far=1., tri_plane
         ub = None if u is None else u[b * n:(b + 1) * n]
         rgb, acc, dep = r.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b], rays_o[b],
                                       rays_d[b], near[b], far[b], z_coarse=None, u=ub,
-                                      seed=torch.initial_seed() + b)
+                                      seed=r._next_seed(b))
         rgbs.append(rgb); accs.append(acc); deps.append(dep)
     rgb = torch.stack(rgbs, 0)
     return [rgb, torch.stack(accs, 0), rgb, torch.stack(deps, 0)]

@@ -316,17 +316,24 @@ class UNetModel(nn.Module):
             raise ValueError(f"H, W must be divisible by {1 << nlev}")
         device = x.device
         with torch.cuda.device(device):
-            self._pack(device)
-            key = (str(device), B, H, W)
-            plan = self._plans.get(key)
-            if plan is None:
-                parts = self.batch_split
-                if parts > 1 and B % parts == 0 and B // parts >= 2:
-                    plan = _SplitPlan(self, device, B, H, W, parts)
-                else:
-                    plan = _StepPlan(self, device, B, H, W)
-                self._plans[key] = plan
-            return plan.run(x, timesteps, x_cond, y)
+            return self.plan_for(device, B, H, W).run(x, timesteps, x_cond, y)
+
+    def plan_for(self, device, B, H, W):
+        """The compiled launch plan (workspace + CUDA graph) of a forward pass at (B, H, W) on ``device``; call
+        under ``torch.cuda.device(device)``.  Keyed on the tuning switches too, so toggling one after the first
+        forward takes effect."""
+        self._pack(device)
+        key = (str(device), B, H, W, self.use_cuda_graph, self.concurrent_encoders, self.batch_split, self.split_k,
+               self.programmatic_launch)
+        plan = self._plans.get(key)
+        if plan is None:
+            parts = self.batch_split
+            if parts > 1 and B % parts == 0 and B // parts >= 2:
+                plan = _SplitPlan(self, device, B, H, W, parts)
+            else:
+                plan = _StepPlan(self, device, B, H, W)
+            self._plans[key] = plan
+        return plan
 
 
 class _Ref:

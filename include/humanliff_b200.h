@@ -197,6 +197,35 @@ int hl_ddim_step(const float *x, const float *eps, const float *noise /*nullable
                  const float *sigma, const int64_t *t, float *sample, float *pred_xstart, int B, int64_t n,
                  int clip, void *stream);
 
+/* ---- sampling loop without library kernels (gaussian_diffusion.py:383-387,390-482; respace.py:117-122) ---- */
+
+/* Counter-based Gaussian generator (Philox4x32-10 + Box-Muller): element e of draw number `draw` under `seed`.
+ * rng_state (nullable): device uint64[2] = {seed, draw} read by the kernel instead of the by-value pair, so a
+ * captured CUDA graph draws fresh noise on every replay (hl_loop_advance increments the draw counter).
+ * Replaces th.randn(*shape) (gaussian_diffusion.py:460).                                                        */
+int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, uint64_t draw, void *stream);
+
+/* hl_ddpm_step with the per-step Gaussian drawn inside the kernel when noise == NULL (replaces the
+ * th.randn_like(x) launch of gaussian_diffusion.py:383): 16 B / element of HBM traffic.  T = table length; a
+ * timestep outside [0, T) fills that sample's row with NaN instead of reading out of bounds.                     */
+int hl_ddpm_step_rng(const float *x, const float *eps, const float *noise /*nullable*/, const float *coef,
+                     const float *sigma, const int64_t *t, int T, float *sample, float *pred_xstart /*nullable*/,
+                     int B, int64_t n, int clip, const uint64_t *rng_state /*nullable*/, uint64_t seed,
+                     uint64_t draw, void *stream);
+
+/* Posterior from a caller-supplied x0 (the denoised_fn route, gaussian_diffusion.py:294-295,312-314):
+ * x0c = clip(x0); sample = c2 x0c + c3 x + sigma_t * noise.                                                      */
+int hl_ddpm_posterior(const float *x, const float *x0, const float *noise /*nullable*/, const float *coef,
+                      const float *sigma, const int64_t *t, int T, float *sample, float *x0_clipped /*nullable*/,
+                      int B, int64_t n, int clip, const uint64_t *rng_state /*nullable*/, uint64_t seed,
+                      uint64_t draw, void *stream);
+
+/* End of a loop iteration, on the device: t[b] -= 1; t_model[b] = scale * (timestep_map ? map[t[b]] : t[b])
+ * (_WrappedModel.__call__, respace.py:117-122; scale = 1000 / T_original iff rescale_timesteps, else 1);
+ * rng_state[1] += 1.  Lets UNet + posterior + advance be ONE CUDA graph replayed per step.                      */
+int hl_loop_advance(int64_t *t, float *t_model, const int64_t *timestep_map /*nullable*/, float scale, int B,
+                    uint64_t *rng_state /*nullable*/, void *stream);
+
 /* ---- tri-plane volume renderer (recon_NeRF/lib/renderer.py:142-295,504-581;
  *      recon_NeRF/run_nerf_batch.py:29-67; human_diffusion/NeRF/renderer.py:234-281) ----------- */
 

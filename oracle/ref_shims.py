@@ -8,6 +8,13 @@ import types
 REF_ROOT = os.environ.get("HUMANLIFF_REF", "/root/reference")
 
 
+def use(root):
+    """Point the shims at another copy of the unmodified reference (``oracle/_ref``, staged by
+    ``oracle/build_ref.py`` for the GPU box where /root/reference does not exist)."""
+    global REF_ROOT
+    REF_ROOT = root
+
+
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "human_diffusion", "improved_diffusion"))
 

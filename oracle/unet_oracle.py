@@ -33,8 +33,19 @@ def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
 
 
 class _Numerics:
+    """``mode``: one operand-rounding mode for every contraction, or a callable ``layer_prefix -> mode`` (a
+    per-layer policy: which layers the product runs in which operand format; used for the error budget and to
+    emulate mixed-precision plans)."""
+
     def __init__(self, mode):
-        self.mode = mode
+        self.policy = mode if callable(mode) else None
+        self.mode = None if callable(mode) else mode
+
+    def at(self, name):
+        """The numerics of layer ``name``."""
+        if self.policy is None:
+            return self
+        return _Numerics(self.policy(name))
 
     def op(self, x, raw=False):
         if self.mode is None:
@@ -43,6 +54,13 @@ class _Numerics:
             return round_tf32(x)
         if self.mode == "tf32_trunc_raw":
             return trunc_tf32(x) if raw else round_tf32(x)
+        if self.mode == "fp16_scaled":
+            # raw-stream operand carried as fp16(x * 2^-8) (weights as fp16(w * 2^8)): range 1.6e7 instead of 65504
+            return (x * 2.0 ** -8).to(torch.float16).to(torch.float32) * 2.0 ** 8
+        if self.mode == "fp16x2":
+            # fp16 hi + lo pair for BOTH operands of the layer (three MMAs: hi.hi + hi.lo + lo.hi): ~22 bits
+            hi = x.to(torch.float16).to(torch.float32)
+            return hi + (x - hi).to(torch.float16).to(torch.float32)
         if self.mode == "fp16":
             # cvt.rn.f16.f32 operands (11-bit significand like TF32, 5-bit exponent), fp32 accumulate
             return x.to(torch.float16).to(torch.float32)
@@ -78,6 +96,17 @@ def _silu(x):
 def _conv(x, sd, prefix, nm, stride=1, raw=False):
     w = sd[prefix + ".weight"]
     pad = w.shape[-1] // 2
+    nm = nm.at(prefix)
+    if nm.mode == "fp16_split3":
+        # the product's high-precision conv: activations * 2^-8 and weights * 2^8 each carried as an fp16 hi + lo
+        # pair, three tensor-core passes hi.hi + lo.hi + hi.lo (the lo.lo term, 2^-22 relative, is dropped)
+        f16 = lambda t: t.to(torch.float16).to(torch.float32)
+        xs, wsc = x * 2.0 ** -8, w * 2.0 ** 8
+        xh, wh = f16(xs), f16(wsc)
+        xl, wl = f16(xs - xh), f16(wsc - wh)
+        y = F.conv2d(xh, wh, None, stride=stride, padding=pad) + F.conv2d(xl, wh, None, stride=stride, padding=pad) \
+            + F.conv2d(xh, wl, None, stride=stride, padding=pad)
+        return y + sd[prefix + ".bias"][None, :, None, None]
     return F.conv2d(nm.op(x, raw), nm.op(w), sd[prefix + ".bias"], stride=stride, padding=pad)
 
 
@@ -98,6 +127,7 @@ def _attention(x, sd, p, heads, nm):
     """unet.py:244-274 -- head-major qkv channel order."""
     b, c, hh, ww = x.shape
     xf = x.reshape(b, c, -1)
+    nm = nm.at(p)
     n = F.group_norm(xf.float(), 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
     qkv = F.conv1d(nm.op(n), nm.op(sd[p + ".qkv.weight"]), sd[p + ".qkv.bias"])
     qkv = qkv.reshape(b * heads, -1, qkv.shape[2])

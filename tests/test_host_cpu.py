@@ -70,15 +70,22 @@ def test_shard_batch():
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from humanliff_b200.dist import all_gather_samples, shard_batch
+from humanliff_b200.dist import all_gather_samples, shard_batch, warm_up
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
 full = torch.arange(6 * 27 * 4 * 4, dtype=torch.float32).reshape(6, 27, 4, 4)
-labels = torch.arange(6)
+labels = torch.arange(6) - 2 + (1 << 40) * (torch.arange(6) % 2)     # negative and > 32-bit labels survive the bit-cast
+warm_up((3, 27, 4, 4), "cpu")
 for G in (6, 5):                                   # equal and ragged shards
     a, b = shard_batch(G, r, w)
     out, lab = all_gather_samples(full[a:b].clone(), labels[a:b].clone())
     assert torch.equal(out, full[:G]) and torch.equal(lab, labels[:G]), (G, r)
+a, b = shard_batch(6, r, w)                        # caller-declared equal shards: one collective, no size exchange
+for rep in range(2):                               # twice: the cached receive buffer is reused
+    out, lab = all_gather_samples(full[a:b] + rep, labels[a:b], equal_shards=True)
+    assert torch.equal(out, full + rep) and torch.equal(lab, labels), r
+out, lab = all_gather_samples(full[a:b], None, equal_shards=True)
+assert torch.equal(out, full) and lab is None
 dist.barrier()
 print("ok", r)
 '''
@@ -214,3 +221,21 @@ def test_state_dict_contract_vs_reference():
                                                           triplane_ch=27, test=True)))
     want = dict((k, s) for k, s in ref["renderer_rn_2_instances"])
     assert got == want, set(got) ^ set(want)
+
+
+def test_reference_staging_recipe(tmp_path):
+    """oracle/build_ref.py: byte-for-byte staging of the reference's hot-path packages + manifest verification.
+    Needs /root/reference (this container); on a box without it the staged copy is only verified if present."""
+    from oracle import build_ref
+    if not os.path.isdir(os.path.join(build_ref.SRC, build_ref.PACKAGES[0])):
+        if build_ref.available():
+            assert build_ref.verify()
+        pytest.skip("reference tree not present")
+    dest = str(tmp_path / "_ref")
+    man = build_ref.stage(dest=dest)
+    assert man and "human_diffusion/improved_diffusion/unet.py" in man["files"]
+    assert "recon_NeRF/lib/renderer.py" in man["files"] and "human_diffusion/NeRF/renderer.py" in man["files"]
+    assert build_ref.verify(dest)
+    with open(os.path.join(dest, "human_diffusion/improved_diffusion/nn.py"), "a") as f:
+        f.write("# edited\n")
+    assert not build_ref.verify(dest)            # a modified copy is detected

@@ -186,13 +186,13 @@ def dominant_kernel_roofline(device, B, peaks, precision, reps=20):
             "hbm_floor_ms": round(bytes_alg / (peaks["hbm_gbs"] * 1e9) * 1e3, 4)}
 
 
-def render_throughput(device, n_rays=262144, reps=3):
+def render_throughput(device, n_rays=262144, reps=3, precision="fp16"):
     """Secondary metric of BASELINE.json (rendered rays/s, 128+128 samples): the fused tensor-core render kernel
     on the 512x512 synthetic camera of SURVEY.md 8(d) config 3 (BASELINE configs[2]: one whole image per launch),
     CUDA events."""
     from humanliff_b200 import synth
     from humanliff_b200.renderer import Renderer
-    r = Renderer(triplane_ch=27, test=True)
+    r = Renderer(triplane_ch=27, test=True, precision=precision)
     synth.randomize_(r, seed=3, weight_gain=1.5)
     r = r.to(device)
     planes = synth.synth_triplane(256, seed=7)[0].to(device)

@@ -52,6 +52,10 @@ SIGNATURES = {
                                c_i64, c_int, c_p]),
     "hl_render_set_profile": (c_int, [c_p]),
     "hl_density_grid_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
+    "hl_render_rays_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_int, c_p, c_p, c_p,
+                                   c_i64, c_int, c_int, c_p]),
+    "hl_density_grid_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_p, c_p]),
+    "hl_render5_set_profile": (c_int, [c_p]),
     "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                   c_i64, c_int, c_p]),
 }
@@ -82,6 +86,8 @@ MLP16_W2 = MLP16_W1 + 128 * 136
 MLP16_WF = MLP16_W2 + 128 * 168
 MLP16_WV = MLP16_WF + 128 * 136
 MLP16_HALVES = MLP16_WV + 64 * 136
+
+MLP16S_BYTES = 16384 + 32768 + 16384 + 32768 + 32768 + 16384
 
 CONV_FORCE_SIMT = 1
 CONV_UPSAMPLE2X = 2

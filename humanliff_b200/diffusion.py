@@ -67,9 +67,6 @@ def _extract_into_tensor(arr, timesteps, broadcast_shape):
     return res.expand(broadcast_shape)
 
 
-_RNG_STATE = {}          # device index -> [seed, draws so far] of the in-kernel Philox generator
-
-
 class GaussianDiffusion:
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False):
         self.model_mean_type = model_mean_type
@@ -135,16 +132,16 @@ class GaussianDiffusion:
         return t
 
     # ------------------------------------------------------------------ sampling
-    def _rng_draw(self, device):
-        """(seed, draw counter) of the in-kernel Philox generator: the seed follows the device's torch generator
-        (``torch.manual_seed`` restarts the sequence), every draw advances a host-side counter."""
+    def _rng_draw(self, device, n_draws=1):
+        """(seed, first draw id) for ``n_draws`` consecutive draws of the in-kernel Philox generator.  Both come
+        from the device's torch CUDA generator -- its seed, and its Philox offset, which is advanced past the ids
+        handed out -- so ``torch.manual_seed`` makes a run reproducible exactly as it does for ``torch.randn``."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        seed = int(torch.cuda.default_generators[idx].initial_seed()) & ((1 << 64) - 1)
-        st = _RNG_STATE.setdefault(idx, [None, 0])
-        if st[0] != seed:
-            st[0], st[1] = seed, 0
-        st[1] += 1
-        return seed, st[1] - 1
+        gen = torch.cuda.default_generators[idx]
+        seed = int(gen.initial_seed()) & ((1 << 64) - 1)
+        off = int(gen.get_offset())
+        gen.set_offset(off + 4 * ((n_draws + 3) // 4))          # torch requires offsets in multiples of 4
+        return seed, off
 
     def _coerce(self, ref, t, name):
         """fp32, contiguous, on ``ref``'s device -- the kernels read raw pointers."""
@@ -533,9 +530,9 @@ class _GraphLoop:
             m_t = float(self.d.timestep_map[t_first] if self.map is not None else t_first) * self.scale
             p.load_inputs(img, torch.full((p.B,), m_t), x_cond, y)
             self.t_idx.fill_(t_first)
-            seed, draw = self.d._rng_draw(p.device)
+            seed, draw = self.d._rng_draw(p.device, n_draws=t_first + 1)      # one draw id per step of the loop
             to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
-            self.rng.copy_(torch.tensor([to_i64(seed), to_i64(draw << 20)], dtype=torch.int64))
+            self.rng.copy_(torch.tensor([to_i64(seed), to_i64(draw)], dtype=torch.int64))
             if p.runs == 0:                      # first use of this plan: one eager pass (function attributes, entry points)
                 keep = (p.x_in.clone(), self.t_idx.clone(), p.t_in.clone(), self.rng.clone())
                 n0, k0 = _lib.launch_count, _lib.load().hl_launch_count()

@@ -10,8 +10,10 @@ its [4.2 M x 155] temporaries and ``empty_cache()`` calls disappear.  Only the i
 built: ``use_canonical_space=False``, ``n_samples == n_importance == 128``, ``perturb == 0``,
 ``white_bkgd=False`` (the reference's white_bkgd branch is shape-broken).
 
-``precision="fp16"`` (default) runs the decoder MLP on the tensor cores (``hl_render_rays_tc``: fp16
-operands, fp32 accumulate, activations in registers); ``"fp32"`` selects the exact CUDA-core kernel.
+``precision="fp16"`` (default) runs the decoder MLP on the 5th-generation tensor cores (``hl_render_rays_tc5``:
+tcgen05.mma, fp16 operands, fp32 accumulators and activations in tensor memory, two ray groups per SM);
+``"fp16_mma"`` keeps the round-1 ``mma.sync`` kernel (``hl_render_rays_tc``, same operand rounding) as a
+cross-check; ``"fp32"`` selects the exact CUDA-core kernel.
 """
 import math
 
@@ -34,6 +36,22 @@ def _linear_params(mod, name, fin, fout):
     return node
 
 
+def _sw128_atoms(w):
+    """[N, K] weight -> list of flattened fp16 atoms [N rows][64 halves], K zero-padded to a multiple of 64, in the
+    K-major SWIZZLE_128B layout tcgen05.mma reads from shared memory: the 16-byte chunk c (8 halves) of row r is
+    stored at chunk position c ^ (r & 7) of the row's 128 bytes."""
+    n, k = w.shape
+    kp = (k + 63) // 64 * 64
+    wp = torch.zeros(n, kp, dtype=torch.float16)
+    wp[:, :k] = w.to(torch.float16)
+    pos = torch.arange(8)[None, :] ^ (torch.arange(n)[:, None] & 7)            # [n, 8]: source chunk of each position
+    out = []
+    for a in range(kp // 64):
+        chunks = wp[:, a * 64:(a + 1) * 64].reshape(n, 8, 8)
+        out.append(chunks.gather(1, pos[:, :, None].expand(n, 8, 8)).reshape(-1))
+    return out
+
+
 class _ViewEnc(nn.Module):
     """Buffers of lib/fields.py:45-67 (kept so that reference checkpoints load with strict=True)."""
 
@@ -54,8 +72,9 @@ class Renderer(nn.Module):
     def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18,
                  smpl_type=None, test=False, precision="fp16"):
         super().__init__()
-        if precision not in ("fp16", "fp32"):
-            raise ValueError("precision must be 'fp16' (tensor-core MLP) or 'fp32' (exact CUDA-core MLP)")
+        if precision not in ("fp16", "fp16_mma", "fp32"):
+            raise ValueError("precision must be 'fp16' (tcgen05 MLP), 'fp16_mma' (mma.sync MLP) or 'fp32' (exact "
+                             "CUDA-core MLP)")
         self.precision = precision
         if use_canonical_space:
             raise NotImplementedError("use_canonical_space=True (TightCap SMPL deformation) is a 'next' row")
@@ -131,6 +150,15 @@ class Renderer(nn.Module):
         put16(L.MLP16_WF, self.feature_linear.weight, 136)
         put16(L.MLP16_WV, self.views_linear.weight[:, :128], 136)
         self._mlp16 = img.to(device)
+        # tcgen05 kernel: the same fp16 weights as K-major SWIZZLE_128B atoms (HL_MLP16S_BYTES in the header)
+        w2 = self.pts_linears[2].weight.detach().float().cpu()
+        atoms = []
+        for w in (self.pts_linears[0].weight, self.pts_linears[1].weight, w2[:, :27], w2[:, 27:],
+                  self.feature_linear.weight, self.views_linear.weight[:, :128]):
+            atoms += _sw128_atoms(w.detach().float().cpu())
+        sw = torch.cat(atoms)
+        assert sw.numel() * 2 == L.MLP16S_BYTES, sw.numel()
+        self._mlp16s = sw.to(device)
         self._pack_key = key
         return self._mlp
 
@@ -152,8 +180,11 @@ class Renderer(nn.Module):
 
     # ------------------------------------------------------------------ the fused launch
     @torch.no_grad()
-    def render_rays(self, tri_planes, bounds, rays_o, rays_d, near, far, z_coarse=None, u=None, seed=0):
-        """One tri-plane ([3, 9, R, R]), one bounds box ([2, 3]), N rays -> (rgb [N,3], acc [N], depth [N])."""
+    def render_rays(self, tri_planes, bounds, rays_o, rays_d, near, far, z_coarse=None, u=None, seed=0,
+                    n_importance=N_SAMPLES):
+        """One tri-plane ([3, 9, R, R]), one bounds box ([2, 3]), N rays -> (rgb [N,3], acc [N], depth [N]).
+        ``bounds`` may be a CUDA tensor (the scripts' ``tp_input['world_bounds']``): it is read on the device, no
+        host synchronisation.  ``n_importance=0``: no coarse pass, the 128 coarse depths are composited."""
         if not rays_o.is_cuda:
             raise RuntimeError("humanliff_b200.Renderer runs on CUDA (sm_100a) only -- no CPU fallback")
         dev = rays_o.device
@@ -172,20 +203,33 @@ class Renderer(nn.Module):
             if u is not None:
                 u = f(u)
                 assert u.shape == (n, N_SAMPLES)
-            b = [float(v) for v in torch.as_tensor(bounds, dtype=torch.float32).reshape(-1).tolist()]
-            assert len(b) == 6
             import ctypes
-            barr = (ctypes.c_float * 6)(*b)
+            if n_importance not in (0, N_SAMPLES):
+                raise NotImplementedError("the fused kernel implements n_importance == n_samples == 128, or 0")
+            tc5 = self.precision == "fp16"
+            if not tc5 and n_importance == 0:
+                raise NotImplementedError("n_importance=0 is served by the tcgen05 kernel (precision='fp16')")
+            bt = torch.as_tensor(bounds, dtype=torch.float32)
+            assert bt.numel() == 6
+            if tc5 and bt.is_cuda:
+                bdev = bt.to(dev).contiguous().view(-1)          # stays on the device: no .tolist() sync
+                bptr, bflag = bdev.data_ptr(), 1
+            else:
+                barr = (ctypes.c_float * 6)(*[float(v) for v in bt.reshape(-1).tolist()])
+                bptr, bflag = ctypes.cast(barr, ctypes.c_void_p), 0
             rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
             acc = torch.empty(n, device=dev, dtype=torch.float32)
             depth = torch.empty(n, device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            tail = (rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+            head = (rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
                     z_coarse.data_ptr() if z_coarse is not None else None,
-                    u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1),
-                    ctypes.cast(barr, ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
-                    1 if self.clamp_depth else 0, stream)
-            if self.precision == "fp16":
+                    u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1))
+            tail = head + (bptr, rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n, 1 if self.clamp_depth else 0, stream)
+            if tc5:
+                call("hl_render_rays_tc5", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16s.data_ptr(), *head,
+                     bptr, bflag, rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n, int(n_importance),
+                     1 if self.clamp_depth else 0, stream)
+            elif self.precision == "fp16_mma":
                 call("hl_render_rays_tc", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16.data_ptr(), *tail)
             else:
                 call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), *tail)
@@ -205,14 +249,23 @@ class Renderer(nn.Module):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).reshape(3, 9, *tri_planes.shape[-2:]).contiguous()
             tex = self._texels(planes)
-            wb = tp_input["world_bounds"]
-            b = [float(v) for v in torch.as_tensor(wb, dtype=torch.float32).reshape(-1, 6)[0].tolist()]
             import ctypes
-            barr = (ctypes.c_float * 6)(*b)
+            wb = torch.as_tensor(tp_input["world_bounds"], dtype=torch.float32).reshape(-1, 6)[0]
             out = torch.empty(resolution, resolution, resolution, device=dev, dtype=torch.float32)
-            call("hl_density_grid_tc", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16.data_ptr(),
-                 ctypes.cast(barr, ctypes.c_void_p), int(resolution), out.data_ptr(),
-                 torch.cuda.current_stream(dev).cuda_stream)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if self.precision == "fp16":
+                if wb.is_cuda:
+                    wbd = wb.to(dev).contiguous()
+                    bptr, bflag = wbd.data_ptr(), 1
+                else:
+                    barr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])
+                    bptr, bflag = ctypes.cast(barr, ctypes.c_void_p), 0
+                call("hl_density_grid_tc5", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16s.data_ptr(),
+                     bptr, bflag, int(resolution), out.data_ptr(), stream)
+            else:
+                barr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])
+                call("hl_density_grid_tc", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16.data_ptr(),
+                     ctypes.cast(barr, ctypes.c_void_p), int(resolution), out.data_ptr(), stream)
         return out
 
     def extract_geometry(self, tp_input, tri_planes=None, resolution=512, threshold=0.0):
@@ -235,8 +288,8 @@ class Renderer(nn.Module):
         if white_bkgd:
             raise NotImplementedError("white_bkgd=True is shape-broken in the reference and not built")
         bs, n_rays, n_samples = z_vals.shape
-        if n_importance != N_SAMPLES or n_samples != N_SAMPLES:
-            raise NotImplementedError("the fused kernel implements n_samples == n_importance == 128")
+        if n_importance not in (0, N_SAMPLES) or n_samples != N_SAMPLES:
+            raise NotImplementedError("the fused kernel implements n_samples == 128 with n_importance == 128 or 0")
         wb = tp_input["world_bounds"]
         outs = {"rgb_map": [], "acc_map": [], "normal_map": [], "depth_map": []}
         for b in range(bs):
@@ -244,7 +297,7 @@ class Renderer(nn.Module):
             rgb, acc, depth = self.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b],
                                                rays_o[b], rays_d[b], near[b].reshape(-1),
                                                far[b].reshape(-1), z_coarse=z_vals[b], u=ub,
-                                               seed=self._next_seed(b))
+                                               seed=self._next_seed(b), n_importance=n_importance)
             outs["rgb_map"].append(rgb)
             outs["acc_map"].append(acc)
             outs["normal_map"].append(rgb)     # normal_map aliases rgb_map (renderer.py:237)
@@ -295,8 +348,8 @@ def render(chunk=1024 * 32, rays_o=None, rays_d=None, near=0., far=1., tri_plane
         raise NotImplementedError("perturb > 0 (training-time stratified jitter) is outside the inference path")
     if white_bkgd:
         raise NotImplementedError("white_bkgd=True is shape-broken in the reference and not built")
-    if n_importance != N_SAMPLES or n_samples != N_SAMPLES:
-        raise NotImplementedError("the fused kernel implements n_samples == n_importance == 128")
+    if n_importance not in (0, N_SAMPLES) or n_samples != N_SAMPLES:
+        raise NotImplementedError("the fused kernel implements n_samples == 128 with n_importance == 128 or 0")
     r = renderer.module if hasattr(renderer, "module") and not isinstance(renderer, Renderer) else renderer
     bs = rays_d.shape[0]
     rays_o = rays_o.reshape(bs, -1, 3)
@@ -312,7 +365,7 @@ def render(chunk=1024 * 32, rays_o=None, rays_d=None, near=0., far=1., tri_plane
         ub = None if u is None else u[b * n:(b + 1) * n]
         rgb, acc, dep = r.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b], rays_o[b],
                                       rays_d[b], near[b], far[b], z_coarse=None, u=ub,
-                                      seed=r._next_seed(b))
+                                      seed=r._next_seed(b), n_importance=n_importance)
         rgbs.append(rgb); accs.append(acc); deps.append(dep)
     rgb = torch.stack(rgbs, 0)
     return [rgb, torch.stack(accs, 0), rgb, torch.stack(deps, 0)]

@@ -299,6 +299,28 @@ int hl_render_set_profile(void *dev_counters);
 int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, const void *mlp_f16,
                        const float *bounds /*host*/, int resolution, float *out, void *stream);
 
+/* ---- tcgen05 / TMEM renderer (the default of precision="fp16") ---------------------------------------------
+ * Same chain and operand rounding as hl_render_rays_tc, but every MLP layer is a tcgen05.mma (M = 128 samples,
+ * accumulators and activations in tensor memory, weights resident in shared memory); two ray groups per SM.
+ * mlp_f16_swizzled: HL_MLP16S_BYTES bytes = the fp16 weights as K-major SWIZZLE_128B atoms [rows][64 halves]
+ * (16-byte chunk c of row r stored at chunk c ^ (r & 7)), in the order
+ *   pts_linears.0 (128 x 64, k = x(27) | 0) | pts_linears.1 (2 atoms) | pts_linears.2 x part (128 x 64) |
+ *   pts_linears.2 h1 part (2 atoms) | feature_linear (2 atoms) | views_linear feature part (2 atoms of 64 rows).
+ * bounds: 6 floats {min xyz, max xyz}, host memory, or device memory when bounds_on_device != 0 (no host sync on
+ * tp_input['world_bounds']).  n_importance: 128, or 0 = no coarse pass: the n_samples = 128 coarse depths are
+ * composited directly (recon_NeRF/lib/renderer.py:258 `if n_importance > 0`).                                  */
+#define HL_MLP16S_BYTES (16384 + 32768 + 16384 + 32768 + 32768 + 16384)
+int hl_render_rays_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+                       const float *rays_o, const float *rays_d, const float *near, const float *far,
+                       const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
+                       const float *bounds, int bounds_on_device, float *rgb, float *acc, float *depth,
+                       int64_t n_rays, int n_importance, int clamp_depth, void *stream);
+int hl_density_grid_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+                        const float *bounds, int bounds_on_device, int resolution, float *out, void *stream);
+/* per-phase cycle counters of (CTA 0, group 0) of following tc5 launches, as hl_render_set_profile */
+int hl_render5_set_profile(void *dev_counters);
+
+
 #ifdef __cplusplus
 }
 #endif

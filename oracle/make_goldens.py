@@ -344,11 +344,87 @@ def unet_full_size_case(name, flags, HW, t, seed_w, seed_in=1234):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def render_noimp_case(name, n_rays=256, seed_w=3):
+    """Renderer.render with n_importance=0 (human_diffusion/NeRF/renderer.py: the `if n_importance > 0` block is
+    skipped, render_core composites the 128 coarse samples) on the first rays of the render_1024 golden's ray set."""
+    t0 = time.time()
+    hd = ref_shims.import_hd_renderer()
+    torch.manual_seed(0)
+    r = hd.Renderer(use_canonical_space=False, triplane_ch=27, smpl_type=None, test=True)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    r.load_state_dict(synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5), strict=False)
+    g = np.load(os.path.join(OUT, "render_1024.npz"))
+    ro, rd, near, far = (torch.from_numpy(g[k][:n_rays]) for k in ("rays_o", "rays_d", "near", "far"))
+    planes = synth.synth_triplane(256, seed=7)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    t = torch.linspace(0., 1., steps=128)
+    z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+    pts = ro[None, :, None, :] + rd[None, :, None, :] * z[..., :, None]
+    with torch.no_grad():
+        ret = r.render({"world_bounds": bounds[None]}, pts.reshape(1, -1, 3), z, ro[None], rd[None], near[None, :, None],
+                       far[None, :, None], planes, 0, False)
+    np.savez(os.path.join(OUT, name), n_rays=np.array(n_rays), rgb=ret["rgb_map"][0].numpy(),
+             acc=ret["acc_map"][0].numpy(), depth=ret["depth_map"][0].numpy(), seed_w=np.array(seed_w))
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
+def loop_noise(k, shape, seed=9000):
+    """Per-step Gaussian of the long free-running goldens: regenerated from (seed + k), never stored."""
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed + k))
+
+
+def unet_long_loop_case(name, flags, HW, steps, seed_w):
+    """>= 50 free-running p_sample steps of the PRODUCTION architecture (SURVEY 8(d) parity metric (ii)), B = 1 at
+    HW x HW: the first `steps` steps of the chain (t = T-1 ... T-steps) from x_T = synth x.  Only the final sample is
+    stored; x_T, x_cond and the per-step noise are regenerated from their seeds (loop_noise)."""
+    t0 = time.time()
+    model, diffusion = build_ref(flags, seed_w)
+    x, x_cond, _ = synth.synth_denoise_inputs(1, 27, HW, HW, seed=1234)
+    y = torch.tensor([2])
+    T = diffusion.num_timesteps
+    noises = [loop_noise(k, x.shape) for k in range(steps)]
+    img = x
+    orig = inject_noise(noises)
+    try:
+        with torch.no_grad():
+            for i in range(T - 1, T - 1 - steps, -1):
+                img = diffusion.p_sample(model, img, x_cond, torch.full((1,), i, dtype=torch.int64), clip_denoised=True,
+                                         model_kwargs={"y": y})["sample"]
+    finally:
+        torch.randn_like = orig
+    np.savez(os.path.join(OUT, name), steps=np.array(steps), y=y.numpy(), loop_final=img.numpy(),
+             respacing=np.array(flags["timestep_respacing"]))
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
+SUB = (slice(None), slice(None), slice(1, None, 4), slice(2, None, 4))      # the stored sub-lattice of a 256^2 epsilon
+
+
+def unet_full_size_sweep_case(name, flags, HW, ts, seed_w, seed_in=1234):
+    """The production model at the BASELINE resolution on the 1000-step ("") schedule at several timesteps (the
+    sweep of SURVEY 8(d) config 1, at config 2's size).  To keep the fixture small only the sub-lattice
+    eps[:, :, 1::4, 2::4] is stored (1/16 of the pixels, 27 x 64 x 64 per timestep): an unbiased sample of the
+    rel-L2 / max-norm statistics the GPU test evaluates on the same sub-lattice."""
+    t0 = time.time()
+    model, diffusion = build_ref(flags, seed_w)
+    x, x_cond, _ = synth.synth_denoise_inputs(1, 27, HW, HW, seed=seed_in)
+    y = torch.tensor([2])
+    out = {"ts": np.array(ts), "seed_in": np.array(seed_in), "y": y.numpy()}
+    with torch.no_grad():
+        for t in ts:
+            eps = model(x, torch.tensor([t]), x_cond, y=y)
+            out[f"eps_sub_{t}"] = eps[SUB].numpy()
+            out[f"eps_norm_{t}"] = np.array(float(eps.double().norm()))
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, "done in %.1fs" % (time.time() - t0), flush=True)
+
+
 if __name__ == "__main__":
     assert ref_shims.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn", "density", "contract"]
+    which = sys.argv[1:] or ["tiny", "render", "prod64", "ddim", "schedules", "variants", "render_rn", "density", "contract",
+                             "render_noimp"]
     if "tiny" in which:
         unet_case("unet_tiny_32.npz", TINY, B=2, HW=32, ts=[0, 100, 249], seed_w=11, loop_steps=12)
     if "render" in which:
@@ -367,6 +443,13 @@ if __name__ == "__main__":
         variants_case("unet_variants_32.npz")
     if "schedules" in which:
         schedule_case("schedules.npz")
+    if "render_noimp" in which:
+        render_noimp_case("render_noimp_256.npz")
+    if "loop50" in which:         # not in the default list: ~40 s of CPU
+        unet_long_loop_case("unet_prod_64_loop50.npz", PROD, HW=64, steps=50, seed_w=0)
+    if "prod256sweep" in which:   # not in the default list: ~1 min of CPU, 1.8 MB
+        unet_full_size_sweep_case("unet_prod_256_sweep.npz", dict(PROD, timestep_respacing=""), HW=256,
+                                  ts=[0, 1, 500, 999], seed_w=0)
     if "render512" in which:      # not in the default list: several minutes of CPU, 5 MB
         render_full_image_case("render_512x512.npz")
     if "prod256" in which:        # not in the default list: ~1 min of CPU, 7 MB

@@ -54,12 +54,16 @@ def mlp(sd, x, viewdir=None):
 
 
 @torch.no_grad()
-def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_depth=True, n=128):
-    """tri_planes [3,9,R,R]; bounds [2,3]; rays [N,3]; near/far [N]; u [N,128] -> rgb, acc, depth."""
+def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_depth=True, n=128, n_importance=128):
+    """tri_planes [3,9,R,R]; bounds [2,3]; rays [N,3]; near/far [N]; u [N,128] -> rgb, acc, depth.
+    ``n_importance=0``: the `if n_importance > 0` block of Renderer.render (recon_NeRF/lib/renderer.py:258-270) is
+    skipped and render_core composites the n coarse samples."""
     N = rays_o.shape[0]
     bmin, bmax = bounds[0], bounds[1]
     t = torch.linspace(0., 1., steps=n)
     z = near[:, None] * (1. - t) + far[:, None] * t
+    if n_importance == 0:
+        return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, z, clamp_depth)
     pts = rays_o[:, None] + rays_d[:, None] * z[..., None]
     sigma = mlp(sd, plane_features(tri_planes, pts.reshape(-1, 3), bmin, bmax)).reshape(N, n)
     # up_sample
@@ -79,7 +83,12 @@ def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_dept
     den = torch.where(den < 1e-5, torch.ones_like(den), den)
     z_new = bb + (u - cb) / den * (ba - bb)
     zf, _ = torch.sort(torch.cat([z, z_new], -1), -1)
-    # fine pass
+    return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth)
+
+
+def _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth):
+    """render_core (recon_NeRF/lib/renderer.py:180-241) + the depth normalisation of render (:283-286)."""
+    N = rays_o.shape[0]
     m = zf.shape[1]
     pts = rays_o[:, None] + rays_d[:, None] * zf[..., None]
     vd = (rays_d / rays_d.norm(dim=-1, keepdim=True))[:, None].expand(N, m, 3).reshape(-1, 3)

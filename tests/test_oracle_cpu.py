@@ -175,3 +175,18 @@ def test_density_field_oracle_matches_reference_golden():
     pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
     u = -render_oracle.mlp(sd, render_oracle.plane_features(planes, pts, bounds[0], bounds[1])).reshape(res, res, res)
     assert rel_l2(u, gd["u"]) < 1e-5, rel_l2(u, gd["u"])
+
+
+def test_render_oracle_n_importance_zero_matches_reference_golden():
+    """n_importance=0 (recon_NeRF/lib/renderer.py:258 `if n_importance > 0` skipped): oracle vs the unmodified reference."""
+    from common import renderer_state_dict
+    from humanliff_b200 import synth
+    from oracle import render_oracle
+    g = load_golden("render_1024.npz")
+    gz = load_golden("render_noimp_256.npz")
+    _, sd = renderer_state_dict(int(gz["seed_w"]))
+    n = int(gz["n_rays"])
+    out = render_oracle.render_rays(sd, synth.synth_triplane(256, seed=7)[0], torch.tensor(synth.WORLD_BOUNDS),
+                                    g["rays_o"][:n], g["rays_d"][:n], g["near"][:n], g["far"][:n], None, n_importance=0)
+    for name, a, b in zip(("rgb", "acc", "depth"), out, (gz["rgb"], gz["acc"], gz["depth"])):
+        assert rel_l2(a, b) < 2e-6, (name, rel_l2(a, b))

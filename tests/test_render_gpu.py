@@ -16,10 +16,11 @@ def _setup(precision="fp16"):
     return r.to("cuda:0"), sd, g, synth.synth_triplane(256, seed=7), torch.tensor(synth.WORLD_BOUNDS)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 3e-4)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 3e-4), ("fp16_mma", 3e-4)])
 def test_render_vs_reference_golden(precision, tol):
-    """fp32 = exact CUDA-core MLP; fp16 = tensor-core MLP (operand rounding averaged over 256 samples per ray:
-    the CPU emulation of the same numerics gives rgb 1.2e-5 / depth 4e-5).  north_star bar: 1e-3."""
+    """fp32 = exact CUDA-core MLP; fp16 = tcgen05 MLP (activations in tensor memory), fp16_mma = the mma.sync MLP
+    (operand rounding averaged over 256 samples per ray: the CPU emulation of the same numerics gives rgb 1.2e-5 /
+    depth 4e-5).  north_star bar: 1e-3."""
     r, sd, g, planes, bounds = _setup(precision)
     dev = torch.device("cuda:0")
     rgb, acc, depth = r.render_rays(planes[0].to(dev), bounds, g["rays_o"].to(dev), g["rays_d"].to(dev),
@@ -30,18 +31,74 @@ def test_render_vs_reference_golden(precision, tol):
     assert float((acc.cpu() - 1).abs().max()) < 1e-3      # reference quirk: acc ~ 1.00002 on every ray
 
 
-def test_render_tensor_core_equals_cuda_core_kernel():
-    """Both kernels on a full-resolution ray block, in-kernel uniforms with the same seed: the only difference
-    is the fp16 rounding of the MLP operands."""
+@pytest.mark.parametrize("precision", ["fp16", "fp16_mma"])
+def test_render_tensor_core_equals_cuda_core_kernel(precision):
+    """Tensor-core and exact kernels on a full-resolution ray block, in-kernel uniforms with the same seed: the only
+    difference is the fp16 rounding of the MLP operands.  An odd ray count exercises the ragged last CTA / group."""
     dev = torch.device("cuda:0")
-    r16, _, g, planes, bounds = _setup("fp16")
+    r16, _, g, planes, bounds = _setup(precision)
     r32, _, _, _, _ = _setup("fp32")
     ro, rd, near, far, hit = synth.synth_camera_rays(128, 128, focal=150.0, azimuth_deg=70.0)
+    ro, rd, near, far = ro[:16383], rd[:16383], near[:16383], far[:16383]
     a = r16.render_rays(planes[0].to(dev), bounds, ro.to(dev), rd.to(dev), near.to(dev), far.to(dev), u=None, seed=5)
     b = r32.render_rays(planes[0].to(dev), bounds, ro.to(dev), rd.to(dev), near.to(dev), far.to(dev), u=None, seed=5)
     for name, x, y in zip(("rgb", "acc", "depth"), a, b):
         assert not torch.isnan(x).any()
         assert rel_l2(x, y) < 3e-4, (name, rel_l2(x, y))
+
+
+def test_tcgen05_and_mma_kernels_agree_closely():
+    """Same operand rounding (fp16 features / activations / weights, fp32 accumulate) in both tensor-core kernels:
+    only the accumulation order inside the MMA differs."""
+    dev = torch.device("cuda:0")
+    r5, _, g, planes, bounds = _setup("fp16")
+    rm, _, _, _, _ = _setup("fp16_mma")
+    args = (planes[0].to(dev), bounds, g["rays_o"].to(dev), g["rays_d"].to(dev), g["near"].to(dev), g["far"].to(dev))
+    a = r5.render_rays(*args, u=g["u"].to(dev))
+    b = rm.render_rays(*args, u=g["u"].to(dev))
+    for name, x, y in zip(("rgb", "acc", "depth"), a, b):
+        assert rel_l2(x, y) < 5e-5, (name, rel_l2(x, y))
+
+
+def test_two_different_triplanes_in_a_row():
+    """a texel cache keyed on the tensor address served plane A's texels for plane B when the
+    allocator reused the address.  Render A, free it, render a same-shaped B: outputs must differ and match the oracle."""
+    from oracle import render_oracle
+    r, sd, g, _, bounds = _setup("fp16")
+    dev = torch.device("cuda:0")
+    n = 128
+    ray = [g[k][:n] for k in ("rays_o", "rays_d", "near", "far")]
+    outs = []
+    for seed in (7, 8):
+        planes = synth.synth_triplane(256, seed=seed)
+        pd = planes[0].to(dev)
+        rgb, acc, dep = r.render_rays(pd, bounds, *[t.to(dev) for t in ray], u=g["u"][:n].to(dev))
+        ref = render_oracle.render_rays(sd, planes[0], bounds, *ray, g["u"][:n])
+        assert rel_l2(rgb, ref[0]) < 3e-4 and rel_l2(dep, ref[2]) < 3e-4, seed
+        outs.append(rgb.clone())
+        del pd, rgb, acc, dep                                   # the next plane may land on the same address
+    assert rel_l2(outs[0], outs[1]) > 1e-2
+
+
+def test_n_importance_zero_vs_reference_golden():
+    """`if n_importance > 0` (recon_NeRF/lib/renderer.py:258): with 0 the coarse pass and sample_pdf are skipped and
+    the 128 coarse samples are composited.  Golden from the unmodified reference + the oracle on the same rays."""
+    from humanliff_b200 import render
+    from oracle import render_oracle
+    r, sd, g, planes, bounds = _setup("fp16")
+    gz = load_golden("render_noimp_256.npz")
+    dev = torch.device("cuda:0")
+    n = int(gz["n_rays"])
+    ray = [g[k][:n] for k in ("rays_o", "rays_d", "near", "far")]
+    ref = render_oracle.render_rays(sd, planes[0], bounds, *ray, None, n_importance=0)
+    for name, a, b in zip(("rgb", "acc", "depth"), ref, (gz["rgb"], gz["acc"], gz["depth"])):
+        assert rel_l2(a, b) < 2e-6, (name, rel_l2(a, b))        # the oracle restates the reference here too
+    tp = {"world_bounds": bounds[None].to(dev)}
+    lst = render(rays_o=ray[0][None].to(dev), rays_d=ray[1][None].to(dev), near=ray[2][None].to(dev),
+                 far=ray[3][None].to(dev), tri_planes=planes.to(dev), tp_input=tp, renderer=r, n_samples=128,
+                 perturb=0., n_importance=0, white_bkgd=False)
+    for name, a, b in (("rgb", lst[0][0], gz["rgb"]), ("acc", lst[1][0], gz["acc"]), ("depth", lst[3][0], gz["depth"])):
+        assert rel_l2(a, b) < 3e-4, (name, rel_l2(a, b))
 
 
 def test_render_reference_shaped_api_and_script_helper():
@@ -104,10 +161,11 @@ def test_render_recon_variant_no_depth_clamp():
         assert rel_l2(a, b) < 3e-4, (name, rel_l2(a, b))
 
 
-def test_density_grid_vs_oracle():
+@pytest.mark.parametrize("precision", ["fp16", "fp16_mma"])
+def test_density_grid_vs_oracle(precision):
     """extract_geometry's field (human_diffusion/NeRF/renderer.py:290-318): -sigma on linspace(min, max, res)^3."""
     from oracle import render_oracle
-    r, sd, g, planes, bounds = _setup("fp16")
+    r, sd, g, planes, bounds = _setup(precision)
     dev = torch.device("cuda:0")
     res = 20
     u = r.density_grid({"world_bounds": bounds[None].to(dev)}, planes.to(dev), resolution=res)

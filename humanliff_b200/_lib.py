@@ -52,9 +52,9 @@ SIGNATURES = {
                                c_i64, c_int, c_p]),
     "hl_render_set_profile": (c_int, [c_p]),
     "hl_density_grid_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
-    "hl_render_rays_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_int, c_p, c_p, c_p,
+    "hl_render_rays_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_int, c_p, c_p, c_p,
                                    c_i64, c_int, c_int, c_p]),
-    "hl_density_grid_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_p, c_p]),
+    "hl_density_grid_tc5": (c_int, [c_p, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "hl_render5_set_profile": (c_int, [c_p]),
     "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                   c_i64, c_int, c_p]),
@@ -87,12 +87,16 @@ MLP16_WF = MLP16_W2 + 128 * 168
 MLP16_WV = MLP16_WF + 128 * 136
 MLP16_HALVES = MLP16_WV + 64 * 136
 
-MLP16S_BYTES = 16384 + 32768 + 16384 + 32768 + 32768 + 16384
+MLP_TC5_BYTES = 16384 + 32768 + 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 392 * 4
 
 CONV_FORCE_SIMT = 1
 CONV_UPSAMPLE2X = 2
 CONV_TF32 = 4
 CONV_OUT_F16 = 8
+CONV_SPLIT3 = 16
+CONV_SPLIT2P = 32
+CONV_OUT_F16_SPLIT = 64
+OP_TF32, OP_SCALED, OP_SPLIT, OP_RAW_SHIFT = 1, 2, 4, 4
 
 _lib = None
 launch_count = 0   # number of C-ABI compute calls issued (each is >= 1 kernel launch)

@@ -27,7 +27,8 @@ struct ConvArgs {
     int Ho, Wo;      // output size
     int Hi, Wi;      // logical input size (after optional upsample)
     int64_t M;
-    int K;
+    int K;           // taps * Cin per operand pass
+    int npass, a_off[3], b_slab[3];   // hi + lo operand passes (HL_CONV_SPLIT3 / SPLIT2P), as in conv_tc.cu
 };
 
 template <typename T>
@@ -70,19 +71,20 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
         for (int j = 0; j < 4; ++j) {
             int k = k0 + lk + j;
             float va = 0.f, vb = 0.f;
-            if (k < a.K) {
-                int tap = k / a.Cin;
-                int ci = k - tap * a.Cin;
+            if (k < a.K * a.npass) {
+                const int pass = k / a.K, kk = k - pass * a.K;
+                int tap = kk / a.Cin;
+                int ci = kk - tap * a.Cin;
                 if (mvalid) {
                     int ky = tap / a.ksize, kx = tap - ky * a.ksize;
                     int iy = oy * a.stride + ky - pad;
                     int ix = ox * a.stride + kx - pad;
                     if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
                         if (a.ups) { iy >>= 1; ix >>= 1; }
-                        va = ldf(a.x, (((int64_t)ob * a.H + iy) * a.W + ix) * a.ldx + ci);
+                        va = ldf(a.x, (((int64_t)ob * a.H + iy) * a.W + ix) * a.ldx + a.a_off[pass] + ci);
                     }
                 }
-                if (nvalid) vb = ldf(a.w, ((int64_t)tap * a.Cout_pad + nrow) * a.Cin + ci);
+                if (nvalid) vb = ldf(a.w, ((int64_t)(a.b_slab[pass] * a.ksize * a.ksize + tap) * a.Cout_pad + nrow) * a.Cin + ci);
             }
             ra[j] = va;
             rb[j] = vb;
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
     };
 
     load_chunk(0);
-    for (int k0 = 0; k0 < a.K; k0 += BK) {
+    const int Ktot = a.K * a.npass;
+    for (int k0 = 0; k0 < Ktot; k0 += BK) {
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
             Bs[lk + j][lrow] = rb[j];
         }
         __syncthreads();
-        if (k0 + BK < a.K) load_chunk(k0 + BK);
+        if (k0 + BK < Ktot) load_chunk(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -122,8 +125,16 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
             if (n >= a.Cout) continue;
             float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
             if (a.res) v += a.res[mm * a.ldr + n];
-            if (a.y_f16) reinterpret_cast<__half *>(a.y)[mm * a.ldy + n] = __float2half_rn(v);
-            else reinterpret_cast<float *>(a.y)[mm * a.ldy + n] = v;
+            if (a.y_f16 == 2) {                          // scaled hi | lo pair (HL_CONV_OUT_F16_SPLIT)
+                const float vs = v * 0.00390625f;
+                const __half h = __float2half_rn(vs);
+                reinterpret_cast<__half *>(a.y)[mm * a.ldy + n] = h;
+                reinterpret_cast<__half *>(a.y)[mm * a.ldy + a.Cout + n] = __float2half_rn(vs - __half2float(h));
+            } else if (a.y_f16) {
+                reinterpret_cast<__half *>(a.y)[mm * a.ldy + n] = __float2half_rn(v);
+            } else {
+                reinterpret_cast<float *>(a.y)[mm * a.ldy + n] = v;
+            }
         }
     }
 }
@@ -133,7 +144,11 @@ static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, con
                        void *y, int ldy, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
                        int flags, cudaStream_t stream) {
     ConvArgs<T> a;
-    a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.y_f16 = (flags & HL_CONV_OUT_F16) ? 1 : 0;
+    a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.y_f16 = (flags & HL_CONV_OUT_F16_SPLIT) ? 2 : (flags & HL_CONV_OUT_F16) ? 1 : 0;
+    a.npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & HL_CONV_SPLIT2P) ? 2 : 1;
+    for (int q = 0; q < 3; ++q) { a.a_off[q] = 0; a.b_slab[q] = 0; }
+    if (a.npass == 3) { a.a_off[1] = Cin; a.b_slab[2] = 1; }
+    if (a.npass == 2) a.b_slab[1] = 1;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = hl_conv_cout_pad(Cout);
     a.ksize = ksize; a.stride = stride; a.ups = (flags & HL_CONV_UPSAMPLE2X) ? 1 : 0;
     a.Hi = a.ups ? 2 * H : H;

@@ -85,8 +85,11 @@ struct TcParams {
     int a_slots, a_slot_bytes, b_slots, b_slot_bytes, nbuf;
     const float *bias;
     int has_res;
-    int y_f16;               // output written as fp16 (an operand buffer) instead of fp32
-    int ksplit, kc_split, tiles_mn;   // split-K: tile = ks * tiles_mn + (m, n); split ks covers kc_split channel chunks
+    int y_f16;               // 1: output written as fp16 (an operand buffer) instead of fp32; 2: as a scaled fp16 hi | lo pair
+    // operand passes (hi + lo operands): the K loop runs npass * kchunks "virtual" chunks; pass q reads
+    // the A channels [a_off[q], a_off[q] + Cin) and the weight slab b_slab[q] (taps b_slab[q]*taps ..)
+    int npass, a_off[3], b_slab[3], vchunks;
+    int ksplit, kc_split, tiles_mn;   // split-K: tile = ks * tiles_mn + (m, n); split ks covers kc_split (virtual) chunks
     int split_b;             // batch-coordinate offset per split in the partial-sum workspace (= B)
     double *stats;
     int stats_ld;
@@ -223,13 +226,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int tile = cid; tile < p.total_tiles; tile += nct) {
                 const int ks = tile / p.tiles_mn;
                 const int mt = (tile - ks * p.tiles_mn) / p.n_tiles;
-                const int cbeg = ks * p.kc_split * chunk_elems;
+                int pass = (ks * p.kc_split) / p.kchunks, kcp = ks * p.kc_split - pass * p.kchunks;   // first virtual chunk
                 int w0[2], h0[2], n0[2];
                 box_origin(p, mt, 0, rank, w0[0], h0[0], n0[0]);
                 box_origin(p, mt, p.mh - 1, rank, w0[1], h0[1], n0[1]);
                 if (p.halo) {
                     const int rows = p.mh + 2;
-                    for (int kc = 0, c0 = cbeg; kc < p.kc_split; ++kc, c0 += chunk_elems) {
+                    for (int kc = 0; kc < p.kc_split; ++kc) {
+                        const int c0 = p.a_off[pass] + kcp * chunk_elems;
+                        if (++kcp == p.kchunks) { kcp = 0; ++pass; }
                         for (int r = 0; r < rows; ++r) {
                             { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
                             if (elect_one_sync()) {
@@ -251,7 +256,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t bytes = (uint32_t)(p.mh * A_BOX_BYTES);
                     const int xs0 = w0[0] * p.stride - pad, ys0 = h0[0] * p.stride - pad;
                     const int xs1 = w0[1] * p.stride - pad, ys1 = h0[1] * p.stride - pad;
-                    for (int kc = 0, c0 = cbeg; kc < p.kc_split; ++kc, c0 += chunk_elems) {
+                    for (int kc = 0; kc < p.kc_split; ++kc) {
+                        const int c0 = p.a_off[pass] + kcp * chunk_elems;
+                        if (++kcp == p.kchunks) { kcp = 0; ++pass; }
                         for (int ty = 0; ty < p.ksize; ++ty) {
                             for (int tx = 0; tx < p.ksize; ++tx) {
                                 { PROF_IF(7, lane == 0); mbar_wait(empty0 + 8 * slot, phase ^ 1u); }
@@ -287,8 +294,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t slot = 0, phase = 0;
             for (int tile = cid; tile < p.total_tiles; tile += nct) {
                 const int nt0 = (tile % p.n_tiles) * p.n_tile + rank * rows_b;     // tiles_mn is a multiple of n_tiles
-                for (int kc = 0, c0 = (tile / p.tiles_mn) * p.kc_split * chunk_elems; kc < p.kc_split; ++kc, c0 += chunk_elems) {
-                    for (int tap = 0; tap < p.taps; ++tap) {
+                const int v0 = (tile / p.tiles_mn) * p.kc_split;
+                int pass = v0 / p.kchunks, kcp = v0 - pass * p.kchunks;
+                for (int kc = 0; kc < p.kc_split; ++kc) {
+                    const int c0 = kcp * chunk_elems, tap0 = p.b_slab[pass] * p.taps;
+                    if (++kcp == p.kchunks) { kcp = 0; ++pass; }
+                    for (int tap = tap0; tap < tap0 + p.taps; ++tap) {
                         { PROF_IF(8, lane == 0); mbar_wait(bar_b_empty + 8 * slot, phase ^ 1u); }
                         if (elect_one_sync()) {
                             if (CTA2) {
@@ -551,6 +562,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                         if (p.has_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
                         const uint32_t hrow = sbuf + (uint32_t)row * 64u, hsw = ((uint32_t)row >> 1) & 3u;
+                        if (p.y_f16 == 2) {
+                            // scaled hi | lo pair (a raw residual-stream operand of a high-precision conv): v * 2^-8 =
+                            // hi + lo to ~22 bits; the hi tile is staged in the first 8 KB of the buffer, lo in the second
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= 0.00390625f;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
@@ -559,6 +576,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                          "r"(*reinterpret_cast<const uint32_t *>(&h0)), "r"(*reinterpret_cast<const uint32_t *>(&h1)),
                                          "r"(*reinterpret_cast<const uint32_t *>(&h2)), "r"(*reinterpret_cast<const uint32_t *>(&h3))
                                          : "memory");
+                            if (p.y_f16 == 2) {
+                                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                                const __half2 l0 = __floats2half2_rn(v[8 * j] - f0.x, v[8 * j + 1] - f0.y);
+                                const __half2 l1 = __floats2half2_rn(v[8 * j + 2] - f1.x, v[8 * j + 3] - f1.y);
+                                const __half2 l2 = __floats2half2_rn(v[8 * j + 4] - f2.x, v[8 * j + 5] - f2.y);
+                                const __half2 l3 = __floats2half2_rn(v[8 * j + 6] - f3.x, v[8 * j + 7] - f3.y);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + 8192u + (((uint32_t)j ^ hsw) << 4)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&l0)), "r"(*reinterpret_cast<const uint32_t *>(&l1)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&l2)), "r"(*reinterpret_cast<const uint32_t *>(&l3))
+                                             : "memory");
+                            }
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -570,6 +598,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
                         tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0 + ks * p.split_b);
+                        if (p.y_f16 == 2) tma_store_4d(&tmY, sbuf + 8192u, p.Cout + nbase, w0, h0, n0);
                         bulk_commit();
                         if (p.has_res) {
                             { PROF_IF(9, eg == 0); bulk_wait_read<1>(); }   // previous store drained -> refill its buffer
@@ -668,11 +697,20 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
                 a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
             }
             if (y_f16) {
-                const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                const float sc = y_f16 == 2 ? 0.00390625f : 1.0f;           // 2: scaled hi | lo pair, lo at channel Cout + c
+                const float4 as = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
+                const __half2 h0 = __floats2half2_rn(as.x, as.y), h1 = __floats2half2_rn(as.z, as.w);
                 uint2 w;
                 w.x = *reinterpret_cast<const uint32_t *>(&h0);
                 w.y = *reinterpret_cast<const uint32_t *>(&h1);
                 *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + c) = w;
+                if (y_f16 == 2) {
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn(as.x - f0.x, as.y - f0.y), l1 = __floats2half2_rn(as.z - f1.x, as.w - f1.y);
+                    w.x = *reinterpret_cast<const uint32_t *>(&l0);
+                    w.y = *reinterpret_cast<const uint32_t *>(&l1);
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + Cout + c) = w;
+                }
             } else {
                 *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + m * ldy + c) = a;
             }
@@ -786,7 +824,7 @@ int acc_stride_for(int n_tile) {
 }
 
 bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, bool has_res,
-               bool want_stats, Plan *pl) {
+               bool want_stats, Plan *pl, int npass = 1) {
     // H, W are OUTPUT dims here
     Tiling t;
     if (!pick_tiling(H, W, &t)) return false;
@@ -796,6 +834,9 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.stride = stride; p.ksize = ksize;
     p.taps = ksize * ksize;
     p.kchunks = Cin / chunk;
+    p.npass = npass;
+    p.vchunks = npass * p.kchunks;
+    for (int q = 0; q < 3; ++q) { p.a_off[q] = 0; p.b_slab[q] = 0; }
     p.kind = kind;
     p.bw = t.bw; p.bh = t.bh; p.bn = t.bn;
     p.tiles_w = W / t.bw;
@@ -933,7 +974,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     }
     (void)want_stats;
     p.ksplit = 1;
-    p.kc_split = p.kchunks;
+    p.kc_split = p.vchunks;
     p.tiles_mn = p.total_tiles;
     p.split_b = 0;
     return true;
@@ -949,25 +990,25 @@ inline int split_batch(const Plan &pl, int B) { return (B + pl.t.bn - 1) / pl.t.
 int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, size_t ws_bytes) {
     TcParams &p = pl.p;
     int S = 1;
-    if (!ws_bytes || g_tune_split == 0 || Cout % 4 || p.kchunks < 2) return 1;
+    if (!ws_bytes || g_tune_split == 0 || Cout % 4 || p.vchunks < 2) return 1;
     const int sms = hl_num_sms();
     // a slice holds whole batch boxes: B rounded up to the box's sample count (the padding rows receive the zero
     // rows TMA fills in for samples beyond B and are never read back)
     const size_t slice_bytes = (size_t)split_batch(pl, B) * H * W * pl.cout_pad * sizeof(float);
     auto fits = [&](const Plan &q, int s) {
-        return q.p.kchunks % s == 0 && (size_t)s * slice_bytes <= ws_bytes && q.grid * s <= sms &&
-               (q.p.kchunks / s) * q.p.taps >= 12;
+        return q.p.vchunks % s == 0 && (size_t)s * slice_bytes <= ws_bytes && q.grid * s <= sms &&
+               (q.p.vchunks / s) * q.p.taps >= 12;
     };
     auto cost = [&](const Plan &q, int s) {        // bytes through shared memory on one CTA's K loop
         const double rows_b = (double)q.p.n_tile / q.p.pair;
         const double stage = 4.0 * (128.0 * q.p.mh + rows_b) * 32.0 + rows_b * ROW_BYTES + (double)q.p.mh * A_BOX_BYTES;
         const int units = q.p.pair == 2 ? q.grid / 2 : q.grid;
         const double tiles = (double)((q.p.total_tiles + units - 1) / units);
-        return tiles * (q.p.kchunks / s) * q.p.taps * stage;
+        return tiles * (q.p.vchunks / s) * q.p.taps * stage;
     };
     if (g_tune_split > 1) {
-        if (p.kchunks % g_tune_split == 0 && (size_t)g_tune_split * slice_bytes <= ws_bytes) S = g_tune_split;
-    } else if (ksize == 3 && !p.halo && pl.grid < sms && p.kchunks * p.taps >= 54) {
+        if (p.vchunks % g_tune_split == 0 && (size_t)g_tune_split * slice_bytes <= ws_bytes) S = g_tune_split;
+    } else if (ksize == 3 && !p.halo && pl.grid < sms && p.vchunks * p.taps >= 54) {
 #ifndef HL_SPLIT_GAIN
 #define HL_SPLIT_GAIN 0.5
 #endif
@@ -981,8 +1022,9 @@ int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int
                 if (keep_ntile > 0) continue;                       // a forced tile is not second-guessed
                 q = Plan{};
                 g_tune_ntile = wdt;
-                const bool ok = make_plan(kind, B, H, W, Cin, Cout, ksize, stride, false, false, &q);
+                const bool ok = make_plan(kind, B, H, W, Cin, Cout, ksize, stride, false, false, &q, p.npass);
                 g_tune_ntile = keep_ntile;
+                if (ok) for (int e = 0; e < 3; ++e) { q.p.a_off[e] = p.a_off[e]; q.p.b_slab[e] = p.b_slab[e]; }
                 if (!ok || q.p.n_tile != wdt || q.p.halo || q.t.bn != pl.t.bn) continue;
             }
             for (int s = 8; s >= 2; --s) {
@@ -1071,7 +1113,7 @@ extern "C" int hl_conv2d_plan_info(int x_dtype, int B, int H, int W, int Cin, in
     (void)units;
     out[0] = 1; out[1] = p.pair; out[2] = p.mh; out[3] = p.n_tile; out[4] = p.halo; out[5] = p.a_slots;
     out[6] = p.b_slots; out[7] = p.nbuf; out[8] = p.acc_stages; out[9] = p.tmem_cols; out[10] = (int)pl.smem;
-    out[11] = grid; out[12] = p.total_tiles * S; out[13] = S; out[14] = p.kchunks / S;
+    out[11] = grid; out[12] = p.total_tiles * S; out[13] = S; out[14] = p.vchunks / S;
     out[15] = plan_epi_stats(pl, want_stats != 0 && S == 1) ? 1 : 0;
     return HL_OK;
 }
@@ -1088,7 +1130,9 @@ bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, 
     if (stride == 2 && (ksize != 3 || (H % 2) || (W % 2))) return false;
     if (x_dtype == HL_DT_F32 && !(flags & HL_CONV_TF32)) return false;
     const int esz = x_dtype == HL_DT_F16 ? 2 : 4;
-    if ((ldx * esz) % 16 || Cin > ldx || ldy % ((flags & HL_CONV_OUT_F16) ? 8 : 4)) return false;
+    if ((ldx * esz) % 16 || Cin > ldx || ldy % ((flags & (HL_CONV_OUT_F16 | HL_CONV_OUT_F16_SPLIT)) ? 8 : 4)) return false;
+    if ((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) && x_dtype != HL_DT_F16) return false;
+    if ((flags & HL_CONV_SPLIT3) && ldx < 2 * Cin) return false;
     Plan pl = {};
     if (!make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, false, false,
                    &pl))
@@ -1101,7 +1145,7 @@ int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *st
 
 int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
                  const float *residual, int ldr, void *y, int y_f16, int ldy, double *stats, int stats_ld, int B,
-                 int Hin, int Win, int Cin, int Cout, int ksize, int stride, cudaStream_t stream) {
+                 int Hin, int Win, int Cin, int Cout, int ksize, int stride, int flags, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) {
         hl_set_error("cuTensorMapEncodeTiled unavailable");
@@ -1111,8 +1155,16 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     const int esz = kind ? 2 : 4;
     const int chunk = kind ? 64 : 32;
     const int H = Hin / stride, W = Win / stride;
+    // hi + lo operand passes (HL_CONV_SPLIT3: x = [hi | lo] with lo at channel Cin, weights {W_hi, W_lo}: hi.hi +
+    // lo.hi + hi.lo; HL_CONV_SPLIT2P: hi and lo packed inside the Cin channels, weights {[W_hi | W_hi], [W_lo | 0]})
+    const int npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & HL_CONV_SPLIT2P) ? 2 : 1;
+    const int nslab = npass > 1 ? 2 : 1;
     Plan pl = {};
-    HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl));
+    HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl, npass));
+    if (npass == 3) { pl.p.a_off[1] = Cin; pl.p.b_slab[2] = 1; }
+    if (npass == 2) pl.p.b_slab[1] = 1;
+    HL_CHECK_ARG(npass == 1 || kind == 1);
+    HL_CHECK_ARG(y_f16 != 2 || (Cout % 32 == 0 && ldy >= 2 * Cout));
     HL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                  bias != nullptr && ((uintptr_t)bias & 15) == 0);
     HL_CHECK_ARG(!residual || (((uintptr_t)residual & 15) == 0 && ldr % 4 == 0));
@@ -1158,7 +1210,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
 
     CUtensorMap tmA, tmB, tmY, tmR;
     {
-        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+        cuuint64_t gdim[4] = {(cuuint64_t)(npass == 3 ? 2 * Cin : Cin), (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)Win * ldx * esz,
                               (cuuint64_t)Hin * Win * ldx * esz};
         cuuint32_t box[4], estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -1177,7 +1229,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         }
     }
     {
-        cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)pl.cout_pad, (cuuint64_t)p.taps};
+        cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)pl.cout_pad, (cuuint64_t)(p.taps * nslab)};
         cuuint64_t gstr[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)pl.cout_pad * Cin * esz};
         cuuint32_t box[3] = {(cuuint32_t)chunk, (cuuint32_t)(p.n_tile / p.pair), 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -1197,8 +1249,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         const int esz_o = f16 ? 2 : 4;
         CUtensorMap *tm = which ? &tmR : &tmY;
         if (!ptr || (which && S > 1)) { *tm = tmY; continue; }
-        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : Cout), (cuuint64_t)W, (cuuint64_t)H,
-                              (cuuint64_t)(S > 1 ? split_batch(pl, B) * S : B)};
+        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : (!which && y_f16 == 2) ? 2 * Cout : Cout), (cuuint64_t)W,
+                              (cuuint64_t)H, (cuuint64_t)(S > 1 ? split_batch(pl, B) * S : B)};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
         cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
         if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
@@ -1273,10 +1325,14 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
     HL_CHECK_ARG(ldx >= Cin && ldy >= Cout && (!residual || ldr >= Cout));
     HL_CHECK_ARG(!((flags & HL_CONV_UPSAMPLE2X) && stride != 1));
     HL_CHECK_ARG(!stats || stats_ld >= Cout);
-    HL_CHECK_ARG(!((flags & HL_CONV_OUT_F16) && stats));    // statistics are defined on fp32 results only
+    HL_CHECK_ARG(!((flags & (HL_CONV_OUT_F16 | HL_CONV_OUT_F16_SPLIT)) && stats));    // statistics are defined on fp32 results only
     if (hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags))
-        return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y, (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, stats,
-                            stats_ld, B, H, W, Cin, Cout, ksize, stride, (cudaStream_t)stream);
+        return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y,
+                            (flags & HL_CONV_OUT_F16_SPLIT) ? 2 : (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, stats,
+                            stats_ld, B, H, W, Cin, Cout, ksize, stride, flags, (cudaStream_t)stream);
+    HL_CHECK_ARG(!(flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) || x_dtype == HL_DT_F16);
+    HL_CHECK_ARG(!(flags & HL_CONV_SPLIT3) || ldx >= 2 * Cin);
+    HL_CHECK_ARG(!(flags & HL_CONV_OUT_F16_SPLIT) || ldy >= 2 * Cout);
     int rc = hl_conv2d_simt(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize, stride,
                             flags, (cudaStream_t)stream);
     if (rc != HL_OK || !stats) return rc;

@@ -33,16 +33,33 @@ int hl_num_sms() {
     return g_num_sms;
 }
 
+// Operand mode word (HL_OP_* in the header): bit 0 = TF32-round an fp32 operand, bit 1 = store value * 2^-8 (the
+// packed weights carry 2^8: a raw residual-stream operand keeps fp16 range up to 1.6e7), bit 2 = store an fp16
+// hi | lo pair (lo = fp16(v - hi), ~22 significant bits) with lo at + (mode >> 8) elements.
+__device__ __forceinline__ uint32_t h2_bits(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t lo_bits(float a, float b, uint32_t hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    return h2_bits(a - f.x, b - f.y);
+}
 // store 4 consecutive channels of an operand buffer: fp32 (optionally TF32-rounded) or fp16
-__device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, float4 v, int round_tf32) {
+__device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, float4 v, int mode) {
     if (dtype == HL_DT_F16) {
-        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        if (mode & HL_OP_SCALED) { v.x *= 0.00390625f; v.y *= 0.00390625f; v.z *= 0.00390625f; v.w *= 0.00390625f; }
         uint2 u;
-        u.x = *reinterpret_cast<uint32_t *>(&lo);
-        u.y = *reinterpret_cast<uint32_t *>(&hi);
+        u.x = h2_bits(v.x, v.y);
+        u.y = h2_bits(v.z, v.w);
         *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + idx) = u;
+        if (mode & HL_OP_SPLIT) {
+            uint2 l;
+            l.x = lo_bits(v.x, v.y, u.x);
+            l.y = lo_bits(v.z, v.w, u.y);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + idx + (mode >> 8)) = l;
+        }
     } else {
-        if (round_tf32) {
+        if (mode & HL_OP_TF32) {
             v.x = hl_rna_tf32(v.x); v.y = hl_rna_tf32(v.y);
             v.z = hl_rna_tf32(v.z); v.w = hl_rna_tf32(v.w);
         }
@@ -51,19 +68,29 @@ __device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, fl
 }
 
 // 8 consecutive channels: one 128-bit store for fp16 operands, two for fp32
-__device__ __forceinline__ void store_oct(void *dst, int dtype, int64_t idx, float4 a, float4 b, int round_tf32) {
+__device__ __forceinline__ void store_oct(void *dst, int dtype, int64_t idx, float4 a, float4 b, int mode) {
     if (dtype == HL_DT_F16) {
-        __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-        __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        if (mode & HL_OP_SCALED) {
+            a.x *= 0.00390625f; a.y *= 0.00390625f; a.z *= 0.00390625f; a.w *= 0.00390625f;
+            b.x *= 0.00390625f; b.y *= 0.00390625f; b.z *= 0.00390625f; b.w *= 0.00390625f;
+        }
         uint4 u;
-        u.x = *reinterpret_cast<uint32_t *>(&h0);
-        u.y = *reinterpret_cast<uint32_t *>(&h1);
-        u.z = *reinterpret_cast<uint32_t *>(&h2);
-        u.w = *reinterpret_cast<uint32_t *>(&h3);
+        u.x = h2_bits(a.x, a.y);
+        u.y = h2_bits(a.z, a.w);
+        u.z = h2_bits(b.x, b.y);
+        u.w = h2_bits(b.z, b.w);
         *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(dst) + idx) = u;
+        if (mode & HL_OP_SPLIT) {
+            uint4 l;
+            l.x = lo_bits(a.x, a.y, u.x);
+            l.y = lo_bits(a.z, a.w, u.y);
+            l.z = lo_bits(b.x, b.y, u.z);
+            l.w = lo_bits(b.z, b.w, u.w);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(dst) + idx + (mode >> 8)) = l;
+        }
     } else {
-        store_quad(dst, dtype, idx, a, round_tf32);
-        store_quad(dst, dtype, idx + 4, b, round_tf32);
+        store_quad(dst, dtype, idx, a, mode);
+        store_quad(dst, dtype, idx + 4, b, mode);
     }
 }
 
@@ -105,8 +132,17 @@ __global__ void k_nchw_to_nhwc(const float *__restrict__ src, const float *__res
                 if (c < ld && p < HW) {
                     float v = tile[threadIdx.x][py];
                     const int64_t o = ((int64_t)b * HW + p) * ld + c;
-                    if (dst_dtype == HL_DT_F16) reinterpret_cast<__half *>(dst)[o] = __float2half_rn(v);
-                    else reinterpret_cast<float *>(dst)[o] = round_tf32 ? hl_rna_tf32(v) : v;
+                    if (dst_dtype == HL_DT_F16) {
+                        const __half h = __float2half_rn(v);
+                        if (!(round_tf32 & HL_OP_SPLIT)) {
+                            reinterpret_cast<__half *>(dst)[o] = h;
+                        } else if (c < (round_tf32 >> 8)) {      // packed pair inside the row: [hi | lo at + lo_off]
+                            reinterpret_cast<__half *>(dst)[o] = h;
+                            reinterpret_cast<__half *>(dst)[o + (round_tf32 >> 8)] = __float2half_rn(v - __half2float(h));
+                        }
+                    } else {
+                        reinterpret_cast<float *>(dst)[o] = (round_tf32 & HL_OP_TF32) ? hl_rna_tf32(v) : v;
+                    }
                 }
             }
             __syncthreads();
@@ -433,8 +469,12 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
                            int stats_ld, const float *__restrict__ gamma, const float *__restrict__ beta,
                            const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
                            int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
-                           int silu, int round_tf32, int pix_per_block, int oct) {
+                           int silu, int op_mode, int pix_per_block, int oct) {
     hl_pdl_enter();
+    // op_mode: bits 0-2 = HL_OP_* of y (lo offset of a split y in bits 8+), bits 4-6 = HL_OP_* of the raw copy (a
+    // split raw copy has its lo half at channel C)
+    const int round_tf32 = (op_mode & 7) | (op_mode & ~0xFF);
+    const int raw_mode = ((op_mode >> 4) & 7) | (C << 8);
     __shared__ float sA[GN_MAX_C];
     __shared__ float sB[GN_MAX_C];
     __shared__ float gmean[64], grstd[64];
@@ -496,7 +536,7 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
         float ca[8], cb[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { ca[e] = sA[8 * j8 + e]; cb[e] = sB[8 * j8 + e]; }
-        const bool fast_silu = (y_dtype == HL_DT_F16) || round_tf32;
+        const bool fast_silu = (y_dtype == HL_DT_F16) || (round_tf32 & HL_OP_TF32);
         constexpr int U = 4;
         for (int pb = tp; pb < np; pb += lanes_p * U) {
             float4 v[U][2];
@@ -523,7 +563,7 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
                 const int64_t oidx = (pix0 + pp) * ldy + 8 * j8;
                 store_oct(y, y_dtype, oidx, make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]),
                           round_tf32);
-                if (raw) store_oct(raw, y_dtype, (pix0 + pp) * ldraw + 8 * j8, v[u][0], v[u][1], round_tf32);
+                if (raw) store_oct(raw, y_dtype, (pix0 + pp) * ldraw + 8 * j8, v[u][0], v[u][1], raw_mode);
             }
         }
         return;
@@ -541,7 +581,7 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
         o.z = fmaf(v.z, a.z, c.z); o.w = fmaf(v.w, a.w, c.w);
         if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
         store_quad(y, y_dtype, pix * ldy + 4 * j, o, round_tf32);
-        if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, round_tf32);
+        if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, raw_mode);
         p += dp;
         j += dj;
         if (j >= q) { j -= q; ++p; }
@@ -570,7 +610,7 @@ extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int sta
     if (threads < 64) threads = 256;
     HL_CHECK_CUDA(hl_launch(k_gn_apply, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
                                                        y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu,
-                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0));
+                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0));      // round_tf32 = the op_mode word
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

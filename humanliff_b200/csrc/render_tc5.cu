@@ -18,8 +18,13 @@
 //     alpha / rgb heads are plain per-thread dot products (a thread holds its sample's whole feature row);
 //   * while one group waits for its MMAs or for L2 gather latency, the other group's epilogue keeps the MUFU
 //     pipe (softplus = ex2 + lg2, the binding unit: 0.33 M transcendentals per ray) busy.
-// TMEM columns per group: accumulator 128 | A_h 64 (128 fp16 hidden activations) | A_x 16 (32 fp16 features).
-// Operand rounding is identical to render_tc.cu (fp16 features / activations / weights, fp32 accumulate).
+//   * the epilogue is 5.5 instructions per activation: biases ride in the GEMMs (feature slot 27 of x is 1.0 and
+//     carries the bias column of pts_linears.0 / .2; a per-ray constant tile A_c = [1 | pe(d) | 0] carries the
+//     biases of pts_linears.1 / feature_linear and the view-direction columns + bias of views_linear), and the
+//     softplus runs in the log2 domain, h' = max(a', 0) + lg2(1 + 2^-|a'|) with a' = a * log2(e): the factor
+//     log2(e) is folded into the weights that produce a', the factor ln 2 into the weights that consume h'.
+// TMEM columns per group: accumulator 128 | A_h 64 (128 fp16 hidden activations) | A_x 16 (32 fp16 features) |
+// A_c 16 (the constant tile).  Operand rounding: fp16 features / activations / weights (and biases), fp32 accumulate.
 #include "common.cuh"
 #include "tc5.cuh"
 
@@ -33,37 +38,33 @@ constexpr int NS = 128;                 // samples per pass = threads per ray gr
 constexpr int GROUPS = 2;
 constexpr int NT5 = NS * GROUPS;        // threads per CTA
 
-// pre-swizzled fp16 weight image (bytes); every atom = [rows][64 halves] K-major, 128 B rows, SWIZZLE_128B
-constexpr int OW0 = 0;                          // pts_linears.0   128 x 64  (k 0..26 used, 27..63 zero)
-constexpr int OW1 = OW0 + 16384;                // pts_linears.1   128 x 128 (2 atoms)
-constexpr int OW2X = OW1 + 32768;               // pts_linears.2, x part   128 x 64 (k 0..26 used)
-constexpr int OW2H = OW2X + 16384;              // pts_linears.2, h1 part  128 x 128 (2 atoms)
-constexpr int OWF = OW2H + 32768;               // feature_linear  128 x 128 (2 atoms)
-constexpr int OWV = OWF + 32768;                // views_linear (feature part)  64 x 128 (2 atoms of 8 KB)
-constexpr int W_BYTES = OWV + 16384;
-static_assert(W_BYTES == HL_MLP16S_BYTES, "header and kernel disagree on the swizzled fp16 MLP image");
-
-// fp32 table in shared memory
-constexpr int FB_B0 = 0, FB_B1 = 128, FB_B2 = 256, FB_BF = 384, FB_WA = 512, FB_BA = 640, FB_BV = 644;
-constexpr int FB_WVPE = 708;                 // [27][64]
-constexpr int FB_WR = FB_WVPE + 27 * 64;     // [64][4]
-constexpr int FB_BR = FB_WR + 64 * 4;        // [4]
-constexpr int FB_FLOATS = FB_BR + 4;
+// tcgen05 MLP image (bytes): pre-swizzled fp16 atoms [rows][64 halves] K-major, 128 B rows, SWIZZLE_128B, then a
+// small fp32 table.  L2E = log2(e), LN2 = ln 2 (see the header comment).
+constexpr int OW0 = 0;                          // pts_linears.0 * L2E   128 x 64  (k 0..26 weights, k 27 = bias * L2E)
+constexpr int OW1 = OW0 + 16384;                // pts_linears.1          128 x 128 (2 atoms)
+constexpr int OW2X = OW1 + 32768;               // pts_linears.2 x part * L2E   128 x 64 (k 27 = bias * L2E)
+constexpr int OW2H = OW2X + 16384;              // pts_linears.2 h1 part  128 x 128 (2 atoms)
+constexpr int OWF = OW2H + 32768;               // feature_linear * LN2   128 x 128 (2 atoms)
+constexpr int OWV = OWF + 32768;                // views_linear (feature part) * L2E   64 x 128 (2 atoms of 8 KB)
+constexpr int OWB = OWV + 16384;                // bias atom 128 x 64: k 0 = pts_linears.1 bias * L2E, k 16 = feature_linear bias
+constexpr int OWVP = OWB + 16384;               // 64 x 64: k 0 = views bias * L2E, k 1..27 = view-direction columns * L2E
+constexpr int W_BYTES = OWVP + 8192;
+constexpr int FB_WA = 0, FB_BA = 128, FB_WR = 132, FB_BR = 388, FB_FLOATS = 392;   // alpha_linear * LN2, rgb_linear^T * LN2 [64][4]
+static_assert(W_BYTES + 4 * FB_FLOATS == HL_MLP_TC5_BYTES, "header and kernel disagree on the tcgen05 MLP image");
 
 // per-group scratch (floats)
-constexpr int SC_ZC = 0, SC_ZN = 128, SC_ZF = 256, SC_CDF = 512, SC_BINS = 640, SC_PEB = 768, SC_PE = 832,
-              SC_RED = 864, SC_FLOATS = 928;
+constexpr int SC_ZC = 0, SC_ZN = 128, SC_ZF = 256, SC_CDF = 512, SC_BINS = 640, SC_PE = 768, SC_RED = 800,
+              SC_FLOATS = 864;
 
 constexpr size_t SMEM5 = 1024 + (size_t)W_BYTES + sizeof(float) * (FB_FLOATS + GROUPS * SC_FLOATS);
 
 // TMEM columns (per group: 256-column stride)
-constexpr uint32_t TM_ACC = 0, TM_AH = 128, TM_AX = 192, TM_GROUP = 256, TM_COLS = 512;
+constexpr uint32_t TM_ACC = 0, TM_AH = 128, TM_AX = 192, TM_AC = 208, TM_GROUP = 256, TM_COLS = 512;
 
 struct Render5Args {
     const float4 *tex;
     int R;
-    const float *mlp;                 // fp32 pack (biases, heads, view-direction weights), HL_MLP_* offsets
-    const uint4 *w16s;                // pre-swizzled fp16 weight image (HL_MLP16S_BYTES)
+    const uint4 *w16s;                // tcgen05 MLP image (HL_MLP_TC5_BYTES)
     const float *o, *d, *near, *far, *u, *zc_in;
     unsigned long long seed;
     float bounds[6];
@@ -78,10 +79,19 @@ struct Render5Args {
     float *grid_out;
 };
 
-__device__ __forceinline__ float softplus_fast(float x) {
-    const float l = hl_lg2(1.0f + hl_ex2(-1.4426950408889634f * fabsf(x)));
-    return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
+// softplus in the log2 domain: a = x * log2(e) in, softplus(x) / ln 2 out (MUFU.EX2, FADD, MUFU.LG2, FMNMX, FADD)
+__device__ __forceinline__ float softplus2(float a) { return fmaxf(a, 0.f) + hl_lg2(1.0f + hl_ex2(-fabsf(a))); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
+__device__ __forceinline__ float4 lds_f128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float softplus_acc(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 __device__ __forceinline__ float uniform_hash(unsigned long long seed, unsigned long long ray, int i) {
@@ -156,7 +166,7 @@ __device__ __noinline__ void gather_to_tmem(const float4 *__restrict__ tex, int 
     float f[28];
     gather_subplanes<0, 5>(tex, R, cx, cy, cz, f);
     gather_subplanes<5, 4>(tex, R, cx, cy, cz, f);
-    f[27] = 0.f;
+    f[27] = 1.0f;              // the bias column of pts_linears.0 / pts_linears.2 multiplies this slot
 #pragma unroll
     for (int k = 0; k < 14; ++k) xa[k] = pack_h2(f[2 * k], f[2 * k + 1]);
     xa[14] = 0u;
@@ -171,9 +181,9 @@ struct Group {
     uint32_t tm_cols;                 // TMEM base of the group (columns only) -- the MMA's D / A addresses
     uint32_t mbar;                    // the group's MMA-completion barrier
     uint32_t phase;
-    uint32_t w_smem;                  // shared-memory address of the weight image
-    const float *fb;                  // fp32 table
-    float *sc;                        // group scratch
+    uint32_t w_smem;                  // shared-memory address of the MLP image
+    uint32_t fb;                      // shared-memory address of the fp32 table
+    uint32_t sc;                      // shared-memory address of the group's scratch
 };
 
 __device__ __forceinline__ void gbar(const Group &G) { named_bar(1 + G.g, NS); }
@@ -221,9 +231,10 @@ __device__ __forceinline__ void run_layer(Group &G, F &&issue) {
 // Drain 32 accumulator columns [c0, c0+32) of this thread's row.
 __device__ __forceinline__ void acc_ld(const Group &G, int c0, uint32_t *r) { tmem_ld32_nowait(G.tm + TM_ACC + (uint32_t)c0, r); }
 
-// hidden layer epilogue: h = softplus(acc + bias) -> fp16 -> A_h; optionally the alpha head on the fp32 values
+// hidden layer epilogue: h' = softplus2(acc) (the bias is already in the accumulator) -> fp16 -> A_h; optionally the
+// alpha head on the fp32 values
 template <bool ALPHA, bool ACT>
-__device__ __forceinline__ float epi_hidden(const Group &G, const float *bias, const float *wa) {
+__device__ __forceinline__ float epi_hidden(const Group &G) {
     float s = 0.f;
     uint32_t va[32], vb[32];
     acc_ld(G, 0, va);
@@ -236,18 +247,14 @@ __device__ __forceinline__ float epi_hidden(const Group &G, const float *bias, c
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 b = *reinterpret_cast<const float4 *>(bias + c * 32 + 4 * j);
-            float h0 = __uint_as_float(cur[4 * j]) + b.x, h1 = __uint_as_float(cur[4 * j + 1]) + b.y;
-            float h2 = __uint_as_float(cur[4 * j + 2]) + b.z, h3 = __uint_as_float(cur[4 * j + 3]) + b.w;
-            if (ACT) { h0 = softplus_fast(h0); h1 = softplus_fast(h1); h2 = softplus_fast(h2); h3 = softplus_fast(h3); }
+            float h0 = __uint_as_float(cur[4 * j]), h1 = __uint_as_float(cur[4 * j + 1]);
+            float h2 = __uint_as_float(cur[4 * j + 2]), h3 = __uint_as_float(cur[4 * j + 3]);
+            if (ACT) { h0 = softplus2(h0); h1 = softplus2(h1); h2 = softplus2(h2); h3 = softplus2(h3); }
             pk[2 * j] = pack_h2(h0, h1);
             pk[2 * j + 1] = pack_h2(h2, h3);
             if (ALPHA) {
-                // same operand as render_tc.cu: the fp16-rounded activation, fp32 weights and accumulation
-                const float4 w = *reinterpret_cast<const float4 *>(wa + c * 32 + 4 * j);
-                const float2 q0 = __half22float2(*reinterpret_cast<const __half2 *>(&pk[2 * j]));
-                const float2 q1 = __half22float2(*reinterpret_cast<const __half2 *>(&pk[2 * j + 1]));
-                s = fmaf(q0.x, w.x, s); s = fmaf(q0.y, w.y, s); s = fmaf(q1.x, w.z, s); s = fmaf(q1.y, w.w, s);
+                const float4 w = lds_f128(G.fb + 4u * (uint32_t)(FB_WA + c * 32 + 4 * j));
+                s = fmaf(h0, w.x, s); s = fmaf(h1, w.y, s); s = fmaf(h2, w.z, s); s = fmaf(h3, w.w, s);
             }
         }
         tmem_st16(G.tm + TM_AH + (uint32_t)(c * 16), pk);
@@ -255,8 +262,8 @@ __device__ __forceinline__ float epi_hidden(const Group &G, const float *bias, c
     return s;
 }
 
-// views_linear epilogue: softplus(acc[0..63] + peb) . rgb_linear -> sigmoid
-__device__ __forceinline__ void epi_views(const Group &G, const float *peb, float (&rgb)[3]) {
+// views_linear epilogue: softplus2(acc[0..63]) . rgb_linear -> sigmoid
+__device__ __forceinline__ void epi_views(const Group &G, float (&rgb)[3]) {
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
     uint32_t va[32], vb[32];
     acc_ld(G, 0, va);
@@ -267,46 +274,51 @@ __device__ __forceinline__ void epi_views(const Group &G, const float *peb, floa
         uint32_t *cur = c ? vb : va;
         if (c) tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float2 b = *reinterpret_cast<const float2 *>(peb + c * 32 + 2 * j);
-            const uint32_t p = pack_h2(softplus_fast(__uint_as_float(cur[2 * j]) + b.x),
-                                       softplus_fast(__uint_as_float(cur[2 * j + 1]) + b.y));
-            const float2 q = __half22float2(*reinterpret_cast<const __half2 *>(&p));
-            const float4 w0 = *reinterpret_cast<const float4 *>(G.fb + FB_WR + (c * 32 + 2 * j) * 4);
-            const float4 w1 = *reinterpret_cast<const float4 *>(G.fb + FB_WR + (c * 32 + 2 * j + 1) * 4);
-            r0 = fmaf(q.x, w0.x, r0); r1 = fmaf(q.x, w0.y, r1); r2 = fmaf(q.x, w0.z, r2);
-            r0 = fmaf(q.y, w1.x, r0); r1 = fmaf(q.y, w1.y, r1); r2 = fmaf(q.y, w1.z, r2);
+        for (int j = 0; j < 32; ++j) {
+            const float h = softplus2(__uint_as_float(cur[j]));
+            const float4 w = lds_f128(G.fb + 4u * (uint32_t)(FB_WR + (c * 32 + j) * 4));
+            r0 = fmaf(h, w.x, r0); r1 = fmaf(h, w.y, r1); r2 = fmaf(h, w.z, r2);
         }
     }
-    rgb[0] = 1.0f / (1.0f + expf(-(r0 + G.fb[FB_BR + 0])));
-    rgb[1] = 1.0f / (1.0f + expf(-(r1 + G.fb[FB_BR + 1])));
-    rgb[2] = 1.0f / (1.0f + expf(-(r2 + G.fb[FB_BR + 2])));
+    rgb[0] = 1.0f / (1.0f + expf(-(r0 + lds_f32(G.fb + 4u * (FB_BR + 0)))));
+    rgb[1] = 1.0f / (1.0f + expf(-(r1 + lds_f32(G.fb + 4u * (FB_BR + 1)))));
+    rgb[2] = 1.0f / (1.0f + expf(-(r2 + lds_f32(G.fb + 4u * (FB_BR + 2)))));
 }
 
-// The decoder MLP for the 128 samples of the group (features already in A_x): returns (sigma, r, g, b).  ONE
-// out-of-line copy for every caller; an odd number of layers either way, so the caller flips G.phase once.
+// The decoder MLP for the 128 samples of the group (features already in A_x, the constant tile in A_c): returns
+// (sigma, r, g, b).  ONE out-of-line copy for every caller; an odd number of layers either way, so the caller flips
+// G.phase once.
 __device__ __noinline__ float4 mlp128(Group G, bool fine) {
-    // pts_linears.0: K = 32 (features), N = 128
+    // pts_linears.0: K = 32 (27 features + the ones slot), N = 128
     run_layer(G, [&] { issue_gemm(G, TM_AX, 2, OW0, 16384, 128, false); });
-    epi_hidden<false, true>(G, G.fb + FB_B0, nullptr);
-    // pts_linears.1: K = 128
-    run_layer(G, [&] { issue_gemm(G, TM_AH, 8, OW1, 16384, 128, false); });
-    epi_hidden<false, true>(G, G.fb + FB_B1, nullptr);
+    epi_hidden<false, true>(G);
+    // pts_linears.1: K = 128 (+ bias through the constant tile)
+    run_layer(G, [&] {
+        issue_gemm(G, TM_AH, 8, OW1, 16384, 128, false);
+        issue_gemm(G, TM_AC, 1, OWB, 16384, 128, true);
+    });
+    epi_hidden<false, true>(G);
     // pts_linears.2 on cat([x, h1])
     run_layer(G, [&] {
         issue_gemm(G, TM_AX, 2, OW2X, 16384, 128, false);
         issue_gemm(G, TM_AH, 8, OW2H, 16384, 128, true);
     });
     float4 out;
-    out.x = epi_hidden<true, true>(G, G.fb + FB_B2, G.fb + FB_WA) + G.fb[FB_BA];
+    out.x = epi_hidden<true, true>(G) + lds_f32(G.fb + 4u * FB_BA);
     out.y = out.z = out.w = 0.f;
     if (fine) {
-        // feature_linear (no activation), then views_linear on [feature | pe(d)] (pe part = per-ray bias peb)
-        run_layer(G, [&] { issue_gemm(G, TM_AH, 8, OWF, 16384, 128, false); });
-        epi_hidden<false, false>(G, G.fb + FB_BF, nullptr);
-        run_layer(G, [&] { issue_gemm(G, TM_AH, 8, OWV, 8192, 64, false); });
+        // feature_linear (no activation), then views_linear on [feature | 1 | pe(d)]
+        run_layer(G, [&] {
+            issue_gemm(G, TM_AH, 8, OWF, 16384, 128, false);
+            issue_gemm(G, TM_AC, 1, OWB + 32, 16384, 128, true);
+        });
+        epi_hidden<false, false>(G);
+        run_layer(G, [&] {
+            issue_gemm(G, TM_AH, 8, OWV, 8192, 64, false);
+            issue_gemm(G, TM_AC, 2, OWVP, 8192, 64, true);
+        });
         float rgb[3];
-        epi_views(G, G.sc + SC_PEB, rgb);
+        epi_views(G, rgb);
         out.y = rgb[0]; out.z = rgb[1]; out.w = rgb[2];
     }
     return out;
@@ -320,54 +332,42 @@ __device__ __forceinline__ float excl_cumprod128(const Group &G, float f, float 
         const float up = __shfl_up_sync(0xffffffffu, v, o);
         if (G.lane >= o) v *= up;
     }
-    float *red = G.sc + SC_RED;
+    const uint32_t red = G.sc + 4u * SC_RED;
     gbar(G);                                     // previous users of `red` are done
-    if (G.lane == 31) red[G.warp] = v;
+    if (G.lane == 31) sts_f32(red + 4u * (uint32_t)G.warp, v);
     gbar(G);
-    float pre = 1.f;
-    for (int i = 0; i < G.warp; ++i) pre *= red[i];
+    const float4 r = lds_f128(red);
+    const float pre = G.warp == 0 ? 1.f : G.warp == 1 ? r.x : G.warp == 2 ? r.x * r.y : (r.x * r.y) * r.z;
     float excl = __shfl_up_sync(0xffffffffu, v, 1);
     if (G.lane == 0) excl = 1.f;
-    if (total) *total = ((red[0] * red[1]) * red[2]) * red[3];
+    if (total) *total = ((r.x * r.y) * r.z) * r.w;
     return pre * excl;
 }
 
 __device__ __forceinline__ float group_sum(const Group &G, float v, int slot) {
     v = hl_warp_sum(v);
-    float *red = G.sc + SC_RED + 8 + slot * 4;
-    if (G.lane == 0) red[G.warp] = v;
+    const uint32_t red = G.sc + 4u * (uint32_t)(SC_RED + 8 + slot * 4);
+    if (G.lane == 0) sts_f32(red + 4u * (uint32_t)G.warp, v);
     gbar(G);
-    return ((red[0] + red[1]) + red[2]) + red[3];
+    const float4 r = lds_f128(red);
+    return ((r.x + r.y) + r.z) + r.w;
 }
 
 __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     extern __shared__ __align__(16) uint8_t smraw5[];
     __shared__ __align__(8) uint64_t mbars[GROUPS];
     __shared__ uint32_t tmem_slot;
+    __shared__ float bnd[8];
     const uint32_t base = (smem_u32(smraw5) + 1023u) & ~1023u;
     uint8_t *aligned = smraw5 + (base - smem_u32(smraw5));
-    float *fb = reinterpret_cast<float *>(aligned + W_BYTES);
     const int tid = threadIdx.x;
 
-    // one-time: weight image + fp32 table -> shared memory, TMEM allocation, barriers
+    // one-time: MLP image (fp16 atoms + fp32 table) -> shared memory, TMEM allocation, barriers
     {
         uint4 *dst = reinterpret_cast<uint4 *>(aligned);
-        for (int i = tid; i < W_BYTES / 16; i += NT5) dst[i] = __ldg(a.w16s + i);
-        for (int i = tid; i < 128; i += NT5) {
-            fb[FB_B0 + i] = __ldg(a.mlp + HL_MLP_B0 + i);
-            fb[FB_B1 + i] = __ldg(a.mlp + HL_MLP_B1 + i);
-            fb[FB_B2 + i] = __ldg(a.mlp + HL_MLP_B2 + i);
-            fb[FB_BF + i] = __ldg(a.mlp + HL_MLP_BF + i);
-            fb[FB_WA + i] = __ldg(a.mlp + HL_MLP_WA + i);
-        }
-        for (int i = tid; i < 4; i += NT5) {
-            fb[FB_BA + i] = __ldg(a.mlp + HL_MLP_BA + i);
-            fb[FB_BR + i] = __ldg(a.mlp + HL_MLP_BR + i);
-        }
-        for (int i = tid; i < 64; i += NT5) fb[FB_BV + i] = __ldg(a.mlp + HL_MLP_BV + i);
-        for (int i = tid; i < 27 * 64; i += NT5) fb[FB_WVPE + i] = __ldg(a.mlp + HL_MLP_WV + 128 * 64 + i);
-        for (int i = tid; i < 64 * 4; i += NT5) fb[FB_WR + i] = __ldg(a.mlp + HL_MLP_WR + i);
+        for (int i = tid; i < (W_BYTES + 4 * FB_FLOATS) / 16; i += NT5) dst[i] = __ldg(a.w16s + i);
     }
+    if (tid < 6) bnd[tid] = a.bounds_dev ? __ldg(a.bounds_dev + tid) : a.bounds[tid];
     if (tid < 32) {
         if (tid == 0) {
             for (int g = 0; g < GROUPS; ++g) mbar_init(smem_u32(&mbars[g]), 1);
@@ -393,15 +393,12 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     G.mbar = smem_u32(&mbars[G.g]);
     G.phase = 0;
     G.w_smem = base;
-    G.fb = fb;
-    G.sc = fb + FB_FLOATS + G.g * SC_FLOATS;
-    float *zc = G.sc + SC_ZC, *zn = G.sc + SC_ZN, *zf = G.sc + SC_ZF, *cdf = G.sc + SC_CDF, *bins = G.sc + SC_BINS;
-    float *peb = G.sc + SC_PEB, *pe = G.sc + SC_PE;
+    G.fb = base + W_BYTES;
+    G.sc = G.fb + 4u * (uint32_t)(FB_FLOATS + G.g * SC_FLOATS);
+    const uint32_t zc = G.sc + 4u * SC_ZC, zn = G.sc + 4u * SC_ZN, zf = G.sc + 4u * SC_ZF, cdf = G.sc + 4u * SC_CDF,
+                   bins = G.sc + 4u * SC_BINS, pe = G.sc + 4u * SC_PE;
     const int tg = G.tg;
-
-    __shared__ float bnd[8];
-    if (tid < 6) bnd[tid] = a.bounds_dev ? __ldg(a.bounds_dev + tid) : a.bounds[tid];
-    __syncthreads();
+    const uint32_t tg4 = 4u * (uint32_t)tg;
 
     const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long tp = prof ? clock64() : 0;
@@ -415,6 +412,13 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
 
     if (a.grid_out) {
         // ---------------- density-grid mode (Renderer.extract_geometry, human_diffusion/NeRF/renderer.py:290-318) -------
+        {   // the constant tile: [1 | 0 ...] (no view direction here; only the bias of pts_linears.1 uses it)
+            uint32_t ac[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) ac[k] = 0u;
+            ac[0] = pack_h2(1.0f, 0.f);
+            tmem_st16(G.tm + TM_AC, ac);
+        }
         const int res = a.grid_res;
         const long long total = (long long)res * res * res;
         const long long tiles = (total + 127) / 128;
@@ -447,26 +451,32 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 zmine = a.zc_in ? a.zc_in[ray * NS + tg] : __fadd_rn(__fmul_rn(nr, 1.0f - t), __fmul_rn(fr, t));
             }
             gbar(G);                                  // the previous ray of this group is fully consumed
-            zc[tg] = zmine;
-            if (tg < 27) {                            // positional encoding of the view direction (fields.py:69-85)
+            sts_f32(zc + tg4, zmine);
+            if (tg < 32) {                            // positional encoding of the view direction (fields.py:69-85)
                 const float dd[3] = {dx / dnorm, dy / dnorm, dz / dnorm};
-                float v;
+                float v = 0.f;
                 if (tg < 3) {
                     v = dd[tg];
-                } else {
+                } else if (tg < 27) {
                     const int f = (tg - 3) / 3, comp = (tg - 3) % 3;
                     const float freq = (float)(1 << (f >> 1));
                     const float phase = (f & 1) ? 1.5707963267948966f : 0.f;
                     v = sinf(__fadd_rn(phase, __fmul_rn(dd[comp], freq)));
                 }
-                pe[tg] = v;
+                sts_f32(pe + tg4, v);
             }
             gbar(G);
-            if (tg < 64) {                            // views_linear bias incl. the positional-encoding columns
-                float s = fb[FB_BV + tg];
+            {   // the constant tile of this ray: [1 | pe(27) | 0(4)] in every row
+                uint32_t ac[16];
+                float prev = 1.0f;
 #pragma unroll
-                for (int k = 0; k < 27; ++k) s = fmaf(fb[FB_WVPE + k * 64 + tg], pe[k], s);
-                peb[tg] = s;
+                for (int k = 0; k < 8; ++k) {
+                    const float4 q = lds_f128(pe + 16u * (uint32_t)k);
+                    ac[2 * k] = pack_h2(prev, q.x);
+                    ac[2 * k + 1] = pack_h2(q.y, q.z);
+                    prev = q.w;
+                }
+                tmem_st16(G.tm + TM_AC, ac);          // (pe[27..31] = 0, so halves 28..31 are zero)
             }
             RPROF(0)
             float rgb0[3] = {0.f, 0.f, 0.f}, rgb1[3] = {0.f, 0.f, 0.f}, sig0 = 0.f, sig1 = 0.f;
@@ -479,9 +489,10 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 G.phase ^= 1u;
                 RPROF(2)
                 // ------------------------------- up_sample + sample_pdf -----------------------------------
-                const float dist = (tg < NS - 1 ? zc[tg + 1] - zmine : 1e10f) * dnorm;
+                const float znext = tg < NS - 1 ? lds_f32(zc + tg4 + 4u) : 0.f;
+                const float dist = (tg < NS - 1 ? znext - zmine : 1e10f) * dnorm;
                 const float al = 1.0f - expf(-softplus_acc(sigma) * dist);
-                if (tg < NS - 1) bins[tg] = 0.5f * (zc[tg + 1] + zmine);
+                if (tg < NS - 1) sts_f32(bins + tg4, 0.5f * (znext + zmine));
                 const float T = excl_cumprod128(G, (1.0f - al) + 1e-10f, nullptr);
                 const float w = al * T;
                 const float wv = (tg >= 1 && tg <= NS - 2) ? w + 1e-5f : 0.f;     // weights[..., 1:-1] + 1e-5
@@ -494,57 +505,62 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                         const float up = __shfl_up_sync(0xffffffffu, v, o);
                         if (G.lane >= o) v += up;
                     }
-                    float *red = G.sc + SC_RED + 16;
-                    if (G.lane == 31) red[G.warp] = v;
+                    const uint32_t red = G.sc + 4u * (SC_RED + 16);
+                    if (G.lane == 31) sts_f32(red + 4u * (uint32_t)G.warp, v);
                     gbar(G);
-                    float pre = 0.f;
-                    for (int i = 0; i < G.warp; ++i) pre += red[i];
-                    if (tg <= NS - 2) cdf[tg] = pre + v;        // cdf[0] = 0, cdf[i] = pdf[1] + ... + pdf[i]
+                    const float4 r = lds_f128(red);
+                    const float pre = G.warp == 0 ? 0.f : G.warp == 1 ? r.x : G.warp == 2 ? r.x + r.y : (r.x + r.y) + r.z;
+                    if (tg <= NS - 2) sts_f32(cdf + tg4, pre + v);        // cdf[0] = 0, cdf[i] = pdf[1] + ... + pdf[i]
                 }
                 gbar(G);
                 float znew;
                 {
                     const float uu = a.u ? a.u[ray * NS + tg] : uniform_hash(a.seed, (unsigned long long)ray, tg);
                     int lo = 0, hi = NS - 1;
-                    while (lo < hi) {
+#pragma unroll
+                    for (int it = 0; it < 7; ++it) {          // 127 entries: 7 halvings always terminate
                         const int mid = (lo + hi) >> 1;
-                        if (cdf[mid] > uu) hi = mid; else lo = mid + 1;
+                        const bool gt = lds_f32(cdf + 4u * (uint32_t)mid) > uu;
+                        if (lo < hi) { if (gt) hi = mid; else lo = mid + 1; }
                     }
                     const int below = max(lo - 1, 0), above = min(NS - 2, lo);
-                    float den = cdf[above] - cdf[below];
+                    const float cb = lds_f32(cdf + 4u * (uint32_t)below), ca = lds_f32(cdf + 4u * (uint32_t)above);
+                    float den = ca - cb;
                     if (den < 1e-5f) den = 1.0f;
-                    const float t = (uu - cdf[below]) / den;
-                    znew = bins[below] + t * (bins[above] - bins[below]);
-                    zn[tg] = znew;
+                    const float t = (uu - cb) / den;
+                    const float bb = lds_f32(bins + 4u * (uint32_t)below), ba = lds_f32(bins + 4u * (uint32_t)above);
+                    znew = bb + t * (ba - bb);
+                    sts_f32(zn + tg4, znew);
                 }
                 gbar(G);
                 {   // sort(cat(z, z_new)) by ranking: coarse z is already sorted
                     int c_lt = 0, n_lt = 0;
-                    const float4 *zn4 = reinterpret_cast<const float4 *>(zn);
 #pragma unroll 4
                     for (int j = 0; j < NS / 4; ++j) {
-                        const float4 q = zn4[j];
+                        const float4 q = lds_f128(zn + 16u * (uint32_t)j);
                         c_lt += (q.x < zmine) + (q.y < zmine) + (q.z < zmine) + (q.w < zmine);
                         const int j4 = 4 * j;
                         n_lt += ((q.x < znew) || (q.x == znew && j4 < tg)) + ((q.y < znew) || (q.y == znew && j4 + 1 < tg)) +
                                 ((q.z < znew) || (q.z == znew && j4 + 2 < tg)) + ((q.w < znew) || (q.w == znew && j4 + 3 < tg));
                     }
                     int lo = 0, hi = NS;                   // number of coarse z <= znew
-                    while (lo < hi) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
                         const int mid = (lo + hi) >> 1;
-                        if (zc[mid] <= znew) lo = mid + 1; else hi = mid;
+                        const bool le = lds_f32(zc + 4u * (uint32_t)min(mid, NS - 1)) <= znew;
+                        if (lo < hi) { if (le) lo = mid + 1; else hi = mid; }
                     }
-                    zf[tg + c_lt] = zmine;
-                    zf[n_lt + lo] = znew;
+                    sts_f32(zf + 4u * (uint32_t)(tg + c_lt), zmine);
+                    sts_f32(zf + 4u * (uint32_t)(n_lt + lo), znew);
                 }
                 gbar(G);
                 RPROF(3)
             } else {
-                zf[tg] = zmine;
+                sts_f32(zf + tg4, zmine);
                 gbar(G);
             }
             // ------------------------------- fine pass: sorted samples tg and 128 + tg ----------------
-            const float z0 = zf[tg], z1 = a.n_importance ? zf[NS + tg] : 0.f;
+            const float z0 = lds_f32(zf + tg4), z1 = a.n_importance ? lds_f32(zf + 4u * NS + tg4) : 0.f;
 #pragma unroll 1
             for (int t = 0; t < n_tiles; ++t) {
                 const float z = t ? z1 : z0;
@@ -560,14 +576,14 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
             // ------------------------------- composite (renderer.py:222-239) --------------------------
             {
                 const int last = n_tiles * NS - 1;
-                const float d0 = tg < last ? zf[tg + 1] - z0 : 1e10f;                  // NOT scaled by |d|
+                const float d0 = tg < last ? lds_f32(zf + tg4 + 4u) - z0 : 1e10f;                  // NOT scaled by |d|
                 const float al0 = 1.0f - expf(-softplus_acc(sig0) * d0);
                 float P0;
                 const float T0 = excl_cumprod128(G, (1.0f - al0) + 1e-7f, &P0);
                 const float w0 = al0 * T0;
                 float w1 = 0.f;
                 if (n_tiles == 2) {
-                    const float d1 = NS + tg < last ? zf[NS + tg + 1] - z1 : 1e10f;
+                    const float d1 = NS + tg < last ? lds_f32(zf + 4u * NS + tg4 + 4u) - z1 : 1e10f;
                     const float al1 = 1.0f - expf(-softplus_acc(sig1) * d1);
                     const float T1 = P0 * excl_cumprod128(G, (1.0f - al1) + 1e-7f, nullptr);
                     w1 = al1 * T1;
@@ -576,17 +592,20 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                                w0 * rgb0[2] + w1 * rgb1[2], w0 * z0 + w1 * z1};
 #pragma unroll
                 for (int k = 0; k < 5; ++k) q5[k] = hl_warp_sum(q5[k]);
-                float *red = G.sc + SC_RED + 24;          // [5][4]
+                const uint32_t red = G.sc + 4u * (SC_RED + 24);          // [5][4]
                 gbar(G);
                 if (G.lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) red[k * 4 + G.warp] = q5[k];
+                    for (int k = 0; k < 5; ++k) sts_f32(red + 4u * (uint32_t)(k * 4 + G.warp), q5[k]);
                 }
                 gbar(G);
                 if (tg == 0) {
                     float s[5];
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) s[k] = ((red[k * 4] + red[k * 4 + 1]) + red[k * 4 + 2]) + red[k * 4 + 3];
+                    for (int k = 0; k < 5; ++k) {
+                        const float4 r = lds_f128(red + 16u * (uint32_t)k);
+                        s[k] = ((r.x + r.y) + r.z) + r.w;
+                    }
                     a.rgb[ray * 3 + 0] = s[1];
                     a.rgb[ray * 3 + 1] = s[2];
                     a.rgb[ray * 3 + 2] = s[3];
@@ -635,20 +654,18 @@ extern "C" int hl_render5_set_profile(void *dev_counters) {
     return HL_OK;
 }
 
-extern "C" int hl_render_rays_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+extern "C" int hl_render_rays_tc5(const float *texels, int R, const void *mlp_tc5,
                                   const float *rays_o, const float *rays_d, const float *near, const float *far,
                                   const float *z_coarse, const float *u, uint64_t seed, const float *bounds,
                                   int bounds_on_device, float *rgb, float *acc, float *depth, int64_t n_rays,
                                   int n_importance, int clamp_depth, void *stream) {
-    HL_CHECK_ARG(texels && mlp_packed && mlp_f16_swizzled && rays_o && rays_d && near && far && bounds && rgb && acc && depth);
-    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0 &&
-                 ((uintptr_t)mlp_f16_swizzled & 15) == 0);
+    HL_CHECK_ARG(texels && mlp_tc5 && rays_o && rays_d && near && far && bounds && rgb && acc && depth);
+    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
     HL_CHECK_ARG(n_importance == 0 || n_importance == NS);
     Render5Args a = {};
     a.tex = reinterpret_cast<const float4 *>(texels);
     a.R = R;
-    a.mlp = mlp_packed;
-    a.w16s = reinterpret_cast<const uint4 *>(mlp_f16_swizzled);
+    a.w16s = reinterpret_cast<const uint4 *>(mlp_tc5);
     a.o = rays_o; a.d = rays_d; a.near = near; a.far = far; a.u = u; a.zc_in = z_coarse;
     a.seed = seed;
     if (bounds_on_device) a.bounds_dev = bounds;
@@ -661,15 +678,14 @@ extern "C" int hl_render_rays_tc5(const float *texels, int R, const float *mlp_p
     return launch5(a, n_rays, (cudaStream_t)stream);
 }
 
-extern "C" int hl_density_grid_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+extern "C" int hl_density_grid_tc5(const float *texels, int R, const void *mlp_tc5,
                                    const float *bounds, int bounds_on_device, int resolution, float *out, void *stream) {
-    HL_CHECK_ARG(texels && mlp_packed && mlp_f16_swizzled && bounds && out && R > 0 && resolution >= 2);
-    HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0 && ((uintptr_t)mlp_f16_swizzled & 15) == 0);
+    HL_CHECK_ARG(texels && mlp_tc5 && bounds && out && R > 0 && resolution >= 2);
+    HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
     Render5Args a = {};
     a.tex = reinterpret_cast<const float4 *>(texels);
     a.R = R;
-    a.mlp = mlp_packed;
-    a.w16s = reinterpret_cast<const uint4 *>(mlp_f16_swizzled);
+    a.w16s = reinterpret_cast<const uint4 *>(mlp_tc5);
     if (bounds_on_device) a.bounds_dev = bounds;
     else for (int i = 0; i < 6; ++i) a.bounds[i] = bounds[i];
     a.grid_res = resolution;

@@ -150,15 +150,33 @@ class Renderer(nn.Module):
         put16(L.MLP16_WF, self.feature_linear.weight, 136)
         put16(L.MLP16_WV, self.views_linear.weight[:, :128], 136)
         self._mlp16 = img.to(device)
-        # tcgen05 kernel: the same fp16 weights as K-major SWIZZLE_128B atoms (HL_MLP16S_BYTES in the header)
-        w2 = self.pts_linears[2].weight.detach().float().cpu()
+        # tcgen05 kernel: fp16 K-major SWIZZLE_128B atoms + a small fp32 table (HL_MLP_TC5_BYTES in the header).  The
+        # softplus runs in the log2 domain (factor log2(e) folded into the producing weights, ln 2 into the consuming
+        # ones) and the biases ride in the GEMMs (slot 27 of x is 1.0; a constant tile [1 | pe(d)] for the others).
+        L2E, LN2 = 1.4426950408889634, 0.6931471805599453
+        f32 = lambda t: t.detach().double().cpu()
+        w0, b0 = f32(self.pts_linears[0].weight), f32(self.pts_linears[0].bias)
+        w1, b1 = f32(self.pts_linears[1].weight), f32(self.pts_linears[1].bias)
+        w2, b2 = f32(self.pts_linears[2].weight), f32(self.pts_linears[2].bias)
+        wf, bf = f32(self.feature_linear.weight), f32(self.feature_linear.bias)
+        wv, bv = f32(self.views_linear.weight), f32(self.views_linear.bias)
+        wa, ba = f32(self.alpha_linear.weight), f32(self.alpha_linear.bias)
+        wr, br = f32(self.rgb_linear.weight), f32(self.rgb_linear.bias)
+        w0p = torch.zeros(128, 28, dtype=torch.float64); w0p[:, :27] = w0 * L2E; w0p[:, 27] = b0 * L2E
+        w2x = torch.zeros(128, 28, dtype=torch.float64); w2x[:, :27] = w2[:, :27] * L2E; w2x[:, 27] = b2 * L2E
+        wb = torch.zeros(128, 64, dtype=torch.float64); wb[:, 0] = b1 * L2E; wb[:, 16] = bf
+        wvp = torch.zeros(64, 64, dtype=torch.float64); wvp[:, 0] = bv * L2E; wvp[:, 1:28] = wv[:, 128:155] * L2E
         atoms = []
-        for w in (self.pts_linears[0].weight, self.pts_linears[1].weight, w2[:, :27], w2[:, 27:],
-                  self.feature_linear.weight, self.views_linear.weight[:, :128]):
-            atoms += _sw128_atoms(w.detach().float().cpu())
-        sw = torch.cat(atoms)
-        assert sw.numel() * 2 == L.MLP16S_BYTES, sw.numel()
-        self._mlp16s = sw.to(device)
+        for w in (w0p, w1, w2x, w2[:, 27:], wf * LN2, wv[:, :128] * L2E, wb, wvp):
+            atoms += _sw128_atoms(w.float())
+        tab = torch.zeros(392, dtype=torch.float32)
+        tab[0:128] = (wa[0] * LN2).float()
+        tab[128] = float(ba[0])
+        tab[132:388].view(64, 4)[:, :3] = (wr.t() * LN2).float()
+        tab[388:391] = br.float()
+        img5 = torch.cat([torch.cat(atoms).view(torch.uint8), tab.view(torch.uint8)])
+        assert img5.numel() == L.MLP_TC5_BYTES, img5.numel()
+        self._mlp_tc5 = img5.to(device)
         self._pack_key = key
         return self._mlp
 
@@ -226,7 +244,7 @@ class Renderer(nn.Module):
                     u.data_ptr() if u is not None else None, int(seed) & ((1 << 64) - 1))
             tail = head + (bptr, rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n, 1 if self.clamp_depth else 0, stream)
             if tc5:
-                call("hl_render_rays_tc5", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16s.data_ptr(), *head,
+                call("hl_render_rays_tc5", tex.data_ptr(), planes.shape[-1], self._mlp_tc5.data_ptr(), *head,
                      bptr, bflag, rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n, int(n_importance),
                      1 if self.clamp_depth else 0, stream)
             elif self.precision == "fp16_mma":
@@ -260,7 +278,7 @@ class Renderer(nn.Module):
                 else:
                     barr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])
                     bptr, bflag = ctypes.cast(barr, ctypes.c_void_p), 0
-                call("hl_density_grid_tc5", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), self._mlp16s.data_ptr(),
+                call("hl_density_grid_tc5", tex.data_ptr(), planes.shape[-1], self._mlp_tc5.data_ptr(),
                      bptr, bflag, int(resolution), out.data_ptr(), stream)
             else:
                 barr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])

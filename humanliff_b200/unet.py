@@ -52,9 +52,17 @@ def _set_param(root, dotted, shape):
     node.register_parameter(parts[-1], nn.Parameter(torch.zeros(*shape), requires_grad=False))
 
 
-def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None):
+HP_SCALE = 256.0     # raw residual-stream operands are stored as value * 2^-8; their weights carry 2^8 (HL_OP_SCALED)
+
+
+def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=None):
     """OIHW (or Conv1d [O, I, 1]) weight -> packed ``[kh*kw][Cout_pad][Cin_pad]`` operand (fp16, TF32-rounded
-    fp32 or exact fp32) + padded fp32 bias.  One-time host-side re-layout at load time."""
+    fp32 or exact fp32) + padded fp32 bias.  One-time host-side re-layout at load time.
+
+    ``mode`` (fp16 only; the high-precision operand passes of DESIGN.md 3, HL_CONV_SPLIT3 / SPLIT2P in the header):
+    ``"scaled"`` weights * 2^8; ``"split"`` / ``"split_unscaled"`` two slabs ``{W_hi, W_lo}`` of the (scaled) weights,
+    ``W_lo = fp16(W - W_hi)``; ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
+    an operand row ``[hi(Cin) 0.. | lo(Cin) 0..]`` with the lo half at channel Cin_pad / 2."""
     lib = _lib.load()
     device = device if device is not None else weight.device
     w = weight.detach().to(device=device, dtype=torch.float32)
@@ -66,7 +74,23 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None):
     pk = torch.zeros(kh * kw, cout_pad, cin_pad, device=device, dtype=torch.float32)
     pk[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     if precision == "fp16":
-        pk = pk.to(torch.float16)          # round-to-nearest-even, as cvt.rn.f16.f32
+        if mode in ("scaled", "split"):
+            pk = pk * HP_SCALE
+        hi = pk.to(torch.float16)          # round-to-nearest-even, as cvt.rn.f16.f32
+        if mode in ("split", "split_unscaled", "split_packed"):
+            lo = (pk - hi.float()).to(torch.float16)
+            if mode == "split_packed":
+                half = cin_pad // 2
+                assert cin <= half, "split_packed needs 2 * Cin <= Cin_pad"
+                s0, s1 = hi.clone(), torch.zeros_like(hi)
+                s0[:, :, half:half + cin] = hi[:, :, :cin]
+                s1[:, :, :cin] = lo[:, :, :cin]
+                pk = torch.cat([s0, s1], 0)
+            else:
+                pk = torch.cat([hi, lo], 0)
+        else:
+            assert mode in (None, "scaled"), mode
+            pk = hi
     elif precision == "tf32":
         flat = pk.view(-1, 4)
         call("hl_cast_operand", _ptr(flat), 4, _ptr(flat), _lib.DT_F32, 4, 4, flat.shape[0], 1,
@@ -77,6 +101,21 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None):
     return pk.contiguous(), b
 
 
+def _hp_mode(name, cin, cin_pad):
+    """Which convs of the fp16 plan run the high-precision operand passes: the ones that read the RAW
+    residual stream -- 1x1 skip, ControlNet projection, Downsample, stem -- and the output conv carry hi + lo fp16
+    pairs (error budget: tools/error_budget.py); the Upsample conv reads a 2^-8-scaled operand (range only)."""
+    if name.endswith("skip_connection") or name.startswith("input_blocks_proj_cond.") or name.endswith(".op"):
+        return "split"
+    if name == "out.2":
+        return "split_unscaled"
+    if name in ("input_blocks.0.0", "input_blocks_cond.0.0"):
+        return "split_packed" if 2 * cin <= cin_pad else None
+    if name.endswith(".conv"):
+        return "scaled"
+    return None
+
+
 class _Conv:
     """One packed convolution / conv1d / linear-over-pixels."""
 
@@ -85,6 +124,7 @@ class _Conv:
         self.cin_pad = cin_pad or cin
         self.w = None
         self.b = None
+        self.hp = None           # high-precision operand mode of the fp16 plan (_hp_mode), set by UNetModel
 
 
 class UNetModel(nn.Module):
@@ -132,7 +172,12 @@ class UNetModel(nn.Module):
         self._convs = {}
         self._film = []          # (prefix, cout, offset) in stacking order
         self._film_rows = 0
+        # hi + lo operand passes for the raw-stream convs and the output conv (fp16 plan only; HL_HIPREC=0 = plain fp16)
+        self.hi_precision = precision == "fp16" and os.environ.get("HL_HIPREC", "1") != "0"
         self._build_plan()
+        if self.hi_precision:
+            for c in self._convs.values():
+                c.hp = _hp_mode(c.name, c.cin, c.cin_pad)
         self._packed_key = None
         self._plans = {}
         self.use_cuda_graph = True
@@ -261,7 +306,7 @@ class UNetModel(nn.Module):
         self._plans = {}          # plans hold pointers into the packed weights
         for c in self._convs.values():
             c.w, c.b = pack_conv(self._p(c.name + ".weight"), self._p(c.name + ".bias"), c.cin_pad,
-                                 self.precision, device)
+                                 self.precision, device, mode=c.hp)
         ws, bs = [], []
         for prefix, cout, off in self._film:
             ws.append(self._p(prefix + ".emb_layers.1.weight").detach().to(device, torch.float32))
@@ -344,7 +389,9 @@ class _Ref:
 
     def __init__(self, ptr, ld, C, H, W, st, st_ld, f16=False):
         self.ptr, self.ld, self.C, self.H, self.W, self.st, self.st_ld = ptr, ld, C, H, W, st, st_ld
-        self.f16 = f16       # an fp16 OPERAND buffer written directly by the producing conv (HL_CONV_OUT_F16)
+        # an fp16 OPERAND buffer written directly by the producing conv: 1 = HL_CONV_OUT_F16, 2 = HL_CONV_OUT_F16_SPLIT
+        # (scaled hi | lo pair, ld >= 2 C)
+        self.f16 = int(f16)
 
 
 class _StepPlan:
@@ -420,19 +467,40 @@ class _StepPlan:
         st = ("stats", dst.st) if (want_stats and dst.st is not None) else None
         if dst.f16:
             assert st is None
-            flags |= _lib.CONV_OUT_F16
+            flags |= _lib.CONV_OUT_F16_SPLIT if dst.f16 == 2 else _lib.CONV_OUT_F16
+        if c.hp in ("split", "split_unscaled"):
+            flags |= _lib.CONV_SPLIT3          # x_ptr = [hi(Cin) | lo(Cin)] rows, weights {W_hi, W_lo}
+            assert ldx >= 2 * c.cin_pad
+        elif c.hp == "split_packed":
+            flags |= _lib.CONV_SPLIT2P
         self.emit("hl_conv2d", x_ptr, self.dt, ldx, _ptr(c.w), _ptr(c.b), res.ptr if res else None,
                   res.ld if res else 0, dst.ptr, dst.ld, st, dst.st_ld if st else 0, self.B, H, W, c.cin_pad,
                   c.cout, c.ksize, c.stride, flags)
 
-    def gn(self, nname, x, out_ptr, ldo, silu, film=None, raw_ptr=None, ldraw=0):
+    def gn(self, nname, x, out_ptr, ldo, silu, film=None, raw_ptr=None, ldraw=0, out_mode=0, raw_mode=0):
+        """out_mode / raw_mode: HL_OP_* flags of the normalised output / the raw operand copy (a split output has
+        its lo half at channel C of a row of pitch >= 2 C)."""
         m = self.m
+        mode = self.rnd | out_mode | (raw_mode << _lib.OP_RAW_SHIFT)
+        if out_mode & _lib.OP_SPLIT:
+            mode |= x.C << 8
         self.emit("hl_gn_apply", x.ptr, x.ld, ("stats", x.st), x.st_ld, _ptr(m._norm_p[nname + ".weight"]),
                   _ptr(m._norm_p[nname + ".bias"]), film, m._film_rows if film is not None else 0, out_ptr,
-                  self.dt, ldo, raw_ptr, ldraw, self.B, x.H * x.W, x.C, 32, 1e-5, 1 if silu else 0, self.rnd)
+                  self.dt, ldo, raw_ptr, ldraw, self.B, x.H * x.W, x.C, 32, 1e-5, 1 if silu else 0, mode)
 
-    def cast(self, x, dst_ptr, ldd):
-        self.emit("hl_cast_operand", x.ptr, x.ld, dst_ptr, self.dt, ldd, x.C, self.B * x.H * x.W, self.rnd)
+    def raw_operand(self, cname, C):
+        """(pitch in elements, HL_OP_* mode) of the operand buffer a raw-stream conv reads."""
+        hp = self.m._convs[cname].hp
+        if hp == "split":
+            return 2 * C, _lib.OP_SPLIT | _lib.OP_SCALED
+        if hp == "scaled":
+            return C, _lib.OP_SCALED
+        return C, 0
+
+    def cast(self, x, dst_ptr, ldd, mode=0):
+        if mode & _lib.OP_SPLIT:
+            mode |= x.C << 8
+        self.emit("hl_cast_operand", x.ptr, x.ld, dst_ptr, self.dt, ldd, x.C, self.B * x.H * x.W, self.rnd | mode)
 
     # ---------------------------------------------------------------- blocks
     def res_block(self, blk, x, dst):
@@ -442,14 +510,17 @@ class _StepPlan:
         assert x.C == cin and dst.C == cout
         act = _ptr(self.scratch("act", self.max_act, op=True))
         h = _Ref(_ptr(self.scratch("h", self.max_act)), cout, cout, H, W, self.stats_row(cout), cout)
-        raw = _ptr(self.scratch("raw", self.max_act, op=True)) if blk["skip"] is not None else None
-        self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=cin)
+        raw, ldraw, raw_mode = None, 0, 0
+        if blk["skip"] is not None:
+            raw = _ptr(self.scratch("raw", self.max_raw, op=True))
+            ldraw, raw_mode = self.raw_operand(blk["skip"], cin)
+        self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=ldraw, raw_mode=raw_mode)
         self.conv(blk["c1"], act, cin, None, h, H, W)
         film = ("film", blk["film_off"])
         self.gn(blk["n2"], h, act, cout, True, film=film)
         if blk["skip"] is not None:
             s = _Ref(_ptr(self.scratch("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
-            self.conv(blk["skip"], raw, cin, None, s, H, W, want_stats=False)
+            self.conv(blk["skip"], raw, ldraw, None, s, H, W, want_stats=False)
             self.conv(blk["c2"], act, cout, s, dst, H, W)
         else:
             self.conv(blk["c2"], act, cout, x, dst, H, W)
@@ -494,12 +565,14 @@ class _StepPlan:
             elif kind == "attn":
                 self.attn_block(blk, x, out)
             elif kind == "down":
-                op = _ptr(self.scratch("raw", self.max_act, op=True))
-                self.cast(x, op, x.C)
-                self.conv(blk["c"], op, x.C, None, out, x.H, x.W)
+                op = _ptr(self.scratch("raw", self.max_raw, op=True))
+                ldop, mode = self.raw_operand(blk["c"], x.C)
+                self.cast(x, op, ldop, mode)
+                self.conv(blk["c"], op, ldop, None, out, x.H, x.W)
             elif kind == "up":
                 op = _ptr(self.scratch("upbuf", self.max_act, op=True))
-                self.emit("hl_upsample2x", x.ptr, x.ld, op, self.dt, x.C, self.B, x.H, x.W, x.C, self.rnd)
+                _, mode = self.raw_operand(blk["c"], x.C)
+                self.emit("hl_upsample2x", x.ptr, x.ld, op, self.dt, x.C, self.B, x.H, x.W, x.C, self.rnd | mode)
                 self.conv(blk["c"], op, x.C, None, out, H, W)
             else:
                 raise AssertionError(kind)
@@ -525,7 +598,9 @@ class _StepPlan:
                 # a ControlNet block's output is consumed only by its projection conv: write the fp16
                 # operand straight from the producing conv's epilogue (no fp32 tensor, no cast pass)
                 C_, H_, W_ = self.geo[i]
-                dst = _Ref(_ptr(self.scratch("hcop", self.max_act, op=True)), C_, C_, H_, W_, None, 0, f16=True)
+                ldp, pmode = self.raw_operand(f"input_blocks_proj_cond.{i}", C_)
+                dst = _Ref(_ptr(self.scratch("hcop", self.max_raw, op=True)), ldp, C_, H_, W_, None, 0,
+                           f16=2 if pmode & _lib.OP_SPLIT else 1)
             if i == 0:
                 out = dst if dst is not None else self.new_ref(f"{tag}{i}", mc, H, W)
                 self.conv(layers[0]["c"], xin_ptr, m.cin_pad, None, out, H, W)
@@ -537,15 +612,16 @@ class _StepPlan:
             if controlnet_branch:
                 cname = f"input_blocks_proj_cond.{i}"
                 if x.f16:
-                    op = x.ptr
+                    op, ldop = x.ptr, x.ld
                 else:
-                    op = _ptr(self.scratch("raw", self.max_act, op=True))
-                    self.cast(x, op, x.C)
+                    op = _ptr(self.scratch("raw", self.max_raw, op=True))
+                    ldop, pmode = self.raw_operand(cname, x.C)
+                    self.cast(x, op, ldop, pmode)
                 hc = self.new_ref(f"{tag}p{i}", x.C, x.H, x.W)
-                self.conv(cname, op, x.C, None, hc, x.H, x.W)                    # h_cond (unet.py:600)
+                self.conv(cname, op, ldop, None, hc, x.H, x.W)                   # h_cond (unet.py:600)
                 if self.concurrent:
                     self.emit_sync("wait", i)                                    # hs[i] of the main encoder
-                self.conv(cname, op, x.C, self.hs[i], cats[i], x.H, x.W)         # hs + hs_cond (unet.py:606)
+                self.conv(cname, op, ldop, self.hs[i], cats[i], x.H, x.W)        # hs + hs_cond (unet.py:606)
                 x = hc
             elif self.keep_hs and self.concurrent:
                 self.emit_sync("signal", i)                                      # hs[i] complete
@@ -570,6 +646,7 @@ class _StepPlan:
         mc, ed = m.model_channels, m.emb_dim
         dev = self.device
         self.max_act, self.max_qkv = self._scratch_sizes()
+        self.max_raw = self.max_act * (2 if m.hi_precision else 1)       # split raw operands are hi | lo pairs
         # static inputs / outputs of the graph
         self.x_in = torch.zeros(B, m.in_channels, H, W, device=dev)
         self.xc_in = torch.zeros(B, m.in_channels, H, W, device=dev) if m.cond_type == "controlnet" else None
@@ -603,8 +680,11 @@ class _StepPlan:
 
         self.emit("hl_zero", ("stats", 0), ("stats_bytes",))
         xin = self.opbuf("xin", B * H * W * m.cin_pad)
+        stem_mode = self.rnd
+        if m._convs["input_blocks.0.0"].hp == "split_packed":
+            stem_mode |= _lib.OP_SPLIT | ((m.cin_pad // 2) << 8)      # row = [hi(27) 0.. | lo(27) 0..]
         self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), None, _ptr(xin), self.dt, B, m.in_channels, H * W,
-                  m.cin_pad, self.rnd)
+                  m.cin_pad, stem_mode)
 
         # --- encoder, middle (unet.py:589-592) and ControlNet encoder (unet.py:594-602) ---
         # The two encoders are independent until the decoder.  With `concurrent` the ControlNet branch is
@@ -619,7 +699,7 @@ class _StepPlan:
         if controlnet:
             xcin = self.opbuf("xcin", B * H * W * m.cin_pad)
             self.emit("hl_nchw_to_nhwc", _ptr(self.x_in), _ptr(self.xc_in), _ptr(xcin), self.dt, B,
-                      m.in_channels, H * W, m.cin_pad, self.rnd)
+                      m.in_channels, H * W, m.cin_pad, stem_mode)
         if self.concurrent:
             self.emit_sync("fork")             # the ControlNet stem conv needs only xcin: it overlaps the embedding GEMVs
         # --- embeddings (unet.py:564,584-586; all ResBlock emb_layers in one GEMV) ---
@@ -659,10 +739,12 @@ class _StepPlan:
 
         # --- out: GN -> SiLU -> conv3x3 (unet.py:471-475,612) ---
         act = _ptr(self.scratch("act", self.max_act, op=True))
-        self.gn("out.0", x, act, x.C, True)
+        ldo, omode = (2 * x.C, _lib.OP_SPLIT) if m._convs["out.2"].hp == "split_unscaled" else (x.C, 0)
+        assert B * H * W * ldo <= self.max_act
+        self.gn("out.0", x, act, ldo, True, out_mode=omode)
         co_pad = 32 * ((m.out_channels + 31) // 32)
         eps = _Ref(_ptr(self.buf("eps_nhwc", B * H * W * co_pad)), co_pad, m.out_channels, H, W, None, 0)
-        self.conv("out.2", act, x.C, None, eps, H, W, want_stats=False)
+        self.conv("out.2", act, ldo, None, eps, H, W, want_stats=False)
         self.emit("hl_nhwc_to_nchw", eps.ptr, co_pad, _ptr(self.out), B, m.out_channels, H * W)
 
         # --- resolve the symbolic statistics / FiLM pointers ---

@@ -42,10 +42,28 @@ extern "C" {
 #define HL_DT_F16 1   /* IEEE fp16: 11-bit significand like TF32, half the bytes, 2x the MMA rate   */
 
 /* hl_conv2d flags */
+/* Operand mode word of the kernels that WRITE conv operands (the `round_tf32` argument of hl_nchw_to_nhwc,
+ * hl_cast_operand, hl_upsample2x, hl_gn_apply): */
+#define HL_OP_TF32 1      /* fp32 operand: round to TF32 (cvt.rna)                                            */
+#define HL_OP_SCALED 2    /* fp16 operand: store value * 2^-8 (the conv's packed weights carry 2^8): a raw
+                             residual-stream operand keeps fp16 range up to 1.6e7 instead of 65504           */
+#define HL_OP_SPLIT 4     /* fp16 operand: store an fp16 hi | lo pair (lo = fp16(v - hi), ~22 significant bits),
+                             lo at + (mode >> 8) elements -- the operand of HL_CONV_SPLIT3 / SPLIT2P convs   */
+#define HL_OP_RAW_SHIFT 4 /* hl_gn_apply: bits 4-6 = the HL_OP_* flags of the raw copy (split: lo at channel C) */
+
 #define HL_CONV_FORCE_SIMT 1   /* use the fp32 CUDA-core kernel even where the tcgen05 path applies */
 #define HL_CONV_UPSAMPLE2X 2   /* input is read through a nearest x2 upsample (unet.py:77)          */
 #define HL_CONV_TF32 4         /* fp32 operands may go through tcgen05 kind::tf32                   */
 #define HL_CONV_OUT_F16 8      /* y is an fp16 operand buffer (pitch ldy in halves); no statistics   */
+/* High-precision operand passes of the fp16 plan (tcgen05 kernel only).  The convs that read the RAW
+ * residual stream (1x1 skip, ControlNet projection, Downsample, stem) and the output conv carry each operand as an
+ * fp16 hi + lo pair (~22 significant bits) and run three (two) tensor-core passes into one accumulator:          */
+#define HL_CONV_SPLIT3 16      /* x = [hi(Cin) | lo(Cin)] per pixel (ldx >= 2 Cin), w = {W_hi, W_lo} slabs
+                                  [2*taps][Cout_pad][Cin]:  y = x_hi.W_hi + x_lo.W_hi + x_hi.W_lo          */
+#define HL_CONV_SPLIT2P 32     /* hi and lo packed INSIDE the Cin channels (stem: [hi(27) 0(5) | lo(27) 0(5)]),
+                                  w = {[W_hi | W_hi], [W_lo | 0]}:  two passes                              */
+#define HL_CONV_OUT_F16_SPLIT 64  /* y = [hi(Cout) | lo(Cout)] fp16 of (result * 2^-8) (ldy >= 2 Cout,
+                                  Cout % 32 == 0): the operand of a following HL_CONV_SPLIT3 conv           */
 
 int hl_version(void);
 const char *hl_last_error(void);
@@ -300,22 +318,31 @@ int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, cons
                        const float *bounds /*host*/, int resolution, float *out, void *stream);
 
 /* ---- tcgen05 / TMEM renderer (the default of precision="fp16") ---------------------------------------------
- * Same chain and operand rounding as hl_render_rays_tc, but every MLP layer is a tcgen05.mma (M = 128 samples,
- * accumulators and activations in tensor memory, weights resident in shared memory); two ray groups per SM.
- * mlp_f16_swizzled: HL_MLP16S_BYTES bytes = the fp16 weights as K-major SWIZZLE_128B atoms [rows][64 halves]
- * (16-byte chunk c of row r stored at chunk c ^ (r & 7)), in the order
- *   pts_linears.0 (128 x 64, k = x(27) | 0) | pts_linears.1 (2 atoms) | pts_linears.2 x part (128 x 64) |
- *   pts_linears.2 h1 part (2 atoms) | feature_linear (2 atoms) | views_linear feature part (2 atoms of 64 rows).
+ * Same chain as hl_render_rays_tc, but every MLP layer is a tcgen05.mma (M = 128 samples, accumulators AND
+ * activations in tensor memory, weights resident in shared memory); two ray groups per SM.
+ * mlp_tc5: HL_MLP_TC5_BYTES bytes.  First the fp16 operands as K-major SWIZZLE_128B atoms [rows][64 halves] (the
+ * 16-byte chunk c of row r stored at chunk c ^ (r & 7)); L2E = log2(e), LN2 = ln 2 (the softplus runs in the log2
+ * domain: the factor L2E is folded into the weights that feed a softplus, LN2 into the weights that read one):
+ *   pts_linears.0 * L2E          128 x 64   k 0..26 = weights, k 27 = bias * L2E (x carries a 1.0 in slot 27)
+ *   pts_linears.1                128 x 128  (2 atoms)
+ *   pts_linears.2 x part * L2E   128 x 64   k 27 = bias * L2E
+ *   pts_linears.2 h1 part        128 x 128  (2 atoms)
+ *   feature_linear * LN2         128 x 128  (2 atoms)
+ *   views_linear[:, :128] * L2E   64 x 128  (2 atoms of 64 rows)
+ *   bias atom                    128 x 64   k 0 = pts_linears.1 bias * L2E, k 16 = feature_linear bias
+ *   views_linear[:, 128:] * L2E   64 x 64   k 0 = views bias * L2E, k 1..27 = view-direction columns
+ * then 392 floats: alpha_linear.weight * LN2 [128], alpha bias [1] + 3 pad, rgb_linear.weight^T * LN2 [64][4],
+ * rgb bias [3] + 1 pad.
  * bounds: 6 floats {min xyz, max xyz}, host memory, or device memory when bounds_on_device != 0 (no host sync on
  * tp_input['world_bounds']).  n_importance: 128, or 0 = no coarse pass: the n_samples = 128 coarse depths are
  * composited directly (recon_NeRF/lib/renderer.py:258 `if n_importance > 0`).                                  */
-#define HL_MLP16S_BYTES (16384 + 32768 + 16384 + 32768 + 32768 + 16384)
-int hl_render_rays_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+#define HL_MLP_TC5_BYTES (16384 + 32768 + 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 392 * 4)
+int hl_render_rays_tc5(const float *texels, int R, const void *mlp_tc5,
                        const float *rays_o, const float *rays_d, const float *near, const float *far,
                        const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
                        const float *bounds, int bounds_on_device, float *rgb, float *acc, float *depth,
                        int64_t n_rays, int n_importance, int clamp_depth, void *stream);
-int hl_density_grid_tc5(const float *texels, int R, const float *mlp_packed, const void *mlp_f16_swizzled,
+int hl_density_grid_tc5(const float *texels, int R, const void *mlp_tc5,
                         const float *bounds, int bounds_on_device, int resolution, float *out, void *stream);
 /* per-phase cycle counters of (CTA 0, group 0) of following tc5 launches, as hl_render_set_profile */
 int hl_render5_set_profile(void *dev_counters);

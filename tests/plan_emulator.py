@@ -36,12 +36,22 @@ def _round_tf32(a):
     return ((i + 0x1000) & ~0x1FFF).view(np.float32)
 
 
-def _store_operand(dst_ptr, dtype_code, rows, cols, ld, values, round_tf32):
-    out = pitched(dst_ptr, rows, cols, ld, _dt(dtype_code))
+OP_TF32, OP_SCALED, OP_SPLIT = 1, 2, 4          # HL_OP_* of include/humanliff_b200.h
+
+
+def _store_operand(dst_ptr, dtype_code, rows, cols, ld, values, mode):
+    """`mode` = the HL_OP_* word: TF32 rounding (fp32), 2^-8 scaling and hi | lo split with lo at + (mode >> 8) (fp16)."""
     if dtype_code == 1:
-        out[...] = values.astype(np.float16)
+        v = values.astype(np.float32) * (np.float32(2.0 ** -8) if mode & OP_SCALED else np.float32(1.0))
+        hi = v.astype(np.float16)
+        pitched(dst_ptr, rows, cols, ld, np.float16)[...] = hi
+        if mode & OP_SPLIT:
+            lo_off = mode >> 8
+            lo = (v - hi.astype(np.float32)).astype(np.float16)
+            pitched(dst_ptr + 2 * lo_off, rows, cols, ld, np.float16)[...] = lo
     else:
-        out[...] = _round_tf32(values) if round_tf32 else values
+        out = pitched(dst_ptr, rows, cols, ld, np.float32)
+        out[...] = _round_tf32(values) if mode & OP_TF32 else values
 
 
 def hl_zero(ptr, nbytes, stream):
@@ -77,6 +87,12 @@ def hl_nchw_to_nhwc(src, src2, dst, dst_dtype, B, C, HW, ld, round_tf32, stream)
         v = v + view(src2, B * C * HW).reshape(B, C, HW)
     full = np.zeros((B * HW, ld), np.float32)
     full[:, :C] = v.transpose(0, 2, 1).reshape(B * HW, C)
+    if dst_dtype == 1 and round_tf32 & OP_SPLIT:          # packed pair inside the row: [hi(C) 0.. | lo(C) 0..]
+        lo_off = round_tf32 >> 8
+        hi = full.astype(np.float16)
+        full[:, lo_off:lo_off + C] = (full[:, :C] - hi[:, :C].astype(np.float32))
+        full[:, :C] = hi[:, :C].astype(np.float32)
+        round_tf32 = 0
     _store_operand(dst, dst_dtype, B * HW, ld, ld, full, round_tf32)
 
 
@@ -122,24 +138,47 @@ def hl_gn_apply(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y, y_dtype,
     if silu:
         t = torch.from_numpy(o)
         o = (t * torch.sigmoid(t)).numpy()
-    _store_operand(y, y_dtype, B * HW, C, ldy, o.reshape(B * HW, C).astype(np.float32), round_tf32)
+    # op-mode word: bits 0-2 = HL_OP_* of y (lo offset in bits 8+), bits 4-6 = HL_OP_* of the raw copy (lo at channel C)
+    y_mode = (round_tf32 & 7) | (round_tf32 & ~0xFF)
+    raw_mode = ((round_tf32 >> 4) & 7) | (C << 8)
+    _store_operand(y, y_dtype, B * HW, C, ldy, o.reshape(B * HW, C).astype(np.float32), y_mode)
     if raw:
-        _store_operand(raw, y_dtype, B * HW, C, ldraw, v.reshape(B * HW, C).copy(), round_tf32)
+        _store_operand(raw, y_dtype, B * HW, C, ldraw, v.reshape(B * HW, C).copy(), raw_mode)
 
 
 def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin, Cout, ksize, stride,
               flags, stream):
     assert not (flags & 2), "the plan upsamples explicitly"
     cout_pad = (Cout + 31) // 32 * 32
-    xv = torch.from_numpy(pitched(x, B * H * W, Cin, ldx, _dt(x_dtype)).astype(np.float32)).reshape(B, H, W, Cin)
-    wv = torch.from_numpy(view(wpk, ksize * ksize * cout_pad * Cin, _dt(x_dtype)).astype(np.float32))
-    wv = wv.reshape(ksize, ksize, cout_pad, Cin)[:, :, :Cout].permute(2, 3, 0, 1).contiguous()
+    esz = 2 if x_dtype == 1 else 4
+    taps = ksize * ksize
+
+    def xop(off):
+        return torch.from_numpy(pitched(x + esz * off, B * H * W, Cin, ldx, _dt(x_dtype)).astype(np.float32)) \
+            .reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+
+    def wslab(i):
+        wv = torch.from_numpy(view(wpk + esz * i * taps * cout_pad * Cin, taps * cout_pad * Cin, _dt(x_dtype)).astype(np.float32))
+        return wv.reshape(ksize, ksize, cout_pad, Cin)[:, :, :Cout].permute(2, 3, 0, 1).contiguous()
+
     bv = torch.from_numpy(view(bias, Cout).copy())
-    out = F.conv2d(xv.permute(0, 3, 1, 2), wv, bv, stride=stride, padding=ksize // 2).permute(0, 2, 3, 1)
+    cv = lambda a, w: F.conv2d(a, w, None, stride=stride, padding=ksize // 2)
+    if flags & 16:        # HL_CONV_SPLIT3: x = [hi | lo], w = {W_hi, W_lo}: hi.hi + lo.hi + hi.lo
+        assert x_dtype == 1 and ldx >= 2 * Cin
+        out = cv(xop(0), wslab(0)) + cv(xop(Cin), wslab(0)) + cv(xop(0), wslab(1))
+    elif flags & 32:      # HL_CONV_SPLIT2P: hi and lo packed inside the Cin channels, w = {[W_hi | W_hi], [W_lo | 0]}
+        out = cv(xop(0), wslab(0)) + cv(xop(0), wslab(1))
+    else:
+        out = cv(xop(0), wslab(0))
+    out = (out + bv[None, :, None, None]).permute(0, 2, 3, 1)
     Ho, Wo = out.shape[1], out.shape[2]
     out = out.reshape(B * Ho * Wo, Cout).numpy()
     if residual:
         out = out + pitched(residual, B * Ho * Wo, Cout, ldr)
+    if flags & 64:                                          # HL_CONV_OUT_F16_SPLIT: [hi | lo] of out * 2^-8
+        assert not stats and ldy >= 2 * Cout
+        _store_operand(y, 1, B * Ho * Wo, Cout, ldy, out, OP_SCALED | OP_SPLIT | (Cout << 8))
+        return
     if flags & 8:                                           # HL_CONV_OUT_F16
         assert not stats
         pitched(y, B * Ho * Wo, Cout, ldy, np.float16)[...] = out.astype(np.float16)

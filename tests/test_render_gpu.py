@@ -74,10 +74,10 @@ def test_two_different_triplanes_in_a_row():
         pd = planes[0].to(dev)
         rgb, acc, dep = r.render_rays(pd, bounds, *[t.to(dev) for t in ray], u=g["u"][:n].to(dev))
         ref = render_oracle.render_rays(sd, planes[0], bounds, *ray, g["u"][:n])
-        assert rel_l2(rgb, ref[0]) < 3e-4 and rel_l2(dep, ref[2]) < 3e-4, seed
+        assert rel_l2(rgb, ref[0]) < 1e-4 and rel_l2(dep, ref[2]) < 3e-4, seed
         outs.append(rgb.clone())
         del pd, rgb, acc, dep                                   # the next plane may land on the same address
-    assert rel_l2(outs[0], outs[1]) > 1e-2
+    assert rel_l2(outs[0], outs[1]) > 1e-3      # colours saturate near 1 on this MLP: 2.5e-3 between the planes, 1e-5 to each oracle
 
 
 def test_n_importance_zero_vs_reference_golden():

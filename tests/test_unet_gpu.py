@@ -79,8 +79,7 @@ def test_cuda_graph_replay_equals_eager():
     outs = [model(x, ts, xc, y=y) for _ in range(3)]          # eager, capture + replay, replay
     assert all(rel_l2(o, e1) < 1e-6 for o in outs), [rel_l2(o, e1) for o in outs]
     assert rel_l2(model(0.5 * x, ts + 7, xc, y=y), e2) < 1e-6
-    plan = next(iter(model._plans.values()))
-    assert plan.graph is not None
+    assert any(p.graph is not None for p in model._plans.values())      # plans are keyed on the execution switches too
 
 
 def test_p_sample_loop_api_with_injected_noise():

@@ -43,9 +43,9 @@ SIGNATURES = {
     "hl_attention": (c_int, [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_ddpm_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
     "hl_ddim_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p]),
-    "hl_randn": (c_int, [c_p, c_i64, c_p, c_u64, c_u64, c_p]),
-    "hl_ddpm_step_rng": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_i64, c_int, c_p, c_u64, c_u64, c_p]),
-    "hl_ddpm_posterior": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_i64, c_int, c_p, c_u64, c_u64, c_p]),
+    "hl_randn": (c_int, [c_p, c_i64, c_p, c_u64, c_u64, c_i64, c_p]),
+    "hl_ddpm_step_rng": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_i64, c_int, c_p, c_u64, c_u64, c_i64, c_p]),
+    "hl_ddpm_posterior": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_i64, c_int, c_p, c_u64, c_u64, c_i64, c_p]),
     "hl_loop_advance": (c_int, [c_p, c_p, c_p, c_f, c_int, c_p, c_p]),
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
@@ -56,6 +56,7 @@ SIGNATURES = {
                                    c_i64, c_int, c_int, c_p]),
     "hl_density_grid_tc5": (c_int, [c_p, c_int, c_p, c_p, c_int, c_int, c_p, c_p]),
     "hl_render5_set_profile": (c_int, [c_p]),
+    "hl_triplane_to_quads": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                   c_i64, c_int, c_p]),
 }

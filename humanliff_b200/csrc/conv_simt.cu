@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvArgs<T> a) {
             float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
             if (a.res) v += a.res[mm * a.ldr + n];
             if (a.y_f16 == 2) {                          // scaled hi | lo pair (HL_CONV_OUT_F16_SPLIT)
-                const float vs = v * 0.00390625f;
+                const float vs = v * HL_OP_SCALE;
                 const __half h = __float2half_rn(vs);
                 reinterpret_cast<__half *>(a.y)[mm * a.ldy + n] = h;
                 reinterpret_cast<__half *>(a.y)[mm * a.ldy + a.Cout + n] = __float2half_rn(vs - __half2float(h));

@@ -563,10 +563,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         if (p.has_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
                         const uint32_t hrow = sbuf + (uint32_t)row * 64u, hsw = ((uint32_t)row >> 1) & 3u;
                         if (p.y_f16 == 2) {
-                            // scaled hi | lo pair (a raw residual-stream operand of a high-precision conv): v * 2^-8 =
+                            // scaled hi | lo pair (a raw residual-stream operand of a high-precision conv): v * 2^-4 =
                             // hi + lo to ~22 bits; the hi tile is staged in the first 8 KB of the buffer, lo in the second
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= 0.00390625f;
+                            for (int j = 0; j < 32; ++j) v[j] *= HL_OP_SCALE;
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
                 a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
             }
             if (y_f16) {
-                const float sc = y_f16 == 2 ? 0.00390625f : 1.0f;           // 2: scaled hi | lo pair, lo at channel Cout + c
+                const float sc = y_f16 == 2 ? HL_OP_SCALE : 1.0f;           // 2: scaled hi | lo pair, lo at channel Cout + c
                 const float4 as = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
                 const __half2 h0 = __floats2half2_rn(as.x, as.y), h1 = __floats2half2_rn(as.z, as.w);
                 uint2 w;
@@ -1184,7 +1184,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     const int ldy_final = ldy, yf16_final = y_f16;
     if (S > 1) {
         p.ksplit = S;
-        p.kc_split = p.kchunks / S;
+        p.kc_split = p.vchunks / S;
         p.split_b = split_batch(pl, B);
         p.total_tiles = p.tiles_mn * S;
         const int sms = hl_num_sms();

@@ -33,8 +33,8 @@ int hl_num_sms() {
     return g_num_sms;
 }
 
-// Operand mode word (HL_OP_* in the header): bit 0 = TF32-round an fp32 operand, bit 1 = store value * 2^-8 (the
-// packed weights carry 2^8: a raw residual-stream operand keeps fp16 range up to 1.6e7), bit 2 = store an fp16
+// Operand mode word (HL_OP_* in the header): bit 0 = TF32-round an fp32 operand, bit 1 = store value * 2^-4 (the
+// packed weights carry 2^4: a raw residual-stream operand keeps fp16 range up to 1.0e6), bit 2 = store an fp16
 // hi | lo pair (lo = fp16(v - hi), ~22 significant bits) with lo at + (mode >> 8) elements.
 __device__ __forceinline__ uint32_t h2_bits(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t lo_bits(float a, float b, uint32_t hi) {
 // store 4 consecutive channels of an operand buffer: fp32 (optionally TF32-rounded) or fp16
 __device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, float4 v, int mode) {
     if (dtype == HL_DT_F16) {
-        if (mode & HL_OP_SCALED) { v.x *= 0.00390625f; v.y *= 0.00390625f; v.z *= 0.00390625f; v.w *= 0.00390625f; }
+        if (mode & HL_OP_SCALED) { v.x *= HL_OP_SCALE; v.y *= HL_OP_SCALE; v.z *= HL_OP_SCALE; v.w *= HL_OP_SCALE; }
         uint2 u;
         u.x = h2_bits(v.x, v.y);
         u.y = h2_bits(v.z, v.w);
@@ -71,8 +71,8 @@ __device__ __forceinline__ void store_quad(void *dst, int dtype, int64_t idx, fl
 __device__ __forceinline__ void store_oct(void *dst, int dtype, int64_t idx, float4 a, float4 b, int mode) {
     if (dtype == HL_DT_F16) {
         if (mode & HL_OP_SCALED) {
-            a.x *= 0.00390625f; a.y *= 0.00390625f; a.z *= 0.00390625f; a.w *= 0.00390625f;
-            b.x *= 0.00390625f; b.y *= 0.00390625f; b.z *= 0.00390625f; b.w *= 0.00390625f;
+            a.x *= HL_OP_SCALE; a.y *= HL_OP_SCALE; a.z *= HL_OP_SCALE; a.w *= HL_OP_SCALE;
+            b.x *= HL_OP_SCALE; b.y *= HL_OP_SCALE; b.z *= HL_OP_SCALE; b.w *= HL_OP_SCALE;
         }
         uint4 u;
         u.x = h2_bits(a.x, a.y);

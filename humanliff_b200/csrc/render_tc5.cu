@@ -62,7 +62,7 @@ constexpr size_t SMEM5 = 1024 + (size_t)W_BYTES + sizeof(float) * (FB_FLOATS + G
 constexpr uint32_t TM_ACC = 0, TM_AH = 128, TM_AX = 192, TM_AC = 208, TM_GROUP = 256, TM_COLS = 512;
 
 struct Render5Args {
-    const float4 *tex;
+    const uint4 *tex;                 // quad texels (hl_triplane_to_quads): [9][R + 1][R + 1] x 32 B
     int R;
     const uint4 *w16s;                // tcgen05 MLP image (HL_MLP_TC5_BYTES)
     const float *o, *d, *near, *far, *u, *zc_in;
@@ -81,6 +81,29 @@ struct Render5Args {
 
 // softplus in the log2 domain: a = x * log2(e) in, softplus(x) / ln 2 out (MUFU.EX2, FADD, MUFU.LG2, FMNMX, FADD)
 __device__ __forceinline__ float softplus2(float a) { return fmaxf(a, 0.f) + hl_lg2(1.0f + hl_ex2(-fabsf(a))); }
+// The same function with the lg2 on the FMA pipe: lg2(1 + t) = t * q(t) on t in (0, 1], q of degree 5 (Lawson / Remez
+// fit, max abs error 2.3e-6 -- two orders below the fp16 rounding of the activation).  The epilogue is bound by the
+// MUFU pipe (16 lanes / clk / SM) while the FMA pipe idles, so a fraction of the activations (HL_R5_POLY of every 4)
+// takes this route: 1 MUFU + 7 FMA-pipe instructions instead of 2 MUFU + 3.
+#ifndef HL_R5_POLY
+#define HL_R5_POLY 3
+#endif
+__device__ __forceinline__ float softplus2_poly(float a) {
+    const float t = hl_ex2(-fabsf(a));
+    float q = fmaf(-0.026457004986457876f, t, 0.12345017983674147f);
+    q = fmaf(q, t, -0.27953670731627006f);
+    q = fmaf(q, t, 0.4582700935445837f);
+    q = fmaf(q, t, -0.7182817634084746f);
+    q = fmaf(q, t, 1.4425531338453292f);
+    return fmaf(q, t, fmaxf(a, 0.f));
+}
+// element e (0..3) of a quad: which route
+template <int E>
+__device__ __forceinline__ float softplus2_mix(float a) {
+    constexpr bool poly = (HL_R5_POLY == 1 && E == 1) || (HL_R5_POLY == 2 && (E & 1)) || (HL_R5_POLY == 3 && E != 0) ||
+                          (HL_R5_POLY == 4);
+    return poly ? softplus2_poly(a) : softplus2(a);
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -106,14 +129,18 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// The 27 features of one world-space point (nine sub-planes x 3 channels), packed as 32 fp16 (27..31 = 0) into
-// xa[16].  Sub-planes are fetched in two batches (5 + 4) so that 16-20 independent 16-byte L2 loads are in flight
-// per thread without holding all 36 taps in registers.
+// The 27 features of one world-space point (nine sub-planes x 3 channels), packed as 32 fp16 into xa[16].
+// Texels come as "quads" (hl_triplane_to_quads): entry (y0, x0) of a sub-plane holds the 2 x 2 bilinear footprint
+// {(y0,x0), (y0,x0+1), (y0+1,x0), (y0+1,x0+1)} x 3 channels as fp16 in ONE 32-byte sector (out-of-range taps stored as
+// the zeros grid_sample pads with), so a sub-plane costs one 256-bit load / one L2 sector instead of four 16-byte
+// loads over 2-4 sectors.  Measured with the four-tap fp32 layout: the gather took the same 13 k cycles per ray with
+// 36 loads per thread or 18 (two threads per sample) -- sector throughput, not latency, bound it.
 template <int C0, int NC>
-__device__ __forceinline__ void gather_subplanes(const float4 *__restrict__ tex, int R, float cx, float cy, float cz,
+__device__ __forceinline__ void gather_subplanes(const uint4 *__restrict__ tex, int R, float cx, float cy, float cz,
                                                  float *f) {
     const float fR = (float)R, shift = 1.0f / fR;
-    float4 tap[NC][4];
+    const int R1 = R + 1;
+    uint32_t q[NC][8];
     float wgt[NC][4];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
@@ -130,42 +157,45 @@ __device__ __forceinline__ void gather_subplanes(const float4 *__restrict__ tex,
         const float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
         const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)R + 1.f);     // clamp before the cast: miss rays are far away
         const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)R + 1.f);
-        const float4 *tp = tex + (size_t)c * R * R;
-        const bool xin0 = x0 >= 0 && x0 < R, xin1 = x0 + 1 >= 0 && x0 + 1 < R;
-        const bool yin0 = y0 >= 0 && y0 < R, yin1 = y0 + 1 >= 0 && y0 + 1 < R;
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        tap[i][0] = (yin0 && xin0) ? __ldg(tp + (size_t)y0 * R + x0) : zero;
-        tap[i][1] = (yin0 && xin1) ? __ldg(tp + (size_t)y0 * R + x0 + 1) : zero;
-        tap[i][2] = (yin1 && xin0) ? __ldg(tp + (size_t)(y0 + 1) * R + x0) : zero;
-        tap[i][3] = (yin1 && xin1) ? __ldg(tp + (size_t)(y0 + 1) * R + x0 + 1) : zero;
-        wgt[i][0] = wx0 * wy0; wgt[i][1] = wx1 * wy0; wgt[i][2] = wx0 * wy1; wgt[i][3] = wx1 * wy1;
+        const bool in = x0 >= -1 && x0 < R && y0 >= -1 && y0 < R;         // at least one tap inside the plane
+        const uint4 *tp = tex + 2 * ((size_t)c * R1 * R1 + (size_t)(in ? y0 + 1 : 0) * R1 + (in ? x0 + 1 : 0));
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(q[i][0]), "=r"(q[i][1]), "=r"(q[i][2]), "=r"(q[i][3]), "=r"(q[i][4]), "=r"(q[i][5]),
+                       "=r"(q[i][6]), "=r"(q[i][7])
+                     : "l"(tp));
+        const float m = in ? 1.f : 0.f;
+        wgt[i][0] = wx0 * wy0 * m; wgt[i][1] = wx1 * wy0 * m; wgt[i][2] = wx0 * wy1 * m; wgt[i][3] = wx1 * wy1 * m;
     }
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        // halves: t00.{0,1,2} t01.{0,1,2} t10.{0,1,2} t11.{0,1,2}; accumulation order 00, 01, 10, 11 as render.cu
+        float h[12];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {      // same accumulation order as render.cu (taps 00, 01, 10, 11)
-            r0 = fmaf(tap[i][k].x, wgt[i][k], r0);
-            r1 = fmaf(tap[i][k].y, wgt[i][k], r1);
-            r2 = fmaf(tap[i][k].z, wgt[i][k], r2);
+        for (int k = 0; k < 6; ++k) {
+            const float2 p = __half22float2(*reinterpret_cast<const __half2 *>(&q[i][k]));
+            h[2 * k] = p.x;
+            h[2 * k + 1] = p.y;
         }
-        f[(C0 + i) * 3 + 0] = r0;
-        f[(C0 + i) * 3 + 1] = r1;
-        f[(C0 + i) * 3 + 2] = r2;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float r = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r = fmaf(h[3 * k + ch], wgt[i][k], r);
+            f[(C0 + i) * 3 + ch] = r;
+        }
     }
 }
 
 // ONE out-of-line copy (the coarse pass, both fine tiles and the density grid call it): fully unrolled it is ~1.5 k
 // instructions, and the r1 kernel showed that duplicated unrolled bodies thrash the instruction cache.
-__device__ __noinline__ void gather_to_tmem(const float4 *__restrict__ tex, int R, const float *bnd, float px,
+__device__ __noinline__ void gather_to_tmem(const uint4 *__restrict__ tex, int R, const float *bnd, float px,
                                             float py, float pz, uint32_t tm_ax) {
     uint32_t xa[16];
     const float cx = 2.f * (px - bnd[0]) / (bnd[3] - bnd[0]) - 1.f;
     const float cy = 2.f * (py - bnd[1]) / (bnd[4] - bnd[1]) - 1.f;
     const float cz = 2.f * (pz - bnd[2]) / (bnd[5] - bnd[2]) - 1.f;
     float f[28];
-    gather_subplanes<0, 5>(tex, R, cx, cy, cz, f);
-    gather_subplanes<5, 4>(tex, R, cx, cy, cz, f);
+    gather_subplanes<0, 9>(tex, R, cx, cy, cz, f);
     f[27] = 1.0f;              // the bias column of pts_linears.0 / pts_linears.2 multiplies this slot
 #pragma unroll
     for (int k = 0; k < 14; ++k) xa[k] = pack_h2(f[2 * k], f[2 * k + 1]);
@@ -249,7 +279,7 @@ __device__ __forceinline__ float epi_hidden(const Group &G) {
         for (int j = 0; j < 8; ++j) {
             float h0 = __uint_as_float(cur[4 * j]), h1 = __uint_as_float(cur[4 * j + 1]);
             float h2 = __uint_as_float(cur[4 * j + 2]), h3 = __uint_as_float(cur[4 * j + 3]);
-            if (ACT) { h0 = softplus2(h0); h1 = softplus2(h1); h2 = softplus2(h2); h3 = softplus2(h3); }
+            if (ACT) { h0 = softplus2_mix<0>(h0); h1 = softplus2_mix<1>(h1); h2 = softplus2_mix<2>(h2); h3 = softplus2_mix<3>(h3); }
             pk[2 * j] = pack_h2(h0, h1);
             pk[2 * j + 1] = pack_h2(h2, h3);
             if (ALPHA) {
@@ -275,7 +305,7 @@ __device__ __forceinline__ void epi_views(const Group &G, float (&rgb)[3]) {
         if (c) tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float h = softplus2(__uint_as_float(cur[j]));
+            const float h = (j & 1) ? softplus2_mix<1>(__uint_as_float(cur[j])) : softplus2_mix<0>(__uint_as_float(cur[j]));
             const float4 w = lds_f128(G.fb + 4u * (uint32_t)(FB_WR + (c * 32 + j) * 4));
             r0 = fmaf(h, w.x, r0); r1 = fmaf(h, w.y, r1); r2 = fmaf(h, w.z, r2);
         }
@@ -629,6 +659,32 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     }
 }
 
+// planes [3][9][R][R] fp32 (channel = sub * 3 + ch) -> quad texels [9][R + 1][R + 1] x 16 halves (see gather_subplanes):
+// entry (yq, xq) = the footprint whose top-left tap is (yq - 1, xq - 1).
+__global__ void k_triplane_to_quads(const float *__restrict__ planes, uint4 *__restrict__ out, int R) {
+    const int R1 = R + 1;
+    const size_t n = (size_t)9 * R1 * R1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % R1), yq = (int)((i / R1) % R1), c = (int)(i / ((size_t)R1 * R1));
+        const int plane = c / 3, sub = c % 3;
+        const float *src = planes + ((size_t)plane * 9 + sub * 3) * R * R;
+        __half h[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y = yq - 1 + (k >> 1), x = xq - 1 + (k & 1);
+            const bool in = y >= 0 && y < R && x >= 0 && x < R;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                h[3 * k + ch] = __float2half_rn(in ? src[(size_t)ch * R * R + (size_t)y * R + x] : 0.f);
+        }
+#pragma unroll
+        for (int k = 12; k < 16; ++k) h[k] = __float2half_rn(0.f);
+        const uint4 *hv = reinterpret_cast<const uint4 *>(h);
+        out[2 * i] = hv[0];
+        out[2 * i + 1] = hv[1];
+    }
+}
+
 unsigned long long *g_prof5 = nullptr;
 
 int launch5(Render5Args &a, long long units, cudaStream_t stream) {
@@ -649,21 +705,32 @@ int launch5(Render5Args &a, long long units, cudaStream_t stream) {
 
 }  // namespace
 
+extern "C" int hl_triplane_to_quads(const float *planes, void *quads, int R, void *stream) {
+    HL_CHECK_ARG(planes && quads && R > 0 && ((uintptr_t)quads & 31) == 0);
+    const size_t n = (size_t)9 * (R + 1) * (R + 1);
+    int grid = (int)((n + 255) / 256);
+    const int cap = hl_num_sms() * 8;
+    if (grid > cap) grid = cap;
+    k_triplane_to_quads<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, reinterpret_cast<uint4 *>(quads), R);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
 extern "C" int hl_render5_set_profile(void *dev_counters) {
     g_prof5 = (unsigned long long *)dev_counters;
     return HL_OK;
 }
 
-extern "C" int hl_render_rays_tc5(const float *texels, int R, const void *mlp_tc5,
+extern "C" int hl_render_rays_tc5(const void *texels, int R, const void *mlp_tc5,
                                   const float *rays_o, const float *rays_d, const float *near, const float *far,
                                   const float *z_coarse, const float *u, uint64_t seed, const float *bounds,
                                   int bounds_on_device, float *rgb, float *acc, float *depth, int64_t n_rays,
                                   int n_importance, int clamp_depth, void *stream) {
     HL_CHECK_ARG(texels && mlp_tc5 && rays_o && rays_d && near && far && bounds && rgb && acc && depth);
-    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
+    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 31) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
     HL_CHECK_ARG(n_importance == 0 || n_importance == NS);
     Render5Args a = {};
-    a.tex = reinterpret_cast<const float4 *>(texels);
+    a.tex = reinterpret_cast<const uint4 *>(texels);
     a.R = R;
     a.w16s = reinterpret_cast<const uint4 *>(mlp_tc5);
     a.o = rays_o; a.d = rays_d; a.near = near; a.far = far; a.u = u; a.zc_in = z_coarse;
@@ -678,12 +745,12 @@ extern "C" int hl_render_rays_tc5(const float *texels, int R, const void *mlp_tc
     return launch5(a, n_rays, (cudaStream_t)stream);
 }
 
-extern "C" int hl_density_grid_tc5(const float *texels, int R, const void *mlp_tc5,
+extern "C" int hl_density_grid_tc5(const void *texels, int R, const void *mlp_tc5,
                                    const float *bounds, int bounds_on_device, int resolution, float *out, void *stream) {
     HL_CHECK_ARG(texels && mlp_tc5 && bounds && out && R > 0 && resolution >= 2);
-    HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
+    HL_CHECK_ARG(((uintptr_t)texels & 31) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
     Render5Args a = {};
-    a.tex = reinterpret_cast<const float4 *>(texels);
+    a.tex = reinterpret_cast<const uint4 *>(texels);
     a.R = R;
     a.w16s = reinterpret_cast<const uint4 *>(mlp_tc5);
     if (bounds_on_device) a.bounds_dev = bounds;

@@ -47,12 +47,12 @@ __device__ __forceinline__ float4 randn4(uint64_t seed, uint64_t draw, uint64_t 
 }
 
 __global__ void k_randn(float *__restrict__ out, int64_t n4, const uint64_t *__restrict__ rng, uint64_t seed,
-                        uint64_t draw) {
+                        uint64_t draw, int64_t off4) {
     hl_pdl_enter();
     if (rng) { seed = rng[0]; draw = rng[1]; }
     float4 *o4 = reinterpret_cast<float4 *>(out);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
-        o4[i] = randn4(seed, draw, (uint64_t)i);
+        o4[i] = randn4(seed, draw, (uint64_t)(off4 + i));
 }
 
 // MODE 0: x0 from eps (k_ddpm_step's arithmetic, noise drawn here)   MODE 1: x0 supplied (posterior only)
@@ -61,7 +61,7 @@ __global__ void k_ddpm_step_rng(const float *__restrict__ x, const float *__rest
                                 const float *__restrict__ noise, const float *__restrict__ coef,
                                 const float *__restrict__ sigma, const int64_t *__restrict__ t, int T,
                                 float *__restrict__ sample, float *__restrict__ x0out, int64_t n4, int clip,
-                                const uint64_t *__restrict__ rng, uint64_t seed, uint64_t draw) {
+                                const uint64_t *__restrict__ rng, uint64_t seed, uint64_t draw, int64_t sample_offset) {
     hl_pdl_enter();
     const int b = blockIdx.y;
     const int64_t ti = t[b];
@@ -83,7 +83,7 @@ __global__ void k_ddpm_step_rng(const float *__restrict__ x, const float *__rest
     };
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 xv = x4[i], ev = e4[i];
-        const float4 zv = z4 ? z4[i] : randn4(seed, draw, (uint64_t)((int64_t)b * n4 + i));
+        const float4 zv = z4 ? z4[i] : randn4(seed, draw, (uint64_t)((sample_offset + b) * n4 + i));
         float4 x0, s;
         one(xv.x, ev.x, zv.x, x0.x, s.x);
         one(xv.y, ev.y, zv.y, x0.y, s.y);
@@ -115,10 +115,11 @@ int grid_for(int64_t n4, int B) {
 
 }  // namespace
 
-extern "C" int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, uint64_t draw, void *stream) {
-    HL_CHECK_ARG(out && n > 0 && n % 4 == 0 && ((uintptr_t)out & 15) == 0);
+extern "C" int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, uint64_t draw,
+                        int64_t element_offset, void *stream) {
+    HL_CHECK_ARG(out && n > 0 && n % 4 == 0 && element_offset % 4 == 0 && ((uintptr_t)out & 15) == 0);
     HL_CHECK_CUDA(hl_launch(k_randn, dim3(grid_for(n / 4, 1)), dim3(256), 0, (cudaStream_t)stream, out, n / 4, rng_state,
-                            seed, draw));
+                            seed, draw, element_offset / 4));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -126,10 +127,10 @@ extern "C" int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64
 extern "C" int hl_ddpm_step_rng(const float *x, const float *eps, const float *noise, const float *coef,
                                 const float *sigma, const int64_t *t, int T, float *sample, float *pred_xstart, int B,
                                 int64_t n, int clip, const uint64_t *rng_state, uint64_t seed, uint64_t draw,
-                                void *stream) {
+                                int64_t sample_offset, void *stream) {
     HL_CHECK_ARG(x && eps && coef && sigma && t && sample && B > 0 && T > 0 && n > 0 && n % 4 == 0);
     HL_CHECK_CUDA(hl_launch(k_ddpm_step_rng<0>, dim3(grid_for(n / 4, B), B), dim3(256), 0, (cudaStream_t)stream, x, eps, noise,
-                            coef, sigma, t, T, sample, pred_xstart, n / 4, clip, rng_state, seed, draw));
+                            coef, sigma, t, T, sample, pred_xstart, n / 4, clip, rng_state, seed, draw, sample_offset));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -137,10 +138,10 @@ extern "C" int hl_ddpm_step_rng(const float *x, const float *eps, const float *n
 extern "C" int hl_ddpm_posterior(const float *x, const float *x0, const float *noise, const float *coef,
                                  const float *sigma, const int64_t *t, int T, float *sample, float *x0_clipped, int B,
                                  int64_t n, int clip, const uint64_t *rng_state, uint64_t seed, uint64_t draw,
-                                 void *stream) {
+                                 int64_t sample_offset, void *stream) {
     HL_CHECK_ARG(x && x0 && coef && sigma && t && sample && B > 0 && T > 0 && n > 0 && n % 4 == 0);
     HL_CHECK_CUDA(hl_launch(k_ddpm_step_rng<1>, dim3(grid_for(n / 4, B), B), dim3(256), 0, (cudaStream_t)stream, x, x0, noise,
-                            coef, sigma, t, T, sample, x0_clipped, n / 4, clip, rng_state, seed, draw));
+                            coef, sigma, t, T, sample, x0_clipped, n / 4, clip, rng_state, seed, draw, sample_offset));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -96,6 +96,9 @@ class GaussianDiffusion:
         self.posterior_mean_coef2 = ((1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas)
                                      / (1.0 - self.alphas_cumprod))
         self._dev_tables = {}
+        # Global index of this process' first sample (data-parallel sampling: rank * samples per rank).  The in-kernel
+        # Gaussian of a sample is keyed on its GLOBAL index, so the gathered batch is the same whatever the sharding.
+        self.sample_offset = 0
 
     # ------------------------------------------------------------------ tables
     def _variance_tables(self):
@@ -178,7 +181,8 @@ class GaussianDiffusion:
         call("hl_ddpm_posterior" if x0_given is not None else "hl_ddpm_step_rng", x.data_ptr(),
              (x0_given if x0_given is not None else eps).data_ptr(), noise.data_ptr() if noise is not None else None,
              tb["coef"].data_ptr(), tb["sigma"].data_ptr(), t64.data_ptr(), self.num_timesteps, sample.data_ptr(),
-             x0.data_ptr() if x0 is not None else None, B, n, 1 if clip_denoised else 0, None, seed, draw, stream)
+             x0.data_ptr() if x0 is not None else None, B, n, 1 if clip_denoised else 0, None, seed, draw,
+             int(self.sample_offset), stream)
         return sample, x0
 
     def _denoise(self, model, x, t, x_cond, clip_denoised, denoised_fn, model_kwargs, noise):
@@ -239,7 +243,8 @@ class GaussianDiffusion:
         if img.numel() % 4:
             return torch.randn(*shape, device=device)
         seed, draw = self._rng_draw(img.device)
-        call("hl_randn", img.data_ptr(), img.numel(), None, seed, draw, torch.cuda.current_stream(img.device).cuda_stream)
+        call("hl_randn", img.data_ptr(), img.numel(), None, seed, draw, int(self.sample_offset) * img[0].numel(),
+             torch.cuda.current_stream(img.device).cuda_stream)
         return img
 
     def _sample_loop(self, model, shape, x_cond, noise, clip_denoised, denoised_fn, model_kwargs, device, progress,
@@ -482,7 +487,7 @@ class _GraphLoop:
             plan = inner.plan_for(img.device, B, H, W)
         if type(plan) is not _StepPlan:
             return None
-        key = (id(diffusion), bool(clip), bool(injected), bool(want_x0))
+        key = (id(diffusion), bool(clip), bool(injected), bool(want_x0), int(diffusion.sample_offset))
         loops = plan.__dict__.setdefault("_loops", {})
         loop = loops.get(key)
         if loop is None:
@@ -514,7 +519,7 @@ class _GraphLoop:
         call("hl_ddpm_step_rng", p.x_in.data_ptr(), p.out.data_ptr(), self.z_in.data_ptr() if self.injected else None,
              tb["coef"].data_ptr(), tb["sigma"].data_ptr(), self.t_idx.data_ptr(), d.num_timesteps, p.x_in.data_ptr(),
              self.x0.data_ptr() if self.x0 is not None else None, p.B, p.x_in[0].numel(), 1 if self.clip else 0,
-             None if self.injected else self.rng.data_ptr(), 0, 0, stream)
+             None if self.injected else self.rng.data_ptr(), 0, 0, int(d.sample_offset), stream)
         call("hl_loop_advance", self.t_idx.data_ptr(), p.t_in.data_ptr(), self.map.data_ptr() if self.map is not None else None,
              float(self.scale), p.B, self.rng.data_ptr(), stream)
 

@@ -190,6 +190,13 @@ class Renderer(nn.Module):
         call("hl_triplane_to_texels", planes.data_ptr(), tex.data_ptr(), R, stream)
         return tex
 
+    def _quads(self, planes):
+        """[3, 9, R, R] device tensor -> the tcgen05 kernel's quad texels (2 x 2 footprints, fp16, 32 B each)."""
+        R = planes.shape[-1]
+        q = torch.empty(9 * (R + 1) * (R + 1) * 16, device=planes.device, dtype=torch.float16)
+        call("hl_triplane_to_quads", planes.data_ptr(), q.data_ptr(), R, torch.cuda.current_stream(planes.device).cuda_stream)
+        return q
+
     def _next_seed(self, b=0):
         """Seed of the in-kernel uniforms of sample_pdf for this call: follows torch's seed (torch.manual_seed
         makes a run reproducible) and advances with every render call, as successive torch.rand draws would."""
@@ -210,7 +217,7 @@ class Renderer(nn.Module):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).contiguous()
             assert planes.shape[0] == 3 and planes.shape[1] == 9 and planes.shape[2] == planes.shape[3]
-            tex = self._texels(planes)
+            tex = self._quads(planes) if self.precision == "fp16" else self._texels(planes)
             n = rays_o.shape[0]
             f = lambda t: t.detach().to(dev, torch.float32).contiguous()
             rays_o, rays_d, near, far = f(rays_o), f(rays_d), f(near).view(-1), f(far).view(-1)
@@ -266,7 +273,7 @@ class Renderer(nn.Module):
         with torch.cuda.device(dev):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).reshape(3, 9, *tri_planes.shape[-2:]).contiguous()
-            tex = self._texels(planes)
+            tex = self._quads(planes) if self.precision == "fp16" else self._texels(planes)
             import ctypes
             wb = torch.as_tensor(tp_input["world_bounds"], dtype=torch.float32).reshape(-1, 6)[0]
             out = torch.empty(resolution, resolution, resolution, device=dev, dtype=torch.float32)

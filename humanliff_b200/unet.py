@@ -52,7 +52,7 @@ def _set_param(root, dotted, shape):
     node.register_parameter(parts[-1], nn.Parameter(torch.zeros(*shape), requires_grad=False))
 
 
-HP_SCALE = 256.0     # raw residual-stream operands are stored as value * 2^-8; their weights carry 2^8 (HL_OP_SCALED)
+HP_SCALE = 16.0      # raw residual-stream operands are stored as value * 2^-4; their weights carry 2^4 (HL_OP_SCALED)
 
 
 def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=None):
@@ -60,7 +60,7 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
     fp32 or exact fp32) + padded fp32 bias.  One-time host-side re-layout at load time.
 
     ``mode`` (fp16 only; the high-precision operand passes of DESIGN.md 3, HL_CONV_SPLIT3 / SPLIT2P in the header):
-    ``"scaled"`` weights * 2^8; ``"split"`` / ``"split_unscaled"`` two slabs ``{W_hi, W_lo}`` of the (scaled) weights,
+    ``"scaled"`` weights * 2^4; ``"split"`` / ``"split_unscaled"`` two slabs ``{W_hi, W_lo}`` of the (scaled) weights,
     ``W_lo = fp16(W - W_hi)``; ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
     an operand row ``[hi(Cin) 0.. | lo(Cin) 0..]`` with the lo half at channel Cin_pad / 2."""
     lib = _lib.load()
@@ -104,7 +104,7 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
 def _hp_mode(name, cin, cin_pad):
     """Which convs of the fp16 plan run the high-precision operand passes: the ones that read the RAW
     residual stream -- 1x1 skip, ControlNet projection, Downsample, stem -- and the output conv carry hi + lo fp16
-    pairs (error budget: tools/error_budget.py); the Upsample conv reads a 2^-8-scaled operand (range only)."""
+    pairs (error budget: tools/error_budget.py); the Upsample conv reads a 2^-4-scaled operand (range only)."""
     if name.endswith("skip_connection") or name.startswith("input_blocks_proj_cond.") or name.endswith(".op"):
         return "split"
     if name == "out.2":

@@ -45,8 +45,10 @@ extern "C" {
 /* Operand mode word of the kernels that WRITE conv operands (the `round_tf32` argument of hl_nchw_to_nhwc,
  * hl_cast_operand, hl_upsample2x, hl_gn_apply): */
 #define HL_OP_TF32 1      /* fp32 operand: round to TF32 (cvt.rna)                                            */
-#define HL_OP_SCALED 2    /* fp16 operand: store value * 2^-8 (the conv's packed weights carry 2^8): a raw
-                             residual-stream operand keeps fp16 range up to 1.6e7 instead of 65504           */
+#define HL_OP_SCALE 0.0625f /* = 2^-4: |x| up to 1.0e6 stays finite in fp16, and the lo half of an O(1) value is still a
+                              normal fp16 number (2^-8 would push it into the subnormals: 15 instead of 22 bits)        */
+#define HL_OP_SCALED 2    /* fp16 operand: store value * 2^-4 (the conv's packed weights carry 2^4): a raw
+                             residual-stream operand keeps fp16 range up to 1.0e6 instead of 65504           */
 #define HL_OP_SPLIT 4     /* fp16 operand: store an fp16 hi | lo pair (lo = fp16(v - hi), ~22 significant bits),
                              lo at + (mode >> 8) elements -- the operand of HL_CONV_SPLIT3 / SPLIT2P convs   */
 #define HL_OP_RAW_SHIFT 4 /* hl_gn_apply: bits 4-6 = the HL_OP_* flags of the raw copy (split: lo at channel C) */
@@ -62,7 +64,7 @@ extern "C" {
                                   [2*taps][Cout_pad][Cin]:  y = x_hi.W_hi + x_lo.W_hi + x_hi.W_lo          */
 #define HL_CONV_SPLIT2P 32     /* hi and lo packed INSIDE the Cin channels (stem: [hi(27) 0(5) | lo(27) 0(5)]),
                                   w = {[W_hi | W_hi], [W_lo | 0]}:  two passes                              */
-#define HL_CONV_OUT_F16_SPLIT 64  /* y = [hi(Cout) | lo(Cout)] fp16 of (result * 2^-8) (ldy >= 2 Cout,
+#define HL_CONV_OUT_F16_SPLIT 64  /* y = [hi(Cout) | lo(Cout)] fp16 of (result * 2^-4) (ldy >= 2 Cout,
                                   Cout % 32 == 0): the operand of a following HL_CONV_SPLIT3 conv           */
 
 int hl_version(void);
@@ -221,7 +223,8 @@ int hl_ddim_step(const float *x, const float *eps, const float *noise /*nullable
  * rng_state (nullable): device uint64[2] = {seed, draw} read by the kernel instead of the by-value pair, so a
  * captured CUDA graph draws fresh noise on every replay (hl_loop_advance increments the draw counter).
  * Replaces th.randn(*shape) (gaussian_diffusion.py:460).                                                        */
-int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, uint64_t draw, void *stream);
+int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, uint64_t draw,
+             int64_t element_offset /* index of out[0] in the global tensor: sharding-invariant noise */, void *stream);
 
 /* hl_ddpm_step with the per-step Gaussian drawn inside the kernel when noise == NULL (replaces the
  * th.randn_like(x) launch of gaussian_diffusion.py:383): 16 B / element of HBM traffic.  T = table length; a
@@ -229,14 +232,15 @@ int hl_randn(float *out, int64_t n, const uint64_t *rng_state, uint64_t seed, ui
 int hl_ddpm_step_rng(const float *x, const float *eps, const float *noise /*nullable*/, const float *coef,
                      const float *sigma, const int64_t *t, int T, float *sample, float *pred_xstart /*nullable*/,
                      int B, int64_t n, int clip, const uint64_t *rng_state /*nullable*/, uint64_t seed,
-                     uint64_t draw, void *stream);
+                     uint64_t draw, int64_t sample_offset /* global index of sample 0: the noise of a sample does not
+                     depend on how the batch is sharded across ranks */, void *stream);
 
 /* Posterior from a caller-supplied x0 (the denoised_fn route, gaussian_diffusion.py:294-295,312-314):
  * x0c = clip(x0); sample = c2 x0c + c3 x + sigma_t * noise.                                                      */
 int hl_ddpm_posterior(const float *x, const float *x0, const float *noise /*nullable*/, const float *coef,
                       const float *sigma, const int64_t *t, int T, float *sample, float *x0_clipped /*nullable*/,
                       int B, int64_t n, int clip, const uint64_t *rng_state /*nullable*/, uint64_t seed,
-                      uint64_t draw, void *stream);
+                      uint64_t draw, int64_t sample_offset, void *stream);
 
 /* End of a loop iteration, on the device: t[b] -= 1; t_model[b] = scale * (timestep_map ? map[t[b]] : t[b])
  * (_WrappedModel.__call__, respace.py:117-122; scale = 1000 / T_original iff rescale_timesteps, else 1);
@@ -336,13 +340,17 @@ int hl_density_grid_tc(const float *texels, int R, const float *mlp_packed, cons
  * bounds: 6 floats {min xyz, max xyz}, host memory, or device memory when bounds_on_device != 0 (no host sync on
  * tp_input['world_bounds']).  n_importance: 128, or 0 = no coarse pass: the n_samples = 128 coarse depths are
  * composited directly (recon_NeRF/lib/renderer.py:258 `if n_importance > 0`).                                  */
+/* texels of the tcgen05 renderer: "quad texels" -- [9 sub-planes][R + 1][R + 1] entries of 32 bytes; entry (yq, xq)
+ * holds the 2 x 2 bilinear footprint whose top-left tap is (yq - 1, xq - 1): 4 taps x 3 channels as fp16 (+ 4 pad),
+ * out-of-range taps = 0 (grid_sample's zero padding), so one sub-plane of one sample point is ONE 32-byte load.   */
+int hl_triplane_to_quads(const float *planes /*[3][9][R][R]*/, void *quads, int R, void *stream);
 #define HL_MLP_TC5_BYTES (16384 + 32768 + 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 392 * 4)
-int hl_render_rays_tc5(const float *texels, int R, const void *mlp_tc5,
+int hl_render_rays_tc5(const void *quads, int R, const void *mlp_tc5,
                        const float *rays_o, const float *rays_d, const float *near, const float *far,
                        const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
                        const float *bounds, int bounds_on_device, float *rgb, float *acc, float *depth,
                        int64_t n_rays, int n_importance, int clamp_depth, void *stream);
-int hl_density_grid_tc5(const float *texels, int R, const void *mlp_tc5,
+int hl_density_grid_tc5(const void *quads, int R, const void *mlp_tc5,
                         const float *bounds, int bounds_on_device, int resolution, float *out, void *stream);
 /* per-phase cycle counters of (CTA 0, group 0) of following tc5 launches, as hl_render_set_profile */
 int hl_render5_set_profile(void *dev_counters);

@@ -55,8 +55,8 @@ class _Numerics:
         if self.mode == "tf32_trunc_raw":
             return trunc_tf32(x) if raw else round_tf32(x)
         if self.mode == "fp16_scaled":
-            # raw-stream operand carried as fp16(x * 2^-8) (weights as fp16(w * 2^8)): range 1.6e7 instead of 65504
-            return (x * 2.0 ** -8).to(torch.float16).to(torch.float32) * 2.0 ** 8
+            # raw-stream operand carried as fp16(x * 2^-4) (weights as fp16(w * 2^4)): range 1.0e6 instead of 65504
+            return (x * 2.0 ** -4).to(torch.float16).to(torch.float32) * 2.0 ** 4
         if self.mode == "fp16x2":
             # fp16 hi + lo pair for BOTH operands of the layer (three MMAs: hi.hi + hi.lo + lo.hi): ~22 bits
             hi = x.to(torch.float16).to(torch.float32)
@@ -75,6 +75,20 @@ class _Numerics:
         if self.mode == "bf16":
             return x.to(torch.bfloat16).to(torch.float32)
         raise ValueError(self.mode)
+
+
+def product_fp16_plan(prefix):
+    """Per-layer policy emulating the product's ``precision="fp16"`` plan: every contraction rounds
+    its operands to fp16 except the convs that read the raw residual stream (1x1 skip, ControlNet projection,
+    Downsample), the stems and the output conv, which carry hi + lo fp16 pairs in three tensor-core passes; the
+    Upsample conv reads a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
+    import re
+    if (prefix.endswith("skip_connection") or prefix.startswith("input_blocks_proj_cond.") or prefix.endswith(".op")
+            or prefix == "out.2" or re.fullmatch(r"input_blocks(_cond)?\.0\.0", prefix)):
+        return "fp16_split3"
+    if prefix.endswith(".conv"):
+        return "fp16_scaled"
+    return "fp16"
 
 
 def timestep_embedding(t, dim, max_period=10000):
@@ -98,10 +112,10 @@ def _conv(x, sd, prefix, nm, stride=1, raw=False):
     pad = w.shape[-1] // 2
     nm = nm.at(prefix)
     if nm.mode == "fp16_split3":
-        # the product's high-precision conv: activations * 2^-8 and weights * 2^8 each carried as an fp16 hi + lo
+        # the product's high-precision conv: activations * 2^-4 and weights * 2^4 each carried as an fp16 hi + lo
         # pair, three tensor-core passes hi.hi + lo.hi + hi.lo (the lo.lo term, 2^-22 relative, is dropped)
         f16 = lambda t: t.to(torch.float16).to(torch.float32)
-        xs, wsc = x * 2.0 ** -8, w * 2.0 ** 8
+        xs, wsc = x * 2.0 ** -4, w * 2.0 ** 4
         xh, wh = f16(xs), f16(wsc)
         xl, wl = f16(xs - xh), f16(wsc - wh)
         y = F.conv2d(xh, wh, None, stride=stride, padding=pad) + F.conv2d(xl, wh, None, stride=stride, padding=pad) \

@@ -40,9 +40,9 @@ OP_TF32, OP_SCALED, OP_SPLIT = 1, 2, 4          # HL_OP_* of include/humanliff_b
 
 
 def _store_operand(dst_ptr, dtype_code, rows, cols, ld, values, mode):
-    """`mode` = the HL_OP_* word: TF32 rounding (fp32), 2^-8 scaling and hi | lo split with lo at + (mode >> 8) (fp16)."""
+    """`mode` = the HL_OP_* word: TF32 rounding (fp32), 2^-4 scaling and hi | lo split with lo at + (mode >> 8) (fp16)."""
     if dtype_code == 1:
-        v = values.astype(np.float32) * (np.float32(2.0 ** -8) if mode & OP_SCALED else np.float32(1.0))
+        v = values.astype(np.float32) * (np.float32(2.0 ** -4) if mode & OP_SCALED else np.float32(1.0))
         hi = v.astype(np.float16)
         pitched(dst_ptr, rows, cols, ld, np.float16)[...] = hi
         if mode & OP_SPLIT:
@@ -175,7 +175,7 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
     out = out.reshape(B * Ho * Wo, Cout).numpy()
     if residual:
         out = out + pitched(residual, B * Ho * Wo, Cout, ldr)
-    if flags & 64:                                          # HL_CONV_OUT_F16_SPLIT: [hi | lo] of out * 2^-8
+    if flags & 64:                                          # HL_CONV_OUT_F16_SPLIT: [hi | lo] of out * 2^-4
         assert not stats and ldy >= 2 * Cout
         _store_operand(y, 1, B * Ho * Wo, Cout, ldy, out, OP_SCALED | OP_SPLIT | (Cout << 8))
         return

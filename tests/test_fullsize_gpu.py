@@ -120,8 +120,35 @@ def test_unet_full_resolution_vs_reference_golden(prod_model):
     eps = model(xb.to(dev), t.to(dev), xcb.to(dev), y=y.to(dev))
     for slot in (0, 3):
         e2, em = rel_l2(eps[slot], g["eps"][0]), rel_max(eps[slot], g["eps"][0])
-        assert e2 < 1e-3 and em < 2e-3, f"slot {slot}: eps rel-L2 {e2:.3e} max {em:.3e}"
+        # gate = north_star's 1e-3 with head-room: the hi + lo operand passes put the fp16 plan at ~4e-4
+        assert e2 < 6e-4 and em < 1e-3, f"slot {slot}: eps rel-L2 {e2:.3e} max {em:.3e}"
     print(f"full-resolution parity: rel-L2 {e2:.3e} max-rel {em:.3e}")
+
+
+def test_unet_full_resolution_timestep_sweep_vs_reference_golden(prod_model):
+    """SURVEY 8(d) config 1's timestep sweep {0, 1, 500, 999} at config 2's size: the production model on the
+    benchmarked 1000-step ("") schedule, 27 x 256 x 256, all four timesteps in ONE B = 4 batch (each sample sits next to
+    different neighbours), against epsilon of the UNMODIFIED reference stored on the sub-lattice [:, :, 1::4, 2::4]
+    (oracle/make_goldens.py prod256sweep)."""
+    from common import load_golden, rel_max
+    model = prod_model[0]
+    g = load_golden("unet_prod_256_sweep.npz")
+    ts = [int(v) for v in g["ts"].tolist()]
+    assert ts == [0, 1, 500, 999]
+    x, xc, _ = synth.synth_denoise_inputs(1, 27, 256, 256, seed=int(g["seed_in"]))
+    dev = torch.device(DEV)
+    xb, xcb = x.expand(4, -1, -1, -1).contiguous(), xc.expand(4, -1, -1, -1).contiguous()
+    y = g["y"].expand(4).contiguous()
+    eps = model(xb.to(dev), torch.tensor(ts).to(dev), xcb.to(dev), y=y.to(dev))
+    worst = 0.0
+    for slot, t in enumerate(ts):
+        sub = eps[slot:slot + 1, :, 1::4, 2::4]
+        e2, em = rel_l2(sub, g[f"eps_sub_{t}"]), rel_max(sub, g[f"eps_sub_{t}"])
+        worst = max(worst, e2)
+        assert e2 < 6e-4 and em < 1e-3, f"t={t}: eps rel-L2 {e2:.3e} max {em:.3e}"
+        # the stored sub-lattice is representative: its norm scales to the full tensor's
+        assert abs(float(sub.double().norm()) * 4.0 / float(g[f"eps_norm_{t}"]) - 1.0) < 2e-2
+    print(f"full-resolution sweep: worst rel-L2 {worst:.3e}")
 
 
 def test_unet_step_full_size_batch_properties(prod_model):

@@ -439,3 +439,136 @@ def test_ddim_step_bit_exact(dev):
             rs, r0 = o.ddim_posterior(x, eps, t, z, eta=eta)
             assert torch.equal(x0.cpu(), r0), (resp, eta)
             assert torch.equal(sample.cpu(), rs), (resp, eta)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# High-precision operand passes of the fp16 plan: raw residual-stream operands as scaled fp16 hi | lo
+# pairs, three tensor-core passes.  Reference = float64 exact products of the fp32 inputs; the bar is the error of a
+# ~22-bit operand (1e-5), two orders below a plain fp16 operand (4e-4), and NO overflow at |x| = 1e5.
+# ---------------------------------------------------------------------------------------------------------------
+def _split_conv_case(dev, B, H, W, Cin, Cout, k, stride, scale, residual=False, out_split=False, force_simt=False, seed=0):
+    from humanliff_b200.unet import pack_conv
+    from humanliff_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, H, W, Cin, generator=g) * scale                      # NHWC raw stream, |x| up to ~5 * scale
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=stride, padding=k // 2)
+    res = None
+    if residual:
+        res = torch.randn(B, ref.shape[2], ref.shape[3], Cout, generator=g) * scale
+        ref = ref + res.permute(0, 3, 1, 2).double()
+    xd = x.to(dev)
+    op = torch.full((B, H, W, 2 * Cin), float("nan"), device=dev, dtype=torch.float16)
+    mode = _lib.OP_SPLIT | _lib.OP_SCALED | (Cin << 8)
+    _call("hl_cast_operand", xd.data_ptr(), Cin, op.data_ptr(), 1, 2 * Cin, Cin, B * H * W, mode, _stream())
+    # the operand pair reconstructs x * 2^-4 to ~2^-22 relative
+    rec = (op[..., :Cin].double() + op[..., Cin:].double()).cpu() * 16.0
+    assert rel_l2(rec, x) < 2e-6 and torch.isfinite(op).all()
+    wpk, bpk = pack_conv(w, b, Cin, "fp16", dev, mode="split")
+    assert wpk.shape[0] == 2 * k * k
+    Ho, Wo = ref.shape[2:]
+    flags = _lib.CONV_SPLIT3 | (_lib.CONV_FORCE_SIMT if force_simt else 0)
+    if out_split:
+        y = torch.full((B, Ho, Wo, 2 * Cout), float("nan"), device=dev, dtype=torch.float16)
+        flags |= _lib.CONV_OUT_F16_SPLIT
+        ldy = 2 * Cout
+    else:
+        y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev)
+        ldy = Cout
+    rd = res.to(dev) if residual else None
+    _call("hl_conv2d", op.data_ptr(), 1, 2 * Cin, wpk.data_ptr(), bpk.data_ptr(), rd.data_ptr() if residual else None, Cout,
+          y.data_ptr(), ldy, None, 0, B, H, W, Cin, Cout, k, stride, flags, _stream())
+    torch.cuda.synchronize()
+    if out_split:
+        out = (y[..., :Cout].double() + y[..., Cout:].double()) * 16.0
+    else:
+        out = y.double()
+    return out.permute(0, 3, 1, 2).cpu(), ref, y
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 192, 384, 1, 1),      # 1x1 skip / ControlNet projection
+                                   (2, 64, 64, 192, 192, 3, 2),      # Downsample
+                                   (4, 8, 8, 768, 768, 3, 2),        # Downsample at 8^2 -> 4^2: split-K territory
+                                   (1, 128, 128, 192, 192, 1, 1)])
+@pytest.mark.parametrize("scale", [1.0, 2e4])
+@pytest.mark.parametrize("residual", [False, True])
+def test_conv_split3_high_precision_and_range(dev, shape, scale, residual):
+    from humanliff_b200 import _lib
+    B, H, W, Cin, Cout, k, s = shape
+    assert _lib.load().hl_conv2d_uses_tensor_cores(1, B, H, W, Cin, Cout, k, s, 2 * Cin, Cout, _lib.CONV_SPLIT3)
+    out, ref, _ = _split_conv_case(dev, B, H, W, Cin, Cout, k, s, scale, residual=residual)
+    assert torch.isfinite(out).all()                     # |x| reaches 1e5 at scale 2e4: a plain fp16 operand is inf there
+    e = rel_l2(out, ref)
+    # K = 3 x 9 x 768 = 20,736 fp32 accumulations (and a split-K second pass) put the 768-channel Downsample at 2e-5
+    assert e < (4e-5 if Cin >= 768 else 1e-5), f"rel-L2 {e:.2e} (a plain fp16 operand gives 4e-4)"
+
+
+def test_conv_split3_simt_fallback_and_split_output(dev):
+    """Shapes the tcgen05 kernel does not tile run the same passes on the CUDA cores; the split fp16 output
+    (HL_CONV_OUT_F16_SPLIT) of one conv is the split operand of the next (ControlNet block -> projection)."""
+    from humanliff_b200.unet import pack_conv
+    from humanliff_b200 import _lib
+    out, ref, _ = _split_conv_case(dev, 1, 12, 12, 64, 96, 1, 1, 3e4, force_simt=True)
+    assert rel_l2(out, ref) < 1e-5
+    for simt in (False, True):
+        out, ref, y = _split_conv_case(dev, 2, 32, 32, 192, 192, 3, 1, 1e4, residual=True, out_split=True, force_simt=simt)
+        assert torch.isfinite(y).all() and rel_l2(out, ref) < 1e-5, simt
+        # ... and feeds a projection conv directly
+        g = torch.Generator().manual_seed(9)
+        w2 = torch.randn(192, 192, 1, 1, generator=g) / math.sqrt(192)
+        b2 = torch.zeros(192)
+        wpk, bpk = pack_conv(w2, b2, 192, "fp16", dev, mode="split")
+        z = torch.empty(2, 32, 32, 192, device=dev)
+        _call("hl_conv2d", y.data_ptr(), 1, 384, wpk.data_ptr(), bpk.data_ptr(), None, 0, z.data_ptr(), 192, None, 0,
+              2, 32, 32, 192, 192, 1, 1, _lib.CONV_SPLIT3, _stream())
+        ref2 = F.conv2d(ref, w2.double())
+        assert rel_l2(z.permute(0, 3, 1, 2), ref2) < 2e-5
+
+
+def test_stem_split_packed(dev):
+    """Stem conv (27 -> 192, one 64-channel K chunk): the operand row carries [hi(27) 0.. | lo(27) 0..], two passes."""
+    from humanliff_b200.unet import pack_conv
+    from humanliff_b200 import _lib
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W, Cout = 2, 27, 64, 64, 192
+    x, x2 = torch.randn(B, C, H, W, generator=g), 0.3 * torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(C * 9)
+    b = torch.randn(Cout, generator=g) * 0.1
+    op = torch.full((B, H, W, 64), float("nan"), device=dev, dtype=torch.float16)
+    xd, x2d = x.to(dev), x2.to(dev)                      # keep the device tensors alive across the launch
+    _call("hl_nchw_to_nhwc", xd.data_ptr(), x2d.data_ptr(), op.data_ptr(), 1, B, C, H * W, 64,
+          _lib.OP_SPLIT | (32 << 8), _stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(op).all() and float(op[..., 27:32].abs().max()) == 0 and float(op[..., 59:].abs().max()) == 0
+    wpk, bpk = pack_conv(w, b, 64, "fp16", dev, mode="split_packed")
+    y = torch.empty(B, H, W, Cout, device=dev)
+    _call("hl_conv2d", op.data_ptr(), 1, 64, wpk.data_ptr(), bpk.data_ptr(), None, 0, y.data_ptr(), Cout, None, 0,
+          B, H, W, 64, Cout, 3, 1, _lib.CONV_SPLIT2P, _stream())
+    ref = F.conv2d((x + x2).double(), w.double(), b.double(), padding=1)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref) < 1e-5
+
+
+def test_gn_apply_split_outputs(dev):
+    """hl_gn_apply op-mode word: a split (unscaled) normalised output for the out conv and a split scaled raw copy
+    for the 1x1 skip conv."""
+    from humanliff_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    B, HW, C = 2, 1024, 192
+    x = torch.randn(B, HW, C, generator=g) * 3e4
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    xd = x.to(dev)
+    stats = torch.zeros(B, C, 2, dtype=torch.float64, device=dev)
+    _call("hl_gn_stats", xd.data_ptr(), C, B, HW, C, stats.data_ptr(), C, _stream())
+    y = torch.full((B, HW, 2 * C), float("nan"), device=dev, dtype=torch.float16)
+    raw = torch.full((B, HW, 2 * C), float("nan"), device=dev, dtype=torch.float16)
+    mode = _lib.OP_SPLIT | (C << 8) | ((_lib.OP_SPLIT | _lib.OP_SCALED) << _lib.OP_RAW_SHIFT)
+    gd, bd = gamma.to(dev), beta.to(dev)                 # keep the device tensors alive across the launch
+    _call("hl_gn_apply", xd.data_ptr(), C, stats.data_ptr(), C, gd.data_ptr(), bd.data_ptr(), None, 0,
+          y.data_ptr(), 1, 2 * C, raw.data_ptr(), 2 * C, B, HW, C, 32, 1e-5, 1, mode, _stream())
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(x.permute(0, 2, 1).double(), 32, gamma.double(), beta.double(), eps=1e-5)).permute(0, 2, 1)
+    yy = (y[..., :C].double() + y[..., C:].double()).cpu()
+    rr = (raw[..., :C].double() + raw[..., C:].double()).cpu() * 16.0
+    assert torch.isfinite(y).all() and torch.isfinite(raw).all()
+    assert rel_l2(yy, ref) < 5e-6 and rel_l2(rr, x) < 2e-6

@@ -105,6 +105,11 @@ def test_operand_rounding_margin():
         assert err["fp16"] < bar, (case, err)
         if case == "tiny":
             assert abs(err["fp16"] / err["tf32"] - 1) < 0.05 and err["bf16"] > 3e-3, err
+        # the product's fp16 plan: hi + lo operand passes on the raw-stream convs, the stems and the output conv
+        # (tools/error_budget.py: those layers carry > half of the error variance) -- more than 2x inside the bar
+        plan = rel_l2(unet_oracle.unet_forward(sd, g["x"], ts, g["x_cond"], g["y"], num_heads=heads,
+                                               operand_round=unet_oracle.product_fp16_plan), ref)
+        assert plan < (4.5e-4 if case == "prod64" else 6e-4) and plan < 0.65 * err["fp16"], (case, plan, err)
 
 
 def test_oracle_matches_full_size_goldens():

@@ -23,9 +23,9 @@ def test_philox_randn_moments_and_reproducibility():
     n = 1 << 22
     st = torch.cuda.current_stream().cuda_stream
     a, b, c = (torch.empty(n, device=DEV) for _ in range(3))
-    call("hl_randn", a.data_ptr(), n, None, 1234, 0, st)
-    call("hl_randn", b.data_ptr(), n, None, 1234, 0, st)
-    call("hl_randn", c.data_ptr(), n, None, 1234, 1, st)
+    call("hl_randn", a.data_ptr(), n, None, 1234, 0, 0, st)
+    call("hl_randn", b.data_ptr(), n, None, 1234, 0, 0, st)
+    call("hl_randn", c.data_ptr(), n, None, 1234, 1, 0, st)
     assert torch.equal(a, b)                                   # counter-based: same (seed, draw) -> same stream
     ad, cd = a.double(), c.double()
     assert abs(float(ad.mean())) < 3e-3 and abs(float(ad.var()) - 1.0) < 5e-3
@@ -35,8 +35,11 @@ def test_philox_randn_moments_and_reproducibility():
     assert float(ad.abs().max()) < 7.0 and torch.isfinite(a).all()
     # device-resident state is read instead of the by-value pair
     state = torch.tensor([1234, 1], dtype=torch.int64, device=DEV)
-    call("hl_randn", b.data_ptr(), n, state.data_ptr(), 0, 0, st)
+    call("hl_randn", b.data_ptr(), n, state.data_ptr(), 0, 0, 0, st)
     assert torch.equal(b, c)
+    # sharding invariance: the second half drawn on its own with its element offset equals the second half of the whole
+    call("hl_randn", b.data_ptr(), n // 2, None, 1234, 0, n // 2, st)
+    assert torch.equal(b[:n // 2], a[n // 2:])
 
 
 def test_ddpm_step_rng_bit_exact_with_injected_noise_and_gaussian_without():

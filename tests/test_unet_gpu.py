@@ -2,19 +2,22 @@
 (tests/golden, made by oracle/make_goldens.py) and against the oracle on fresh seeded inputs.
 
 Tolerances (north_star: 1e-3 relative fp32): ``precision="fp32"`` (CUDA-core kernels, same arithmetic
-as the reference up to summation order) 5e-5; ``precision="fp16"`` / ``"tf32"`` (tcgen05; operands rounded to
-an 11-bit significand, fp32 accumulation) 1e-3 rel-L2 on the PRODUCTION architecture (prod64 case).  The
-2-head, 64-channel "tiny" test model averages the operand-rounding noise over 3x fewer channels per
-contraction; the CPU emulation of the same numerics (tests/test_oracle_cpu.py::test_operand_rounding_margin)
-puts it at 0.99e-3, so its gate is 1.5e-3."""
+as the reference up to summation order) 5e-5.  ``precision="fp16"`` (the production mode: tcgen05, operands rounded to
+an 11-bit significand, fp32 accumulation, PLUS hi + lo operand pairs for the raw-stream convs and the output conv,
+DESIGN.md 3): the CPU emulation of the same numerics (tests/test_oracle_cpu.py::test_operand_rounding_margin) predicts
+3.7e-4 on the production architecture and 5.0e-4 on the 2-head 64-channel "tiny" model -> gates 6e-4 / 8e-4, i.e. 40 % /
+20 % under north_star's bar.  ``precision="tf32"`` (every operand TF32-rounded, NO hi + lo passes) is a kernel
+cross-check mode, not a shippable one: measured 1.10e-3 on the production architecture at t = 0 (8.1e-4 emulated at
+t = 100) -- over north_star's bar, which is exactly what the hi + lo passes of the fp16 plan buy back; its gates
+(1.25e-3 / 1.5e-3) only guard against regressions of the kind::tf32 kernel path."""
 import pytest
 import torch
 
 from common import CASES, load_golden, model_state_dict, rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
-TOL = {("tiny", "fp32"): 5e-5, ("prod64", "fp32"): 5e-5, ("prod64", "fp16"): 1e-3, ("prod64", "tf32"): 1e-3,
-       ("tiny", "fp16"): 1.5e-3, ("tiny", "tf32"): 1.5e-3}
+TOL = {("tiny", "fp32"): 5e-5, ("prod64", "fp32"): 5e-5, ("prod64", "fp16"): 6e-4, ("prod64", "tf32"): 1.25e-3,
+       ("tiny", "fp16"): 8e-4, ("tiny", "tf32"): 1.5e-3}
 
 
 def _model(case, precision):
@@ -25,7 +28,7 @@ def _model(case, precision):
 
 
 @pytest.mark.parametrize("case,precision", [("tiny", "fp32"), ("tiny", "fp16"), ("tiny", "tf32"), ("prod64", "fp32"),
-                                            ("prod64", "fp16")])
+                                            ("prod64", "fp16"), ("prod64", "tf32")])
 def test_unet_forward_and_p_sample_vs_reference_golden(case, precision):
     model, diffusion, g, _, _ = _model(case, precision)
     dev = torch.device("cuda:0")
@@ -61,7 +64,65 @@ def test_free_running_loop_vs_reference_golden(precision):
         tt = torch.full((img.shape[0],), i, dtype=torch.int64, device=dev)
         img = diffusion.p_sample(model, img, xc, tt, model_kwargs={"y": y}, noise=g["loop_noise"][k].to(dev))["sample"]
     err = rel_l2(img, g["loop_final"])
-    assert err < (1e-4 if precision == "fp32" else 2e-3), err
+    assert err < (1e-4 if precision == "fp32" else 1e-3), err
+
+
+def test_free_running_loop_production_architecture_vs_reference_golden():
+    """Parity metric (ii) of SURVEY 8(d) on the PRODUCTION architecture, fp16 plan, gate = north_star's 1e-3:
+    (a) the 6-step chain stored in unet_prod_64.npz, driven step by step through p_sample;
+    (b) 50 free-running steps (unet_prod_64_loop50.npz; x_T, x_cond and the per-step noise regenerate from their
+        seeds) through p_sample_loop -- i.e. through the one-CUDA-graph-per-step loop with injected noise."""
+    from humanliff_b200 import synth
+    from oracle.make_goldens import loop_noise
+    model, diffusion, g, _, _ = _model("prod64", "fp16")
+    dev = torch.device("cuda:0")
+    n, T = int(g["loop_steps"]), diffusion.num_timesteps
+    img, xc, y = g["x"].to(dev), g["x_cond"].to(dev), g["y"].to(dev)
+    for k, i in enumerate(range(T - 1, T - 1 - n, -1)):
+        tt = torch.full((img.shape[0],), i, dtype=torch.int64, device=dev)
+        img = diffusion.p_sample(model, img, xc, tt, model_kwargs={"y": y}, noise=g["loop_noise"][k].to(dev))["sample"]
+    e6 = rel_l2(img, g["loop_final"])
+    assert e6 < 1e-3, e6
+    g50 = load_golden("unet_prod_64_loop50.npz")
+    steps = int(g50["steps"])
+    x, xc, _ = synth.synth_denoise_inputs(1, 27, 64, 64, seed=1234)
+    y = g50["y"].to(dev)
+    # p_sample_loop walks i = T-1 .. 0; the golden holds the state after the first `steps` steps: stop there
+    it = diffusion.p_sample_loop_progressive(model, tuple(x.shape), x_cond=xc.to(dev), noise=x.to(dev).clone(),
+                                             model_kwargs={"y": y},
+                                             step_noise=lambda i: loop_noise(T - 1 - i, x.shape).to(dev))
+    out = None
+    for k, out in enumerate(it):
+        if k == steps - 1:
+            break
+    e50 = rel_l2(out["sample"], g50["loop_final"])
+    print(f"production-architecture free-running loop: 6 steps {e6:.3e}, {steps} steps {e50:.3e}")
+    assert e50 < 1e-3, e50
+
+
+def test_large_magnitude_residual_stream_fp16_range():
+    """fp16 range guard: the stem weights are scaled so that the raw residual stream -- what the
+    1x1 skip, Downsample, ControlNet-projection and Upsample convs read un-normalised -- reaches |x| ~ 1e5, beyond
+    fp16's 65504.  The scaled hi | lo operands (x * 2^-4) must keep the output finite and at parity with the fp32
+    oracle; a plain fp16 cast of the same stream is inf."""
+    from oracle import unet_oracle
+    fname, flags, seed, heads = CASES["tiny"]
+    model, diffusion, sd = model_state_dict(dict(flags, precision="fp16"), seed)
+    sd = dict(sd)
+    for k in ("input_blocks.0.0.weight", "input_blocks.0.0.bias", "input_blocks_cond.0.0.weight", "input_blocks_cond.0.0.bias"):
+        sd[k] = sd[k] * 3e4
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda:0").eval()
+    g = load_golden(fname)
+    dev = torch.device("cuda:0")
+    ts = torch.tensor([400, 400])
+    ref = unet_oracle.unet_forward(sd, g["x"], ts, g["x_cond"], g["y"], num_heads=heads)
+    hs0 = torch.nn.functional.conv2d(g["x"], sd["input_blocks.0.0.weight"], sd["input_blocks.0.0.bias"], padding=1)
+    assert float(hs0.abs().max()) > 65504 * 1.2          # the stream really leaves fp16's range
+    eps = model(g["x"].to(dev), ts.to(dev), g["x_cond"].to(dev), y=g["y"].to(dev))
+    assert torch.isfinite(eps).all()
+    e = rel_l2(eps, ref)
+    assert e < 1e-3, e
 
 
 def test_cuda_graph_replay_equals_eager():

@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Headline benchmark: tri-plane denoise sample-steps/s (27x256x256), BASELINE.json configs[1].
+"""Headline benchmark: tri-plane denoise sample-steps/s (27x256x256) and rendered rays/s, BASELINE.json.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
 
-One "step" = one DDPM ``p_sample`` (production UNet forward + fused posterior update) over one batch
-of B = 4 samples per GPU (weak scaling: per-GPU work is fixed as N grows; samples are independent so
-there is no data-path collective inside the loop -- the single all-gather of finished samples,
-triplane_sample_layered.py:211-219, is issued once after the K timed steps, inside the timed region).
+One "step" = one DDPM ``p_sample`` (production UNet forward + fused posterior update) over one batch of B = 4 samples
+per GPU (configs[1]; weak scaling: per-GPU work is fixed as N grows; samples are independent so there is no data-path
+collective inside the loop -- the single all-gather of finished samples, triplane_sample_layered.py:211-219, is issued
+once after the K timed steps, inside the timed region).
 
-Prints ONE JSON line (rank 0).  ``value`` = device-resident inputs; ``e2e`` = the public API
-(``SpacedDiffusion.p_sample``) fed from pinned HOST buffers with H2D/D2H inside the timed region.
-``--impl reference`` times the reference algorithm's CPU path (the oracle port; /root/reference does
-not exist on the GPU box) on the host cores.  The oracle is used here ONLY as that CPU baseline.
+Prints ONE JSON line (rank 0):
+  value / ms_per_step   device-resident: K steps of the production loop (`p_sample_loop`: one CUDA-graph replay per step)
+  sustained             the same loop for >= 3 s (the regime of a 1000-step run)
+  e2e                   the public API (`SpacedDiffusion.p_sample`) fed from pinned HOST buffers, H2D / D2H in the timed region
+  roofline              the dominant conv launch timed alone + the whole step against the bf16 peaks
+  cpu_baseline          the reference's CPU path on a bounded sample (N = 1)
+  b64                   configs[4]: batch=64 sharded over the N ranks, one all-gather, checksum of the gathered result
+  render                the second half of the metric (configs[2]): rays/s, roofline, host-buffer e2e, CPU reference
+  layered               configs[3]: 4-layer generation + 40 views + 512^3 density grids at batch 1, end to end (N = 1)
+``--impl reference`` times the UNMODIFIED reference (staged in oracle/_ref by oracle/build_ref.py; /root/reference does
+not exist on the GPU box) on the host cores at the same config; the oracle port is the fallback and says so.
 """
 import argparse
 import json
@@ -177,49 +184,131 @@ def dominant_kernel_roofline(device, B, peaks, precision, reps=20):
     return {"kernel": "k_conv_tc (tcgen05 %s implicit-GEMM conv3x3 192->192 @256^2 + residual + GN statistics, B=%d)" % (kind, B),
             "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_burst"], 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
-            # (profiles/r1_conv_full_v10.md: 302.75 + 165.85 MB; only quoted for the shape / precision it was taken on)
-            "traffic": 468.6e6 if (B == 4 and precision == "fp16") else None, "traffic_unit": "bytes/launch",
+            "traffic": None, "traffic_unit": "bytes/launch",     # filled from the committed ncu summary (conv_traffic_from_profile)
             "peak_source": peaks["source"] + "; " + note,
             "ms_per_launch": round(ms, 4), "algorithmic_gflop_per_launch": round(flops / 1e9, 2),
             "algorithmic_hbm_mb_per_launch": round(bytes_alg / 1e6, 1),
             "hbm_floor_ms": round(bytes_alg / (peaks["hbm_gbs"] * 1e9) * 1e3, 4)}
 
 
-def render_throughput(device, n_rays=262144, reps=3, precision="fp16"):
-    """Secondary metric of BASELINE.json (rendered rays/s, 128+128 samples): the fused tensor-core render kernel
-    on the 512x512 synthetic camera of SURVEY.md 8(d) config 3 (BASELINE configs[2]: one whole image per launch),
-    CUDA events."""
+MFLOP_PER_RAY = 44.14                    # 2 * (128 * 39,808 + 256 * 66,304) MAC
+TRANSCENDENTALS_PER_RAY = 327680          # 163,840 softplus activations x (exp + log) -- SURVEY 8(d): ~0.34 M per ray
+RENDER_METRIC = "rendered rays/sec (128+128 samples/ray, 27x256x256 tri-plane)"
+
+
+def _render_setup(device, precision="fp16", n_rays=262144):
     from humanliff_b200 import synth
     from humanliff_b200.renderer import Renderer
     r = Renderer(triplane_ch=27, test=True, precision=precision)
     synth.randomize_(r, seed=3, weight_gain=1.5)
     r = r.to(device)
-    planes = synth.synth_triplane(256, seed=7)[0].to(device)
+    planes = synth.synth_triplane(256, seed=7)
     bounds = torch.tensor(synth.WORLD_BOUNDS)
     ro, rd, near, far, _ = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=30.0)
     if n_rays < ro.shape[0]:
         sel = slice(512 * 192, 512 * 192 + n_rays)           # rows through the middle of the body box
         ro, rd, near, far = (t[sel] for t in (ro, rd, near, far))
+    return r, planes, bounds, [t.contiguous() for t in (ro, rd, near, far)]
+
+
+def render_throughput(device, n_rays=262144, reps=3, precision="fp16"):
+    """Rendered rays/s on the 512x512 synthetic camera of SURVEY.md 8(d) config 3 (BASELINE configs[2]: one whole
+    image per launch), device-resident inputs, in-kernel counter-based uniforms, CUDA events."""
+    r, planes, bounds, rays = _render_setup(device, precision, n_rays)
+    planes_d = planes[0].to(device)
+    ro, rd, near, far = (t.to(device) for t in rays)
     n_rays = ro.shape[0]
-    ro, rd, near, far = (t.contiguous().to(device) for t in (ro, rd, near, far))
     st = torch.cuda.current_stream(device)
-    r.render_rays(planes, bounds, ro, rd, near, far, u=None, seed=1)
+    r.render_rays(planes_d, bounds, ro, rd, near, far, u=None, seed=1)
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(reps):
-        r.render_rays(planes, bounds, ro, rd, near, far, u=None, seed=2 + i)
+        r.render_rays(planes_d, bounds, ro, rd, near, far, u=None, seed=2 + i)
     e1.record(st)
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / reps
     rays_s = n_rays / (ms * 1e-3)
-    return {"metric": "rendered rays/sec (128+128 samples/ray, 27x256x256 tri-plane)", "value": round(rays_s, 1),
+    return {"metric": RENDER_METRIC, "value": round(rays_s, 1),
             "unit": "rays/s", "rays_per_launch": n_rays, "ms_per_launch": round(ms, 3),
-            "mlp_tflops": round(rays_s * 44.14e6 / 1e12, 2),
-            "precision": r.precision,
-            "note": "512x512 image, 44.14 MFLOP/ray (BASELINE.md section 2); in-kernel counter-based uniforms "
-                    "(throughput mode); MLP on mma.sync fp16 / fp32 accumulate"}
+            "mlp_tflops": round(rays_s * MFLOP_PER_RAY * 1e6 / 1e12, 2),
+            "precision": r.precision}
+
+
+def render_block(device, peaks, clocks_mhz, cpu=True, reps=3):
+    """The render half of BASELINE's metric as a measured row: device-resident rays/s (in-kernel uniforms and injected
+    uniforms), its roofline position, the host-buffer end-to-end number through the script-level render() API, and the
+    reference's CPU renderer on one of its own 16,384-ray chunks."""
+    from humanliff_b200 import render as render_api
+    r, planes, bounds, rays = _render_setup(device)
+    out = render_throughput(device, reps=reps)
+    out["workload"] = ("tri-plane volume render, 512x512 image = 262,144 rays in ONE launch, 128 + 128 samples/ray, random "
+                       "27x256x256 tri-plane (configs[2])")
+    out["uniforms"] = "in-kernel counter-based generator (the reference draws torch.rand on the CPU per chunk)"
+    n = rays[0].shape[0]
+    planes_d = planes[0].to(device)
+    ro, rd, near, far = (t.to(device) for t in rays)
+    st = torch.cuda.current_stream(device)
+    # --- injected uniforms (the parity mode: u[ray, 128] read from HBM, +512 B/ray) ---
+    u = torch.rand(n, 128, device=device)
+    r.render_rays(planes_d, bounds, ro, rd, near, far, u=u)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        r.render_rays(planes_d, bounds, ro, rd, near, far, u=u)
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    out["injected_uniforms"] = {"value": round(n / (e0.elapsed_time(e1) / reps * 1e-3), 1), "unit": "rays/s"}
+    # --- roofline: MLP arithmetic on the tensor pipe, MUFU co-limiting (SURVEY 8(d)); HBM is not the bound ---
+    rays_s = out["value"]
+    sm_mhz = clocks_mhz or 1965.0
+    mufu_peak = 16.0 * 148 * sm_mhz * 1e6                      # MUFU lanes / clk / SM x SMs x clock
+    out["roofline"] = {
+        "kernel": "k_render_tc5 (tcgen05 kind::f16 MLP, activations in tensor memory, 2 ray groups per SM)",
+        "bound": "tensor", "achieved": round(rays_s * MFLOP_PER_RAY * 1e6 / 1e12, 2), "peak": peaks["bf16_burst"],
+        "unit": "TFLOP/s", "frac": round(rays_s * MFLOP_PER_RAY * 1e6 / 1e12 / peaks["bf16_burst"], 4),
+        "traffic": None, "peak_source": peaks["source"],
+        "algorithmic_mflop_per_ray": MFLOP_PER_RAY,
+        "mufu": {"algorithmic_transcendentals_per_ray": TRANSCENDENTALS_PER_RAY,
+                 "achieved_gops": round(rays_s * TRANSCENDENTALS_PER_RAY / 1e9, 1),
+                 "peak_gops": round(mufu_peak / 1e9, 1), "frac": round(rays_s * TRANSCENDENTALS_PER_RAY / mufu_peak, 4),
+                 "note": "peak = 16 MUFU lanes/clk/SM x 148 SMs x the sampled SM clock; the kernel evaluates 3 of 4 lg2 on "
+                         "the FMA pipe, so the algorithmic count may exceed what the MUFU pipe actually executed"},
+        "hbm": {"compulsory_bytes_per_ray": 64, "achieved_gbs": round(rays_s * 64 / 1e9, 2), "peak_gbs": peaks["hbm_gbs"],
+                "note": "rays in, maps out; the 19 MB quad-texel table and the 170 KB MLP stay in L2 / shared memory"}}
+    # --- end to end through the script-level API with HOST buffers: tri-plane, rays up; rgb / acc / depth maps down ---
+    h_in = [t.pin_memory() for t in (planes, rays[0][None], rays[1][None], rays[2][None], rays[3][None])]
+    h_out = [torch.empty(1, n, 3).pin_memory(), torch.empty(1, n).pin_memory(), torch.empty(1, n).pin_memory()]
+    tp = {"world_bounds": bounds[None].to(device)}
+
+    def one_image():
+        d = [t.to(device, non_blocking=True) for t in h_in]
+        rgb, acc, _, dep = render_api(rays_o=d[1], rays_d=d[2], near=d[3], far=d[4], tri_planes=d[0], tp_input=tp, renderer=r,
+                                      n_samples=128, perturb=0., n_importance=128, white_bkgd=False)
+        h_out[0].copy_(rgb, non_blocking=True)
+        h_out[1].copy_(acc, non_blocking=True)
+        h_out[2].copy_(dep, non_blocking=True)
+
+    one_image()
+    torch.cuda.synchronize(device)
+    e0.record(st)
+    for _ in range(reps):
+        one_image()
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    out["e2e"] = {"value": round(n / (ms * 1e-3), 1), "unit": "rays/s", "ms_per_image": round(ms, 3),
+                  "h2d_bytes_per_step": sum(t.numel() * 4 for t in h_in), "d2h_bytes_per_step": sum(t.numel() * 4 for t in h_out),
+                  "api": "humanliff_b200.render(...) (script-level helper of run_nerf_batch.py:29-67), pinned host buffers"}
+    if cpu:
+        threads = os.cpu_count() or 1
+        cr = CpuRender(threads)
+        rv, rdt = cr.time()
+        out["cpu_baseline"] = {"value": round(rv, 1), "unit": "rays/s", "cores": threads, "kind": cr.kind,
+                               "sample": "Renderer.render on one 16,384-ray chunk of the same camera (the reference's own "
+                                         "chunk size), 1 timed call after 1 warm-up (%.1f s), injected uniforms" % rdt}
+    return out
 
 
 def _reference_root():
@@ -364,7 +453,6 @@ class CpuRender:
 
 WORKLOAD = ("1000-step DDPM p_sample_loop, 27x256x256 tri-plane, batch=4 per GPU (configs[1]); one step = one p_sample "
             "(UNet 497M params + posterior update)")
-RENDER_METRIC = "rendered rays/sec (128+128 samples/ray, 27x256x256 tri-plane)"
 
 
 def run_reference(args):
@@ -424,10 +512,166 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+class LoopStepper:
+    """The production sampling loop as the bench's "step": `diffusion.p_sample_loop` (one CUDA-graph replay per step:
+    UNet + posterior with in-kernel noise + on-device timestep advance), restarted when its T steps are used up."""
+
+    def __init__(self, model, diffusion, shape, xc, y, device):
+        self.args = (model, diffusion, shape, xc, y, device)
+        self.it, self.last = None, None
+
+    def step(self):
+        model, diffusion, shape, xc, y, device = self.args
+        for _ in range(2):
+            if self.it is None:
+                self.it = diffusion._sample_loop(model, shape, xc, None, True, None, {"y": y}, device, False, None,
+                                                 fresh=False)
+            try:
+                self.last = next(self.it)
+                return self.last["sample"]
+            except StopIteration:
+                self.it = None
+        raise RuntimeError("sampling loop yielded nothing")
+
+
+def b64_block(model, diffusion, device, world, rank, steps, dist_mod):
+    """BASELINE configs[4]: the batch=64 p_sample_loop sharded data-parallel over the N ranks of this run (64 / N samples
+    per rank; N = 1 runs all 64 on one GPU), ONE all-gather of the finished samples at the end.  Strong scaling of a
+    fixed job.  x_T and the per-step Gaussians come from the in-kernel generator keyed on the GLOBAL sample index
+    (diffusion.sample_offset), so the gathered [64, 27, 256, 256] is the same tensor for every N up to summation-order
+    rounding: `checksum` lets the lines of different N be compared."""
+    from humanliff_b200 import _lib
+    from humanliff_b200.dist import all_gather_samples, warm_up
+    G = 64
+    if G % world:
+        return {"skipped": "64 samples do not divide over %d ranks" % world}
+    b = G // world
+    shape = (b, C, HW, HW)
+    xc = torch.zeros(shape, device=device)
+    y = ((torch.arange(G) % 4)[rank * b:(rank + 1) * b]).to(device)
+    diffusion.sample_offset = rank * b
+    try:
+        torch.manual_seed(4321)                               # same seed on every rank: the global noise field
+        stepper = LoopStepper(model, diffusion, shape, xc, y, device)
+        warm_up(shape, device)
+        for _ in range(2):
+            stepper.step()
+        torch.manual_seed(4321)
+        stepper.it = None                                     # restart the chain so that every N times the same steps
+        if world > 1:
+            dist_mod.barrier()
+        torch.cuda.synchronize(device)
+        st = torch.cuda.current_stream(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count
+        e0.record(st)
+        for _ in range(steps):
+            img = stepper.step()
+        gathered, labels = all_gather_samples(img, y, equal_shards=True)
+        e1.record(st)
+        if world > 1:
+            dist_mod.barrier()
+        torch.cuda.synchronize(device)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist_mod.all_reduce(ms, op=dist_mod.ReduceOp.MAX)
+        ms = float(ms.item())
+        gd = gathered.double()
+        wts = torch.linspace(0.5, 1.5, gd[0].numel(), device=device, dtype=torch.float64)
+        return {"workload": "batch=64 p_sample_loop sharded over %d GPU(s), one all-gather (configs[4])" % world,
+                "global_batch": G, "batch_per_gpu": b, "steps": steps, "scaling": "strong",
+                "value": round(G * steps / (ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms / steps, 3),
+                "gpu_launches": _lib.launch_count - n0,
+                "gathered_shape": list(gathered.shape), "labels_ok": bool(torch.equal(labels.cpu(), torch.arange(G) % 4)),
+                "checksum": {"sum": float(gd.sum()), "abs_sum": float(gd.abs().sum()),
+                             "weighted": float((gd.reshape(G, -1) * wts).sum())}}
+    finally:
+        diffusion.sample_offset = 0
+        for k in [k for k in model._plans if k[1] == b and b != 4]:
+            del model._plans[k]                               # give the 64 / N-sample workspace back
+        torch.cuda.empty_cache()
+
+
+def layered_block(model, device, peaks, views=40, grid_res=512):
+    """BASELINE configs[3]: one human, end to end -- 4 clothing layers x 250-step respaced loop at batch 1 (layer k is
+    conditioned on layer k-1's tri-plane, kept in HBM), every layer rendered for `views` 512x512 views and its density
+    grid evaluated at `grid_res`^3 (the GPU part of extract_geometry).  Seconds, wall clock around synchronised regions."""
+    from humanliff_b200 import factory, layered, synth
+    from humanliff_b200.renderer import Renderer
+    _, diff250 = factory.create_model_and_diffusion(**factory.production_flags("250"))
+    r = Renderer(triplane_ch=27, test=True)
+    synth.randomize_(r, seed=3, weight_gain=1.5)
+    r = r.to(device)
+    bounds = torch.tensor(synth.WORLD_BOUNDS)
+    tp = {"world_bounds": bounds[None].to(device)}
+    cams = []
+    for v in range(views):
+        ro, rd, near, far, _ = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=360.0 * v / views)
+        cams.append([t.to(device) for t in (ro, rd, near, far)])
+    torch.manual_seed(99)
+    # warm-up: plan build + graph capture at B = 1, renderer packing
+    layered.sample_layer(model, _ShortLoop(diff250, 3), 0, 1, device=device)
+    r.render_rays(torch.zeros(3, 9, 256, 256, device=device), bounds, *cams[0])
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    outs = layered.sample_all_layers(model, diff250, 1, device=device)
+    torch.cuda.synchronize(device)
+    t1 = time.perf_counter()
+    for sample, _ in outs:
+        planes = sample[0].reshape(3, 9, 256, 256)
+        for cam in cams:
+            r.render_rays(planes, tp["world_bounds"][0], *cam)
+    torch.cuda.synchronize(device)
+    t2 = time.perf_counter()
+    for sample, _ in outs:
+        r.density_grid(tp, sample, resolution=grid_res)
+    torch.cuda.synchronize(device)
+    t3 = time.perf_counter()
+    steps = 4 * diff250.num_timesteps
+    ms_step = 1e3 * (t1 - t0) / steps
+    wbytes = sum(c.w.numel() * c.w.element_size() for c in model._convs.values()) + model._film_w.numel() * 4
+    return {"workload": "layer-conditioned 4-layer generation + render, batch=1 (configs[3]): 4 x %d denoise steps, 4 x %d views "
+                        "of 512x512, 4 density grids of %d^3" % (diff250.num_timesteps, views, grid_res),
+            "total_s": round(t3 - t0, 3), "denoise_s": round(t1 - t0, 3), "render_s": round(t2 - t1, 3), "grid_s": round(t3 - t2, 3),
+            "denoise_steps": steps, "ms_per_step_b1": round(ms_step, 3), "sample_steps_per_s_b1": round(1e3 / ms_step, 2),
+            "rays_per_s": round(4 * views * 262144 / (t2 - t1), 1), "grid_points_per_s": round(4 * grid_res ** 3 / (t3 - t2), 1),
+            "roofline_b1": {"bound": "hbm", "note": "at batch 1 every layer below 128^2 streams its weights for a handful of "
+                            "pixels: the step's floor is the weight stream", "weight_bytes_per_step": wbytes,
+                            "achieved": round(wbytes / (ms_step * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(wbytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                            "tensor_frac_of_bf16_sustained": round(GFLOP_PER_SAMPLE_STEP / ms_step / peaks["bf16_sustained"], 4)}}
+
+
+class _ShortLoop:
+    """A diffusion object whose loop runs only its first `n` steps (bench warm-up of the layered path)."""
+
+    def __init__(self, diffusion, n):
+        self.d, self.n = diffusion, n
+
+    def p_sample_loop(self, model, shape, **kw):
+        it = self.d.p_sample_loop_progressive(model, shape, **{k: v for k, v in kw.items() if k != "noise" or v is not None})
+        out = None
+        for k, out in enumerate(it):
+            if k + 1 >= self.n:
+                break
+        return out["sample"]
+
+
+def conv_traffic_from_profile(B, precision):
+    """dram bytes per launch of the dominant conv from the committed `ncu --set full` summary of this round (a citation of
+    a profile, looked up by shape -- None when the committed profile does not cover the configuration)."""
+    path = os.path.join(ROOT, "profiles", "r2_conv_dram_bytes.json")
+    try:
+        d = json.load(open(path))
+        return d.get("%s_B%d" % (precision, B))
+    except Exception:                       # noqa: BLE001
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from humanliff_b200 import _lib
-    from humanliff_b200.dist import all_gather_samples
+    from humanliff_b200.dist import all_gather_samples, warm_up
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -440,30 +684,27 @@ def run_ours(args):
     model, diffusion, sd = build_model(device, args.precision)
     g = torch.Generator().manual_seed(1234 + rank)
     shape = (B, C, HW, HW)
-    # inputs: a few rotating noise buffers (resident in HBM for `value`, pinned on the host for `e2e`)
+    # inputs: resident in HBM for `value`, pinned on the host for `e2e`
     h_x = torch.randn(shape, generator=g).pin_memory()
     h_xc = torch.zeros(shape).pin_memory()
     h_z = [torch.randn(shape, generator=g).pin_memory() for _ in range(2)]
     y = (torch.arange(B) % 4).to(device)
-    x, xc = h_x.to(device), h_xc.to(device)
-    zs = [z.to(device) for z in h_z]
+    xc = h_xc.to(device)
     T = diffusion.num_timesteps
     t_dev = torch.empty(B, dtype=torch.int64, device=device)
     st = torch.cuda.current_stream(device)
-
-    def step_resident(img, i):
-        t_dev.fill_(T - 1 - (i % T))
-        return diffusion.p_sample(model, img, xc, t_dev, clip_denoised=True, model_kwargs={"y": y}, noise=zs[i % 2])["sample"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # ---------------- device-resident timing (`value`) ----------------
-    img = x
+    # ---------------- device-resident timing (`value`): the production loop, one graph replay per step ----------------
+    torch.manual_seed(1234 + rank)
+    stepper = LoopStepper(model, diffusion, shape, xc, y, device)
     for i in range(W):
-        img = step_resident(img, i)
+        img = stepper.step()
+    warm_up(shape, device)                                   # communicator channels + receive buffer, outside the timed region
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -472,8 +713,8 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(K):
-        img = step_resident(img, W + i)
-    gathered, _ = all_gather_samples(img, y)
+        img = stepper.step()
+    gathered, _ = all_gather_samples(img, y, equal_shards=True)
     e1.record(st)
     barrier()
     launches = _lib.launch_count - calls0
@@ -483,6 +724,20 @@ def run_ours(args):
     ms_total = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms_total * 1e-3)
+
+    # ---------------- sustained: the same loop for >= 3 s (a 1000-step loop runs ~15 s: power-capped clocks) -----------
+    n_sus = max(K, int(3200.0 / (ms_total / K)) + 1)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(st)
+    for i in range(n_sus):
+        stepper.step()
+    e5.record(st)
+    barrier()
+    ms_sus = torch.tensor([e4.elapsed_time(e5)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_sus, op=dist.ReduceOp.MAX)
+    ms_sus = float(ms_sus.item())
 
     # ---------------- end-to-end through the public API with HOST buffers (`e2e`) ----------------
     # Every step uploads its three inputs (x, x_cond, noise) from pinned host memory and downloads the sample.
@@ -504,49 +759,67 @@ def run_ours(args):
             stage[s][2].copy_(h_z[i % 2], non_blocking=True)
             up_done[s].record(copy_st)
 
-    barrier()
     d_out = [torch.empty(shape, device=device) for _ in range(2)]
     down_done = [torch.cuda.Event() for _ in range(2)]
-    for s_ in range(2):
-        free[s_].record(st)
-        down_done[s_].record(st)
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(st)
-    copy_st.wait_event(e2)                                   # no upload starts before the timed region
-    upload(0)
-    for i in range(K):
-        s_ = i % 2
-        if i + 1 < K:
-            upload(i + 1)
-        st.wait_event(up_done[s_])
-        t_dev.fill_(T - 1 - (i % T))
-        out = diffusion.p_sample(model, stage[s_][0], stage[s_][1], t_dev, clip_denoised=True, model_kwargs={"y": y},
-                                 noise=stage[s_][2])["sample"]
-        if args.e2e_download == "inline":
+
+    def e2e_pass(n):
+        for s_ in range(2):
             free[s_].record(st)
-            h_out[s_].copy_(out, non_blocking=True)
-        else:
-            st.wait_event(down_done[s_])                     # the download that last used this slot has finished
-            d_out[s_].copy_(out)                             # 28 MB device copy; frees `out` for the allocator
-            free[s_].record(st)
-            down_st.wait_event(free[s_])
-            with torch.cuda.stream(down_st):
-                h_out[s_].copy_(d_out[s_], non_blocking=True)    # overlaps step i+1
-                down_done[s_].record(down_st)
-    st.wait_stream(down_st)                                  # every download lands inside the timed region
-    e3.record(st)
+            down_done[s_].record(st)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(st)
+        copy_st.wait_event(a0)                               # no upload starts before the timed region
+        upload(0)
+        for i in range(n):
+            s_ = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            st.wait_event(up_done[s_])
+            t_dev.fill_(T - 1 - (i % T))
+            out = diffusion.p_sample(model, stage[s_][0], stage[s_][1], t_dev, clip_denoised=True, model_kwargs={"y": y},
+                                     noise=stage[s_][2])["sample"]
+            if args.e2e_download == "inline":
+                free[s_].record(st)
+                h_out[s_].copy_(out, non_blocking=True)
+            else:
+                st.wait_event(down_done[s_])                 # the download that last used this slot has finished
+                d_out[s_].copy_(out)                         # 28 MB device copy; frees `out` for the allocator
+                free[s_].record(st)
+                down_st.wait_event(free[s_])
+                with torch.cuda.stream(down_st):
+                    h_out[s_].copy_(d_out[s_], non_blocking=True)    # overlaps step i+1
+                    down_done[s_].record(down_st)
+        st.wait_stream(down_st)                              # every download lands inside the timed region
+        a1.record(st)
+        barrier()
+        m = torch.tensor([a0.elapsed_time(a1)], device=device)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        return float(m.item())
+
     barrier()
-    ms2 = torch.tensor([e2.elapsed_time(e3)], device=device)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(ms2.item()) * 1e-3)
+    e2e_pass(2)                                              # the per-step path (own plan replay + posterior launch) warmed
+    barrier()
+    ms2 = e2e_pass(K)
+    e2e_value = world * B * K / (ms2 * 1e-3)
     nbytes = B * C * HW * HW * 4
+
+    b64 = None
+    if not args.no_b64:
+        try:
+            b64 = b64_block(model, diffusion, device, world, rank, min(K, args.b64_steps), dist)
+        except Exception as e:                               # noqa: BLE001 -- a secondary block must not take the headline down
+            b64 = {"error": repr(e)[:300]}
 
     if rank == 0:
         roof = dominant_kernel_roofline(device, B, peaks, args.precision)
+        roof["traffic"] = conv_traffic_from_profile(B, args.precision)
         step_tflops = GFLOP_PER_SAMPLE_STEP * B / (ms_total / K)          # GFLOP / ms = TFLOP/s
+        sus_tflops = GFLOP_PER_SAMPLE_STEP * B / (ms_sus / n_sus)
         roof["whole_step_tflops"] = round(step_tflops, 2)
-        roof["whole_step_frac_of_bf16_sustained"] = round(step_tflops / peaks["bf16_sustained"], 4)
+        roof["whole_step_frac_of_bf16_burst"] = round(step_tflops / peaks["bf16_burst"], 4)
+        roof["whole_step_tflops_sustained"] = round(sus_tflops, 2)
+        roof["whole_step_frac_of_bf16_sustained"] = round(sus_tflops / peaks["bf16_sustained"], 4)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -558,25 +831,35 @@ def run_ours(args):
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,
-                "dtype": {"fp16": "fp16 operands (11-bit significand, = TF32) x fp32 accumulate, fp32 residual stream / "
-                                  "GroupNorm / softmax / posterior", "tf32": "tf32", "fp32": "f32"}[args.precision],
+                "dtype": {"fp16": "fp16 operands (11-bit significand, = TF32; hi + lo fp16 pairs for the raw-stream convs and the "
+                                  "output conv) x fp32 accumulate, fp32 residual stream / GroupNorm / softmax / posterior",
+                          "tf32": "tf32", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD,
                            "batch_per_gpu": B, "global_batch": B * world, "resolution": "27x256x256",
                            "parallelism": "dp%d (batch sharded, no data-path collective; one all-gather of finished samples)" % world,
                            "l2_policy": "per-step working set (>= 6 GB of activations + 1 GB of fp16 weights) exceeds the 126 MB L2",
-                           "execution": "one CUDA graph replay per UNet forward (%d kernels on two streams) + 1 posterior kernel" % (
-                               launches // K - 1),
+                           "execution": "p_sample_loop: ONE CUDA graph replay per step (%d kernels on two streams: UNet, posterior "
+                                        "with in-kernel Philox noise, on-device timestep advance)" % (launches // K),
                            "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches,
+                "sustained": {"steps": n_sus, "seconds": round(ms_sus * 1e-3, 3), "ms_per_step": round(ms_sus / n_sus, 3),
+                              "value": round(world * B * n_sus / (ms_sus * 1e-3), 3), "unit": UNIT},
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes,
-                        "d2h_bytes_per_step": nbytes, "ms_per_step": round(float(ms2.item()) / K, 3)},
-                "roofline": roof, "cpu_baseline": cpu}
+                        "d2h_bytes_per_step": nbytes, "ms_per_step": round(ms2 / K, 3),
+                        "api": "SpacedDiffusion.p_sample(model, x, x_cond, t, ...) with pinned host buffers"},
+                "roofline": roof, "cpu_baseline": cpu, "b64": b64}
         if world == 1 and not args.no_render:
             try:
-                line["render"] = render_throughput(device)
+                line["render"] = render_block(device, peaks, clocks.get("sm_mhz") if clocks else None,
+                                              cpu=not args.no_cpu_baseline)
             except Exception as e:                      # the secondary metric must not take the headline down
-                line["render"] = {"error": repr(e)[:200]}
+                line["render"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_layered:
+            try:
+                line["layered"] = layered_block(model, device, peaks, views=args.layered_views, grid_res=args.layered_grid)
+            except Exception as e:                      # noqa: BLE001
+                line["layered"] = {"error": repr(e)[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -594,6 +877,11 @@ def main():
                     help="e2e: read each finished sample back on a copy stream (overlapping the next step) or in line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-b64", action="store_true", help="skip the configs[4] block (batch=64 sharded over the ranks)")
+    ap.add_argument("--b64-steps", type=int, default=5)
+    ap.add_argument("--no-layered", action="store_true", help="skip the configs[3] block (4-layer generation + render, B=1)")
+    ap.add_argument("--layered-views", type=int, default=40)
+    ap.add_argument("--layered-grid", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -214,6 +214,7 @@ struct Group {
     uint32_t w_smem;                  // shared-memory address of the MLP image
     uint32_t fb;                      // shared-memory address of the fp32 table
     uint32_t sc;                      // shared-memory address of the group's scratch
+    unsigned long long *prof;         // non-null in the one profiled thread: [6] barrier + issue, [7] wait for the MMAs
 };
 
 __device__ __forceinline__ void gbar(const Group &G) { named_bar(1 + G.g, NS); }
@@ -227,52 +228,70 @@ __device__ __forceinline__ uint64_t wdesc(uint32_t saddr) {
 // instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
-// Issue D[acc] (+)= A[tmem a_col, K = 16 * ksteps] . W[atoms at w_off]^T.  Called by ONE elected thread.
+// Issue D[acc + n_off .. + n) (+)= A[tmem a_col, K = 16 * ksteps] . W[rows n_off .. + n of the atoms at w_off]^T.
+// Called by ONE elected thread.
 __device__ __forceinline__ void issue_gemm(const Group &G, uint32_t a_col, int ksteps, uint32_t w_off, uint32_t atom_bytes,
-                                           int n, bool accumulate) {
+                                           int n, bool accumulate, int n_off = 0) {
     const uint32_t id = idesc_n(n);
-    const uint32_t d = G.tm_cols + TM_ACC;
+    const uint32_t d = G.tm_cols + TM_ACC + (uint32_t)n_off;
+    const uint32_t w0 = G.w_smem + w_off + (uint32_t)n_off * 128u;
 #pragma unroll 1
     for (int k = 0; k < ksteps; ++k) {
-        const uint64_t bd = wdesc(G.w_smem + w_off + (uint32_t)(k >> 2) * atom_bytes) + (uint64_t)(2 * (k & 3));
+        const uint64_t bd = wdesc(w0 + (uint32_t)(k >> 2) * atom_bytes) + (uint64_t)(2 * (k & 3));
         umma_ts_f16(d, G.tm_cols + a_col + 8u * (uint32_t)k, bd, id, (accumulate || k > 0) ? 1u : 0u);
     }
 }
 
-// everyone's tcgen05.st has landed -> one thread issues the layer's MMAs and commits to the group barrier
+// Everyone's tcgen05.st has landed -> one thread issues the layer's MMAs in TWO column halves, each committed to its own
+// barrier: the epilogue drains half 0 while the tensor core still computes half 1 (`issue(half)` issues one half;
+// views_linear, N = 64, is one half and commits both barriers together).
 template <typename F>
-__device__ __forceinline__ void run_layer(Group &G, F &&issue) {
+__device__ __forceinline__ void start_layer(Group &G, bool two_halves, F &&issue) {
+    const long long t0 = G.prof ? clock64() : 0;
     tmem_st_wait();
     tc_fence_before();
     gbar(G);
     if (G.warp == 0) {
         tc_fence_after();
         if (elect_one_sync()) {
-            issue();
-            umma_commit(G.mbar);
+            issue(0);
+            if (two_halves) {
+                umma_commit(G.mbar);
+                issue(1);
+            } else {
+                umma_commit(G.mbar);
+            }
+            umma_commit(G.mbar + 8u);
         }
         __syncwarp();
     }
-    mbar_wait(G.mbar, G.phase);
-    G.phase ^= 1u;
+    if (G.prof) atomicAdd(G.prof + 6, (unsigned long long)(clock64() - t0));
+}
+__device__ __forceinline__ void wait_half(Group &G, int half) {
+    const long long t0 = G.prof ? clock64() : 0;
+    mbar_wait(G.mbar + 8u * (uint32_t)half, G.phase);
     tc_fence_after();
+    if (G.prof) atomicAdd(G.prof + 7, (unsigned long long)(clock64() - t0));
 }
 
 // Drain 32 accumulator columns [c0, c0+32) of this thread's row.
 __device__ __forceinline__ void acc_ld(const Group &G, int c0, uint32_t *r) { tmem_ld32_nowait(G.tm + TM_ACC + (uint32_t)c0, r); }
 
 // hidden layer epilogue: h' = softplus2(acc) (the bias is already in the accumulator) -> fp16 -> A_h; optionally the
-// alpha head on the fp32 values
+// alpha head on the fp32 values.  Column half 0 is drained as soon as ITS MMAs have retired; its packed activations wait
+// in registers until half 1 has retired too (those MMAs still read the old A_h), then both halves are stored.
 template <bool ALPHA, bool ACT>
-__device__ __forceinline__ float epi_hidden(const Group &G) {
+__device__ __forceinline__ float epi_hidden(Group &G) {
     float s = 0.f;
-    uint32_t va[32], vb[32];
+    uint32_t va[32], vb[32], pk0[32];
+    wait_half(G, 0);
     acc_ld(G, 0, va);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t *cur = (c & 1) ? vb : va;
         uint32_t *nxt = (c & 1) ? va : vb;
         tmem_ld_wait();
+        if (c == 1) wait_half(G, 1);                    // chunk 2 belongs to half 1; chunk 1's data is already in registers
         if (c < 3) acc_ld(G, (c + 1) * 32, nxt);
         uint32_t pk[16];
 #pragma unroll
@@ -287,15 +306,28 @@ __device__ __forceinline__ float epi_hidden(const Group &G) {
                 s = fmaf(h0, w.x, s); s = fmaf(h1, w.y, s); s = fmaf(h2, w.z, s); s = fmaf(h3, w.w, s);
             }
         }
-        tmem_st16(G.tm + TM_AH + (uint32_t)(c * 16), pk);
+        if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk0[j] = pk[j];
+        } else if (c == 1) {
+            // half 1 has retired (waited above): nobody reads the old A_h any more
+            tmem_st16(G.tm + TM_AH, pk0);
+            tmem_st16(G.tm + TM_AH + 16u, pk);
+        } else {
+            tmem_st16(G.tm + TM_AH + (uint32_t)(c * 16), pk);
+        }
     }
+    G.phase ^= 1u;
     return s;
 }
 
 // views_linear epilogue: softplus2(acc[0..63]) . rgb_linear -> sigmoid
-__device__ __forceinline__ void epi_views(const Group &G, float (&rgb)[3]) {
+__device__ __forceinline__ void epi_views(Group &G, float (&rgb)[3]) {
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
     uint32_t va[32], vb[32];
+    wait_half(G, 0);
+    wait_half(G, 1);
+    G.phase ^= 1u;
     acc_ld(G, 0, va);
     tmem_ld_wait();
     acc_ld(G, 32, vb);
@@ -319,31 +351,31 @@ __device__ __forceinline__ void epi_views(const Group &G, float (&rgb)[3]) {
 // (sigma, r, g, b).  ONE out-of-line copy for every caller; an odd number of layers either way, so the caller flips
 // G.phase once.
 __device__ __noinline__ float4 mlp128(Group G, bool fine) {
-    // pts_linears.0: K = 32 (27 features + the ones slot), N = 128
-    run_layer(G, [&] { issue_gemm(G, TM_AX, 2, OW0, 16384, 128, false); });
+    // pts_linears.0: K = 32 (27 features + the ones slot), N = 128 in two column halves
+    start_layer(G, true, [&](int h) { issue_gemm(G, TM_AX, 2, OW0, 16384, 64, false, 64 * h); });
     epi_hidden<false, true>(G);
     // pts_linears.1: K = 128 (+ bias through the constant tile)
-    run_layer(G, [&] {
-        issue_gemm(G, TM_AH, 8, OW1, 16384, 128, false);
-        issue_gemm(G, TM_AC, 1, OWB, 16384, 128, true);
+    start_layer(G, true, [&](int h) {
+        issue_gemm(G, TM_AH, 8, OW1, 16384, 64, false, 64 * h);
+        issue_gemm(G, TM_AC, 1, OWB, 16384, 64, true, 64 * h);
     });
     epi_hidden<false, true>(G);
     // pts_linears.2 on cat([x, h1])
-    run_layer(G, [&] {
-        issue_gemm(G, TM_AX, 2, OW2X, 16384, 128, false);
-        issue_gemm(G, TM_AH, 8, OW2H, 16384, 128, true);
+    start_layer(G, true, [&](int h) {
+        issue_gemm(G, TM_AX, 2, OW2X, 16384, 64, false, 64 * h);
+        issue_gemm(G, TM_AH, 8, OW2H, 16384, 64, true, 64 * h);
     });
     float4 out;
     out.x = epi_hidden<true, true>(G) + lds_f32(G.fb + 4u * FB_BA);
     out.y = out.z = out.w = 0.f;
     if (fine) {
         // feature_linear (no activation), then views_linear on [feature | 1 | pe(d)]
-        run_layer(G, [&] {
-            issue_gemm(G, TM_AH, 8, OWF, 16384, 128, false);
-            issue_gemm(G, TM_AC, 1, OWB + 32, 16384, 128, true);
+        start_layer(G, true, [&](int h) {
+            issue_gemm(G, TM_AH, 8, OWF, 16384, 64, false, 64 * h);
+            issue_gemm(G, TM_AC, 1, OWB + 32, 16384, 64, true, 64 * h);
         });
         epi_hidden<false, false>(G);
-        run_layer(G, [&] {
+        start_layer(G, false, [&](int) {
             issue_gemm(G, TM_AH, 8, OWV, 8192, 64, false);
             issue_gemm(G, TM_AC, 2, OWVP, 8192, 64, true);
         });
@@ -385,7 +417,7 @@ __device__ __forceinline__ float group_sum(const Group &G, float v, int slot) {
 
 __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     extern __shared__ __align__(16) uint8_t smraw5[];
-    __shared__ __align__(8) uint64_t mbars[GROUPS];
+    __shared__ __align__(8) uint64_t mbars[2 * GROUPS];      // per group: column half 0 / half 1 of the layer in flight
     __shared__ uint32_t tmem_slot;
     __shared__ float bnd[8];
     const uint32_t base = (smem_u32(smraw5) + 1023u) & ~1023u;
@@ -400,7 +432,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     if (tid < 6) bnd[tid] = a.bounds_dev ? __ldg(a.bounds_dev + tid) : a.bounds[tid];
     if (tid < 32) {
         if (tid == 0) {
-            for (int g = 0; g < GROUPS; ++g) mbar_init(smem_u32(&mbars[g]), 1);
+            for (int g = 0; g < 2 * GROUPS; ++g) mbar_init(smem_u32(&mbars[g]), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -420,7 +452,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     G.lane = tid & 31;
     G.tm_cols = tmem_slot + (uint32_t)G.g * TM_GROUP;
     G.tm = G.tm_cols + ((uint32_t)(G.warp * 32) << 16);
-    G.mbar = smem_u32(&mbars[G.g]);
+    G.mbar = smem_u32(&mbars[2 * G.g]);
     G.phase = 0;
     G.w_smem = base;
     G.fb = base + W_BYTES;
@@ -431,6 +463,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     const uint32_t tg4 = 4u * (uint32_t)tg;
 
     const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    G.prof = prof ? a.prof : nullptr;
     long long tp = prof ? clock64() : 0;
     const long long tp0 = tp;
 #define RPROF(slot)                                                        \

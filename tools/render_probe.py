@@ -23,5 +23,5 @@ hook(None)
 p = prof.cpu().tolist()
 per_cta = 262144 // 148 + 1
 rays = 2 * (per_cta // 2 if precision == "fp16" else per_cta)      # warm-up launch + 1 timed launch; tc5: 2 groups share a CTA's rays
-names = ["setup", "gather", "mlp", "resample+sort", "composite", "total"]
+names = ["setup", "gather", "mlp", "resample+sort", "composite", "total", "mlp:barrier+issue", "mlp:wait_mma"]
 print({n: round(v / rays) for n, v in zip(names, p)}, "cycles per ray (CTA 0%s)" % (", group 0" if precision == "fp16" else ""))

@@ -97,6 +97,7 @@ CONV_OUT_F16 = 8
 CONV_SPLIT3 = 16
 CONV_SPLIT2P = 32
 CONV_OUT_F16_SPLIT = 64
+CONV_SPLIT2A = 128
 OP_TF32, OP_SCALED, OP_SPLIT, OP_RAW_SHIFT = 1, 2, 4, 4
 
 _lib = None

@@ -145,10 +145,11 @@ static int launch_simt(const T *x, int ldx, const T *wpk, const float *bias, con
                        int flags, cudaStream_t stream) {
     ConvArgs<T> a;
     a.x = x; a.ldx = ldx; a.w = wpk; a.bias = bias; a.res = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.y_f16 = (flags & HL_CONV_OUT_F16_SPLIT) ? 2 : (flags & HL_CONV_OUT_F16) ? 1 : 0;
-    a.npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & HL_CONV_SPLIT2P) ? 2 : 1;
+    a.npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & (HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) ? 2 : 1;
     for (int q = 0; q < 3; ++q) { a.a_off[q] = 0; a.b_slab[q] = 0; }
     if (a.npass == 3) { a.a_off[1] = Cin; a.b_slab[2] = 1; }
-    if (a.npass == 2) a.b_slab[1] = 1;
+    if (flags & HL_CONV_SPLIT2P) a.b_slab[1] = 1;
+    if (flags & HL_CONV_SPLIT2A) a.a_off[1] = Cin;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = hl_conv_cout_pad(Cout);
     a.ksize = ksize; a.stride = stride; a.ups = (flags & HL_CONV_UPSAMPLE2X) ? 1 : 0;
     a.Hi = a.ups ? 2 * H : H;

@@ -1131,8 +1131,8 @@ bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, 
     if (x_dtype == HL_DT_F32 && !(flags & HL_CONV_TF32)) return false;
     const int esz = x_dtype == HL_DT_F16 ? 2 : 4;
     if ((ldx * esz) % 16 || Cin > ldx || ldy % ((flags & (HL_CONV_OUT_F16 | HL_CONV_OUT_F16_SPLIT)) ? 8 : 4)) return false;
-    if ((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) && x_dtype != HL_DT_F16) return false;
-    if ((flags & HL_CONV_SPLIT3) && ldx < 2 * Cin) return false;
+    if ((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) && x_dtype != HL_DT_F16) return false;
+    if ((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2A)) && ldx < 2 * Cin) return false;
     Plan pl = {};
     if (!make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, false, false,
                    &pl))
@@ -1157,12 +1157,14 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     const int H = Hin / stride, W = Win / stride;
     // hi + lo operand passes (HL_CONV_SPLIT3: x = [hi | lo] with lo at channel Cin, weights {W_hi, W_lo}: hi.hi +
     // lo.hi + hi.lo; HL_CONV_SPLIT2P: hi and lo packed inside the Cin channels, weights {[W_hi | W_hi], [W_lo | 0]})
-    const int npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & HL_CONV_SPLIT2P) ? 2 : 1;
-    const int nslab = npass > 1 ? 2 : 1;
+    // HL_CONV_SPLIT2A: x = [hi | lo] as SPLIT3, one weight slab: hi.W + lo.W (the activation pair only)
+    const int npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & (HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) ? 2 : 1;
+    const int nslab = (flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) ? 2 : 1;
     Plan pl = {};
     HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl, npass));
     if (npass == 3) { pl.p.a_off[1] = Cin; pl.p.b_slab[2] = 1; }
-    if (npass == 2) pl.p.b_slab[1] = 1;
+    if (flags & HL_CONV_SPLIT2P) pl.p.b_slab[1] = 1;
+    if (flags & HL_CONV_SPLIT2A) pl.p.a_off[1] = Cin;
     HL_CHECK_ARG(npass == 1 || kind == 1);
     HL_CHECK_ARG(y_f16 != 2 || (Cout % 32 == 0 && ldy >= 2 * Cout));
     HL_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpk & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
@@ -1210,7 +1212,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
 
     CUtensorMap tmA, tmB, tmY, tmR;
     {
-        cuuint64_t gdim[4] = {(cuuint64_t)(npass == 3 ? 2 * Cin : Cin), (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+        cuuint64_t gdim[4] = {(cuuint64_t)((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2A)) ? 2 * Cin : Cin), (cuuint64_t)Win,
+                              (cuuint64_t)Hin, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)Win * ldx * esz,
                               (cuuint64_t)Hin * Win * ldx * esz};
         cuuint32_t box[4], estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -1330,8 +1333,8 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
         return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y,
                             (flags & HL_CONV_OUT_F16_SPLIT) ? 2 : (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, stats,
                             stats_ld, B, H, W, Cin, Cout, ksize, stride, flags, (cudaStream_t)stream);
-    HL_CHECK_ARG(!(flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) || x_dtype == HL_DT_F16);
-    HL_CHECK_ARG(!(flags & HL_CONV_SPLIT3) || ldx >= 2 * Cin);
+    HL_CHECK_ARG(!(flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) || x_dtype == HL_DT_F16);
+    HL_CHECK_ARG(!(flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2A)) || ldx >= 2 * Cin);
     HL_CHECK_ARG(!(flags & HL_CONV_OUT_F16_SPLIT) || ldy >= 2 * Cout);
     int rc = hl_conv2d_simt(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, B, H, W, Cin, Cout, ksize, stride,
                             flags, (cudaStream_t)stream);

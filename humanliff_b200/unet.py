@@ -60,8 +60,8 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
     fp32 or exact fp32) + padded fp32 bias.  One-time host-side re-layout at load time.
 
     ``mode`` (fp16 only; the high-precision operand passes of DESIGN.md 3, HL_CONV_SPLIT3 / SPLIT2P in the header):
-    ``"scaled"`` weights * 2^4; ``"split"`` / ``"split_unscaled"`` two slabs ``{W_hi, W_lo}`` of the (scaled) weights,
-    ``W_lo = fp16(W - W_hi)``; ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
+    ``"scaled"`` weights * 2^4; ``"split"`` two slabs ``{W_hi, W_lo}`` of the scaled weights, ``W_lo = fp16(W - W_hi)``;
+    ``"split_a"`` plain weights for an operand that is an (unscaled) hi | lo pair; ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
     an operand row ``[hi(Cin) 0.. | lo(Cin) 0..]`` with the lo half at channel Cin_pad / 2."""
     lib = _lib.load()
     device = device if device is not None else weight.device
@@ -77,7 +77,7 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
         if mode in ("scaled", "split"):
             pk = pk * HP_SCALE
         hi = pk.to(torch.float16)          # round-to-nearest-even, as cvt.rn.f16.f32
-        if mode in ("split", "split_unscaled", "split_packed"):
+        if mode in ("split", "split_packed"):
             lo = (pk - hi.float()).to(torch.float16)
             if mode == "split_packed":
                 half = cin_pad // 2
@@ -89,7 +89,7 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
             else:
                 pk = torch.cat([hi, lo], 0)
         else:
-            assert mode in (None, "scaled"), mode
+            assert mode in (None, "scaled", "split_a"), mode
             pk = hi
     elif precision == "tf32":
         flat = pk.view(-1, 4)
@@ -105,14 +105,14 @@ def _hp_mode(name, cin, cin_pad):
     """Which convs of the fp16 plan run the high-precision operand passes: the ones that read the RAW
     residual stream -- 1x1 skip, ControlNet projection, Downsample, stem -- and the output conv carry hi + lo fp16
     pairs (error budget: tools/error_budget.py); the Upsample conv reads a 2^-4-scaled operand (range only)."""
-    if name.endswith("skip_connection") or name.startswith("input_blocks_proj_cond.") or name.endswith(".op"):
+    if name.endswith("skip_connection") or name.startswith("input_blocks_proj_cond."):
         return "split"
     if name == "out.2":
-        return "split_unscaled"
+        return "split_a"          # activation pair only: N = 27 runs the tensor core at 20 %, a third pass costs 0.13 ms
     if name in ("input_blocks.0.0", "input_blocks_cond.0.0"):
         return "split_packed" if 2 * cin <= cin_pad else None
-    if name.endswith(".conv"):
-        return "scaled"
+    if name.endswith(".conv") or name.endswith(".op"):
+        return "scaled"           # Upsample / Downsample convs: range only (3 % of the error variance, tools/error_budget.py)
     return None
 
 
@@ -468,8 +468,11 @@ class _StepPlan:
         if dst.f16:
             assert st is None
             flags |= _lib.CONV_OUT_F16_SPLIT if dst.f16 == 2 else _lib.CONV_OUT_F16
-        if c.hp in ("split", "split_unscaled"):
+        if c.hp == "split":
             flags |= _lib.CONV_SPLIT3          # x_ptr = [hi(Cin) | lo(Cin)] rows, weights {W_hi, W_lo}
+            assert ldx >= 2 * c.cin_pad
+        elif c.hp == "split_a":
+            flags |= _lib.CONV_SPLIT2A         # x_ptr = [hi | lo] rows, one weight slab
             assert ldx >= 2 * c.cin_pad
         elif c.hp == "split_packed":
             flags |= _lib.CONV_SPLIT2P
@@ -739,7 +742,7 @@ class _StepPlan:
 
         # --- out: GN -> SiLU -> conv3x3 (unet.py:471-475,612) ---
         act = _ptr(self.scratch("act", self.max_act, op=True))
-        ldo, omode = (2 * x.C, _lib.OP_SPLIT) if m._convs["out.2"].hp == "split_unscaled" else (x.C, 0)
+        ldo, omode = (2 * x.C, _lib.OP_SPLIT) if m._convs["out.2"].hp == "split_a" else (x.C, 0)
         assert B * H * W * ldo <= self.max_act
         self.gn("out.0", x, act, ldo, True, out_mode=omode)
         co_pad = 32 * ((m.out_channels + 31) // 32)

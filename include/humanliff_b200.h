@@ -64,6 +64,8 @@ extern "C" {
                                   [2*taps][Cout_pad][Cin]:  y = x_hi.W_hi + x_lo.W_hi + x_hi.W_lo          */
 #define HL_CONV_SPLIT2P 32     /* hi and lo packed INSIDE the Cin channels (stem: [hi(27) 0(5) | lo(27) 0(5)]),
                                   w = {[W_hi | W_hi], [W_lo | 0]}:  two passes                              */
+#define HL_CONV_SPLIT2A 128    /* x = [hi(Cin) | lo(Cin)] as SPLIT3, ONE weight slab: y = x_hi.W + x_lo.W (the
+                                  activation pair only: the output conv, whose N = 27 makes a third pass dear)  */
 #define HL_CONV_OUT_F16_SPLIT 64  /* y = [hi(Cout) | lo(Cout)] fp16 of (result * 2^-4) (ldy >= 2 Cout,
                                   Cout % 32 == 0): the operand of a following HL_CONV_SPLIT3 conv           */
 

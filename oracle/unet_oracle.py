@@ -80,13 +80,15 @@ class _Numerics:
 def product_fp16_plan(prefix):
     """Per-layer policy emulating the product's ``precision="fp16"`` plan: every contraction rounds
     its operands to fp16 except the convs that read the raw residual stream (1x1 skip, ControlNet projection,
-    Downsample), the stems and the output conv, which carry hi + lo fp16 pairs in three tensor-core passes; the
-    Upsample conv reads a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
+    the stems), which carry hi + lo fp16 pairs for both operands in three tensor-core passes, and the output conv
+    (activation pair only, two passes); the Upsample / Downsample convs read a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
     import re
-    if (prefix.endswith("skip_connection") or prefix.startswith("input_blocks_proj_cond.") or prefix.endswith(".op")
-            or prefix == "out.2" or re.fullmatch(r"input_blocks(_cond)?\.0\.0", prefix)):
+    if (prefix.endswith("skip_connection") or prefix.startswith("input_blocks_proj_cond.")
+            or re.fullmatch(r"input_blocks(_cond)?\.0\.0", prefix)):
         return "fp16_split3"
-    if prefix.endswith(".conv"):
+    if prefix == "out.2":
+        return "fp16_split2a"                    # activation pair only (weights plain fp16)
+    if prefix.endswith(".conv") or prefix.endswith(".op"):
         return "fp16_scaled"
     return "fp16"
 
@@ -111,6 +113,10 @@ def _conv(x, sd, prefix, nm, stride=1, raw=False):
     w = sd[prefix + ".weight"]
     pad = w.shape[-1] // 2
     nm = nm.at(prefix)
+    if nm.mode == "fp16_split2a":
+        f16 = lambda t: t.to(torch.float16).to(torch.float32)
+        xh = f16(x)
+        return F.conv2d(xh + f16(x - xh), f16(w), sd[prefix + ".bias"], stride=stride, padding=pad)
     if nm.mode == "fp16_split3":
         # the product's high-precision conv: activations * 2^-4 and weights * 2^4 each carried as an fp16 hi + lo
         # pair, three tensor-core passes hi.hi + lo.hi + hi.lo (the lo.lo term, 2^-22 relative, is dropped)

@@ -166,6 +166,9 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
     if flags & 16:        # HL_CONV_SPLIT3: x = [hi | lo], w = {W_hi, W_lo}: hi.hi + lo.hi + hi.lo
         assert x_dtype == 1 and ldx >= 2 * Cin
         out = cv(xop(0), wslab(0)) + cv(xop(Cin), wslab(0)) + cv(xop(0), wslab(1))
+    elif flags & 128:     # HL_CONV_SPLIT2A: x = [hi | lo], one weight slab: hi.W + lo.W
+        assert x_dtype == 1 and ldx >= 2 * Cin
+        out = cv(xop(0), wslab(0)) + cv(xop(Cin), wslab(0))
     elif flags & 32:      # HL_CONV_SPLIT2P: hi and lo packed inside the Cin channels, w = {[W_hi | W_hi], [W_lo | 0]}
         out = cv(xop(0), wslab(0)) + cv(xop(0), wslab(1))
     else:

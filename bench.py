@@ -678,6 +678,8 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: ONE JSON line is the contract
         dist.init_process_group("nccl", device_id=device)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     peaks = measured_peaks()

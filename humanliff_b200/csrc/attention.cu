@@ -396,6 +396,9 @@ int launch_mma(const void *qkv, int qkv_f16, int ldq, __half *out, int ldo, int 
 
 }  // namespace
 
+bool hl_attention_tc5_applicable(const void *qkv, int ldq, const void *out, int ldo, int T, int ch);
+int hl_attention_tc5(const void *qkv, int ldq, void *out, int ldo, int B, int T, int C, int heads, cudaStream_t stream);
+
 extern "C" int hl_attention(const void *qkv, int qkv_dtype, int ldq, void *out, int out_dtype, int ldo, int B, int T,
                             int C, int heads, int round_tf32, void *stream) {
     HL_CHECK_ARG(qkv && out && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0);
@@ -406,6 +409,9 @@ extern "C" int hl_attention(const void *qkv, int qkv_dtype, int ldq, void *out, 
     if (out_dtype == HL_DT_F16 && !(round_tf32 & 2) && ldo % 2 == 0 && ((uintptr_t)out & 3) == 0 &&
         (!qf16 || ((uintptr_t)qkv & 15) == 0)) {
         __half *oh = (__half *)out;
+        // fp16 in / out: the tcgen05 kernel (attention_tc5.cu) where it tiles the shape, else the mma.sync kernel
+        if (qf16 && !(round_tf32 & 4) && hl_attention_tc5_applicable(qkv, ldq, out, ldo, T, ch))
+            return hl_attention_tc5(qkv, ldq, out, ldo, B, T, C, heads, st);
         switch (ch) {
             case 32: return launch_mma<32>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);
             case 64: return launch_mma<64>(qkv, qf16, ldq, oh, ldo, B, T, heads, st);

@@ -196,8 +196,10 @@ int64_t hl_launch_count(void);
  * out[b, t, head*ch + c] = sum_s softmax_s( q_t.k_s / sqrt(ch) ) v_s[c], written as an operand
  * (out_dtype) for the proj_out GEMM.  With an fp16 output both contractions run on the tensor
  * cores (q, k, v, softmax weights rounded to fp16; scores / softmax / accumulation fp32); an fp32
- * output selects the exact CUDA-core kernel.  round_tf32: bit 0 = TF32-round an fp32 output,
- * bit 1 = force the CUDA-core kernel (tests).                                                     */
+ * output selects the exact CUDA-core kernel.  fp16 qkv AND output with T % 64 == 0 and a head width of 64 / 96 /
+ * 128 / 192 run on the tcgen05 kernel (S and O accumulators and the softmax weights in tensor memory, Q / K / V
+ * tiles by TMA; attention_tc5.cu).  round_tf32: bit 0 = TF32-round an fp32 output, bit 1 = force the CUDA-core
+ * kernel, bit 2 = force the mma.sync kernel where the tcgen05 one would run (tests).              */
 int hl_attention(const void *qkv, int qkv_dtype, int ldq, void *out, int out_dtype, int ldo, int B, int T, int C,
                  int heads, int round_tf32, void *stream);
 

@@ -393,11 +393,43 @@ def test_attention(dev, B, T, C, heads):
     assert not torch.isnan(outm.float()).any()
     assert rel_l2(outm.float().permute(0, 2, 1), refh) < 6e-4      # P and the output rounded to fp16
     assert rel_l2(outm.float().permute(0, 2, 1), ref) < 2e-3
-    # fp16 qkv (as written by a HL_CONV_OUT_F16 conv): cp.async double-buffered variant, same arithmetic
+    # fp16 qkv (as written by a HL_CONV_OUT_F16 conv): cp.async double-buffered mma.sync variant, same arithmetic
+    # (flag 4 keeps the call on the mma.sync kernel where the tcgen05 kernel would serve the shape)
     qh16 = qd.half()
     outf = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
-    _call("hl_attention", qh16.data_ptr(), 1, 3 * C, outf.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", qh16.data_ptr(), 1, 3 * C, outf.data_ptr(), 1, C, B, T, C, heads, 4, _stream())
     assert torch.equal(outf.cpu(), outm.cpu())
+
+
+@pytest.mark.parametrize("B,T,C,heads", [(4, 1024, 384, 4), (4, 256, 768, 4), (4, 64, 768, 4),      # the production blocks
+                                         (2, 128, 256, 4), (1, 192, 512, 4), (3, 64, 192, 2)])
+def test_attention_tcgen05(dev, B, T, C, heads):
+    """The tcgen05 / TMEM / TMA attention kernel (fp16 qkv and output, T % 64 == 0): against fp32 attention on the
+    fp16-rounded q, k, v (isolates the kernel from the operand rounding), against the exact result, and against the
+    mma.sync kernel on the same operands."""
+    g = torch.Generator().manual_seed(T + C)
+    qkv = torch.randn(B, 3 * C, T, generator=g)
+    ch = C // heads
+    r = qkv.reshape(B * heads, 3 * ch, T)
+    q, k, v = torch.split(r, ch, dim=1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), -1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
+    rh = qkv.half().float().reshape(B * heads, 3 * ch, T)
+    qh, kh, vh = torch.split(rh, ch, dim=1)
+    wh = torch.softmax(torch.einsum("bct,bcs->bts", qh, kh) / math.sqrt(ch), -1)
+    refh = torch.einsum("bts,bcs->bct", wh, vh).reshape(B, C, T)
+    q16 = qkv.permute(0, 2, 1).contiguous().to(dev).half()               # [B, T, 3C] head-major channels
+    out5 = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
+    outm = torch.full((B, T, C), float("nan"), device=dev, dtype=torch.float16)
+    _call("hl_attention", q16.data_ptr(), 1, 3 * C, out5.data_ptr(), 1, C, B, T, C, heads, 0, _stream())
+    _call("hl_attention", q16.data_ptr(), 1, 3 * C, outm.data_ptr(), 1, C, B, T, C, heads, 4, _stream())
+    torch.cuda.synchronize()
+    assert not torch.isnan(out5.float()).any()
+    o5, om = out5.float().permute(0, 2, 1), outm.float().permute(0, 2, 1)
+    assert rel_l2(o5, refh) < 6e-4, rel_l2(o5, refh)
+    assert rel_l2(o5, ref) < 2e-3
+    assert rel_l2(o5, om) < 6e-4, rel_l2(o5, om)
 
 
 def test_ddpm_step_bit_exact(dev):

@@ -32,6 +32,7 @@ SIGNATURES = {
     "hl_timestep_embedding": (c_int, [c_p, c_p, c_int, c_int, c_p, c_p]),
     "hl_linear_small": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_int, c_p]),
+    "hl_gn_set_tuning": (c_int, [c_int]),
     "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_p, c_int,
                             c_int, c_int, c_int, c_int, c_f, c_int, c_int, c_p]),
     "hl_conv_cout_pad": (c_int, [c_int]),
@@ -98,7 +99,7 @@ CONV_SPLIT3 = 16
 CONV_SPLIT2P = 32
 CONV_OUT_F16_SPLIT = 64
 CONV_SPLIT2A = 128
-OP_TF32, OP_SCALED, OP_SPLIT, OP_RAW_SHIFT = 1, 2, 4, 4
+OP_TF32, OP_SCALED, OP_SPLIT, OP_RAW_SHIFT, OP_X_F16 = 1, 2, 4, 4, 8
 
 _lib = None
 launch_count = 0   # number of C-ABI compute calls issued (each is >= 1 kernel launch)

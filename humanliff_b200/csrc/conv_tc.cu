@@ -611,16 +611,33 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // group, and only then added (one uncontended fp64 atomic per channel) to the CTA totals
                         const int col = et & 31, rq = et >> 5;
                         float s = 0.f, ss = 0.f;
+                        if (!p.y_f16) {
 #pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            const int rr = rq * 32 + r;
-                            const uint32_t addr = sbuf + (uint32_t)rr * 128u +
-                                                  ((((uint32_t)col >> 2) ^ (uint32_t)(rr & 7)) << 4) +
-                                                  (((uint32_t)col & 3u) << 2);
-                            float x;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
-                            s += x;
-                            ss = fmaf(x, x, ss);
+                            for (int r = 0; r < 32; ++r) {
+                                const int rr = rq * 32 + r;
+                                const uint32_t addr = sbuf + (uint32_t)rr * 128u +
+                                                      ((((uint32_t)col >> 2) ^ (uint32_t)(rr & 7)) << 4) +
+                                                      (((uint32_t)col & 3u) << 2);
+                                float x;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+                                s += x;
+                                ss = fmaf(x, x, ss);
+                            }
+                        } else {
+                            // fp16 tile ([128 rows][64 B], SWIZZLE_64B pattern): the statistics of the ROUNDED values,
+                            // i.e. of the tensor the following GroupNorm actually reads
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                const int rr = rq * 32 + r;
+                                const uint32_t addr = sbuf + (uint32_t)rr * 64u +
+                                                      ((((uint32_t)col >> 3) ^ (((uint32_t)rr >> 1) & 3u)) << 4) +
+                                                      (((uint32_t)col & 7u) << 1);
+                                unsigned short hb;
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hb) : "r"(addr));
+                                const float x = __half2float(__ushort_as_half(hb));
+                                s += x;
+                                ss = fmaf(x, x, ss);
+                            }
                         }
                         spart[eg][rq][col] = make_float2(s, ss);
                         named_bar(4 + eg, EPI_THREADS);
@@ -664,13 +681,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // (hl_conv_set_workspace) the K loop is cut into S slices run by S x as many CTAs, every slice stores its
 // fp32 partial tile into ws[s][B*H*W][cout_pad], and this kernel adds the slices in a FIXED order
 // (deterministic), then bias, residual, the per-channel GroupNorm statistics and the output rounding
-// exactly as the one-pass epilogue does.  One block = 32 channels of one sample (no contended atomics).
+// exactly as the one-pass epilogue does.  One block = 32 channels of one pixel slab of one sample.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__ ws, int S, int64_t slice, int ldw,
                                                        const float *__restrict__ bias,
                                                        const float *__restrict__ res, int ldr, void *__restrict__ y,
                                                        int y_f16, int ldy, double *__restrict__ stats, int stats_ld,
-                                                       int HW, int Cout) {
+                                                       int HW, int Cout, int slab) {
     hl_pdl_enter();
     // block = (32-channel group, sample); warp w, lane = (pixel lane pl, channel quad q): a warp reads 4 pixels x 128 B
     __shared__ double red[8][8][8];
@@ -682,7 +699,9 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
     if (live) {
         const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + c));
 #pragma unroll 2
-        for (int pp = warp * 4 + pl; pp < HW; pp += 32) {
+        // blockIdx.z = pixel slab of the sample (B = 1 at 32^2 would otherwise run 12 blocks of 32 serial rounds)
+        const int pend = min(HW, ((int)blockIdx.z + 1) * slab);
+        for (int pp = (int)blockIdx.z * slab + warp * 4 + pl; pp < pend; pp += 32) {
             const int64_t m = (int64_t)b * HW + pp;
             const float *src = ws + m * ldw + c;
             float4 a = __ldcs(reinterpret_cast<const float4 *>(src));
@@ -710,6 +729,9 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
                     w.x = *reinterpret_cast<const uint32_t *>(&l0);
                     w.y = *reinterpret_cast<const uint32_t *>(&l1);
                     *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + m * ldy + Cout + c) = w;
+                } else {
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);     // statistics of the rounded tensor
+                    a = make_float4(f0.x, f0.y, f1.x, f1.y);
                 }
             } else {
                 *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + m * ldy + c) = a;
@@ -739,7 +761,7 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) t += red[w][qq][v];
-            atomicAdd(stats + ((size_t)b * stats_ld + cc) * 2 + (v >> 2), t);    // the only writer of this row
+            atomicAdd(stats + ((size_t)b * stats_ld + cc) * 2 + (v >> 2), t);    // fp64: slab order perturbs at 1e-16
         }
     }
 }
@@ -1140,7 +1162,7 @@ bool hl_conv_tc_applicable(int x_dtype, int B, int H, int W, int Cin, int Cout, 
     return get_encode() != nullptr;
 }
 
-int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
+int hl_gn_stats_launch(const void *x, int x_f16, int ldx, int B, int HW, int C, double *stats, int stats_ld,
                        cudaStream_t stream);
 
 int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
@@ -1173,7 +1195,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     TcParams &p = pl.p;
     p.bias = bias;
     p.y_f16 = y_f16;
-    HL_CHECK_ARG(!(y_f16 && stats));
+    HL_CHECK_ARG(!(y_f16 == 2 && stats));
     bool epi_stats = plan_epi_stats(pl, stats != nullptr);
 
     // split-K (see choose_split / k_splitk_reduce)
@@ -1295,13 +1317,17 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     HL_CHECK_LAUNCH();
     if (S > 1) {
         const int HW = H * W;
-        dim3 grid(hl_cdiv(Cout, 32), B);
+        // pixel slabs (multiples of 32 pixels) until the grid covers the SMs about twice
+        int slabs = 1;
+        while (hl_cdiv(Cout, 32) * B * slabs < 2 * hl_num_sms() && HW / (2 * slabs) >= 64) slabs *= 2;
+        const int slab = hl_cdiv(hl_cdiv(HW, slabs), 32) * 32;
+        dim3 grid(hl_cdiv(Cout, 32), B, hl_cdiv(HW, slab));
         HL_CHECK_CUDA(hl_launch(k_splitk_reduce, grid, dim3(256), 0, stream, (const float *)wsp->ptr, S,
                                 (int64_t)split_batch(pl, B) * HW * pl.cout_pad, pl.cout_pad, bias, residual, ldr, (void *)y_final,
-                                yf16_final, ldy_final, stats, stats_ld, HW, Cout));
+                                yf16_final, ldy_final, stats, stats_ld, HW, Cout, slab));
         return HL_OK;
     }
-    if (stats && !epi_stats) return hl_gn_stats_launch((const float *)y, ldy, B, H * W, Cout, stats, stats_ld, stream);
+    if (stats && !epi_stats) return hl_gn_stats_launch(y, y_f16, ldy, B, H * W, Cout, stats, stats_ld, stream);
     return HL_OK;
 }
 
@@ -1328,7 +1354,7 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
     HL_CHECK_ARG(ldx >= Cin && ldy >= Cout && (!residual || ldr >= Cout));
     HL_CHECK_ARG(!((flags & HL_CONV_UPSAMPLE2X) && stride != 1));
     HL_CHECK_ARG(!stats || stats_ld >= Cout);
-    HL_CHECK_ARG(!((flags & (HL_CONV_OUT_F16 | HL_CONV_OUT_F16_SPLIT)) && stats));    // statistics are defined on fp32 results only
+    HL_CHECK_ARG(!((flags & HL_CONV_OUT_F16_SPLIT) && stats));    // no statistics of a scaled hi | lo pair
     if (hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags))
         return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y,
                             (flags & HL_CONV_OUT_F16_SPLIT) ? 2 : (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, stats,
@@ -1342,5 +1368,5 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
     const int ups = (flags & HL_CONV_UPSAMPLE2X) ? 2 : 1;
     const int pad = ksize / 2;
     const int Ho = (H * ups + 2 * pad - ksize) / stride + 1, Wo = (W * ups + 2 * pad - ksize) / stride + 1;
-    return hl_gn_stats_launch((const float *)y, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
+    return hl_gn_stats_launch(y, (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
 }

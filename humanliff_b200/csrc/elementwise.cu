@@ -401,7 +401,16 @@ extern "C" int hl_linear_small(const float *x, const float *W, const float *bias
 // fp64 accumulators (fp64 atomics: arrival order changes the result far below fp32 resolution).
 // ------------------------------------------------------------------------------------------
 #define GN_MAX_C 2048
-__global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, int pix_per_block,
+// four consecutive channels of an fp32 tensor or of an fp16 tensor (HL_CONV_OUT_F16 results) as floats
+__device__ __forceinline__ float4 load_quad(const void *x, int64_t idx, bool f16) {
+    if (!f16) return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(x) + idx);
+    const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(x) + idx);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void k_gn_stats(const void *__restrict__ x, int x_f16, int ldx, int HW, int C, int pix_per_block,
                            double *__restrict__ stats, int stats_ld) {
     hl_pdl_enter();
     __shared__ double s_sum[GN_MAX_C];   // fp64: atomics then commute to ~1e-16 -> reproducible statistics
@@ -416,9 +425,9 @@ __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, 
     int p1 = min(HW, p0 + pix_per_block);
     float4 s = make_float4(0, 0, 0, 0), ss = make_float4(0, 0, 0, 0);
     if (tp < lanes_p) {
-        const float *base = x + (int64_t)b * HW * ldx + 4 * tq;
+        const int64_t base = (int64_t)b * HW * ldx + 4 * tq;
         for (int p = p0 + tp; p < p1; p += lanes_p) {
-            float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)p * ldx);
+            float4 v = load_quad(x, base + (int64_t)p * ldx, x_f16 != 0);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y);
             ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
@@ -436,7 +445,7 @@ __global__ void k_gn_stats(const float *__restrict__ x, int ldx, int HW, int C, 
     }
 }
 
-int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
+int hl_gn_stats_launch(const void *x, int x_f16, int ldx, int B, int HW, int C, double *stats, int stats_ld,
                        cudaStream_t stream) {
     HL_CHECK_ARG(x && stats && B > 0 && HW > 0 && C > 0 && C <= GN_MAX_C);
     HL_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && ldx >= C && stats_ld >= C);
@@ -451,36 +460,25 @@ int hl_gn_stats_launch(const float *x, int ldx, int B, int HW, int C, double *st
     int min_ppb = lanes_p * 8;
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    HL_CHECK_CUDA(hl_launch(k_gn_stats, dim3(grid), dim3(threads), 0, stream, x, ldx, HW, C, pix_per_block, stats, stats_ld));
+    HL_CHECK_CUDA(hl_launch(k_gn_stats, dim3(grid), dim3(threads), 0, stream, x, x_f16, ldx, HW, C, pix_per_block, stats, stats_ld));
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 extern "C" int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, int stats_ld,
                            void *stream) {
-    return hl_gn_stats_launch(x, ldx, B, HW, C, stats, stats_ld, (cudaStream_t)stream);
+    return hl_gn_stats_launch(x, 0, ldx, B, HW, C, stats, stats_ld, (cudaStream_t)stream);
 }
 
 // apply: y = act(x * A[b,c] + Bc[b,c]) where A, Bc fold mean/rstd/gamma/beta and the FiLM
 // scale/shift; A and Bc are built per block in shared memory from the per-channel fp64 sums.
-// Each thread walks (pixel, channel-quad) pairs with an incrementally updated index (no divisions
-// in the loop); loads are 128-bit, stores 64-bit (fp16 operand) or 128-bit (fp32 operand).
-__global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *__restrict__ stats,
-                           int stats_ld, const float *__restrict__ gamma, const float *__restrict__ beta,
-                           const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
-                           int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
-                           int silu, int op_mode, int pix_per_block, int oct) {
-    hl_pdl_enter();
-    // op_mode: bits 0-2 = HL_OP_* of y (lo offset of a split y in bits 8+), bits 4-6 = HL_OP_* of the raw copy (a
-    // split raw copy has its lo half at channel C)
-    const int round_tf32 = (op_mode & 7) | (op_mode & ~0xFF);
-    const int raw_mode = ((op_mode >> 4) & 7) | (C << 8);
-    __shared__ float sA[GN_MAX_C];
-    __shared__ float sB[GN_MAX_C];
-    __shared__ float gmean[64], grstd[64];
-    int b = blockIdx.y;
-    int cpg = C / groups;
-    double n = (double)HW * cpg;
+__device__ __forceinline__ void gn_coefficients(const double *__restrict__ stats, int stats_ld,
+                                                const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                const float *__restrict__ film, int film_ld, int b, int HW, int C,
+                                                int groups, float eps, float *sA, float *sB, float *gmean,
+                                                float *grstd) {
+    const int cpg = C / groups;
+    const double n = (double)HW * cpg;
     // group statistics: 8 lanes per group, independent loads, shuffle reduction (a serial loop over the
     // group's channels cost ~15 us of dependent L2 latency per launch on the small feature maps)
     for (int g0 = 0; g0 < groups; g0 += blockDim.x / 8) {
@@ -522,71 +520,142 @@ __global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *_
         sB[c] = be;
     }
     __syncthreads();
+}
+
+// Generic kernel (any dtype / operand mode; the fp32 and TF32 plans, odd channel counts): each thread walks
+// (pixel, channel-quad) pairs with an incrementally updated index (no divisions in the loop).
+__global__ void k_gn_apply(const float *__restrict__ x, int ldx, const double *__restrict__ stats,
+                           int stats_ld, const float *__restrict__ gamma, const float *__restrict__ beta,
+                           const float *__restrict__ film, int film_ld, void *__restrict__ y, int y_dtype,
+                           int ldy, void *__restrict__ raw, int ldraw, int HW, int C, int groups, float eps,
+                           int silu, int op_mode, int pix_per_block) {
+    hl_pdl_enter();
+    // op_mode: bits 0-2 = HL_OP_* of y (lo offset of a split y in bits 8+), bit 3 = HL_OP_X_F16, bits 4-6 = HL_OP_* of
+    // the raw copy (a split raw copy has its lo half at channel C)
+    const int y_mode = (op_mode & 7) | (op_mode & ~0xFF);
+    const int raw_mode = ((op_mode >> 4) & 7) | (C << 8);
+    const bool x_f16 = (op_mode & HL_OP_X_F16) != 0;       // x is an fp16 tensor (a conv's HL_CONV_OUT_F16 result)
+    __shared__ float sA[GN_MAX_C];
+    __shared__ float sB[GN_MAX_C];
+    __shared__ float gmean[64], grstd[64];
+    const int b = blockIdx.y;
+    gn_coefficients(stats, stats_ld, gamma, beta, film, film_ld, b, HW, C, groups, eps, sA, sB, gmean, grstd);
     const int p0 = blockIdx.x * pix_per_block;
     const int np = min(HW, p0 + pix_per_block) - p0;
     const int64_t pix0 = (int64_t)b * HW + p0;
-    if (oct) {
-        // fast path: a thread owns 8 fixed channels (coefficients in registers) and walks pixels with U rows in
-        // flight; 2 x 128-bit loads and one 128-bit (fp16) / two 128-bit (fp32) stores per 8 elements.  The
-        // first version of this loop (per-element index arithmetic, smem coefficients, IEEE reciprocal) was
-        // issue-bound at 53 % of the HBM roofline (ncu: warps stalled "not selected").
-        const int q8 = C >> 3;
-        const int lanes_p = blockDim.x / q8;
-        const int j8 = threadIdx.x % q8, tp = threadIdx.x / q8;
-        float ca[8], cb[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { ca[e] = sA[8 * j8 + e]; cb[e] = sB[8 * j8 + e]; }
-        const bool fast_silu = (y_dtype == HL_DT_F16) || (round_tf32 & HL_OP_TF32);
-        constexpr int U = 4;
-        for (int pb = tp; pb < np; pb += lanes_p * U) {
-            float4 v[U][2];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int pp = pb + u * lanes_p;
-                if (pp < np) {
-                    const float4 *src = reinterpret_cast<const float4 *>(x + (pix0 + pp) * ldx + 8 * j8);
-                    v[u][0] = __ldcs(src);
-                    v[u][1] = __ldcs(src + 1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int pp = pb + u * lanes_p;
-                if (pp >= np) break;
-                const float in[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    o[e] = fmaf(in[e], ca[e], cb[e]);
-                    if (silu) o[e] = fast_silu ? hl_silu_fast(o[e]) : hl_silu(o[e]);
-                }
-                const int64_t oidx = (pix0 + pp) * ldy + 8 * j8;
-                store_oct(y, y_dtype, oidx, make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]),
-                          round_tf32);
-                if (raw) store_oct(raw, y_dtype, (pix0 + pp) * ldraw + 8 * j8, v[u][0], v[u][1], raw_mode);
-            }
-        }
-        return;
-    }
+    const bool fast_silu = (y_dtype == HL_DT_F16) || (y_mode & HL_OP_TF32);
     const int q = C >> 2;
     const int dp = blockDim.x / q, dj = blockDim.x % q;
     int p = threadIdx.x / q, j = threadIdx.x % q;
     while (p < np) {
         const int64_t pix = pix0 + p;
-        const float4 v = *reinterpret_cast<const float4 *>(x + pix * ldx + 4 * j);
+        const float4 v = load_quad(x, pix * ldx + 4 * j, x_f16);
         const float4 a = *reinterpret_cast<const float4 *>(&sA[4 * j]);
         const float4 c = *reinterpret_cast<const float4 *>(&sB[4 * j]);
         float4 o;
         o.x = fmaf(v.x, a.x, c.x); o.y = fmaf(v.y, a.y, c.y);
         o.z = fmaf(v.z, a.z, c.z); o.w = fmaf(v.w, a.w, c.w);
-        if (silu) { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
-        store_quad(y, y_dtype, pix * ldy + 4 * j, o, round_tf32);
+        if (silu) {
+            if (fast_silu) { o.x = hl_silu_fast(o.x); o.y = hl_silu_fast(o.y); o.z = hl_silu_fast(o.z); o.w = hl_silu_fast(o.w); }
+            else { o.x = hl_silu(o.x); o.y = hl_silu(o.y); o.z = hl_silu(o.z); o.w = hl_silu(o.w); }
+        }
+        store_quad(y, y_dtype, pix * ldy + 4 * j, o, y_mode);
         if (raw) store_quad(raw, y_dtype, pix * ldraw + 4 * j, v, raw_mode);
         p += dp;
         j += dj;
         if (j >= q) { j -= q; ++p; }
     }
 }
+
+// The fp16 plan's kernel, specialised at compile time (the one-kernel-for-every-mode version was 7,200 SASS
+// instructions with every flag re-tested inside the unrolled loops: ncu showed instruction-fetch stalls of 2-3
+// issue slots per instruction).  y is a plain fp16 operand; XF16: the input is fp16; RAW: additionally the
+// 2^-4-scaled hi | lo copy of the input for a 1x1 skip conv (lo at channel C); YSPLIT: y itself is an unscaled
+// hi | lo pair with lo at channel C (the output conv's operand).  A thread owns 8 fixed channels (coefficients in
+// registers) and walks pixels with 8 x 16 B of loads in flight per round (fp32 input: 4 rows x two 128-bit loads;
+// fp16 input: 8 rows x one); the first round is issued BEFORE the statistics prologue, whose two dependent L2
+// round trips and barriers then hide under the first DRAM round trip.
+template <bool XF16, bool SILU, bool RAW, bool YSPLIT>
+__global__ void __launch_bounds__(256, 3)
+k_gn_apply_f16(const void *__restrict__ x, int ldx, const double *__restrict__ stats, int stats_ld,
+               const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ film,
+               int film_ld, __half *__restrict__ y, int ldy, __half *__restrict__ raw, int ldraw, int HW, int C,
+               int groups, float eps, int pix_per_block) {
+    hl_pdl_enter();
+    __shared__ float sA[GN_MAX_C];
+    __shared__ float sB[GN_MAX_C];
+    __shared__ float gmean[64], grstd[64];
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int np = min(HW, p0 + pix_per_block) - p0;
+    const int64_t pix0 = (int64_t)b * HW + p0;
+    const int q8 = C >> 3;
+    const int lanes_p = blockDim.x / q8;
+    const int j8 = threadIdx.x % q8, tp = threadIdx.x / q8;
+    constexpr int U = XF16 ? 8 : 4;
+    uint4 buf[8];
+    auto load_round = [&](int pb) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = pb + u * lanes_p;
+            if (pp < np) {
+                if (XF16) {
+                    buf[u] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(x) + (pix0 + pp) * ldx + 8 * j8));
+                } else {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(x) + (pix0 + pp) * ldx + 8 * j8);
+                    buf[2 * u] = __ldcs(src);
+                    buf[2 * u + 1] = __ldcs(src + 1);
+                }
+            }
+        }
+    };
+    if (tp < np) load_round(tp);
+    gn_coefficients(stats, stats_ld, gamma, beta, film, film_ld, b, HW, C, groups, eps, sA, sB, gmean, grstd);
+    float ca[8], cb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ca[e] = sA[8 * j8 + e]; cb[e] = sB[8 * j8 + e]; }
+    for (int pb = tp; pb < np;) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = pb + u * lanes_p;
+            if (pp >= np) break;
+            float in[8];
+            if (XF16) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&buf[u].x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&buf[u].y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&buf[u].z));
+                const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&buf[u].w));
+                in[0] = f0.x; in[1] = f0.y; in[2] = f1.x; in[3] = f1.y; in[4] = f2.x; in[5] = f2.y; in[6] = f3.x; in[7] = f3.y;
+            } else {
+                const float4 v0 = *reinterpret_cast<const float4 *>(&buf[2 * u]);
+                const float4 v1 = *reinterpret_cast<const float4 *>(&buf[2 * u + 1]);
+                in[0] = v0.x; in[1] = v0.y; in[2] = v0.z; in[3] = v0.w; in[4] = v1.x; in[5] = v1.y; in[6] = v1.z; in[7] = v1.w;
+            }
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                o[e] = fmaf(in[e], ca[e], cb[e]);
+                if (SILU) o[e] = hl_silu_fast(o[e]);
+            }
+            store_oct(y, HL_DT_F16, (pix0 + pp) * ldy + 8 * j8, make_float4(o[0], o[1], o[2], o[3]),
+                      make_float4(o[4], o[5], o[6], o[7]), YSPLIT ? (HL_OP_SPLIT | (C << 8)) : 0);
+            if (RAW && !XF16)
+                store_oct(raw, HL_DT_F16, (pix0 + pp) * ldraw + 8 * j8, make_float4(in[0], in[1], in[2], in[3]),
+                          make_float4(in[4], in[5], in[6], in[7]), HL_OP_SCALED | HL_OP_SPLIT | (C << 8));
+        }
+        pb += lanes_p * U;
+        if (pb < np) load_round(pb);
+    }
+}
+
+static int g_gn_blocks_per_sm = 0;      // blocks of k_gn_apply_f16 per SM and launch; 0 = one wave by occupancy (hl_gn_set_tuning)
+extern "C" int hl_gn_set_tuning(int blocks_per_sm) {
+    g_gn_blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 0;
+    return HL_OK;
+}
+
+typedef void (*GnF16Kernel)(const void *, int, const double *, int, const float *, const float *, const float *, int,
+                            __half *, int, __half *, int, int, int, int, float, int);
 
 extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma,
                            const float *beta, const float *film, int film_ld, void *y, int y_dtype, int ldy,
@@ -597,20 +666,57 @@ extern "C" int hl_gn_apply(const float *x, int ldx, const double *stats, int sta
                  ldx >= C && ldy >= C && stats_ld >= C);
     HL_CHECK_ARG(y_dtype == HL_DT_F32 || y_dtype == HL_DT_F16);
     HL_CHECK_ARG(!raw || (ldraw % 4 == 0 && ldraw >= C));
-    const bool oct_ok = C % 8 == 0 && C / 8 <= 256 && ldy % 8 == 0 && (!raw || ldraw % 8 == 0) &&
-                        ((uintptr_t)y & 15) == 0 && (!raw || ((uintptr_t)raw & 15) == 0);
-    int64_t want_blocks = (int64_t)hl_num_sms() * 8 / B;
+    const int op_mode = round_tf32;
+    const bool x_f16 = (op_mode & HL_OP_X_F16) != 0;
+    HL_CHECK_ARG(!x_f16 || (((uintptr_t)x & 7) == 0 && !raw));
+    const int y_mode = op_mode & 7, y_lo = op_mode >> 8, raw_mode = (op_mode >> 4) & 7;
+    // the specialised fp16 kernel: whole channel octets, y a plain fp16 operand or an unscaled hi | lo pair with lo
+    // at channel C, raw (if any) the scaled hi | lo pair
+    const bool fast = y_dtype == HL_DT_F16 && C % 8 == 0 && C / 8 <= 256 && ldy % 8 == 0 && ((uintptr_t)y & 15) == 0 &&
+                      ldx % 8 == 0 && ((uintptr_t)x & 15) == 0 &&
+                      (y_mode == 0 || (y_mode == HL_OP_SPLIT && y_lo == C && ldy >= 2 * C)) &&
+                      (!raw || (raw_mode == (HL_OP_SPLIT | HL_OP_SCALED) && ldraw % 8 == 0 && ldraw >= 2 * C &&
+                                ((uintptr_t)raw & 15) == 0));
+    int threads = 256;
+    if (fast) threads = (256 / (C / 8)) * (C / 8);
+    int per_sm = 8;
+    GnF16Kernel kern = nullptr;
+    if (fast) {
+        const bool ys = y_mode == HL_OP_SPLIT, rw = raw != nullptr;
+#define HL_GN_PICK(XF, SI, RW, YS) if (x_f16 == XF && (silu != 0) == SI && rw == RW && ys == YS) kern = k_gn_apply_f16<XF, SI, RW, YS>;
+        HL_GN_PICK(false, true, false, false) HL_GN_PICK(false, false, false, false) HL_GN_PICK(false, true, true, false)
+        HL_GN_PICK(false, false, true, false) HL_GN_PICK(true, true, false, false) HL_GN_PICK(true, false, false, false)
+        HL_GN_PICK(false, true, false, true) HL_GN_PICK(false, false, false, true)
+#undef HL_GN_PICK
+    }
+    if (kern) {
+        // grid: whole waves of resident blocks (measured at 256^2, B = 4, 3 resident blocks / SM: 3 / SM = one wave
+        // 57.7 us, 4 / SM = a wave and a third 68.2 us, 6 / SM = two waves 55.8 us -- profiles/r2_gn_sweep*.log);
+        // the store-heavy variant with the raw hi | lo copy (10 B / element, 6 of them written) prefers many short
+        // blocks (16 / SM: 167.6 us vs 185.5 us for one wave).  Small tensors are bounded below by min_ppb.
+        // hl_gn_set_tuning overrides the blocks-per-SM figure.
+        per_sm = g_gn_blocks_per_sm;
+        if (per_sm <= 0) {
+            int occ = 0;
+            HL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
+            per_sm = raw ? 16 : 2 * (occ > 0 ? occ : 1);
+        }
+    }
+    int64_t want_blocks = (int64_t)hl_num_sms() * per_sm / B;
     if (want_blocks < 1) want_blocks = 1;
     int pix_per_block = hl_cdiv(HW, want_blocks);
     int min_ppb = hl_cdiv(256 * 4 * 4, C / 4);  // >= 4 float4 per thread
     if (pix_per_block < min_ppb) pix_per_block = min_ppb;
     dim3 grid(hl_cdiv(HW, pix_per_block), B);
-    int threads = 256;
-    if (oct_ok) threads = (256 / (C / 8)) * (C / 8);   // fast path: whole channel octets
-    if (threads < 64) threads = 256;
-    HL_CHECK_CUDA(hl_launch(k_gn_apply, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y,
-                                                       y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu,
-                                                       round_tf32, pix_per_block, oct_ok ? 1 : 0));      // round_tf32 = the op_mode word
+    if (kern) {
+        HL_CHECK_CUDA(hl_launch(kern, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, (const void *)x, ldx, stats, stats_ld,
+                                gamma, beta, film, film_ld, (__half *)y, ldy, (__half *)raw, ldraw, HW, C, groups, eps,
+                                pix_per_block));
+    } else {
+        HL_CHECK_CUDA(hl_launch(k_gn_apply, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, ldx, stats, stats_ld, gamma,
+                                beta, film, film_ld, y, y_dtype, ldy, raw, ldraw, HW, C, groups, eps, silu, op_mode,
+                                pix_per_block));
+    }
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -52,11 +52,15 @@ extern "C" {
 #define HL_OP_SPLIT 4     /* fp16 operand: store an fp16 hi | lo pair (lo = fp16(v - hi), ~22 significant bits),
                              lo at + (mode >> 8) elements -- the operand of HL_CONV_SPLIT3 / SPLIT2P convs   */
 #define HL_OP_RAW_SHIFT 4 /* hl_gn_apply: bits 4-6 = the HL_OP_* flags of the raw copy (split: lo at channel C) */
+#define HL_OP_X_F16 8     /* hl_gn_apply: the INPUT x is an fp16 tensor (pitch ldx in halves) -- the result of a conv
+                             run with HL_CONV_OUT_F16 whose only reader is this GroupNorm (a ResBlock's in_layers
+                             output, unet.py:201-206); no raw copy in this mode                                */
 
 #define HL_CONV_FORCE_SIMT 1   /* use the fp32 CUDA-core kernel even where the tcgen05 path applies */
 #define HL_CONV_UPSAMPLE2X 2   /* input is read through a nearest x2 upsample (unet.py:77)          */
 #define HL_CONV_TF32 4         /* fp32 operands may go through tcgen05 kind::tf32                   */
-#define HL_CONV_OUT_F16 8      /* y is an fp16 operand buffer (pitch ldy in halves); no statistics   */
+#define HL_CONV_OUT_F16 8      /* y is an fp16 buffer (pitch ldy in halves); statistics, if asked for, are those
+                                  of the ROUNDED values (what the reader of y sees)                  */
 /* High-precision operand passes of the fp16 plan (tcgen05 kernel only).  The convs that read the RAW
  * residual stream (1x1 skip, ControlNet projection, Downsample, stem) and the output conv carry each operand as an
  * fp16 hi + lo pair (~22 significant bits) and run three (two) tensor-core passes into one accumulator:          */
@@ -151,6 +155,8 @@ int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, in
  * scale/shift optional (film + b*film_ld points at [scale(C) | shift(C)] of sample b); act = SiLU if
  * silu; `raw` (nullable) additionally receives the plain operand copy of x (same dtype, pitch ldraw)
  * for the ResBlock's 1x1 skip convolution, saving a second pass over x.                          */
+/* experiment hook: blocks of hl_gn_apply per SM and launch (<= 0 restores the default) */
+int hl_gn_set_tuning(int blocks_per_sm);
 int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma,
                 const float *beta, const float *film /*nullable*/, int film_ld, void *y, int y_dtype,
                 int ldy, void *raw /*nullable*/, int ldraw, int B, int HW, int C, int groups, float eps,
@@ -168,7 +174,8 @@ int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, cons
  * decoder's concat is never materialised).  stats (nullable): per-channel sum / sum-of-squares of
  * y, layout as hl_gn_stats, ACCUMULATED into the caller-zeroed buffer.  With HL_CONV_OUT_F16 the result
  * (same fp32 arithmetic, rounded once) is written as an fp16 operand buffer: used where the tensor is only
- * ever consumed as an operand (qkv -> attention, ControlNet block output -> its projection conv).
+ * ever consumed as an operand (qkv -> attention, ControlNet block output -> its projection conv) or only by a
+ * GroupNorm (the tensor between the two convs of a ResBlock: hl_gn_apply with HL_OP_X_F16).
  * A 1x1 conv over [B*T, C] rows is the Conv1d / GEMM of the attention block.                    */
 int hl_conv_cout_pad(int Cout);
 int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,

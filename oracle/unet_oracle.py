@@ -83,6 +83,8 @@ def product_fp16_plan(prefix):
     the stems), which carry hi + lo fp16 pairs for both operands in three tensor-core passes, and the output conv
     (activation pair only, two passes); the Upsample / Downsample convs read a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
     import re
+    if prefix.endswith(".h"):
+        return "fp16"                            # ResBlock intermediate (in_layers output) stored as fp16
     if (prefix.endswith("skip_connection") or prefix.startswith("input_blocks_proj_cond.")
             or re.fullmatch(r"input_blocks(_cond)?\.0\.0", prefix)):
         return "fp16_split3"
@@ -133,6 +135,9 @@ def _conv(x, sd, prefix, nm, stride=1, raw=False):
 def _resblock(x, emb, sd, p, nm):
     """unet.py:198-219 (scale-shift norm)."""
     h = _conv(_silu(_gn(x, sd, p + ".in_layers.0")), sd, p + ".in_layers.2", nm)
+    if nm.at(p + ".h").mode == "fp16":
+        # the product stores the tensor between the two convs (read only by out_layers' GroupNorm) as fp16
+        h = h.to(torch.float16).to(torch.float32)
     e = F.linear(_silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
     cout = h.shape[1]
     scale, shift = e[:, :cout, None, None], e[:, cout:, None, None]

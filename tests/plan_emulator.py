@@ -111,8 +111,8 @@ def hl_upsample2x(src, lds, dst, dst_dtype, ldd, B, H, W, C, round_tf32, stream)
     _store_operand(dst, dst_dtype, B * 4 * H * W, C, ldd, up, round_tf32)
 
 
-def hl_gn_stats(x, ldx, B, HW, C, stats, stats_ld, stream):
-    v = pitched(x, B * HW, C, ldx).reshape(B, HW, C).astype(np.float64)
+def hl_gn_stats(x, ldx, B, HW, C, stats, stats_ld, stream, dtype=np.float32):
+    v = pitched(x, B * HW, C, ldx, dtype).reshape(B, HW, C).astype(np.float64)
     st = pitched(stats, B, 2 * C, 2 * stats_ld, np.float64).reshape(B, C, 2)
     st[:, :, 0] += v.sum(1)
     st[:, :, 1] += (v * v).sum(1)
@@ -120,7 +120,9 @@ def hl_gn_stats(x, ldx, B, HW, C, stats, stats_ld, stream):
 
 def hl_gn_apply(x, ldx, stats, stats_ld, gamma, beta, film, film_ld, y, y_dtype, ldy, raw, ldraw, B, HW, C, groups,
                 eps, silu, round_tf32, stream):
-    v = pitched(x, B * HW, C, ldx).reshape(B, HW, C)
+    x_f16 = bool(round_tf32 & 8)                      # HL_OP_X_F16: the input is an fp16 tensor
+    assert not (x_f16 and raw)
+    v = pitched(x, B * HW, C, ldx, np.float16 if x_f16 else np.float32).reshape(B, HW, C).astype(np.float32)
     st = pitched(stats, B, 2 * C, 2 * stats_ld, np.float64).reshape(B, groups, C // groups, 2).sum(2)
     n = HW * (C // groups)
     mean = st[..., 0] / n
@@ -182,9 +184,10 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
         assert not stats and ldy >= 2 * Cout
         _store_operand(y, 1, B * Ho * Wo, Cout, ldy, out, OP_SCALED | OP_SPLIT | (Cout << 8))
         return
-    if flags & 8:                                           # HL_CONV_OUT_F16
-        assert not stats
+    if flags & 8:                                           # HL_CONV_OUT_F16 (statistics: of the rounded values)
         pitched(y, B * Ho * Wo, Cout, ldy, np.float16)[...] = out.astype(np.float16)
+        if stats:
+            hl_gn_stats(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, stream, dtype=np.float16)
         return
     pitched(y, B * Ho * Wo, Cout, ldy)[...] = out
     if stats:

@@ -148,6 +148,30 @@ def test_groupnorm_silu_film(dev, C, HW, B):
                 assert rel_l2(y.float(), exact.float()) < 2e-5
 
 
+@pytest.mark.parametrize("C,HW,B", [(192, 64 * 64, 2), (768, 64, 3), (384, 1024, 1), (36, 16, 2)])
+def test_groupnorm_fp16_input(dev, C, HW, B):
+    """HL_OP_X_F16: the GroupNorm input is an fp16 tensor (a conv's HL_CONV_OUT_F16 result): same output as the fp32
+    path fed the same (exactly representable) values -- both the 8-channel fast path and the generic one (C = 36)."""
+    from humanliff_b200 import _lib
+    g = torch.Generator().manual_seed(C + HW)
+    x = (torch.randn(B, HW, C, generator=g) * 2 + 0.5).half()
+    groups = 32 if C % 32 == 0 else 4
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    film = 0.3 * torch.randn(B, 2 * C, generator=g)
+    x16, x32, gd, bd, fd = x.to(dev), x.float().to(dev), gamma.to(dev), beta.to(dev), film.to(dev)
+    stats = torch.zeros(B * C * 2, device=dev, dtype=torch.float64)
+    _call("hl_gn_stats", x32.data_ptr(), C, B, HW, C, stats.data_ptr(), C, _stream())
+    outs = []
+    for xin, flag in ((x32, 0), (x16, _lib.OP_X_F16)):
+        y = torch.empty(B, HW, C, device=dev, dtype=torch.float16)
+        _call("hl_gn_apply", xin.data_ptr(), C, stats.data_ptr(), C, gd.data_ptr(), bd.data_ptr(), fd.data_ptr(), 2 * C,
+              y.data_ptr(), 1, C, None, 0, B, HW, C, groups, 1e-5, 1, flag, _stream())
+        outs.append(y.cpu())
+    assert torch.equal(outs[0], outs[1])
+    xn = F.group_norm(x.float().permute(0, 2, 1), groups, gamma, beta, eps=1e-5) * (1 + film[:, :C, None]) + film[:, C:, None]
+    assert rel_l2(outs[1].float().permute(0, 2, 1), xn * torch.sigmoid(xn)) < 6e-4
+
+
 def _operand(t, mode):
     """fp32 tensor -> (device-ready operand tensor, dtype code, fp32 view of the rounded values)."""
     from oracle.unet_oracle import round_tf32
@@ -310,9 +334,11 @@ def test_conv_fp16_output(dev, shape, residual, cta2):
     B, H, W, Cin, Cout, k, s = shape
     kw = dict(mode="fp16", residual=residual, seed=11, tuning2=(-1, -1, cta2))
     y32 = _conv_case(dev, B, H, W, Cin, Cout, k, s, **kw)[0]
-    y16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
+    y16, _, _, st = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, stats=Cout % 4 == 0, **kw)
     assert not torch.isnan(y16).any()
     assert torch.equal(y16, y32.half().float())
+    if st is not None:        # statistics of an fp16 result = those of the ROUNDED values (epilogue, stats kernel, CUDA-core path)
+        _check_stats(st, y16, Cout)
 
 
 @pytest.mark.parametrize("shape,split", [
@@ -338,8 +364,9 @@ def test_conv_split_k(dev, shape, split, residual, cta2):
     _check_stats(st, y, Cout)
     y2 = _conv_case(dev, B, H, W, Cin, Cout, k, s, stats=True, **kw)[0]
     assert torch.equal(y, y2), "fixed-order reduction: bit-reproducible"
-    y16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
+    y16, _, _, st16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, stats=True, **kw)
     assert torch.equal(y16, y.half().float())
+    _check_stats(st16, y16, Cout)
 
 
 def test_conv_tc_strided_output_and_input(dev):

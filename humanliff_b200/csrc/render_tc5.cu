@@ -4,6 +4,10 @@
 // run_nerf_batch.py:29-67):
 //   coarse z -> nine-plane bilinear gather -> density MLP -> up_sample / sample_pdf -> merge-sort ->
 //   256-sample fine pass (+ view-direction branch) -> alpha compositing.
+// The coarse samples go through the WHOLE network once: the reference evaluates their density layers for up_sample and
+// then again, identically, inside render_core on the sorted union (renderer.py:258-279); here the colour branch runs on
+// the coarse activations while they still sit in tensor memory, the fine pass evaluates only the 128 new samples, and the
+// (sigma, rgb) of both sets are scattered into sorted order for compositing: 10 layer passes per ray instead of 13.
 // What changed against the mma.sync kernel (220 registers / thread, 8 warps per SM, every phase of a ray alone
 // on the SM -- profiles/r1_kernels_full_v10.md): the activations no longer live in registers.
 //   * one persistent CTA per SM runs TWO independent ray groups of 128 threads; thread i of a group owns
@@ -54,7 +58,7 @@ static_assert(W_BYTES + 4 * FB_FLOATS == HL_MLP_TC5_BYTES, "header and kernel di
 
 // per-group scratch (floats)
 constexpr int SC_ZC = 0, SC_ZN = 128, SC_ZF = 256, SC_CDF = 512, SC_BINS = 640, SC_PE = 768, SC_RED = 800,
-              SC_FLOATS = 864;
+              SC_VAL = 864 /* (sigma, r, g, b) of the 256 samples in sorted order */, SC_FLOATS = 864 + 1024;
 
 constexpr size_t SMEM5 = 1024 + (size_t)W_BYTES + sizeof(float) * (FB_FLOATS + GROUPS * SC_FLOATS);
 
@@ -543,14 +547,21 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
             }
             RPROF(0)
             float rgb0[3] = {0.f, 0.f, 0.f}, rgb1[3] = {0.f, 0.f, 0.f}, sig0 = 0.f, sig1 = 0.f;
+            // ------------------------------- coarse samples: the WHOLE network, once ---------------------------
+            // The reference evaluates NeRF_network twice on the coarse points: density only for up_sample
+            // (renderer.py:258-264), then again -- same points, same weights -- inside render_core on the sorted
+            // union of coarse and new samples (renderer.py:266-279,199-201).  The second evaluation reproduces the
+            // first bit for bit, so the colour branch runs right here on the activations still sitting in tensor
+            // memory and the fine pass only evaluates the 128 NEW samples: 10 layer passes per ray instead of 13,
+            // two gathers instead of three.
+            gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, zmine)), __fadd_rn(oy, __fmul_rn(dy, zmine)),
+                           __fadd_rn(oz, __fmul_rn(dz, zmine)), G.tm + TM_AX);
+            RPROF(1)
+            const float4 rc = mlp128(G, true);
+            G.phase ^= 1u;
+            RPROF(2)
             if (a.n_importance) {
-                // ------------------------------- coarse pass (density only) -------------------------------
-                gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, zmine)), __fadd_rn(oy, __fmul_rn(dy, zmine)),
-                               __fadd_rn(oz, __fmul_rn(dz, zmine)), G.tm + TM_AX);
-                RPROF(1)
-                const float sigma = mlp128(G, false).x;
-                G.phase ^= 1u;
-                RPROF(2)
+                const float sigma = rc.x;
                 // ------------------------------- up_sample + sample_pdf -----------------------------------
                 const float znext = tg < NS - 1 ? lds_f32(zc + tg4 + 4u) : 0.f;
                 const float dist = (tg < NS - 1 ? znext - zmine : 1e10f) * dnorm;
@@ -577,6 +588,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 }
                 gbar(G);
                 float znew;
+                int pos_c, pos_n;
                 {
                     const float uu = a.u ? a.u[ray * NS + tg] : uniform_hash(a.seed, (unsigned long long)ray, tg);
                     int lo = 0, hi = NS - 1;
@@ -613,29 +625,35 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                         const bool le = lds_f32(zc + 4u * (uint32_t)min(mid, NS - 1)) <= znew;
                         if (lo < hi) { if (le) lo = mid + 1; else hi = mid; }
                     }
-                    sts_f32(zf + 4u * (uint32_t)(tg + c_lt), zmine);
-                    sts_f32(zf + 4u * (uint32_t)(n_lt + lo), znew);
+                    pos_c = tg + c_lt;                     // sorted position of this thread's coarse / new sample
+                    pos_n = n_lt + lo;
+                    sts_f32(zf + 4u * (uint32_t)pos_c, zmine);
+                    sts_f32(zf + 4u * (uint32_t)pos_n, znew);
                 }
-                gbar(G);
                 RPROF(3)
+                // ------------------------------- fine pass: the 128 new samples ----------------------------
+                gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, znew)), __fadd_rn(oy, __fmul_rn(dy, znew)),
+                               __fadd_rn(oz, __fmul_rn(dz, znew)), G.tm + TM_AX);
+                RPROF(1)
+                const float4 rn = mlp128(G, true);
+                G.phase ^= 1u;
+                RPROF(2)
+                // both sets of (sigma, r, g, b) into sorted order; this thread composites samples tg and 128 + tg
+                const uint32_t val = G.sc + 4u * SC_VAL;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(val + 16u * (uint32_t)pos_c), "f"(rc.x), "f"(rc.y),
+                             "f"(rc.z), "f"(rc.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(val + 16u * (uint32_t)pos_n), "f"(rn.x), "f"(rn.y),
+                             "f"(rn.z), "f"(rn.w) : "memory");
+                gbar(G);                                   // also orders the sorted z (zf) before the reads below
+                const float4 v0 = lds_f128(val + 4u * tg4), v1 = lds_f128(val + 16u * (uint32_t)(NS + tg));
+                sig0 = v0.x; rgb0[0] = v0.y; rgb0[1] = v0.z; rgb0[2] = v0.w;
+                sig1 = v1.x; rgb1[0] = v1.y; rgb1[1] = v1.z; rgb1[2] = v1.w;
             } else {
                 sts_f32(zf + tg4, zmine);
                 gbar(G);
+                sig0 = rc.x; rgb0[0] = rc.y; rgb0[1] = rc.z; rgb0[2] = rc.w;
             }
-            // ------------------------------- fine pass: sorted samples tg and 128 + tg ----------------
             const float z0 = lds_f32(zf + tg4), z1 = a.n_importance ? lds_f32(zf + 4u * NS + tg4) : 0.f;
-#pragma unroll 1
-            for (int t = 0; t < n_tiles; ++t) {
-                const float z = t ? z1 : z0;
-                gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, z)), __fadd_rn(oy, __fmul_rn(dy, z)),
-                               __fadd_rn(oz, __fmul_rn(dz, z)), G.tm + TM_AX);
-                RPROF(1)
-                const float4 r = mlp128(G, true);
-                G.phase ^= 1u;
-                if (t == 0) { sig0 = r.x; rgb0[0] = r.y; rgb0[1] = r.z; rgb0[2] = r.w; }
-                else { sig1 = r.x; rgb1[0] = r.y; rgb1[1] = r.z; rgb1[2] = r.w; }
-                RPROF(2)
-            }
             // ------------------------------- composite (renderer.py:222-239) --------------------------
             {
                 const int last = n_tiles * NS - 1;

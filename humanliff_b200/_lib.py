@@ -38,6 +38,8 @@ SIGNATURES = {
     "hl_conv_cout_pad": (c_int, [c_int]),
     "hl_conv2d": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_int, c_int, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "hl_conv2d_dual": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int,
+                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_set_pdl": (c_int, [c_int]),
     "hl_pdl_barrier": (None, []),
     "hl_launch_count": (c_i64, []),

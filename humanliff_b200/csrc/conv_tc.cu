@@ -93,6 +93,12 @@ struct TcParams {
     int split_b;             // batch-coordinate offset per split in the partial-sum workspace (= B)
     double *stats;
     int stats_ld;
+    // dual output (hl_conv2d_dual): epilogue group 0 writes y = conv + bias + residual (tmY, stats), group 1 writes
+    // y2 = conv + bias (tmY2, stats2) from the same accumulators -- both groups drain EVERY chunk
+    int dual;
+    double *stats2;
+    int stats2_ld;
+    int sacc2_off;           // byte offset (from the aligned dynamic shared-memory base) of group 1's fp64 accumulators
 };
 
 // profiling: cycles CTA 0 spends blocked in each wait, accumulated into p.prof[slot]
@@ -134,7 +140,7 @@ template <bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-          const TcParams p) {
+          const __grid_constant__ CUtensorMap tmY2, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + EPI_GROUPS * MAX_NBUF];
     __shared__ uint32_t tmem_slot;
@@ -168,6 +174,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        if (p.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY2) : "memory");
     }
     if (warp == 2) {
         if (lane == 0) {
@@ -199,8 +206,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
+    // group 1's accumulators in dual mode live in dynamic shared memory (only those launches pay for them)
+    double *const sacc2 = reinterpret_cast<double *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.sacc2_off);
     if (warp >= 3 && p.stats) {
-        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_GROUPS * EPI_THREADS) (&sacc[0][0])[i] = 0.0;
+        for (int i = threadIdx.x - 96; i < 2 * STATS_MAX_C; i += EPI_GROUPS * EPI_THREADS) {
+            (&sacc[0][0])[i] = 0.0;
+            if (p.dual) sacc2[i] = 0.0;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CTA2) cluster_sync_all(); else __syncthreads();     // barriers initialised + TMEM allocated in both CTAs
@@ -450,6 +462,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t smem_g = smem_e + (uint32_t)(eg * p.nbuf) * STAGE_BUF_BYTES;
         const uint32_t bar_r = bar_r_full + 8u * (uint32_t)(eg * MAX_NBUF);
         const uint32_t nbuf = (uint32_t)p.nbuf;   // staging ring of this group: 2, 3 or 4 buffers
+        // dual output: group 1 is the "plain" group (no residual, second output map, second statistics row)
+        const bool plain_g = p.dual && eg == 1;
+        const bool g_res = p.has_res && !plain_g;
+        const CUtensorMap *const tm_out = plain_g ? &tmY2 : &tmY;
+        double *const sacc_s = plain_g ? sacc2 : &sacc[0][0];                  // [2][STATS_MAX_C]
+        const uint32_t own_mask = p.dual ? 0u : (uint32_t)(EPI_GROUPS - 1);   // dual: every chunk belongs to both groups
         uint32_t rb = 0, rph = 0;                 // ring slot / phase of the chunk being processed
         uint32_t qn = 0;                          // global chunk counter of this CTA
         uint32_t ql = 0;                          // chunks owned by this group so far (staging ring position)
@@ -463,7 +481,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (;;) {
                 if (l_tile >= p.total_tiles) return;
                 const int nt0 = (l_tile % p.n_tiles) * p.n_tile;
-                const bool mine = (int)(l_qn & (EPI_GROUPS - 1)) == eg;
+                const bool mine = (int)(l_qn & own_mask) == (p.dual ? 0 : eg);
                 if (mine) {
                     int w0, h0, n0;
                     box_origin(p, (l_tile % p.tiles_mn) / p.n_tiles, l_half, rank, w0, h0, n0);
@@ -480,7 +498,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (mine) return;
             }
         };
-        if (p.has_res && e0)
+        if (g_res && e0)
             for (int i = 0; i < p.nbuf - 1; ++i) issue_res_load();
 
         auto flush_stats = [&]() {
@@ -491,6 +509,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 atomicAdd(dst + 1, sacc[1][c]);
                 sacc[0][c] = 0.0;
                 sacc[1][c] = 0.0;
+                if (p.dual) {
+                    double *dst2 = p.stats2 + ((size_t)cur_n * p.stats2_ld + c) * 2;
+                    atomicAdd(dst2, sacc2[c]);
+                    atomicAdd(dst2 + 1, sacc2[STATS_MAX_C + c]);
+                    sacc2[c] = 0.0;
+                    sacc2[STATS_MAX_C + c] = 0.0;
+                }
             }
             named_bar(3, EPI_GROUPS * EPI_THREADS);
         };
@@ -516,13 +541,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int cc = 0; cc < p.nchunks; ++cc, ++qn) {
                     const int nbase = nt0 + cc * 32;
                     if (nbase >= p.Cout) break;
-                    if ((int)(qn & (EPI_GROUPS - 1)) != eg) continue;       // the other group's chunk
+                    if (!p.dual && (int)(qn & (EPI_GROUPS - 1)) != eg) continue;       // the other group's chunk
                     const uint32_t b = rb;
                     const uint32_t sbuf = smem_g + b * STAGE_BUF_BYTES;
                     const uint32_t srow = sbuf + (uint32_t)row * 128u;
                     float v[32];
                     tmem_ld32(acc + (uint32_t)(cc * 32), v);
-                    if (p.has_res) {
+                    if (g_res) {
                         PROF_IF(5, pt);
                         mbar_wait(bar_r + 8 * b, rph);
                     }
@@ -534,7 +559,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
                                                    v[4 * j + 3] + bz.w);
                             const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
-                            if (p.has_res) {
+                            if (g_res) {
                                 float4 r;
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
@@ -552,7 +577,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int j = 0; j < 8; ++j) {
                             const float4 bz = p.bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             v[4 * j] += bz.x; v[4 * j + 1] += bz.y; v[4 * j + 2] += bz.z; v[4 * j + 3] += bz.w;
-                            if (p.has_res) {
+                            if (g_res) {
                                 float4 r;
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
@@ -560,7 +585,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
                             }
                         }
-                        if (p.has_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
+                        if (g_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
                         const uint32_t hrow = sbuf + (uint32_t)row * 64u, hsw = ((uint32_t)row >> 1) & 3u;
                         if (p.y_f16 == 2) {
                             // scaled hi | lo pair (a raw residual-stream operand of a high-precision conv): v * 2^-4 =
@@ -590,17 +615,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (!p.has_res && e0) {
+                    if (!g_res && e0) {
                         // the buffer the group's NEXT chunk writes must have been read out by its old store
                         PROF_IF(9, eg == 0);
                         if (nbuf == 2) bulk_wait_read<0>(); else if (nbuf == 3) bulk_wait_read<1>(); else bulk_wait_read<2>();
                     }
                     { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
-                        tma_store_4d(&tmY, sbuf, nbase, w0, h0, n0 + ks * p.split_b);
+                        tma_store_4d(tm_out, sbuf, nbase, w0, h0, n0 + ks * p.split_b);
                         if (p.y_f16 == 2) tma_store_4d(&tmY, sbuf + 8192u, p.Cout + nbase, w0, h0, n0);
                         bulk_commit();
-                        if (p.has_res) {
+                        if (g_res) {
                             { PROF_IF(9, eg == 0); bulk_wait_read<1>(); }   // previous store drained -> refill its buffer
                             issue_res_load();
                         }
@@ -644,8 +669,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         if (rq == 0 && nbase + col < p.Cout) {
                             const float2 p0 = spart[eg][0][col], p1 = spart[eg][1][col], p2 = spart[eg][2][col],
                                          p3 = spart[eg][3][col];
-                            atomicAdd(&sacc[0][nbase + col], (double)((p0.x + p1.x) + (p2.x + p3.x)));
-                            atomicAdd(&sacc[1][nbase + col], (double)((p0.y + p1.y) + (p2.y + p3.y)));
+                            atomicAdd(&sacc_s[nbase + col], (double)((p0.x + p1.x) + (p2.x + p3.x)));
+                            atomicAdd(&sacc_s[STATS_MAX_C + nbase + col], (double)((p0.y + p1.y) + (p2.y + p3.y)));
                         }
                     }
                     if (++rb == nbuf) { rb = 0; rph ^= 1u; }
@@ -698,9 +723,9 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
     double sm[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
     if (live) {
         const float4 bz = __ldg(reinterpret_cast<const float4 *>(bias + c));
-#pragma unroll 2
         // blockIdx.z = pixel slab of the sample (B = 1 at 32^2 would otherwise run 12 blocks of 32 serial rounds)
         const int pend = min(HW, ((int)blockIdx.z + 1) * slab);
+#pragma unroll 2
         for (int pp = (int)blockIdx.z * slab + warp * 4 + pl; pp < pend; pp += 32) {
             const int64_t m = (int64_t)b * HW + pp;
             const float *src = ws + m * ldw + c;
@@ -846,7 +871,7 @@ int acc_stride_for(int n_tile) {
 }
 
 bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int stride, bool has_res,
-               bool want_stats, Plan *pl, int npass = 1) {
+               bool want_stats, Plan *pl, int npass = 1, int reserve = 0 /* bytes of dynamic shared memory kept free */) {
     // H, W are OUTPUT dims here
     Tiling t;
     if (!pick_tiling(H, W, &t)) return false;
@@ -952,7 +977,7 @@ bool make_plan(int kind, int B, int H, int W, int Cin, int Cout, int ksize, int 
     p.tmem_cols = cols;
 
     // shared-memory budget: staging ring, then A slots, the rest to B slots
-    const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/;
+    const int budget = DYN_SMEM_MAX - 1024 /*alignment slack*/ - reserve;
     p.b_slot_bytes = (n_tile / pair) * ROW_BYTES;
     p.has_res = has_res ? 1 : 0;
     // staging buffers PER epilogue group: 2; the HBM-bound 1x1 convs with a residual want a deeper residual
@@ -1121,10 +1146,11 @@ extern "C" int hl_conv2d_plan_info(int x_dtype, int B, int H, int W, int Cin, in
     const int kind = x_dtype == HL_DT_F16 ? 1 : 0;
     Plan pl = {};
     if ((stride != 1 && stride != 2) || (ksize != 1 && ksize != 3) || (stride == 2 && (ksize != 3 || H % 2 || W % 2)) ||
-        !make_plan(kind, B, H / stride, W / stride, Cin, Cout, ksize, stride, has_res != 0, want_stats != 0, &pl))
+        !make_plan(kind, B, H / stride, W / stride, Cin, Cout, ksize, stride, has_res != 0, want_stats != 0, &pl, 1,
+                   has_res == 2 ? 2 * STATS_MAX_C * (int)sizeof(double) : 0))      // has_res == 2: the dual-output launch
         return HL_OK;                                   // out[0] = 0: the CUDA-core kernel serves this shape
-    const int S = choose_split(pl, kind, B, H / stride, W / stride, Cin, Cout, ksize, stride,
-                               ws_bytes > 0 ? (size_t)ws_bytes : 0);
+    const int S = has_res == 2 ? 1 : choose_split(pl, kind, B, H / stride, W / stride, Cin, Cout, ksize, stride,
+                                                  ws_bytes > 0 ? (size_t)ws_bytes : 0);
     const TcParams &p = pl.p;
     const int units = p.pair == 2 ? pl.grid / 2 : pl.grid;
     int grid = pl.grid;
@@ -1167,7 +1193,8 @@ int hl_gn_stats_launch(const void *x, int x_f16, int ldx, int B, int HW, int C, 
 
 int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
                  const float *residual, int ldr, void *y, int y_f16, int ldy, double *stats, int stats_ld, int B,
-                 int Hin, int Win, int Cin, int Cout, int ksize, int stride, int flags, cudaStream_t stream) {
+                 int Hin, int Win, int Cin, int Cout, int ksize, int stride, int flags, cudaStream_t stream,
+                 float *y2 = nullptr, int ldy2 = 0, double *stats2 = nullptr, int stats2_ld = 0) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) {
         hl_set_error("cuTensorMapEncodeTiled unavailable");
@@ -1183,7 +1210,9 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     const int npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & (HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) ? 2 : 1;
     const int nslab = (flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2P)) ? 2 : 1;
     Plan pl = {};
-    HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl, npass));
+    constexpr int DUAL_RESERVE = 2 * STATS_MAX_C * (int)sizeof(double);
+    HL_CHECK_ARG(make_plan(kind, B, H, W, Cin, Cout, ksize, stride, residual != nullptr, stats != nullptr, &pl, npass,
+                           y2 ? DUAL_RESERVE : 0));
     if (npass == 3) { pl.p.a_off[1] = Cin; pl.p.b_slab[2] = 1; }
     if (flags & HL_CONV_SPLIT2P) pl.p.b_slab[1] = 1;
     if (flags & HL_CONV_SPLIT2A) pl.p.a_off[1] = Cin;
@@ -1197,11 +1226,24 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     p.y_f16 = y_f16;
     HL_CHECK_ARG(!(y_f16 == 2 && stats));
     bool epi_stats = plan_epi_stats(pl, stats != nullptr);
+    // dual output: y = conv + residual, y2 = conv (one pass over the operands; see TcParams::dual)
+    const bool dual = y2 != nullptr;
+    HL_CHECK_ARG(!dual || (residual && !y_f16 && ((uintptr_t)y2 & 15) == 0 && ldy2 % 4 == 0 && ldy2 >= Cout &&
+                           (stats == nullptr) == (stats2 == nullptr)));
+    p.dual = dual ? 1 : 0;
+    p.stats2 = nullptr;
+    p.stats2_ld = 0;
+    p.sacc2_off = 0;
+    if (dual) {
+        p.sacc2_off = (int)pl.smem - 1024;            // pl.smem = rings + staging + 1024 B of alignment slack
+        pl.smem += DUAL_RESERVE;
+        HL_CHECK_ARG(pl.smem <= (size_t)DYN_SMEM_MAX);
+    }
 
     // split-K (see choose_split / k_splitk_reduce)
     const Workspace *wsp = find_ws(stream);
     const float *keep_bias = p.bias;
-    const int S = choose_split(pl, kind, B, H, W, Cin, Cout, ksize, stride, wsp ? wsp->bytes : 0);
+    const int S = dual ? 1 : choose_split(pl, kind, B, H, W, Cin, Cout, ksize, stride, wsp ? wsp->bytes : 0);
     p.bias = keep_bias;
     p.y_f16 = y_f16;
     const void *y_final = y;
@@ -1229,10 +1271,12 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     if (epi_stats) {
         p.stats = stats;
         p.stats_ld = stats_ld;
+        p.stats2 = stats2;
+        p.stats2_ld = stats2_ld;
     }
     const CUtensorMapDataType dt = kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
-    CUtensorMap tmA, tmB, tmY, tmR;
+    CUtensorMap tmA, tmB, tmY, tmR, tmY2;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2A)) ? 2 * Cin : Cin), (cuuint64_t)Win,
                               (cuuint64_t)Hin, (cuuint64_t)B};
@@ -1267,13 +1311,13 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
             return HL_E_CUDA;
         }
     }
-    for (int which = 0; which < 2; ++which) {
-        const void *ptr = which ? (const void *)residual : (const void *)y;
-        const int ld = which ? ldr : ldy;
+    for (int which = 0; which < 3; ++which) {
+        const void *ptr = which == 1 ? (const void *)residual : which == 2 ? (const void *)y2 : (const void *)y;
+        const int ld = which == 1 ? ldr : which == 2 ? ldy2 : ldy;
         const bool f16 = !which && y_f16;
         const int esz_o = f16 ? 2 : 4;
-        CUtensorMap *tm = which ? &tmR : &tmY;
-        if (!ptr || (which && S > 1)) { *tm = tmY; continue; }
+        CUtensorMap *tm = which == 1 ? &tmR : which == 2 ? &tmY2 : &tmY;
+        if (!ptr || (which == 1 && S > 1)) { *tm = tmY; continue; }
         cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : (!which && y_f16 == 2) ? 2 * Cout : Cout), (cuuint64_t)W,
                               (cuuint64_t)H, (cuuint64_t)(S > 1 ? split_batch(pl, B) * S : B)};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
@@ -1286,7 +1330,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             hl_set_error("cuTensorMapEncodeTiled(%s) failed: %d (B=%d H=%d W=%d Cout=%d ld=%d)",
-                         which ? "residual" : "output", (int)r, B, H, W, Cout, ld);
+                         which == 1 ? "residual" : which == 2 ? "second output" : "output", (int)r, B, H, W, Cout, ld);
             return HL_E_CUDA;
         }
     }
@@ -1310,9 +1354,9 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = hl_pdl_attr(attr, 1);
-        HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, tmA, tmB, tmY, tmR, p));
+        HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, tmA, tmB, tmY, tmR, tmY2, p));
     } else {
-        HL_CHECK_CUDA(hl_launch(k_conv_tc<false>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, p));
+        HL_CHECK_CUDA(hl_launch(k_conv_tc<false>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, tmY2, p));
     }
     HL_CHECK_LAUNCH();
     if (S > 1) {
@@ -1327,7 +1371,11 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
                                 yf16_final, ldy_final, stats, stats_ld, HW, Cout, slab));
         return HL_OK;
     }
-    if (stats && !epi_stats) return hl_gn_stats_launch(y, y_f16, ldy, B, H * W, Cout, stats, stats_ld, stream);
+    if (stats && !epi_stats) {
+        int rc = hl_gn_stats_launch(y, y_f16, ldy, B, H * W, Cout, stats, stats_ld, stream);
+        if (rc != HL_OK || !dual) return rc;
+        return hl_gn_stats_launch(y2, 0, ldy2, B, H * W, Cout, stats2, stats2_ld, stream);
+    }
     return HL_OK;
 }
 
@@ -1369,4 +1417,37 @@ extern "C" int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, c
     const int pad = ksize / 2;
     const int Ho = (H * ups + 2 * pad - ksize) / stride + 1, Wo = (W * ups + 2 * pad - ksize) / stride + 1;
     return hl_gn_stats_launch(y, (flags & HL_CONV_OUT_F16) ? 1 : 0, ldy, B, Ho * Wo, Cout, stats, stats_ld, (cudaStream_t)stream);
+}
+
+// y = conv(x) + bias + residual AND y2 = conv(x) + bias from ONE pass over the operands (see the header): the ControlNet
+// projection, whose result both feeds the next ControlNet block (y2 = h_cond, unet.py:600) and, added to the main
+// encoder's skip tensor, fills the decoder's concat slice (y = hs + hs_cond, unet.py:606).  Shapes the tcgen05 kernel
+// does not serve (and the fp32 plan) run as the two launches this call replaces.
+extern "C" int hl_conv2d_dual(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias,
+                              const float *residual, int ldr, float *y, int ldy, double *stats, int stats_ld,
+                              float *y2, int ldy2, double *stats2, int stats2_ld, int B, int H, int W, int Cin,
+                              int Cout, int ksize, int stride, int flags, void *stream) {
+    HL_CHECK_ARG(x && wpk && y && y2 && residual && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+    HL_CHECK_ARG(x_dtype == HL_DT_F32 || x_dtype == HL_DT_F16);
+    HL_CHECK_ARG(ksize == 1 || ksize == 3);
+    HL_CHECK_ARG(stride == 1 || stride == 2);
+    HL_CHECK_ARG(ldx >= Cin && ldy >= Cout && ldy2 >= Cout && ldr >= Cout);
+    HL_CHECK_ARG(!(flags & (HL_CONV_OUT_F16 | HL_CONV_OUT_F16_SPLIT | HL_CONV_UPSAMPLE2X)));
+    HL_CHECK_ARG((stats == nullptr) == (stats2 == nullptr));
+    HL_CHECK_ARG(!stats || (stats_ld >= Cout && stats2_ld >= Cout));
+    if (hl_conv_tc_applicable(x_dtype, B, H, W, Cin, Cout, ksize, stride, ldx, ldy, flags) && ldy2 % 4 == 0 &&
+        ((uintptr_t)y2 & 15) == 0) {
+        // the second staging ring shares the budget of the first: check that the plan still fits with both
+        Plan pl = {};
+        const int npass = (flags & HL_CONV_SPLIT3) ? 3 : (flags & (HL_CONV_SPLIT2P | HL_CONV_SPLIT2A)) ? 2 : 1;
+        if (make_plan(x_dtype == HL_DT_F16 ? 1 : 0, B, H / stride, W / stride, Cin, Cout, ksize, stride, true, stats != nullptr,
+                      &pl, npass, 2 * STATS_MAX_C * (int)sizeof(double)))
+            return hl_conv2d_tc(x, x_dtype, ldx, wpk, bias, residual, ldr, y, 0, ldy, stats, stats_ld, B, H, W, Cin, Cout,
+                                ksize, stride, flags, (cudaStream_t)stream, y2, ldy2, stats2, stats2_ld);
+    }
+    int rc = hl_conv2d(x, x_dtype, ldx, wpk, bias, nullptr, 0, y2, ldy2, stats2, stats2_ld, B, H, W, Cin, Cout, ksize,
+                       stride, flags, stream);
+    if (rc != HL_OK) return rc;
+    return hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin, Cout, ksize, stride,
+                     flags, stream);
 }

@@ -175,6 +175,7 @@ class UNetModel(nn.Module):
         # hi + lo operand passes for the raw-stream convs and the output conv (fp16 plan only; HL_HIPREC=0 = plain fp16)
         self.hi_precision = precision == "fp16" and os.environ.get("HL_HIPREC", "1") != "0"
         self.h_f16 = precision == "fp16" and os.environ.get("HL_H_F16", "1") != "0"     # ResBlock intermediate as fp16
+        self.dual_proj = os.environ.get("HL_DUAL_PROJ", "1") != "0"    # ControlNet projection: one launch, two results
         self._build_plan()
         if self.hi_precision:
             for c in self._convs.values():
@@ -370,7 +371,7 @@ class UNetModel(nn.Module):
         forward takes effect."""
         self._pack(device)
         key = (str(device), B, H, W, self.use_cuda_graph, self.concurrent_encoders, self.batch_split, self.split_k,
-               self.programmatic_launch, self.h_f16)
+               self.programmatic_launch, self.h_f16, self.dual_proj)
         plan = self._plans.get(key)
         if plan is None:
             parts = self.batch_split
@@ -479,6 +480,25 @@ class _StepPlan:
             flags |= _lib.CONV_SPLIT2P
         self.emit("hl_conv2d", x_ptr, self.dt, ldx, _ptr(c.w), _ptr(c.b), res.ptr if res else None,
                   res.ld if res else 0, dst.ptr, dst.ld, st, dst.st_ld if st else 0, self.B, H, W, c.cin_pad,
+                  c.cout, c.ksize, c.stride, flags)
+
+    def conv_dual(self, cname, x_ptr, ldx, res, dst, dst2, H, W):
+        """One launch, two results (hl_conv2d_dual): dst = conv + res, dst2 = conv; both fp32 with statistics."""
+        m = self.m
+        c = m._convs[cname]
+        flags = 0
+        if m.precision == "fp32":
+            flags |= _lib.CONV_FORCE_SIMT
+        elif m.precision == "tf32":
+            flags |= _lib.CONV_TF32
+        assert not dst.f16 and not dst2.f16 and dst.st is not None and dst2.st is not None
+        if c.hp == "split":
+            flags |= _lib.CONV_SPLIT3
+            assert ldx >= 2 * c.cin_pad
+        else:
+            assert c.hp is None, c.hp
+        self.emit("hl_conv2d_dual", x_ptr, self.dt, ldx, _ptr(c.w), _ptr(c.b), res.ptr, res.ld, dst.ptr, dst.ld,
+                  ("stats", dst.st), dst.st_ld, dst2.ptr, dst2.ld, ("stats", dst2.st), dst2.st_ld, self.B, H, W, c.cin_pad,
                   c.cout, c.ksize, c.stride, flags)
 
     def gn(self, nname, x, out_ptr, ldo, silu, film=None, raw_ptr=None, ldraw=0, out_mode=0, raw_mode=0):
@@ -629,10 +649,16 @@ class _StepPlan:
                     ldop, pmode = self.raw_operand(cname, x.C)
                     self.cast(x, op, ldop, pmode)
                 hc = self.new_ref(f"{tag}p{i}", x.C, x.H, x.W)
-                self.conv(cname, op, ldop, None, hc, x.H, x.W)                   # h_cond (unet.py:600)
-                if self.concurrent:
-                    self.emit_sync("wait", i)                                    # hs[i] of the main encoder
-                self.conv(cname, op, ldop, self.hs[i], cats[i], x.H, x.W)        # hs + hs_cond (unet.py:606)
+                if m.dual_proj:
+                    # h_cond (unet.py:600) and hs + hs_cond (unet.py:606) from one pass over the operands
+                    if self.concurrent:
+                        self.emit_sync("wait", i)                                # hs[i] of the main encoder
+                    self.conv_dual(cname, op, ldop, self.hs[i], cats[i], hc, x.H, x.W)
+                else:
+                    self.conv(cname, op, ldop, None, hc, x.H, x.W)               # h_cond (unet.py:600)
+                    if self.concurrent:
+                        self.emit_sync("wait", i)                                # hs[i] of the main encoder
+                    self.conv(cname, op, ldop, self.hs[i], cats[i], x.H, x.W)    # hs + hs_cond (unet.py:606)
                 x = hc
             elif self.keep_hs and self.concurrent:
                 self.emit_sync("signal", i)                                      # hs[i] complete

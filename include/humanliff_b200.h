@@ -96,7 +96,8 @@ int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream);
  * 0 tensor-core path applies, 1 CTAs per MMA (1 | 2 = cta_group::2), 2 halves per CTA tile, 3 N tile,
  * 4 HALO operand path, 5 A slots, 6 B slots, 7 staging buffers per epilogue group, 8 TMEM accumulator stages,
  * 9 TMEM columns, 10 dynamic shared memory bytes, 11 grid, 12 tiles, 13 K slices (split-K with a workspace of
- * ws_bytes), 14 channel chunks per slice, 15 statistics in the epilogue.                                       */
+ * ws_bytes), 14 channel chunks per slice, 15 statistics in the epilogue.                                        has_res = 2 asks for the plan of the
+ * dual-output launch (hl_conv2d_dual: 12 KB of shared memory reserved for the second statistics row, never split). */
 int hl_conv2d_plan_info(int x_dtype, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int has_res,
                         int want_stats, int64_t ws_bytes, int *out);
 int hl_conv_set_split(int ksplit);
@@ -182,6 +183,15 @@ int hl_conv2d(const void *x, int x_dtype, int ldx, const void *wpk, const float 
               const float *residual /*nullable*/, int ldr, void *y, int ldy, double *stats /*nullable*/,
               int stats_ld, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int flags,
               void *stream);
+/* Two results from ONE pass over the operands:  y = conv(x) + bias + residual  and  y2 = conv(x) + bias  (both fp32,
+ * each with its own optional statistics row; stats and stats2 are given together or not at all).  Replaces the two
+ * launches of the ControlNet projection: y2 = h_cond feeds the next ControlNet block (unet.py:599-601), y = hs + h_cond
+ * is the decoder's skip slice (unet.py:606).  On the tcgen05 kernel one epilogue warpgroup drains every accumulator
+ * chunk with the residual into y while the other writes the plain chunk into y2; other shapes run as two launches. */
+int hl_conv2d_dual(const void *x, int x_dtype, int ldx, const void *wpk, const float *bias, const float *residual,
+                   int ldr, float *y, int ldy, double *stats /*nullable*/, int stats_ld, float *y2, int ldy2,
+                   double *stats2 /*nullable*/, int stats2_ld, int B, int H, int W, int Cin, int Cout, int ksize,
+                   int stride, int flags, void *stream);
 
 /* ---- launch mode ------------------------------------------------------------------------------ */
 

@@ -194,6 +194,13 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
         hl_gn_stats(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, stream)
 
 
+def hl_conv2d_dual(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, y2, ldy2, stats2, stats2_ld, B, H, W,
+                   Cin, Cout, ksize, stride, flags, stream):
+    """y = conv + residual, y2 = conv: the two launches the entry point replaces."""
+    hl_conv2d(x, x_dtype, ldx, wpk, bias, None, 0, y2, ldy2, stats2, stats2_ld, B, H, W, Cin, Cout, ksize, stride, flags, stream)
+    hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, B, H, W, Cin, Cout, ksize, stride, flags, stream)
+
+
 def hl_attention(qkv, qkv_dtype, ldq, out, out_dtype, ldo, B, T, C, heads, round_tf32, stream):
     v = torch.from_numpy(pitched(qkv, B * T, 3 * C, ldq, _dt(qkv_dtype)).astype(np.float32))
     v = v.reshape(B, T, heads, 3, C // heads)

@@ -157,19 +157,26 @@ def test_conv_planner_on_every_production_launch(B):
     plan = _StepPlan(model, torch.device("cpu"), B, 256, 256)
     lib = _lib.load()
     n_conv = n_split = 0
+    n_dual = 0
     for name, a, _br in plan.calls:
-        if name != "hl_conv2d":
+        if name == "hl_conv2d_dual":          # the 24 ControlNet projections: one launch, two results (never split)
+            n_dual += 1
+            Bn, H, W, Cin, Cout, k, s = a[15:22]
+            has_res, want_stats, ws = 2, 1, 0       # has_res = 2: plan of the dual-output launch
+        elif name == "hl_conv2d":
+            Bn, H, W, Cin, Cout, k, s = a[11:18]
+            has_res, want_stats, ws = int(a[5] is not None), int(a[9] is not None), plan.SPLITK_BYTES
+        else:
             continue
         n_conv += 1
-        Bn, H, W, Cin, Cout, k, s = a[11:18]
         out = (ctypes.c_int * 16)()
-        assert lib.hl_conv2d_plan_info(1, Bn, H, W, Cin, Cout, k, s, int(a[5] is not None), int(a[9] is not None),
-                                       plan.SPLITK_BYTES, out) == 0
+        assert lib.hl_conv2d_plan_info(1, Bn, H, W, Cin, Cout, k, s, has_res, want_stats, ws, out) == 0
         o = list(out)
-        assert o[0] == 1, ("tensor-core path must apply", a[11:18])
+        assert o[0] == 1, ("tensor-core path must apply", (Bn, H, W, Cin, Cout, k, s))
         pair, mh, n_tile, halo, a_slots, b_slots, nbuf, acc, tmem, smem, grid, tiles, S, kc = o[1:15]
         assert pair in (1, 2) and mh in (1, 2) and n_tile % 32 == 0 and 32 <= n_tile <= 256
-        assert smem <= (227 - 15) * 1024 and tmem <= 512 and tmem >= acc * mh * n_tile
+        assert smem + (12288 if name == "hl_conv2d_dual" else 0) <= (227 - 15) * 1024     # dual: + group 1's accumulators
+        assert tmem <= 512 and tmem >= acc * mh * n_tile
         assert a_slots >= 2 and b_slots >= 2 and 2 <= nbuf <= 4
         assert 1 <= grid <= 148 and tiles >= 1
         assert kc * S == Cin // 64
@@ -179,7 +186,7 @@ def test_conv_planner_on_every_production_launch(B):
             assert k == 3 and tiles <= 148 // (pair if pair == 2 else 1) * pair   # one wave
             assert S * Bn * Ho * Wo * _lib.load().hl_conv_cout_pad(Cout) * 4 <= plan.SPLITK_BYTES
             assert o[15] == 0                                    # statistics move to the second pass
-    assert n_conv == 280 and n_split >= 20
+    assert n_conv == 256 and n_dual == 24 and n_split >= 20
 
 
 def test_state_dict_contract_vs_reference():

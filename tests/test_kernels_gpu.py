@@ -369,6 +369,63 @@ def test_conv_split_k(dev, shape, split, residual, cta2):
     _check_stats(st16, y16, Cout)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 192, 192, 1), (4, 32, 32, 384, 384, 1), (4, 8, 8, 768, 768, 1),   # ControlNet projections
+                                   (1, 128, 128, 192, 192, 1), (2, 32, 32, 192, 192, 3), (2, 8, 8, 96, 40, 1)])
+@pytest.mark.parametrize("split3", [False, True])
+def test_conv_dual_output(dev, shape, split3):
+    """hl_conv2d_dual: y = conv + residual and y2 = conv from one launch, each with its statistics row -- bit-identical
+    to the two hl_conv2d launches it replaces (epilogue statistics, the separate statistics kernel at 8^2, the 3x3
+    shape, and the last shape's CUDA-core fallback)."""
+    from humanliff_b200.unet import pack_conv
+    from humanliff_b200 import _lib
+    B, H, W, Cin, Cout, k = shape
+    if split3 and Cin % 64:
+        pytest.skip("the hi + lo operand passes exist on the tensor-core path only")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, Cin, generator=g) * 3
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    if split3:
+        xs = x * 2.0 ** -4
+        hi = xs.half()
+        xop = torch.cat([hi, (xs - hi.float()).half()], -1).contiguous().to(dev)
+        ldx, flags, mode = 2 * Cin, _lib.CONV_SPLIT3, "split"
+    else:
+        xop, ldx, flags, mode = x.half().to(dev), Cin, 0, None
+    wpk, bpk = pack_conv(w, b, Cin, "fp16", dev, mode=mode)
+    ldy, ldy2 = Cout + 32, Cout                                    # y: a slice of a wider (concat) buffer
+
+    def run(dual):
+        y = torch.zeros(B, H, W, ldy, device=dev)
+        y2 = torch.zeros(B, H, W, ldy2, device=dev)
+        st = torch.zeros(B * ldy * 2, device=dev, dtype=torch.float64)
+        st2 = torch.zeros(B * ldy2 * 2, device=dev, dtype=torch.float64)
+        want = Cout % 4 == 0
+        if dual:
+            _call("hl_conv2d_dual", xop.data_ptr(), 1, ldx, wpk.data_ptr(), bpk.data_ptr(), res.data_ptr(), Cout, y.data_ptr(), ldy,
+                  st.data_ptr() if want else None, ldy, y2.data_ptr(), ldy2, st2.data_ptr() if want else None, ldy2, B, H, W, Cin,
+                  Cout, k, 1, flags, _stream())
+        else:
+            _call("hl_conv2d", xop.data_ptr(), 1, ldx, wpk.data_ptr(), bpk.data_ptr(), None, 0, y2.data_ptr(), ldy2,
+                  st2.data_ptr() if want else None, ldy2, B, H, W, Cin, Cout, k, 1, flags, _stream())
+            _call("hl_conv2d", xop.data_ptr(), 1, ldx, wpk.data_ptr(), bpk.data_ptr(), res.data_ptr(), Cout, y.data_ptr(), ldy,
+                  st.data_ptr() if want else None, ldy, B, H, W, Cin, Cout, k, 1, flags, _stream())
+        torch.cuda.synchronize()
+        return y.cpu(), y2.cpu(), st.cpu().reshape(B, ldy, 2), st2.cpu().reshape(B, ldy2, 2)
+    y, y2, st, st2 = run(True)
+    ry, ry2, rst, rst2 = run(False)
+    assert torch.equal(y, ry) and torch.equal(y2, ry2)
+    assert float(y[..., Cout:].abs().max()) == 0.0, "channels beyond Cout of the wider buffer stay untouched"
+    assert torch.allclose(st, rst, rtol=1e-12, atol=1e-9) and torch.allclose(st2, rst2, rtol=1e-12, atol=1e-9)
+    ref2 = F.conv2d(x.half().float().permute(0, 3, 1, 2), w.half().float(), b, padding=k // 2).permute(0, 2, 3, 1)
+    assert rel_l2(y2, ref2) < (2e-5 if not split3 else 1e-3)      # split3 carries MORE bits than the fp16 reference here
+    assert rel_l2(y[..., :Cout] - y2, res.cpu()) < 1e-6
+    if Cout % 4 == 0:
+        _check_stats(st2, y2.permute(0, 3, 1, 2), Cout)
+        _check_stats(st, y[..., :Cout].permute(0, 3, 1, 2), Cout)
+
+
 def test_conv_tc_strided_output_and_input(dev):
     """Operands living inside wider (concat) buffers: ldx > Cin, ldy > Cout, statistics row at an offset."""
     from humanliff_b200.unet import pack_conv

@@ -27,9 +27,23 @@ def conv_h(a):
     return a[12]
 
 
+def is_conv(n):
+    return n in ("hl_conv2d", "hl_conv2d_dual")
+
+
+def H_of(n, a):
+    return a[16] if n == "hl_conv2d_dual" else a[12]
+
+
+def k_of(n, a):
+    return a[20] if n == "hl_conv2d_dual" else a[16]
+
+
 def pix(name, a):
     if name == "hl_conv2d":
         return a[12] * a[13]
+    if name == "hl_conv2d_dual":
+        return a[16] * a[17]
     if name == "hl_gn_apply":
         return a[14]
     if name == "hl_attention":
@@ -56,13 +70,13 @@ print(f"full step (graph replay, no I/O copies): {base:.3f} ms, {len(full)} entr
 if os.environ.get("HL_ABLATE_FULL_ONLY"):
     sys.exit(0)
 cases = {
-    "conv H<=8": lambda n, a: n == "hl_conv2d" and conv_h(a) <= 8,
-    "conv H==16": lambda n, a: n == "hl_conv2d" and conv_h(a) == 16,
-    "conv H==32": lambda n, a: n == "hl_conv2d" and conv_h(a) == 32,
-    "conv H==64": lambda n, a: n == "hl_conv2d" and conv_h(a) == 64,
-    "conv H==128": lambda n, a: n == "hl_conv2d" and conv_h(a) == 128,
-    "conv H==256": lambda n, a: n == "hl_conv2d" and conv_h(a) == 256,
-    "conv 1x1 H>=128": lambda n, a: n == "hl_conv2d" and conv_h(a) >= 128 and a[16] == 1,
+    "conv H<=8": lambda n, a: is_conv(n) and H_of(n, a) <= 8,
+    "conv H==16": lambda n, a: is_conv(n) and H_of(n, a) == 16,
+    "conv H==32": lambda n, a: is_conv(n) and H_of(n, a) == 32,
+    "conv H==64": lambda n, a: is_conv(n) and H_of(n, a) == 64,
+    "conv H==128": lambda n, a: is_conv(n) and H_of(n, a) == 128,
+    "conv H==256": lambda n, a: is_conv(n) and H_of(n, a) == 256,
+    "conv 1x1 H>=128": lambda n, a: is_conv(n) and H_of(n, a) >= 128 and k_of(n, a) == 1,
     "gn_apply all": lambda n, a: n == "hl_gn_apply",
     "gn_apply HW>=128^2": lambda n, a: n == "hl_gn_apply" and a[14] >= 128 * 128,
     "gn_apply HW<=32^2": lambda n, a: n == "hl_gn_apply" and a[14] <= 32 * 32,

@@ -621,6 +621,7 @@ def layered_block(model, device, peaks, views=40, grid_res=512):
     # warm-up: plan build + graph capture at B = 1, renderer packing
     layered.sample_layer(model, _ShortLoop(diff250, 3), 0, 1, device=device)
     r.render_rays(torch.zeros(3, 9, 256, 256, device=device), bounds, *cams[0])
+    r.density_grid(tp, torch.zeros(3, 9, 256, 256, device=device), resolution=grid_res)   # the 4 B x res^3 output block enters the caching allocator
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     outs = layered.sample_all_layers(model, diff250, 1, device=device)

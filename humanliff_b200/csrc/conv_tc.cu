@@ -1334,7 +1334,11 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
             return HL_E_CUDA;
         }
     }
-    static bool smem_configured = false;
+    // cudaFuncSetAttribute is per device: remember which ordinals have been configured
+    static bool configured[64] = {};
+    int dev_ord = 0;
+    HL_CHECK_CUDA(cudaGetDevice(&dev_ord));
+    bool &smem_configured = configured[dev_ord & 63];
     if (!smem_configured) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));

@@ -162,7 +162,7 @@ extern "C" int hl_nchw_to_nhwc(const float *src, const float *src2, void *dst, i
     return HL_OK;
 }
 
-__global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, float *__restrict__ dst,
+__global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, int off2, float *__restrict__ dst,
                                int C, int HW, int64_t n_tiles, int tiles_per_img) {
     hl_pdl_enter();
     __shared__ float tile[32][33];
@@ -172,7 +172,12 @@ __global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, float *__r
         for (int c0 = 0; c0 < C; c0 += 32) {
             for (int py = threadIdx.y; py < 32; py += blockDim.y) {
                 int c = c0 + threadIdx.x, p = p0 + py;
-                tile[py][threadIdx.x] = (c < C && p < HW) ? src[((int64_t)b * HW + p) * ld + c] : 0.f;
+                float v = 0.f;
+                if (c < C && p < HW) {
+                    const float *row = src + ((int64_t)b * HW + p) * ld + c;
+                    v = off2 ? row[0] + row[off2] : row[0];       // off2: the two halves of a split-weight conv result
+                }
+                tile[py][threadIdx.x] = v;
             }
             __syncthreads();
             for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
@@ -184,16 +189,26 @@ __global__ void k_nhwc_to_nchw(const float *__restrict__ src, int ld, float *__r
     }
 }
 
-extern "C" int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW,
-                               void *stream) {
-    HL_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && ld >= C);
+static int nhwc_to_nchw_launch(const float *src, int ld, int off2, float *dst, int B, int C, int HW, void *stream) {
+    HL_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && ld >= C && off2 >= 0 && (off2 == 0 || ld >= off2 + C));
     int tiles_per_img = hl_cdiv(HW, 32);
     int64_t n_tiles = (int64_t)B * tiles_per_img;
     dim3 blk(32, 8);
-    HL_CHECK_CUDA(hl_launch(k_nhwc_to_nchw, dim3(grid_for(n_tiles, 1, 16)), dim3(blk), 0, (cudaStream_t)stream, 
-        src, ld, dst, C, HW, n_tiles, tiles_per_img));
+    HL_CHECK_CUDA(hl_launch(k_nhwc_to_nchw, dim3(grid_for(n_tiles, 1, 16)), dim3(blk), 0, (cudaStream_t)stream,
+        src, ld, off2, dst, C, HW, n_tiles, tiles_per_img));
     HL_CHECK_LAUNCH();
     return HL_OK;
+}
+
+extern "C" int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW,
+                               void *stream) {
+    return nhwc_to_nchw_launch(src, ld, 0, dst, B, C, HW, stream);
+}
+
+extern "C" int hl_nhwc_to_nchw_sum2(const float *src, int ld, int off2, float *dst, int B, int C, int HW,
+                                    void *stream) {
+    HL_CHECK_ARG(off2 > 0);
+    return nhwc_to_nchw_launch(src, ld, off2, dst, B, C, HW, stream);
 }
 
 // ------------------------------------------------------------------------------------------

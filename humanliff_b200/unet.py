@@ -61,7 +61,9 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
 
     ``mode`` (fp16 only; the high-precision operand passes of DESIGN.md 3, HL_CONV_SPLIT3 / SPLIT2P in the header):
     ``"scaled"`` weights * 2^4; ``"split"`` two slabs ``{W_hi, W_lo}`` of the scaled weights, ``W_lo = fp16(W - W_hi)``;
-    ``"split_a"`` plain weights for an operand that is an (unscaled) hi | lo pair; ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
+    ``"split_a"`` plain weights for an operand that is an (unscaled) hi | lo pair; ``"split_w"`` the weights as an fp16
+    hi + lo pair stacked along Cout -- rows ``[0, Cout)`` = W_hi, rows ``[Cout_pad, Cout_pad + Cout)`` = W_lo of a
+    ``2 * Cout_pad``-row operand whose two result halves the caller sums (plain fp16 activations); ``"split_packed"`` (stem: 2 * Cin <= Cin_pad) slabs ``{[W_hi | W_hi], [W_lo | 0]}`` for
     an operand row ``[hi(Cin) 0.. | lo(Cin) 0..]`` with the lo half at channel Cin_pad / 2."""
     lib = _lib.load()
     device = device if device is not None else weight.device
@@ -73,6 +75,13 @@ def pack_conv(weight, bias, cin_pad=None, precision="fp16", device=None, mode=No
     cout_pad = lib.hl_conv_cout_pad(cout)
     pk = torch.zeros(kh * kw, cout_pad, cin_pad, device=device, dtype=torch.float32)
     pk[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    if precision == "fp16" and mode == "split_w":
+        hi = pk.to(torch.float16)
+        lo = (pk - hi.float()).to(torch.float16)
+        b = torch.zeros(2 * cout_pad, device=device, dtype=torch.float32)
+        if bias is not None:
+            b[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+        return torch.cat([hi, lo], 1).contiguous(), b                 # [taps][2 * Cout_pad][Cin_pad]
     if precision == "fp16":
         if mode in ("scaled", "split"):
             pk = pk * HP_SCALE
@@ -108,7 +117,10 @@ def _hp_mode(name, cin, cin_pad):
     if name.endswith("skip_connection") or name.startswith("input_blocks_proj_cond."):
         return "split"
     if name == "out.2":
-        return "split_a"          # activation pair only: N = 27 runs the tensor core at 20 %, a third pass costs 0.13 ms
+        # weight pair only, stacked along Cout (N = 64 costs the tensor core what N = 32 does: at this width the MMA
+        # is bound by fetching its 128 activation rows): ONE pass, the same emulated error as the activation pair in
+        # two passes (4.75e-4 either way, tools/error_budget.py), -0.13 ms/step
+        return os.environ.get("HL_OUT_CONV", "split_w")
     if name in ("input_blocks.0.0", "input_blocks_cond.0.0"):
         return "split_packed" if 2 * cin <= cin_pad else None
     if name.endswith(".conv") or name.endswith(".op"):
@@ -121,6 +133,7 @@ class _Conv:
 
     def __init__(self, name, cin, cout, ksize, stride=1, cin_pad=None):
         self.name, self.cin, self.cout, self.ksize, self.stride = name, cin, cout, ksize, stride
+        self.cout_launch = cout  # output channels of the launch (split_w: 2 * Cout_pad, the hi and lo halves)
         self.cin_pad = cin_pad or cin
         self.w = None
         self.b = None
@@ -180,6 +193,8 @@ class UNetModel(nn.Module):
         if self.hi_precision:
             for c in self._convs.values():
                 c.hp = _hp_mode(c.name, c.cin, c.cin_pad)
+                if c.hp == "split_w":
+                    c.cout_launch = 2 * (32 * ((c.cout + 31) // 32))
         self._packed_key = None
         self._plans = {}
         self.use_cuda_graph = True
@@ -480,7 +495,7 @@ class _StepPlan:
             flags |= _lib.CONV_SPLIT2P
         self.emit("hl_conv2d", x_ptr, self.dt, ldx, _ptr(c.w), _ptr(c.b), res.ptr if res else None,
                   res.ld if res else 0, dst.ptr, dst.ld, st, dst.st_ld if st else 0, self.B, H, W, c.cin_pad,
-                  c.cout, c.ksize, c.stride, flags)
+                  c.cout_launch, c.ksize, c.stride, flags)
 
     def conv_dual(self, cname, x_ptr, ldx, res, dst, dst2, H, W):
         """One launch, two results (hl_conv2d_dual): dst = conv + res, dst2 = conv; both fp32 with statistics."""
@@ -535,6 +550,8 @@ class _StepPlan:
         m, B = self.m, self.B
         cin, cout, H, W = blk["cin"], blk["cout"], x.H, x.W
         assert x.C == cin and dst.C == cout
+        # the shared scratch buffers are sized by _scratch_sizes' bound: check the real footprint of every block
+        assert B * H * W * max(cin, cout) <= self.max_act, ("scratch bound", blk["p"], cin, cout, H, W)
         act = _ptr(self.scratch("act", self.max_act, op=True))
         # the tensor between the two convs is read by out_layers' GroupNorm only: in the fp16 plan conv1's epilogue
         # rounds it once to fp16 (statistics of the rounded values), halving its write, its read and the epilogue's
@@ -545,6 +562,7 @@ class _StepPlan:
         if blk["skip"] is not None:
             raw = _ptr(self.scratch("raw", self.max_raw, op=True))
             ldraw, raw_mode = self.raw_operand(blk["skip"], cin)
+            assert B * H * W * ldraw <= self.max_raw, ("scratch bound (raw)", blk["p"])
         self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=ldraw, raw_mode=raw_mode)
         self.conv(blk["c1"], act, cin, None, h, H, W)
         film = ("film", blk["film_off"])
@@ -560,6 +578,7 @@ class _StepPlan:
         """unet.py:244-274."""
         m, B = self.m, self.B
         C, H, W = blk["c"], x.H, x.W
+        assert B * H * W * C <= self.max_act and B * H * W * 3 * C <= self.max_qkv, ("scratch bound", blk["p"])
         act = _ptr(self.scratch("act", self.max_act, op=True))
         # fp16 mode: qkv is only ever an attention operand -> the conv writes it as fp16
         f16 = self.dt == _lib.DT_F16
@@ -598,11 +617,13 @@ class _StepPlan:
             elif kind == "down":
                 op = _ptr(self.scratch("raw", self.max_raw, op=True))
                 ldop, mode = self.raw_operand(blk["c"], x.C)
+                assert self.B * x.H * x.W * ldop <= self.max_raw, ("scratch bound (raw)", dst_name)
                 self.cast(x, op, ldop, mode)
                 self.conv(blk["c"], op, ldop, None, out, x.H, x.W)
             elif kind == "up":
                 op = _ptr(self.scratch("upbuf", self.max_act, op=True))
                 _, mode = self.raw_operand(blk["c"], x.C)
+                assert self.B * H * W * x.C <= self.max_act, ("scratch bound", dst_name)
                 self.emit("hl_upsample2x", x.ptr, x.ld, op, self.dt, x.C, self.B, x.H, x.W, x.C, self.rnd | mode)
                 self.conv(blk["c"], op, x.C, None, out, H, W)
             else:
@@ -780,9 +801,15 @@ class _StepPlan:
         assert B * H * W * ldo <= self.max_act
         self.gn("out.0", x, act, ldo, True, out_mode=omode)
         co_pad = 32 * ((m.out_channels + 31) // 32)
-        eps = _Ref(_ptr(self.buf("eps_nhwc", B * H * W * co_pad)), co_pad, m.out_channels, H, W, None, 0)
-        self.conv("out.2", act, ldo, None, eps, H, W, want_stats=False)
-        self.emit("hl_nhwc_to_nchw", eps.ptr, co_pad, _ptr(self.out), B, m.out_channels, H * W)
+        if m._convs["out.2"].hp == "split_w":
+            # result = [conv with W_hi | conv with W_lo]: the halves are summed on the way to NCHW
+            eps = _Ref(_ptr(self.buf("eps_nhwc", B * H * W * 2 * co_pad)), 2 * co_pad, 2 * co_pad, H, W, None, 0)
+            self.conv("out.2", act, ldo, None, eps, H, W, want_stats=False)
+            self.emit("hl_nhwc_to_nchw_sum2", eps.ptr, 2 * co_pad, co_pad, _ptr(self.out), B, m.out_channels, H * W)
+        else:
+            eps = _Ref(_ptr(self.buf("eps_nhwc", B * H * W * co_pad)), co_pad, m.out_channels, H, W, None, 0)
+            self.conv("out.2", act, ldo, None, eps, H, W, want_stats=False)
+            self.emit("hl_nhwc_to_nchw", eps.ptr, co_pad, _ptr(self.out), B, m.out_channels, H * W)
 
         # --- resolve the symbolic statistics / FiLM pointers ---
         self.stats = torch.zeros(max(self._stats_off, 2), device=dev, dtype=torch.float64)

@@ -116,6 +116,10 @@ int hl_nchw_to_nhwc(const float *src, const float *src2 /*nullable*/, void *dst,
                     int C, int HW, int ld, int round_tf32, void *stream);
 /* NHWC fp32 (pitch ld) -> NCHW fp32.                                                             */
 int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW, void *stream);
+/* dst[b, c, p] = src[b, p, c] + src[b, p, off2 + c]: the output conv of the fp16 plan carries its weights as an fp16
+ * hi + lo pair stacked along Cout (rows [0, C) = W_hi, rows [off2, off2 + C) = W_lo; unet.py:475,612), so the two
+ * halves of its NHWC result are summed on the way to NCHW.                                                      */
+int hl_nhwc_to_nchw_sum2(const float *src, int ld, int off2, float *dst, int B, int C, int HW, void *stream);
 /* dst[:, 0:C1] = a ; dst[:, C1:C1+C2] = b (+ c)   -- th.cat([h, hs.pop()+hs_cond.pop()], 1),
  * unet.py:606.  Any of the three sources may alias a slice of another buffer via its pitch.     */
 int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb, const float *c /*nullable*/,

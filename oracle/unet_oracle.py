@@ -81,7 +81,7 @@ def product_fp16_plan(prefix):
     """Per-layer policy emulating the product's ``precision="fp16"`` plan: every contraction rounds
     its operands to fp16 except the convs that read the raw residual stream (1x1 skip, ControlNet projection,
     the stems), which carry hi + lo fp16 pairs for both operands in three tensor-core passes, and the output conv
-    (activation pair only, two passes); the Upsample / Downsample convs read a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
+    (weight pair only, stacked along Cout: one pass); the Upsample / Downsample convs read a 2^-4-scaled fp16 operand.  Pass as ``operand_round=product_fp16_plan``."""
     import re
     if prefix.endswith(".h"):
         return "fp16"                            # ResBlock intermediate (in_layers output) stored as fp16
@@ -89,7 +89,7 @@ def product_fp16_plan(prefix):
             or re.fullmatch(r"input_blocks(_cond)?\.0\.0", prefix)):
         return "fp16_split3"
     if prefix == "out.2":
-        return "fp16_split2a"                    # activation pair only (weights plain fp16)
+        return "fp16_split2w"                    # weight pair only (activations plain fp16), one tensor-core pass
     if prefix.endswith(".conv") or prefix.endswith(".op"):
         return "fp16_scaled"
     return "fp16"
@@ -119,6 +119,11 @@ def _conv(x, sd, prefix, nm, stride=1, raw=False):
         f16 = lambda t: t.to(torch.float16).to(torch.float32)
         xh = f16(x)
         return F.conv2d(xh + f16(x - xh), f16(w), sd[prefix + ".bias"], stride=stride, padding=pad)
+    if nm.mode == "fp16_split2w":
+        f16 = lambda t: t.to(torch.float16).to(torch.float32)
+        wh = f16(w)
+        return F.conv2d(f16(x), wh, sd[prefix + ".bias"], stride=stride, padding=pad) + \
+            F.conv2d(f16(x), f16(w - wh), None, stride=stride, padding=pad)
     if nm.mode == "fp16_split3":
         # the product's high-precision conv: activations * 2^-4 and weights * 2^4 each carried as an fp16 hi + lo
         # pair, three tensor-core passes hi.hi + lo.hi + hi.lo (the lo.lo term, 2^-22 relative, is dropped)

@@ -101,6 +101,11 @@ def hl_nhwc_to_nchw(src, ld, dst, B, C, HW, stream):
     view(dst, B * C * HW).reshape(B, C, HW)[...] = v.reshape(B, HW, C).transpose(0, 2, 1)
 
 
+def hl_nhwc_to_nchw_sum2(src, ld, off2, dst, B, C, HW, stream):
+    v = pitched(src, B * HW, C, ld) + pitched(src + 4 * off2, B * HW, C, ld)
+    view(dst, B * C * HW).reshape(B, C, HW)[...] = v.reshape(B, HW, C).transpose(0, 2, 1)
+
+
 def hl_cast_operand(src, lds, dst, dst_dtype, ldd, C, npix, round_tf32, stream):
     _store_operand(dst, dst_dtype, npix, C, ldd, pitched(src, npix, C, lds).copy(), round_tf32)
 

@@ -189,6 +189,7 @@ class UNetModel(nn.Module):
         self.hi_precision = precision == "fp16" and os.environ.get("HL_HIPREC", "1") != "0"
         self.h_f16 = precision == "fp16" and os.environ.get("HL_H_F16", "1") != "0"     # ResBlock intermediate as fp16
         self.dual_proj = os.environ.get("HL_DUAL_PROJ", "1") != "0"    # ControlNet projection: one launch, two results
+        self.side_skip = os.environ.get("HL_SIDE_SKIP", "1") != "0"    # decoder <= 32^2: 1x1 skip conv on the side stream
         self._build_plan()
         if self.hi_precision:
             for c in self._convs.values():
@@ -386,7 +387,7 @@ class UNetModel(nn.Module):
         forward takes effect."""
         self._pack(device)
         key = (str(device), B, H, W, self.use_cuda_graph, self.concurrent_encoders, self.batch_split, self.split_k,
-               self.programmatic_launch, self.h_f16, self.dual_proj)
+               self.programmatic_launch, self.h_f16, self.dual_proj, self.side_skip)
         plan = self._plans.get(key)
         if plan is None:
             parts = self.batch_split
@@ -564,12 +565,26 @@ class _StepPlan:
             ldraw, raw_mode = self.raw_operand(blk["skip"], cin)
             assert B * H * W * ldraw <= self.max_raw, ("scratch bound (raw)", blk["p"])
         self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=ldraw, raw_mode=raw_mode)
+        # The 1x1 skip conv needs only GroupNorm-1's raw copy: in the decoder's low-resolution stretch (one stream, every
+        # kernel a fraction of a wave, the chain bound by launch latency) it runs on the side stream next to conv1 / GroupNorm-2
+        overlap_skip = (blk["skip"] is not None and self.side_skip and self.branch == 0 and self.decoding
+                        and H * W <= 32 * 32)
+        s = None
+        if blk["skip"] is not None:
+            s = _Ref(_ptr(self.scratch("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
+        if overlap_skip:
+            self.emit_sync("fork")
+            self.branch = 1
+            self.conv(blk["skip"], raw, ldraw, None, s, H, W, want_stats=False)
+            self.branch = 0
         self.conv(blk["c1"], act, cin, None, h, H, W)
         film = ("film", blk["film_off"])
         self.gn(blk["n2"], h, act, cout, True, film=film)
         if blk["skip"] is not None:
-            s = _Ref(_ptr(self.scratch("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
-            self.conv(blk["skip"], raw, ldraw, None, s, H, W, want_stats=False)
+            if overlap_skip:
+                self.emit_sync("join")
+            else:
+                self.conv(blk["skip"], raw, ldraw, None, s, H, W, want_stats=False)
             self.conv(blk["c2"], act, cout, s, dst, H, W)
         else:
             self.conv(blk["c2"], act, cout, x, dst, H, W)
@@ -752,6 +767,8 @@ class _StepPlan:
         controlnet = m._enc_cond is not None
         self.concurrent = controlnet and m.concurrent_encoders
         self.hs, self.keep_hs = None, controlnet
+        self.decoding = False                  # set once the two encoders have joined
+        self.side_skip = self.concurrent and m.side_skip
         self.n_events = len(m._enc) + 1 if self.concurrent else 0
         self.film_event = len(m._enc)          # recorded on the main stream once the FiLM table is complete
         if controlnet:
@@ -790,6 +807,7 @@ class _StepPlan:
             self.emit_sync("join")
 
         # --- decoder (unet.py:604-609) ---
+        self.decoding = True
         ndec = len(m._dec)
         for j, layers in enumerate(m._dec):
             dst = self.cat_h[j + 1] if j + 1 < ndec else None

@@ -99,6 +99,8 @@ struct TcParams {
     double *stats2;
     int stats2_ld;
     int sacc2_off;           // byte offset (from the aligned dynamic shared-memory base) of group 1's fp64 accumulators
+    int stats_rows;          // 0: one sample per 128-pixel box (per-CTA fp64 accumulators); 32 | 64: a box holds 128 / rows
+                             // samples of `rows` pixels each (8^2: 64): the per-quarter sums go straight to global memory
 };
 
 // profiling: cycles CTA 0 spends blocked in each wait, accumulated into p.prof[slot]
@@ -532,7 +534,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
                 box_origin(p, mt, half, rank, w0, h0, n0);
-                if (p.stats && n0 != cur_n) {
+                if (p.stats && !p.stats_rows && n0 != cur_n) {
                     if (cur_n >= 0) flush_stats();
                     cur_n = n0;
                 }
@@ -666,7 +668,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                         spart[eg][rq][col] = make_float2(s, ss);
                         named_bar(4 + eg, EPI_THREADS);
-                        if (rq == 0 && nbase + col < p.Cout) {
+                        if (p.stats_rows) {
+                            // several samples per box (8^2: rows 0-63 sample n0, 64-127 sample n0 + 1): quarter sums of
+                            // one sample are combined in a fixed order and added to the global fp64 row directly (a
+                            // handful of CTAs per launch at these sizes: no contention worth a shared-memory stage)
+                            const int per = p.stats_rows >> 5;                 // quarters per sample: 1 | 2
+                            if (rq % per == 0 && nbase + col < p.Cout) {
+                                const int nn = n0 + rq / per;
+                                if (nn < p.B) {
+                                    float2 t = spart[eg][rq][col];
+                                    if (per == 2) { const float2 u = spart[eg][rq + 1][col]; t.x += u.x; t.y += u.y; }
+                                    double *dst = (plain_g ? p.stats2 + ((size_t)nn * p.stats2_ld + nbase + col) * 2
+                                                           : p.stats + ((size_t)nn * p.stats_ld + nbase + col) * 2);
+                                    atomicAdd(dst, (double)t.x);
+                                    atomicAdd(dst + 1, (double)t.y);
+                                }
+                            }
+                        } else if (rq == 0 && nbase + col < p.Cout) {
                             const float2 p0 = spart[eg][0][col], p1 = spart[eg][1][col], p2 = spart[eg][2][col],
                                          p3 = spart[eg][3][col];
                             atomicAdd(&sacc_s[nbase + col], (double)((p0.x + p1.x) + (p2.x + p3.x)));
@@ -1088,8 +1106,11 @@ int choose_split(Plan &pl, int kind, int B, int H, int W, int Cin, int Cout, int
 // in-epilogue GroupNorm statistics need one sample per 128-pixel box (every box row valid)
 bool plan_epi_stats(const Plan &pl, bool want_stats) {
     if (!want_stats || g_tune_epi_stats == 0) return false;
-    return pl.t.bn == 1 && pl.cout_pad <= STATS_MAX_C;
+    if (pl.cout_pad > STATS_MAX_C) return false;
+    // one sample per box, or whole 32-row quarters per sample (8^2: two samples of 64 rows; 4^2 and below: stats kernel)
+    return pl.t.bn == 1 || (128 / pl.t.bn) % 32 == 0;
 }
+int plan_stats_rows(const Plan &pl) { return pl.t.bn == 1 ? 0 : 128 / pl.t.bn; }
 
 }  // namespace
 
@@ -1268,11 +1289,13 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         ldy = pl.cout_pad;
         y_f16 = 0;
     }
+    p.stats_rows = 0;
     if (epi_stats) {
         p.stats = stats;
         p.stats_ld = stats_ld;
         p.stats2 = stats2;
         p.stats2_ld = stats2_ld;
+        p.stats_rows = plan_stats_rows(pl);
     }
     const CUtensorMapDataType dt = kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 

@@ -280,6 +280,7 @@ TC_SHAPES = [
     (1, 16, 16, 384, 1152, 1, 1),    # qkv GEMM
     (1, 64, 64, 192, 27, 3, 1),      # out conv: Cout 27 (TMA store clipped at the channel edge)
     (3, 8, 8, 64, 32, 3, 1),         # bn = 2 with B = 3: out-of-range batch rows zero-filled / clipped
+    (3, 8, 8, 768, 768, 1, 1),       # 1x1 at 8^2, B odd: statistics of two samples per box from the epilogue, padded sample skipped
     (1, 16, 8, 128, 64, 3, 1),       # non-square
     (2, 64, 64, 192, 192, 3, 2),     # Downsample conv: stride 2 through TMA element strides
     (1, 256, 256, 64, 128, 3, 2),    # stride 2, 256-wide traversal box

@@ -26,7 +26,6 @@ SIGNATURES = {
     "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_nhwc_to_nchw": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
     "hl_nhwc_to_nchw_sum2": (c_int, [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_p]),
-    "hl_concat_add": (c_int, [c_p, c_int, c_int, c_p, c_int, c_p, c_int, c_int, c_p, c_int, c_i64, c_p]),
     "hl_upsample2x": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "hl_cast_operand": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_i64, c_int, c_p]),
     "hl_zero": (c_int, [c_p, c_i64, c_p]),

@@ -212,45 +212,8 @@ extern "C" int hl_nhwc_to_nchw_sum2(const float *src, int ld, int off2, float *d
 }
 
 // ------------------------------------------------------------------------------------------
-// concat (+ add), upsample, tf32 staging copy -- float4 over channels (all C are multiples of 4)
+// upsample, operand cast -- float4 over channels (all C are multiples of 4)
 // ------------------------------------------------------------------------------------------
-__global__ void k_concat_add(const float *__restrict__ a, int lda, int C1,
-                             const float *__restrict__ b, int ldb, const float *__restrict__ c,
-                             int ldc, int C2, float *__restrict__ dst, int ldd, int64_t npix) {
-    hl_pdl_enter();
-    int q1 = C1 >> 2, q = (C1 + C2) >> 2;
-    int64_t total = npix * q;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t p = i / q;
-        int j = (int)(i - p * q);
-        float4 v;
-        if (j < q1) {
-            v = *reinterpret_cast<const float4 *>(a + p * lda + 4 * j);
-        } else {
-            int jj = j - q1;
-            v = *reinterpret_cast<const float4 *>(b + p * ldb + 4 * jj);
-            if (c) {
-                float4 w = *reinterpret_cast<const float4 *>(c + p * ldc + 4 * jj);
-                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-            }
-        }
-        *reinterpret_cast<float4 *>(dst + p * ldd + 4 * j) = v;
-    }
-}
-
-extern "C" int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb,
-                             const float *c, int ldc, int C2, float *dst, int ldd, int64_t npix,
-                             void *stream) {
-    HL_CHECK_ARG(a && b && dst && npix > 0 && C1 % 4 == 0 && C2 % 4 == 0 && lda % 4 == 0 &&
-                 ldb % 4 == 0 && ldd % 4 == 0 && (!c || ldc % 4 == 0) && ldd >= C1 + C2);
-    int64_t total = npix * ((C1 + C2) / 4);
-    HL_CHECK_CUDA(hl_launch(k_concat_add, dim3(grid_for(total, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, a, lda, C1, b, ldb, c,
-                                                                             ldc, C2, dst, ldd, npix));
-    HL_CHECK_LAUNCH();
-    return HL_OK;
-}
-
 __global__ void k_upsample2x(const float *__restrict__ src, int lds, void *__restrict__ dst, int dst_dtype,
                              int ldd, int H, int W, int C, int round_tf32, int64_t total) {
     hl_pdl_enter();

@@ -120,10 +120,6 @@ int hl_nhwc_to_nchw(const float *src, int ld, float *dst, int B, int C, int HW, 
  * hi + lo pair stacked along Cout (rows [0, C) = W_hi, rows [off2, off2 + C) = W_lo; unet.py:475,612), so the two
  * halves of its NHWC result are summed on the way to NCHW.                                                      */
 int hl_nhwc_to_nchw_sum2(const float *src, int ld, int off2, float *dst, int B, int C, int HW, void *stream);
-/* dst[:, 0:C1] = a ; dst[:, C1:C1+C2] = b (+ c)   -- th.cat([h, hs.pop()+hs_cond.pop()], 1),
- * unet.py:606.  Any of the three sources may alias a slice of another buffer via its pitch.     */
-int hl_concat_add(const float *a, int lda, int C1, const float *b, int ldb, const float *c /*nullable*/,
-                  int ldc, int C2, float *dst, int ldd, int64_t npix, void *stream);
 /* nearest x2 upsample of the fp32 residual stream into an operand buffer,
  * F.interpolate(scale_factor=2, mode="nearest"), unet.py:77                                     */
 int hl_upsample2x(const float *src, int lds, void *dst, int dst_dtype, int ldd, int B, int H, int W,

@@ -68,18 +68,14 @@ def test_cast_operand_matches_emulation(dev):
     assert torch.equal(outh.cpu(), x.half())          # round-to-nearest-even, like torch
 
 
-def test_concat_add_and_upsample(dev):
+def test_upsample_and_summed_layout(dev):
     g = torch.Generator().manual_seed(1)
-    npix, C1, C2 = 50, 8, 12
-    a, b, c = torch.randn(npix, C1, generator=g), torch.randn(npix, C2, generator=g), torch.randn(npix, C2, generator=g)
-    ad, bd, cd = a.to(dev), b.to(dev), c.to(dev)
-    out = torch.empty(npix, C1 + C2, device=dev)
-    _call("hl_concat_add", ad.data_ptr(), C1, C1, bd.data_ptr(), C2, cd.data_ptr(), C2, C2, out.data_ptr(),
-          C1 + C2, npix, _stream())
-    assert torch.equal(out.cpu(), torch.cat([a, b + c], 1))
-    _call("hl_concat_add", ad.data_ptr(), C1, C1, bd.data_ptr(), C2, None, C2, C2, out.data_ptr(),
-          C1 + C2, npix, _stream())
-    assert torch.equal(out.cpu(), torch.cat([a, b], 1))
+    # hl_nhwc_to_nchw_sum2: the two halves of a split-weight conv result summed on the way to NCHW
+    B, C, HW, ld, off2 = 2, 27, 70, 64, 32
+    src = torch.randn(B, HW, ld, generator=g)
+    out = torch.empty(B, C, HW, device=dev)
+    _call("hl_nhwc_to_nchw_sum2", src.to(dev).data_ptr(), ld, off2, out.data_ptr(), B, C, HW, _stream())
+    assert torch.equal(out.cpu(), (src[..., :C] + src[..., off2:off2 + C]).permute(0, 2, 1))
     x = torch.randn(2, 3, 5, 8, generator=g)                       # NHWC [B,H,W,C]
     ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
     xd = x.to(dev)

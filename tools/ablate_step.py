@@ -10,7 +10,7 @@ import torch  # noqa: E402
 from bench import build_model  # noqa: E402
 
 dev = torch.device("cuda:0")
-B = 4
+B = int(os.environ.get("HL_B", "4"))
 model, diffusion, _ = build_model(dev, "fp16")
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, 27, 256, 256, generator=g).to(dev)

@@ -21,6 +21,7 @@ SIGNATURES = {
     "hl_conv_set_tuning2": (c_int, [c_int] * 3),
     "hl_conv_set_workspace": (c_int, [c_p, c_i64, c_p]),
     "hl_conv_set_split": (c_int, [c_int]),
+    "hl_conv_set_split_reduce": (c_int, [c_int]),
     "hl_conv2d_plan_info": (c_int, [c_int] * 10 + [c_i64, c_p]),
     "hl_conv_set_profile": (c_int, [c_p]),
     "hl_nchw_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),

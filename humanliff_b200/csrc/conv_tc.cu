@@ -99,6 +99,18 @@ struct TcParams {
     double *stats2;
     int stats2_ld;
     int sacc2_off;           // byte offset (from the aligned dynamic shared-memory base) of group 1's fp64 accumulators
+    // split-K with the second pass INSIDE the kernel (red = 1): every slice CTA stores its fp32 partial tile, bumps the
+    // tile's counter, and the CTA that arrives last adds the S partial tiles in slice order and runs the real epilogue
+    // (bias, residual, rounding, statistics) through the final output map tmF
+    int red;
+    const float *red_ws;     // partial-sum workspace [S][split_b][H][W][red_ldw]
+    long long red_slice;     // elements between slices
+    int red_ldw;
+    const float *red_bias, *red_res;
+    int red_ldr, red_yf16;
+    double *red_stats;
+    int red_stats_ld, red_rows;   // red_rows: pixels per sample inside a 128-pixel box (128 | 64)
+    unsigned *red_ctr;       // one counter per (128-pixel box, n tile); zero between launches (the last CTA resets it)
     int stats_rows;          // 0: one sample per 128-pixel box (per-CTA fp64 accumulators); 32 | 64: a box holds 128 / rows
                              // samples of `rows` pixels each (8^2: 64): the per-quarter sums go straight to global memory
 };
@@ -138,11 +150,17 @@ __device__ __forceinline__ void box_origin(const TcParams &p, int mt, int half, 
     }
 }
 
-template <bool CTA2>
+// RED: split-K launch whose second pass runs inside the kernel (hl_conv_set_split_reduce(1); a separate instantiation, so
+// that the one-pass launches keep the lean epilogue: with the two-pass loop compiled into every launch the step lost 1.2 ms).
+// EXPERIMENT, off by default -- measured on B200: bit-identical results, but +0.9 ms/step at B = 4 and +1.0 ms at B = 1
+// against the separate k_splitk_reduce launch: the last CTA of a tile re-reads the S partial tiles with 256 threads after a
+// full store-completion wait and a device-scope fence, where the separate launch spreads the same reads over the whole
+// GPU.  The 49 (B = 4) / 72 (B = 1) reduction launches are cheaper than that serialisation.
+template <bool CTA2, bool RED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-          const __grid_constant__ CUtensorMap tmY2, const TcParams p) {
+          const __grid_constant__ CUtensorMap tmY2, const __grid_constant__ CUtensorMap tmF, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4 * MAX_SLOTS + 4 + EPI_GROUPS * MAX_NBUF];
     __shared__ uint32_t tmem_slot;
@@ -150,6 +168,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // (1e-16) is far below the fp32 resolution of everything downstream -> results are reproducible run to run
     __shared__ double sacc[2][STATS_MAX_C];
     __shared__ float2 spart[EPI_GROUPS][4][32];     // per chunk: (sum, sum of squares) of each 32-row quarter
+    __shared__ int s_last;                          // split-K: this CTA arrived last at its tile's counter
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -177,6 +196,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
         if (p.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY2) : "memory");
+        if (RED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmF) : "memory");
     }
     if (warp == 2) {
         if (lane == 0) {
@@ -531,12 +551,48 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int mt = (tile - ks * p.tiles_mn) / p.n_tiles;
             { PROF_IF(4, pt); mbar_wait(bar_t_full + 8 * as, aph); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // pass 0 drains the accumulators; pass 1 (split-K with in-kernel reduction, last CTA of the tile only) re-runs
+            // the chunk loop on the sum of the S partial tiles with the real bias / residual / rounding / statistics
+            for (int fin_i = 0; fin_i <= (RED ? 1 : 0); ++fin_i) {
+            const bool fin = RED && fin_i != 0;                       // compile-time false in the one-pass instantiations
+            if (fin) {
+                if (e0) bulk_wait_all();                              // this group's partial tile is in global memory
+                asm volatile("fence.proxy.async;" ::: "memory");
+                named_bar(3, EPI_GROUPS * EPI_THREADS);
+                if (threadIdx.x == 96) {
+                    __threadfence();
+                    unsigned *ctr = p.red_ctr + (size_t)(tile - ks * p.tiles_mn) * p.pair + rank;
+                    const unsigned old = atomicAdd(ctr, 1u);
+                    s_last = old == (unsigned)(p.ksplit - 1);
+                    if (s_last) *ctr = 0u;                            // every slice has arrived: ready for the next launch
+                }
+                named_bar(3, EPI_GROUPS * EPI_THREADS);
+                if (!s_last) break;
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            const float *const bias_c = fin ? p.red_bias : p.bias;
+            const int yf16_c = fin ? p.red_yf16 : p.y_f16;
+            const CUtensorMap *const tm_c = fin ? &tmF : tm_out;
+            const bool stats_c = fin ? p.red_stats != nullptr : p.stats != nullptr;
+            const int srows_c = fin ? p.red_rows : p.stats_rows;
+            double *const gstats_c = fin ? p.red_stats : (plain_g ? p.stats2 : p.stats);
+            const int gstats_ld_c = fin ? p.red_stats_ld : (plain_g ? p.stats2_ld : p.stats_ld);
             for (int half = 0; half < p.mh; ++half) {
                 int w0, h0, n0;
                 box_origin(p, mt, half, rank, w0, h0, n0);
-                if (p.stats && !p.stats_rows && n0 != cur_n) {
+                if (!fin && p.stats && !p.stats_rows && n0 != cur_n) {
                     if (cur_n >= 0) flush_stats();
                     cur_n = n0;
+                }
+                // pass 1: this thread's pixel inside the box -> its row of the partial tiles (and of the residual)
+                size_t m_pix = 0;
+                int nn_pix = 0;
+                if (fin) {
+                    int xr = row, yr = 0, nr = 0;
+                    if (!p.halo) { xr = row % p.bw; yr = (row / p.bw) % p.bh; nr = row / (p.bw * p.bh); }
+                    nn_pix = n0 + nr;
+                    m_pix = ((size_t)nn_pix * p.H + (size_t)(h0 + yr)) * p.W + (size_t)(w0 + xr);
                 }
                 const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) +
                                      (uint32_t)((as * p.mh + half) * p.acc_stride);
@@ -548,16 +604,49 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t sbuf = smem_g + b * STAGE_BUF_BYTES;
                     const uint32_t srow = sbuf + (uint32_t)row * 128u;
                     float v[32];
-                    tmem_ld32(acc + (uint32_t)(cc * 32), v);
+                    if (!fin) {
+                        tmem_ld32(acc + (uint32_t)(cc * 32), v);
+                    } else {
+                        // the S partial tiles in slice order (fixed order: bit-reproducible), then the residual
+                        const float *src = p.red_ws + m_pix * (size_t)p.red_ldw + nbase;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldcg(reinterpret_cast<const float4 *>(src) + j);
+                            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                        }
+                        for (int sl = 1; sl < p.ksplit; ++sl) {
+                            src += p.red_slice;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldcg(reinterpret_cast<const float4 *>(src) + j);
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        }
+                    }
                     if (g_res) {
                         PROF_IF(5, pt);
                         mbar_wait(bar_r + 8 * b, rph);
                     }
-                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + nbase);
-                    if (!p.y_f16) {
+                    const float4 *bias4 = reinterpret_cast<const float4 *>(bias_c + nbase);
+                    if (fin && p.red_res && nn_pix < p.B) {
+                        // (the bias is added below, after the residual: the order of the one-pass epilogue is bias first --
+                        // fp32 addition of three terms, so add in the same order: partial sum + bias, then + residual)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 bz = p.bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (nbase + 4 * j < p.Cout) {
+                                const float4 bz = bias_c ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.red_res + m_pix * (size_t)p.red_ldr + nbase) + j);
+                                v[4 * j] = (v[4 * j] + bz.x) + r.x; v[4 * j + 1] = (v[4 * j + 1] + bz.y) + r.y;
+                                v[4 * j + 2] = (v[4 * j + 2] + bz.z) + r.z; v[4 * j + 3] = (v[4 * j + 3] + bz.w) + r.w;
+                                // bias consumed for these columns
+                            }
+                        }
+                    }
+                    const bool bias_on = bias_c != nullptr && !(fin && p.red_res && nn_pix < p.B);
+                    if (!yf16_c) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bz = bias_on ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 o = make_float4(v[4 * j] + bz.x, v[4 * j + 1] + bz.y, v[4 * j + 2] + bz.z,
                                                    v[4 * j + 3] + bz.w);
                             const uint32_t addr = srow + (((uint32_t)j ^ sw) << 4);
@@ -577,7 +666,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // arithmetic, then one rounding; staged as [128 rows][64 B] in the SWIZZLE_64B pattern
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 bz = p.bias ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 bz = bias_on ? __ldg(bias4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                             v[4 * j] += bz.x; v[4 * j + 1] += bz.y; v[4 * j + 2] += bz.z; v[4 * j + 3] += bz.w;
                             if (g_res) {
                                 float4 r;
@@ -589,7 +678,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                         if (g_res) named_bar(6 + eg, EPI_THREADS);   // all residual rows read before the fp16 tile lands
                         const uint32_t hrow = sbuf + (uint32_t)row * 64u, hsw = ((uint32_t)row >> 1) & 3u;
-                        if (p.y_f16 == 2) {
+                        if (yf16_c == 2) {
                             // scaled hi | lo pair (a raw residual-stream operand of a high-precision conv): v * 2^-4 =
                             // hi + lo to ~22 bits; the hi tile is staged in the first 8 KB of the buffer, lo in the second
 #pragma unroll
@@ -603,7 +692,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                          "r"(*reinterpret_cast<const uint32_t *>(&h0)), "r"(*reinterpret_cast<const uint32_t *>(&h1)),
                                          "r"(*reinterpret_cast<const uint32_t *>(&h2)), "r"(*reinterpret_cast<const uint32_t *>(&h3))
                                          : "memory");
-                            if (p.y_f16 == 2) {
+                            if (yf16_c == 2) {
                                 const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
                                 const __half2 l0 = __floats2half2_rn(v[8 * j] - f0.x, v[8 * j + 1] - f0.y);
                                 const __half2 l1 = __floats2half2_rn(v[8 * j + 2] - f1.x, v[8 * j + 3] - f1.y);
@@ -624,21 +713,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     { PROF_IF(6, pt); named_bar(1 + eg, EPI_THREADS); }
                     if (e0) {
-                        tma_store_4d(tm_out, sbuf, nbase, w0, h0, n0 + ks * p.split_b);
-                        if (p.y_f16 == 2) tma_store_4d(&tmY, sbuf + 8192u, p.Cout + nbase, w0, h0, n0);
+                        tma_store_4d(tm_c, sbuf, nbase, w0, h0, n0 + (fin ? 0 : ks * p.split_b));
+                        if (yf16_c == 2) tma_store_4d(tm_c, sbuf + 8192u, p.Cout + nbase, w0, h0, n0);
                         bulk_commit();
                         if (g_res) {
                             { PROF_IF(9, eg == 0); bulk_wait_read<1>(); }   // previous store drained -> refill its buffer
                             issue_res_load();
                         }
                     }
-                    if (p.stats) {
+                    if (stats_c) {
                         // column sums of the finished chunk: each thread sums one column over its 32-row quarter
                         // (fixed order), the four quarters are combined in a fixed order by the first warp of the
                         // group, and only then added (one uncontended fp64 atomic per channel) to the CTA totals
                         const int col = et & 31, rq = et >> 5;
                         float s = 0.f, ss = 0.f;
-                        if (!p.y_f16) {
+                        if (!yf16_c) {
 #pragma unroll 8
                             for (int r = 0; r < 32; ++r) {
                                 const int rr = rq * 32 + r;
@@ -668,18 +757,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                         spart[eg][rq][col] = make_float2(s, ss);
                         named_bar(4 + eg, EPI_THREADS);
-                        if (p.stats_rows) {
-                            // several samples per box (8^2: rows 0-63 sample n0, 64-127 sample n0 + 1): quarter sums of
-                            // one sample are combined in a fixed order and added to the global fp64 row directly (a
-                            // handful of CTAs per launch at these sizes: no contention worth a shared-memory stage)
-                            const int per = p.stats_rows >> 5;                 // quarters per sample: 1 | 2
+                        if (srows_c) {
+                            // several samples per box (8^2: rows 0-63 sample n0, 64-127 sample n0 + 1), or the final pass of
+                            // a split-K tile: quarter sums of one sample are combined in a fixed order and added to the
+                            // global fp64 row directly (a handful of CTAs per launch at these sizes: no contention worth
+                            // a shared-memory stage)
+                            const int per = srows_c >> 5;                      // quarters per sample: 1 | 2 | 4
                             if (rq % per == 0 && nbase + col < p.Cout) {
                                 const int nn = n0 + rq / per;
                                 if (nn < p.B) {
                                     float2 t = spart[eg][rq][col];
-                                    if (per == 2) { const float2 u = spart[eg][rq + 1][col]; t.x += u.x; t.y += u.y; }
-                                    double *dst = (plain_g ? p.stats2 + ((size_t)nn * p.stats2_ld + nbase + col) * 2
-                                                           : p.stats + ((size_t)nn * p.stats_ld + nbase + col) * 2);
+                                    for (int k = 1; k < per; ++k) { const float2 u = spart[eg][rq + k][col]; t.x += u.x; t.y += u.y; }
+                                    double *dst = gstats_c + ((size_t)nn * gstats_ld_c + nbase + col) * 2;
                                     atomicAdd(dst, (double)t.x);
                                     atomicAdd(dst + 1, (double)t.y);
                                 }
@@ -695,9 +784,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     ++ql;
                 }
             }
-            // all tcgen05.ld of this tile have completed (wait::ld) -> hand the accumulators back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (CTA2) mbar_arrive_cluster(mapa_u32(bar_t_empty + 8 * as, 0)); else mbar_arrive(bar_t_empty + 8 * as);
+            if (!fin) {
+                // all tcgen05.ld of this tile have completed (wait::ld) -> hand the accumulators back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (CTA2) mbar_arrive_cluster(mapa_u32(bar_t_empty + 8 * as, 0)); else mbar_arrive(bar_t_empty + 8 * as);
+            }
+            }   // fin
         }
         if (p.stats && cur_n >= 0) flush_stats();
         if (e0) bulk_wait_read<0>();
@@ -810,6 +902,8 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float *__restrict__
 }
 
 // partial-sum workspaces, one per stream that issues split-K convolutions (two streams run concurrently)
+constexpr int RED_CTR_BYTES = 8192;          // 2048 tile counters behind the partial sums
+int g_tune_red = 0;                          // 1: second pass inside the conv kernel (experiment, measured slower); 0: the k_splitk_reduce launch
 struct Workspace { cudaStream_t stream; float *ptr; size_t bytes; };
 Workspace g_ws[8];
 int g_n_ws = 0;
@@ -1135,6 +1229,12 @@ extern "C" int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2) {
 extern "C" int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     HL_CHECK_ARG(((uintptr_t)ws & 15) == 0 && bytes >= 0);
+    // the last RED_CTR_BYTES hold the tile counters of the in-kernel reduction: zero now, and every launch leaves them zero
+    if (ws) {
+        HL_CHECK_ARG(bytes > RED_CTR_BYTES && bytes % 16 == 0);
+        HL_CHECK_CUDA(cudaMemsetAsync((char *)ws + bytes - RED_CTR_BYTES, 0, RED_CTR_BYTES, st));
+        bytes -= RED_CTR_BYTES;
+    }
     for (int i = 0; i < g_n_ws; ++i)
         if (g_ws[i].stream == st) {
             g_ws[i].ptr = (float *)ws;
@@ -1157,6 +1257,11 @@ extern "C" int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream) {
 
 extern "C" int hl_conv_set_split(int ksplit) {
     g_tune_split = ksplit;
+    return HL_OK;
+}
+
+extern "C" int hl_conv_set_split_reduce(int in_kernel) {
+    g_tune_red = in_kernel;
     return HL_OK;
 }
 
@@ -1269,6 +1374,8 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     p.y_f16 = y_f16;
     const void *y_final = y;
     const int ldy_final = ldy, yf16_final = y_f16;
+    p.red = 0;
+    p.red_ctr = nullptr;
     if (S > 1) {
         p.ksplit = S;
         p.kc_split = p.vchunks / S;
@@ -1288,6 +1395,23 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         y = wsp->ptr;
         ldy = pl.cout_pad;
         y_f16 = 0;
+        // second pass inside the kernel (the last CTA of a tile reduces): whole 32-row quarters per sample, counters fit
+        const int rows = 128 / pl.t.bn;
+        if (g_tune_red == 1 && rows % 32 == 0 && rows >= 64 && p.tiles_mn * p.pair <= RED_CTR_BYTES / 4 &&
+            (!residual || ldr % 4 == 0)) {
+            p.red = 1;
+            p.red_ws = wsp->ptr;
+            p.red_slice = (long long)split_batch(pl, B) * H * W * pl.cout_pad;
+            p.red_ldw = pl.cout_pad;
+            p.red_bias = keep_bias;
+            p.red_res = residual;
+            p.red_ldr = ldr;
+            p.red_yf16 = yf16_final;
+            p.red_stats = stats;
+            p.red_stats_ld = stats_ld;
+            p.red_rows = rows;
+            p.red_ctr = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(wsp->ptr) + wsp->bytes);
+        }
     }
     p.stats_rows = 0;
     if (epi_stats) {
@@ -1299,7 +1423,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     }
     const CUtensorMapDataType dt = kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
-    CUtensorMap tmA, tmB, tmY, tmR, tmY2;
+    CUtensorMap tmA, tmB, tmY, tmR, tmY2, tmF;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)((flags & (HL_CONV_SPLIT3 | HL_CONV_SPLIT2A)) ? 2 * Cin : Cin), (cuuint64_t)Win,
                               (cuuint64_t)Hin, (cuuint64_t)B};
@@ -1334,15 +1458,20 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
             return HL_E_CUDA;
         }
     }
-    for (int which = 0; which < 3; ++which) {
-        const void *ptr = which == 1 ? (const void *)residual : which == 2 ? (const void *)y2 : (const void *)y;
-        const int ld = which == 1 ? ldr : which == 2 ? ldy2 : ldy;
-        const bool f16 = !which && y_f16;
+    for (int which = 0; which < 4; ++which) {
+        // 0: output (the partial-sum workspace when K is split), 1: residual, 2: second output (dual), 3: the real
+        // output of a split-K launch that reduces inside the kernel
+        const void *ptr = which == 1 ? (const void *)residual : which == 2 ? (const void *)y2
+                        : which == 3 ? (p.red ? y_final : nullptr) : (const void *)y;
+        const int ld = which == 1 ? ldr : which == 2 ? ldy2 : which == 3 ? ldy_final : ldy;
+        const int yf = which == 0 ? y_f16 : which == 3 ? yf16_final : 0;
+        const bool f16 = yf != 0;
         const int esz_o = f16 ? 2 : 4;
-        CUtensorMap *tm = which == 1 ? &tmR : which == 2 ? &tmY2 : &tmY;
+        CUtensorMap *tm = which == 1 ? &tmR : which == 2 ? &tmY2 : which == 3 ? &tmF : &tmY;
         if (!ptr || (which == 1 && S > 1)) { *tm = tmY; continue; }
-        cuuint64_t gdim[4] = {(cuuint64_t)(S > 1 ? pl.cout_pad : (!which && y_f16 == 2) ? 2 * Cout : Cout), (cuuint64_t)W,
-                              (cuuint64_t)H, (cuuint64_t)(S > 1 ? split_batch(pl, B) * S : B)};
+        const bool wsmap = which == 0 && S > 1;
+        cuuint64_t gdim[4] = {(cuuint64_t)(wsmap ? pl.cout_pad : yf == 2 ? 2 * Cout : Cout), (cuuint64_t)W,
+                              (cuuint64_t)H, (cuuint64_t)(wsmap ? split_batch(pl, B) * S : B)};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * esz_o, (cuuint64_t)W * ld * esz_o, (cuuint64_t)H * W * ld * esz_o};
         cuuint32_t box[4] = {32, (cuuint32_t)pl.t.bw, (cuuint32_t)pl.t.bh, (cuuint32_t)pl.t.bn};
         if (p.halo) { box[1] = BLOCK_M; box[2] = 1; box[3] = 1; }
@@ -1353,7 +1482,7 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             hl_set_error("cuTensorMapEncodeTiled(%s) failed: %d (B=%d H=%d W=%d Cout=%d ld=%d)",
-                         which == 1 ? "residual" : which == 2 ? "second output" : "output", (int)r, B, H, W, Cout, ld);
+                         which == 1 ? "residual" : which == 2 ? "second output" : which == 3 ? "final output" : "output", (int)r, B, H, W, Cout, ld);
             return HL_E_CUDA;
         }
     }
@@ -1363,8 +1492,10 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
     HL_CHECK_CUDA(cudaGetDevice(&dev_ord));
     bool &smem_configured = configured[dev_ord & 63];
     if (!smem_configured) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_MAX));
         smem_configured = true;
     }
     HL_CHECK_ARG(pl.smem <= (size_t)DYN_SMEM_MAX);
@@ -1381,11 +1512,14 @@ int hl_conv2d_tc(const void *x, int x_dtype, int ldx, const void *wpk, const flo
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = hl_pdl_attr(attr, 1);
-        HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, tmA, tmB, tmY, tmR, tmY2, p));
+        if (p.red) HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true, true>, tmA, tmB, tmY, tmR, tmY2, tmF, p));
+        else HL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true, false>, tmA, tmB, tmY, tmR, tmY2, tmF, p));
     } else {
-        HL_CHECK_CUDA(hl_launch(k_conv_tc<false>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, tmY2, p));
+        if (p.red) HL_CHECK_CUDA(hl_launch(k_conv_tc<false, true>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, tmY2, tmF, p));
+        else HL_CHECK_CUDA(hl_launch(k_conv_tc<false, false>, dim3(pl.grid), dim3(NUM_THREADS), pl.smem, stream, tmA, tmB, tmY, tmR, tmY2, tmF, p));
     }
     HL_CHECK_LAUNCH();
+    if (S > 1 && p.red) return HL_OK;          // the last CTA of every tile has run the second pass
     if (S > 1) {
         const int HW = H * W;
         // pixel slabs (multiples of 32 pixels) until the grid covers the SMs about twice

@@ -190,6 +190,7 @@ class UNetModel(nn.Module):
         self.h_f16 = precision == "fp16" and os.environ.get("HL_H_F16", "1") != "0"     # ResBlock intermediate as fp16
         self.dual_proj = os.environ.get("HL_DUAL_PROJ", "1") != "0"    # ControlNet projection: one launch, two results
         self.side_skip = os.environ.get("HL_SIDE_SKIP", "1") != "0"    # decoder <= 32^2: 1x1 skip conv on the side stream
+        self.split_reduce_in_kernel = os.environ.get("HL_SPLIT_RED", "0") == "1"   # experiment: split-K second pass inside the conv kernel (measured slower)
         self._build_plan()
         if self.hi_precision:
             for c in self._convs.values():
@@ -387,7 +388,7 @@ class UNetModel(nn.Module):
         forward takes effect."""
         self._pack(device)
         key = (str(device), B, H, W, self.use_cuda_graph, self.concurrent_encoders, self.batch_split, self.split_k,
-               self.programmatic_launch, self.h_f16, self.dual_proj, self.side_skip)
+               self.programmatic_launch, self.h_f16, self.dual_proj, self.side_skip, self.split_reduce_in_kernel)
         plan = self._plans.get(key)
         if plan is None:
             parts = self.batch_split
@@ -860,6 +861,7 @@ class _StepPlan:
             self.splitk_ws = [torch.empty(self.SPLITK_BYTES // 4, device=self.device) for _ in range(n)]
         for ws, st in zip(self.splitk_ws if self.m.split_k else [], streams):
             _lib.check(lib.hl_conv_set_workspace(_ptr(ws), self.SPLITK_BYTES, st), "hl_conv_set_workspace")
+        lib.hl_conv_set_split_reduce(1 if self.m.split_reduce_in_kernel else 0)
         try:
             for name, args, br in self.calls:
                 if name[0] != "#":

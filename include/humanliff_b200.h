@@ -92,6 +92,12 @@ int hl_conv_set_tuning2(int max_stages, int nbuf, int cta2);
  * rounding.  Streams that run concurrently need distinct workspaces.  hl_conv_set_split: -1 automatic
  * (default), 0 off, n > 1 forces n slices wherever n divides the K chunk count (tests).                     */
 int hl_conv_set_workspace(void *ws, int64_t bytes, void *stream);
+/* Where the second pass of a split-K convolution runs: 0 (default) = the separate fixed-order reduction launch; 1 = inside
+ * the conv kernel -- every slice CTA stores its partial tile and bumps the tile's counter (the last 8 KB of the registered
+ * workspace, zeroed at registration and left zero by every launch), the CTA that arrives last adds the slices in slice
+ * order and runs the real epilogue.  Same results bit for bit (tests compare the two); the in-kernel form measured
+ * 0.9 ms/step SLOWER on B200 (one CTA per tile re-reads all partial tiles) and stays an experiment.               */
+int hl_conv_set_split_reduce(int in_kernel);
 /* Host-only query of the tiling hl_conv2d would use (no device work; 148 SMs assumed without a GPU).  out[16]:
  * 0 tensor-core path applies, 1 CTAs per MMA (1 | 2 = cta_group::2), 2 halves per CTA tile, 3 N tile,
  * 4 HALO operand path, 5 A slots, 6 B slots, 7 staging buffers per epilogue group, 8 TMEM accumulator stages,

@@ -364,6 +364,18 @@ def test_conv_split_k(dev, shape, split, residual, cta2):
     y16, _, _, st16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, stats=True, **kw)
     assert torch.equal(y16, y.half().float())
     _check_stats(st16, y16, Cout)
+    # the experimental second pass inside the conv kernel (the last CTA of a tile reduces) vs the separate reduction
+    # launch: the same slice order, so the same bits
+    from humanliff_b200 import _lib
+    lib = _lib.load()
+    lib.hl_conv_set_split_reduce(1)
+    try:
+        ys, _, _, sts = _conv_case(dev, B, H, W, Cin, Cout, k, s, stats=True, **kw)
+        ys16 = _conv_case(dev, B, H, W, Cin, Cout, k, s, out_f16=True, **kw)[0]
+    finally:
+        lib.hl_conv_set_split_reduce(0)
+    assert torch.equal(y, ys) and torch.equal(y16, ys16)
+    assert torch.allclose(st, sts, rtol=2e-5, atol=1e-4)      # fp32 quarter sums (epilogue) vs fp64 (reduction kernel)
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 192, 192, 1), (4, 32, 32, 384, 384, 1), (4, 8, 8, 768, 768, 1),   # ControlNet projections

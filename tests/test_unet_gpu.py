@@ -311,6 +311,15 @@ def test_optional_launch_modes_agree():
     halves, plan2 = run(batch_split=2)
     assert type(plan2) is _SplitPlan and plan2.n_launches >= 2 * 100
     assert rel_l2(halves, base) < 2e-3
+    # round-2 launch-plan options that only re-arrange the SAME arithmetic must reproduce the default bit for bit:
+    # the ControlNet projection as two launches instead of the dual-output one, the decoder's low-resolution skip convs
+    # on the main stream, the split-K second pass inside the conv kernel
+    for attrs in (dict(dual_proj=False), dict(side_skip=False), dict(split_reduce_in_kernel=True)):
+        alt, _ = run(**attrs)
+        assert torch.equal(alt, base), attrs
+    # numerics options: the fp32 ResBlock intermediate (HL_H_F16=0) agrees at the operand-rounding level
+    h32, _ = run(h_f16=False)
+    assert 0 < rel_l2(h32, base) < 2e-3
     # within the split plan a sample's result does not depend on which half it sits in
     perm = torch.tensor([2, 3, 0, 1], device=dev)
     model, _, sd = model_state_dict(dict(flags, precision="fp16"), seed)

@@ -16,7 +16,7 @@ _TAG = os.environ.get("HL_BUILD_TAG", "")
 OBJ_DIR = os.path.join(HERE, "csrc", "build" + ("_" + _TAG if _TAG else ""))
 LIB_PATH = os.path.join(HERE, "libhumanliff_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
-SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "attention_tc5.cu", "render.cu", "render_tc.cu", "render_tc5.cu", "sampler.cu"]
+SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "attention_tc5.cu", "render.cu", "render_tc.cu", "render_tc5.cu", "sampler.cu", "gn_skip_tc5.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -190,6 +190,7 @@ class UNetModel(nn.Module):
         self.h_f16 = precision == "fp16" and os.environ.get("HL_H_F16", "1") != "0"     # ResBlock intermediate as fp16
         self.dual_proj = os.environ.get("HL_DUAL_PROJ", "1") != "0"    # ControlNet projection: one launch, two results
         self.side_skip = os.environ.get("HL_SIDE_SKIP", "1") != "0"    # decoder <= 32^2: 1x1 skip conv on the side stream
+        self.fused_gn_skip = os.environ.get("HL_FUSED_GN_SKIP", "1") != "0"   # GroupNorm-1 + 1x1 skip conv in one kernel (hl_gn_skip)
         self.split_reduce_in_kernel = os.environ.get("HL_SPLIT_RED", "0") == "1"   # experiment: split-K second pass inside the conv kernel (measured slower)
         self._build_plan()
         if self.hi_precision:
@@ -388,7 +389,7 @@ class UNetModel(nn.Module):
         forward takes effect."""
         self._pack(device)
         key = (str(device), B, H, W, self.use_cuda_graph, self.concurrent_encoders, self.batch_split, self.split_k,
-               self.programmatic_launch, self.h_f16, self.dual_proj, self.side_skip, self.split_reduce_in_kernel)
+               self.programmatic_launch, self.h_f16, self.dual_proj, self.side_skip, self.split_reduce_in_kernel, self.fused_gn_skip)
         plan = self._plans.get(key)
         if plan is None:
             parts = self.batch_split
@@ -565,6 +566,22 @@ class _StepPlan:
             raw = _ptr(self.scratch("raw", self.max_raw, op=True))
             ldraw, raw_mode = self.raw_operand(blk["skip"], cin)
             assert B * H * W * ldraw <= self.max_raw, ("scratch bound (raw)", blk["p"])
+        # GroupNorm-1 + the 1x1 skip conv in ONE kernel (hl_gn_skip): x is read once, the hi | lo operand pair of the skip
+        # conv is built in shared memory instead of travelling through HBM.  Used where the launch fills the GPU (>= 96
+        # tiles of 128 pixels); below that the two-launch form (skip conv on the side stream) is faster.
+        fused_skip = (blk["skip"] is not None and m.fused_gn_skip and self.dt == _lib.DT_F16
+                      and m._convs[blk["skip"]].hp == "split" and B * H * W >= 96 * 128 and x.ld % 4 == 0
+                      and bool(_lib.load().hl_gn_skip_supported(B, H * W, cin, cout)))
+        if fused_skip:
+            sc = m._convs[blk["skip"]]
+            s = _Ref(_ptr(self.scratch("skipbuf", self.max_act)), cout, cout, H, W, None, 0)
+            self.emit("hl_gn_skip", x.ptr, x.ld, ("stats", x.st), x.st_ld, _ptr(m._norm_p[blk["n1"] + ".weight"]),
+                      _ptr(m._norm_p[blk["n1"] + ".bias"]), act, cin, _ptr(sc.w), _ptr(sc.b), s.ptr, s.ld, B, H * W, cin, cout,
+                      32, 1e-5)
+            self.conv(blk["c1"], act, cin, None, h, H, W)
+            self.gn(blk["n2"], h, act, cout, True, film=("film", blk["film_off"]))
+            self.conv(blk["c2"], act, cout, s, dst, H, W)
+            return
         self.gn(blk["n1"], x, act, cin, True, raw_ptr=raw, ldraw=ldraw, raw_mode=raw_mode)
         # The 1x1 skip conv needs only GroupNorm-1's raw copy: in the decoder's low-resolution stretch (one stream, every
         # kernel a fraction of a wave, the chain bound by launch latency) it runs on the side stream next to conv1 / GroupNorm-2

@@ -162,6 +162,16 @@ int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, in
  * scale/shift optional (film + b*film_ld points at [scale(C) | shift(C)] of sample b); act = SiLU if
  * silu; `raw` (nullable) additionally receives the plain operand copy of x (same dtype, pitch ldraw)
  * for the ResBlock's 1x1 skip convolution, saving a second pass over x.                          */
+/* GroupNorm-1 + SiLU operand pass FUSED with the ResBlock's 1x1 skip convolution (unet.py:198-201,208-219): x is read
+ * once (fp32, TMA); act[b, p, :Cin] = fp16(SiLU(GN(x))) (pitch ld_act halves) and skip[b, p, :Cout] = W . x + bias (fp32,
+ * pitch ld_skip) come out of one kernel -- the conv on tcgen05 with the hi + lo operand pair of x * 2^-4 built in shared
+ * memory (weights: the HL_CONV_SPLIT3 packing {W_hi, W_lo} of w * 2^4).  Same arithmetic as hl_gn_apply (+ raw copy)
+ * followed by hl_conv2d(HL_CONV_SPLIT3): act bit-identical, skip up to fp32 accumulation order.  Half the HBM bytes.
+ * hl_gn_skip_supported: H*W % 128 == 0, Cin % 64 == 0, Cout <= 256 (or 2 x 192 / 2 x 256).                            */
+int hl_gn_skip_supported(int B, int HW, int Cin, int Cout);
+int hl_gn_skip(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma, const float *beta,
+               void *act, int ld_act, const void *wpk, const float *bias, float *skip, int ld_skip, int B, int HW,
+               int Cin, int Cout, int groups, float eps, void *stream);
 /* experiment hook: blocks of hl_gn_apply per SM and launch (<= 0 restores the default) */
 int hl_gn_set_tuning(int blocks_per_sm);
 int hl_gn_apply(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma,

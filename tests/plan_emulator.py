@@ -199,6 +199,16 @@ def hl_conv2d(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld
         hl_gn_stats(y, ldy, B, Ho * Wo, Cout, stats, stats_ld, stream)
 
 
+def hl_gn_skip(x, ldx, stats, stats_ld, gamma, beta, act, ld_act, wpk, bias, skip, ld_skip, B, HW, Cin, Cout, groups, eps, stream):
+    """GroupNorm-1 + SiLU operand pass fused with the 1x1 skip conv = hl_gn_apply with the scaled hi | lo raw copy, then
+    hl_conv2d(HL_CONV_SPLIT3) on that copy (H x W = HW x 1: a 1x1 conv does not look at the geometry)."""
+    raw = np.zeros((B * HW, 2 * Cin), np.float16)
+    raw_ptr = raw.ctypes.data
+    hl_gn_apply(x, ldx, stats, stats_ld, gamma, beta, None, 0, act, 1, ld_act, raw_ptr, 2 * Cin, B, HW, Cin, groups, eps, 1,
+                (OP_SPLIT | OP_SCALED) << 4, stream)
+    hl_conv2d(raw_ptr, 1, 2 * Cin, wpk, bias, None, 0, skip, ld_skip, None, 0, B, HW, 1, Cin, Cout, 1, 1, 16, stream)
+
+
 def hl_conv2d_dual(x, x_dtype, ldx, wpk, bias, residual, ldr, y, ldy, stats, stats_ld, y2, ldy2, stats2, stats2_ld, B, H, W,
                    Cin, Cout, ksize, stride, flags, stream):
     """y = conv + residual, y2 = conv: the two launches the entry point replaces."""

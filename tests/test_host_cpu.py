@@ -186,7 +186,9 @@ def test_conv_planner_on_every_production_launch(B):
             assert k == 3 and tiles <= 148 // (pair if pair == 2 else 1) * pair   # one wave
             assert S * Bn * Ho * Wo * _lib.load().hl_conv_cout_pad(Cout) * 4 <= plan.SPLITK_BYTES
             assert o[15] == 0                                    # statistics move to the second pass
-    assert n_conv == 256 and n_dual == 24 and n_split >= 20
+    # the 1x1 skip convs of the ResBlocks whose launch fills the GPU run inside hl_gn_skip (fused with GroupNorm-1)
+    n_fused = sum(1 for name, _a, _br in plan.calls if name == "hl_gn_skip")
+    assert n_conv + n_fused == 256 and n_fused == (14 if B == 4 else 8) and n_dual == 24 and n_split >= 20
 
 
 def test_state_dict_contract_vs_reference():

@@ -168,6 +168,49 @@ def test_groupnorm_fp16_input(dev, C, HW, B):
     assert rel_l2(outs[1].float().permute(0, 2, 1), xn * torch.sigmoid(xn)) < 6e-4
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 384, 192), (1, 32, 32, 576, 192), (2, 32, 32, 768, 384),
+                                             (1, 16, 8, 192, 384), (4, 16, 16, 384, 256), (3, 128, 128, 384, 192)])
+def test_gn_skip_fused(dev, B, H, W, Cin, Cout):
+    """hl_gn_skip (GroupNorm-1 + SiLU operand pass fused with the 1x1 skip conv, hi + lo operand pair built in shared
+    memory) against the two launches it replaces: hl_gn_apply with the raw hi | lo copy, then hl_conv2d(HL_CONV_SPLIT3).
+    act: equal but for rare one-ulp fp16 differences; skip: fp32 accumulation order only (5e-6)."""
+    from humanliff_b200 import _lib
+    from humanliff_b200.unet import pack_conv
+    lib = _lib.load()
+    HW = H * W
+    assert lib.hl_gn_skip_supported(B, HW, Cin, Cout) == 1
+    g = torch.Generator().manual_seed(Cin + Cout + HW)
+    x = (torch.randn(B, HW, Cin, generator=g) * 3 + 0.7).to(dev)
+    gamma, beta = (1 + 0.1 * torch.randn(Cin, generator=g)).to(dev), (0.1 * torch.randn(Cin, generator=g)).to(dev)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / math.sqrt(Cin)
+    b = torch.randn(Cout, generator=g) * 0.1
+    wpk, bpk = pack_conv(w, b, Cin, "fp16", dev, mode="split")
+    stats = torch.zeros(B * Cin * 2, device=dev, dtype=torch.float64)
+    _call("hl_gn_stats", x.data_ptr(), Cin, B, HW, Cin, stats.data_ptr(), Cin, _stream())
+    # reference: the two-kernel form
+    act_ref = torch.empty(B, HW, Cin, device=dev, dtype=torch.float16)
+    raw = torch.empty(B, HW, 2 * Cin, device=dev, dtype=torch.float16)
+    mode = (_lib.OP_SPLIT | _lib.OP_SCALED) << _lib.OP_RAW_SHIFT
+    _call("hl_gn_apply", x.data_ptr(), Cin, stats.data_ptr(), Cin, gamma.data_ptr(), beta.data_ptr(), None, 0,
+          act_ref.data_ptr(), 1, Cin, raw.data_ptr(), 2 * Cin, B, HW, Cin, 32, 1e-5, 1, mode, _stream())
+    skip_ref = torch.empty(B, HW, Cout, device=dev)
+    _call("hl_conv2d", raw.data_ptr(), 1, 2 * Cin, wpk.data_ptr(), bpk.data_ptr(), None, 0, skip_ref.data_ptr(), Cout, None, 0,
+          B, H, W, Cin, Cout, 1, 1, _lib.CONV_SPLIT3, _stream())
+    # fused
+    act = torch.full((B, HW, Cin), float("nan"), device=dev, dtype=torch.float16)
+    skip = torch.full((B, HW, Cout), float("nan"), device=dev)
+    _call("hl_gn_skip", x.data_ptr(), Cin, stats.data_ptr(), Cin, gamma.data_ptr(), beta.data_ptr(), act.data_ptr(), Cin,
+          wpk.data_ptr(), bpk.data_ptr(), skip.data_ptr(), Cout, B, HW, Cin, Cout, 32, 1e-5, _stream())
+    torch.cuda.synchronize()
+    assert not torch.isnan(skip).any() and not torch.isnan(act.float()).any()
+    # a few elements per million land one fp16 ulp away (the two kernels' SiLU instruction sequences differ in the last bit)
+    assert float((act != act_ref).float().mean()) < 1e-5 and rel_max(act.float(), act_ref.float()) < 2e-3
+    assert rel_l2(skip, skip_ref) < 5e-6, rel_l2(skip, skip_ref)
+    # and against the exact fp32 statement (the hi + lo pair carries ~22 bits: far inside the fp16 operand error)
+    ref = x.cpu().double() @ w.reshape(Cout, Cin).double().T + b.double()
+    assert rel_l2(skip, ref) < 2e-5, rel_l2(skip, ref)
+
+
 def _operand(t, mode):
     """fp32 tensor -> (device-ready operand tensor, dtype code, fp32 view of the rounded values)."""
     from oracle.unet_oracle import round_tf32

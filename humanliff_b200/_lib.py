@@ -35,6 +35,7 @@ SIGNATURES = {
     "hl_gn_stats": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_int, c_p]),
     "hl_gn_set_tuning": (c_int, [c_int]),
     "hl_gn_skip_supported": (c_int, [c_int] * 4),
+    "hl_gn_skip_set_profile": (c_int, [c_p]),
     "hl_gn_skip": (c_int, [c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
                            c_int, c_f, c_p]),
     "hl_gn_apply": (c_int, [c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_p, c_int,

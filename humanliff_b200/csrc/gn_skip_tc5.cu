@@ -9,9 +9,11 @@
 // (TMA, fp32), every pixel row is owned by one thread that
 //   * applies the per-(sample, channel) affine + SiLU and writes its 128 B of `act` into a staging tile that leaves by
 //     TMA store (per-thread 16-byte global stores were measured L2-request-bound: 2.5 TB/s),
-//   * splits x * 2^-4 into fp16 hi + lo and writes both K-major SWIZZLE_128B operand tiles into shared memory,
-// and the skip conv's MMAs (tcgen05 kind::f16, M = 128, both operands from shared memory, fp32 accumulators in tensor
-// memory) run on those tiles against W_hi / W_lo tiles streamed by TMA.  HBM bytes per pixel: 4 Cin in, 2 Cin + 4 Cout
+//   * splits x * 2^-4 into fp16 hi + lo and writes both as A operands into TENSOR MEMORY (tcgen05.st; double-buffered, so
+//     the split of chunk c + 1 overlaps the MMAs of chunk c -- with the operand tiles in shared memory there was room for
+//     one buffer and a two-deep weight ring only, and the kernel sat at 3.2 TB/s),
+// and the skip conv's MMAs (tcgen05 kind::f16 in the .ts form: A from tensor memory, B = W_hi / W_lo tiles streamed by TMA
+// into a three-deep ring, fp32 accumulators in tensor memory) run on them.  HBM bytes per pixel: 4 Cin in, 2 Cin + 4 Cout
 // out -- half of the two-kernel form.  The arithmetic is the two-kernel form's: `act` equals k_gn_apply_f16's (same
 // coefficient formulas and reduction order; a few elements per million land one fp16 ulp away), `skip` differs only in
 // fp32 accumulation order (chunk-major instead of pass-major).
@@ -22,6 +24,7 @@
 //               MMAs; after the last chunk: tcgen05.ld of the accumulator row + bias -> staging tiles -> TMA store of `skip`
 //               (four compute warps -- one per scheduler, nothing to hide their dependent latencies -- ran at 3.0 TB/s)
 //   warp 8      X producer: two TMA boxes {32 ch, 128 px} fp32 per chunk into a ring of 3 slots (the bytes in flight)
+//   warp 10     MMA issuer (a chunk's 12 MMAs are issued at the pace they execute: a compute warp must not do it)
 //   warp 9      W producer: per chunk the W_hi tiles of every n tile, then the W_lo tiles ({64 ch, nt rows} fp16)
 #include "common.cuh"
 #include "tc5.cuh"
@@ -38,8 +41,9 @@ constexpr int GS_XSLOT = 32 * 1024;      // one 64-channel fp32 chunk of 128 pix
 constexpr int GS_ATILE = 16 * 1024;      // one fp16 operand tile [128 rows][128 B]
 constexpr int GS_MAX_C = 1536;
 constexpr int GS_COMPUTE = 256;         // 8 compute warps: two threads per pixel row
-constexpr int GS_THREADS = GS_COMPUTE + 64;
+constexpr int GS_THREADS = GS_COMPUTE + 96;      // + X producer, W producer, MMA issuer
 constexpr int GS_MAX_NX = 4, GS_MAX_NW = 3;
+constexpr uint32_t GS_TM_A = 384;        // tensor memory: accumulators in columns [0, Cout <= 384), two A buffers (hi 32 | lo 32) behind
 
 struct GsParams {
     int Cin, Cout, kchunks, nt, n_tiles, nx, nw, HW, total_tiles, groups, stats_ld, ld_act, ld_skip, tmem_cols;
@@ -48,6 +52,7 @@ struct GsParams {
     const float *gamma, *beta, *bias;
     __half *act;
     float *skip;
+    unsigned long long *prof;     // optional cycle counters of (CTA 0, thread 0): hl_gn_skip_set_profile
 };
 
 __device__ __forceinline__ uint32_t gs_h2(float a, float b) {
@@ -67,21 +72,21 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
 k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
               const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmSkip, const GsParams p) {
     extern __shared__ uint8_t gs_smem[];
-    __shared__ __align__(8) uint64_t bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 1];
+    __shared__ __align__(8) uint64_t bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 5];
     __shared__ uint32_t tmem_slot;
     __shared__ float gmean[64], grstd[64];
 
     const int warp = threadIdx.x >> 5;
     const uint32_t base = (smem_u32(gs_smem) + 1023u) & ~1023u;
     const uint32_t sm_x = base;
-    const uint32_t sm_a = sm_x + (uint32_t)p.nx * GS_XSLOT;                 // A_hi, A_lo
-    const uint32_t sm_w = sm_a + 2u * GS_ATILE;
+    const uint32_t sm_w = sm_x + (uint32_t)p.nx * GS_XSLOT;
     const uint32_t w_bytes = (uint32_t)p.nt * 128u;
     const uint32_t sm_o = sm_w + (uint32_t)p.nw * w_bytes;                  // two output staging tiles [128 rows][128 B]
     float *coef = reinterpret_cast<float *>(gs_smem + (sm_o + 2u * GS_ATILE - smem_u32(gs_smem)));   // ca[Cin] | cb[Cin]
     const uint32_t bar_x_full = smem_u32(&bars[0]), bar_x_empty = smem_u32(&bars[GS_MAX_NX]);
     const uint32_t bar_w_full = smem_u32(&bars[2 * GS_MAX_NX]), bar_w_empty = smem_u32(&bars[2 * GS_MAX_NX + GS_MAX_NW]);
     const uint32_t bar_a_empty = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW]);
+    const uint32_t bar_a_full = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 2]);
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -91,6 +96,10 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int s = 0; s < GS_MAX_NX; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, GS_COMPUTE); }
         for (int s = 0; s < GS_MAX_NW; ++s) { mbar_init(bar_w_full + 8 * s, 1); mbar_init(bar_w_empty + 8 * s, 1); }
         mbar_init(bar_a_empty, 1);
+        mbar_init(bar_a_empty + 8, 1);
+        mbar_init(bar_a_full, GS_COMPUTE);
+        mbar_init(bar_a_full + 8, GS_COMPUTE);
+        mbar_init(bar_a_full + 16, GS_COMPUTE);            // accumulators drained (once per tile)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -139,20 +148,65 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 }
             }
         }
+    } else if (warp == 10) {
+        // ---------------------------------- MMA issuer ----------------------------------
+        // A dedicated warp: the issue of a chunk's 12 MMAs proceeds at the pace they EXECUTE (measured 1.7 k cycles per chunk
+        // when a compute warp issued them, stalling all eight at the next barrier).  Per n tile:
+        //   acc += x_hi.W_hi + x_lo.W_hi   (slab 0),   acc += x_hi.W_lo   (slab 1)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(GS_ROWS >> 4) << 24);   // f16 x f16 -> f32, K-major
+        uint32_t swr = 0, phw = 0, g = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int c = 0; c < p.kchunks; ++c, ++g) {
+                const uint32_t ab = g & 1u;
+                mbar_wait(bar_a_full + 8 * ab, (g >> 1) & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t ah = tmem + GS_TM_A + ab * 64u, al = ah + 32u;      // A_hi / A_lo: 64 halves = 32 columns each
+                    for (int wi = 0; wi < n_w; ++wi) {
+                        const int slab = wi / p.n_tiles, nti = wi - slab * p.n_tiles;
+                        mbar_wait(bar_w_full + 8 * swr, phw);
+                        tc_fence_after();
+                        const uint64_t bd = gs_desc(sm_w + swr * w_bytes);
+                        const uint32_t d = tmem + (uint32_t)(nti * p.nt);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_ts_f16(d, ah + 8u * (uint32_t)k, bd + 2 * k, idesc, (c | slab | k) != 0 ? 1u : 0u);
+                        if (!slab) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_ts_f16(d, al + 8u * (uint32_t)k, bd + 2 * k, idesc, 1u);
+                        }
+                        umma_commit(bar_w_empty + 8 * swr);
+                        if (++swr == (uint32_t)p.nw) { swr = 0; phw ^= 1u; }
+                    }
+                    umma_commit(bar_a_empty + 8 * ab);
+                }
+                __syncwarp();
+            }
+            // the next tile's first MMA overwrites the accumulators: every row must have left tensor memory
+            mbar_wait(bar_a_full + 16, (uint32_t)((tile - (int)blockIdx.x) / (int)gridDim.x) & 1u);
+            tc_fence_after();
+        }
     } else {
         // ------------- compute: 8 warps; thread = (pixel row = TMEM lane, channel half of the 64-channel chunk) -------------
         const int tid = threadIdx.x;                       // 0..255
         const int row = tid & (GS_ROWS - 1), half = tid >> 7;
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(GS_ROWS >> 4) << 24);   // f16 x f16 -> f32, K-major
         float *ca = coef, *cb = coef + p.Cin;
-        uint32_t sx = 0, phx = 0, swr = 0, phw = 0;
+        uint32_t sx = 0, phx = 0;
         uint32_t so = 0;                                    // output staging tile of the next chunk
         const bool issuer = tid == 32;                      // issues the TMA stores (warp 0's elected lane issues the MMAs)
         uint32_t g = 0;                                     // chunks issued so far (a_empty completes once per chunk)
         int cur_b = -1;
         const int cpg = p.Cin / p.groups;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        long long tp = prof ? clock64() : 0;
+#define GSPROF(slot)                                                      \
+    if (prof) {                                                           \
+        const long long now_ = clock64();                                 \
+        atomicAdd(p.prof + (slot), (unsigned long long)(now_ - tp));      \
+        tp = now_;                                                        \
+    }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int b = (int)(((long long)tile * GS_ROWS) / p.HW);
             if (b != cur_b) {
@@ -160,24 +214,25 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 // (8 strided partial sums per group, xor-tree 4, 2, 1)
                 cur_b = b;
                 const double n = (double)p.HW * cpg;
-                for (int gi = tid; gi < p.groups; gi += GS_COMPUTE) {
-                    const double2 *st = reinterpret_cast<const double2 *>(p.stats + ((long long)b * p.stats_ld + (long long)gi * cpg) * 2);
-                    double a[8], a2[8];
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        a[l] = 0.0; a2[l] = 0.0;
-                        for (int c = l; c < cpg; c += 8) { const double2 v = st[c]; a[l] += v.x; a2[l] += v.y; }
+                for (int g0 = 0; g0 < p.groups; g0 += GS_COMPUTE / 8) {
+                    const int gi = g0 + (tid >> 3), l = tid & 7;
+                    double a = 0.0, a2 = 0.0;
+                    if (gi < p.groups) {
+                        const double2 *st = reinterpret_cast<const double2 *>(p.stats + ((long long)b * p.stats_ld + (long long)gi * cpg) * 2);
+                        for (int c = l; c < cpg; c += 8) { const double2 v = st[c]; a += v.x; a2 += v.y; }
                     }
 #pragma unroll
-                    for (int o = 4; o > 0; o >>= 1)
-#pragma unroll
-                        for (int l = 0; l < 8; ++l)
-                            if (l < o) { a[l] += a[l + o]; a2[l] += a2[l + o]; }
-                    const double mean = a[0] / n;
-                    double var = a2[0] / n - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    gmean[gi] = (float)mean;
-                    grstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
+                    for (int o = 4; o > 0; o >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                    }
+                    if (gi < p.groups && l == 0) {
+                        const double mean = a / n;
+                        double var = a2 / n - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        gmean[gi] = (float)mean;
+                        grstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
+                    }
                 }
                 named_bar(1, GS_COMPUTE);
                 for (int c = tid; c < p.Cin; c += GS_COMPUTE) {
@@ -190,7 +245,9 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
             for (int c = 0; c < p.kchunks; ++c, ++g) {
                 // ---- this thread's 32 fp32 channels: its pixel's row of box `half` ----
+                GSPROF(0)                                           // (tile / chunk bookkeeping, coefficient refresh)
                 mbar_wait(bar_x_full + 8 * sx, phx);
+                GSPROF(1)                                           // waiting for x
                 float xv[32];
                 {
                     const uint32_t r0 = sm_x + sx * GS_XSLOT + (uint32_t)half * (GS_XSLOT / 2) + (uint32_t)row * 128u;
@@ -203,7 +260,7 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         xv[4 * j] = t.x; xv[4 * j + 1] = t.y; xv[4 * j + 2] = t.z; xv[4 * j + 3] = t.w;
                     }
                 }
-                mbar_arrive(bar_x_empty + 8 * sx);
+                const uint32_t sx_used = sx;          // released below, once every value has been CONSUMED (see there)
                 if (++sx == (uint32_t)p.nx) { sx = 0; phx ^= 1u; }
                 // ---- act = fp16(SiLU(x * ca + cb)): this thread's 64 B of the pixel's row in the staging tile ----
                 {
@@ -222,63 +279,51 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                                      "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                 }
-                // ---- hi / lo operand rows of x * 2^-4 (the tensor core may still read the previous chunk's tiles) ----
-                if (g) mbar_wait(bar_a_empty, (g - 1u) & 1u);
+                // ---- hi / lo A operands of x * 2^-4 into tensor memory: buffer g & 1 (the MMAs of chunk g - 2 read it last) ----
+                GSPROF(2)                                           // x row -> act staging
+                const uint32_t ab = g & 1u;
+                if (g >= 2) mbar_wait(bar_a_empty + 8 * ab, ((g >> 1) - 1u) & 1u);
+                GSPROF(3)                                           // waiting for the A buffer
+                tc_fence_after();
                 {
-                    const uint32_t ar = sm_a + (uint32_t)row * 128u;
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = xv[8 * j + e] * HL_OP_SCALE;
-                        uint4 h, l;
-                        h.x = gs_h2(v[0], v[1]); h.y = gs_h2(v[2], v[3]); h.z = gs_h2(v[4], v[5]); h.w = gs_h2(v[6], v[7]);
-                        l.x = gs_lo(v[0], v[1], h.x); l.y = gs_lo(v[2], v[3], h.y); l.z = gs_lo(v[4], v[5], h.z); l.w = gs_lo(v[6], v[7], h.w);
-                        const uint32_t off = (((uint32_t)(half * 4 + j) ^ sw) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ar + off), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ar + GS_ATILE + off), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w) : "memory");
+                    for (int j = 0; j < 16; ++j) {
+                        const float v0 = xv[2 * j] * HL_OP_SCALE, v1 = xv[2 * j + 1] * HL_OP_SCALE;
+                        hi[j] = gs_h2(v0, v1);
+                        lo[j] = gs_lo(v0, v1, hi[j]);
                     }
+                    const uint32_t acol = tlane + GS_TM_A + ab * 64u + (uint32_t)half * 16u;
+                    tmem_st16(acol, hi);
+                    tmem_st16(acol + 32u, lo);
                 }
+                tmem_st_wait();
+                // The X slot goes back to the producer only here: every loaded value has been used by now.  Arriving right
+                // after the ld.shared instructions let the refill (TMA) overtake the last loads of slow threads -- measured:
+                // the final 16-32 bytes of a few rows per launch came from the slot's NEXT chunk once the compute warps no
+                // longer waited for the MMA issue.
+                mbar_arrive(bar_x_empty + 8 * sx_used);
+                tc_fence_before();
+                mbar_arrive(bar_a_full + 8 * ab);                   // -> the MMA warp
                 fence_async_smem();
                 tc_fence_before();
                 // every store issued so far has left its staging tile: after the barrier the OTHER tile may be rewritten
+                GSPROF(4)                                           // hi / lo -> tensor memory
                 if (issuer) bulk_wait_read<0>();
                 named_bar(1, GS_COMPUTE);
+                GSPROF(5)                                           // chunk barrier
                 if (issuer) {
                     tma_store_2d(&tmAct, sm_o + so * GS_ATILE, c * 64, tile * GS_ROWS);
                     bulk_commit();
                 }
                 so ^= 1u;
-                // ---- one thread issues the chunk: per n tile  acc += x_hi.W_hi + x_lo.W_hi, then acc += x_hi.W_lo ----
-                if (warp == 0) {
-                    tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t ah = gs_desc(sm_a), al = gs_desc(sm_a + GS_ATILE);
-                        for (int wi = 0; wi < n_w; ++wi) {
-                            const int slab = wi / p.n_tiles, nti = wi - slab * p.n_tiles;
-                            mbar_wait(bar_w_full + 8 * swr, phw);
-                            tc_fence_after();
-                            const uint64_t bd = gs_desc(sm_w + swr * w_bytes);
-                            const uint32_t d = tmem + (uint32_t)(nti * p.nt);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma(1, d, ah + 2 * k, bd + 2 * k, idesc, (c | slab | k) != 0 ? 1u : 0u);
-                            if (!slab) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma(1, d, al + 2 * k, bd + 2 * k, idesc, 1u);
-                            }
-                            umma_commit(bar_w_empty + 8 * swr);
-                            if (++swr == (uint32_t)p.nw) { swr = 0; phw ^= 1u; }
-                        }
-                        umma_commit(bar_a_empty);
-                    }
-                    __syncwarp();
-                }
+                GSPROF(6)                                           // act store issue
             }
             // ---- skip = accumulators + bias: two 32-column chunks per round (one per channel half of the threads), each
             //      through its own staging tile ----
-            mbar_wait(bar_a_empty, (g - 1u) & 1u);
+            mbar_wait(bar_a_empty + 8 * ((g - 1u) & 1u), ((g - 1u) >> 1) & 1u);     // the last chunk's MMAs (and all before) retired
             tc_fence_after();
+            GSPROF(7)                                               // waiting for the tile's last MMAs
             for (int col0 = 0; col0 < p.Cout; col0 += 64) {
                 const int col = col0 + 32 * half;
                 if (issuer) bulk_wait_read<0>();           // the stores that last used the two tiles have read them out
@@ -306,8 +351,12 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             // every row has left tensor memory and both staging tiles have been read out before the next tile starts
             if (issuer) bulk_wait_read<0>();
             tc_fence_before();
+            mbar_arrive(bar_a_full + 16);                           // accumulators drained -> the MMA warp may start the next tile
             named_bar(1, GS_COMPUTE);
+            GSPROF(8)                                               // epilogue
+            if (prof) atomicAdd(p.prof + 9, 1ull);                  // tiles of CTA 0
         }
+#undef GSPROF
     }
 
     if (threadIdx.x == 32) bulk_wait_read<0>();          // the last stores have read their staging tiles
@@ -328,10 +377,10 @@ bool gs_plan(int B, int HW, int Cin, int Cout, GsParams *p, size_t *smem) {
     else return false;
     p->nt = nt;
     p->n_tiles = n_tiles;
-    p->tmem_cols = nt * n_tiles <= 128 ? 128 : nt * n_tiles <= 256 ? 256 : 512;
-    p->nw = 2;
-    const int fixed = 1024 + 2 * GS_ATILE /* operand tiles */ + p->nw * nt * 128 + 2 * GS_ATILE /* output staging */ +
-                      2 * Cin * (int)sizeof(float);
+    if (nt * n_tiles > (int)GS_TM_A) return false;
+    p->tmem_cols = 512;
+    p->nw = 3;
+    const int fixed = 1024 + p->nw * nt * 128 + 2 * GS_ATILE /* output staging */ + 2 * Cin * (int)sizeof(float);
     const int budget = 227 * 1024 - 2048;        // static shared memory: barriers, group statistics
     int nx = (budget - fixed) / GS_XSLOT;
     if (nx > GS_MAX_NX) nx = GS_MAX_NX;
@@ -344,6 +393,12 @@ bool gs_plan(int B, int HW, int Cin, int Cout, GsParams *p, size_t *smem) {
 }
 
 }  // namespace
+
+static unsigned long long *g_gs_prof = nullptr;
+extern "C" int hl_gn_skip_set_profile(void *dev_counters) {
+    g_gs_prof = (unsigned long long *)dev_counters;
+    return HL_OK;
+}
 
 extern "C" int hl_gn_skip_supported(int B, int HW, int Cin, int Cout) {
     GsParams p = {};
@@ -368,7 +423,7 @@ extern "C" int hl_gn_skip(const float *x, int ldx, const double *stats, int stat
         return HL_E_CUDA;
     }
     p.Cin = Cin; p.Cout = Cout; p.HW = HW; p.groups = groups; p.stats_ld = stats_ld; p.ld_act = ld_act; p.ld_skip = ld_skip;
-    p.eps = eps; p.stats = stats; p.gamma = gamma; p.beta = beta; p.bias = bias; p.act = (__half *)act; p.skip = skip;
+    p.eps = eps; p.stats = stats; p.gamma = gamma; p.beta = beta; p.bias = bias; p.act = (__half *)act; p.skip = skip; p.prof = g_gs_prof;
     CUtensorMap tmX, tmW;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)B * HW};

@@ -169,6 +169,9 @@ int hl_gn_stats(const float *x, int ldx, int B, int HW, int C, double *stats, in
  * followed by hl_conv2d(HL_CONV_SPLIT3): act bit-identical, skip up to fp32 accumulation order.  Half the HBM bytes.
  * hl_gn_skip_supported: H*W % 128 == 0, Cin % 64 == 0, Cout <= 256 (or 2 x 192 / 2 x 256).                            */
 int hl_gn_skip_supported(int B, int HW, int Cin, int Cout);
+/* diagnostics: 10 cycle counters of (CTA 0, thread 0) -- bookkeeping, wait x, act, wait A buffer, split, barrier, MMA issue,
+ * wait last MMAs, epilogue, tiles -- accumulated while non-null */
+int hl_gn_skip_set_profile(void *dev_counters);
 int hl_gn_skip(const float *x, int ldx, const double *stats, int stats_ld, const float *gamma, const float *beta,
                void *act, int ld_act, const void *wpk, const float *bias, float *skip, int ld_skip, int B, int HW,
                int Cin, int Cout, int groups, float eps, void *stream);

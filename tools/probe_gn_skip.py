@@ -48,6 +48,16 @@ for H, Cin, Cout in ((256, 384, 192), (128, 576, 192), (128, 384, 192), (64, 768
         e1.record()
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / 20 * 1e3
+    prof = torch.zeros(16, device=dev, dtype=torch.int64)
+    lib = _lib.load()
+    lib.hl_gn_skip_set_profile(prof.data_ptr())
+    fused()
+    torch.cuda.synchronize()
+    lib.hl_gn_skip_set_profile(None)
+    pr = prof.cpu().tolist()
+    names = ["bookkeeping", "wait_x", "act", "wait_A", "split", "barrier", "mma_issue", "wait_last_mma", "epilogue"]
+    tiles = max(pr[9], 1)
+    print("      cycles per tile (CTA 0, thread 0): " + ", ".join("%s %d" % (n_, v // tiles) for n_, v in zip(names, pr)) + ", tiles %d" % tiles)
     nb = B * HW * (Cin * 6 + Cout * 4)
     print("%3d^2 %4d->%3d B=%d: two launches %6.1f us, fused %6.1f us (%5.0f GB/s of %d MB compulsory)" % (
         H, Cin, Cout, B, res["two launches"], res["fused"], nb / res["fused"] / 1e3, nb >> 20), flush=True)

@@ -21,9 +21,10 @@
 //   tile        128 consecutive pixels of one sample (H*W % 128 == 0), all Cout channels (Cout <= 256, or 2 x 192)
 //   warps 0-7   compute: thread = (pixel i of the tile = TMEM lane i, one 32-channel half of the chunk): x row from the X
 //               ring -> act into the staging tile, hi / lo operand rows -> barrier -> one elected thread issues the chunk's
-//               MMAs; after the last chunk: tcgen05.ld of the accumulator row + bias -> staging tiles -> TMA store of `skip`
+//               MMAs
 //               (four compute warps -- one per scheduler, nothing to hide their dependent latencies -- ran at 3.0 TB/s)
 //   warp 8      X producer: two TMA boxes {32 ch, 128 px} fp32 per chunk into a ring of 3 slots (the bytes in flight)
+//   warps 11-14 epilogue: accumulator row + bias -> staging tile -> TMA store of `skip` (two accumulator tiles when Cout <= 192)
 //   warp 10     MMA issuer (a chunk's 12 MMAs are issued at the pace they execute: a compute warp must not do it)
 //   warp 9      W producer: per chunk the W_hi tiles of every n tile, then the W_lo tiles ({64 ch, nt rows} fp16)
 #include "common.cuh"
@@ -41,12 +42,15 @@ constexpr int GS_XSLOT = 32 * 1024;      // one 64-channel fp32 chunk of 128 pix
 constexpr int GS_ATILE = 16 * 1024;      // one fp16 operand tile [128 rows][128 B]
 constexpr int GS_MAX_C = 1536;
 constexpr int GS_COMPUTE = 256;         // 8 compute warps: two threads per pixel row
-constexpr int GS_THREADS = GS_COMPUTE + 96;      // + X producer, W producer, MMA issuer
+constexpr int GS_EPI = 128;             // 4 epilogue warps (one thread per TMEM lane)
+constexpr int GS_THREADS = GS_COMPUTE + 96 + GS_EPI;      // + X producer, W producer, MMA issuer, epilogue
 constexpr int GS_MAX_NX = 4, GS_MAX_NW = 3;
 constexpr uint32_t GS_TM_A = 384;        // tensor memory: accumulators in columns [0, Cout <= 384), two A buffers (hi 32 | lo 32) behind
 
 struct GsParams {
     int Cin, Cout, kchunks, nt, n_tiles, nx, nw, HW, total_tiles, groups, stats_ld, ld_act, ld_skip, tmem_cols;
+    int acc_bufs;                 // 2 when two accumulator tiles fit in front of the A buffers (Cout <= 192): the epilogue of
+                                  // tile t overlaps the MMAs of tile t + 1
     float eps;
     const double *stats;
     const float *gamma, *beta, *bias;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
 k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
               const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmSkip, const GsParams p) {
     extern __shared__ uint8_t gs_smem[];
-    __shared__ __align__(8) uint64_t bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 5];
+    __shared__ __align__(8) uint64_t bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 8];
     __shared__ uint32_t tmem_slot;
     __shared__ float gmean[64], grstd[64];
 
@@ -81,12 +85,16 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t sm_x = base;
     const uint32_t sm_w = sm_x + (uint32_t)p.nx * GS_XSLOT;
     const uint32_t w_bytes = (uint32_t)p.nt * 128u;
-    const uint32_t sm_o = sm_w + (uint32_t)p.nw * w_bytes;                  // two output staging tiles [128 rows][128 B]
-    float *coef = reinterpret_cast<float *>(gs_smem + (sm_o + 2u * GS_ATILE - smem_u32(gs_smem)));   // ca[Cin] | cb[Cin]
+    const uint32_t sm_o = sm_w + (uint32_t)p.nw * w_bytes;                  // two act staging tiles [128 rows][128 B] + one for skip
+    const uint32_t sm_s = sm_o + 2u * GS_ATILE;
+    float *coef = reinterpret_cast<float *>(gs_smem + (sm_s + GS_ATILE - smem_u32(gs_smem)));   // ca[Cin] | cb[Cin]
     const uint32_t bar_x_full = smem_u32(&bars[0]), bar_x_empty = smem_u32(&bars[GS_MAX_NX]);
     const uint32_t bar_w_full = smem_u32(&bars[2 * GS_MAX_NX]), bar_w_empty = smem_u32(&bars[2 * GS_MAX_NX + GS_MAX_NW]);
     const uint32_t bar_a_empty = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW]);
     const uint32_t bar_a_full = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 2]);
+    const uint32_t bar_acc_full = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 4]);
+    const uint32_t bar_acc_free = smem_u32(&bars[2 * GS_MAX_NX + 2 * GS_MAX_NW + 6]);
+    const uint32_t acc_stride = (uint32_t)(p.nt * p.n_tiles);
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -99,7 +107,10 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         mbar_init(bar_a_empty + 8, 1);
         mbar_init(bar_a_full, GS_COMPUTE);
         mbar_init(bar_a_full + 8, GS_COMPUTE);
-        mbar_init(bar_a_full + 16, GS_COMPUTE);            // accumulators drained (once per tile)
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_full + 8, 1);
+        mbar_init(bar_acc_free, GS_EPI);
+        mbar_init(bar_acc_free + 8, GS_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -154,8 +165,12 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         // when a compute warp issued them, stalling all eight at the next barrier).  Per n tile:
         //   acc += x_hi.W_hi + x_lo.W_hi   (slab 0),   acc += x_hi.W_lo   (slab 1)
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(GS_ROWS >> 4) << 24);   // f16 x f16 -> f32, K-major
-        uint32_t swr = 0, phw = 0, g = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        uint32_t swr = 0, phw = 0, g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            // accumulator tile of this output tile; its previous contents must have left tensor memory
+            const uint32_t buf = p.acc_bufs == 2 ? (it & 1u) : 0u, use = it / (uint32_t)p.acc_bufs;
+            if (use) mbar_wait(bar_acc_free + 8 * buf, (use - 1u) & 1u);
+            tc_fence_after();
             for (int c = 0; c < p.kchunks; ++c, ++g) {
                 const uint32_t ab = g & 1u;
                 mbar_wait(bar_a_full + 8 * ab, (g >> 1) & 1u);
@@ -167,7 +182,7 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         mbar_wait(bar_w_full + 8 * swr, phw);
                         tc_fence_after();
                         const uint64_t bd = gs_desc(sm_w + swr * w_bytes);
-                        const uint32_t d = tmem + (uint32_t)(nti * p.nt);
+                        const uint32_t d = tmem + buf * acc_stride + (uint32_t)(nti * p.nt);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_ts_f16(d, ah + 8u * (uint32_t)k, bd + 2 * k, idesc, (c | slab | k) != 0 ? 1u : 0u);
@@ -179,13 +194,50 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         if (++swr == (uint32_t)p.nw) { swr = 0; phw ^= 1u; }
                     }
                     umma_commit(bar_a_empty + 8 * ab);
+                    if (c == p.kchunks - 1) umma_commit(bar_acc_full + 8 * buf);     // the tile's accumulators are complete
                 }
                 __syncwarp();
             }
-            // the next tile's first MMA overwrites the accumulators: every row must have left tensor memory
-            mbar_wait(bar_a_full + 16, (uint32_t)((tile - (int)blockIdx.x) / (int)gridDim.x) & 1u);
-            tc_fence_after();
         }
+    } else if (warp >= 11) {
+        // ---------------------------------- epilogue: skip = accumulators + bias ----------------------------------
+        // 4 warps, thread = TMEM lane = pixel row; 32 columns at a time through ONE staging tile and a TMA store.  Its own
+        // warps, so that the compute warps go straight to the next tile (as part of their loop it was 22 % of a tile).
+        const int et = threadIdx.x - (GS_COMPUTE + 96);           // 0..127
+        const int q = warp & 3;                                    // the lane quarter this warp may access
+        const int row = q * 32 + (threadIdx.x & 31);
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const bool issuer = et == 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = p.acc_bufs == 2 ? (it & 1u) : 0u, use = it / (uint32_t)p.acc_bufs;
+            mbar_wait(bar_acc_full + 8 * buf, use & 1u);
+            tc_fence_after();
+            for (int col = 0; col < p.Cout; col += 32) {
+                float v[32];
+                tmem_ld32(tlane + buf * acc_stride + (uint32_t)col, v);
+                const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + col);
+                if (issuer) bulk_wait_read<0>();           // the previous chunk's store has read the tile out
+                named_bar(2, GS_EPI);
+                const uint32_t orow = sm_s + (uint32_t)row * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bz = __ldg(bias4 + j);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(v[4 * j] + bz.x),
+                                 "f"(v[4 * j + 1] + bz.y), "f"(v[4 * j + 2] + bz.z), "f"(v[4 * j + 3] + bz.w) : "memory");
+                }
+                fence_async_smem();
+                named_bar(2, GS_EPI);
+                if (issuer) {
+                    tma_store_2d(&tmSkip, sm_s, col, tile * GS_ROWS);
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_acc_free + 8 * buf);            // every row of this accumulator tile has left tensor memory
+        }
+        if (issuer) bulk_wait_read<0>();
     } else {
         // ------------- compute: 8 warps; thread = (pixel row = TMEM lane, channel half of the 64-channel chunk) -------------
         const int tid = threadIdx.x;                       // 0..255
@@ -319,41 +371,6 @@ k_gn_skip_tc5(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 so ^= 1u;
                 GSPROF(6)                                           // act store issue
             }
-            // ---- skip = accumulators + bias: two 32-column chunks per round (one per channel half of the threads), each
-            //      through its own staging tile ----
-            mbar_wait(bar_a_empty + 8 * ((g - 1u) & 1u), ((g - 1u) >> 1) & 1u);     // the last chunk's MMAs (and all before) retired
-            tc_fence_after();
-            GSPROF(7)                                               // waiting for the tile's last MMAs
-            for (int col0 = 0; col0 < p.Cout; col0 += 64) {
-                const int col = col0 + 32 * half;
-                if (issuer) bulk_wait_read<0>();           // the stores that last used the two tiles have read them out
-                named_bar(1, GS_COMPUTE);
-                if (col < p.Cout) {
-                    float v[32];
-                    tmem_ld32(tlane + (uint32_t)col, v);
-                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + col);
-                    const uint32_t orow = sm_o + (uint32_t)half * GS_ATILE + (uint32_t)row * 128u;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 bz = __ldg(bias4 + j);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + (((uint32_t)j ^ sw) << 4)), "f"(v[4 * j] + bz.x),
-                                     "f"(v[4 * j + 1] + bz.y), "f"(v[4 * j + 2] + bz.z), "f"(v[4 * j + 3] + bz.w) : "memory");
-                    }
-                }
-                fence_async_smem();
-                named_bar(1, GS_COMPUTE);
-                if (issuer) {
-                    tma_store_2d(&tmSkip, sm_o, col0, tile * GS_ROWS);
-                    if (col0 + 32 < p.Cout) tma_store_2d(&tmSkip, sm_o + GS_ATILE, col0 + 32, tile * GS_ROWS);
-                    bulk_commit();
-                }
-            }
-            // every row has left tensor memory and both staging tiles have been read out before the next tile starts
-            if (issuer) bulk_wait_read<0>();
-            tc_fence_before();
-            mbar_arrive(bar_a_full + 16);                           // accumulators drained -> the MMA warp may start the next tile
-            named_bar(1, GS_COMPUTE);
-            GSPROF(8)                                               // epilogue
             if (prof) atomicAdd(p.prof + 9, 1ull);                  // tiles of CTA 0
         }
 #undef GSPROF
@@ -379,8 +396,9 @@ bool gs_plan(int B, int HW, int Cin, int Cout, GsParams *p, size_t *smem) {
     p->n_tiles = n_tiles;
     if (nt * n_tiles > (int)GS_TM_A) return false;
     p->tmem_cols = 512;
+    p->acc_bufs = 2 * nt * n_tiles <= (int)GS_TM_A ? 2 : 1;
     p->nw = 3;
-    const int fixed = 1024 + p->nw * nt * 128 + 2 * GS_ATILE /* output staging */ + 2 * Cin * (int)sizeof(float);
+    const int fixed = 1024 + p->nw * nt * 128 + 3 * GS_ATILE /* act staging x 2, skip staging */ + 2 * Cin * (int)sizeof(float);
     const int budget = 227 * 1024 - 2048;        // static shared memory: barriers, group statistics
     int nx = (budget - fixed) / GS_XSLOT;
     if (nx > GS_MAX_NX) nx = GS_MAX_NX;

@@ -19,14 +19,22 @@
 // fp32 accumulation order (chunk-major instead of pass-major).
 //
 //   tile        128 consecutive pixels of one sample (H*W % 128 == 0), all Cout channels (Cout <= 256, or 2 x 192)
-//   warps 0-7   compute: thread = (pixel i of the tile = TMEM lane i, one 32-channel half of the chunk): x row from the X
-//               ring -> act into the staging tile, hi / lo operand rows -> barrier -> one elected thread issues the chunk's
-//               MMAs
-//               (four compute warps -- one per scheduler, nothing to hide their dependent latencies -- ran at 3.0 TB/s)
+//   warps 0-7   compute: thread = (pixel i of the tile = TMEM lane i, one 32-channel half of the 64-channel chunk): x row
+//               from the X ring -> act into the staging tile, hi / lo operand halves -> tensor memory -> arrive on the
+//               MMA warp's barrier; one of them issues the act tile's TMA store
 //   warp 8      X producer: two TMA boxes {32 ch, 128 px} fp32 per chunk into a ring of 3 slots (the bytes in flight)
-//   warps 11-14 epilogue: accumulator row + bias -> staging tile -> TMA store of `skip` (two accumulator tiles when Cout <= 192)
-//   warp 10     MMA issuer (a chunk's 12 MMAs are issued at the pace they execute: a compute warp must not do it)
 //   warp 9      W producer: per chunk the W_hi tiles of every n tile, then the W_lo tiles ({64 ch, nt rows} fp16)
+//   warp 10     MMA issuer: per chunk and n tile  acc += x_hi.W_hi + x_lo.W_hi, then acc += x_hi.W_lo
+//   warps 11-14 epilogue: accumulator row + bias -> staging tile -> TMA store of `skip`; two accumulator tiles when
+//               Cout <= 192, so the epilogue of tile t overlaps the MMAs of tile t + 1
+// Measured on B200 (tools/probe_gn_skip.py, 384 -> 192 at 256^2, B = 4; two launches: 295 us):
+//   v0  4 compute warps, per-thread 16-byte global stores, MMAs issued by warp 0, operands in shared memory     323 us
+//   v1  outputs through staging tiles + TMA stores (the direct stores were L2-request-bound)                      266 us
+//   v2  8 compute warps (two per scheduler)                                                                       248 us
+//   v3  operands in tensor memory (double-buffered), three-deep weight ring                                       243 us
+//   v4  dedicated MMA-issue warp (issue proceeds at the pace of execution: 1.7 k cycles per chunk of a compute
+//       warp's time), coefficient refresh on 8 lanes per group                                                    205 us
+//   v5  dedicated epilogue warps, two accumulator tiles                                                           170 us = 4.7 TB/s
 #include "common.cuh"
 #include "tc5.cuh"
 

@@ -46,6 +46,8 @@ def pix(name, a):
         return a[16] * a[17]
     if name == "hl_gn_apply":
         return a[14]
+    if name == "hl_gn_skip":
+        return a[13]
     if name == "hl_attention":
         return a[7]
     return None
@@ -80,6 +82,7 @@ cases = {
     "gn_apply all": lambda n, a: n == "hl_gn_apply",
     "gn_apply HW>=128^2": lambda n, a: n == "hl_gn_apply" and a[14] >= 128 * 128,
     "gn_apply HW<=32^2": lambda n, a: n == "hl_gn_apply" and a[14] <= 32 * 32,
+    "gn_skip (fused GN1 + 1x1 skip)": lambda n, a: n == "hl_gn_skip",
     "attention": lambda n, a: n == "hl_attention",
     "cast/upsample/stats": lambda n, a: n in ("hl_cast_operand", "hl_upsample2x", "hl_gn_stats"),
     "everything at H<=32": lambda n, a: (pix(n, a) or 1 << 30) <= 32 * 32,

@@ -38,6 +38,8 @@ def key_of(name, a):
     if name == "hl_conv2d_dual":
         Bn, H, W, Cin, Cout, k, s, flags = a[15:23]
         return (name, H, Cin, Cout, k, s, "f%d" % flags)
+    if name == "hl_gn_skip":
+        return (name, a[13], a[14], a[15])
     if name == "hl_gn_apply":
         return (name, a[14], a[15], "film" if a[6] else "-", "raw" if a[11] else "-", "m%d" % a[19])
     if name == "hl_attention":

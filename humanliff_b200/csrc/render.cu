@@ -11,6 +11,18 @@
 // live in shared memory as [feature][point] so each layer is a 128x128xK register-tiled product
 // (8x8 micro-tile per thread) whose weights stream from L1/L2 (k-major packed, 267 KB total).
 // Compulsory HBM traffic: 32 B in + 20 B out per ray (+512 B of uniforms) + the 9.4 MB texel array once.
+//
+// Canonical-space variant (use_canonical_space=True, the TightCap branch of triplane_sample_layered.py:73-76;
+// human_diffusion/NeRF/renderer.py:52-133 deform_target2c / deform_target2c_op): every sample point is taken to the
+// posed body's SMPL frame, snapped to its nearest body vertex (pytorch3d knn_points, K = 1) and carried to the canonical
+// "big pose" by that vertex's skinning transforms; the view direction follows the same rotations, so the positional
+// encoding of views_linear becomes per sample instead of per ray.  Everything the reference does per *point* after the
+// nearest-vertex lookup depends on the vertex only (blend weights, blend-shape offsets and both joint-transform blends
+// are indexed by vert_ids), so k_smpl_vertex_tables folds the whole chain -- inverse skinning, minus pose and shape
+// offsets, plus big-pose offsets, forward skinning -- into one 3x4 affine per vertex (fp64 arithmetic, stored fp32),
+// once per frame.  Per point the render kernel then does: nearest vertex (exact, brute force over the vertex positions
+// staged in the 128 KB of shared memory the MLP activations do not need during the gather; two threads per point,
+// four vertices per 3 x LDS.128) and one affine.
 #include "common.cuh"
 
 int hl_num_sms();
@@ -31,6 +43,11 @@ struct RenderArgs {
     float *rgb, *acc, *depth;
     long long n_rays;
     int clamp_depth;
+    // canonical space (k_render<true> / k_density_canon only)
+    const float4 *knn;      // [V4][3] float4: x, y, z of four SMPL-frame vertices
+    const float4 *aff;      // [V][3] float4: rows of M | c  (canonical = M q + c, canonical direction = M v)
+    int V4;
+    float Rm[9], Th[3];     // params['R'], params['Th']: q = (p - Th) R
 };
 
 // F.softplus(beta=1, threshold=20).  log1p(exp(x)) = max(x,0) + log(1 + exp(-|x|)).
@@ -91,15 +108,62 @@ __device__ __forceinline__ void zero8x8(float (&acc)[8][8]) {
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 }
 
-// Nine-plane gather of one 128-point tile into Xs[27][128]  (renderer.py:504-549; A.5 of SURVEY)
-__device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_s, float ox, float oy,
-                                            float oz, float dx, float dy, float dz, float *Xs) {
+// Nearest body vertex of q (knn_points K = 1: fp32 squared distances, strict '<' so the lowest index wins ties) over the
+// vertex groups [g0, g1) staged in shared memory.
+__device__ __forceinline__ void nearest_scan(const float4 *kn, int g0, int g1, float qx, float qy, float qz,
+                                             float &best, int &bi) {
+    best = __int_as_float(0x7f800000);
+    bi = g0 * 4;
+#pragma unroll 2
+    for (int g = g0; g < g1; ++g) {
+        const float4 X = kn[g * 3 + 0], Y = kn[g * 3 + 1], Z = kn[g * 3 + 2];
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float ax = qx - xs[i], ay = qy - ys[i], az = qz - zs[i];
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+            if (d < best) { best = d; bi = g * 4 + i; }
+        }
+    }
+}
+
+// deform_target2c for the tile's 128 points (two threads per point): world point -> canonical point; optionally the
+// canonical view direction of the sample into vdc[3][128].  `kn_s` = the staged vertex positions (Ha | Hb), `nn_s` =
+// [2][128] (distance, index) exchange.  Ends with every thread holding its point's canonical position.
+__device__ __forceinline__ void canon_tile(const RenderArgs &a, float4 *kn_s, float *nn_s, float &px, float &py,
+                                           float &pz, const float *sv, float *vdc) {
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const float z = z_s[p];
-    // pts = o + d*z (separately rounded, as the reference's broadcasting arithmetic does)
-    const float px = __fadd_rn(ox, __fmul_rn(dx, z));
-    const float py = __fadd_rn(oy, __fmul_rn(dy, z));
-    const float pz = __fadd_rn(oz, __fmul_rn(dz, z));
+    for (int i = threadIdx.x; i < a.V4 * 3; i += NT) kn_s[i] = __ldg(a.knn + i);
+    const float ex = px - a.Th[0], ey = py - a.Th[1], ez = pz - a.Th[2];
+    const float qx = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
+    const float qy = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
+    const float qz = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
+    __syncthreads();
+    const int mid = a.V4 >> 1;
+    float best;
+    int bi;
+    nearest_scan(kn_s, half ? mid : 0, half ? a.V4 : mid, qx, qy, qz, best, bi);
+    nn_s[half * 256 + p] = best;
+    nn_s[half * 256 + 128 + p] = __int_as_float(bi);
+    __syncthreads();
+    const float d0 = nn_s[p], d1 = nn_s[256 + p];
+    const int v = d1 < d0 ? __float_as_int(nn_s[256 + 128 + p]) : __float_as_int(nn_s[128 + p]);
+    const float4 m0 = __ldg(a.aff + (size_t)v * 3), m1 = __ldg(a.aff + (size_t)v * 3 + 1), m2 = __ldg(a.aff + (size_t)v * 3 + 2);
+    px = fmaf(m0.z, qz, fmaf(m0.y, qy, fmaf(m0.x, qx, m0.w)));
+    py = fmaf(m1.z, qz, fmaf(m1.y, qy, fmaf(m1.x, qx, m1.w)));
+    pz = fmaf(m2.z, qz, fmaf(m2.y, qy, fmaf(m2.x, qx, m2.w)));
+    if (vdc && half == 0) {
+        vdc[p] = fmaf(m0.z, sv[2], fmaf(m0.y, sv[1], m0.x * sv[0]));
+        vdc[LDP + p] = fmaf(m1.z, sv[2], fmaf(m1.y, sv[1], m1.x * sv[0]));
+        vdc[2 * LDP + p] = fmaf(m2.z, sv[2], fmaf(m2.y, sv[1], m2.x * sv[0]));
+    }
+    __syncthreads();          // the staged vertices (Ha | Hb) and nn_s may be overwritten from here on
+}
+
+// Nine-plane gather of one 128-point tile into Xs[27][128]  (renderer.py:504-549; A.5 of SURVEY); thread (p, half) holds
+// point p = (px, py, pz)
+__device__ __forceinline__ void gather_point(const RenderArgs &a, float px, float py, float pz, float *Xs) {
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
     const float cx = 2.f * (px - a.bmin[0]) / (a.bmax[0] - a.bmin[0]) - 1.f;
     const float cy = 2.f * (py - a.bmin[1]) / (a.bmax[1] - a.bmin[1]) - 1.f;
     const float cz = 2.f * (pz - a.bmin[2]) / (a.bmax[2] - a.bmin[2]) - 1.f;
@@ -131,6 +195,20 @@ __device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_
         Xs[(c * 3 + 1) * LDP + p] = r1;
         Xs[(c * 3 + 2) * LDP + p] = r2;
     }
+}
+
+// one 128-sample tile of a ray: pts = o + d*z (separately rounded, as the reference's broadcasting arithmetic does)
+template <bool CANON>
+__device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_s, float ox, float oy,
+                                            float oz, float dx, float dy, float dz, float *Xs,
+                                            float4 *kn_s = nullptr, float *nn_s = nullptr, const float *sv = nullptr,
+                                            float *vdc = nullptr) {
+    const float z = z_s[threadIdx.x & 127];
+    float px = __fadd_rn(ox, __fmul_rn(dx, z));
+    float py = __fadd_rn(oy, __fmul_rn(dy, z));
+    float pz = __fadd_rn(oz, __fmul_rn(dz, z));
+    if (CANON) canon_tile(a, kn_s, nn_s, px, py, pz, sv, vdc);
+    gather_point(a, px, py, pz, Xs);
 }
 
 // pts_linears 0..2 (renderer.py:144-151): Xs -> Ha (h2);  uses Hb as scratch.
@@ -177,6 +255,7 @@ __device__ __forceinline__ float block_sum(float v, float *red_s) {
     return t;
 }
 
+template <bool CANON>
 __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
     extern __shared__ __align__(16) float sm[];
     float *Xs = sm;                       // [28][128]
@@ -194,6 +273,9 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
     float *part = peb + 64;               // [128] scratch
     float *red = part + NS;               // [8]
     float *pe = red + 8;                  // [28]
+    float *nn = pe + 28 + 4;              // CANON: [2][256] nearest-vertex exchange
+    float *vdc = nn + 512;                // CANON: [3][128] canonical view direction of the tile's samples
+    float4 *kn_s = reinterpret_cast<float4 *>(Ha);   // CANON: vertex positions during the gather (Ha | Hb are free then)
 
     const int tid = threadIdx.x;
     const int pg = tid & 15, og = tid >> 4;
@@ -230,13 +312,23 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
         __syncthreads();
         if (tid < 64) {
             float s = __ldg(mlp + HL_MLP_BV + tid);
+            if (!CANON) {          // per-ray view direction: its encoding folds into the bias of views_linear
 #pragma unroll
-            for (int k = 0; k < 27; ++k) s = fmaf(__ldg(mlp + HL_MLP_WV + (128 + k) * 64 + tid), pe[k], s);
+                for (int k = 0; k < 27; ++k) s = fmaf(__ldg(mlp + HL_MLP_WV + (128 + k) * 64 + tid), pe[k], s);
+            }
             peb[tid] = s;
+        }
+        // CANON: smpl_viewdir = (viewdir - Th) R  (renderer.py:125 subtracts Th from the direction too)
+        float sv[3] = {0.f, 0.f, 0.f};
+        if (CANON) {
+            const float ex = dx / dnorm - a.Th[0], ey = dy / dnorm - a.Th[1], ez = dz / dnorm - a.Th[2];
+            sv[0] = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
+            sv[1] = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
+            sv[2] = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
         }
 
         // ------------------------------- coarse pass (density only) -------------------------------
-        gather_tile(a, zc, ox, oy, oz, dx, dy, dz, Xs);
+        gather_tile<CANON>(a, zc, ox, oy, oz, dx, dy, dz, Xs, kn_s, nn);
         __syncthreads();
         trunk(mlp, Xs, Ha, Hb, pg, og);
         alpha_head(mlp, Ha, part, sig);
@@ -312,10 +404,25 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
 
         // ------------------------------- fine pass: 2 tiles of 128 --------------------------------
         for (int t = 0; t < 2; ++t) {
-            gather_tile(a, zf + t * NS, ox, oy, oz, dx, dy, dz, Xs);
+            gather_tile<CANON>(a, zf + t * NS, ox, oy, oz, dx, dy, dz, Xs, kn_s, nn, sv, vdc);
             __syncthreads();
             trunk(mlp, Xs, Ha, Hb, pg, og);
             alpha_head(mlp, Ha, part, sig + t * NS);
+            if (CANON) {   // Xs is free after the trunk: rows 0..26 <- positional encoding of the canonical direction
+                const int p = tid & 127;
+                for (int k = tid >> 7; k < 27; k += 2) {
+                    float v;
+                    if (k < 3) {
+                        v = vdc[k * LDP + p];
+                    } else {
+                        const int f = (k - 3) / 3, comp = (k - 3) % 3;
+                        const float freq = (float)(1 << (f >> 1));
+                        const float phase = (f & 1) ? 1.5707963267948966f : 0.f;
+                        v = sinf(__fadd_rn(phase, __fmul_rn(vdc[comp * LDP + p], freq)));
+                    }
+                    Xs[k * LDP + p] = v;
+                }
+            }
             {   // feature_linear (no activation): Hb = Wf . h2 + bf
                 float acc[8][8];
                 zero8x8(acc);
@@ -341,6 +448,19 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], w[j], acc[i][j]);
+                }
+                if (CANON) {       // views_linear columns 128..154: the per-sample view encoding
+                    for (int k = 0; k < 27; ++k) {
+                        const float4 a0 = *reinterpret_cast<const float4 *>(Xs + k * LDP + pg4 * 4);
+                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(mlp + HL_MLP_WV + (128 + k) * 64 + og8 * 8));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(mlp + HL_MLP_WV + (128 + k) * 64 + og8 * 8 + 4));
+                        const float av[4] = {a0.x, a0.y, a0.z, a0.w};
+                        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], w[j], acc[i][j]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -410,6 +530,152 @@ __global__ void k_triplane_to_texels(const float *__restrict__ planes, float4 *_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Per-frame vertex tables of the canonical-space deformation.  One warp per vertex.
+//   consts (device, fp64; J = joints, 24 for SMPL): A_pose [J][12] | A_big [J][12] (rows of the 3x4 joint transforms of
+//   get_transform_params_torch for params and for t_params with zero shape) | pose_feature [9(J-1)] | pose_feature_big
+//   [9(J-1)] (rot_mats[1:] - I, renderer.py:80-83,98-100) | betas [16] | R [9] | Th [3]
+// Per vertex v (everything deform_target2c_op indexes by vert_ids):
+//   A  = sum_j w[v][j] A_pose[j],  Ab = sum_j w[v][j] A_big[j]
+//   po = posedirs[v] . pose_feature,  pob = posedirs[v] . pose_feature_big,  so = shapedirs[v] . betas
+//   canonical(q) = Ab_R (A_R^-1 (q - A_t) - po - so + pob) + Ab_t  =  M q + c,   M = Ab_R A_R^-1
+// and the vertex position in the SMPL frame, (vertices[v] - Th) R, for the nearest-vertex search.
+
+__global__ void k_smpl_vertex_tables(const float *__restrict__ weights, const float *__restrict__ posedirs,
+                                     const float *__restrict__ shapedirs, int S_asset, int S,
+                                     const float *__restrict__ vertices, const double *__restrict__ cst, int V, int J,
+                                     float *__restrict__ knn, float4 *__restrict__ aff) {
+    const int PF = (J - 1) * 9;           // pose-feature length (207 for SMPL)
+    const int SC_APOSE = 0, SC_ABIG = J * 12, SC_PF = 2 * J * 12, SC_PFB = SC_PF + PF, SC_BETAS = SC_PFB + PF,
+              SC_R = SC_BETAS + 16, SC_TH = SC_R + 9;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int V4 = (V + 3) >> 2;
+    if (warp >= V4 * 4) return;
+    const int v = warp;
+    if (v >= V) {      // padding slots of the last group: never the nearest
+        if (lane < 3) knn[(size_t)(v >> 2) * 12 + lane * 4 + (v & 3)] = 1e18f;
+        return;
+    }
+    double po[3] = {0, 0, 0}, pob[3] = {0, 0, 0};
+    for (int k = lane; k < 3 * PF; k += 32) {
+        const int c = k / PF, f = k - c * PF;
+        const double pd = (double)posedirs[(size_t)v * 3 * PF + k];
+        po[c] += pd * cst[SC_PF + f];
+        pob[c] += pd * cst[SC_PFB + f];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            po[c] += __shfl_xor_sync(0xffffffffu, po[c], o);
+            pob[c] += __shfl_xor_sync(0xffffffffu, pob[c], o);
+        }
+    if (lane) return;
+    double A[12], Ab[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A[i] = Ab[i] = 0.0;
+    for (int j = 0; j < J; ++j) {
+        const double w = (double)weights[(size_t)v * J + j];
+        if (w == 0.0) continue;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            A[i] += w * cst[SC_APOSE + j * 12 + i];
+            Ab[i] += w * cst[SC_ABIG + j * 12 + i];
+        }
+    }
+    double so[3] = {0, 0, 0};
+    for (int c = 0; c < 3; ++c)
+        for (int b = 0; b < S; ++b) so[c] += (double)shapedirs[((size_t)v * 3 + c) * S_asset + b] * cst[SC_BETAS + b];
+    // inverse of the 3x3 block of A (row-major, row r = A[r*4 .. r*4+2], translation A[r*4+3])
+    const double a00 = A[0], a01 = A[1], a02 = A[2], a10 = A[4], a11 = A[5], a12 = A[6], a20 = A[8], a21 = A[9], a22 = A[10];
+    const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    const double id = 1.0 / det;
+    const double inv[9] = {c00 * id, (a02 * a21 - a01 * a22) * id, (a01 * a12 - a02 * a11) * id,
+                           c01 * id, (a00 * a22 - a02 * a20) * id, (a02 * a10 - a00 * a12) * id,
+                           c02 * id, (a01 * a20 - a00 * a21) * id, (a00 * a11 - a01 * a10) * id};
+    double off[3];           // -inv t - po - so + pob
+    for (int r = 0; r < 3; ++r)
+        off[r] = -(inv[r * 3] * A[3] + inv[r * 3 + 1] * A[7] + inv[r * 3 + 2] * A[11]) - po[r] - so[r] + pob[r];
+    for (int r = 0; r < 3; ++r) {
+        double m[3];
+        for (int c = 0; c < 3; ++c)
+            m[c] = Ab[r * 4] * inv[c] + Ab[r * 4 + 1] * inv[3 + c] + Ab[r * 4 + 2] * inv[6 + c];
+        const double cc = Ab[r * 4] * off[0] + Ab[r * 4 + 1] * off[1] + Ab[r * 4 + 2] * off[2] + Ab[r * 4 + 3];
+        aff[(size_t)v * 3 + r] = make_float4((float)m[0], (float)m[1], (float)m[2], (float)cc);
+    }
+    // smpl_pts = (vertices - Th) R in fp32, as the reference computes the search set (renderer.py:61)
+    const float ex = vertices[(size_t)v * 3] - (float)cst[SC_TH], ey = vertices[(size_t)v * 3 + 1] - (float)cst[SC_TH + 1],
+                ez = vertices[(size_t)v * 3 + 2] - (float)cst[SC_TH + 2];
+    for (int c = 0; c < 3; ++c)
+        knn[(size_t)(v >> 2) * 12 + c * 4 + (v & 3)] =
+            fmaf(ez, (float)cst[SC_R + 6 + c], fmaf(ey, (float)cst[SC_R + 3 + c], ex * (float)cst[SC_R + c]));
+}
+
+// deform_target2c on arbitrary points (tests / extract_geometry's canonical branch share it): 128 points per block
+__global__ void __launch_bounds__(NT, 1) k_canon_points(const RenderArgs a, const float *__restrict__ pts,
+                                                        const float *__restrict__ dirs, long long n,
+                                                        float *__restrict__ out_pts, float *__restrict__ out_dirs) {
+    extern __shared__ __align__(16) float sm[];
+    float4 *kn_s = reinterpret_cast<float4 *>(sm);
+    float *nn = sm + (size_t)a.V4 * 12;
+    float *vdc = nn + 512;
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    for (long long base = (long long)blockIdx.x * 128; base < n; base += (long long)gridDim.x * 128) {
+        const long long i = base + p < n ? base + p : n - 1;
+        float px = pts[i * 3], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
+        float sv[3] = {0.f, 0.f, 0.f};
+        if (dirs) {
+            const float ex = dirs[i * 3] - a.Th[0], ey = dirs[i * 3 + 1] - a.Th[1], ez = dirs[i * 3 + 2] - a.Th[2];
+            sv[0] = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
+            sv[1] = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
+            sv[2] = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
+        }
+        canon_tile(a, kn_s, nn, px, py, pz, sv, dirs ? vdc : nullptr);
+        if (half == 0 && base + p < n) {
+            out_pts[i * 3] = px; out_pts[i * 3 + 1] = py; out_pts[i * 3 + 2] = pz;
+            if (dirs) { out_dirs[i * 3] = vdc[p]; out_dirs[i * 3 + 1] = vdc[LDP + p]; out_dirs[i * 3 + 2] = vdc[2 * LDP + p]; }
+        }
+        __syncthreads();
+    }
+}
+
+// Density on a regular grid of the posed-space box with every grid point deformed to the canonical space
+// (extract_geometry with use_canonical_space=True, human_diffusion/NeRF/renderer.py:290-318: linspace^3 of
+// tp_input['world_bounds'], deform_target2c, features inside t_world_bounds, -sigma); 128 points per tile.
+__global__ void __launch_bounds__(NT, 1) k_density_grid_canon(const RenderArgs a, float3 wmin, float3 wmax, int res,
+                                                              float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float *Xs = sm;
+    float *Ha = Xs + 28 * LDP;
+    float *Hb = Ha + 128 * LDP;
+    float *sig = Hb + 128 * LDP;          // [128]
+    float *part = sig + NS;               // [128]
+    float *nn = part + NS;                // [512]
+    float4 *kn_s = reinterpret_cast<float4 *>(Ha);
+    const int tid = threadIdx.x, pg = tid & 15, og = tid >> 4;
+    const long long total = (long long)res * res * res;
+    const long long tiles = (total + 127) / 128;
+    // torch.linspace(lo, hi, R): lo + i*step below the midpoint, hi - (R-1-i)*step above (ATen)
+    auto lin = [&](float lo, float hi, int i) {
+        const float step = (hi - lo) / (float)(res - 1);
+        return i < res / 2 ? __fadd_rn(lo, __fmul_rn(step, (float)i)) : __fsub_rn(hi, __fmul_rn(step, (float)(res - 1 - i)));
+    };
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        long long idx = tile * 128 + (tid & 127);
+        if (idx >= total) idx = total - 1;
+        const int zi = (int)(idx % res), yi = (int)((idx / res) % res), xi = (int)(idx / ((long long)res * res));
+        float px = lin(wmin.x, wmax.x, xi), py = lin(wmin.y, wmax.y, yi), pz = lin(wmin.z, wmax.z, zi);
+        __syncthreads();     // previous tile consumed
+        canon_tile(a, kn_s, nn, px, py, pz, nullptr, nullptr);
+        gather_point(a, px, py, pz, Xs);
+        __syncthreads();
+        trunk(a.mlp, Xs, Ha, Hb, pg, og);
+        alpha_head(a.mlp, Ha, part, sig);
+        if (tid < 128 && tile * 128 + tid < total) out[tile * 128 + tid] = -sig[tid];
+    }
+}
+
 }  // namespace
 
 extern "C" int hl_triplane_to_texels(const float *planes, float *texels, int R, void *stream) {
@@ -423,14 +689,16 @@ extern "C" int hl_triplane_to_texels(const float *planes, float *texels, int R, 
     return HL_OK;
 }
 
-extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packed, const float *rays_o,
-                              const float *rays_d, const float *near, const float *far,
-                              const float *z_coarse, const float *u, uint64_t seed, const float *bounds,
-                              float *rgb, float *acc, float *depth,
-                              int64_t n_rays, int clamp_depth, void *stream) {
-    HL_CHECK_ARG(texels && mlp_packed && rays_o && rays_d && near && far && bounds && rgb && acc && depth);
-    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
-    RenderArgs a;
+
+static size_t render_smem_bytes() {
+    return sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + NS * 2 + 2 * NS * 3 + NS * 2 + 3 * 2 * NS + 64 + NS + 8 +
+                                    28 + 4 + 512 + 3 * LDP);
+}
+
+static int fill_render_args(RenderArgs &a, const float *texels, int R, const float *mlp_packed, const float *rays_o,
+                            const float *rays_d, const float *near, const float *far, const float *z_coarse,
+                            const float *u, uint64_t seed, const float *bounds, float *rgb, float *acc, float *depth,
+                            int64_t n_rays, int clamp_depth) {
     a.tex = reinterpret_cast<const float4 *>(texels);
     a.R = R;
     a.mlp = mlp_packed;
@@ -440,16 +708,134 @@ extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packe
     a.rgb = rgb; a.acc = acc; a.depth = depth;
     a.n_rays = n_rays;
     a.clamp_depth = clamp_depth;
-    const size_t smem = sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + NS * 2 + 2 * NS * 3 + NS * 2 +
-                                                 3 * 2 * NS + 64 + NS + 8 + 28 + 4);
+    a.knn = nullptr; a.aff = nullptr; a.V4 = 0;
+    for (int i = 0; i < 9; ++i) a.Rm[i] = (i % 4 == 0) ? 1.f : 0.f;
+    a.Th[0] = a.Th[1] = a.Th[2] = 0.f;
+    return HL_OK;
+}
+
+extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packed, const float *rays_o,
+                              const float *rays_d, const float *near, const float *far,
+                              const float *z_coarse, const float *u, uint64_t seed, const float *bounds,
+                              float *rgb, float *acc, float *depth,
+                              int64_t n_rays, int clamp_depth, void *stream) {
+    HL_CHECK_ARG(texels && mlp_packed && rays_o && rays_d && near && far && bounds && rgb && acc && depth);
+    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
+    RenderArgs a;
+    fill_render_args(a, texels, R, mlp_packed, rays_o, rays_d, near, far, z_coarse, u, seed, bounds, rgb, acc, depth,
+                     n_rays, clamp_depth);
+    const size_t smem = render_smem_bytes();
     static bool configured = false;
     if (!configured) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int64_t grid = hl_num_sms();
     if (grid > n_rays) grid = n_rays;
-    k_render<<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a);
+    k_render<false><<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+extern "C" int hl_smpl_vertex_tables(const float *weights, const float *posedirs, const float *shapedirs, int n_betas_asset,
+                                     int n_betas, const float *vertices, const double *consts, int n_verts, int n_joints,
+                                     float *knn_table, float *affine_table, void *stream) {
+    HL_CHECK_ARG(n_joints >= 2 && n_joints <= 64);
+    HL_CHECK_ARG(weights && posedirs && shapedirs && vertices && consts && knn_table && affine_table);
+    HL_CHECK_ARG(n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS && n_betas >= 0 && n_betas <= 16 && n_betas <= n_betas_asset);
+    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+    const int slots = (n_verts + 3) / 4 * 4;
+    k_smpl_vertex_tables<<<hl_cdiv((int64_t)slots * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        weights, posedirs, shapedirs, n_betas_asset, n_betas, vertices, consts, n_verts, n_joints, knn_table,
+        reinterpret_cast<float4 *>(affine_table));
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+static int set_canon(RenderArgs &a, const float *knn_table, const float *affine_table, int n_verts, const float *rot,
+                     const float *trans) {
+    a.knn = reinterpret_cast<const float4 *>(knn_table);
+    a.aff = reinterpret_cast<const float4 *>(affine_table);
+    a.V4 = (n_verts + 3) / 4;
+    for (int i = 0; i < 9; ++i) a.Rm[i] = rot[i];
+    for (int i = 0; i < 3; ++i) a.Th[i] = trans[i];
+    return HL_OK;
+}
+
+extern "C" int hl_render_rays_canon(const float *texels, int R, const float *mlp_packed, const float *rays_o,
+                                    const float *rays_d, const float *near, const float *far, const float *z_coarse,
+                                    const float *u, uint64_t seed, const float *t_bounds, const float *knn_table,
+                                    const float *affine_table, int n_verts, const float *rot, const float *trans,
+                                    float *rgb, float *acc, float *depth, int64_t n_rays, int clamp_depth, void *stream) {
+    HL_CHECK_ARG(texels && mlp_packed && rays_o && rays_d && near && far && t_bounds && rgb && acc && depth);
+    HL_CHECK_ARG(knn_table && affine_table && rot && trans && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
+    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
+    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+    RenderArgs a;
+    fill_render_args(a, texels, R, mlp_packed, rays_o, rays_d, near, far, z_coarse, u, seed, t_bounds, rgb, acc, depth,
+                     n_rays, clamp_depth);
+    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
+    const size_t smem = render_smem_bytes();
+    static bool configured = false;
+    if (!configured) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t grid = hl_num_sms();
+    if (grid > n_rays) grid = n_rays;
+    k_render<true><<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+extern "C" int hl_canonical_points(const float *pts, const float *dirs, int64_t n, const float *knn_table,
+                                   const float *affine_table, int n_verts, const float *rot, const float *trans,
+                                   float *out_pts, float *out_dirs, void *stream) {
+    HL_CHECK_ARG(pts && out_pts && n > 0 && knn_table && affine_table && rot && trans);
+    HL_CHECK_ARG((dirs == nullptr) == (out_dirs == nullptr) && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
+    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+    RenderArgs a = {};
+    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
+    const size_t smem = sizeof(float) * ((size_t)a.V4 * 12 + 512 + 3 * LDP);
+    static bool configured = false;
+    if (!configured) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_canon_points, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(float) * ((size_t)HL_SMPL_MAX_VERTS * 3 + 512 + 3 * LDP))));
+        configured = true;
+    }
+    int64_t grid = (n + 127) / 128;
+    if (grid > 2 * hl_num_sms()) grid = 2 * hl_num_sms();
+    k_canon_points<<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a, pts, dirs, (long long)n, out_pts, out_dirs);
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+
+extern "C" int hl_density_grid_canon(const float *texels, int R, const float *mlp_packed, const float *world_bounds,
+                                     const float *t_bounds, const float *knn_table, const float *affine_table,
+                                     int n_verts, const float *rot, const float *trans, int resolution, float *out,
+                                     void *stream) {
+    HL_CHECK_ARG(texels && mlp_packed && world_bounds && t_bounds && knn_table && affine_table && rot && trans && out);
+    HL_CHECK_ARG(R > 0 && resolution >= 2 && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
+    HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
+    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+    RenderArgs a = {};
+    a.tex = reinterpret_cast<const float4 *>(texels);
+    a.R = R;
+    a.mlp = mlp_packed;
+    for (int i = 0; i < 3; ++i) { a.bmin[i] = t_bounds[i]; a.bmax[i] = t_bounds[3 + i]; }
+    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
+    const size_t smem = sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + 2 * NS + 512);
+    static bool configured = false;
+    if (!configured) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_density_grid_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long tiles = ((long long)resolution * resolution * resolution + 127) / 128;
+    long long grid = hl_num_sms();
+    if (grid > tiles) grid = tiles;
+    k_density_grid_canon<<<(int)grid, NT, smem, (cudaStream_t)stream>>>(
+        a, make_float3(world_bounds[0], world_bounds[1], world_bounds[2]),
+        make_float3(world_bounds[3], world_bounds[4], world_bounds[5]), resolution, out);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }

@@ -7,8 +7,14 @@ State-dict keys match the reference (pts_linears.{0,1,2}, feature_linear, alpha_
 rgb_linear, view_enc._freqs/_phases [, tri_planes]); the whole coarse -> resample -> fine -> composite
 chain of one ray batch is ONE kernel launch (``hl_render_rays``), so the reference's 16-chunk loop,
 its [4.2 M x 155] temporaries and ``empty_cache()`` calls disappear.  Only the inference envelope is
-built: ``use_canonical_space=False``, ``n_samples == n_importance == 128``, ``perturb == 0``,
-``white_bkgd=False`` (the reference's white_bkgd branch is shape-broken).
+built: ``n_samples == 128``, ``n_importance in {0, 128}``, ``perturb == 0``, ``white_bkgd=False`` (the reference's
+white_bkgd branch is shape-broken).
+
+``use_canonical_space=True`` (the TightCap branch of triplane_sample_layered.py:73-76; renderer.py:52-133): every sample
+point is deformed to the canonical big-pose space inside the kernel -- nearest SMPL vertex (the reference's pytorch3d
+``knn_points``), then that vertex's skinning affine from a per-frame table (``smpl.py``, ``hl_smpl_vertex_tables``).  This
+mode runs on the exact fp32 kernel (``hl_render_rays_canon``) whatever ``precision`` says: its cost is the nearest-vertex
+search, not the MLP.
 
 ``precision="fp16"`` (default) runs the decoder MLP on the 5th-generation tensor cores (``hl_render_rays_tc5``:
 tcgen05.mma, fp16 operands, fp32 accumulators and activations in tensor memory, two ray groups per SM);
@@ -16,6 +22,7 @@ tcgen05.mma, fp16 operands, fp32 accumulators and activations in tensor memory, 
 cross-check; ``"fp32"`` selects the exact CUDA-core kernel.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -70,14 +77,24 @@ class Renderer(nn.Module):
     clamp_depth = True   # human_diffusion/NeRF/renderer.py:273-274
 
     def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18,
-                 smpl_type=None, test=False, precision="fp16"):
+                 smpl_type="smpl", test=False, precision="fp16", smpl=None, smpl_path=None):
+        """``smpl`` (extension): the body-model arrays as a dict (keys of SMPL_NEUTRAL.pkl) instead of the asset file the
+        reference reads at construction (``assets/SMPL_NEUTRAL.pkl`` / ``assets/models/smplx/SMPLX_NEUTRAL.npz``,
+        renderer.py:41-50); only needed -- and only loaded -- when ``use_canonical_space=True``."""
         super().__init__()
         if precision not in ("fp16", "fp16_mma", "fp32"):
             raise ValueError("precision must be 'fp16' (tcgen05 MLP), 'fp16_mma' (mma.sync MLP) or 'fp32' (exact "
                              "CUDA-core MLP)")
         self.precision = precision
+        self.smpl = None
         if use_canonical_space:
-            raise NotImplementedError("use_canonical_space=True (TightCap SMPL deformation) is a 'next' row")
+            from .smpl import SmplModel, read_asset
+            if smpl is None:
+                default = (os.path.join("assets", "models", "smplx", "SMPLX_NEUTRAL.npz") if smpl_type == "smplx"
+                           else os.path.join("assets", "SMPL_NEUTRAL.pkl"))
+                smpl = read_asset(smpl_path or default)
+            self.smpl = smpl if isinstance(smpl, SmplModel) else SmplModel(smpl)
+            self.faces = self.smpl.faces
         if triplane_ch != 27:
             raise NotImplementedError("the fused kernel is built for the 27-channel nine-plane layout")
         self.use_canonical_space = use_canonical_space
@@ -206,10 +223,12 @@ class Renderer(nn.Module):
     # ------------------------------------------------------------------ the fused launch
     @torch.no_grad()
     def render_rays(self, tri_planes, bounds, rays_o, rays_d, near, far, z_coarse=None, u=None, seed=0,
-                    n_importance=N_SAMPLES):
+                    n_importance=N_SAMPLES, canon=None):
         """One tri-plane ([3, 9, R, R]), one bounds box ([2, 3]), N rays -> (rgb [N,3], acc [N], depth [N]).
         ``bounds`` may be a CUDA tensor (the scripts' ``tp_input['world_bounds']``): it is read on the device, no
-        host synchronisation.  ``n_importance=0``: no coarse pass, the 128 coarse depths are composited."""
+        host synchronisation.  ``n_importance=0``: no coarse pass, the 128 coarse depths are composited.
+        ``canon``: the frame tables of ``SmplModel.frame_tables`` -- canonical-space mode; ``bounds`` is then the
+        frame's ``t_world_bounds``."""
         if not rays_o.is_cuda:
             raise RuntimeError("humanliff_b200.Renderer runs on CUDA (sm_100a) only -- no CPU fallback")
         dev = rays_o.device
@@ -217,7 +236,7 @@ class Renderer(nn.Module):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).contiguous()
             assert planes.shape[0] == 3 and planes.shape[1] == 9 and planes.shape[2] == planes.shape[3]
-            tex = self._quads(planes) if self.precision == "fp16" else self._texels(planes)
+            tex = self._quads(planes) if (self.precision == "fp16" and canon is None) else self._texels(planes)
             n = rays_o.shape[0]
             f = lambda t: t.detach().to(dev, torch.float32).contiguous()
             rays_o, rays_d, near, far = f(rays_o), f(rays_d), f(near).view(-1), f(far).view(-1)
@@ -231,6 +250,21 @@ class Renderer(nn.Module):
             import ctypes
             if n_importance not in (0, N_SAMPLES):
                 raise NotImplementedError("the fused kernel implements n_importance == n_samples == 128, or 0")
+            if canon is not None:
+                if n_importance == 0:
+                    raise NotImplementedError("canonical space with n_importance=0")
+                barr = (ctypes.c_float * 6)(*[float(v) for v in torch.as_tensor(bounds).reshape(-1).tolist()])
+                rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+                acc = torch.empty(n, device=dev, dtype=torch.float32)
+                depth = torch.empty(n, device=dev, dtype=torch.float32)
+                call("hl_render_rays_canon", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), rays_o.data_ptr(),
+                     rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                     z_coarse.data_ptr() if z_coarse is not None else None, u.data_ptr() if u is not None else None,
+                     int(seed) & ((1 << 64) - 1), ctypes.cast(barr, ctypes.c_void_p), canon["knn"].data_ptr(),
+                     canon["aff"].data_ptr(), canon["n_verts"], ctypes.cast(canon["rot"], ctypes.c_void_p),
+                     ctypes.cast(canon["trans"], ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
+                     1 if self.clamp_depth else 0, torch.cuda.current_stream(dev).cuda_stream)
+                return rgb, acc, depth
             tc5 = self.precision == "fp16"
             if not tc5 and n_importance == 0:
                 raise NotImplementedError("n_importance=0 is served by the tcgen05 kernel (precision='fp16')")
@@ -260,6 +294,36 @@ class Renderer(nn.Module):
                 call("hl_render_rays", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), *tail)
         return rgb, acc, depth
 
+    # ------------------------------------------------------------------ canonical space
+    @torch.no_grad()
+    def deform_target2c(self, tp_input, pts, viewdir=None):
+        """human_diffusion/NeRF/renderer.py:115-133: ``pts`` [bs, M, 3] (+ ``viewdir`` [bs, M, 3]) -> (canonical_pts,
+        canonical_viewdir, box_warp).  With ``use_canonical_space=False`` the inputs are handed back with
+        ``world_bounds``; otherwise ``hl_canonical_points`` (nearest SMPL vertex + its per-frame skinning affine)."""
+        if not self.use_canonical_space:
+            return pts, viewdir, tp_input["world_bounds"]
+        if not pts.is_cuda:
+            raise RuntimeError("humanliff_b200.Renderer runs on CUDA (sm_100a) only -- no CPU fallback")
+        import ctypes
+        dev = pts.device
+        outs_p, outs_d = [], []
+        with torch.cuda.device(dev):
+            for b in range(pts.shape[0]):
+                canon = self.smpl.frame_tables(tp_input, b, dev)
+                p = pts[b].detach().to(dev, torch.float32).contiguous()
+                d = None if viewdir is None else viewdir[b].detach().to(dev, torch.float32).contiguous()
+                op = torch.empty_like(p)
+                od = None if d is None else torch.empty_like(d)
+                call("hl_canonical_points", p.data_ptr(), d.data_ptr() if d is not None else None, p.shape[0],
+                     canon["knn"].data_ptr(), canon["aff"].data_ptr(), canon["n_verts"],
+                     ctypes.cast(canon["rot"], ctypes.c_void_p), ctypes.cast(canon["trans"], ctypes.c_void_p),
+                     op.data_ptr(), od.data_ptr() if od is not None else None,
+                     torch.cuda.current_stream(dev).cuda_stream)
+                outs_p.append(op)
+                outs_d.append(od)
+        return (torch.stack(outs_p, 0), None if viewdir is None else torch.stack(outs_d, 0),
+                tp_input["t_world_bounds"])
+
     # ------------------------------------------------------------------ extract_geometry ("next" row)
     @torch.no_grad()
     def density_grid(self, tp_input, tri_planes, resolution=512):
@@ -273,11 +337,22 @@ class Renderer(nn.Module):
         with torch.cuda.device(dev):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).reshape(3, 9, *tri_planes.shape[-2:]).contiguous()
-            tex = self._quads(planes) if self.precision == "fp16" else self._texels(planes)
+            tex = None if self.use_canonical_space else (self._quads(planes) if self.precision == "fp16"
+                                                         else self._texels(planes))
             import ctypes
             wb = torch.as_tensor(tp_input["world_bounds"], dtype=torch.float32).reshape(-1, 6)[0]
             out = torch.empty(resolution, resolution, resolution, device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
+            if self.use_canonical_space:
+                canon = self.smpl.frame_tables(tp_input, 0, dev)
+                tb = torch.as_tensor(tp_input["t_world_bounds"], dtype=torch.float32).reshape(-1, 6)[0]
+                warr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])
+                tarr = (ctypes.c_float * 6)(*[float(v) for v in tb.tolist()])
+                call("hl_density_grid_canon", self._texels(planes).data_ptr(), planes.shape[-1], mlp.data_ptr(),
+                     ctypes.cast(warr, ctypes.c_void_p), ctypes.cast(tarr, ctypes.c_void_p), canon["knn"].data_ptr(),
+                     canon["aff"].data_ptr(), canon["n_verts"], ctypes.cast(canon["rot"], ctypes.c_void_p),
+                     ctypes.cast(canon["trans"], ctypes.c_void_p), int(resolution), out.data_ptr(), stream)
+                return out
             if self.precision == "fp16":
                 if wb.is_cuda:
                     wbd = wb.to(dev).contiguous()
@@ -315,14 +390,15 @@ class Renderer(nn.Module):
         bs, n_rays, n_samples = z_vals.shape
         if n_importance not in (0, N_SAMPLES) or n_samples != N_SAMPLES:
             raise NotImplementedError("the fused kernel implements n_samples == 128 with n_importance == 128 or 0")
-        wb = tp_input["world_bounds"]
+        wb = tp_input["t_world_bounds" if self.use_canonical_space else "world_bounds"]
         outs = {"rgb_map": [], "acc_map": [], "normal_map": [], "depth_map": []}
         for b in range(bs):
             ub = None if u is None else u[b * n_rays:(b + 1) * n_rays]
+            canon = self.smpl.frame_tables(tp_input, b, rays_o.device) if self.use_canonical_space else None
             rgb, acc, depth = self.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b],
                                                rays_o[b], rays_d[b], near[b].reshape(-1),
                                                far[b].reshape(-1), z_coarse=z_vals[b], u=ub,
-                                               seed=self._next_seed(b), n_importance=n_importance)
+                                               seed=self._next_seed(b), n_importance=n_importance, canon=canon)
             outs["rgb_map"].append(rgb)
             outs["acc_map"].append(acc)
             outs["normal_map"].append(rgb)     # normal_map aliases rgb_map (renderer.py:237)
@@ -345,8 +421,9 @@ class ReconRenderer(Renderer):
     clamp_depth = False
 
     def __init__(self, use_canonical_space=False, num_instances=1, triplane_dim=256, triplane_ch=18, test=False,
-                 precision="fp16"):
-        super().__init__(use_canonical_space, num_instances, triplane_dim, triplane_ch, None, test, precision)
+                 precision="fp16", smpl=None, smpl_path=None):
+        super().__init__(use_canonical_space, num_instances, triplane_dim, triplane_ch, "smpl", test, precision,
+                         smpl, smpl_path)
         self.tri_planes = nn.Parameter(torch.empty(num_instances, 4, 3, triplane_ch // 3, triplane_dim,
                                                    triplane_dim).normal_(0, 0.1), requires_grad=False)
 
@@ -384,13 +461,14 @@ def render(chunk=1024 * 32, rays_o=None, rays_d=None, near=0., far=1., tri_plane
     far = far.reshape(bs, -1)
     if tri_planes is None:
         tri_planes = r.tri_planes[tp_input["instance_idx"], tp_input["cloth_layer_index"]]
-    wb = tp_input["world_bounds"]
+    wb = tp_input["t_world_bounds" if r.use_canonical_space else "world_bounds"]
     rgbs, accs, deps = [], [], []
     for b in range(bs):
         ub = None if u is None else u[b * n:(b + 1) * n]
+        canon = r.smpl.frame_tables(tp_input, b, rays_o.device) if r.use_canonical_space else None
         rgb, acc, dep = r.render_rays(tri_planes[b].reshape(3, 9, *tri_planes.shape[-2:]), wb[b], rays_o[b],
                                       rays_d[b], near[b], far[b], z_coarse=None, u=ub,
-                                      seed=r._next_seed(b), n_importance=n_importance)
+                                      seed=r._next_seed(b), n_importance=n_importance, canon=canon)
         rgbs.append(rgb); accs.append(acc); deps.append(dep)
     rgb = torch.stack(rgbs, 0)
     return [rgb, torch.stack(accs, 0), rgb, torch.stack(deps, 0)]

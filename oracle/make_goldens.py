@@ -368,6 +368,64 @@ def render_noimp_case(name, n_rays=256, seed_w=3):
     print(name, "done in %.1fs" % (time.time() - t0), flush=True)
 
 
+def knn_points_bruteforce(p1, p2, K=1):
+    """Stand-in for pytorch3d.ops.knn.knn_points (pytorch3d 0.7.x, absent from this image; the reference calls it with
+    K=1, renderer.py:62).  Published behaviour restated: squared Euclidean distances in fp32, the K smallest per query
+    in ascending order, lowest index on ties -> (dists [N,P1,K], idx [N,P1,K] int64, None)."""
+    assert K == 1
+    ds, ids = [], []
+    for s in range(0, p1.shape[1], 8192):
+        q = p1[:, s:s + 8192]
+        d = ((q[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+        m, i = d.min(-1)
+        ds.append(m[..., None]); ids.append(i[..., None])
+    return torch.cat(ds, 1), torch.cat(ids, 1), None
+
+
+def render_canon_case(name, n_rays=384, seed_w=3, seed_smpl=5, seed_pose=21):
+    """use_canonical_space=True (the TightCap branch of triplane_sample_layered.py:73-76): the unmodified
+    human_diffusion/NeRF/renderer.py -- deform_target2c / deform_target2c_op (:52-133), get_transform_params_torch,
+    get_rigid_transformation_torch, batch_rodrigues, SMPL_to_tensor -- on a seeded SMPL-shaped asset
+    (synth.synth_smpl; the licensed SMPL_NEUTRAL.pkl ships with neither repo) and a brute-force stand-in for
+    pytorch3d's knn_points.  Also stores the per-point intermediates of the first 8 rays' coarse points."""
+    t0 = time.time()
+    hd = ref_shims.import_hd_renderer()
+    smpl = synth.synth_smpl(seed_smpl)
+    saved = (hd.read_pickle, hd.SMPL_to_tensor, hd.knn_points, torch.Tensor.cuda)
+    to_tensor = hd.SMPL_to_tensor
+    hd.read_pickle = lambda path: {k: v.copy() for k, v in smpl.items()}
+    hd.SMPL_to_tensor = lambda params, device=None: to_tensor(params, torch.device("cpu"))
+    hd.knn_points = knn_points_bruteforce
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    if not torch.cuda.is_available():
+        torch.cuda.current_device = lambda: 0
+    orig_rand = torch.rand
+    try:
+        torch.manual_seed(0)
+        r = hd.Renderer(use_canonical_space=True, triplane_ch=27, smpl_type="smpl", test=True)
+        shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+        r.load_state_dict(synth.synth_state_dict(shapes, seed=seed_w, weight_gain=1.5), strict=False)
+        planes = synth.synth_triplane(256, seed=7)
+        tp = synth.synth_canonical_frame(smpl, seed_pose)
+        ro, rd, near, far, u = synth.synth_canonical_rays(tp, n_rays)
+        torch.rand = lambda *a, **k: u.clone()
+        t = torch.linspace(0., 1., steps=128)
+        z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+        pts = ro[None, :, None, :] + rd[None, :, None, :] * z[..., :, None]
+        with torch.no_grad():
+            ret = r.render(tp, pts.reshape(1, -1, 3), z, ro[None], rd[None], near[None, :, None], far[None, :, None],
+                           planes, 128, False)
+            vd = (rd / rd.norm(dim=-1, keepdim=True))[:8, None].expand(8, 128, 3).reshape(1, -1, 3)
+            cpts, cdirs, _ = r.deform_target2c(tp, pts[:, :8].reshape(1, -1, 3), vd)
+    finally:
+        torch.rand = orig_rand
+        hd.read_pickle, hd.SMPL_to_tensor, hd.knn_points, torch.Tensor.cuda = saved
+    np.savez(os.path.join(OUT, name), n_rays=np.array(n_rays), seed_w=np.array(seed_w), seed_smpl=np.array(seed_smpl),
+             seed_pose=np.array(seed_pose), rgb=ret["rgb_map"][0].numpy(), acc=ret["acc_map"][0].numpy(),
+             depth=ret["depth_map"][0].numpy(), canonical_pts=cpts[0].numpy(), canonical_dirs=cdirs[0].numpy())
+    print(name, "done in %.1fs" % (time.time() - t0), "acc mean %.3f" % float(ret["acc_map"].mean()), flush=True)
+
+
 def loop_noise(k, shape, seed=9000):
     """Per-step Gaussian of the long free-running goldens: regenerated from (seed + k), never stored."""
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed + k))
@@ -445,6 +503,8 @@ if __name__ == "__main__":
         schedule_case("schedules.npz")
     if "render_noimp" in which:
         render_noimp_case("render_noimp_256.npz")
+    if "render_canon" in which:   # not in the default list: ~1 min of CPU (brute-force nearest vertex)
+        render_canon_case("render_canon_384.npz")
     if "loop50" in which:         # not in the default list: ~40 s of CPU
         unet_long_loop_case("unet_prod_64_loop50.npz", PROD, HW=64, steps=50, seed_w=0)
     if "prod256sweep" in which:   # not in the default list: ~1 min of CPU, 1.8 MB

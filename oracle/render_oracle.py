@@ -53,19 +53,108 @@ def mlp(sd, x, viewdir=None):
     return lin("rgb_linear", hv), sigma
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Canonical-space deformation (use_canonical_space=True): human_diffusion/NeRF/renderer.py:52-133 (deform_target2c_op,
+# deform_target2c), :354-420 (get_transform_params_torch, get_rigid_transformation_torch, batch_rodrigues_torch),
+# :435-462 (batch_rodrigues).  `smpl` = the asset as fp32 tensors (v_template [V,3], shapedirs [V,3,S], posedirs
+# [V,3,207], J_regressor [24,V], weights [V,24], parents [24]); `frame` = tp_input of one sample (batch 1).
+# pytorch3d's knn_points (K=1; third-party, pinned by the reference's environment to pytorch3d 0.7, absent here) is
+# restated as: fp32 squared distances, smallest wins, lowest index on ties.
+
+def smpl_tensors(asset):
+    f = lambda a: torch.as_tensor(a, dtype=torch.float64).float()
+    out = {k: f(asset[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")}
+    out["parents"] = [int(v) for v in asset["kintree_table"][0]]
+    return out
+
+
+def axis_angle_matrices(rv):
+    """[N,3] -> [N,3,3]: I + sin(a) K + (1 - cos(a)) K^2 with a = |rv + 1e-8| (both batch_rodrigues variants)."""
+    a = torch.norm(rv + 1e-8, dim=1, keepdim=True)
+    k = rv / a
+    z = torch.zeros_like(k[:, 0])
+    K = torch.stack([z, -k[:, 2], k[:, 1], k[:, 2], z, -k[:, 0], -k[:, 1], k[:, 0], z], 1).view(-1, 3, 3)
+    return torch.eye(3)[None] + torch.sin(a)[:, None] * K + (1 - torch.cos(a))[:, None] * torch.matmul(K, K)
+
+
+def joint_transforms(smpl, poses, shapes):
+    """get_transform_params_torch: poses [72], shapes [S] -> A [24,4,4] (posed joint frames with the rest joints
+    removed, i.e. the matrices linear blend skinning applies to rest-pose points)."""
+    v_shaped = smpl["v_template"] + (smpl["shapedirs"][..., :shapes.numel()] * shapes.view(1, 1, -1)).sum(-1)
+    rot = axis_angle_matrices(poses.reshape(-1, 3))
+    J = smpl["J_regressor"] @ v_shaped
+    par = smpl["parents"]
+    rel = J.clone()
+    rel[1:] = J[1:] - J[par[1:]]
+    local = torch.zeros(24, 4, 4)
+    local[:, :3, :3] = rot
+    local[:, :3, 3] = rel
+    local[:, 3, 3] = 1
+    chain = [local[0]]
+    for j in range(1, 24):
+        chain.append(chain[par[j]] @ local[j])
+    A = torch.stack(chain)
+    Jh = torch.cat([J, torch.zeros(24, 1)], -1)
+    A[..., 3] = A[..., 3] - (A * Jh[:, None, :]).sum(-1)
+    return A
+
+
+def nearest_vertex(q, v):
+    out = []
+    for s in range(0, q.shape[0], 8192):
+        out.append(((q[s:s + 8192, None, :] - v[None]) ** 2).sum(-1).argmin(-1))
+    return torch.cat(out)
+
+
+def deform_to_canonical(smpl, frame, pts, viewdir=None):
+    """deform_target2c + deform_target2c_op for batch 1: pts [M,3] world -> canonical big-pose space; viewdir [M,3] ->
+    canonical directions (the reference subtracts Th from the *direction* too, renderer.py:125 -- reproduced)."""
+    prm, tprm = frame["params"], frame["t_params"]
+    R, Th = prm["R"][0], prm["Th"][0]
+    poses, shapes = prm["poses"].reshape(-1), prm["shapes"].reshape(-1)
+    q = (pts - Th) @ R
+    qv = (viewdir - Th) @ R if viewdir is not None else None
+    verts = (frame["vertices"][0] - Th) @ R
+    vid = nearest_vertex(q.float(), verts.float())
+    bw = smpl["weights"][vid]                                          # [M,24]
+    A = (bw @ joint_transforms(smpl, poses, shapes).reshape(24, 16)).view(-1, 4, 4)
+    Rinv = torch.inverse(A[:, :3, :3].float())
+    c = (Rinv @ (q - A[:, :3, 3])[..., None])[..., 0]
+    if qv is not None:
+        qv = (Rinv @ qv[..., None])[..., 0]
+    eye = torch.eye(3)
+    pdirs = smpl["posedirs"].reshape(-1, 207).t()                     # [207, V*3]
+    feat = (axis_angle_matrices(poses.view(-1, 3))[1:] - eye).reshape(1, -1)
+    c = c - (feat @ pdirs).view(-1, 3)[vid]
+    c = c - (smpl["shapedirs"][..., :shapes.numel()] @ shapes.view(-1, 1))[..., 0][vid]
+    tposes = tprm["poses"].reshape(-1)
+    tfeat = (axis_angle_matrices(tposes.view(-1, 3))[1:] - eye).reshape(1, -1)
+    c = c + (tfeat @ pdirs).view(-1, 3)[vid]
+    Ab = (bw @ joint_transforms(smpl, tposes, torch.zeros_like(shapes)).reshape(24, 16)).view(-1, 4, 4)
+    c = (Ab[:, :3, :3] @ c[..., None])[..., 0] + Ab[:, :3, 3]
+    if qv is not None:
+        qv = (Ab[:, :3, :3] @ qv[..., None])[..., 0]
+    return c, qv
+
+
 @torch.no_grad()
-def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_depth=True, n=128, n_importance=128):
+def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_depth=True, n=128, n_importance=128,
+                canon=None):
     """tri_planes [3,9,R,R]; bounds [2,3]; rays [N,3]; near/far [N]; u [N,128] -> rgb, acc, depth.
     ``n_importance=0``: the `if n_importance > 0` block of Renderer.render (recon_NeRF/lib/renderer.py:258-270) is
-    skipped and render_core composites the n coarse samples."""
+    skipped and render_core composites the n coarse samples.
+    ``canon=(smpl, frame)``: use_canonical_space=True -- every sample point (and, in render_core, its view direction) goes
+    through deform_to_canonical and ``bounds`` must be the frame's t_world_bounds."""
     N = rays_o.shape[0]
     bmin, bmax = bounds[0], bounds[1]
     t = torch.linspace(0., 1., steps=n)
     z = near[:, None] * (1. - t) + far[:, None] * t
     if n_importance == 0:
-        return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, z, clamp_depth)
-    pts = rays_o[:, None] + rays_d[:, None] * z[..., None]
-    sigma = mlp(sd, plane_features(tri_planes, pts.reshape(-1, 3), bmin, bmax)).reshape(N, n)
+        return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, z, clamp_depth, canon)
+    pts = (rays_o[:, None] + rays_d[:, None] * z[..., None]).reshape(-1, 3)
+    if canon is not None:
+        pts, _ = deform_to_canonical(canon[0], canon[1], pts)
+    sigma = mlp(sd, plane_features(tri_planes, pts, bmin, bmax)).reshape(N, n)
     # up_sample
     dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((N, 1), 1e10)], -1) * rays_d.norm(dim=-1, keepdim=True)
     alpha = 1. - torch.exp(-F.softplus(sigma) * dists)
@@ -83,16 +172,18 @@ def render_rays(sd, tri_planes, bounds, rays_o, rays_d, near, far, u, clamp_dept
     den = torch.where(den < 1e-5, torch.ones_like(den), den)
     z_new = bb + (u - cb) / den * (ba - bb)
     zf, _ = torch.sort(torch.cat([z, z_new], -1), -1)
-    return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth)
+    return _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth, canon)
 
 
-def _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth):
+def _render_core(sd, tri_planes, bmin, bmax, rays_o, rays_d, near, far, zf, clamp_depth, canon=None):
     """render_core (recon_NeRF/lib/renderer.py:180-241) + the depth normalisation of render (:283-286)."""
     N = rays_o.shape[0]
     m = zf.shape[1]
-    pts = rays_o[:, None] + rays_d[:, None] * zf[..., None]
+    pts = (rays_o[:, None] + rays_d[:, None] * zf[..., None]).reshape(-1, 3)
     vd = (rays_d / rays_d.norm(dim=-1, keepdim=True))[:, None].expand(N, m, 3).reshape(-1, 3)
-    rgb_raw, sigma = mlp(sd, plane_features(tri_planes, pts.reshape(-1, 3), bmin, bmax), vd)
+    if canon is not None:
+        pts, vd = deform_to_canonical(canon[0], canon[1], pts, vd)
+    rgb_raw, sigma = mlp(sd, plane_features(tri_planes, pts, bmin, bmax), vd)
     sigma = sigma.reshape(N, m)
     d2 = torch.cat([zf[:, 1:] - zf[:, :-1], torch.full((N, 1), 1e10)], -1)      # not scaled by |d|
     alpha = 1. - torch.exp(-F.softplus(sigma) * d2)

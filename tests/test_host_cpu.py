@@ -56,7 +56,7 @@ def test_flag_envelope_raises_cleanly():
             factory.create_model_and_diffusion(**dict(flags, image_size=32, num_channels=64, **bad))
     from humanliff_b200.renderer import Renderer
     with pytest.raises(NotImplementedError):
-        Renderer(use_canonical_space=True, triplane_ch=27)
+        Renderer(triplane_ch=18, test=True)
 
 
 def test_shard_batch():
@@ -248,3 +248,27 @@ def test_reference_staging_recipe(tmp_path):
     with open(os.path.join(dest, "human_diffusion/improved_diffusion/nn.py"), "a") as f:
         f.write("# edited\n")
     assert not build_ref.verify(dest)            # a modified copy is detected
+
+
+def test_smpl_joint_chain_matches_oracle_and_asset_is_required():
+    """Host half of the canonical-space path (humanliff_b200/smpl.py): the float64 joint chain against the oracle's fp32
+    restatement of get_transform_params_torch (itself pinned to the reference by the render_canon_384 golden); the
+    constant block has the layout the header states; without an asset the constructor fails the way the reference's
+    open() does."""
+    import numpy as np
+    from humanliff_b200 import _lib, synth
+    from humanliff_b200.renderer import Renderer
+    from humanliff_b200.smpl import SmplModel
+    from oracle import render_oracle
+    asset = synth.synth_smpl(5)
+    m = SmplModel(asset)
+    tp = synth.synth_canonical_frame(asset, 21)
+    A, _ = m.joint_transforms(tp["params"]["poses"].reshape(-1).numpy(), tp["params"]["shapes"].reshape(-1).numpy())
+    ref = render_oracle.joint_transforms(render_oracle.smpl_tensors(asset), tp["params"]["poses"].reshape(-1),
+                                         tp["params"]["shapes"].reshape(-1))
+    assert np.abs(A - ref.double().numpy()).max() < 2e-6
+    c, nb, R, Th = m.frame_constants(tp["params"], tp["t_params"])
+    assert c.size == _lib.smpl_consts(24) == 1018 and nb == 10 and c.dtype == np.float64
+    assert np.allclose(c[:12].reshape(3, 4), A[0, :3]) and np.allclose(c[-3:], Th) and np.allclose(c[-12:-3], R.reshape(-1))
+    with pytest.raises(FileNotFoundError):
+        Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl_path="/nonexistent/SMPL_NEUTRAL.pkl")

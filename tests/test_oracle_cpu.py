@@ -196,3 +196,26 @@ def test_render_oracle_n_importance_zero_matches_reference_golden():
                                     g["rays_o"][:n], g["rays_d"][:n], g["near"][:n], g["far"][:n], None, n_importance=0)
     for name, a, b in zip(("rgb", "acc", "depth"), out, (gz["rgb"], gz["acc"], gz["depth"])):
         assert rel_l2(a, b) < 2e-6, (name, rel_l2(a, b))
+
+
+def test_render_oracle_canonical_space_matches_reference_golden():
+    """use_canonical_space=True (human_diffusion/NeRF/renderer.py:52-133): the oracle's deformation + render vs the
+    unmodified reference on the seeded SMPL-shaped asset (golden render_canon_384: per-point canonical positions /
+    directions of 1024 coarse points, and the rendered maps)."""
+    gz = load_golden("render_canon_384.npz")
+    asset = synth.synth_smpl(int(gz["seed_smpl"]))
+    smpl = render_oracle.smpl_tensors(asset)
+    tp = synth.synth_canonical_frame(asset, int(gz["seed_pose"]))
+    n = int(gz["n_rays"])
+    ro, rd, near, far, u = synth.synth_canonical_rays(tp, n)
+    t = torch.linspace(0., 1., steps=128)
+    z = near[:8, None] * (1. - t) + far[:8, None] * t
+    pts = (ro[:8, None] + rd[:8, None] * z[..., None]).reshape(-1, 3)
+    vd = (rd / rd.norm(dim=-1, keepdim=True))[:8, None].expand(8, 128, 3).reshape(-1, 3)
+    c, cd = render_oracle.deform_to_canonical(smpl, tp, pts, vd)
+    assert rel_max(c, gz["canonical_pts"]) < 2e-6 and rel_max(cd, gz["canonical_dirs"]) < 2e-6
+    _, sd = renderer_state_dict(int(gz["seed_w"]))
+    out = render_oracle.render_rays(sd, synth.synth_triplane(256, seed=7)[0], tp["t_world_bounds"][0], ro, rd, near, far,
+                                    u, canon=(smpl, tp))
+    for name, a, b in zip(("rgb", "acc", "depth"), out, (gz["rgb"], gz["acc"], gz["depth"])):
+        assert rel_l2(a, b) < 2e-6, (name, rel_l2(a, b))

@@ -192,3 +192,94 @@ def test_density_grid_vs_reference_golden():
     assert u.shape == (res, res, res)
     assert rel_l2(u, gd["u"]) < 1e-3, rel_l2(u, gd["u"])
     assert rel_max(u, gd["u"]) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# use_canonical_space=True (the TightCap branch of triplane_sample_layered.py:73-76)
+def _canon_setup():
+    from humanliff_b200.renderer import Renderer
+    gz = load_golden("render_canon_384.npz")
+    asset = synth.synth_smpl(int(gz["seed_smpl"]))
+    r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    sd = synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5)
+    r.load_state_dict(sd, strict=False)
+    tp = synth.synth_canonical_frame(asset, int(gz["seed_pose"]))
+    return r.to("cuda:0"), sd, gz, asset, tp
+
+
+def _to_dev(tp, dev):
+    mv = lambda v: {k: mv(x) for k, x in v.items()} if isinstance(v, dict) else v.to(dev)
+    return mv(tp)
+
+
+def test_canonical_deformation_vs_reference_golden():
+    """Renderer.deform_target2c (hl_smpl_vertex_tables + hl_canonical_points) against the per-point canonical positions
+    and directions the unmodified reference computed for 1024 coarse points; then 200k random points in the posed box
+    against the oracle: the nearest vertex is discontinuous, so a point within rounding of a cell boundary may pick the
+    other vertex -- those are counted (must be < 1e-4 of the points) and the rest must agree to 2e-5 of the box size."""
+    from oracle import render_oracle
+    r, _, gz, asset, tp = _canon_setup()
+    dev = torch.device("cuda:0")
+    n = int(gz["n_rays"])
+    ro, rd, near, far, _ = synth.synth_canonical_rays(tp, n)
+    t = torch.linspace(0., 1., steps=128)
+    z = near[:8, None] * (1. - t) + far[:8, None] * t
+    pts = (ro[:8, None] + rd[:8, None] * z[..., None]).reshape(1, -1, 3)
+    vd = (rd / rd.norm(dim=-1, keepdim=True))[:8, None].expand(8, 128, 3).reshape(1, -1, 3)
+    c, cd, box = r.deform_target2c(_to_dev(tp, dev), pts.to(dev), vd.to(dev))
+    assert torch.equal(box.cpu(), tp["t_world_bounds"])
+    ep = (c[0].cpu() - gz["canonical_pts"]).abs().max(-1).values
+    ed = (cd[0].cpu() - gz["canonical_dirs"]).abs().max(-1).values
+    assert int((ep > 2e-5).sum()) == 0 and int((ed > 2e-5).sum()) == 0, (float(ep.max()), float(ed.max()))
+    # bulk check vs the oracle
+    g = torch.Generator(); g.manual_seed(4)
+    wb = tp["world_bounds"][0]
+    P = wb[0] + (wb[1] - wb[0]) * torch.rand(200_000, 3, generator=g)
+    c2, _, _ = r.deform_target2c(_to_dev(tp, dev), P[None].to(dev))
+    ref, _ = render_oracle.deform_to_canonical(render_oracle.smpl_tensors(asset), tp, P)
+    err = (c2[0].cpu() - ref).abs().max(-1).values
+    flips = int((err > 4e-5).sum())
+    assert flips < 20, (flips, float(err.max()))
+
+
+def test_canonical_render_vs_reference_golden():
+    """Rendered maps of 384 rays with every sample deformed to the canonical space (golden: the unmodified
+    human_diffusion/NeRF/renderer.py with use_canonical_space=True on the seeded SMPL-shaped asset), through the
+    reference-shaped Renderer.render and the script-level render()."""
+    from humanliff_b200.renderer import render as script_render
+    r, _, gz, asset, tp = _canon_setup()
+    dev = torch.device("cuda:0")
+    n = int(gz["n_rays"])
+    ro, rd, near, far, u = synth.synth_canonical_rays(tp, n)
+    t = torch.linspace(0., 1., steps=128)
+    z = near[None, :, None] * (1. - t) + far[None, :, None] * t
+    tpd = _to_dev(tp, dev)
+    out = r.render(tpd, None, z.to(dev), ro[None].to(dev), rd[None].to(dev), near[None, :, None].to(dev),
+                   far[None, :, None].to(dev), synth.synth_triplane(256, seed=7).to(dev), 128, False, u=u.to(dev))
+    for name, key in (("rgb", "rgb_map"), ("acc", "acc_map"), ("depth", "depth_map")):
+        e = rel_l2(out[key][0], gz[name])
+        assert e < 2e-4, f"{name}: rel-L2 {e:.3e} max {rel_max(out[key][0], gz[name]):.3e}"
+    lst = script_render(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
+                        tri_planes=synth.synth_triplane(256, seed=7).to(dev), tp_input=tpd, renderer=r, n_samples=128,
+                        n_importance=128, u=u.to(dev))
+    assert rel_l2(lst[0][0], gz["rgb"]) < 2e-4 and rel_l2(lst[3][0], gz["depth"]) < 2e-4
+
+
+def test_canonical_density_grid_vs_oracle():
+    """extract_geometry's field with use_canonical_space=True (renderer.py:290-318): grid points of the posed box are
+    deformed, then looked up inside t_world_bounds."""
+    from oracle import render_oracle
+    r, sd, gz, asset, tp = _canon_setup()
+    dev = torch.device("cuda:0")
+    res = 20
+    planes = synth.synth_triplane(256, seed=7)
+    got = r.density_grid(_to_dev(tp, dev), planes.to(dev), resolution=res).cpu()
+    wb = tp["world_bounds"][0]
+    ax = [torch.linspace(float(wb[0, i]), float(wb[1, i]), res) for i in range(3)]
+    P = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    c, _ = render_oracle.deform_to_canonical(render_oracle.smpl_tensors(asset), tp, P)
+    tb = tp["t_world_bounds"][0]
+    want = -render_oracle.mlp(sd, render_oracle.plane_features(planes[0], c, tb[0], tb[1])).reshape(res, res, res)
+    bad = ((got - want).abs() > 1e-3 * want.abs().max()).sum()
+    assert int(bad) <= 2, (int(bad), rel_l2(got, want))

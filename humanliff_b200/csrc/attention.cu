@@ -160,11 +160,10 @@ int launch(const float *qkv, int ldq, void *out, int out_dtype, int ldo, int B, 
            int round_tf32, cudaStream_t stream) {
     constexpr int LD = CH + 4;
     size_t smem = sizeof(float) * (size_t)(3 * 64 * LD + 64 * 65 + 3 * 64);
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_attention<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-        configured = true;
     }
     dim3 grid(hl_cdiv(T, TQ), heads, B);
     float scale = 1.0f / sqrtf((float)CH);
@@ -377,10 +376,9 @@ template <int CH, bool F16IN>
 int launch_mma_t(const void *qkv, int ldq, __half *out, int ldo, int B, int T, int heads, cudaStream_t stream) {
     constexpr int PITCH = CH * 2 + 16;
     size_t smem = (size_t)(F16IN ? 5 : 3) * 64 * PITCH;
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_attention_mma<CH, F16IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     dim3 grid(hl_cdiv(T, 64), heads, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)CH);

@@ -37,6 +37,20 @@ void hl_set_error(const char *fmt, ...);
         }                                                                          \
     } while (0)
 
+// cudaFuncSetAttribute (opt-in dynamic shared memory) is per device: `static HlPerDeviceOnce once; if (once.need()) ...`
+// runs the configuration once for every device ordinal a process launches on.
+struct HlPerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 static inline int hl_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // cvt.rna.tf32.f32 : round-to-nearest, ties away -- the operand format of tcgen05 kind::tf32.

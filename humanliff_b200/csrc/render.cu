@@ -725,10 +725,9 @@ extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packe
     fill_render_args(a, texels, R, mlp_packed, rays_o, rays_d, near, far, z_coarse, u, seed, bounds, rgb, acc, depth,
                      n_rays, clamp_depth);
     const size_t smem = render_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     int64_t grid = hl_num_sms();
     if (grid > n_rays) grid = n_rays;
@@ -776,10 +775,9 @@ extern "C" int hl_render_rays_canon(const float *texels, int R, const float *mlp
                      n_rays, clamp_depth);
     set_canon(a, knn_table, affine_table, n_verts, rot, trans);
     const size_t smem = render_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     int64_t grid = hl_num_sms();
     if (grid > n_rays) grid = n_rays;
@@ -797,11 +795,10 @@ extern "C" int hl_canonical_points(const float *pts, const float *dirs, int64_t 
     RenderArgs a = {};
     set_canon(a, knn_table, affine_table, n_verts, rot, trans);
     const size_t smem = sizeof(float) * ((size_t)a.V4 * 12 + 512 + 3 * LDP);
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_canon_points, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(sizeof(float) * ((size_t)HL_SMPL_MAX_VERTS * 3 + 512 + 3 * LDP))));
-        configured = true;
     }
     int64_t grid = (n + 127) / 128;
     if (grid > 2 * hl_num_sms()) grid = 2 * hl_num_sms();
@@ -825,10 +822,9 @@ extern "C" int hl_density_grid_canon(const float *texels, int R, const float *ml
     for (int i = 0; i < 3; ++i) { a.bmin[i] = t_bounds[i]; a.bmax[i] = t_bounds[3 + i]; }
     set_canon(a, knn_table, affine_table, n_verts, rot, trans);
     const size_t smem = sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + 2 * NS + 512);
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_density_grid_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const long long tiles = ((long long)resolution * resolution * resolution + 127) / 128;
     long long grid = hl_num_sms();

@@ -604,10 +604,9 @@ extern "C" int hl_density_grid_tc(const float *texels, int R, const float *mlp_p
     a.w16 = reinterpret_cast<const __half *>(mlp_f16);
     for (int i = 0; i < 3; ++i) { a.bmin[i] = bounds[i]; a.bmax[i] = bounds[3 + i]; }
     const size_t smem = (size_t)W_HALVES * 2 + sizeof(float) * FB_FLOATS + (size_t)128 * XP * 2 + sizeof(float) * 128;
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_density_grid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const long long tiles = ((long long)resolution * resolution * resolution + 127) / 128;
     long long grid = hl_num_sms();
@@ -645,10 +644,9 @@ extern "C" int hl_render_rays_tc(const float *texels, int R, const float *mlp_pa
     a.prof = g_render_prof;
     const size_t smem = (size_t)W_HALVES * 2 + sizeof(float) * FB_FLOATS + (size_t)256 * XP * 2 +
                         sizeof(float) * (size_t)(NS * 2 + 2 * NS * 3 + NS * 2 + 3 * 2 * NS + 64 + NS + 8 + 28 + 4);
-    static bool configured = false;
-    if (!configured) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     int64_t grid = hl_num_sms();
     if (grid > n_rays) grid = n_rays;

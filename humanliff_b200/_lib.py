@@ -58,11 +58,13 @@ SIGNATURES = {
     "hl_triplane_to_texels": (c_int, [c_p, c_p, c_int, c_p]),
     "hl_render_rays": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_p,
                                c_i64, c_int, c_p]),
-    "hl_smpl_vertex_tables": (c_int, [c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_p, c_p]),
-    "hl_render_rays_canon": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_int, c_p, c_p,
-                                     c_p, c_p, c_p, c_i64, c_int, c_p]),
-    "hl_canonical_points": (c_int, [c_p, c_p, c_i64, c_p, c_p, c_int, c_p, c_p, c_p, c_p, c_p]),
-    "hl_density_grid_canon": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_p]),
+    "hl_smpl_vertex_tables": (c_int, [c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_int, c_int, c_p, c_int, c_int, c_p, c_p, c_p]),
+    "hl_render_rays_canon": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_int, c_int,
+                                     c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_p]),
+    "hl_render_rays_tc5_canon": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_p, c_p, c_int, c_int,
+                                         c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_int, c_p]),
+    "hl_canonical_points": (c_int, [c_p, c_p, c_i64, c_p, c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
+    "hl_density_grid_canon": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_int, c_p, c_p]),
     "hl_render_set_profile": (c_int, [c_p]),
     "hl_density_grid_tc": (c_int, [c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p]),
     "hl_render_rays_tc5": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_u64, c_p, c_int, c_p, c_p, c_p,
@@ -101,7 +103,7 @@ MLP16_WF = MLP16_W2 + 128 * 168
 MLP16_WV = MLP16_WF + 128 * 136
 MLP16_HALVES = MLP16_WV + 64 * 136
 
-SMPL_MAX_VERTS = 10920
+SMPL_CLUSTERS = 128                                     # spatial clusters of the nearest-vertex search
 smpl_consts = lambda J: 24 * J + 18 * (J - 1) + 28     # HL_SMPL_CONSTS(J)
 
 MLP_TC5_BYTES = 16384 + 32768 + 16384 + 32768 + 32768 + 16384 + 16384 + 8192 + 392 * 4

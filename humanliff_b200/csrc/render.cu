@@ -20,10 +20,10 @@
 // nearest-vertex lookup depends on the vertex only (blend weights, blend-shape offsets and both joint-transform blends
 // are indexed by vert_ids), so k_smpl_vertex_tables folds the whole chain -- inverse skinning, minus pose and shape
 // offsets, plus big-pose offsets, forward skinning -- into one 3x4 affine per vertex (fp64 arithmetic, stored fp32),
-// once per frame.  Per point the render kernel then does: nearest vertex (exact, brute force over the vertex positions
-// staged in the 128 KB of shared memory the MLP activations do not need during the gather; two threads per point,
-// four vertices per 3 x LDS.128) and one affine.
+// once per frame.  Per point the render kernel then does: nearest vertex (exact; cluster bounding spheres prune the scan,
+// canon.cuh; the two threads of a point split the clusters) and one affine.
 #include "common.cuh"
+#include "canon.cuh"
 
 int hl_num_sms();
 
@@ -43,11 +43,7 @@ struct RenderArgs {
     float *rgb, *acc, *depth;
     long long n_rays;
     int clamp_depth;
-    // canonical space (k_render<true> / k_density_canon only)
-    const float4 *knn;      // [V4][3] float4: x, y, z of four SMPL-frame vertices
-    const float4 *aff;      // [V][3] float4: rows of M | c  (canonical = M q + c, canonical direction = M v)
-    int V4;
-    float Rm[9], Th[3];     // params['R'], params['Th']: q = (p - Th) R
+    CanonTables ct;         // canonical space (k_render<true> / k_canon_points / k_density_grid_canon only)
 };
 
 // F.softplus(beta=1, threshold=20).  log1p(exp(x)) = max(x,0) + log(1 + exp(-|x|)).
@@ -108,56 +104,33 @@ __device__ __forceinline__ void zero8x8(float (&acc)[8][8]) {
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 }
 
-// Nearest body vertex of q (knn_points K = 1: fp32 squared distances, strict '<' so the lowest index wins ties) over the
-// vertex groups [g0, g1) staged in shared memory.
-__device__ __forceinline__ void nearest_scan(const float4 *kn, int g0, int g1, float qx, float qy, float qz,
-                                             float &best, int &bi) {
-    best = __int_as_float(0x7f800000);
-    bi = g0 * 4;
-#pragma unroll 2
-    for (int g = g0; g < g1; ++g) {
-        const float4 X = kn[g * 3 + 0], Y = kn[g * 3 + 1], Z = kn[g * 3 + 2];
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float ax = qx - xs[i], ay = qy - ys[i], az = qz - zs[i];
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
-            if (d < best) { best = d; bi = g * 4 + i; }
-        }
-    }
-}
-
-// deform_target2c for the tile's 128 points (two threads per point): world point -> canonical point; optionally the
-// canonical view direction of the sample into vdc[3][128].  `kn_s` = the staged vertex positions (Ha | Hb), `nn_s` =
-// [2][128] (distance, index) exchange.  Ends with every thread holding its point's canonical position.
-__device__ __forceinline__ void canon_tile(const RenderArgs &a, float4 *kn_s, float *nn_s, float &px, float &py,
-                                           float &pz, const float *sv, float *vdc) {
+// deform_target2c for the tile's 128 points (two threads per point, each searching half of the clusters): world point ->
+// canonical point; optionally the canonical view direction of the sample into vdc[3][128].  `nn_s` = [2][256] (distance,
+// index) exchange.  Ends with every thread holding its point's canonical position.
+__device__ __forceinline__ void canon_tile(const RenderArgs &a, float *nn_s, float &px, float &py, float &pz,
+                                           const float *sv, float *vdc) {
+    float4 *sm_f4 = reinterpret_cast<float4 *>(nn_s + 512);      // search scratch follows the exchange area
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
-    for (int i = threadIdx.x; i < a.V4 * 3; i += NT) kn_s[i] = __ldg(a.knn + i);
-    const float ex = px - a.Th[0], ey = py - a.Th[1], ez = pz - a.Th[2];
-    const float qx = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
-    const float qy = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
-    const float qz = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
-    __syncthreads();
-    const int mid = a.V4 >> 1;
+    float qx, qy, qz;
+    hl_to_smpl_frame(a.ct, px, py, pz, qx, qy, qz);
+    const int mid = a.ct.NC >> 1;
     float best;
     int bi;
-    nearest_scan(kn_s, half ? mid : 0, half ? a.V4 : mid, qx, qy, qz, best, bi);
+    hl_nearest_vertex(a.ct, sm_f4, qx, qy, qz, half ? mid : 0, half ? a.ct.NC : mid, best, bi);
     nn_s[half * 256 + p] = best;
     nn_s[half * 256 + 128 + p] = __int_as_float(bi);
     __syncthreads();
     const float d0 = nn_s[p], d1 = nn_s[256 + p];
-    const int v = d1 < d0 ? __float_as_int(nn_s[256 + 128 + p]) : __float_as_int(nn_s[128 + p]);
-    const float4 m0 = __ldg(a.aff + (size_t)v * 3), m1 = __ldg(a.aff + (size_t)v * 3 + 1), m2 = __ldg(a.aff + (size_t)v * 3 + 2);
-    px = fmaf(m0.z, qz, fmaf(m0.y, qy, fmaf(m0.x, qx, m0.w)));
-    py = fmaf(m1.z, qz, fmaf(m1.y, qy, fmaf(m1.x, qx, m1.w)));
-    pz = fmaf(m2.z, qz, fmaf(m2.y, qy, fmaf(m2.x, qx, m2.w)));
+    const int i0 = __float_as_int(nn_s[128 + p]), i1 = __float_as_int(nn_s[256 + 128 + p]);
+    const int v = (d1 < d0 || (d1 == d0 && i1 < i0)) ? i1 : i0;
+    float dc[3];
+    hl_canon_affine(a.ct, v, qx, qy, qz, px, py, pz, sv, vdc ? dc : nullptr);
     if (vdc && half == 0) {
-        vdc[p] = fmaf(m0.z, sv[2], fmaf(m0.y, sv[1], m0.x * sv[0]));
-        vdc[LDP + p] = fmaf(m1.z, sv[2], fmaf(m1.y, sv[1], m1.x * sv[0]));
-        vdc[2 * LDP + p] = fmaf(m2.z, sv[2], fmaf(m2.y, sv[1], m2.x * sv[0]));
+        vdc[p] = dc[0];
+        vdc[LDP + p] = dc[1];
+        vdc[2 * LDP + p] = dc[2];
     }
-    __syncthreads();          // the staged vertices (Ha | Hb) and nn_s may be overwritten from here on
+    __syncthreads();          // nn_s may be overwritten from here on
 }
 
 // Nine-plane gather of one 128-point tile into Xs[27][128]  (renderer.py:504-549; A.5 of SURVEY); thread (p, half) holds
@@ -201,13 +174,12 @@ __device__ __forceinline__ void gather_point(const RenderArgs &a, float px, floa
 template <bool CANON>
 __device__ __forceinline__ void gather_tile(const RenderArgs &a, const float *z_s, float ox, float oy,
                                             float oz, float dx, float dy, float dz, float *Xs,
-                                            float4 *kn_s = nullptr, float *nn_s = nullptr, const float *sv = nullptr,
-                                            float *vdc = nullptr) {
+                                            float *nn_s = nullptr, const float *sv = nullptr, float *vdc = nullptr) {
     const float z = z_s[threadIdx.x & 127];
     float px = __fadd_rn(ox, __fmul_rn(dx, z));
     float py = __fadd_rn(oy, __fmul_rn(dy, z));
     float pz = __fadd_rn(oz, __fmul_rn(dz, z));
-    if (CANON) canon_tile(a, kn_s, nn_s, px, py, pz, sv, vdc);
+    if (CANON) canon_tile(a, nn_s, px, py, pz, sv, vdc);
     gather_point(a, px, py, pz, Xs);
 }
 
@@ -273,9 +245,12 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
     float *part = peb + 64;               // [128] scratch
     float *red = part + NS;               // [8]
     float *pe = red + 8;                  // [28]
-    float *nn = pe + 28 + 4;              // CANON: [2][256] nearest-vertex exchange
-    float *vdc = nn + 512;                // CANON: [3][128] canonical view direction of the tile's samples
-    float4 *kn_s = reinterpret_cast<float4 *>(Ha);   // CANON: vertex positions during the gather (Ha | Hb are free then)
+    float *nn = pe + 28 + 4;              // CANON: [2][256] nearest-vertex exchange | search scratch (canon.cuh)
+    float *vdc = nn + 512 + 4 * HL_CANON_SMEM_F4;   // CANON: [3][128] canonical view direction of the tile's samples
+    if (CANON) {
+        hl_canon_stage_spheres(a.ct, reinterpret_cast<float4 *>(nn + 512));
+        __syncthreads();
+    }
 
     const int tid = threadIdx.x;
     const int pg = tid & 15, og = tid >> 4;
@@ -321,14 +296,11 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
         // CANON: smpl_viewdir = (viewdir - Th) R  (renderer.py:125 subtracts Th from the direction too)
         float sv[3] = {0.f, 0.f, 0.f};
         if (CANON) {
-            const float ex = dx / dnorm - a.Th[0], ey = dy / dnorm - a.Th[1], ez = dz / dnorm - a.Th[2];
-            sv[0] = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
-            sv[1] = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
-            sv[2] = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
+            hl_to_smpl_frame(a.ct, dx / dnorm, dy / dnorm, dz / dnorm, sv[0], sv[1], sv[2]);
         }
 
         // ------------------------------- coarse pass (density only) -------------------------------
-        gather_tile<CANON>(a, zc, ox, oy, oz, dx, dy, dz, Xs, kn_s, nn);
+        gather_tile<CANON>(a, zc, ox, oy, oz, dx, dy, dz, Xs, nn);
         __syncthreads();
         trunk(mlp, Xs, Ha, Hb, pg, og);
         alpha_head(mlp, Ha, part, sig);
@@ -404,7 +376,7 @@ __global__ void __launch_bounds__(NT, 1) k_render(const RenderArgs a) {
 
         // ------------------------------- fine pass: 2 tiles of 128 --------------------------------
         for (int t = 0; t < 2; ++t) {
-            gather_tile<CANON>(a, zf + t * NS, ox, oy, oz, dx, dy, dz, Xs, kn_s, nn, sv, vdc);
+            gather_tile<CANON>(a, zf + t * NS, ox, oy, oz, dx, dy, dz, Xs, nn, sv, vdc);
             __syncthreads();
             trunk(mlp, Xs, Ha, Hb, pg, og);
             alpha_head(mlp, Ha, part, sig + t * NS);
@@ -531,7 +503,7 @@ __global__ void k_triplane_to_texels(const float *__restrict__ planes, float4 *_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Per-frame vertex tables of the canonical-space deformation.  One warp per vertex.
+// Per-frame vertex tables of the canonical-space deformation.  One warp per table slot (cluster order).
 //   consts (device, fp64; J = joints, 24 for SMPL): A_pose [J][12] | A_big [J][12] (rows of the 3x4 joint transforms of
 //   get_transform_params_torch for params and for t_params with zero shape) | pose_feature [9(J-1)] | pose_feature_big
 //   [9(J-1)] (rot_mats[1:] - I, renderer.py:80-83,98-100) | betas [16] | R [9] | Th [3]
@@ -540,20 +512,19 @@ __global__ void k_triplane_to_texels(const float *__restrict__ planes, float4 *_
 //   po = posedirs[v] . pose_feature,  pob = posedirs[v] . pose_feature_big,  so = shapedirs[v] . betas
 //   canonical(q) = Ab_R (A_R^-1 (q - A_t) - po - so + pob) + Ab_t  =  M q + c,   M = Ab_R A_R^-1
 // and the vertex position in the SMPL frame, (vertices[v] - Th) R, for the nearest-vertex search.
-
 __global__ void k_smpl_vertex_tables(const float *__restrict__ weights, const float *__restrict__ posedirs,
                                      const float *__restrict__ shapedirs, int S_asset, int S,
                                      const float *__restrict__ vertices, const double *__restrict__ cst, int V, int J,
-                                     float *__restrict__ knn, float4 *__restrict__ aff) {
+                                     const int *__restrict__ slot_vertex, int n_slots, float4 *__restrict__ verts,
+                                     float4 *__restrict__ aff) {
     const int PF = (J - 1) * 9;           // pose-feature length (207 for SMPL)
     const int SC_APOSE = 0, SC_ABIG = J * 12, SC_PF = 2 * J * 12, SC_PFB = SC_PF + PF, SC_BETAS = SC_PFB + PF,
               SC_R = SC_BETAS + 16, SC_TH = SC_R + 9;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int V4 = (V + 3) >> 2;
-    if (warp >= V4 * 4) return;
-    const int v = warp;
-    if (v >= V) {      // padding slots of the last group: never the nearest
-        if (lane < 3) knn[(size_t)(v >> 2) * 12 + lane * 4 + (v & 3)] = 1e18f;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= n_slots) return;
+    const int v = slot_vertex[slot];
+    if (v < 0 || v >= V) {      // unused slot of its cluster: never the nearest
+        if (lane == 0) verts[slot] = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(0x7fffffff));
         return;
     }
     double po[3] = {0, 0, 0}, pob[3] = {0, 0, 0};
@@ -607,31 +578,50 @@ __global__ void k_smpl_vertex_tables(const float *__restrict__ weights, const fl
     // smpl_pts = (vertices - Th) R in fp32, as the reference computes the search set (renderer.py:61)
     const float ex = vertices[(size_t)v * 3] - (float)cst[SC_TH], ey = vertices[(size_t)v * 3 + 1] - (float)cst[SC_TH + 1],
                 ez = vertices[(size_t)v * 3 + 2] - (float)cst[SC_TH + 2];
+    float q[3];
     for (int c = 0; c < 3; ++c)
-        knn[(size_t)(v >> 2) * 12 + c * 4 + (v & 3)] =
-            fmaf(ez, (float)cst[SC_R + 6 + c], fmaf(ey, (float)cst[SC_R + 3 + c], ex * (float)cst[SC_R + c]));
+        q[c] = fmaf(ez, (float)cst[SC_R + 6 + c], fmaf(ey, (float)cst[SC_R + 3 + c], ex * (float)cst[SC_R + c]));
+    verts[slot] = make_float4(q[0], q[1], q[2], __int_as_float(v));
 }
 
-// deform_target2c on arbitrary points (tests / extract_geometry's canonical branch share it): 128 points per block
-__global__ void __launch_bounds__(NT, 1) k_canon_points(const RenderArgs a, const float *__restrict__ pts,
-                                                        const float *__restrict__ dirs, long long n,
-                                                        float *__restrict__ out_pts, float *__restrict__ out_dirs) {
-    extern __shared__ __align__(16) float sm[];
-    float4 *kn_s = reinterpret_cast<float4 *>(sm);
-    float *nn = sm + (size_t)a.V4 * 12;
-    float *vdc = nn + 512;
+// Bounding sphere of each cluster's posed vertices (one warp per cluster): centre = centroid, radius = the largest
+// distance, rounded up so that the bounds of hl_nearest_vertex stay conservative.
+__global__ void k_smpl_cluster_bounds(const float4 *__restrict__ verts, int NC, int CL, float4 *__restrict__ spheres) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= NC) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f, n = 0.f;
+    for (int k = lane; k < CL; k += 32) {
+        const float4 p = verts[(size_t)c * CL + k];
+        if (p.x < 1e17f) { sx += p.x; sy += p.y; sz += p.z; n += 1.f; }
+    }
+    sx = hl_warp_sum(sx); sy = hl_warp_sum(sy); sz = hl_warp_sum(sz); n = hl_warp_sum(n);
+    const float cx = n > 0.f ? sx / n : 0.f, cy = n > 0.f ? sy / n : 0.f, cz = n > 0.f ? sz / n : 0.f;
+    float r = 0.f;
+    for (int k = lane; k < CL; k += 32) {
+        const float4 p = verts[(size_t)c * CL + k];
+        if (p.x < 1e17f) r = fmaxf(r, sqrtf(hl_dist2(cx, cy, cz, p.x, p.y, p.z)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    // an empty cluster gets a far-away centre: its lower bound never passes, its upper bound never wins
+    if (lane == 0) spheres[c] = n > 0.f ? make_float4(cx, cy, cz, r * (1.0f + 4e-6f) + 1e-7f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+}
+
+// deform_target2c on arbitrary points (tests / Renderer.deform_target2c): 128 points per block, two threads per point
+__global__ void __launch_bounds__(NT) k_canon_points(const RenderArgs a, const float *__restrict__ pts,
+                                                     const float *__restrict__ dirs, long long n,
+                                                     float *__restrict__ out_pts, float *__restrict__ out_dirs) {
+    __shared__ __align__(16) float nn[512 + 4 * HL_CANON_SMEM_F4];
+    __shared__ float vdc[3 * LDP];
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    hl_canon_stage_spheres(a.ct, reinterpret_cast<float4 *>(nn + 512));
+    __syncthreads();
     for (long long base = (long long)blockIdx.x * 128; base < n; base += (long long)gridDim.x * 128) {
         const long long i = base + p < n ? base + p : n - 1;
         float px = pts[i * 3], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
         float sv[3] = {0.f, 0.f, 0.f};
-        if (dirs) {
-            const float ex = dirs[i * 3] - a.Th[0], ey = dirs[i * 3 + 1] - a.Th[1], ez = dirs[i * 3 + 2] - a.Th[2];
-            sv[0] = fmaf(ez, a.Rm[6], fmaf(ey, a.Rm[3], ex * a.Rm[0]));
-            sv[1] = fmaf(ez, a.Rm[7], fmaf(ey, a.Rm[4], ex * a.Rm[1]));
-            sv[2] = fmaf(ez, a.Rm[8], fmaf(ey, a.Rm[5], ex * a.Rm[2]));
-        }
-        canon_tile(a, kn_s, nn, px, py, pz, sv, dirs ? vdc : nullptr);
+        if (dirs) hl_to_smpl_frame(a.ct, dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2], sv[0], sv[1], sv[2]);
+        canon_tile(a, nn, px, py, pz, sv, dirs ? vdc : nullptr);
         if (half == 0 && base + p < n) {
             out_pts[i * 3] = px; out_pts[i * 3 + 1] = py; out_pts[i * 3 + 2] = pz;
             if (dirs) { out_dirs[i * 3] = vdc[p]; out_dirs[i * 3 + 1] = vdc[LDP + p]; out_dirs[i * 3 + 2] = vdc[2 * LDP + p]; }
@@ -651,9 +641,10 @@ __global__ void __launch_bounds__(NT, 1) k_density_grid_canon(const RenderArgs a
     float *Hb = Ha + 128 * LDP;
     float *sig = Hb + 128 * LDP;          // [128]
     float *part = sig + NS;               // [128]
-    float *nn = part + NS;                // [512]
-    float4 *kn_s = reinterpret_cast<float4 *>(Ha);
+    float *nn = part + NS;                // [512] | search scratch
     const int tid = threadIdx.x, pg = tid & 15, og = tid >> 4;
+    hl_canon_stage_spheres(a.ct, reinterpret_cast<float4 *>(nn + 512));
+    __syncthreads();
     const long long total = (long long)res * res * res;
     const long long tiles = (total + 127) / 128;
     // torch.linspace(lo, hi, R): lo + i*step below the midpoint, hi - (R-1-i)*step above (ATen)
@@ -667,7 +658,7 @@ __global__ void __launch_bounds__(NT, 1) k_density_grid_canon(const RenderArgs a
         const int zi = (int)(idx % res), yi = (int)((idx / res) % res), xi = (int)(idx / ((long long)res * res));
         float px = lin(wmin.x, wmax.x, xi), py = lin(wmin.y, wmax.y, yi), pz = lin(wmin.z, wmax.z, zi);
         __syncthreads();     // previous tile consumed
-        canon_tile(a, kn_s, nn, px, py, pz, nullptr, nullptr);
+        canon_tile(a, nn, px, py, pz, nullptr, nullptr);
         gather_point(a, px, py, pz, Xs);
         __syncthreads();
         trunk(a.mlp, Xs, Ha, Hb, pg, og);
@@ -692,13 +683,14 @@ extern "C" int hl_triplane_to_texels(const float *planes, float *texels, int R, 
 
 static size_t render_smem_bytes() {
     return sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + NS * 2 + 2 * NS * 3 + NS * 2 + 3 * 2 * NS + 64 + NS + 8 +
-                                    28 + 4 + 512 + 3 * LDP);
+                                    28 + 4 + 512 + 4 * HL_CANON_SMEM_F4 + 3 * LDP);
 }
 
-static int fill_render_args(RenderArgs &a, const float *texels, int R, const float *mlp_packed, const float *rays_o,
-                            const float *rays_d, const float *near, const float *far, const float *z_coarse,
-                            const float *u, uint64_t seed, const float *bounds, float *rgb, float *acc, float *depth,
-                            int64_t n_rays, int clamp_depth) {
+static void fill_render_args(RenderArgs &a, const float *texels, int R, const float *mlp_packed, const float *rays_o,
+                             const float *rays_d, const float *near, const float *far, const float *z_coarse,
+                             const float *u, uint64_t seed, const float *bounds, float *rgb, float *acc, float *depth,
+                             int64_t n_rays, int clamp_depth) {
+    a = RenderArgs{};
     a.tex = reinterpret_cast<const float4 *>(texels);
     a.R = R;
     a.mlp = mlp_packed;
@@ -708,10 +700,6 @@ static int fill_render_args(RenderArgs &a, const float *texels, int R, const flo
     a.rgb = rgb; a.acc = acc; a.depth = depth;
     a.n_rays = n_rays;
     a.clamp_depth = clamp_depth;
-    a.knn = nullptr; a.aff = nullptr; a.V4 = 0;
-    for (int i = 0; i < 9; ++i) a.Rm[i] = (i % 4 == 0) ? 1.f : 0.f;
-    a.Th[0] = a.Th[1] = a.Th[2] = 0.f;
-    return HL_OK;
 }
 
 extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packed, const float *rays_o,
@@ -738,42 +726,54 @@ extern "C" int hl_render_rays(const float *texels, int R, const float *mlp_packe
 
 extern "C" int hl_smpl_vertex_tables(const float *weights, const float *posedirs, const float *shapedirs, int n_betas_asset,
                                      int n_betas, const float *vertices, const double *consts, int n_verts, int n_joints,
-                                     float *knn_table, float *affine_table, void *stream) {
-    HL_CHECK_ARG(n_joints >= 2 && n_joints <= 64);
-    HL_CHECK_ARG(weights && posedirs && shapedirs && vertices && consts && knn_table && affine_table);
-    HL_CHECK_ARG(n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS && n_betas >= 0 && n_betas <= 16 && n_betas <= n_betas_asset);
+                                     const int *slot_vertex, int n_clusters, int cluster_slots, float *knn_table,
+                                     float *affine_table, void *stream) {
+    HL_CHECK_ARG(weights && posedirs && shapedirs && vertices && consts && slot_vertex && knn_table && affine_table);
+    HL_CHECK_ARG(n_verts > 0 && n_betas >= 0 && n_betas <= 16 && n_betas <= n_betas_asset);
+    HL_CHECK_ARG(n_joints >= 2 && n_joints <= 64 && n_clusters >= 2 && n_clusters <= 128 && cluster_slots >= 1);
+    HL_CHECK_ARG((int64_t)n_clusters * cluster_slots >= n_verts);
     HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
-    const int slots = (n_verts + 3) / 4 * 4;
-    k_smpl_vertex_tables<<<hl_cdiv((int64_t)slots * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        weights, posedirs, shapedirs, n_betas_asset, n_betas, vertices, consts, n_verts, n_joints, knn_table,
-        reinterpret_cast<float4 *>(affine_table));
+    const int n_slots = n_clusters * cluster_slots;
+    float4 *spheres = reinterpret_cast<float4 *>(knn_table);
+    float4 *verts = spheres + n_clusters;
+    k_smpl_vertex_tables<<<hl_cdiv((int64_t)n_slots * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        weights, posedirs, shapedirs, n_betas_asset, n_betas, vertices, consts, n_verts, n_joints, slot_vertex, n_slots,
+        verts, reinterpret_cast<float4 *>(affine_table));
+    HL_CHECK_LAUNCH();
+    k_smpl_cluster_bounds<<<hl_cdiv((int64_t)n_clusters * 32, 256), 256, 0, (cudaStream_t)stream>>>(verts, n_clusters,
+                                                                                                 cluster_slots, spheres);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
-static int set_canon(RenderArgs &a, const float *knn_table, const float *affine_table, int n_verts, const float *rot,
-                     const float *trans) {
-    a.knn = reinterpret_cast<const float4 *>(knn_table);
-    a.aff = reinterpret_cast<const float4 *>(affine_table);
-    a.V4 = (n_verts + 3) / 4;
-    for (int i = 0; i < 9; ++i) a.Rm[i] = rot[i];
-    for (int i = 0; i < 3; ++i) a.Th[i] = trans[i];
+// knn_table = [spheres n_clusters | verts n_clusters * cluster_slots] float4 (hl_smpl_vertex_tables)
+int hl_set_canon_tables(CanonTables &t, const float *knn_table, const float *affine_table, int n_clusters, int cluster_slots,
+                        const float *rot, const float *trans) {
+    HL_CHECK_ARG(knn_table && affine_table && rot && trans && n_clusters >= 2 && n_clusters <= HL_CANON_NC_MAX && cluster_slots >= 1 &&
+                 cluster_slots <= HL_CANON_CL_MAX);
+    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+    t.spheres = reinterpret_cast<const float4 *>(knn_table);
+    t.verts = t.spheres + n_clusters;
+    t.aff = reinterpret_cast<const float4 *>(affine_table);
+    t.NC = n_clusters;
+    t.CL = cluster_slots;
+    for (int i = 0; i < 9; ++i) t.Rm[i] = rot[i];
+    for (int i = 0; i < 3; ++i) t.Th[i] = trans[i];
     return HL_OK;
 }
 
 extern "C" int hl_render_rays_canon(const float *texels, int R, const float *mlp_packed, const float *rays_o,
                                     const float *rays_d, const float *near, const float *far, const float *z_coarse,
                                     const float *u, uint64_t seed, const float *t_bounds, const float *knn_table,
-                                    const float *affine_table, int n_verts, const float *rot, const float *trans,
-                                    float *rgb, float *acc, float *depth, int64_t n_rays, int clamp_depth, void *stream) {
+                                    const float *affine_table, int n_clusters, int cluster_slots, const float *rot,
+                                    const float *trans, float *rgb, float *acc, float *depth, int64_t n_rays,
+                                    int clamp_depth, void *stream) {
     HL_CHECK_ARG(texels && mlp_packed && rays_o && rays_d && near && far && t_bounds && rgb && acc && depth);
-    HL_CHECK_ARG(knn_table && affine_table && rot && trans && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
     HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
-    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
     RenderArgs a;
     fill_render_args(a, texels, R, mlp_packed, rays_o, rays_d, near, far, z_coarse, u, seed, t_bounds, rgb, acc, depth,
                      n_rays, clamp_depth);
-    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
+    if (int rc = hl_set_canon_tables(a.ct, knn_table, affine_table, n_clusters, cluster_slots, rot, trans)) return rc;
     const size_t smem = render_smem_bytes();
     static HlPerDeviceOnce once;
     if (once.need()) {
@@ -787,41 +787,31 @@ extern "C" int hl_render_rays_canon(const float *texels, int R, const float *mlp
 }
 
 extern "C" int hl_canonical_points(const float *pts, const float *dirs, int64_t n, const float *knn_table,
-                                   const float *affine_table, int n_verts, const float *rot, const float *trans,
-                                   float *out_pts, float *out_dirs, void *stream) {
-    HL_CHECK_ARG(pts && out_pts && n > 0 && knn_table && affine_table && rot && trans);
-    HL_CHECK_ARG((dirs == nullptr) == (out_dirs == nullptr) && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
-    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
+                                   const float *affine_table, int n_clusters, int cluster_slots, const float *rot,
+                                   const float *trans, float *out_pts, float *out_dirs, void *stream) {
+    HL_CHECK_ARG(pts && out_pts && n > 0 && (dirs == nullptr) == (out_dirs == nullptr));
     RenderArgs a = {};
-    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
-    const size_t smem = sizeof(float) * ((size_t)a.V4 * 12 + 512 + 3 * LDP);
-    static HlPerDeviceOnce once;
-    if (once.need()) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_canon_points, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(float) * ((size_t)HL_SMPL_MAX_VERTS * 3 + 512 + 3 * LDP))));
-    }
+    if (int rc = hl_set_canon_tables(a.ct, knn_table, affine_table, n_clusters, cluster_slots, rot, trans)) return rc;
     int64_t grid = (n + 127) / 128;
-    if (grid > 2 * hl_num_sms()) grid = 2 * hl_num_sms();
-    k_canon_points<<<(int)grid, NT, smem, (cudaStream_t)stream>>>(a, pts, dirs, (long long)n, out_pts, out_dirs);
+    if (grid > 8 * hl_num_sms()) grid = 8 * hl_num_sms();
+    k_canon_points<<<(int)grid, NT, 0, (cudaStream_t)stream>>>(a, pts, dirs, (long long)n, out_pts, out_dirs);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
 
 extern "C" int hl_density_grid_canon(const float *texels, int R, const float *mlp_packed, const float *world_bounds,
                                      const float *t_bounds, const float *knn_table, const float *affine_table,
-                                     int n_verts, const float *rot, const float *trans, int resolution, float *out,
-                                     void *stream) {
-    HL_CHECK_ARG(texels && mlp_packed && world_bounds && t_bounds && knn_table && affine_table && rot && trans && out);
-    HL_CHECK_ARG(R > 0 && resolution >= 2 && n_verts > 0 && n_verts <= HL_SMPL_MAX_VERTS);
+                                     int n_clusters, int cluster_slots, const float *rot, const float *trans,
+                                     int resolution, float *out, void *stream) {
+    HL_CHECK_ARG(texels && mlp_packed && world_bounds && t_bounds && out && R > 0 && resolution >= 2);
     HL_CHECK_ARG(((uintptr_t)texels & 15) == 0 && ((uintptr_t)mlp_packed & 15) == 0);
-    HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
     RenderArgs a = {};
     a.tex = reinterpret_cast<const float4 *>(texels);
     a.R = R;
     a.mlp = mlp_packed;
     for (int i = 0; i < 3; ++i) { a.bmin[i] = t_bounds[i]; a.bmax[i] = t_bounds[3 + i]; }
-    set_canon(a, knn_table, affine_table, n_verts, rot, trans);
-    const size_t smem = sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + 2 * NS + 512);
+    if (int rc = hl_set_canon_tables(a.ct, knn_table, affine_table, n_clusters, cluster_slots, rot, trans)) return rc;
+    const size_t smem = sizeof(float) * (size_t)(28 * LDP + 2 * 128 * LDP + 2 * NS + 512 + 4 * HL_CANON_SMEM_F4);
     static HlPerDeviceOnce once;
     if (once.need()) {
         HL_CHECK_CUDA(cudaFuncSetAttribute(k_density_grid_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -31,6 +31,7 @@
 // A_c 16 (the constant tile).  Operand rounding: fp16 features / activations / weights (and biases), fp32 accumulate.
 #include "common.cuh"
 #include "tc5.cuh"
+#include "canon.cuh"
 
 #include <cuda_fp16.h>
 
@@ -81,6 +82,9 @@ struct Render5Args {
     // density-grid mode
     int grid_res;
     float *grid_out;
+    // canonical space (canon != 0): every sample is deformed before the gather (canon.cuh); `bounds` = t_world_bounds
+    CanonTables ct;
+    int canon;
 };
 
 // softplus in the log2 domain: a = x * log2(e) in, softplus(x) / ln 2 out (MUFU.EX2, FADD, MUFU.LG2, FMNMX, FADD)
@@ -419,7 +423,48 @@ __device__ __forceinline__ float group_sum(const Group &G, float v, int slot) {
     return ((r.x + r.y) + r.z) + r.w;
 }
 
+// Canonical-space mode, one sample per thread: SMPL-frame point q -> nearest vertex -> canonical point; the sample's own
+// canonical view direction M sv goes, positionally encoded, into this thread's row of the constant tile
+// A_c = [1 | pe(d) (27) | 0 (4)] (per ray in the other modes, per sample here: human_diffusion/NeRF/renderer.py:107-110,
+// 155-157).  Out of line: its registers (and the sincos code) stay out of the render loop.
+__device__ __forceinline__ void canon_sample(const float4 *sph_s, float4 *stage, const float4 *__restrict__ verts,
+                                          const float4 *__restrict__ aff, int NC, int CL, float qx, float qy, float qz,
+                                          float svx, float svy, float svz, uint32_t tm_ac, float *pc) {
+    float best;
+    int v;
+    hl_nearest_vertex_impl(sph_s, verts, stage, NC, CL, qx, qy, qz, 0, NC, best, v);
+    const float4 m0 = __ldg(aff + (size_t)v * 3), m1 = __ldg(aff + (size_t)v * 3 + 1), m2 = __ldg(aff + (size_t)v * 3 + 2);
+    pc[0] = fmaf(m0.z, qz, fmaf(m0.y, qy, fmaf(m0.x, qx, m0.w)));
+    pc[1] = fmaf(m1.z, qz, fmaf(m1.y, qy, fmaf(m1.x, qx, m1.w)));
+    pc[2] = fmaf(m2.z, qz, fmaf(m2.y, qy, fmaf(m2.x, qx, m2.w)));
+    const float dd[3] = {fmaf(m0.z, svz, fmaf(m0.y, svy, m0.x * svx)), fmaf(m1.z, svz, fmaf(m1.y, svy, m1.x * svx)),
+                         fmaf(m2.z, svz, fmaf(m2.y, svy, m2.x * svx))};
+    float h[32];
+    h[0] = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float val;
+        if (k < 3) {
+            val = dd[k];
+        } else {
+            const int f = (k - 3) / 3, comp = (k - 3) % 3;
+            const float freq = (float)(1 << (f >> 1));
+            const float phase = (f & 1) ? 1.5707963267948966f : 0.f;
+            val = sinf(__fadd_rn(phase, __fmul_rn(dd[comp], freq)));
+        }
+        h[1 + k] = val;
+    }
+#pragma unroll
+    for (int k = 28; k < 32; ++k) h[k] = 0.f;
+    uint32_t ac[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ac[k] = pack_h2(h[2 * k], h[2 * k + 1]);
+    tmem_st16(tm_ac, ac);
+}
+
 __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
+    // (a template parameter would keep the two modes apart at compile time; ptxas 12.9 crashes on that instantiation)
+    const bool CANON = a.canon != 0;
     extern __shared__ __align__(16) uint8_t smraw5[];
     __shared__ __align__(8) uint64_t mbars[2 * GROUPS];      // per group: column half 0 / half 1 of the layer in flight
     __shared__ uint32_t tmem_slot;
@@ -433,6 +478,10 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
         uint4 *dst = reinterpret_cast<uint4 *>(aligned);
         for (int i = tid; i < (W_BYTES + 4 * FB_FLOATS) / 16; i += NT5) dst[i] = __ldg(a.w16s + i);
     }
+    // canonical-space search scratch (only allocated by canon launches): spheres | one staging row per warp
+    float4 *canon_f4 = reinterpret_cast<float4 *>(aligned + W_BYTES + 4 * (FB_FLOATS + GROUPS * SC_FLOATS));
+    float4 *canon_stage = canon_f4 + HL_CANON_NC_MAX + (tid >> 5) * HL_CANON_CL_MAX;
+    if (CANON) hl_canon_stage_spheres(a.ct, canon_f4);
     if (tid < 6) bnd[tid] = a.bounds_dev ? __ldg(a.bounds_dev + tid) : a.bounds[tid];
     if (tid < 32) {
         if (tid == 0) {
@@ -533,7 +582,10 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 sts_f32(pe + tg4, v);
             }
             gbar(G);
-            {   // the constant tile of this ray: [1 | pe(27) | 0(4)] in every row
+            float sv[3] = {0.f, 0.f, 0.f};
+            if (CANON) {   // smpl_viewdir = (viewdir - Th) R  (renderer.py:125 subtracts Th from the direction too)
+                hl_to_smpl_frame(a.ct, dx / dnorm, dy / dnorm, dz / dnorm, sv[0], sv[1], sv[2]);
+            } else {       // the constant tile of this ray: [1 | pe(27) | 0(4)] in every row
                 uint32_t ac[16];
                 float prev = 1.0f;
 #pragma unroll
@@ -554,8 +606,17 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
             // first bit for bit, so the colour branch runs right here on the activations still sitting in tensor
             // memory and the fine pass only evaluates the 128 NEW samples: 10 layer passes per ray instead of 13,
             // two gathers instead of three.
-            gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, zmine)), __fadd_rn(oy, __fmul_rn(dy, zmine)),
-                           __fadd_rn(oz, __fmul_rn(dz, zmine)), G.tm + TM_AX);
+            {
+                float pc[3] = {__fadd_rn(ox, __fmul_rn(dx, zmine)), __fadd_rn(oy, __fmul_rn(dy, zmine)),
+                               __fadd_rn(oz, __fmul_rn(dz, zmine))};
+                if (CANON) {
+                    float qx, qy, qz;
+                    hl_to_smpl_frame(a.ct, pc[0], pc[1], pc[2], qx, qy, qz);
+                    canon_sample(canon_f4, canon_stage, a.ct.verts, a.ct.aff, a.ct.NC, a.ct.CL, qx, qy, qz, sv[0], sv[1], sv[2],
+                                 G.tm + TM_AC, pc);
+                }
+                gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
+            }
             RPROF(1)
             const float4 rc = mlp128(G, true);
             G.phase ^= 1u;
@@ -632,8 +693,17 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 }
                 RPROF(3)
                 // ------------------------------- fine pass: the 128 new samples ----------------------------
-                gather_to_tmem(a.tex, a.R, bnd, __fadd_rn(ox, __fmul_rn(dx, znew)), __fadd_rn(oy, __fmul_rn(dy, znew)),
-                               __fadd_rn(oz, __fmul_rn(dz, znew)), G.tm + TM_AX);
+                {
+                    float pc[3] = {__fadd_rn(ox, __fmul_rn(dx, znew)), __fadd_rn(oy, __fmul_rn(dy, znew)),
+                                   __fadd_rn(oz, __fmul_rn(dz, znew))};
+                    if (CANON) {
+                        float qx, qy, qz;
+                        hl_to_smpl_frame(a.ct, pc[0], pc[1], pc[2], qx, qy, qz);
+                        canon_sample(canon_f4, canon_stage, a.ct.verts, a.ct.aff, a.ct.NC, a.ct.CL, qx, qy, qz, sv[0], sv[1], sv[2],
+                                     G.tm + TM_AC, pc);
+                    }
+                    gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
+                }
                 RPROF(1)
                 const float4 rn = mlp128(G, true);
                 G.phase ^= 1u;
@@ -738,18 +808,17 @@ __global__ void k_triplane_to_quads(const float *__restrict__ planes, uint4 *__r
 
 unsigned long long *g_prof5 = nullptr;
 
-int launch5(Render5Args &a, long long units, cudaStream_t stream) {
-    static bool configured[64] = {};
-    int dev = 0;
-    HL_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM5));
-        configured[dev] = true;
+int launch5(Render5Args &a, long long units, cudaStream_t stream, bool canon = false) {
+    constexpr size_t SMEM5_CANON = SMEM5 + 16 * (size_t)HL_CANON_SMEM_F4;
+    static HlPerDeviceOnce once;
+    if (once.need()) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM5_CANON));
     }
     long long grid = hl_num_sms();
     const long long need = (units + GROUPS - 1) / GROUPS;
     if (grid > need) grid = need;
-    k_render_tc5<<<(int)grid, NT5, SMEM5, stream>>>(a);
+    a.canon = canon ? 1 : 0;
+    k_render_tc5<<<(int)grid, NT5, canon ? SMEM5_CANON : SMEM5, stream>>>(a);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -794,6 +863,34 @@ extern "C" int hl_render_rays_tc5(const void *texels, int R, const void *mlp_tc5
     a.n_importance = n_importance;
     a.prof = g_prof5;
     return launch5(a, n_rays, (cudaStream_t)stream);
+}
+
+int hl_set_canon_tables(CanonTables &t, const float *knn_table, const float *affine_table, int n_clusters, int cluster_slots,
+                        const float *rot, const float *trans);      // render.cu
+
+extern "C" int hl_render_rays_tc5_canon(const void *texels, int R, const void *mlp_tc5, const float *rays_o,
+                                        const float *rays_d, const float *near, const float *far, const float *z_coarse,
+                                        const float *u, uint64_t seed, const float *t_bounds, const float *knn_table,
+                                        const float *affine_table, int n_clusters, int cluster_slots, const float *rot,
+                                        const float *trans, float *rgb, float *acc, float *depth, int64_t n_rays,
+                                        int n_importance, int clamp_depth, void *stream) {
+    HL_CHECK_ARG(texels && mlp_tc5 && rays_o && rays_d && near && far && t_bounds && rgb && acc && depth);
+    HL_CHECK_ARG(R > 0 && n_rays > 0 && ((uintptr_t)texels & 31) == 0 && ((uintptr_t)mlp_tc5 & 15) == 0);
+    HL_CHECK_ARG(n_importance == 0 || n_importance == NS);
+    Render5Args a = {};
+    a.tex = reinterpret_cast<const uint4 *>(texels);
+    a.R = R;
+    a.w16s = reinterpret_cast<const uint4 *>(mlp_tc5);
+    a.o = rays_o; a.d = rays_d; a.near = near; a.far = far; a.u = u; a.zc_in = z_coarse;
+    a.seed = seed;
+    for (int i = 0; i < 6; ++i) a.bounds[i] = t_bounds[i];
+    a.rgb = rgb; a.acc = acc; a.depth = depth;
+    a.n_rays = n_rays;
+    a.clamp_depth = clamp_depth;
+    a.n_importance = n_importance;
+    a.prof = g_prof5;
+    if (int rc = hl_set_canon_tables(a.ct, knn_table, affine_table, n_clusters, cluster_slots, rot, trans)) return rc;
+    return launch5(a, n_rays, (cudaStream_t)stream, true);
 }
 
 extern "C" int hl_density_grid_tc5(const void *texels, int R, const void *mlp_tc5,

@@ -12,9 +12,8 @@ white_bkgd branch is shape-broken).
 
 ``use_canonical_space=True`` (the TightCap branch of triplane_sample_layered.py:73-76; renderer.py:52-133): every sample
 point is deformed to the canonical big-pose space inside the kernel -- nearest SMPL vertex (the reference's pytorch3d
-``knn_points``), then that vertex's skinning affine from a per-frame table (``smpl.py``, ``hl_smpl_vertex_tables``).  This
-mode runs on the exact fp32 kernel (``hl_render_rays_canon``) whatever ``precision`` says: its cost is the nearest-vertex
-search, not the MLP.
+``knn_points``, exact, pruned by cluster bounding spheres), then that vertex's skinning affine from a per-frame table
+(``smpl.py``, ``hl_smpl_vertex_tables``); ``hl_render_rays_tc5_canon`` (``precision="fp16"``) / ``hl_render_rays_canon`` (fp32).
 
 ``precision="fp16"`` (default) runs the decoder MLP on the 5th-generation tensor cores (``hl_render_rays_tc5``:
 tcgen05.mma, fp16 operands, fp32 accumulators and activations in tensor memory, two ray groups per SM);
@@ -236,7 +235,7 @@ class Renderer(nn.Module):
             mlp = self._pack(dev)
             planes = tri_planes.detach().to(dev, torch.float32).contiguous()
             assert planes.shape[0] == 3 and planes.shape[1] == 9 and planes.shape[2] == planes.shape[3]
-            tex = self._quads(planes) if (self.precision == "fp16" and canon is None) else self._texels(planes)
+            tex = self._quads(planes) if self.precision == "fp16" else self._texels(planes)
             n = rays_o.shape[0]
             f = lambda t: t.detach().to(dev, torch.float32).contiguous()
             rays_o, rays_d, near, far = f(rays_o), f(rays_d), f(near).view(-1), f(far).view(-1)
@@ -251,19 +250,23 @@ class Renderer(nn.Module):
             if n_importance not in (0, N_SAMPLES):
                 raise NotImplementedError("the fused kernel implements n_importance == n_samples == 128, or 0")
             if canon is not None:
-                if n_importance == 0:
-                    raise NotImplementedError("canonical space with n_importance=0")
                 barr = (ctypes.c_float * 6)(*[float(v) for v in torch.as_tensor(bounds).reshape(-1).tolist()])
                 rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
                 acc = torch.empty(n, device=dev, dtype=torch.float32)
                 depth = torch.empty(n, device=dev, dtype=torch.float32)
-                call("hl_render_rays_canon", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), rays_o.data_ptr(),
-                     rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
-                     z_coarse.data_ptr() if z_coarse is not None else None, u.data_ptr() if u is not None else None,
-                     int(seed) & ((1 << 64) - 1), ctypes.cast(barr, ctypes.c_void_p), canon["knn"].data_ptr(),
-                     canon["aff"].data_ptr(), canon["n_verts"], ctypes.cast(canon["rot"], ctypes.c_void_p),
-                     ctypes.cast(canon["trans"], ctypes.c_void_p), rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n,
-                     1 if self.clamp_depth else 0, torch.cuda.current_stream(dev).cuda_stream)
+                head = (rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                        z_coarse.data_ptr() if z_coarse is not None else None, u.data_ptr() if u is not None else None,
+                        int(seed) & ((1 << 64) - 1), ctypes.cast(barr, ctypes.c_void_p), *self.smpl.table_args(canon),
+                        rgb.data_ptr(), acc.data_ptr(), depth.data_ptr(), n)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                if self.precision == "fp16":
+                    call("hl_render_rays_tc5_canon", tex.data_ptr(), planes.shape[-1], self._mlp_tc5.data_ptr(), *head,
+                         int(n_importance), 1 if self.clamp_depth else 0, stream)
+                else:
+                    if n_importance == 0:
+                        raise NotImplementedError("n_importance=0 is served by the tcgen05 kernel (precision='fp16')")
+                    call("hl_render_rays_canon", tex.data_ptr(), planes.shape[-1], mlp.data_ptr(), *head,
+                         1 if self.clamp_depth else 0, stream)
                 return rgb, acc, depth
             tc5 = self.precision == "fp16"
             if not tc5 and n_importance == 0:
@@ -315,9 +318,7 @@ class Renderer(nn.Module):
                 op = torch.empty_like(p)
                 od = None if d is None else torch.empty_like(d)
                 call("hl_canonical_points", p.data_ptr(), d.data_ptr() if d is not None else None, p.shape[0],
-                     canon["knn"].data_ptr(), canon["aff"].data_ptr(), canon["n_verts"],
-                     ctypes.cast(canon["rot"], ctypes.c_void_p), ctypes.cast(canon["trans"], ctypes.c_void_p),
-                     op.data_ptr(), od.data_ptr() if od is not None else None,
+                     *self.smpl.table_args(canon), op.data_ptr(), od.data_ptr() if od is not None else None,
                      torch.cuda.current_stream(dev).cuda_stream)
                 outs_p.append(op)
                 outs_d.append(od)
@@ -349,9 +350,8 @@ class Renderer(nn.Module):
                 warr = (ctypes.c_float * 6)(*[float(v) for v in wb.tolist()])
                 tarr = (ctypes.c_float * 6)(*[float(v) for v in tb.tolist()])
                 call("hl_density_grid_canon", self._texels(planes).data_ptr(), planes.shape[-1], mlp.data_ptr(),
-                     ctypes.cast(warr, ctypes.c_void_p), ctypes.cast(tarr, ctypes.c_void_p), canon["knn"].data_ptr(),
-                     canon["aff"].data_ptr(), canon["n_verts"], ctypes.cast(canon["rot"], ctypes.c_void_p),
-                     ctypes.cast(canon["trans"], ctypes.c_void_p), int(resolution), out.data_ptr(), stream)
+                     ctypes.cast(warr, ctypes.c_void_p), ctypes.cast(tarr, ctypes.c_void_p),
+                     *self.smpl.table_args(canon), int(resolution), out.data_ptr(), stream)
                 return out
             if self.precision == "fp16":
                 if wb.is_cuda:

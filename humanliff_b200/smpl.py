@@ -51,6 +51,47 @@ def axis_angle_matrices(rv):
     return np.eye(3)[None] + np.sin(ang)[:, :, None] * K + (1.0 - np.cos(ang))[:, :, None] * (K @ K)
 
 
+def spatial_clusters(points, n_clusters, part=None):
+    """Partition the template vertices into ``n_clusters`` compact groups of near-equal size: vertices are first grouped by
+    body part (``part`` [V]: the joint with the largest skinning weight -- a part moves almost rigidly, whereas template
+    neighbours of different parts, e.g. the two thighs, separate under a pose), every part gets clusters in proportion to
+    its size, and inside a part a k-d split cuts the largest extent at the matching quantile.
+    -> (slot_vertex int32 [n_clusters * slots], slots): the vertex of every table slot in cluster order, -1 = unused.
+    The nearest-vertex search is exact for ANY partition; compact clusters make its bounding-sphere pruning effective."""
+    n = points.shape[0]
+    part = np.zeros(n, dtype=np.int64) if part is None else np.asarray(part)
+    groups = [np.nonzero(part == g)[0] for g in np.unique(part)]
+    # largest-remainder allocation, at least one cluster per part
+    share = np.array([g.size for g in groups], dtype=np.float64) * n_clusters / n
+    k = np.maximum(1, np.floor(share).astype(int))
+    while k.sum() > n_clusters:
+        k[np.argmax(k - share)] -= 1
+    while k.sum() < n_clusters:
+        k[np.argmax(share - k)] += 1
+    leaves = []
+
+    def split(idx, kk):
+        if kk == 1 or idx.size <= 1:
+            leaves.append(idx)
+            for _ in range(kk - 1):
+                leaves.append(idx[:0])
+            return
+        p = points[idx]
+        order = idx[np.argsort(p[:, int(np.argmax(p.max(0) - p.min(0)))], kind="stable")]
+        k1 = kk // 2
+        cut = int(round(order.size * k1 / kk))
+        split(order[:cut], k1)
+        split(order[cut:], kk - k1)
+
+    for g, kk in zip(groups, k):
+        split(g, int(kk))
+    slots = max(4, (max(l.size for l in leaves) + 3) // 4 * 4)
+    table = np.full((n_clusters, slots), -1, dtype=np.int32)
+    for c, idx in enumerate(leaves):
+        table[c, : idx.size] = np.sort(idx)
+    return table.reshape(-1), slots
+
+
 class SmplModel:
     """The asset's tables: fp32 on the device for the per-vertex kernel, float64 on the host for the joint chain."""
 
@@ -65,21 +106,23 @@ class SmplModel:
         self.posedirs = _dense(p["posedirs"]).reshape(self.n_verts, 3, -1)
         if self.posedirs.shape[2] != 9 * (self.n_joints - 1):
             raise ValueError(f"posedirs has {self.posedirs.shape[2]} pose features, expected {9 * (self.n_joints - 1)}")
-        if self.n_verts > _lib.SMPL_MAX_VERTS:
-            raise NotImplementedError(f"{self.n_verts} vertices > {_lib.SMPL_MAX_VERTS} (shared-memory staging)")
         jr = _dense(p["J_regressor"])                                   # [J,V]
         self.parents = [int(v) for v in np.asarray(p["kintree_table"])[0][: self.n_joints]]
         # joints = J_regressor (v_template + shapedirs betas) is linear in betas: regress the tables once
         self.j_template = jr @ self.v_template                          # [J,3]
         self.j_shapedirs = np.einsum("jv,vcs->jcs", jr, self.shapedirs)  # [J,3,S]
         self.faces = np.asarray(p["f"]).astype(np.int64) if "f" in p else None
+        self.n_clusters = _lib.SMPL_CLUSTERS
+        self.slot_vertex, self.cluster_slots = spatial_clusters(self.v_template, self.n_clusters,
+                                                                 np.argmax(self.weights, axis=1))
         self._dev = {}
 
     def device_tables(self, device):
         key = str(device)
         if key not in self._dev:
             f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
-            self._dev[key] = (f(self.weights), f(self.posedirs), f(self.shapedirs))
+            self._dev[key] = (f(self.weights), f(self.posedirs), f(self.shapedirs),
+                              torch.from_numpy(self.slot_vertex).to(device))
         return self._dev[key]
 
     def joint_transforms(self, poses, betas):
@@ -119,17 +162,23 @@ class SmplModel:
     def frame_tables(self, tp_input, b, device):
         """-> dict(knn, aff, n_verts, rot, trans): the device tables of one frame + the host constants of the launch."""
         c, n_betas, R, Th = self.frame_constants(tp_input["params"], tp_input["t_params"], b)
-        w, pd, sd = self.device_tables(device)
+        w, pd, sd, slots = self.device_tables(device)
         verts = torch.as_tensor(tp_input["vertices"])[b].detach().to(device, torch.float32).contiguous()
         if verts.shape != (self.n_verts, 3):
             raise ValueError(f"tp_input['vertices'] is {tuple(verts.shape)}, the asset has {self.n_verts} vertices")
         consts = torch.from_numpy(c).to(device)
-        v4 = (self.n_verts + 3) // 4
-        knn = torch.empty(v4 * 12, device=device, dtype=torch.float32)
+        nc, cl = self.n_clusters, self.cluster_slots
+        knn = torch.empty((nc + nc * cl) * 4, device=device, dtype=torch.float32)
         aff = torch.empty(self.n_verts * 12, device=device, dtype=torch.float32)
         call("hl_smpl_vertex_tables", w.data_ptr(), pd.data_ptr(), sd.data_ptr(), self.shapedirs.shape[2], n_betas,
-             verts.data_ptr(), consts.data_ptr(), self.n_verts, self.n_joints, knn.data_ptr(), aff.data_ptr(),
-             torch.cuda.current_stream(device).cuda_stream)
+             verts.data_ptr(), consts.data_ptr(), self.n_verts, self.n_joints, slots.data_ptr(), nc, cl, knn.data_ptr(),
+             aff.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
         rot = (ctypes.c_float * 9)(*[float(v) for v in R.reshape(-1)])
         trans = (ctypes.c_float * 3)(*[float(v) for v in Th])
-        return {"knn": knn, "aff": aff, "n_verts": self.n_verts, "rot": rot, "trans": trans, "_keep": (consts, verts)}
+        return {"knn": knn, "aff": aff, "n_clusters": nc, "cluster_slots": cl, "rot": rot, "trans": trans,
+                "_keep": (consts, verts)}
+
+    def table_args(self, canon):
+        """The (knn_table, affine_table, n_clusters, cluster_slots, rot, trans) run of the C-ABI calls."""
+        return (canon["knn"].data_ptr(), canon["aff"].data_ptr(), canon["n_clusters"], canon["cluster_slots"],
+                ctypes.cast(canon["rot"], ctypes.c_void_p), ctypes.cast(canon["trans"], ctypes.c_void_p))

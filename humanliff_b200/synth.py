@@ -138,16 +138,23 @@ def synth_smpl(seed=5, n_verts=6890, n_betas=10):
     r = (rad[par[bone]] * (1 - s[:, 0]) + rad[bone] * s[:, 0]) * (0.9 + 0.2 * rs.rand(n_verts))
     v = centre + dirs * r[:, None]
     d2 = ((v[:, None, :] - J[None]) ** 2).sum(-1)                       # [V, 24]
-    w = np.exp(-d2 / (2 * 0.09 ** 2))
-    keep = np.argsort(-w, axis=1)[:, :4]                                 # four joints per vertex, as SMPL
-    mask = np.zeros_like(w)
-    np.put_along_axis(mask, keep, 1.0, axis=1)
-    w = w * mask
-    w /= w.sum(1, keepdims=True)
+    # skinning as on a real body: the segment between joint p = parent(j) and joint j moves with p, blends into j over
+    # its last 30 % and into p's own parent over its first 30 % (at most three joints per vertex, smooth along the limb)
+    smooth = lambda x: np.clip(x, 0.0, 1.0) ** 2 * (3.0 - 2.0 * np.clip(x, 0.0, 1.0))
+    w = np.zeros((n_verts, 24))
+    pj = par[bone]
+    w_child = 0.5 * smooth((s[:, 0] - 0.7) / 0.3)
+    w_grand = np.where(par[pj] >= 0, 0.5 * smooth((0.3 - s[:, 0]) / 0.3), 0.0)
+    rows = np.arange(n_verts)
+    np.add.at(w, (rows, bone), w_child)
+    np.add.at(w, (rows, np.maximum(par[pj], 0)), w_grand)
+    np.add.at(w, (rows, pj), 1.0 - w_child - w_grand)
     jr = np.exp(-d2.T / (2 * 0.05 ** 2)) + 1e-12                         # [24, V]
     jr /= jr.sum(1, keepdims=True)
-    shapedirs = 0.01 * rs.randn(n_verts, 3, n_betas)
-    posedirs = 0.002 * rs.randn(n_verts, 3, 207)
+    # blend shapes are smooth displacement fields on a real body: affine functions of the rest position here
+    hom = np.concatenate([v, np.ones((n_verts, 1))], axis=1)                       # [V, 4]
+    shapedirs = np.einsum("vh,hck->vck", hom, 0.02 * rs.randn(4, 3, n_betas))
+    posedirs = np.einsum("vh,hcf->vcf", hom, 0.004 * rs.randn(4, 3, 207))
     kin = np.stack([np.where(par < 0, 4294967295, par), np.arange(24)]).astype(np.int64)
     faces = rs.randint(0, n_verts, size=(13776, 3)).astype(np.int64)
     return {"v_template": v, "shapedirs": shapedirs, "posedirs": posedirs, "J_regressor": jr, "weights": w,

@@ -335,43 +335,57 @@ int hl_render_rays(const float *texels, int R, const float *mlp_packed, const fl
  *
  * hl_smpl_vertex_tables: once per frame.  Folds everything deform_target2c_op indexes by the nearest vertex -- blended
  * joint transforms of the frame's pose and of the canonical big pose, pose / shape blend-shape offsets -- into one 3x4
- * affine per vertex, and writes the vertex positions in the SMPL frame for the nearest-vertex search.
+ * affine per vertex, and writes the vertex positions in the SMPL frame, grouped into spatial clusters with their
+ * bounding spheres, for the exact nearest-vertex search.
  *   weights [V,J], posedirs [V,3,9(J-1)], shapedirs [V,3,n_betas_asset]: device fp32 tables of the SMPL asset (J = 24
  *   joints for SMPL, 55 for SMPL-X); vertices [V,3]: tp_input['vertices'] (world space, device fp32)
  *   consts: device fp64[HL_SMPL_CONSTS(J)]: A_pose[J][3][4] | A_big[J][3][4] (get_transform_params_torch of params and of
  *           t_params with zero shape, rows of the 4x4) | pose_feature[9(J-1)] | pose_feature_big[9(J-1)] | betas[16] |
  *           R[9] | Th[3]
- *   knn_table: (V+3)/4 groups x 12 floats (x[4] | y[4] | z[4]); affine_table: [V][3][4] floats (rows M | c)          */
-#define HL_SMPL_MAX_VERTS 10920          /* vertex positions are staged in 128 KB of shared memory */
+ *   slot_vertex: device int32 [n_clusters * cluster_slots]: the vertex of every table slot, -1 = unused (clusters are a
+ *           property of the asset: any partition is correct, a spatially compact one is fast)
+ *   knn_table: float4 [n_clusters] bounding spheres {centre, radius} | float4 [n_clusters * cluster_slots] {x, y, z,
+ *           vertex index}; affine_table: [V][3][4] floats (rows M | c)                                              */
 #define HL_SMPL_CONSTS(J) (24 * (J) + 18 * ((J) - 1) + 28)
 int hl_smpl_vertex_tables(const float *weights, const float *posedirs, const float *shapedirs, int n_betas_asset,
                           int n_betas, const float *vertices, const double *consts, int n_verts, int n_joints,
-                          float *knn_table, float *affine_table, void *stream);
+                          const int *slot_vertex, int n_clusters, int cluster_slots, float *knn_table,
+                          float *affine_table, void *stream);
 
 /* hl_render_rays with every sample point (and, in the fine pass, its view direction) deformed to the canonical space:
  * q = (p - trans) rot; nearest vertex of q (exact; lowest index on ties); p_canonical = M q + c; viewdir_canonical =
  * M ((viewdir - trans) rot) (the reference subtracts Th from the direction as well, renderer.py:125).  t_bounds =
- * tp_input['t_world_bounds'] (HOST float[6]); rot = params['R'] row-major (HOST float[9]); trans = params['Th'] (HOST). */
+ * tp_input['t_world_bounds'] (HOST float[6]); rot = params['R'] row-major (HOST float[9]); trans = params['Th'] (HOST).
+ * Exact fp32 MLP on the CUDA cores. */
 int hl_render_rays_canon(const float *texels, int R, const float *mlp_packed, const float *rays_o,
                          const float *rays_d, const float *near, const float *far,
                          const float *z_coarse /*nullable*/, const float *u /*nullable*/, uint64_t seed,
-                         const float *t_bounds /*host*/, const float *knn_table, const float *affine_table, int n_verts,
-                         const float *rot /*host*/, const float *trans /*host*/, float *rgb, float *acc, float *depth,
-                         int64_t n_rays, int clamp_depth, void *stream);
+                         const float *t_bounds /*host*/, const float *knn_table, const float *affine_table,
+                         int n_clusters, int cluster_slots, const float *rot /*host*/, const float *trans /*host*/,
+                         float *rgb, float *acc, float *depth, int64_t n_rays, int clamp_depth, void *stream);
 
-/* deform_target2c on caller-supplied points [n,3] (and optionally directions [n,3]): what extract_geometry's canonical
- * branch (renderer.py:309) and the parity tests use. */
+/* The same on the tcgen05 render kernel (hl_render_rays_tc5: fp16 operands, activations in tensor memory): the sample's
+ * encoded canonical direction is written per thread into its row of the constant tile.  n_importance: 128 or 0. */
+int hl_render_rays_tc5_canon(const void *quads, int R, const void *mlp_tc5, const float *rays_o, const float *rays_d,
+                             const float *near, const float *far, const float *z_coarse /*nullable*/,
+                             const float *u /*nullable*/, uint64_t seed, const float *t_bounds /*host*/,
+                             const float *knn_table, const float *affine_table, int n_clusters, int cluster_slots,
+                             const float *rot /*host*/, const float *trans /*host*/, float *rgb, float *acc, float *depth,
+                             int64_t n_rays, int n_importance, int clamp_depth, void *stream);
+
+/* deform_target2c on caller-supplied points [n,3] (and optionally directions [n,3]): Renderer.deform_target2c and the
+ * parity tests. */
 int hl_canonical_points(const float *pts, const float *dirs /*nullable*/, int64_t n, const float *knn_table,
-                        const float *affine_table, int n_verts, const float *rot /*host*/, const float *trans /*host*/,
-                        float *out_pts, float *out_dirs /*nullable*/, void *stream);
+                        const float *affine_table, int n_clusters, int cluster_slots, const float *rot /*host*/,
+                        const float *trans /*host*/, float *out_pts, float *out_dirs /*nullable*/, void *stream);
 
 /* extract_geometry's field with use_canonical_space=True (human_diffusion/NeRF/renderer.py:290-318): out[xi][yi][zi] =
  * -sigma at linspace(world_bounds)^3, each grid point deformed to the canonical space first and looked up inside
  * t_bounds.  world_bounds / t_bounds / rot / trans: HOST arrays. */
 int hl_density_grid_canon(const float *texels, int R, const float *mlp_packed, const float *world_bounds /*host[6]*/,
                           const float *t_bounds /*host[6]*/, const float *knn_table, const float *affine_table,
-                          int n_verts, const float *rot /*host*/, const float *trans /*host*/, int resolution,
-                          float *out, void *stream);
+                          int n_clusters, int cluster_slots, const float *rot /*host*/, const float *trans /*host*/,
+                          int resolution, float *out, void *stream);
 
 /* Tensor-core variant of hl_render_rays: every 128-point layer of the decoder MLP runs on mma.sync
  * (fp16 operands, fp32 accumulate; activations stay in registers between layers).  mlp_f16 is the fp16

@@ -196,11 +196,11 @@ def test_density_grid_vs_reference_golden():
 
 # ------------------------------------------------------------------------------------------------------------------
 # use_canonical_space=True (the TightCap branch of triplane_sample_layered.py:73-76)
-def _canon_setup():
+def _canon_setup(precision="fp16"):
     from humanliff_b200.renderer import Renderer
     gz = load_golden("render_canon_384.npz")
     asset = synth.synth_smpl(int(gz["seed_smpl"]))
-    r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset)
+    r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset, precision=precision)
     shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
     sd = synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5)
     r.load_state_dict(sd, strict=False)
@@ -243,12 +243,14 @@ def test_canonical_deformation_vs_reference_golden():
     assert flips < 20, (flips, float(err.max()))
 
 
-def test_canonical_render_vs_reference_golden():
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 3e-4)])
+def test_canonical_render_vs_reference_golden(precision, tol):
     """Rendered maps of 384 rays with every sample deformed to the canonical space (golden: the unmodified
     human_diffusion/NeRF/renderer.py with use_canonical_space=True on the seeded SMPL-shaped asset), through the
-    reference-shaped Renderer.render and the script-level render()."""
+    reference-shaped Renderer.render and the script-level render().  fp16 = the tcgen05 kernel (per-sample view encoding
+    in the constant tile), fp32 = the exact CUDA-core kernel."""
     from humanliff_b200.renderer import render as script_render
-    r, _, gz, asset, tp = _canon_setup()
+    r, _, gz, asset, tp = _canon_setup(precision)
     dev = torch.device("cuda:0")
     n = int(gz["n_rays"])
     ro, rd, near, far, u = synth.synth_canonical_rays(tp, n)
@@ -259,18 +261,18 @@ def test_canonical_render_vs_reference_golden():
                    far[None, :, None].to(dev), synth.synth_triplane(256, seed=7).to(dev), 128, False, u=u.to(dev))
     for name, key in (("rgb", "rgb_map"), ("acc", "acc_map"), ("depth", "depth_map")):
         e = rel_l2(out[key][0], gz[name])
-        assert e < 2e-4, f"{name}: rel-L2 {e:.3e} max {rel_max(out[key][0], gz[name]):.3e}"
+        assert e < tol, f"{name}: rel-L2 {e:.3e} max {rel_max(out[key][0], gz[name]):.3e}"
     lst = script_render(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
                         tri_planes=synth.synth_triplane(256, seed=7).to(dev), tp_input=tpd, renderer=r, n_samples=128,
                         n_importance=128, u=u.to(dev))
-    assert rel_l2(lst[0][0], gz["rgb"]) < 2e-4 and rel_l2(lst[3][0], gz["depth"]) < 2e-4
+    assert rel_l2(lst[0][0], gz["rgb"]) < tol and rel_l2(lst[3][0], gz["depth"]) < tol
 
 
 def test_canonical_density_grid_vs_oracle():
     """extract_geometry's field with use_canonical_space=True (renderer.py:290-318): grid points of the posed box are
     deformed, then looked up inside t_world_bounds."""
     from oracle import render_oracle
-    r, sd, gz, asset, tp = _canon_setup()
+    r, sd, gz, asset, tp = _canon_setup("fp32")
     dev = torch.device("cuda:0")
     res = 20
     planes = synth.synth_triplane(256, seed=7)

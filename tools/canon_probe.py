@@ -15,56 +15,49 @@ from humanliff_b200.renderer import Renderer, render  # noqa: E402
 dev = torch.device("cuda:0")
 gz = load_golden("render_canon_384.npz")
 asset = synth.synth_smpl(int(gz["seed_smpl"]))
-r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset)
-shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
-r.load_state_dict(synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5), strict=False)
-r.to(dev)
 tp = synth.synth_canonical_frame(asset, int(gz["seed_pose"]))
 mv = lambda v: {k: mv(x) for k, x in v.items()} if isinstance(v, dict) else v.to(dev)
 tpd = mv(tp)
 planes = synth.synth_triplane(256, seed=7).to(dev)
 n = int(gz["n_rays"])
-ro, rd, near, far, u = synth.synth_canonical_rays(tp, n)
-out = render(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
-             tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128, u=u.to(dev))
-print("parity vs the unmodified reference (384 rays): rgb %.2e  acc %.2e  depth %.2e" %
-      (rel_l2(out[0][0], gz["rgb"]), rel_l2(out[1][0], gz["acc"]), rel_l2(out[3][0], gz["depth"])))
-
-wb = tp["world_bounds"][0].tolist()
-ro, rd, near, far, hit = synth.synth_camera_rays(256, 256, focal=300.0, azimuth_deg=30.0, bounds=wb)
-args = dict(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
-            tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128)
-for _ in range(2):
-    render(**args)
-torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 3
-e0.record()
-for _ in range(reps):
-    render(**args)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-print("256 x 256 frame, canonical space (vertex tables + render, %d rays, %.0f%% hit the box): %.1f ms = %.2f M rays/s"
-      % (ro.shape[0], 100.0 * float(hit.float().mean()), ms, ro.shape[0] / ms / 1e3))
-r2 = Renderer(use_canonical_space=False, triplane_ch=27, test=True, precision="fp32")
-r2.load_state_dict(r.state_dict(), strict=False)
-r2.to(dev)
-args2 = dict(args, renderer=r2, tp_input={"world_bounds": tpd["world_bounds"]})
-for _ in range(2):
-    render(**args2)
-torch.cuda.synchronize()
-e0.record()
-for _ in range(reps):
-    render(**args2)
-e1.record()
-torch.cuda.synchronize()
-ms2 = e0.elapsed_time(e1) / reps
-print("same frame without the deformation, same fp32 kernel: %.1f ms = %.2f M rays/s  (deformation share %.0f%%)"
-      % (ms2, ro.shape[0] / ms2 / 1e3, 100.0 * (ms - ms2) / ms))
-e0.record()
-for _ in range(10):
-    r.smpl.frame_tables(tpd, 0, dev)
-e1.record()
-torch.cuda.synchronize()
-print("per-frame vertex tables (host joint chain + hl_smpl_vertex_tables): %.2f ms" % (e0.elapsed_time(e1) / 10))
+
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for precision in ("fp16", "fp32"):
+    r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset, precision=precision)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc")}
+    r.load_state_dict(synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5), strict=False)
+    r.to(dev)
+    ro, rd, near, far, u = synth.synth_canonical_rays(tp, n)
+    out = render(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
+                 tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128, u=u.to(dev))
+    print("[%s] parity vs the unmodified reference (384 rays): rgb %.2e  acc %.2e  depth %.2e" %
+          (precision, rel_l2(out[0][0], gz["rgb"]), rel_l2(out[1][0], gz["acc"]), rel_l2(out[3][0], gz["depth"])))
+    for HW in (256, 512):
+        wb = tp["world_bounds"][0].tolist()
+        ro, rd, near, far, hit = synth.synth_camera_rays(HW, HW, focal=300.0 * HW / 256, azimuth_deg=30.0, bounds=wb)
+        args = dict(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
+                    tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128)
+        ms = timed(lambda: render(**args))
+        r2 = Renderer(use_canonical_space=False, triplane_ch=27, test=True, precision=precision)
+        r2.load_state_dict(r.state_dict(), strict=False)
+        r2.to(dev)
+        args2 = dict(args, renderer=r2, tp_input={"world_bounds": tpd["world_bounds"]})
+        ms2 = timed(lambda: render(**args2))
+        print("[%s] %d x %d frame (%d rays, %.0f%% hit the box): canonical space %.1f ms = %.2f M rays/s; the same rays "
+              "without the deformation %.1f ms = %.2f M rays/s" % (precision, HW, HW, ro.shape[0],
+              100.0 * float(hit.float().mean()), ms, ro.shape[0] / ms / 1e3, ms2, ro.shape[0] / ms2 / 1e3))
+ms = timed(lambda: r.smpl.frame_tables(tpd, 0, dev), reps=10)
+print("per-frame vertex tables (host joint chain + hl_smpl_vertex_tables): %.2f ms" % ms)

@@ -319,6 +319,10 @@ def render_block(device, peaks, clocks_mhz, cpu=True, reps=3):
     out["e2e"] = {"value": round(n / (ms * 1e-3), 1), "unit": "rays/s", "ms_per_image": round(ms, 3),
                   "h2d_bytes_per_step": sum(t.numel() * 4 for t in h_in), "d2h_bytes_per_step": sum(t.numel() * 4 for t in h_out),
                   "api": "humanliff_b200.render(...) (script-level helper of run_nerf_batch.py:29-67), pinned host buffers"}
+    try:
+        out["canonical_space"] = canonical_render_block(device, reps=reps)
+    except Exception as e:           # noqa: BLE001 -- a sub-measurement must not take the headline line down
+        out["canonical_space"] = {"error": repr(e)[:200]}
     if cpu:
         threads = os.cpu_count() or 1
         cr = CpuRender(threads)
@@ -327,6 +331,41 @@ def render_block(device, peaks, clocks_mhz, cpu=True, reps=3):
                                "sample": "Renderer.render on one 16,384-ray chunk of the same camera (the reference's own "
                                          "chunk size), 1 timed call after 1 warm-up (%.1f s), injected uniforms" % rdt}
     return out
+
+
+def canonical_render_block(device, reps=3):
+    """use_canonical_space=True (the TightCap branch of triplane_sample_layered.py:73-76): a whole 512 x 512 frame with every
+    sample snapped to its nearest of 6,890 body vertices and deformed to the canonical pose, on the seeded SMPL-shaped
+    asset of the parity golden; per-frame vertex tables inside the timed region."""
+    from humanliff_b200 import render as render_api, synth
+    from humanliff_b200.renderer import Renderer
+    asset = synth.synth_smpl(5)
+    r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset)
+    synth.randomize_(r, seed=3, weight_gain=1.5)
+    r = r.to(device)
+    tp = synth.synth_canonical_frame(asset, 21)
+    mv = lambda v: {k: mv(x) for k, x in v.items()} if isinstance(v, dict) else v.to(device)
+    tpd = mv(tp)
+    planes = synth.synth_triplane(256, seed=7).to(device)
+    ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=30.0, bounds=tp["world_bounds"][0].tolist())
+    args = dict(rays_o=ro[None].to(device), rays_d=rd[None].to(device), near=near[None].to(device), far=far[None].to(device),
+                tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128)
+    render_api(**args)
+    torch.cuda.synchronize(device)
+    st = torch.cuda.current_stream(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        render_api(**args)
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    n = ro.shape[0]
+    return {"metric": "rendered rays/sec, canonical space (nearest SMPL vertex + skinning affine per sample)",
+            "value": round(n / (ms * 1e-3), 1), "unit": "rays/s", "ms_per_image": round(ms, 3), "rays": n,
+            "rays_hitting_the_box": round(float(hit.float().mean()), 3), "body_vertices": 6890,
+            "kernel": "k_render_tc5 (canon) + k_smpl_vertex_tables",
+            "asset": "synthetic SMPL-shaped body (humanliff_b200.synth.synth_smpl): the licensed SMPL_NEUTRAL.pkl is not shipped"}
 
 
 def _reference_root():

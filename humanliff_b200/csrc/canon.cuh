@@ -9,9 +9,8 @@
 //   aff     [V][3] float4: rows of M | c -- everything deform_target2c_op gathers per point depends on the nearest vertex
 //           only, so the whole chain is one affine per vertex: canonical = M q + c, canonical direction = M d
 //
-// Nearest vertex (pytorch3d knn_points, K = 1), EXACT: pass 1 bounds the answer by U = min over clusters of
-// (|q - centre| + radius); pass 2 scans only clusters whose lower bound |q - centre| - radius does not exceed the best
-// distance so far.  The distance of a vertex is evaluated with the same fp32 operations in the same order as the
+// Nearest vertex (pytorch3d knn_points, K = 1), EXACT: the cluster with the nearest centre is scanned first; after it only
+// clusters whose lower bound |q - centre| - radius does not exceed the best distance so far can hold the answer.  The distance of a vertex is evaluated with the same fp32 operations in the same order as the
 // brute-force scan, and ties go to the lowest ORIGINAL vertex index, so the result equals the full scan's -- the bounds
 // only skip vertices that cannot win (slack factors make them conservative under rounding).  A warp scans a cluster when
 // any of its lanes needs it (adjacent samples of a ray need the same few clusters): loads stay warp-uniform broadcasts
@@ -42,6 +41,13 @@ __device__ __forceinline__ float hl_dist2(float qx, float qy, float qz, float x,
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
 }
 
+// sqrt.approx (2 ulp): every use below carries a relative slack of 4e-6 or more
+__device__ __forceinline__ float hl_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Shared-memory scratch of the search (float4 units): the NC bounding spheres, staged once per CTA, then one staging row
 // of HL_CANON_CL_MAX vertices per warp (8 warps).  With ~200 KB of a CTA's shared memory holding MLP weights the L1 is
 // too small to keep the 110 KB vertex table, and a warp-uniform load that misses it costs an L2 round trip per vertex:
@@ -49,62 +55,177 @@ __device__ __forceinline__ float hl_dist2(float qx, float qy, float qz, float x,
 constexpr int HL_CANON_NC_MAX = 128, HL_CANON_CL_MAX = 96;
 constexpr int HL_CANON_SMEM_F4 = HL_CANON_NC_MAX + 8 * HL_CANON_CL_MAX;
 
+// all HL_CANON_NC_MAX entries are written (unused ones far away, radius 0: never the arg-min, never a candidate), so the
+// loops over the spheres run a fixed trip count in blocks of four without bounds checks
 __device__ __forceinline__ void hl_canon_stage_spheres(const CanonTables &t, float4 *sm_f4) {
-    for (int i = threadIdx.x; i < t.NC; i += blockDim.x) sm_f4[i] = __ldg(t.spheres + i);
+    for (int i = threadIdx.x; i < HL_CANON_NC_MAX; i += blockDim.x)
+        sm_f4[i] = i < t.NC ? __ldg(t.spheres + i) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
 }
 
-// scan one cluster: the warp copies it into its staging row, then every lane updates its own (best, bi)
-__device__ __forceinline__ void hl_scan_cluster(const float4 *__restrict__ v, float4 *stage, int CL, int lane, float qx,
-                                                float qy, float qz, float &best, int &bi) {
-    for (int k = lane; k < CL; k += 32) stage[k] = __ldg(v + k);
-    __syncwarp();
-#pragma unroll 4
-    for (int k = 0; k < CL; ++k) {
-        const float4 p = stage[k];
-        const float d = hl_dist2(qx, qy, qz, p.x, p.y, p.z);
-        const int idx = __float_as_int(p.w);
-        if (d < best || (d == best && idx < bi)) { best = d; bi = idx; }
+// A cluster in flight: lane l holds slots l, l + 32, l + 64 of the cluster (CL <= 96) in registers.
+struct HlClusterRegs { float4 a, b, c; };
+__device__ __forceinline__ void hl_cluster_load(HlClusterRegs &r, const float4 *__restrict__ v, int CL, int lane) {
+    const float4 pad = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(0x7fffffff));
+    r.a = lane < CL ? __ldg(v + lane) : pad;
+    r.b = lane + 32 < CL ? __ldg(v + lane + 32) : pad;
+    r.c = lane + 64 < CL ? __ldg(v + lane + 64) : pad;
+}
+__device__ __forceinline__ void hl_cluster_store(const HlClusterRegs &r, float4 *stage, int CL, int lane) {
+    if (lane < CL) stage[lane] = r.a;
+    if (lane + 32 < CL) stage[lane + 32] = r.b;
+    if (lane + 64 < CL) stage[lane + 64] = r.c;
+}
+// scan the staged cluster: every lane updates its own (best, bi); branch-free, the loads are warp-uniform broadcasts
+__device__ __forceinline__ void hl_scan_staged(const float4 *stage, int CL, float qx, float qy, float qz, float &best,
+                                               int &bi) {
+    // four vertices at a time (CL is a multiple of 4): four independent distance chains, then ONE comparison of their
+    // minimum against `best` -- after the first cluster almost no group can win, so the serial compare-select chain of a
+    // per-vertex update (which bounded this loop by latency, not by issue) is off the common path
+#pragma unroll 2
+    for (int k = 0; k < CL; k += 4) {
+        const float4 p0 = stage[k], p1 = stage[k + 1], p2 = stage[k + 2], p3 = stage[k + 3];
+        const float d0 = hl_dist2(qx, qy, qz, p0.x, p0.y, p0.z), d1 = hl_dist2(qx, qy, qz, p1.x, p1.y, p1.z);
+        const float d2 = hl_dist2(qx, qy, qz, p2.x, p2.y, p2.z), d3 = hl_dist2(qx, qy, qz, p3.x, p3.y, p3.z);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {
+            const float ds[4] = {d0, d1, d2, d3};
+            const int is[4] = {__float_as_int(p0.w), __float_as_int(p1.w), __float_as_int(p2.w), __float_as_int(p3.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool take = (ds[j] < best) | ((ds[j] == best) & (is[j] < bi));
+                best = take ? ds[j] : best;
+                bi = take ? is[j] : bi;
+            }
+        }
     }
-    __syncwarp();
 }
 
 // Nearest vertex of q.  Must be called by all 32 lanes of a warp; NC <= 128, CL <= HL_CANON_CL_MAX.
-//   pass 1: U = min_c (|q - centre_c| + radius_c) bounds the answer from above, c* = its arg-min;
+//   pass 1: c* = the cluster with the nearest centre; U = |q - centre| + radius of c* bounds the answer from above;
 //   phase A: the warp scans the c* of each of its lanes (usually one or two distinct clusters: adjacent samples of a ray) --
 //            after it `best` is within a cluster diameter of the true minimum, which is what makes phase B selective even
 //            for points metres away from the body (miss rays), where all upper bounds look alike;
-//   phase B: clusters [c0, c1) not scanned yet whose lower bound |q - centre| - radius does not exceed `best`.
+//   phase B: candidate mask = clusters of [c0, c1) not scanned yet whose lower bound |q - centre| - radius does not exceed
+//            `best` for ANY lane (one pipelined pass over the spheres, OR-reduced over the warp); the candidates are then
+//            visited in turn -- re-tested against the current `best`, fetched one ahead into registers while the
+//            previous one is scanned out of shared memory.
 // `sph_s` = the spheres in shared memory, `stage` = this warp's staging row.  Callers that split [c0, c1) between threads
 // combine the parts by (best, bi), smallest first.
 static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, const float4 *__restrict__ verts,
                                                            float4 *stage, int NC, int CL, float qx, float qy, float qz,
-                                                           int c0, int c1, float &best, int &bi) {
-    const int lane = threadIdx.x & 31;
-    float U = 3.0e38f;
-    int cstar = 0;
-#pragma unroll 4
-    for (int c = 0; c < NC; ++c) {
-        const float4 s = sph_s[c];
-        const float ub = sqrtf(hl_dist2(qx, qy, qz, s.x, s.y, s.z)) + s.w;
-        if (ub < U) { U = ub; cstar = c; }
+                                                           int c0, int c1, float &best_out, int &bi_out,
+                                                           unsigned long long *prof = nullptr) {
+    // prof (one thread of a probe run): [0] pass 1, [1] phase A, [2] candidate mask, [3] phase B cycles; [4] clusters
+    // scanned in phase A, [5] candidates, [6] candidates scanned, [7] calls
+    long long tq = prof ? clock64() : 0;
+#define HL_CPROF(slot)                                                         \
+    if (prof) {                                                                \
+        const long long now_ = clock64();                                      \
+        atomicAdd(prof + (slot), (unsigned long long)(now_ - tq));             \
+        tq = now_;                                                             \
     }
+    const int lane = threadIdx.x & 31;
+    float best;            // registers, not the caller's stack slots: the references are written once at the end
+    int bi;
+    // pass 1: c* = the cluster with the nearest centre (any choice is correct; this one needs no square root per cluster)
+    float dmin = 3.0e38f;
+    int cstar = 0;
+#pragma unroll 2
+    for (int c = 0; c < HL_CANON_NC_MAX; c += 4) {
+        const float4 s0 = sph_s[c], s1 = sph_s[c + 1], s2 = sph_s[c + 2], s3 = sph_s[c + 3];
+        const float u0 = hl_dist2(qx, qy, qz, s0.x, s0.y, s0.z), u1 = hl_dist2(qx, qy, qz, s1.x, s1.y, s1.z);
+        const float u2 = hl_dist2(qx, qy, qz, s2.x, s2.y, s2.z), u3 = hl_dist2(qx, qy, qz, s3.x, s3.y, s3.z);
+        const bool b01 = u1 < u0, b23 = u3 < u2;
+        const float m01 = b01 ? u1 : u0, m23 = b23 ? u3 : u2;
+        const int i01 = b01 ? c + 1 : c, i23 = b23 ? c + 3 : c + 2;
+        const bool b = m23 < m01;
+        const float mm = b ? m23 : m01;
+        const int im = b ? i23 : i01;
+        if (mm < dmin) { dmin = mm; cstar = im; }
+    }
+    const float U = hl_sqrt_approx(dmin) + sph_s[cstar].w;
     best = U * U * (1.0f + 8e-6f) + 1e-20f;       // >= the squared distance of the farthest vertex of cluster c*
     bi = 0x7fffffff;
-    uint32_t done[4] = {0u, 0u, 0u, 0u};            // warp-uniform: clusters scanned in phase A
+    HL_CPROF(0)
+    uint32_t done0 = 0u, done1 = 0u, done2 = 0u, done3 = 0u;     // warp-uniform: clusters scanned in phase A
     uint32_t todo = 0xffffffffu;
+    HlClusterRegs regs;
     while (todo) {
         const int c = __shfl_sync(0xffffffffu, cstar, __ffs(todo) - 1);
-        hl_scan_cluster(verts + (size_t)c * CL, stage, CL, lane, qx, qy, qz, best, bi);
-        done[(c >> 5) & 3] |= 1u << (c & 31);
+        hl_cluster_load(regs, verts + (size_t)c * CL, CL, lane);
+        hl_cluster_store(regs, stage, CL, lane);
+        __syncwarp();
+        hl_scan_staged(stage, CL, qx, qy, qz, best, bi);
+        __syncwarp();
+        const uint32_t bit = 1u << (c & 31);
+        if ((c >> 5) == 0) done0 |= bit; else if ((c >> 5) == 1) done1 |= bit; else if ((c >> 5) == 2) done2 |= bit; else done3 |= bit;
         todo &= ~__ballot_sync(0xffffffffu, cstar == c);
+        if (prof) atomicAdd(prof + 4, 1ull);
     }
-    for (int c = c0; c < c1; ++c) {
-        if ((done[(c >> 5) & 3] >> (c & 31)) & 1u) continue;
-        const float4 s = sph_s[c];
-        const float lb = sqrtf(hl_dist2(qx, qy, qz, s.x, s.y, s.z)) * (1.0f - 4e-6f) - s.w;
-        const bool need = lb <= 0.f || lb * lb <= best;
-        if (__any_sync(0xffffffffu, need)) hl_scan_cluster(verts + (size_t)c * CL, stage, CL, lane, qx, qy, qz, best, bi);
+    HL_CPROF(1)
+    // candidate mask: |q - centre| - radius <= sqrt(best)  <=>  |q - centre|^2 <= (sqrt(best) + radius)^2
+    float sb = hl_sqrt_approx(best) * (1.0f + 4e-6f) + 1e-18f;
+    // (compact loops throughout: the render kernels are instruction-cache bound -- ncu: 2.3 warps stalled on instruction
+    // fetch per issued instruction before this function was shrunk -- so nothing here is unrolled beyond a block of four)
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+    for (int w = 0; w < 4; ++w) {
+        uint32_t bits = 0u;
+#pragma unroll 2
+        for (int b = 0; b < 32; b += 4) {
+            const float4 s0 = sph_s[w * 32 + b], s1 = sph_s[w * 32 + b + 1], s2 = sph_s[w * 32 + b + 2], s3 = sph_s[w * 32 + b + 3];
+            const float r0 = sb + s0.w, r1 = sb + s1.w, r2 = sb + s2.w, r3 = sb + s3.w;
+            const uint32_t n0 = hl_dist2(qx, qy, qz, s0.x, s0.y, s0.z) * (1.0f - 8e-6f) <= r0 * r0;
+            const uint32_t n1 = hl_dist2(qx, qy, qz, s1.x, s1.y, s1.z) * (1.0f - 8e-6f) <= r1 * r1;
+            const uint32_t n2 = hl_dist2(qx, qy, qz, s2.x, s2.y, s2.z) * (1.0f - 8e-6f) <= r2 * r2;
+            const uint32_t n3 = hl_dist2(qx, qy, qz, s3.x, s3.y, s3.z) * (1.0f - 8e-6f) <= r3 * r3;
+            bits |= (n0 | (n1 << 1) | (n2 << 2) | (n3 << 3)) << b;
+        }
+        // clusters [c0, c1) only
+        const int lo = c0 - w * 32, hi = c1 - w * 32;
+        const uint32_t range = (hi <= 0 || lo >= 32) ? 0u
+                               : ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u)));
+        bits = __reduce_or_sync(0xffffffffu, bits & range);
+        m[0] = w == 0 ? bits : m[0];
+        m[1] = w == 1 ? bits : m[1];
+        m[2] = w == 2 ? bits : m[2];
+        m[3] = w == 3 ? bits : m[3];
     }
+    m[0] &= ~done0; m[1] &= ~done1; m[2] &= ~done2; m[3] &= ~done3;
+    HL_CPROF(2)
+    if (prof) atomicAdd(prof + 5, (unsigned long long)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3])));
+    // visit the candidates; the next one is in flight while the current one is scanned
+    auto pop = [&]() -> int {          // lowest candidate, or -1
+        int c = -1;
+        if (m[0]) { c = __ffs(m[0]) - 1; m[0] &= m[0] - 1u; }
+        else if (m[1]) { c = 32 + __ffs(m[1]) - 1; m[1] &= m[1] - 1u; }
+        else if (m[2]) { c = 64 + __ffs(m[2]) - 1; m[2] &= m[2] - 1u; }
+        else if (m[3]) { c = 96 + __ffs(m[3]) - 1; m[3] &= m[3] - 1u; }
+        return c;
+    };
+    int cur = pop();
+    if (cur >= 0) hl_cluster_load(regs, verts + (size_t)cur * CL, CL, lane);
+#pragma unroll 1
+    while (cur >= 0) {
+        hl_cluster_store(regs, stage, CL, lane);
+        __syncwarp();
+        const int now = cur;
+        cur = pop();
+        if (cur >= 0) hl_cluster_load(regs, verts + (size_t)cur * CL, CL, lane);
+        const float4 s = sph_s[now];
+        const float reach = sb + s.w;
+        const bool need = hl_dist2(qx, qy, qz, s.x, s.y, s.z) * (1.0f - 8e-6f) <= reach * reach;
+        if (__any_sync(0xffffffffu, need)) {
+            hl_scan_staged(stage, CL, qx, qy, qz, best, bi);
+            sb = hl_sqrt_approx(best) * (1.0f + 4e-6f) + 1e-18f;
+            if (prof) atomicAdd(prof + 6, 1ull);
+        }
+        __syncwarp();
+    }
+    HL_CPROF(3)
+    if (prof) atomicAdd(prof + 7, 1ull);
+#undef HL_CPROF
+    best_out = best;
+    bi_out = bi;
 }
 
 // `sm_f4`: the CTA's search scratch (HL_CANON_SMEM_F4 float4, spheres staged by hl_canon_stage_spheres)

@@ -427,12 +427,13 @@ __device__ __forceinline__ float group_sum(const Group &G, float v, int slot) {
 // canonical view direction M sv goes, positionally encoded, into this thread's row of the constant tile
 // A_c = [1 | pe(d) (27) | 0 (4)] (per ray in the other modes, per sample here: human_diffusion/NeRF/renderer.py:107-110,
 // 155-157).  Out of line: its registers (and the sincos code) stay out of the render loop.
-__device__ __forceinline__ void canon_sample(const float4 *sph_s, float4 *stage, const float4 *__restrict__ verts,
+__device__ __noinline__ void canon_sample(const float4 *sph_s, float4 *stage, const float4 *__restrict__ verts,
                                           const float4 *__restrict__ aff, int NC, int CL, float qx, float qy, float qz,
-                                          float svx, float svy, float svz, uint32_t tm_ac, float *pc) {
+                                          float svx, float svy, float svz, uint32_t tm_ac, float *pc,
+                                          unsigned long long *prof) {
     float best;
     int v;
-    hl_nearest_vertex_impl(sph_s, verts, stage, NC, CL, qx, qy, qz, 0, NC, best, v);
+    hl_nearest_vertex_impl(sph_s, verts, stage, NC, CL, qx, qy, qz, 0, NC, best, v, prof);
     const float4 m0 = __ldg(aff + (size_t)v * 3), m1 = __ldg(aff + (size_t)v * 3 + 1), m2 = __ldg(aff + (size_t)v * 3 + 2);
     pc[0] = fmaf(m0.z, qz, fmaf(m0.y, qy, fmaf(m0.x, qx, m0.w)));
     pc[1] = fmaf(m1.z, qz, fmaf(m1.y, qy, fmaf(m1.x, qx, m1.w)));
@@ -450,7 +451,7 @@ __device__ __forceinline__ void canon_sample(const float4 *sph_s, float4 *stage,
             const int f = (k - 3) / 3, comp = (k - 3) % 3;
             const float freq = (float)(1 << (f >> 1));
             const float phase = (f & 1) ? 1.5707963267948966f : 0.f;
-            val = sinf(__fadd_rn(phase, __fmul_rn(dd[comp], freq)));
+            val = __sinf(__fadd_rn(phase, __fmul_rn(dd[comp], freq)));     // MUFU: the value is rounded to fp16 next
         }
         h[1 + k] = val;
     }
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                     float qx, qy, qz;
                     hl_to_smpl_frame(a.ct, pc[0], pc[1], pc[2], qx, qy, qz);
                     canon_sample(canon_f4, canon_stage, a.ct.verts, a.ct.aff, a.ct.NC, a.ct.CL, qx, qy, qz, sv[0], sv[1], sv[2],
-                                 G.tm + TM_AC, pc);
+                                 G.tm + TM_AC, pc, prof ? a.prof + 8 : nullptr);
                 }
                 gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
             }
@@ -690,6 +691,24 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                     pos_n = n_lt + lo;
                     sts_f32(zf + 4u * (uint32_t)pos_c, zmine);
                     sts_f32(zf + 4u * (uint32_t)pos_n, znew);
+                    if (CANON) {
+                        // Hand the new samples out in depth order (thread tg takes the tg-th smallest): the uniforms are
+                        // unsorted, so a warp's 32 samples would otherwise be scattered over the whole ray and the
+                        // nearest-vertex search -- a warp scans the union of the clusters its lanes need -- would touch
+                        // four times as many clusters.  The set of (position, value) pairs is unchanged.
+                        gbar(G);                           // everyone has finished reading zn
+                        sts_f32(zn + 4u * (uint32_t)n_lt, znew);
+                        gbar(G);
+                        znew = lds_f32(zn + tg4);
+                        int l2 = 0, h2 = NS;               // number of coarse z <= znew
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int mid = (l2 + h2) >> 1;
+                            const bool le = lds_f32(zc + 4u * (uint32_t)min(mid, NS - 1)) <= znew;
+                            if (l2 < h2) { if (le) l2 = mid + 1; else h2 = mid; }
+                        }
+                        pos_n = tg + l2;
+                    }
                 }
                 RPROF(3)
                 // ------------------------------- fine pass: the 128 new samples ----------------------------
@@ -700,7 +719,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                         float qx, qy, qz;
                         hl_to_smpl_frame(a.ct, pc[0], pc[1], pc[2], qx, qy, qz);
                         canon_sample(canon_f4, canon_stage, a.ct.verts, a.ct.aff, a.ct.NC, a.ct.CL, qx, qy, qz, sv[0], sv[1], sv[2],
-                                     G.tm + TM_AC, pc);
+                                     G.tm + TM_AC, pc, prof ? a.prof + 8 : nullptr);
                     }
                     gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
                 }

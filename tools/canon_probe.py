@@ -61,3 +61,28 @@ for precision in ("fp16", "fp32"):
               100.0 * float(hit.float().mean()), ms, ro.shape[0] / ms / 1e3, ms2, ro.shape[0] / ms2 / 1e3))
 ms = timed(lambda: r.smpl.frame_tables(tpd, 0, dev), reps=10)
 print("per-frame vertex tables (host joint chain + hl_smpl_vertex_tables): %.2f ms" % ms)
+
+# phase counters of the tcgen05 kernel in canonical mode (cycles of CTA 0 / group 0; "gather" includes the deformation)
+from humanliff_b200 import _lib  # noqa: E402
+r = Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl=asset, precision="fp16")
+r.load_state_dict(synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5), strict=False)
+r.to(dev)
+wb = tp["world_bounds"][0].tolist()
+ro, rd, near, far, hit = synth.synth_camera_rays(512, 512, focal=600.0, azimuth_deg=30.0, bounds=wb)
+args = dict(rays_o=ro[None].to(dev), rays_d=rd[None].to(dev), near=near[None].to(dev), far=far[None].to(dev),
+            tri_planes=planes, tp_input=tpd, renderer=r, n_samples=128, n_importance=128)
+render(**args)
+prof = torch.zeros(16, device=dev, dtype=torch.int64)
+lib = _lib.load()
+lib.hl_render5_set_profile(prof.data_ptr())
+render(**args)
+torch.cuda.synchronize()
+lib.hl_render5_set_profile(None)
+p = prof.cpu().tolist()
+rays = (262144 // 148 + 1) // 2
+names = ["setup", "gather+deform", "mlp", "resample+sort", "composite", "total", "mlp:barrier+issue", "mlp:wait_mma"]
+print({k: round(v / rays) for k, v in zip(names, p)}, "cycles per ray (CTA 0, group 0), canonical mode")
+calls = max(p[15], 1)
+print("nearest-vertex search per call (thread 0): pass 1 %d, phase A %d, candidate mask %d, phase B %d cycles; clusters in "
+      "phase A %.2f, candidates %.2f, scanned %.2f; %d calls" % (p[8] / calls, p[9] / calls, p[10] / calls, p[11] / calls,
+                                                                 p[12] / calls, p[13] / calls, p[14] / calls, calls))

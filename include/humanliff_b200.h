@@ -451,7 +451,9 @@ int hl_render_rays_tc5(const void *quads, int R, const void *mlp_tc5,
                        int64_t n_rays, int n_importance, int clamp_depth, void *stream);
 int hl_density_grid_tc5(const void *quads, int R, const void *mlp_tc5,
                         const float *bounds, int bounds_on_device, int resolution, float *out, void *stream);
-/* per-phase cycle counters of (CTA 0, group 0) of following tc5 launches, as hl_render_set_profile */
+/* per-phase cycle counters of (CTA 0, group 0) of following tc5 launches, as hl_render_set_profile: 8 x uint64; a
+ * canonical-space launch (hl_render_rays_tc5_canon) also fills slots 8..15 with the counters of its nearest-vertex search
+ * (tools/canon_probe.py), so the buffer must then hold 16 */
 int hl_render5_set_profile(void *dev_counters);
 
 

@@ -272,3 +272,20 @@ def test_smpl_joint_chain_matches_oracle_and_asset_is_required():
     assert np.allclose(c[:12].reshape(3, 4), A[0, :3]) and np.allclose(c[-3:], Th) and np.allclose(c[-12:-3], R.reshape(-1))
     with pytest.raises(FileNotFoundError):
         Renderer(use_canonical_space=True, triplane_ch=27, test=True, smpl_path="/nonexistent/SMPL_NEUTRAL.pkl")
+
+
+def test_spatial_clusters_partition_every_vertex_exactly_once():
+    """The nearest-vertex search is exact for any partition of the vertices into table slots -- provided it IS a partition."""
+    import numpy as np
+    from humanliff_b200 import _lib, synth
+    from humanliff_b200.smpl import SmplModel, spatial_clusters
+    m = SmplModel(synth.synth_smpl(5))
+    sv = m.slot_vertex
+    assert sv.size == m.n_clusters * m.cluster_slots and m.n_clusters == _lib.SMPL_CLUSTERS and m.cluster_slots % 4 == 0
+    used = np.sort(sv[sv >= 0])
+    assert np.array_equal(used, np.arange(m.n_verts))
+    # degenerate inputs: fewer points than clusters, one body part only
+    rs = np.random.RandomState(0)
+    for n, parts in ((50, None), (1000, rs.randint(0, 3, 1000)), (777, np.zeros(777, dtype=np.int64))):
+        t, slots = spatial_clusters(rs.randn(n, 3), 128, parts)
+        assert t.size == 128 * slots and np.array_equal(np.sort(t[t >= 0]), np.arange(n))

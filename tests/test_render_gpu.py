@@ -285,3 +285,44 @@ def test_canonical_density_grid_vs_oracle():
     want = -render_oracle.mlp(sd, render_oracle.plane_features(planes[0], c, tb[0], tb[1])).reshape(res, res, res)
     bad = ((got - want).abs() > 1e-3 * want.abs().max()).sum()
     assert int(bad) <= 2, (int(bad), rel_l2(got, want))
+
+
+def test_canonical_recon_variant_and_n_importance_zero_vs_oracle():
+    """The reconstruction-side renderer (recon_NeRF/lib/renderer.py: owns tri_planes, no depth clamp) in canonical-space
+    mode, with n_importance = 128 and 0 (coarse samples only), against the oracle; two frames in one batch."""
+    from humanliff_b200.renderer import ReconRenderer
+    from oracle import render_oracle
+    gz = load_golden("render_canon_384.npz")
+    asset = synth.synth_smpl(int(gz["seed_smpl"]))
+    r = ReconRenderer(use_canonical_space=True, num_instances=1, triplane_dim=256, triplane_ch=27, test=True, smpl=asset)
+    shapes = {k: v.shape for k, v in r.state_dict().items() if not k.startswith("view_enc") and k != "tri_planes"}
+    sd = synth.synth_state_dict(shapes, seed=int(gz["seed_w"]), weight_gain=1.5)
+    r.load_state_dict(sd, strict=False)
+    planes = synth.synth_triplane(256, seed=7)
+    with torch.no_grad():
+        r.tri_planes[0, 1] = planes[0]
+    dev = torch.device("cuda:0")
+    r = r.to(dev)
+    frames = [synth.synth_canonical_frame(asset, s) for s in (21, 22)]
+    cat = lambda key: torch.cat([f[key] for f in frames], 0)
+    tp = {"params": {k: torch.cat([f["params"][k] for f in frames], 0) for k in frames[0]["params"]},
+          "t_params": {k: torch.cat([f["t_params"][k] for f in frames], 0) for k in frames[0]["t_params"]},
+          "vertices": cat("vertices"), "world_bounds": cat("world_bounds"), "t_world_bounds": cat("t_world_bounds"),
+          "instance_idx": torch.tensor([0, 0]), "cloth_layer_index": torch.tensor([1, 1])}
+    n = 96
+    rays = [synth.synth_canonical_rays(f, n, seed=5 + i) for i, f in enumerate(frames)]
+    st = lambda j: torch.stack([rr[j] for rr in rays], 0)
+    ro, rd, near, far, u = st(0), st(1), st(2), st(3), torch.cat([rr[4] for rr in rays], 0)
+    t = torch.linspace(0., 1., steps=128)
+    z = near[:, :, None] * (1. - t) + far[:, :, None] * t
+    mv = lambda v: {k: mv(x) for k, x in v.items()} if isinstance(v, dict) else v.to(dev)
+    smpl = render_oracle.smpl_tensors(asset)
+    for n_imp in (128, 0):
+        out = r.render(mv(tp), None, z.to(dev), ro.to(dev), rd.to(dev), near[..., None].to(dev), far[..., None].to(dev),
+                       n_importance=n_imp, u=u.to(dev))
+        for b, f in enumerate(frames):
+            ref = render_oracle.render_rays(sd, planes[0], f["t_world_bounds"][0], ro[b], rd[b], near[b], far[b],
+                                            u[b * n:(b + 1) * n], clamp_depth=False, n_importance=n_imp, canon=(smpl, f))
+            for name, key, want in (("rgb", "rgb_map", ref[0]), ("acc", "acc_map", ref[1]), ("depth", "depth_map", ref[2])):
+                e = rel_l2(out[key][b], want)
+                assert e < 3e-4, f"n_importance={n_imp} frame {b} {name}: rel-L2 {e:.3e}"

@@ -771,17 +771,20 @@ def run_ours(args):
         sampler.start()
     calls0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_loop = torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(K):
         img = stepper.step()
+    e_loop.record(st)
     gathered, _ = all_gather_samples(img, y, equal_shards=True)
     e1.record(st)
     barrier()
     launches = _lib.launch_count - calls0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    ms = torch.tensor([e0.elapsed_time(e1), e_loop.elapsed_time(e1), -e0.elapsed_time(e_loop)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = float(ms[0].item())
+    gather_ms, fastest_rank_loop_ms = float(ms[1].item()), -float(ms[2].item())
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms_total * 1e-3)
 
@@ -903,6 +906,10 @@ def run_ours(args):
                                         "with in-kernel Philox noise, on-device timestep advance)" % (launches // K),
                            "precision": args.precision},
                 "clocks": clocks, "gpu_launches": launches,
+                "timed_region": {"what": "K graph-replayed steps + the all-gather of the finished samples (max over ranks)",
+                                 "all_gather_ms": round(gather_ms, 3),
+                                 "loop_ms_fastest_rank": round(fastest_rank_loop_ms, 3),
+                                 "loop_ms_slowest_rank_incl_gather": round(ms_total, 3)},
                 "sustained": {"steps": n_sus, "seconds": round(ms_sus * 1e-3, 3), "ms_per_step": round(ms_sus / n_sus, 3),
                               "value": round(world * B * n_sus / (ms_sus * 1e-3), 3), "unit": UNIT},
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 3 * nbytes,

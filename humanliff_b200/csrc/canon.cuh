@@ -2,10 +2,12 @@
 // human_diffusion/NeRF/renderer.py:52-133 (deform_target2c, deform_target2c_op) == recon_NeRF/lib/renderer.py:60-140.
 //
 // Per frame hl_smpl_vertex_tables leaves three tables in HBM (L2-resident: 6,890 vertices -> 110 KB + 2 KB + 330 KB):
-//   verts   [NC * CL] float4 {x, y, z, vertex index}: body vertices in the SMPL frame, grouped into NC spatial clusters of
-//           CL slots (clusters are fixed per asset: a k-d split of the template, humanliff_b200/smpl.py; skinning is smooth,
+//   verts   [NC * CL] float4, two vertices per PAIR of float4 {x0, x1, y0, y1} {z0, z1, index0, index1} (the layout the packed
+//           fp32 instructions of sm_100 -- FADD2 / FMUL2: two lanes per instruction, each rounded like the scalar one --
+//           want): body vertices in the SMPL frame, grouped into NC spatial clusters of CL slots (clusters are fixed per asset: a k-d split of the template, humanliff_b200/smpl.py; skinning is smooth,
 //           so they stay compact under any pose); unused slots hold x = 1e18
-//   spheres [NC] float4 {centre, radius} of each cluster's posed vertices
+//   spheres [NC] float4 in the same pair layout {cx0, cx1, cy0, cy1} {cz0, cz1, r0, r1}: centre and radius of each cluster's
+//           posed vertices
 //   aff     [V][3] float4: rows of M | c -- everything deform_target2c_op gathers per point depends on the nearest vertex
 //           only, so the whole chain is one affine per vertex: canonical = M q + c, canonical direction = M d
 //
@@ -41,6 +43,35 @@ __device__ __forceinline__ float hl_dist2(float qx, float qy, float qz, float x,
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
 }
 
+// ---- packed fp32 (two IEEE single operations per instruction; every lane is rounded exactly like its scalar counterpart) ----
+typedef unsigned long long hl_f32x2;
+__device__ __forceinline__ hl_f32x2 hl_pk(float lo, float hi) {
+    hl_f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void hl_unpk(hl_f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ hl_f32x2 hl_sub2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ hl_f32x2 hl_add2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ hl_f32x2 hl_mul2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// squared distances of q to the two points of a pair {x0, x1, y0, y1} {z0, z1, ., .}: ((dx^2 + dy^2) + dz^2) per lane, the
+// operation order of hl_dist2
+__device__ __forceinline__ hl_f32x2 hl_dist2x2(hl_f32x2 qx, hl_f32x2 qy, hl_f32x2 qz, const ulonglong2 &a, const ulonglong2 &b) {
+    const hl_f32x2 dx = hl_sub2(qx, a.x), dy = hl_sub2(qy, a.y), dz = hl_sub2(qz, b.x);
+    return hl_add2(hl_add2(hl_mul2(dx, dx), hl_mul2(dy, dy)), hl_mul2(dz, dz));
+}
+// element e of pair-layout entry i (spheres: x, y, z = centre, w = radius; vertices: w = index bits)
+__device__ __forceinline__ float4 hl_pair_get(const float4 *t, int i) {
+    const float *a = reinterpret_cast<const float *>(t + 2 * (i >> 1)), *b = a + 4;
+    const int e = i & 1;
+    return make_float4(a[e], a[2 + e], b[e], b[2 + e]);
+}
+__device__ __forceinline__ void hl_pair_put(float4 *t, int i, float x, float y, float z, float w) {
+    float *a = reinterpret_cast<float *>(t + 2 * (i >> 1)), *b = a + 4;
+    const int e = i & 1;
+    a[e] = x; a[2 + e] = y; b[e] = z; b[2 + e] = w;
+}
+
 // sqrt.approx (2 ulp): every use below carries a relative slack of 4e-6 or more
 __device__ __forceinline__ float hl_sqrt_approx(float x) {
     float r;
@@ -58,14 +89,14 @@ constexpr int HL_CANON_SMEM_F4 = HL_CANON_NC_MAX + 8 * HL_CANON_CL_MAX;
 // all HL_CANON_NC_MAX entries are written (unused ones far away, radius 0: never the arg-min, never a candidate), so the
 // loops over the spheres run a fixed trip count in blocks of four without bounds checks
 __device__ __forceinline__ void hl_canon_stage_spheres(const CanonTables &t, float4 *sm_f4) {
-    for (int i = threadIdx.x; i < HL_CANON_NC_MAX; i += blockDim.x)
-        sm_f4[i] = i < t.NC ? __ldg(t.spheres + i) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    for (int i = threadIdx.x; i < HL_CANON_NC_MAX; i += blockDim.x)      // pair layout: even float4 = x | y, odd = z | radius
+        sm_f4[i] = i < t.NC ? __ldg(t.spheres + i) : ((i & 1) ? make_float4(1e18f, 1e18f, 0.f, 0.f) : make_float4(1e18f, 1e18f, 1e18f, 1e18f));
 }
 
 // A cluster in flight: lane l holds slots l, l + 32, l + 64 of the cluster (CL <= 96) in registers.
 struct HlClusterRegs { float4 a, b, c; };
 __device__ __forceinline__ void hl_cluster_load(HlClusterRegs &r, const float4 *__restrict__ v, int CL, int lane) {
-    const float4 pad = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(0x7fffffff));
+    const float4 pad = make_float4(1e18f, 1e18f, 1e18f, 1e18f);      // (never used: CL float4 are always present)
     r.a = lane < CL ? __ldg(v + lane) : pad;
     r.b = lane + 32 < CL ? __ldg(v + lane + 32) : pad;
     r.c = lane + 64 < CL ? __ldg(v + lane + 64) : pad;
@@ -78,17 +109,20 @@ __device__ __forceinline__ void hl_cluster_store(const HlClusterRegs &r, float4 
 // scan the staged cluster: every lane updates its own (best, bi); branch-free, the loads are warp-uniform broadcasts
 __device__ __forceinline__ void hl_scan_staged(const float4 *stage, int CL, float qx, float qy, float qz, float &best,
                                                int &bi) {
-    // four vertices at a time (CL is a multiple of 4): four independent distance chains, then ONE comparison of their
-    // minimum against `best` -- after the first cluster almost no group can win, so the serial compare-select chain of a
-    // per-vertex update (which bounded this loop by latency, not by issue) is off the common path
+    // four vertices = two pairs at a time (CL is a multiple of 4): 16 packed instructions for the four distances, then ONE
+    // comparison of their minimum against `best` -- after the first cluster almost no group can win, so the serial
+    // compare-select chain of a per-vertex update is off the common path
+    const hl_f32x2 q2x = hl_pk(qx, qx), q2y = hl_pk(qy, qy), q2z = hl_pk(qz, qz);
+    const ulonglong2 *st2 = reinterpret_cast<const ulonglong2 *>(stage);
 #pragma unroll 2
     for (int k = 0; k < CL; k += 4) {
-        const float4 p0 = stage[k], p1 = stage[k + 1], p2 = stage[k + 2], p3 = stage[k + 3];
-        const float d0 = hl_dist2(qx, qy, qz, p0.x, p0.y, p0.z), d1 = hl_dist2(qx, qy, qz, p1.x, p1.y, p1.z);
-        const float d2 = hl_dist2(qx, qy, qz, p2.x, p2.y, p2.z), d3 = hl_dist2(qx, qy, qz, p3.x, p3.y, p3.z);
+        const ulonglong2 a0 = st2[k], b0 = st2[k + 1], a1 = st2[k + 2], b1 = st2[k + 3];
+        float d0, d1, d2, d3;
+        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a0, b0), d0, d1);
+        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a1, b1), d2, d3);
         if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {
             const float ds[4] = {d0, d1, d2, d3};
-            const int is[4] = {__float_as_int(p0.w), __float_as_int(p1.w), __float_as_int(p2.w), __float_as_int(p3.w)};
+            const int is[4] = {(int)(unsigned)b0.y, (int)(unsigned)(b0.y >> 32), (int)(unsigned)b1.y, (int)(unsigned)(b1.y >> 32)};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool take = (ds[j] < best) | ((ds[j] == best) & (is[j] < bi));
@@ -129,11 +163,14 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
     // pass 1: c* = the cluster with the nearest centre (any choice is correct; this one needs no square root per cluster)
     float dmin = 3.0e38f;
     int cstar = 0;
+    const hl_f32x2 q2x = hl_pk(qx, qx), q2y = hl_pk(qy, qy), q2z = hl_pk(qz, qz);
+    const ulonglong2 *sp2 = reinterpret_cast<const ulonglong2 *>(sph_s);
 #pragma unroll 2
     for (int c = 0; c < HL_CANON_NC_MAX; c += 4) {
-        const float4 s0 = sph_s[c], s1 = sph_s[c + 1], s2 = sph_s[c + 2], s3 = sph_s[c + 3];
-        const float u0 = hl_dist2(qx, qy, qz, s0.x, s0.y, s0.z), u1 = hl_dist2(qx, qy, qz, s1.x, s1.y, s1.z);
-        const float u2 = hl_dist2(qx, qy, qz, s2.x, s2.y, s2.z), u3 = hl_dist2(qx, qy, qz, s3.x, s3.y, s3.z);
+        const ulonglong2 a0 = sp2[c], b0 = sp2[c + 1], a1 = sp2[c + 2], b1 = sp2[c + 3];
+        float u0, u1, u2, u3;
+        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a0, b0), u0, u1);
+        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a1, b1), u2, u3);
         const bool b01 = u1 < u0, b23 = u3 < u2;
         const float m01 = b01 ? u1 : u0, m23 = b23 ? u3 : u2;
         const int i01 = b01 ? c + 1 : c, i23 = b23 ? c + 3 : c + 2;
@@ -142,7 +179,7 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
         const int im = b ? i23 : i01;
         if (mm < dmin) { dmin = mm; cstar = im; }
     }
-    const float U = hl_sqrt_approx(dmin) + sph_s[cstar].w;
+    const float U = hl_sqrt_approx(dmin) + hl_pair_get(sph_s, cstar).w;
     best = U * U * (1.0f + 8e-6f) + 1e-20f;       // >= the squared distance of the farthest vertex of cluster c*
     bi = 0x7fffffff;
     HL_CPROF(0)
@@ -167,17 +204,20 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
     // (compact loops throughout: the render kernels are instruction-cache bound -- ncu: 2.3 warps stalled on instruction
     // fetch per issued instruction before this function was shrunk -- so nothing here is unrolled beyond a block of four)
     uint32_t m[4] = {0u, 0u, 0u, 0u};
+    const hl_f32x2 sb2 = hl_pk(sb, sb), slack2 = hl_pk(1.0f - 8e-6f, 1.0f - 8e-6f);
 #pragma unroll 1
     for (int w = 0; w < 4; ++w) {
         uint32_t bits = 0u;
 #pragma unroll 2
         for (int b = 0; b < 32; b += 4) {
-            const float4 s0 = sph_s[w * 32 + b], s1 = sph_s[w * 32 + b + 1], s2 = sph_s[w * 32 + b + 2], s3 = sph_s[w * 32 + b + 3];
-            const float r0 = sb + s0.w, r1 = sb + s1.w, r2 = sb + s2.w, r3 = sb + s3.w;
-            const uint32_t n0 = hl_dist2(qx, qy, qz, s0.x, s0.y, s0.z) * (1.0f - 8e-6f) <= r0 * r0;
-            const uint32_t n1 = hl_dist2(qx, qy, qz, s1.x, s1.y, s1.z) * (1.0f - 8e-6f) <= r1 * r1;
-            const uint32_t n2 = hl_dist2(qx, qy, qz, s2.x, s2.y, s2.z) * (1.0f - 8e-6f) <= r2 * r2;
-            const uint32_t n3 = hl_dist2(qx, qy, qz, s3.x, s3.y, s3.z) * (1.0f - 8e-6f) <= r3 * r3;
+            const ulonglong2 a0 = sp2[w * 32 + b], b0 = sp2[w * 32 + b + 1], a1 = sp2[w * 32 + b + 2], b1 = sp2[w * 32 + b + 3];
+            const hl_f32x2 r01 = hl_add2(sb2, b0.y), r23 = hl_add2(sb2, b1.y);            // sb + radius
+            float e0, e1, e2, e3, f0, f1, f2, f3;
+            hl_unpk(hl_mul2(hl_dist2x2(q2x, q2y, q2z, a0, b0), slack2), e0, e1);
+            hl_unpk(hl_mul2(hl_dist2x2(q2x, q2y, q2z, a1, b1), slack2), e2, e3);
+            hl_unpk(hl_mul2(r01, r01), f0, f1);
+            hl_unpk(hl_mul2(r23, r23), f2, f3);
+            const uint32_t n0 = e0 <= f0, n1 = e1 <= f1, n2 = e2 <= f2, n3 = e3 <= f3;
             bits |= (n0 | (n1 << 1) | (n2 << 2) | (n3 << 3)) << b;
         }
         // clusters [c0, c1) only
@@ -211,7 +251,7 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
         const int now = cur;
         cur = pop();
         if (cur >= 0) hl_cluster_load(regs, verts + (size_t)cur * CL, CL, lane);
-        const float4 s = sph_s[now];
+        const float4 s = hl_pair_get(sph_s, now);
         const float reach = sb + s.w;
         const bool need = hl_dist2(qx, qy, qz, s.x, s.y, s.z) * (1.0f - 8e-6f) <= reach * reach;
         if (__any_sync(0xffffffffu, need)) {

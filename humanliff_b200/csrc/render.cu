@@ -524,7 +524,7 @@ __global__ void k_smpl_vertex_tables(const float *__restrict__ weights, const fl
     if (slot >= n_slots) return;
     const int v = slot_vertex[slot];
     if (v < 0 || v >= V) {      // unused slot of its cluster: never the nearest
-        if (lane == 0) verts[slot] = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(0x7fffffff));
+        if (lane == 0) hl_pair_put(verts, slot, 1e18f, 1e18f, 1e18f, __int_as_float(0x7fffffff));
         return;
     }
     double po[3] = {0, 0, 0}, pob[3] = {0, 0, 0};
@@ -581,7 +581,7 @@ __global__ void k_smpl_vertex_tables(const float *__restrict__ weights, const fl
     float q[3];
     for (int c = 0; c < 3; ++c)
         q[c] = fmaf(ez, (float)cst[SC_R + 6 + c], fmaf(ey, (float)cst[SC_R + 3 + c], ex * (float)cst[SC_R + c]));
-    verts[slot] = make_float4(q[0], q[1], q[2], __int_as_float(v));
+    hl_pair_put(verts, slot, q[0], q[1], q[2], __int_as_float(v));      // pair layout (canon.cuh); CL is even, so a pair never straddles two clusters
 }
 
 // Bounding sphere of each cluster's posed vertices (one warp per cluster): centre = centroid, radius = the largest
@@ -591,20 +591,23 @@ __global__ void k_smpl_cluster_bounds(const float4 *__restrict__ verts, int NC, 
     if (c >= NC) return;
     float sx = 0.f, sy = 0.f, sz = 0.f, n = 0.f;
     for (int k = lane; k < CL; k += 32) {
-        const float4 p = verts[(size_t)c * CL + k];
+        const float4 p = hl_pair_get(verts + (size_t)c * CL, k);
         if (p.x < 1e17f) { sx += p.x; sy += p.y; sz += p.z; n += 1.f; }
     }
     sx = hl_warp_sum(sx); sy = hl_warp_sum(sy); sz = hl_warp_sum(sz); n = hl_warp_sum(n);
     const float cx = n > 0.f ? sx / n : 0.f, cy = n > 0.f ? sy / n : 0.f, cz = n > 0.f ? sz / n : 0.f;
     float r = 0.f;
     for (int k = lane; k < CL; k += 32) {
-        const float4 p = verts[(size_t)c * CL + k];
+        const float4 p = hl_pair_get(verts + (size_t)c * CL, k);
         if (p.x < 1e17f) r = fmaxf(r, sqrtf(hl_dist2(cx, cy, cz, p.x, p.y, p.z)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
     // an empty cluster gets a far-away centre: its lower bound never passes, its upper bound never wins
-    if (lane == 0) spheres[c] = n > 0.f ? make_float4(cx, cy, cz, r * (1.0f + 4e-6f) + 1e-7f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    if (lane == 0) {
+        if (n > 0.f) hl_pair_put(spheres, c, cx, cy, cz, r * (1.0f + 4e-6f) + 1e-7f);
+        else hl_pair_put(spheres, c, 1e18f, 1e18f, 1e18f, 0.f);
+    }
 }
 
 // deform_target2c on arbitrary points (tests / Renderer.deform_target2c): 128 points per block, two threads per point
@@ -731,7 +734,7 @@ extern "C" int hl_smpl_vertex_tables(const float *weights, const float *posedirs
     HL_CHECK_ARG(weights && posedirs && shapedirs && vertices && consts && slot_vertex && knn_table && affine_table);
     HL_CHECK_ARG(n_verts > 0 && n_betas >= 0 && n_betas <= 16 && n_betas <= n_betas_asset);
     HL_CHECK_ARG(n_joints >= 2 && n_joints <= 64 && n_clusters >= 2 && n_clusters <= 128 && cluster_slots >= 1);
-    HL_CHECK_ARG((int64_t)n_clusters * cluster_slots >= n_verts);
+    HL_CHECK_ARG((int64_t)n_clusters * cluster_slots >= n_verts && n_clusters % 2 == 0 && cluster_slots % 4 == 0);
     HL_CHECK_ARG(((uintptr_t)knn_table & 15) == 0 && ((uintptr_t)affine_table & 15) == 0);
     const int n_slots = n_clusters * cluster_slots;
     float4 *spheres = reinterpret_cast<float4 *>(knn_table);

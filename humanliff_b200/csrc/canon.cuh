@@ -3,8 +3,7 @@
 //
 // Per frame hl_smpl_vertex_tables leaves three tables in HBM (L2-resident: 6,890 vertices -> 110 KB + 2 KB + 330 KB):
 //   verts   [NC * CL] float4, two vertices per PAIR of float4 {x0, x1, y0, y1} {z0, z1, index0, index1} (the layout the packed
-//           fp32 instructions of sm_100 -- FADD2 / FMUL2: two lanes per instruction, each rounded like the scalar one --
-//           want): body vertices in the SMPL frame, grouped into NC spatial clusters of CL slots (clusters are fixed per asset: a k-d split of the template, humanliff_b200/smpl.py; skinning is smooth,
+//           fp32 instructions of sm_100 -- FADD2 / FMUL2 / FFMA2: two lanes per instruction -- want): body vertices in the SMPL frame, grouped into NC spatial clusters of CL slots (clusters are fixed per asset: a k-d split of the template, humanliff_b200/smpl.py; skinning is smooth,
 //           so they stay compact under any pose); unused slots hold x = 1e18
 //   spheres [NC] float4 in the same pair layout {cx0, cx1, cy0, cy1} {cz0, cz1, r0, r1}: centre and radius of each cluster's
 //           posed vertices
@@ -43,7 +42,12 @@ __device__ __forceinline__ float hl_dist2(float qx, float qy, float qz, float x,
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
 }
 
-// ---- packed fp32 (two IEEE single operations per instruction; every lane is rounded exactly like its scalar counterpart) ----
+// ---- packed fp32 (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE single lanes per instruction) ----
+// ptxas 12.9 CONTRACTS mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (unlike the scalar mul.rn / add.rn, which it leaves alone:
+// 40 of 172 packed PTX instructions of this file came out fused), so a packed distance cannot reproduce the separately
+// rounded hl_dist2.  The packed distance is therefore DEFINED with explicit fused multiply-adds and used only where a
+// bound with slack is all that is needed: the sphere passes, and the FILTER of the vertex scans.  Every nearest-vertex
+// decision is taken on the scalar, separately rounded hl_dist2 (the oracle's arithmetic).
 typedef unsigned long long hl_f32x2;
 __device__ __forceinline__ hl_f32x2 hl_pk(float lo, float hi) {
     hl_f32x2 r;
@@ -51,14 +55,18 @@ __device__ __forceinline__ hl_f32x2 hl_pk(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ void hl_unpk(hl_f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ hl_f32x2 hl_sub2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ hl_f32x2 hl_add2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ hl_f32x2 hl_mul2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-// squared distances of q to the two points of a pair {x0, x1, y0, y1} {z0, z1, ., .}: ((dx^2 + dy^2) + dz^2) per lane, the
-// operation order of hl_dist2
-__device__ __forceinline__ hl_f32x2 hl_dist2x2(hl_f32x2 qx, hl_f32x2 qy, hl_f32x2 qz, const ulonglong2 &a, const ulonglong2 &b) {
+__device__ __forceinline__ hl_f32x2 hl_sub2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ hl_f32x2 hl_add2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ hl_f32x2 hl_mul2(hl_f32x2 a, hl_f32x2 b) { hl_f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ hl_f32x2 hl_fma2(hl_f32x2 a, hl_f32x2 b, hl_f32x2 c) { hl_f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// squared distances of q to the two points of a pair {x0, x1, y0, y1} {z0, z1, ., .}: fma(dz, dz, fma(dy, dy, dx * dx)) per
+// lane, 6 packed instructions.  With d = hl_dist2 of the same point and D the real-number sum of the three squares (the
+// differences dx, dy, dz are the same fp32 values on both paths): |d - D| <= 3 * 2^-24 D and |d_fma - D| <= 3 * 2^-24 D, so
+// d_fma <= d (1 + 4e-7): a group of vertices can only hold a winner (d <= best) if min(d_fma) (1 - 1e-6) <= best.
+constexpr float HL_CANON_FILTER_SLACK = 1.0f - 1e-6f;
+__device__ __forceinline__ hl_f32x2 hl_dist2x2_fma(hl_f32x2 qx, hl_f32x2 qy, hl_f32x2 qz, const ulonglong2 &a, const ulonglong2 &b) {
     const hl_f32x2 dx = hl_sub2(qx, a.x), dy = hl_sub2(qy, a.y), dz = hl_sub2(qz, b.x);
-    return hl_add2(hl_add2(hl_mul2(dx, dx), hl_mul2(dy, dy)), hl_mul2(dz, dz));
+    return hl_fma2(dz, dz, hl_fma2(dy, dy, hl_mul2(dx, dx)));
 }
 // element e of pair-layout entry i (spheres: x, y, z = centre, w = radius; vertices: w = index bits)
 __device__ __forceinline__ float4 hl_pair_get(const float4 *t, int i) {
@@ -83,6 +91,10 @@ __device__ __forceinline__ float hl_sqrt_approx(float x) {
 // of HL_CANON_CL_MAX vertices per warp (8 warps).  With ~200 KB of a CTA's shared memory holding MLP weights the L1 is
 // too small to keep the 110 KB vertex table, and a warp-uniform load that misses it costs an L2 round trip per vertex:
 // a cluster is therefore fetched with ONE coalesced load per lane and scanned out of shared memory.
+#ifndef HL_CANON_UNROLL
+#define HL_CANON_UNROLL 2      // blocks of four per loop iteration of the sphere / vertex scans (measured: profiles/r2_canon_search_ab.log)
+#endif
+constexpr int kCanonUnroll = HL_CANON_UNROLL;      // (#pragma unroll takes a constant expression, not a macro)
 constexpr int HL_CANON_NC_MAX = 128, HL_CANON_CL_MAX = 96;
 constexpr int HL_CANON_SMEM_F4 = HL_CANON_NC_MAX + 8 * HL_CANON_CL_MAX;
 
@@ -109,18 +121,23 @@ __device__ __forceinline__ void hl_cluster_store(const HlClusterRegs &r, float4 
 // scan the staged cluster: every lane updates its own (best, bi); branch-free, the loads are warp-uniform broadcasts
 __device__ __forceinline__ void hl_scan_staged(const float4 *stage, int CL, float qx, float qy, float qz, float &best,
                                                int &bi) {
-    // four vertices = two pairs at a time (CL is a multiple of 4): 16 packed instructions for the four distances, then ONE
-    // comparison of their minimum against `best` -- after the first cluster almost no group can win, so the serial
-    // compare-select chain of a per-vertex update is off the common path
+    // four vertices = two pairs at a time (CL is a multiple of 4): 12 packed instructions for the four FILTER distances, then
+    // ONE comparison of their minimum against `best` -- after the first cluster almost no group can win, so the exact
+    // distances and the serial compare-select chain of the update are off the common path
     const hl_f32x2 q2x = hl_pk(qx, qx), q2y = hl_pk(qy, qy), q2z = hl_pk(qz, qz);
     const ulonglong2 *st2 = reinterpret_cast<const ulonglong2 *>(stage);
-#pragma unroll 2
+#pragma unroll kCanonUnroll
     for (int k = 0; k < CL; k += 4) {
         const ulonglong2 a0 = st2[k], b0 = st2[k + 1], a1 = st2[k + 2], b1 = st2[k + 3];
         float d0, d1, d2, d3;
-        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a0, b0), d0, d1);
-        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a1, b1), d2, d3);
-        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {
+        hl_unpk(hl_dist2x2_fma(q2x, q2y, q2z, a0, b0), d0, d1);
+        hl_unpk(hl_dist2x2_fma(q2x, q2y, q2z, a1, b1), d2, d3);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) * HL_CANON_FILTER_SLACK <= best) {
+            float x0, x1, y0, y1, z0, z1;                               // the separately rounded distances decide
+            hl_unpk(a0.x, x0, x1); hl_unpk(a0.y, y0, y1); hl_unpk(b0.x, z0, z1);
+            d0 = hl_dist2(qx, qy, qz, x0, y0, z0); d1 = hl_dist2(qx, qy, qz, x1, y1, z1);
+            hl_unpk(a1.x, x0, x1); hl_unpk(a1.y, y0, y1); hl_unpk(b1.x, z0, z1);
+            d2 = hl_dist2(qx, qy, qz, x0, y0, z0); d3 = hl_dist2(qx, qy, qz, x1, y1, z1);
             const float ds[4] = {d0, d1, d2, d3};
             const int is[4] = {(int)(unsigned)b0.y, (int)(unsigned)(b0.y >> 32), (int)(unsigned)b1.y, (int)(unsigned)(b1.y >> 32)};
 #pragma unroll
@@ -165,12 +182,12 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
     int cstar = 0;
     const hl_f32x2 q2x = hl_pk(qx, qx), q2y = hl_pk(qy, qy), q2z = hl_pk(qz, qz);
     const ulonglong2 *sp2 = reinterpret_cast<const ulonglong2 *>(sph_s);
-#pragma unroll 2
+#pragma unroll kCanonUnroll
     for (int c = 0; c < HL_CANON_NC_MAX; c += 4) {
         const ulonglong2 a0 = sp2[c], b0 = sp2[c + 1], a1 = sp2[c + 2], b1 = sp2[c + 3];
         float u0, u1, u2, u3;
-        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a0, b0), u0, u1);
-        hl_unpk(hl_dist2x2(q2x, q2y, q2z, a1, b1), u2, u3);
+        hl_unpk(hl_dist2x2_fma(q2x, q2y, q2z, a0, b0), u0, u1);
+        hl_unpk(hl_dist2x2_fma(q2x, q2y, q2z, a1, b1), u2, u3);
         const bool b01 = u1 < u0, b23 = u3 < u2;
         const float m01 = b01 ? u1 : u0, m23 = b23 ? u3 : u2;
         const int i01 = b01 ? c + 1 : c, i23 = b23 ? c + 3 : c + 2;
@@ -208,13 +225,13 @@ static __device__ __noinline__ void hl_nearest_vertex_impl(const float4 *sph_s, 
 #pragma unroll 1
     for (int w = 0; w < 4; ++w) {
         uint32_t bits = 0u;
-#pragma unroll 2
+#pragma unroll kCanonUnroll
         for (int b = 0; b < 32; b += 4) {
             const ulonglong2 a0 = sp2[w * 32 + b], b0 = sp2[w * 32 + b + 1], a1 = sp2[w * 32 + b + 2], b1 = sp2[w * 32 + b + 3];
             const hl_f32x2 r01 = hl_add2(sb2, b0.y), r23 = hl_add2(sb2, b1.y);            // sb + radius
             float e0, e1, e2, e3, f0, f1, f2, f3;
-            hl_unpk(hl_mul2(hl_dist2x2(q2x, q2y, q2z, a0, b0), slack2), e0, e1);
-            hl_unpk(hl_mul2(hl_dist2x2(q2x, q2y, q2z, a1, b1), slack2), e2, e3);
+            hl_unpk(hl_mul2(hl_dist2x2_fma(q2x, q2y, q2z, a0, b0), slack2), e0, e1);
+            hl_unpk(hl_mul2(hl_dist2x2_fma(q2x, q2y, q2z, a1, b1), slack2), e2, e3);
             hl_unpk(hl_mul2(r01, r01), f0, f1);
             hl_unpk(hl_mul2(r23, r23), f2, f3);
             const uint32_t n0 = e0 <= f0, n1 = e1 <= f1, n2 = e2 <= f2, n3 = e3 <= f3;

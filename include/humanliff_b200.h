@@ -346,7 +346,8 @@ int hl_render_rays(const float *texels, int R, const float *mlp_packed, const fl
  *           property of the asset: any partition is correct, a spatially compact one is fast)
  *   knn_table: float4 [n_clusters] bounding spheres | float4 [n_clusters * cluster_slots] vertices, both two entries per
  *           pair of float4 -- {x0, x1, y0, y1} {z0, z1, w0, w1}, w = radius | vertex index -- the operand layout of the packed
- *           fp32 instructions (n_clusters even, <= 128; cluster_slots a multiple of 4, <= 96);
+ *           fp32 instructions, which serve bounds and the scan filter only: decisions are taken on separately rounded
+ *           distances (n_clusters even, <= 128; cluster_slots a multiple of 4, <= 96);
  *           affine_table: [V][3][4] floats (rows M | c)                                                             */
 #define HL_SMPL_CONSTS(J) (24 * (J) + 18 * ((J) - 1) + 28)
 int hl_smpl_vertex_tables(const float *weights, const float *posedirs, const float *shapedirs, int n_betas_asset,

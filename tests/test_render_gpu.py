@@ -326,3 +326,122 @@ def test_canonical_recon_variant_and_n_importance_zero_vs_oracle():
             for name, key, want in (("rgb", "rgb_map", ref[0]), ("acc", "acc_map", ref[1]), ("depth", "depth_map", ref[2])):
                 e = rel_l2(out[key][b], want)
                 assert e < 3e-4, f"n_importance={n_imp} frame {b} {name}: rel-L2 {e:.3e}"
+
+
+def _pair_layout(t):
+    """[n, 4] (x, y, z, w) rows -> the two-entries-per-pair-of-float4 layout of the search tables (canon.cuh)."""
+    import numpy as np
+    t = np.asarray(t, dtype=np.float32).reshape(-1, 2, 4)             # [pairs, entry, xyzw]
+    a = np.stack([t[:, 0, 0], t[:, 1, 0], t[:, 0, 1], t[:, 1, 1]], -1)
+    b = np.stack([t[:, 0, 2], t[:, 1, 2], t[:, 0, 3], t[:, 1, 3]], -1)
+    return np.stack([a, b], 1).reshape(-1, 4)
+
+
+def test_nearest_vertex_decisions_are_separately_rounded_with_ties_to_the_lower_index():
+    """hl_canonical_points on a hand-built table (the C ABI takes the tables as plain pointers).  Every query has exactly two
+    candidate vertices at (nearly) the same distance, either in one cluster or in two; everything else is 3 units away.
+    * adversarial pairs: found by a seeded search so that the separately rounded distance ((dx^2 + dy^2) + dz^2, each
+      operation rounded: the oracle's / the torch stand-in's arithmetic) and the fused one (fma(dz, dz, fma(dy, dy, dx^2)):
+      what the packed filter computes, and what ptxas makes of packed mul + add) DISAGREE about the nearer vertex -- the kernel must side with the separately rounded one;
+    * exact ties (v = q +- delta, exactly representable): the lower vertex index wins although the higher one is scanned
+      first (earlier slot / earlier cluster).
+    The per-vertex affine is M = 0, c = (index, 0, 0), so the returned canonical x IS the chosen vertex."""
+    import ctypes
+    import numpy as np
+    from humanliff_b200._lib import call
+    f32 = np.float32
+    rs = np.random.RandomState(11)
+
+    def d_sep(q, v):
+        d = (q - v).astype(f32)
+        s = (d * d).astype(f32)
+        return f32(f32(s[0] + s[1]) + s[2])
+
+    def d_fma(q, v):
+        d = (q - v).astype(f32).astype(np.float64)
+        r = f32(d[0] * d[0])
+        r = f32(d[1] * d[1] + np.float64(r))
+        return f32(d[2] * d[2] + np.float64(r))
+
+    NC, CL = 64, 4
+    n_same_adv, n_same_tie, n_cross_adv, n_cross_tie = 24, 8, 12, 4
+    cases = []                                            # (q, v_first_scanned, v_second_scanned)
+    centre = lambda k: np.array([3.0 * k - 90.0, 0.37, -0.21], dtype=f32)
+    k = 0
+    while len(cases) < n_same_adv + n_cross_adv:          # adversarial: the two roundings disagree
+        c = centre(len(cases))
+        q = (c + rs.uniform(-0.2, 0.2, 3)).astype(f32)
+        off = rs.normal(size=3); off *= rs.uniform(0.05, 0.4) / np.linalg.norm(off)
+        v1 = (q + off).astype(f32)
+        # v2: random x, y; z solved so that the REAL distances agree to about one ulp (rounding of v2.z only)
+        D1 = float((((q - v1).astype(f32).astype(np.float64)) ** 2).sum())
+        v2 = (q + rs.uniform(-0.6, 0.6, 3) * np.sqrt(D1)).astype(f32)
+        dxy = (q - v2).astype(f32).astype(np.float64)[:2]
+        v2[2] = f32(np.float64(q[2]) + rs.choice([-1.0, 1.0]) * np.sqrt(D1 - float((dxy ** 2).sum())))
+        s = np.sign(float(d_sep(q, v1)) - float(d_sep(q, v2)))
+        if s != 0 and s == -np.sign(float(d_fma(q, v1)) - float(d_fma(q, v2))):      # strict reversal
+            cases.append((q, v1, v2))
+        k += 1
+        assert k < 200000
+    adv = cases[:n_same_adv]
+    cross_adv = cases[n_same_adv:]
+    ties = []
+    for j in range(n_same_tie + n_cross_tie):             # exact ties
+        q = (np.round(centre(100 + j) * 256) / 256 + rs.randint(-64, 64, 3) / 256.0).astype(f32)
+        dl = (rs.randint(-1500, 1500, 3) / 4096.0).astype(f32)
+        v1, v2 = (q + dl).astype(f32), (q - dl).astype(f32)
+        assert d_sep(q, v1) == d_sep(q, v2) and np.all(q - v1 == -dl)
+        ties.append((q, v1, v2))
+    verts = np.full((NC * CL, 4), 1e18, dtype=f32)
+    idx = np.full(NC * CL, 0x7fffffff, dtype=np.int32)
+    queries, expect, fused_would_differ = [], [], 0
+
+    def place(case, slot_a, slot_b, ia, ib):
+        nonlocal fused_would_differ
+        q, va, vb = case
+        verts[slot_a, :3], verts[slot_b, :3] = va, vb
+        idx[slot_a], idx[slot_b] = ia, ib
+        key = lambda v, i, dist: (float(dist(q, v)), i)
+        want = min((key(va, ia, d_sep), ia), (key(vb, ib, d_sep), ib))[1]
+        fused = min((key(va, ia, d_fma), ia), (key(vb, ib, d_fma), ib))[1]
+        fused_would_differ += int(want != fused)
+        queries.append(q); expect.append(want)
+
+    # same cluster: slot 0 (scanned first) carries the HIGHER index
+    for c, case in enumerate(adv + ties[:n_same_tie]):
+        place(case, c * CL, c * CL + 1, 2 * c + 1, 2 * c)
+    # two clusters: the earlier cluster carries the HIGHER index
+    for j, case in enumerate(cross_adv + ties[n_same_tie:]):
+        # (odd j: the first vertex sits in a cluster of the OTHER half of the table, whose bounding sphere it blows up to
+        # ~100 units -- any partition is legal -- and whose half is searched by the other thread of the point)
+        ca, cb = (32 + j, 48 + j) if j % 2 == 0 else (j, 48 + j)
+        place(case, ca * CL + 2, cb * CL + 2, 1000 + 2 * j + 1, 1000 + 2 * j)
+    assert fused_would_differ == n_same_adv + n_cross_adv, fused_would_differ      # the test has teeth
+    spheres = np.zeros((NC, 4), dtype=f32)
+    for c in range(NC):
+        m = verts[c * CL:(c + 1) * CL]
+        m = m[m[:, 0] < 1e17, :3].astype(np.float64)
+        if len(m) == 0:
+            spheres[c] = (1e18, 1e18, 1e18, 0.0)
+            continue
+        cen = m.mean(0).astype(f32)
+        rad = np.sqrt(((m - cen.astype(np.float64)) ** 2).sum(-1)).max()
+        spheres[c] = (*cen, f32(rad * (1 + 1e-5) + 1e-6))
+    verts[:, 3] = idx.view(f32)
+    dev = torch.device("cuda:0")
+    knn = torch.from_numpy(np.concatenate([_pair_layout(spheres), _pair_layout(verts)]).reshape(-1)).to(dev)
+    n_idx = 1000 + 2 * 16
+    aff = np.zeros((n_idx, 3, 4), dtype=f32)
+    aff[:, 0, 3] = np.arange(n_idx, dtype=f32)
+    aff = torch.from_numpy(aff.reshape(-1)).to(dev)
+    rot = (ctypes.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    trans = (ctypes.c_float * 3)(0, 0, 0)
+    pts = torch.from_numpy(np.stack(queries)).to(dev).contiguous()
+    out = torch.empty_like(pts)
+    call("hl_canonical_points", pts.data_ptr(), None, pts.shape[0], knn.data_ptr(), aff.data_ptr(), NC, CL,
+         ctypes.cast(rot, ctypes.c_void_p), ctypes.cast(trans, ctypes.c_void_p), out.data_ptr(), None,
+         torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    got = out[:, 0].cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, np.asarray(expect)), [(i, int(g), int(e)) for i, (g, e) in enumerate(zip(got, expect)) if g != e]
+    assert float(out[:, 1:].abs().max()) == 0.0

@@ -16,7 +16,9 @@ _TAG = os.environ.get("HL_BUILD_TAG", "")
 OBJ_DIR = os.path.join(HERE, "csrc", "build" + ("_" + _TAG if _TAG else ""))
 LIB_PATH = os.path.join(HERE, "libhumanliff_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
-SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "attention_tc5.cu", "render.cu", "render_tc.cu", "render_tc5.cu", "sampler.cu", "gn_skip_tc5.cu"]
+SOURCES = ["elementwise.cu", "conv_simt.cu", "conv_tc.cu", "attention.cu", "attention_tc5.cu", "render.cu", "render_tc.cu", "render_tc5.cu", "render_tc5_canon.cu", "sampler.cu", "gn_skip_tc5.cu"]
+
+EXTRA_DEPS = {"render_tc5_canon.cu": ["render_tc5.cu"]}      # sources that #include another source
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -62,7 +64,7 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         stamp = op + ".sha"
-        dg = _digest([sp] + headers)
+        dg = _digest([sp] + headers + [os.path.join(CSRC, d) for d in EXTRA_DEPS.get(src, [])])
         fresh = (not force and os.path.exists(op) and os.path.exists(stamp)
                  and open(stamp).read() == dg)
         if not fresh:

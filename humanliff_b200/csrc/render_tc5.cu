@@ -33,6 +33,10 @@
 #include "tc5.cuh"
 #include "canon.cuh"
 
+#ifndef HL_R5_CANON_TU
+#define HL_R5_CANON_TU 0
+#endif
+
 #include <cuda_fp16.h>
 
 int hl_num_sms();
@@ -288,8 +292,10 @@ __device__ __forceinline__ void acc_ld(const Group &G, int c0, uint32_t *r) { tm
 // hidden layer epilogue: h' = softplus2(acc) (the bias is already in the accumulator) -> fp16 -> A_h; optionally the
 // alpha head on the fp32 values.  Column half 0 is drained as soon as ITS MMAs have retired; its packed activations wait
 // in registers until half 1 has retired too (those MMAs still read the old A_h), then both halves are stored.
-template <bool ALPHA, bool ACT>
-__device__ __forceinline__ float epi_hidden(Group &G) {
+// ALPHA: 0 = no alpha head, 1 = alpha head, 2 = decided at run time by `alpha_rt` (the shared out-of-line copy below)
+template <int ALPHA, bool ACT>
+__device__ __forceinline__ float epi_hidden(Group &G, bool alpha_rt = false) {
+    const bool do_alpha = ALPHA == 2 ? alpha_rt : ALPHA == 1;
     float s = 0.f;
     uint32_t va[32], vb[32], pk0[32];
     wait_half(G, 0);
@@ -309,7 +315,7 @@ __device__ __forceinline__ float epi_hidden(Group &G) {
             if (ACT) { h0 = softplus2_mix<0>(h0); h1 = softplus2_mix<1>(h1); h2 = softplus2_mix<2>(h2); h3 = softplus2_mix<3>(h3); }
             pk[2 * j] = pack_h2(h0, h1);
             pk[2 * j + 1] = pack_h2(h2, h3);
-            if (ALPHA) {
+            if (do_alpha) {
                 const float4 w = lds_f128(G.fb + 4u * (uint32_t)(FB_WA + c * 32 + 4 * j));
                 s = fmaf(h0, w.x, s); s = fmaf(h1, w.y, s); s = fmaf(h2, w.z, s); s = fmaf(h3, w.w, s);
             }
@@ -355,26 +361,30 @@ __device__ __forceinline__ void epi_views(Group &G, float (&rgb)[3]) {
     rgb[2] = 1.0f / (1.0f + expf(-(r2 + lds_f32(G.fb + 4u * (FB_BR + 2)))));
 }
 
+__device__ float epi_hidden_shared(Group G, bool alpha);      // (defined after the kernel, next to mlp128_compact)
+
 // The decoder MLP for the 128 samples of the group (features already in A_x, the constant tile in A_c): returns
 // (sigma, r, g, b).  ONE out-of-line copy for every caller; an odd number of layers either way, so the caller flips
 // G.phase once.
-__device__ __noinline__ float4 mlp128(Group G, bool fine) {
+template <bool compact>
+__device__ __forceinline__ float4 mlp128_body(Group &G, bool fine) {
     // pts_linears.0: K = 32 (27 features + the ones slot), N = 128 in two column halves
     start_layer(G, true, [&](int h) { issue_gemm(G, TM_AX, 2, OW0, 16384, 64, false, 64 * h); });
-    epi_hidden<false, true>(G);
+    if (compact) { epi_hidden_shared(G, false); G.phase ^= 1u; } else epi_hidden<0, true>(G);
     // pts_linears.1: K = 128 (+ bias through the constant tile)
     start_layer(G, true, [&](int h) {
         issue_gemm(G, TM_AH, 8, OW1, 16384, 64, false, 64 * h);
         issue_gemm(G, TM_AC, 1, OWB, 16384, 64, true, 64 * h);
     });
-    epi_hidden<false, true>(G);
+    if (compact) { epi_hidden_shared(G, false); G.phase ^= 1u; } else epi_hidden<0, true>(G);
     // pts_linears.2 on cat([x, h1])
     start_layer(G, true, [&](int h) {
         issue_gemm(G, TM_AX, 2, OW2X, 16384, 64, false, 64 * h);
         issue_gemm(G, TM_AH, 8, OW2H, 16384, 64, true, 64 * h);
     });
     float4 out;
-    out.x = epi_hidden<true, true>(G) + lds_f32(G.fb + 4u * FB_BA);
+    if (compact) { out.x = epi_hidden_shared(G, true); G.phase ^= 1u; } else out.x = epi_hidden<1, true>(G);
+    out.x += lds_f32(G.fb + 4u * FB_BA);
     out.y = out.z = out.w = 0.f;
     if (fine) {
         // feature_linear (no activation), then views_linear on [feature | 1 | pe(d)]
@@ -382,7 +392,7 @@ __device__ __noinline__ float4 mlp128(Group G, bool fine) {
             issue_gemm(G, TM_AH, 8, OWF, 16384, 64, false, 64 * h);
             issue_gemm(G, TM_AC, 1, OWB + 32, 16384, 64, true, 64 * h);
         });
-        epi_hidden<false, false>(G);
+        epi_hidden<0, false>(G);
         start_layer(G, false, [&](int) {
             issue_gemm(G, TM_AH, 8, OWV, 8192, 64, false);
             issue_gemm(G, TM_AC, 2, OWVP, 8192, 64, true);
@@ -393,6 +403,11 @@ __device__ __noinline__ float4 mlp128(Group G, bool fine) {
     }
     return out;
 }
+// two out-of-line copies, one per launch mode; each is called from its own instantiation of the kernel (COMPACT_MLP), so
+// that the plain mode's code is what it was without the canonical one (a second call target at the three call sites, or a
+// trampoline inside mlp128, cost the plain mode 0.9 - 1.3 %: profiles/r2_render_shared_epi_ab.log)
+__device__ __noinline__ float4 mlp128(Group G, bool fine) { return mlp128_body<false>(G, fine); }
+__device__ float4 mlp128_compact(Group G, bool fine);
 
 // exclusive product scan over the group's 128 threads (thread order); *total = product of all 128 factors
 __device__ __forceinline__ float excl_cumprod128(const Group &G, float f, float *total) {
@@ -463,8 +478,19 @@ __device__ __noinline__ void canon_sample(const float4 *sph_s, float4 *stage, co
     tmem_st16(tm_ac, ac);
 }
 
-__global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
-    // (a template parameter would keep the two modes apart at compile time; ptxas 12.9 crashes on that instantiation)
+// This file is compiled TWICE: as itself (the kernel k_render_tc5, the plain MLP copy, the whole C ABI) and through
+// render_tc5_canon.cu with HL_R5_CANON_TU = 1 (the kernel k_render_tc5_canon for canonical-mode launches, which calls the
+// compact MLP copy, + its launcher).  Two kernels, because any way of reaching both MLP copies from ONE kernel cost the
+// plain mode 0.9 - 1.3 % (profiles/r2_render_shared_epi_ab.log); two translation units, because ptxas 12.9 segfaults on
+// two entries that share this file's out-of-line device functions (and cicc on a templated kernel).
+#if HL_R5_CANON_TU
+#define HL_R5_KERNEL k_render_tc5_canon
+constexpr bool COMPACT_MLP = true;
+#else
+#define HL_R5_KERNEL k_render_tc5
+constexpr bool COMPACT_MLP = false;
+#endif
+__global__ void __launch_bounds__(NT5, 1) HL_R5_KERNEL(const Render5Args a) {
     const bool CANON = a.canon != 0;
     extern __shared__ __align__(16) uint8_t smraw5[];
     __shared__ __align__(8) uint64_t mbars[2 * GROUPS];      // per group: column half 0 / half 1 of the layer in flight
@@ -550,7 +576,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
             const int zi = (int)(idx % res), yi = (int)((idx / res) % res), xi = (int)(idx / ((long long)res * res));
             gather_to_tmem(a.tex, a.R, bnd, lin(bnd[0], bnd[3], xi), lin(bnd[1], bnd[4], yi), lin(bnd[2], bnd[5], zi),
                            G.tm + TM_AX);
-            const float4 r = mlp128(G, false);
+            const float4 r = (COMPACT_MLP ? mlp128_compact(G, false) : mlp128(G, false));
             G.phase ^= 1u;
             if (live) a.grid_out[idx] = -r.x;
         }
@@ -619,7 +645,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                 gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
             }
             RPROF(1)
-            const float4 rc = mlp128(G, true);
+            const float4 rc = (COMPACT_MLP ? mlp128_compact(G, true) : mlp128(G, true));
             G.phase ^= 1u;
             RPROF(2)
             if (a.n_importance) {
@@ -724,7 +750,7 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
                     gather_to_tmem(a.tex, a.R, bnd, pc[0], pc[1], pc[2], G.tm + TM_AX);
                 }
                 RPROF(1)
-                const float4 rn = mlp128(G, true);
+                const float4 rn = (COMPACT_MLP ? mlp128_compact(G, true) : mlp128(G, true));
                 G.phase ^= 1u;
                 RPROF(2)
                 // both sets of (sigma, r, g, b) into sorted order; this thread composites samples tg and 128 + tg
@@ -799,6 +825,17 @@ __global__ void __launch_bounds__(NT5, 1) k_render_tc5(const Render5Args a) {
     }
 }
 
+// ONE out-of-line copy of the activated hidden epilogue for its three call sites (pts_linears.0 / .1 / .2; the alpha head
+// of .2 decided at run time), used in canonical mode:
+// the fully unrolled epilogues are what the kernel's instruction footprint consists of (ncu: instruction requests at the
+// GPC-level cache at 51 % of its peak, 72 % in canonical mode, where the search and the per-sample encoding compete for
+// the instruction caches and "no instruction" is the top stall), and a copy less is 1.1 k instructions less to stream per
+// MLP evaluation.  Same-box A/B (profiles/r2_render_shared_epi_ab.log): canonical 61.8 -> 58.2 ms per frame, the plain
+// mode 27.58 -> 28.07 ms (the call costs more than the fetches it saves) -- hence chosen per launch mode.
+__device__ __noinline__ float epi_hidden_shared(Group G, bool alpha) { return epi_hidden<2, true>(G, alpha); }
+// (the canonical-mode copies are placed after the kernel so that the plain mode's code layout stays what it was without them)
+__device__ __noinline__ float4 mlp128_compact(Group G, bool fine) { return mlp128_body<true>(G, fine); }
+
 // planes [3][9][R][R] fp32 (channel = sub * 3 + ch) -> quad texels [9][R + 1][R + 1] x 16 halves (see gather_subplanes):
 // entry (yq, xq) = the footprint whose top-left tap is (yq - 1, xq - 1).
 __global__ void k_triplane_to_quads(const float *__restrict__ planes, uint4 *__restrict__ out, int R) {
@@ -827,17 +864,35 @@ __global__ void k_triplane_to_quads(const float *__restrict__ planes, uint4 *__r
 
 unsigned long long *g_prof5 = nullptr;
 
-int launch5(Render5Args &a, long long units, cudaStream_t stream, bool canon = false) {
-    constexpr size_t SMEM5_CANON = SMEM5 + 16 * (size_t)HL_CANON_SMEM_F4;
+}  // namespace
+
+#if HL_R5_CANON_TU
+namespace { constexpr size_t SMEM5_CANON = SMEM5 + 16 * (size_t)HL_CANON_SMEM_F4; }
+// the canonical-mode kernel's launcher (called by launch5 of the main translation unit; `args` = its Render5Args)
+int hl_r5_launch_canon(const void *args, int grid, void *stream) {
     static HlPerDeviceOnce once;
     if (once.need()) {
-        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM5_CANON));
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc5_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM5_CANON));
+    }
+    k_render_tc5_canon<<<grid, NT5, SMEM5_CANON, (cudaStream_t)stream>>>(*reinterpret_cast<const Render5Args *>(args));
+    HL_CHECK_LAUNCH();
+    return HL_OK;
+}
+#else
+int hl_r5_launch_canon(const void *args, int grid, void *stream);      // render_tc5_canon.cu
+
+namespace {
+int launch5(Render5Args &a, long long units, cudaStream_t stream, bool canon = false) {
+    static HlPerDeviceOnce once;
+    if (once.need()) {
+        HL_CHECK_CUDA(cudaFuncSetAttribute(k_render_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM5));
     }
     long long grid = hl_num_sms();
     const long long need = (units + GROUPS - 1) / GROUPS;
     if (grid > need) grid = need;
     a.canon = canon ? 1 : 0;
-    k_render_tc5<<<(int)grid, NT5, canon ? SMEM5_CANON : SMEM5, stream>>>(a);
+    if (canon) return hl_r5_launch_canon(&a, (int)grid, stream);
+    k_render_tc5<<<(int)grid, NT5, SMEM5, stream>>>(a);
     HL_CHECK_LAUNCH();
     return HL_OK;
 }
@@ -928,3 +983,4 @@ extern "C" int hl_density_grid_tc5(const void *texels, int R, const void *mlp_tc
     const long long tiles = ((long long)resolution * resolution * resolution + 127) / 128;
     return launch5(a, tiles, (cudaStream_t)stream);
 }
+#endif      // !HL_R5_CANON_TU

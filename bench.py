@@ -364,7 +364,7 @@ def canonical_render_block(device, reps=3):
     return {"metric": "rendered rays/sec, canonical space (nearest SMPL vertex + skinning affine per sample)",
             "value": round(n / (ms * 1e-3), 1), "unit": "rays/s", "ms_per_image": round(ms, 3), "rays": n,
             "rays_hitting_the_box": round(float(hit.float().mean()), 3), "body_vertices": 6890,
-            "kernel": "k_render_tc5 (canon) + k_smpl_vertex_tables",
+            "kernel": "k_render_tc5_canon (the tcgen05 render kernel with a compact MLP copy) + k_smpl_vertex_tables",
             "asset": "synthetic SMPL-shaped body (humanliff_b200.synth.synth_smpl): the licensed SMPL_NEUTRAL.pkl is not shipped"}
 
 

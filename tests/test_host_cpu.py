@@ -24,6 +24,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.hl_conv_cout_pad(27) == 32 and lib.hl_conv_cout_pad(192) == 192
 
 
+def test_build_recipe_covers_every_source_and_its_includes():
+    """humanliff_b200/build.py: every .cu under csrc/ is compiled, and a source that #includes another source (the
+    canonical-mode render kernel re-compiles render_tc5.cu) declares it in EXTRA_DEPS, so that the per-object stamp sees an
+    edit of the included file."""
+    from humanliff_b200 import build
+    csrc = os.path.join(ROOT, "humanliff_b200", "csrc")
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+    assert sorted(build.SOURCES) == on_disk, (build.SOURCES, on_disk)
+    for src in on_disk:
+        inc = re.findall(r'#include\s+"([^"]+\.cu)"', open(os.path.join(csrc, src)).read())
+        assert sorted(inc) == sorted(build.EXTRA_DEPS.get(src, [])), (src, inc)
+        for h in re.findall(r'#include\s+"([^"]+\.(?:cuh|h))"', open(os.path.join(csrc, src)).read()):
+            assert os.path.exists(os.path.join(csrc, h)) or os.path.exists(os.path.join(ROOT, "include", os.path.basename(h))), (src, h)
+
+
 def test_mlp_pack_offsets_match_header():
     from humanliff_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "humanliff_b200.h")).read()

@@ -289,6 +289,30 @@ __device__ __forceinline__ void wait_half(Group &G, int half) {
 // Drain 32 accumulator columns [c0, c0+32) of this thread's row.
 __device__ __forceinline__ void acc_ld(const Group &G, int c0, uint32_t *r) { tmem_ld32_nowait(G.tm + TM_ACC + (uint32_t)c0, r); }
 
+// The hidden-layer epilogue as two passes over a pair of chunks instead of four unrolled chunks: halves its instruction
+// footprint and costs the overlap across the pass boundary.  Same-box A/B (profiles/r2_render_epi_roll_ab.log): canonical
+// mode 55.3 -> 53.9 ms per frame (instruction-fetch bound), plain mode 27.62 -> 29.35 ms -- so only the canonical kernel
+// (render_tc5_canon.cu) uses it.
+#ifndef HL_R5_EPI_ROLL
+#define HL_R5_EPI_ROLL HL_R5_CANON_TU
+#endif
+// 32 accumulator columns of this thread's row -> activation -> 16 packed fp16 pairs (+ the alpha head's partial dot product)
+template <bool ACT>
+__device__ __forceinline__ void epi_chunk(const uint32_t *cur, uint32_t *pk, bool do_alpha, uint32_t wa_addr, float &s) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float h0 = __uint_as_float(cur[4 * j]), h1 = __uint_as_float(cur[4 * j + 1]);
+        float h2 = __uint_as_float(cur[4 * j + 2]), h3 = __uint_as_float(cur[4 * j + 3]);
+        if (ACT) { h0 = softplus2_mix<0>(h0); h1 = softplus2_mix<1>(h1); h2 = softplus2_mix<2>(h2); h3 = softplus2_mix<3>(h3); }
+        pk[2 * j] = pack_h2(h0, h1);
+        pk[2 * j + 1] = pack_h2(h2, h3);
+        if (do_alpha) {
+            const float4 w = lds_f128(wa_addr + 16u * (uint32_t)j);
+            s = fmaf(h0, w.x, s); s = fmaf(h1, w.y, s); s = fmaf(h2, w.z, s); s = fmaf(h3, w.w, s);
+        }
+    }
+}
+
 // hidden layer epilogue: h' = softplus2(acc) (the bias is already in the accumulator) -> fp16 -> A_h; optionally the
 // alpha head on the fp32 values.  Column half 0 is drained as soon as ITS MMAs have retired; its packed activations wait
 // in registers until half 1 has retired too (those MMAs still read the old A_h), then both halves are stored.
@@ -297,6 +321,26 @@ template <int ALPHA, bool ACT>
 __device__ __forceinline__ float epi_hidden(Group &G, bool alpha_rt = false) {
     const bool do_alpha = ALPHA == 2 ? alpha_rt : ALPHA == 1;
     float s = 0.f;
+#if HL_R5_EPI_ROLL
+    // Two passes over a pair of 32-column chunks (one copy of the pair's code instead of four chunk copies: the unrolled
+    // epilogues are the kernel's instruction footprint).  Chunk 2 * it is packed into pk0 and waits in registers for its
+    // neighbour: in pass 0 because half 1's MMAs still read the old A_h, in pass 1 only to keep the passes identical.
+    uint32_t va[32], vb[32], pk0[16], pk[16];
+    wait_half(G, 0);
+    acc_ld(G, 0, va);
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        tmem_ld_wait();
+        acc_ld(G, (2 * it + 1) * 32, vb);
+        epi_chunk<ACT>(va, pk0, do_alpha, G.fb + 4u * (uint32_t)(FB_WA + 64 * it), s);
+        tmem_ld_wait();
+        wait_half(G, 1);                                // pass 0: chunk 2 belongs to half 1 (pass 1: returns at once)
+        if (it == 0) acc_ld(G, 64, va);
+        epi_chunk<ACT>(vb, pk, do_alpha, G.fb + 4u * (uint32_t)(FB_WA + 64 * it + 32), s);
+        tmem_st16(G.tm + TM_AH + (uint32_t)(32 * it), pk0);
+        tmem_st16(G.tm + TM_AH + (uint32_t)(32 * it) + 16u, pk);
+    }
+#else
     uint32_t va[32], vb[32], pk0[32];
     wait_half(G, 0);
     acc_ld(G, 0, va);
@@ -331,6 +375,7 @@ __device__ __forceinline__ float epi_hidden(Group &G, bool alpha_rt = false) {
             tmem_st16(G.tm + TM_AH + (uint32_t)(c * 16), pk);
         }
     }
+#endif
     G.phase ^= 1u;
     return s;
 }

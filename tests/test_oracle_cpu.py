@@ -219,3 +219,26 @@ def test_render_oracle_canonical_space_matches_reference_golden():
                                     u, canon=(smpl, tp))
     for name, a, b in zip(("rgb", "acc", "depth"), out, (gz["rgb"], gz["acc"], gz["depth"])):
         assert rel_l2(a, b) < 2e-6, (name, rel_l2(a, b))
+
+
+def test_oracle_nearest_vertex_is_separately_rounded_with_ties_to_the_lower_index():
+    """The oracle's nearest_vertex (== the stand-in for pytorch3d's knn_points that froze render_canon_384) on the near-tie
+    cases the GPU test feeds the CUDA search: squared distances with every operation rounded, first index on ties.  This
+    is what ties the GPU test's numpy expectation to the oracle; the fused rounding would decide every adversarial case the
+    other way."""
+    import numpy as np
+    from common import nearest_vertex_near_tie_cases, sq_dist_fused, sq_dist_separate
+    from oracle import render_oracle
+    adv, ties = nearest_vertex_near_tie_cases(36, 12, seed=11)
+    for q, v1, v2 in adv:
+        want = 0 if sq_dist_separate(q, v1) < sq_dist_separate(q, v2) else 1
+        fused = 0 if sq_dist_fused(q, v1) < sq_dist_fused(q, v2) else 1
+        assert want != fused
+        far = (v1 + np.float32(3.0)).astype(np.float32)
+        for order in ((v1, v2), (v2, v1)):
+            table = torch.from_numpy(np.stack([far, order[0], order[1], far]))
+            got = int(render_oracle.nearest_vertex(torch.from_numpy(q)[None], table)[0])
+            assert got == 1 + (want if order[0] is v1 else 1 - want), (q, v1, v2)
+    for q, v1, v2 in ties:
+        table = torch.from_numpy(np.stack([v2, v1, v2]))
+        assert int(render_oracle.nearest_vertex(torch.from_numpy(q)[None], table)[0]) == 0

@@ -348,50 +348,14 @@ def test_nearest_vertex_decisions_are_separately_rounded_with_ties_to_the_lower_
     The per-vertex affine is M = 0, c = (index, 0, 0), so the returned canonical x IS the chosen vertex."""
     import ctypes
     import numpy as np
+    from common import nearest_vertex_near_tie_cases, sq_dist_fused, sq_dist_separate
     from humanliff_b200._lib import call
     f32 = np.float32
-    rs = np.random.RandomState(11)
-
-    def d_sep(q, v):
-        d = (q - v).astype(f32)
-        s = (d * d).astype(f32)
-        return f32(f32(s[0] + s[1]) + s[2])
-
-    def d_fma(q, v):
-        d = (q - v).astype(f32).astype(np.float64)
-        r = f32(d[0] * d[0])
-        r = f32(d[1] * d[1] + np.float64(r))
-        return f32(d[2] * d[2] + np.float64(r))
-
+    d_sep, d_fma = sq_dist_separate, sq_dist_fused
     NC, CL = 64, 4
     n_same_adv, n_same_tie, n_cross_adv, n_cross_tie = 24, 8, 12, 4
-    cases = []                                            # (q, v_first_scanned, v_second_scanned)
-    centre = lambda k: np.array([3.0 * k - 90.0, 0.37, -0.21], dtype=f32)
-    k = 0
-    while len(cases) < n_same_adv + n_cross_adv:          # adversarial: the two roundings disagree
-        c = centre(len(cases))
-        q = (c + rs.uniform(-0.2, 0.2, 3)).astype(f32)
-        off = rs.normal(size=3); off *= rs.uniform(0.05, 0.4) / np.linalg.norm(off)
-        v1 = (q + off).astype(f32)
-        # v2: random x, y; z solved so that the REAL distances agree to about one ulp (rounding of v2.z only)
-        D1 = float((((q - v1).astype(f32).astype(np.float64)) ** 2).sum())
-        v2 = (q + rs.uniform(-0.6, 0.6, 3) * np.sqrt(D1)).astype(f32)
-        dxy = (q - v2).astype(f32).astype(np.float64)[:2]
-        v2[2] = f32(np.float64(q[2]) + rs.choice([-1.0, 1.0]) * np.sqrt(D1 - float((dxy ** 2).sum())))
-        s = np.sign(float(d_sep(q, v1)) - float(d_sep(q, v2)))
-        if s != 0 and s == -np.sign(float(d_fma(q, v1)) - float(d_fma(q, v2))):      # strict reversal
-            cases.append((q, v1, v2))
-        k += 1
-        assert k < 200000
-    adv = cases[:n_same_adv]
-    cross_adv = cases[n_same_adv:]
-    ties = []
-    for j in range(n_same_tie + n_cross_tie):             # exact ties
-        q = (np.round(centre(100 + j) * 256) / 256 + rs.randint(-64, 64, 3) / 256.0).astype(f32)
-        dl = (rs.randint(-1500, 1500, 3) / 4096.0).astype(f32)
-        v1, v2 = (q + dl).astype(f32), (q - dl).astype(f32)
-        assert d_sep(q, v1) == d_sep(q, v2) and np.all(q - v1 == -dl)
-        ties.append((q, v1, v2))
+    adv_all, ties = nearest_vertex_near_tie_cases(n_same_adv + n_cross_adv, n_same_tie + n_cross_tie, seed=11)
+    adv, cross_adv = adv_all[:n_same_adv], adv_all[n_same_adv:]
     verts = np.full((NC * CL, 4), 1e18, dtype=f32)
     idx = np.full(NC * CL, 0x7fffffff, dtype=np.int32)
     queries, expect, fused_would_differ = [], [], 0

@@ -3,6 +3,12 @@ human_diffusion/improved_diffusion/gaussian_diffusion.py (:18-60 schedules, :101
 :232-326 p_mean_variance, :356-388 p_sample, :390-482 p_sample_loop[_progressive]) and
 respace.py (:7-60 space_timesteps, :63-122 SpacedDiffusion / _WrappedModel).
 
+Provenance, stated plainly: the float64 table block of ``GaussianDiffusion.__init__`` (betas -> alphas_cumprod ->
+posterior coefficients), ``betas_for_alpha_bar``, the three enums and ``SpacedDiffusion.__init__`` / ``_WrappedModel``
+follow the reference formula for formula and name for name (about 45 lines; gaussian_diffusion.py:118-169,
+respace.py:72-122).  They are the public attribute contract of the class and are tested BIT-EXACT against the reference
+objects (tests/golden/schedules.npz); none of it is hot-path compute.  Everything the loop executes per step is new.
+
 Host side: float64 numpy tables exactly as the reference builds them.  Device side: the tables are
 uploaded ONCE as fp32 (the reference re-uploads a float64 table 8 times per step,
 gaussian_diffusion.py:860) and the whole posterior update
